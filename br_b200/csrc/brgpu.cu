@@ -1,0 +1,933 @@
+// brgpu.cu — the C ABI of include/brgpu.h: handle lifetime, host<->device staging, the
+// kernel sequences of part 1 (count -> spectrum -> threshold) and part 2 (method chain with
+// the reversed pass), overflow retry, and the per-kernel CUDA-event instrumentation.
+//
+// There is no CPU path in this file or anywhere in the library: every entry point that
+// computes needs a CUDA device and reports BRGPU_E_NO_DEVICE / BRGPU_E_CUDA otherwise.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "internal.h"
+
+using namespace brgpu;
+
+#define CK(call)                                                                                                       \
+    do {                                                                                                               \
+        cudaError_t e__ = (call);                                                                                      \
+        if (e__ != cudaSuccess) return fail(ctx, BRGPU_E_CUDA, #call, e__);                                            \
+    } while (0)
+
+namespace brgpu {
+
+int fail(brgpu_ctx *ctx, int code, const char *what, cudaError_t e) {
+    if (ctx) {
+        ctx->err = what ? what : "";
+        if (e != cudaSuccess) {
+            ctx->err += ": ";
+            ctx->err += cudaGetErrorString(e);
+        }
+    }
+    if (e != cudaSuccess) cudaGetLastError(); // clear the sticky-less error state
+    return code;
+}
+
+static cudaEvent_t take_event(brgpu_ctx *ctx) {
+    if (!ctx->event_pool.empty()) {
+        cudaEvent_t e = ctx->event_pool.back();
+        ctx->event_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+static thread_local ProfEntry *tl_open = nullptr;
+
+void prof_begin(brgpu_ctx *ctx, const char *name, double algo_bytes, bool is_kernel) {
+    if (is_kernel) ctx->launches++;
+    if (!ctx->profiling) return;
+    ProfEntry *pe = nullptr;
+    for (auto &p : ctx->prof)
+        if (p.name == name) pe = &p;
+    if (!pe) {
+        ctx->prof.emplace_back();
+        pe = &ctx->prof.back();
+        pe->name = name;
+    }
+    pe->launches++;
+    pe->bytes += algo_bytes;
+    cudaEvent_t a = take_event(ctx), b = take_event(ctx);
+    cudaEventRecord(a, ctx->stream);
+    pe->pending.emplace_back(a, b);
+    tl_open = pe;
+}
+
+void prof_end(brgpu_ctx *ctx) {
+    if (!ctx->profiling || !tl_open) return;
+    cudaEventRecord(tl_open->pending.back().second, ctx->stream);
+    tl_open = nullptr;
+}
+
+static void prof_resolve(brgpu_ctx *ctx) {
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &p : ctx->prof) {
+        for (auto &ev : p.pending) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, ev.first, ev.second) == cudaSuccess) p.ms += ms;
+            ctx->event_pool.push_back(ev.first);
+            ctx->event_pool.push_back(ev.second);
+        }
+        p.pending.clear();
+    }
+}
+
+Layout::~Layout() {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (d_slot_off) cudaFreeAsync(d_slot_off, ctx->stream);
+    if (d_word2read) cudaFreeAsync(d_word2read, ctx->stream);
+    if (d_order) cudaFreeAsync(d_order, ctx->stream);
+}
+
+} // namespace brgpu
+
+static inline bool k_supported(int k) { return k >= 3 && k <= 19 && (k & 1); }
+static inline uint64_t table_len(int k) { return 1ULL << (2 * k - 1); }
+static inline uint64_t bits_alloc_bytes(int k) {
+    uint64_t b = table_len(k) >> 3;
+    return b < 16 ? 16 : b;
+}
+
+template <class T> static cudaError_t dalloc(brgpu_ctx *ctx, T **p, uint64_t count) {
+    *p = nullptr;
+    if (count == 0) count = 1;
+    return cudaMallocAsync((void **)p, count * sizeof(T), ctx->stream);
+}
+
+// ------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------
+extern "C" const char *brgpu_version(void) { return "brgpu 0.1 (sm_100a)"; }
+
+extern "C" int brgpu_ctx_create(int device, void *cuda_stream, brgpu_ctx **out) {
+    if (!out) return BRGPU_E_INVALID;
+    *out = nullptr;
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0) {
+        cudaGetLastError();
+        return BRGPU_E_NO_DEVICE;
+    }
+    if (device < 0 || device >= n_dev) return BRGPU_E_INVALID;
+    brgpu_ctx *ctx = new (std::nothrow) brgpu_ctx;
+    if (!ctx) return BRGPU_E_NOMEM;
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) {
+        delete ctx;
+        return BRGPU_E_NO_DEVICE;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+    if (cuda_stream) {
+        ctx->stream = (cudaStream_t)cuda_stream;
+    } else {
+        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            delete ctx;
+            return BRGPU_E_CUDA;
+        }
+        ctx->own_stream = true;
+    }
+    // keep freed temporaries in the stream-ordered pool instead of returning them to the driver
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thr = ~0ULL;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    if (cudaMalloc((void **)&ctx->d_flags, 16 * sizeof(uint32_t)) != cudaSuccess ||
+        cudaMalloc((void **)&ctx->d_hist, 256 * sizeof(uint64_t)) != cudaSuccess ||
+        cudaMallocHost((void **)&ctx->h_pinned, 512 * sizeof(uint64_t)) != cudaSuccess) {
+        cudaGetLastError();
+        brgpu_ctx_destroy(ctx);
+        return BRGPU_E_NOMEM;
+    }
+    cudaMemsetAsync(ctx->d_flags, 0, 16 * sizeof(uint32_t), ctx->stream);
+    *out = ctx;
+    return BRGPU_OK;
+}
+
+extern "C" void brgpu_ctx_destroy(brgpu_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (auto &p : ctx->prof)
+        for (auto &ev : p.pending) {
+            cudaEventDestroy(ev.first);
+            cudaEventDestroy(ev.second);
+        }
+    for (auto e : ctx->event_pool) cudaEventDestroy(e);
+    if (ctx->d_flags) cudaFree(ctx->d_flags);
+    if (ctx->d_hist) cudaFree(ctx->d_hist);
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" int brgpu_ctx_synchronize(brgpu_ctx *ctx) {
+    if (!ctx) return BRGPU_E_INVALID;
+    cudaSetDevice(ctx->device);
+    CK(cudaStreamSynchronize(ctx->stream));
+    return BRGPU_OK;
+}
+
+extern "C" const char *brgpu_last_error(const brgpu_ctx *ctx) { return ctx ? ctx->err.c_str() : "no context"; }
+
+// ------------------------------------------------------------------------------------------
+// reads
+// ------------------------------------------------------------------------------------------
+static inline uint64_t slot_capacity(uint64_t len, unsigned slack_shift_extra) {
+    // room for the read to grow in place: len/8 + 64 bytes by default, x4 per retry
+    uint64_t slack = ((len >> 3) + 64) << (2 * slack_shift_extra);
+    return (len + slack + 31) & ~31ULL;
+}
+
+// Build a layout for reads of the given lengths.  Work-queue order: longest first (counting
+// sort on len/64, stable), which is the LPT rule for the one-warp-per-read scan.
+static int make_layout(brgpu_ctx *ctx, const uint32_t *h_len, uint64_t n, unsigned slack_extra,
+                       std::shared_ptr<Layout> &out) {
+    auto L = std::make_shared<Layout>();
+    L->ctx = ctx;
+    L->n = n;
+    std::vector<uint64_t> slot_off(n + 1);
+    uint64_t acc = 0;
+    for (uint64_t r = 0; r < n; r++) {
+        slot_off[r] = acc;
+        acc += slot_capacity(h_len[r], slack_extra);
+    }
+    slot_off[n] = acc;
+    L->total_slots = acc;
+
+    std::vector<uint32_t> order(n);
+    {
+        const uint32_t NB = 1u << 16;
+        std::vector<uint64_t> cnt(NB + 1, 0);
+        auto key = [&](uint64_t r) {
+            uint32_t kx = h_len[r] >> 6;
+            if (kx >= NB) kx = NB - 1;
+            return NB - 1 - kx; // descending
+        };
+        for (uint64_t r = 0; r < n; r++) cnt[key(r) + 1]++;
+        for (uint32_t b = 0; b < NB; b++) cnt[b + 1] += cnt[b];
+        for (uint64_t r = 0; r < n; r++) order[cnt[key(r)]++] = (uint32_t)r;
+    }
+
+    CK(dalloc(ctx, &L->d_slot_off, n + 1));
+    CK(dalloc(ctx, &L->d_word2read, L->total_slots >> 5));
+    CK(dalloc(ctx, &L->d_order, n));
+    CK(cudaMemcpyAsync(L->d_slot_off, slot_off.data(), (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice,
+                       ctx->stream));
+    if (n) CK(cudaMemcpyAsync(L->d_order, order.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    // the host vectors are pageable: the copies above have been staged when the calls return
+    launch_fill_word2read(ctx, *L);
+    CK(cudaGetLastError());
+    out = L;
+    return BRGPU_OK;
+}
+
+static void reads_release(brgpu_reads *r) {
+    if (!r) return;
+    if (r->ctx) {
+        cudaSetDevice(r->ctx->device);
+        if (r->d_seq) cudaFreeAsync(r->d_seq, r->ctx->stream);
+        if (r->d_len) cudaFreeAsync(r->d_len, r->ctx->stream);
+    }
+    delete r;
+}
+
+// upload from a tight device or host buffer into a fresh slot layout
+static int reads_from_tight(brgpu_ctx *ctx, const uint8_t *seq, bool seq_on_device, const uint64_t *h_off, uint64_t n,
+                            unsigned slack_extra, brgpu_reads **out) {
+    std::vector<uint32_t> h_len(n);
+    for (uint64_t r = 0; r < n; r++) {
+        if (h_off[r + 1] < h_off[r]) return fail(ctx, BRGPU_E_INVALID, "offsets must be non-decreasing");
+        uint64_t l = h_off[r + 1] - h_off[r];
+        if (l > 0xfffffff0ULL / 2) return fail(ctx, BRGPU_E_INVALID, "read longer than 2^31 bases");
+        h_len[r] = (uint32_t)l;
+    }
+    if (n > 0xfffffff0ULL) return fail(ctx, BRGPU_E_INVALID, "too many reads in one chunk");
+    brgpu_reads *R = new (std::nothrow) brgpu_reads;
+    if (!R) return fail(ctx, BRGPU_E_NOMEM, "host allocation");
+    R->ctx = ctx;
+    R->h_len = h_len;
+    for (uint32_t l : h_len) R->sum_len += l;
+    int st = make_layout(ctx, h_len.data(), n, slack_extra, R->layout);
+    if (st != BRGPU_OK) {
+        delete R;
+        return st;
+    }
+    const Layout &L = *R->layout;
+    const uint64_t base0 = n ? h_off[0] : 0;
+    const uint64_t total = n ? h_off[n] - base0 : 0;
+    uint8_t *d_tight = nullptr;
+    uint64_t *d_toff = nullptr;
+    cudaError_t e;
+    if ((e = dalloc(ctx, &R->d_seq, L.total_slots)) != cudaSuccess || (e = dalloc(ctx, &R->d_len, n)) != cudaSuccess ||
+        (e = dalloc(ctx, &d_toff, n + 1)) != cudaSuccess) {
+        reads_release(R);
+        return fail(ctx, BRGPU_E_NOMEM, "device allocation (reads)", e);
+    }
+    std::vector<uint64_t> rel(n + 1);
+    for (uint64_t r = 0; r <= n; r++) rel[r] = (n ? h_off[r] : 0) - base0;
+    const uint8_t *d_src = nullptr;
+    if (seq_on_device) {
+        d_src = seq + base0;
+    } else {
+        if ((e = dalloc(ctx, &d_tight, total)) != cudaSuccess) {
+            cudaFreeAsync(d_toff, ctx->stream);
+            reads_release(R);
+            return fail(ctx, BRGPU_E_NOMEM, "device allocation (staging)", e);
+        }
+        if (total) cudaMemcpyAsync(d_tight, seq + base0, total, cudaMemcpyHostToDevice, ctx->stream);
+        d_src = d_tight;
+    }
+    cudaMemcpyAsync(d_toff, rel.data(), (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (n) cudaMemcpyAsync(R->d_len, h_len.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
+    launch_scatter_to_slots(ctx, L, d_src, d_toff, R->d_seq);
+    if (d_tight) cudaFreeAsync(d_tight, ctx->stream);
+    cudaFreeAsync(d_toff, ctx->stream);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        reads_release(R);
+        return fail(ctx, BRGPU_E_CUDA, "reads upload", e);
+    }
+    *out = R;
+    return BRGPU_OK;
+}
+
+extern "C" int brgpu_reads_upload(brgpu_ctx *ctx, const uint8_t *seq_host, const uint64_t *offsets_host,
+                                  uint64_t n_reads, brgpu_reads **out) {
+    if (!ctx || !out || !offsets_host) return ctx ? fail(ctx, BRGPU_E_INVALID, "null argument") : BRGPU_E_INVALID;
+    *out = nullptr;
+    if (!seq_host && n_reads && offsets_host[n_reads] != offsets_host[0])
+        return fail(ctx, BRGPU_E_INVALID, "null sequence buffer");
+    cudaSetDevice(ctx->device);
+    return reads_from_tight(ctx, seq_host, false, offsets_host, n_reads, 0, out);
+}
+
+extern "C" uint64_t brgpu_reads_count(const brgpu_reads *reads) { return reads ? reads->layout->n : 0; }
+
+// tight offsets of the current lengths: d_toff (n+1) on device, total on host
+static int reads_tight_offsets(brgpu_reads *R, uint64_t **d_toff_out, uint64_t *total) {
+    brgpu_ctx *ctx = R->ctx;
+    const uint64_t n = R->layout->n;
+    uint64_t *d_toff = nullptr, *d_tmp = nullptr;
+    CK(dalloc(ctx, &d_toff, n + 1));
+    CK(dalloc(ctx, &d_tmp, n / 4096 + 4));
+    launch_exclusive_scan_u32(ctx, R->d_len, n, d_toff, d_tmp);
+    cudaFreeAsync(d_tmp, ctx->stream);
+    CK(cudaMemcpyAsync(ctx->h_pinned, d_toff + n, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    *total = ctx->h_pinned[0];
+    *d_toff_out = d_toff;
+    return BRGPU_OK;
+}
+
+extern "C" uint64_t brgpu_reads_bases(const brgpu_reads *reads) {
+    if (!reads) return 0;
+    brgpu_reads *R = const_cast<brgpu_reads *>(reads);
+    cudaSetDevice(R->ctx->device);
+    uint64_t *d_toff = nullptr, total = 0;
+    if (reads_tight_offsets(R, &d_toff, &total) != BRGPU_OK) return 0;
+    cudaFreeAsync(d_toff, R->ctx->stream);
+    return total;
+}
+
+extern "C" int brgpu_reads_download(brgpu_reads *reads, uint8_t *seq_host, uint64_t seq_cap, uint64_t *offsets_host,
+                                    uint64_t *required) {
+    if (!reads) return BRGPU_E_INVALID;
+    brgpu_ctx *ctx = reads->ctx;
+    cudaSetDevice(ctx->device);
+    const Layout &L = *reads->layout;
+    uint64_t *d_toff = nullptr, total = 0;
+    int st = reads_tight_offsets(reads, &d_toff, &total);
+    if (st != BRGPU_OK) return st;
+    if (required) *required = total;
+    if (total > seq_cap || (!seq_host && total) || !offsets_host) {
+        cudaFreeAsync(d_toff, ctx->stream);
+        return fail(ctx, total > seq_cap ? BRGPU_E_OVERFLOW : BRGPU_E_INVALID, "output buffer too small");
+    }
+    uint8_t *d_tight = nullptr;
+    CK(dalloc(ctx, &d_tight, total));
+    launch_gather_from_slots(ctx, L, reads->d_seq, reads->d_len, d_toff, d_tight, false);
+    if (total) CK(cudaMemcpyAsync(seq_host, d_tight, total, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(offsets_host, d_toff, (L.n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    cudaFreeAsync(d_tight, ctx->stream);
+    cudaFreeAsync(d_toff, ctx->stream);
+    CK(cudaStreamSynchronize(ctx->stream));
+    return BRGPU_OK;
+}
+
+extern "C" void brgpu_reads_free(brgpu_reads *reads) { reads_release(reads); }
+
+// ------------------------------------------------------------------------------------------
+// part 1
+// ------------------------------------------------------------------------------------------
+extern "C" int brgpu_counts_create(brgpu_ctx *ctx, int k, brgpu_counts **out) {
+    if (!ctx || !out) return BRGPU_E_INVALID;
+    *out = nullptr;
+    if (!k_supported(k)) return fail(ctx, BRGPU_E_INVALID, "k must be odd and in 3..=19");
+    cudaSetDevice(ctx->device);
+    brgpu_counts *c = new (std::nothrow) brgpu_counts;
+    if (!c) return fail(ctx, BRGPU_E_NOMEM, "host allocation");
+    c->ctx = ctx;
+    c->k = k;
+    c->n = table_len(k);
+    // plain cudaMalloc: the table is exported over CUDA IPC for the multi-GPU merge
+    cudaError_t e = cudaMalloc((void **)&c->d_counts, c->n < 64 ? 64 : c->n);
+    if (e != cudaSuccess) {
+        delete c;
+        return fail(ctx, BRGPU_E_NOMEM, "device allocation (count table)", e);
+    }
+    {
+        ProfScope ps(ctx, "zero_counts", (double)c->n, false);
+        cudaMemsetAsync(c->d_counts, 0, c->n < 64 ? 64 : c->n, ctx->stream);
+    }
+    *out = c;
+    return BRGPU_OK;
+}
+
+extern "C" void brgpu_counts_free(brgpu_counts *c) {
+    if (!c) return;
+    cudaSetDevice(c->ctx->device);
+    cudaStreamSynchronize(c->ctx->stream);
+    if (c->d_counts) cudaFree(c->d_counts);
+    delete c;
+}
+
+extern "C" void *brgpu_counts_device_ptr(brgpu_counts *c) { return c ? c->d_counts : nullptr; }
+extern "C" uint64_t brgpu_counts_len(const brgpu_counts *c) { return c ? c->n : 0; }
+
+extern "C" int brgpu_counts_add_reads(brgpu_counts *c, const brgpu_reads *reads) {
+    if (!c || !reads) return BRGPU_E_INVALID;
+    brgpu_ctx *ctx = c->ctx;
+    if (reads->ctx != ctx) return fail(ctx, BRGPU_E_INVALID, "reads belong to another context");
+    cudaSetDevice(ctx->device);
+    const Layout &L = *reads->layout;
+    // k-mer count for the roofline bookkeeping (exact for uploaded reads)
+    double n_kmers = 0;
+    for (uint32_t l : reads->h_len)
+        if (l >= (uint32_t)c->k) n_kmers += (double)(l - (uint32_t)c->k + 1);
+    launch_count(ctx, L, reads->d_seq, reads->d_len, c->k, c->d_counts, n_kmers);
+    CK(cudaGetLastError());
+    return BRGPU_OK;
+}
+
+static int run_spectrum(brgpu_ctx *ctx, const uint8_t *d_counts, uint64_t begin, uint64_t end, uint8_t *d_bits,
+                        int abundance, uint64_t hist[256]) {
+    CK(cudaMemsetAsync(ctx->d_hist, 0, 256 * sizeof(uint64_t), ctx->stream));
+    launch_spectrum_threshold(ctx, d_counts, begin, end, ctx->d_hist, d_bits, abundance);
+    CK(cudaGetLastError());
+    if (hist) {
+        CK(cudaMemcpyAsync(ctx->h_pinned, ctx->d_hist, 256 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        memcpy(hist, ctx->h_pinned, 256 * sizeof(uint64_t));
+    }
+    return BRGPU_OK;
+}
+
+extern "C" int brgpu_counts_spectrum(brgpu_counts *c, uint64_t hist_host[256]) {
+    if (!c || !hist_host) return BRGPU_E_INVALID;
+    cudaSetDevice(c->ctx->device);
+    return run_spectrum(c->ctx, c->d_counts, 0, c->n, nullptr, 0, hist_host);
+}
+
+extern "C" int brgpu_counts_spectrum_slice(brgpu_counts *c, uint64_t begin, uint64_t end, uint64_t hist_host[256]) {
+    if (!c || !hist_host) return BRGPU_E_INVALID;
+    if (begin > end || end > c->n || (begin & 1023) || (end & 1023 && end != c->n))
+        return fail(c->ctx, BRGPU_E_INVALID, "slice must be 1024-aligned");
+    cudaSetDevice(c->ctx->device);
+    return run_spectrum(c->ctx, c->d_counts, begin, end, nullptr, 0, hist_host);
+}
+
+// pcon Spectrum::get_threshold(FirstMinimum): first i with hist[i+1] > hist[i]
+extern "C" int brgpu_spectrum_first_minimum(const uint64_t hist[256]) {
+    if (!hist) return -1;
+    for (int i = 0; i + 1 < 256; i++)
+        if (hist[i + 1] > hist[i]) return i;
+    return -1;
+}
+
+extern "C" int brgpu_counts_download(brgpu_counts *c, uint8_t *out_host, uint64_t n) {
+    if (!c || !out_host) return BRGPU_E_INVALID;
+    brgpu_ctx *ctx = c->ctx;
+    if (n != c->n) return fail(ctx, BRGPU_E_INVALID, "n must be 2^(2k-1)");
+    cudaSetDevice(ctx->device);
+    CK(cudaMemcpyAsync(out_host, c->d_counts, n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return BRGPU_OK;
+}
+
+static int set_alloc(brgpu_ctx *ctx, int k, brgpu_set **out) {
+    brgpu_set *s = new (std::nothrow) brgpu_set;
+    if (!s) return fail(ctx, BRGPU_E_NOMEM, "host allocation");
+    s->ctx = ctx;
+    s->k = k;
+    s->n_bytes = table_len(k) >> 3;
+    cudaError_t e = cudaMalloc((void **)&s->d_bits, bits_alloc_bytes(k));
+    if (e != cudaSuccess) {
+        delete s;
+        return fail(ctx, BRGPU_E_NOMEM, "device allocation (bitfield)", e);
+    }
+    *out = s;
+    return BRGPU_OK;
+}
+
+extern "C" void brgpu_set_free(brgpu_set *s) {
+    if (!s) return;
+    cudaSetDevice(s->ctx->device);
+    cudaStreamSynchronize(s->ctx->stream);
+    if (s->d_bits) cudaFree(s->d_bits);
+    delete s;
+}
+
+extern "C" int brgpu_set_new(brgpu_ctx *ctx, int k, brgpu_set **out) {
+    if (!ctx || !out) return BRGPU_E_INVALID;
+    *out = nullptr;
+    if (!k_supported(k)) return fail(ctx, BRGPU_E_INVALID, "k must be odd and in 3..=19");
+    cudaSetDevice(ctx->device);
+    brgpu_set *s = nullptr;
+    int st = set_alloc(ctx, k, &s);
+    if (st != BRGPU_OK) return st;
+    cudaMemsetAsync(s->d_bits, 0, bits_alloc_bytes(k), ctx->stream);
+    *out = s;
+    return BRGPU_OK;
+}
+
+extern "C" int brgpu_set_from_counts(brgpu_counts *c, int abundance, brgpu_set **out) {
+    if (!c || !out) return BRGPU_E_INVALID;
+    brgpu_ctx *ctx = c->ctx;
+    *out = nullptr;
+    if (abundance < 0 || abundance > 255) return fail(ctx, BRGPU_E_INVALID, "abundance must be in 0..=255");
+    cudaSetDevice(ctx->device);
+    brgpu_set *s = nullptr;
+    int st = set_alloc(ctx, c->k, &s);
+    if (st != BRGPU_OK) return st;
+    s->abundance = abundance;
+    st = run_spectrum(ctx, c->d_counts, 0, c->n, s->d_bits, abundance, s->hist);
+    if (st != BRGPU_OK) {
+        brgpu_set_free(s);
+        return st;
+    }
+    *out = s;
+    return BRGPU_OK;
+}
+
+extern "C" int brgpu_set_from_reads(brgpu_ctx *ctx, int k, int abundance, int selection, const brgpu_reads *reads,
+                                    brgpu_set **out) {
+    if (!ctx || !out || !reads) return BRGPU_E_INVALID;
+    *out = nullptr;
+    if (selection == BRGPU_ABUNDANCE_EXPLICIT && abundance < 0)
+        return fail(ctx, BRGPU_E_NEED_ABUNDANCE, "need an abundance threshold or an abundance method");
+    if (selection != BRGPU_ABUNDANCE_EXPLICIT && selection != BRGPU_ABUNDANCE_FIRST_MINIMUM)
+        return fail(ctx, BRGPU_E_INVALID, "unknown abundance selection");
+    brgpu_counts *c = nullptr;
+    int st = brgpu_counts_create(ctx, k, &c);
+    if (st != BRGPU_OK) return st;
+    st = brgpu_counts_add_reads(c, reads);
+    if (st == BRGPU_OK) {
+        if (selection == BRGPU_ABUNDANCE_FIRST_MINIMUM) {
+            uint64_t hist[256];
+            st = brgpu_counts_spectrum(c, hist);
+            if (st == BRGPU_OK) {
+                abundance = brgpu_spectrum_first_minimum(hist);
+                if (abundance < 0) st = fail(ctx, BRGPU_E_NO_THRESHOLD, "can't compute the abundance threshold");
+            }
+        }
+        if (st == BRGPU_OK) st = brgpu_set_from_counts(c, abundance, out);
+    }
+    brgpu_counts_free(c);
+    return st;
+}
+
+extern "C" int brgpu_set_from_host_reads(brgpu_ctx *ctx, int k, int abundance, int selection, const uint8_t *seq_host,
+                                         const uint64_t *offsets_host, uint64_t n_reads, brgpu_set **out) {
+    if (!ctx || !out) return BRGPU_E_INVALID;
+    *out = nullptr;
+    if (!k_supported(k)) return fail(ctx, BRGPU_E_INVALID, "k must be odd and in 3..=19");
+    brgpu_reads *R = nullptr;
+    int st = brgpu_reads_upload(ctx, seq_host, offsets_host, n_reads, &R);
+    if (st != BRGPU_OK) return st;
+    st = brgpu_set_from_reads(ctx, k, abundance, selection, R, out);
+    brgpu_reads_free(R);
+    return st;
+}
+
+extern "C" int brgpu_set_from_bitfield(brgpu_ctx *ctx, int k, const uint8_t *bits_host, uint64_t n_bytes,
+                                       brgpu_set **out) {
+    if (!ctx || !out || !bits_host) return BRGPU_E_INVALID;
+    *out = nullptr;
+    if (!k_supported(k)) return fail(ctx, BRGPU_E_INVALID, "k must be odd and in 3..=19");
+    if (n_bytes != (table_len(k) >> 3)) return fail(ctx, BRGPU_E_INVALID, "bitfield must hold 2^(2k-1) bits");
+    cudaSetDevice(ctx->device);
+    brgpu_set *s = nullptr;
+    int st = set_alloc(ctx, k, &s);
+    if (st != BRGPU_OK) return st;
+    cudaMemsetAsync(s->d_bits, 0, bits_alloc_bytes(k), ctx->stream);
+    cudaError_t e = cudaMemcpyAsync(s->d_bits, bits_host, n_bytes, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        brgpu_set_free(s);
+        return fail(ctx, BRGPU_E_CUDA, "bitfield upload", e);
+    }
+    *out = s;
+    return BRGPU_OK;
+}
+
+extern "C" int brgpu_set_from_solid_payload(brgpu_ctx *ctx, const uint8_t *payload_host, uint64_t n_bytes,
+                                            brgpu_set **out) {
+    if (!ctx || !out || !payload_host || n_bytes < 2) return BRGPU_E_INVALID;
+    return brgpu_set_from_bitfield(ctx, (int)payload_host[0], payload_host + 1, n_bytes - 1, out);
+}
+
+extern "C" int brgpu_set_insert_batch(brgpu_set *s, const uint64_t *kmers_host, uint64_t n) {
+    if (!s || (!kmers_host && n)) return BRGPU_E_INVALID;
+    brgpu_ctx *ctx = s->ctx;
+    cudaSetDevice(ctx->device);
+    if (!n) return BRGPU_OK;
+    uint64_t *d_k = nullptr;
+    CK(dalloc(ctx, &d_k, n));
+    CK(cudaMemcpyAsync(d_k, kmers_host, n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    launch_insert_batch(ctx, s->d_bits, s->k, d_k, n);
+    cudaFreeAsync(d_k, ctx->stream);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    return BRGPU_OK;
+}
+
+extern "C" int brgpu_set_k(const brgpu_set *s) { return s ? s->k : 0; }
+extern "C" int brgpu_set_abundance(const brgpu_set *s) { return s ? s->abundance : -1; }
+extern "C" uint64_t brgpu_set_bitfield_bytes(const brgpu_set *s) { return s ? s->n_bytes : 0; }
+extern "C" void *brgpu_set_device_ptr(brgpu_set *s) { return s ? s->d_bits : nullptr; }
+
+extern "C" int brgpu_set_export_bitfield(brgpu_set *s, uint8_t *out_host, uint64_t cap) {
+    if (!s || !out_host) return BRGPU_E_INVALID;
+    brgpu_ctx *ctx = s->ctx;
+    if (cap < s->n_bytes) return fail(ctx, BRGPU_E_OVERFLOW, "output buffer too small");
+    cudaSetDevice(ctx->device);
+    CK(cudaMemcpyAsync(out_host, s->d_bits, s->n_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return BRGPU_OK;
+}
+
+extern "C" int brgpu_set_get_batch(brgpu_set *s, const uint64_t *kmers_host, uint64_t n, uint8_t *out_host) {
+    if (!s || ((!kmers_host || !out_host) && n)) return BRGPU_E_INVALID;
+    brgpu_ctx *ctx = s->ctx;
+    cudaSetDevice(ctx->device);
+    if (!n) return BRGPU_OK;
+    uint64_t *d_k = nullptr;
+    uint8_t *d_o = nullptr;
+    CK(dalloc(ctx, &d_k, n));
+    CK(dalloc(ctx, &d_o, n));
+    CK(cudaMemcpyAsync(d_k, kmers_host, n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    launch_get_batch(ctx, s->d_bits, s->k, d_k, n, d_o);
+    CK(cudaMemcpyAsync(out_host, d_o, n, cudaMemcpyDeviceToHost, ctx->stream));
+    cudaFreeAsync(d_k, ctx->stream);
+    cudaFreeAsync(d_o, ctx->stream);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    return BRGPU_OK;
+}
+
+extern "C" int brgpu_set_spectrum(const brgpu_set *s, uint64_t hist[256]) {
+    if (!s || !hist) return BRGPU_E_INVALID;
+    memcpy(hist, s->hist, sizeof(s->hist));
+    return BRGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// part 2
+// ------------------------------------------------------------------------------------------
+static int validate_methods(brgpu_ctx *ctx, const uint8_t *methods, uint64_t n_methods, int confirm, int max_search) {
+    if (!methods && n_methods) return fail(ctx, BRGPU_E_INVALID, "null method list");
+    for (uint64_t i = 0; i < n_methods; i++)
+        if (methods[i] > BRGPU_GAP_SIZE) return fail(ctx, BRGPU_E_INVALID, "unknown correction method");
+    // confirm == 0 makes every scenario "pass" and hits .expect in the reference
+    if (confirm < 1 || confirm > 255) return fail(ctx, BRGPU_E_INVALID, "confirm must be in 1..=255");
+    if (max_search < 0 || max_search > 255) return fail(ctx, BRGPU_E_INVALID, "max_search must be in 0..=255");
+    return BRGPU_OK;
+}
+
+// one attempt at the whole chain on the given layout; *overflow tells whether a read outgrew its slot
+static int correct_attempt(brgpu_ctx *ctx, const brgpu_set *set, const uint8_t *methods, uint64_t n_methods, int confirm,
+                           int max_search, int two_side, const brgpu_reads *in, brgpu_reads **out, bool *overflow) {
+    const Layout &L = *in->layout;
+    const uint64_t n = L.n;
+    uint8_t *buf[2] = {nullptr, nullptr};
+    uint32_t *len[2] = {nullptr, nullptr};
+    uint32_t *d_bitmap = nullptr;
+    uint8_t *d_scratch = nullptr;
+    cudaError_t e = cudaSuccess;
+    auto cleanup = [&]() {
+        for (int b = 0; b < 2; b++) {
+            if (buf[b]) cudaFreeAsync(buf[b], ctx->stream);
+            if (len[b]) cudaFreeAsync(len[b], ctx->stream);
+        }
+        if (d_bitmap) cudaFreeAsync(d_bitmap, ctx->stream);
+        if (d_scratch) cudaFreeAsync(d_scratch, ctx->stream);
+    };
+    size_t scratch_per_warp = 0;
+    for (uint64_t i = 0; i < n_methods; i++) {
+        CorrectParams p{set->k, methods[i], confirm, max_search};
+        scratch_per_warp = std::max(scratch_per_warp, scan_scratch_per_warp(p));
+    }
+    const int n_warps = scan_grid_warps(ctx);
+    for (int b = 0; b < 2 && e == cudaSuccess; b++) {
+        e = dalloc(ctx, &buf[b], L.total_slots);
+        if (e == cudaSuccess) e = dalloc(ctx, &len[b], n);
+    }
+    if (e == cudaSuccess) e = dalloc(ctx, &d_bitmap, L.total_slots >> 5);
+    if (e == cudaSuccess && scratch_per_warp) e = dalloc(ctx, &d_scratch, scratch_per_warp * (size_t)n_warps);
+    if (e != cudaSuccess) {
+        cleanup();
+        return fail(ctx, BRGPU_E_NOMEM, "device allocation (correction buffers)", e);
+    }
+    cudaMemsetAsync(ctx->d_flags + 1, 0, sizeof(uint32_t), ctx->stream); // overflow flag
+
+    const uint8_t *src = in->d_seq;
+    const uint32_t *src_len = in->d_len;
+    int nxt = 0;
+    auto run_methods = [&]() {
+        for (uint64_t i = 0; i < n_methods; i++) {
+            CorrectParams p{set->k, methods[i], confirm, max_search};
+            launch_solid_bitmap(ctx, L, src, src_len, set->d_bits, set->k, d_bitmap, (double)in->sum_len);
+            launch_scan(ctx, L, src, src_len, buf[nxt], len[nxt], d_bitmap, set->d_bits, p, d_scratch, scratch_per_warp,
+                        n_warps, (double)in->sum_len);
+            src = buf[nxt];
+            src_len = len[nxt];
+            nxt ^= 1;
+        }
+    };
+    auto run_reverse = [&]() {
+        launch_reverse_slots(ctx, L, src, src_len, buf[nxt]);
+        // lengths are unchanged by a reversal: copy them along so (buf, len) stay paired
+        cudaMemcpyAsync(len[nxt], src_len, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream);
+        src = buf[nxt];
+        src_len = len[nxt];
+        nxt ^= 1;
+    };
+    run_methods(); // src/lib.rs:44-46
+    if (!two_side) { // src/lib.rs:48-55 (the flag is inverted: default runs the reversed pass)
+        run_reverse();
+        run_methods();
+        run_reverse();
+    }
+    if (src == in->d_seq) { // no method at all and two_side: plain copy
+        cudaMemcpyAsync(buf[0], in->d_seq, L.total_slots, cudaMemcpyDeviceToDevice, ctx->stream);
+        cudaMemcpyAsync(len[0], in->d_len, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream);
+        src = buf[0];
+        src_len = len[0];
+    }
+    e = cudaGetLastError();
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(ctx->h_pinned, ctx->d_flags + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        cleanup();
+        return fail(ctx, BRGPU_E_CUDA, "correction kernels", e);
+    }
+    *overflow = (*(volatile uint32_t *)ctx->h_pinned) != 0;
+    if (*overflow) {
+        cleanup();
+        return BRGPU_OK;
+    }
+    brgpu_reads *R = new (std::nothrow) brgpu_reads;
+    if (!R) {
+        cleanup();
+        return fail(ctx, BRGPU_E_NOMEM, "host allocation");
+    }
+    R->ctx = ctx;
+    R->layout = in->layout;
+    R->sum_len = in->sum_len; // hint only: lengths change by a few bases per event
+    int keep = (src == buf[0]) ? 0 : 1;
+    R->d_seq = buf[keep];
+    R->d_len = len[keep];
+    buf[keep] = nullptr;
+    len[keep] = nullptr;
+    cleanup();
+    *out = R;
+    return BRGPU_OK;
+}
+
+// re-slot `in` with 4^extra times the default slack (rare: a read outgrew its slot)
+static int reads_reslot(brgpu_reads *in, unsigned slack_extra, brgpu_reads **out) {
+    brgpu_ctx *ctx = in->ctx;
+    const uint64_t n = in->layout->n;
+    uint64_t *d_toff = nullptr, total = 0;
+    int st = reads_tight_offsets(in, &d_toff, &total);
+    if (st != BRGPU_OK) return st;
+    std::vector<uint64_t> h_off(n + 1);
+    uint8_t *d_tight = nullptr;
+    CK(dalloc(ctx, &d_tight, total));
+    launch_gather_from_slots(ctx, *in->layout, in->d_seq, in->d_len, d_toff, d_tight, false);
+    CK(cudaMemcpyAsync(h_off.data(), d_toff, (n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    st = reads_from_tight(ctx, d_tight, true, h_off.data(), n, slack_extra, out);
+    cudaFreeAsync(d_tight, ctx->stream);
+    cudaFreeAsync(d_toff, ctx->stream);
+    return st;
+}
+
+extern "C" int brgpu_correct_reads(brgpu_ctx *ctx, const brgpu_set *set, const uint8_t *methods, uint64_t n_methods,
+                                   int confirm, int max_search, int two_side, const brgpu_reads *in, brgpu_reads **out) {
+    if (!ctx || !set || !in || !out) return ctx ? fail(ctx, BRGPU_E_INVALID, "null argument") : BRGPU_E_INVALID;
+    *out = nullptr;
+    if (set->ctx != ctx || in->ctx != ctx) return fail(ctx, BRGPU_E_INVALID, "handles belong to another context");
+    int st = validate_methods(ctx, methods, n_methods, confirm, max_search);
+    if (st != BRGPU_OK) return st;
+    cudaSetDevice(ctx->device);
+
+    const brgpu_reads *cur = in;
+    brgpu_reads *owned = nullptr;
+    for (unsigned attempt = 0; attempt < 8; attempt++) {
+        bool overflow = false;
+        st = correct_attempt(ctx, set, methods, n_methods, confirm, max_search, two_side, cur, out, &overflow);
+        if (st != BRGPU_OK || !overflow) break;
+        // a read outgrew its slot: re-slot the original input with 4x more slack and start over
+        brgpu_reads *bigger = nullptr;
+        st = reads_reslot(const_cast<brgpu_reads *>(in), attempt + 1, &bigger);
+        if (owned) reads_release(owned);
+        owned = bigger;
+        cur = bigger;
+        if (st != BRGPU_OK) break;
+    }
+    if (owned) reads_release(owned);
+    if (st == BRGPU_OK && !*out) st = fail(ctx, BRGPU_E_OVERFLOW, "a corrected read outgrew its slot after 8 retries");
+    return st;
+}
+
+extern "C" int brgpu_correct_batch(brgpu_ctx *ctx, const brgpu_set *set, const uint8_t *methods, uint64_t n_methods,
+                                   int confirm, int max_search, int two_side, const uint8_t *seq_host,
+                                   const uint64_t *offsets_host, uint64_t n_reads, uint8_t *out_host, uint64_t out_cap,
+                                   uint64_t *out_offsets_host, uint64_t *required) {
+    if (!ctx) return BRGPU_E_INVALID;
+    brgpu_reads *R = nullptr, *C = nullptr;
+    int st = brgpu_reads_upload(ctx, seq_host, offsets_host, n_reads, &R);
+    if (st != BRGPU_OK) return st;
+    st = brgpu_correct_reads(ctx, set, methods, n_methods, confirm, max_search, two_side, R, &C);
+    if (st == BRGPU_OK) st = brgpu_reads_download(C, out_host, out_cap, out_offsets_host, required);
+    brgpu_reads_free(R);
+    brgpu_reads_free(C);
+    return st;
+}
+
+extern "C" int brgpu_correct_one(brgpu_ctx *ctx, const brgpu_set *set, int method, int confirm, int max_search,
+                                 const uint8_t *seq_host, uint64_t len, uint8_t *out_host, uint64_t out_cap,
+                                 uint64_t *out_len) {
+    if (!ctx || !out_len) return BRGPU_E_INVALID;
+    if (method < 0 || method > BRGPU_GAP_SIZE) return fail(ctx, BRGPU_E_INVALID, "unknown correction method");
+    uint8_t m = (uint8_t)method;
+    uint64_t off[2] = {0, len}, ooff[2] = {0, 0};
+    // Corrector::correct is a single forward pass: two_side = 1 disables the reversed pass
+    int st = brgpu_correct_batch(ctx, set, &m, 1, confirm, max_search, 1, seq_host, off, 1, out_host, out_cap, ooff,
+                                 out_len);
+    return st;
+}
+
+// ------------------------------------------------------------------------------------------
+// multi-GPU plumbing
+// ------------------------------------------------------------------------------------------
+extern "C" int brgpu_counts_ipc_export(brgpu_counts *c, uint8_t handle_out[64]) {
+    if (!c || !handle_out) return BRGPU_E_INVALID;
+    brgpu_ctx *ctx = c->ctx;
+    cudaSetDevice(ctx->device);
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, c->d_counts));
+    memcpy(handle_out, &h, 64);
+    return BRGPU_OK;
+}
+
+extern "C" int brgpu_ipc_open(brgpu_ctx *ctx, const uint8_t handle[64], void **peer_dev_ptr) {
+    if (!ctx || !handle || !peer_dev_ptr) return BRGPU_E_INVALID;
+    cudaSetDevice(ctx->device);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CK(cudaIpcOpenMemHandle(peer_dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return BRGPU_OK;
+}
+
+extern "C" int brgpu_ipc_close(brgpu_ctx *ctx, void *peer_dev_ptr) {
+    if (!ctx || !peer_dev_ptr) return BRGPU_E_INVALID;
+    cudaSetDevice(ctx->device);
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaIpcCloseMemHandle(peer_dev_ptr));
+    return BRGPU_OK;
+}
+
+extern "C" int brgpu_counts_merge_slice(brgpu_counts *c, void *const *peer_tables, int n_peers, uint64_t begin,
+                                        uint64_t end) {
+    if (!c || (!peer_tables && n_peers)) return BRGPU_E_INVALID;
+    brgpu_ctx *ctx = c->ctx;
+    if (n_peers < 0 || n_peers > 15) return fail(ctx, BRGPU_E_INVALID, "at most 15 peers");
+    if (begin > end || end > c->n || (begin & 1023) || ((end & 1023) && end != c->n))
+        return fail(ctx, BRGPU_E_INVALID, "slice must be 1024-aligned");
+    cudaSetDevice(ctx->device);
+    launch_merge_slice(ctx, c->d_counts, peer_tables, n_peers, begin, end);
+    CK(cudaGetLastError());
+    return BRGPU_OK;
+}
+
+extern "C" int brgpu_set_threshold_slice(brgpu_set *s, brgpu_counts *c, int abundance, uint64_t begin, uint64_t end) {
+    if (!s || !c) return BRGPU_E_INVALID;
+    brgpu_ctx *ctx = s->ctx;
+    if (c->ctx != ctx || c->k != s->k) return fail(ctx, BRGPU_E_INVALID, "set and counts do not match");
+    if (abundance < 0 || abundance > 255) return fail(ctx, BRGPU_E_INVALID, "abundance must be in 0..=255");
+    if (begin > end || end > c->n || (begin & 1023) || ((end & 1023) && end != c->n))
+        return fail(ctx, BRGPU_E_INVALID, "slice must be 1024-aligned");
+    cudaSetDevice(ctx->device);
+    s->abundance = abundance;
+    return run_spectrum(ctx, c->d_counts, begin, end, s->d_bits, abundance, nullptr);
+}
+
+// ------------------------------------------------------------------------------------------
+// instrumentation
+// ------------------------------------------------------------------------------------------
+extern "C" int brgpu_profile_enable(brgpu_ctx *ctx, int on) {
+    if (!ctx) return BRGPU_E_INVALID;
+    cudaSetDevice(ctx->device);
+    prof_resolve(ctx);
+    ctx->profiling = on != 0;
+    return BRGPU_OK;
+}
+
+extern "C" int brgpu_profile_reset(brgpu_ctx *ctx) {
+    if (!ctx) return BRGPU_E_INVALID;
+    cudaSetDevice(ctx->device);
+    prof_resolve(ctx);
+    ctx->prof.clear();
+    return BRGPU_OK;
+}
+
+extern "C" int brgpu_profile_count(brgpu_ctx *ctx) {
+    if (!ctx) return 0;
+    cudaSetDevice(ctx->device);
+    prof_resolve(ctx);
+    return (int)ctx->prof.size();
+}
+
+extern "C" int brgpu_profile_get(brgpu_ctx *ctx, int i, char *name_out, size_t name_cap, double *ms,
+                                 uint64_t *launches, double *algo_bytes) {
+    if (!ctx || i < 0 || i >= (int)ctx->prof.size()) return BRGPU_E_INVALID;
+    const ProfEntry &p = ctx->prof[(size_t)i];
+    if (name_out && name_cap) {
+        strncpy(name_out, p.name.c_str(), name_cap - 1);
+        name_out[name_cap - 1] = 0;
+    }
+    if (ms) *ms = p.ms;
+    if (launches) *launches = p.launches;
+    if (algo_bytes) *algo_bytes = p.bytes;
+    return BRGPU_OK;
+}
+
+extern "C" uint64_t brgpu_launch_count(const brgpu_ctx *ctx) { return ctx ? ctx->launches : 0; }

@@ -1,0 +1,1012 @@
+// correct_kernels.cu — part 2 of br's hot path on sm_100a: the per-read correction pass.
+//
+// One pass of one method over all reads is two kernels:
+//
+//   solid_bitmap_kernel   ("phase A") — embarrassingly parallel and HBM-sector bound: one thread
+//       per 32 read positions rolls the k-mers in registers and gathers their solidity bits
+//       (32 independent random 32 B sector reads in flight per thread) into a per-read bitmap.
+//   scan_kernel           ("phase B") — Corrector::correct (src/correct/mod.rs:53-107) is
+//       sequential inside a read (kmer / previous / i carry across events), so one warp owns one
+//       read and walks it in order; reads are handed out longest-first from an atomic work
+//       queue.  While the rolling k-mer consists of input bases only, the scan just looks for
+//       the next solid->weak transition in the phase-A bitmap (1024 positions per step); at a
+//       transition the lanes enumerate the candidate lookups of the method in parallel
+//       (alternatives, scenario scores, successor sets) and the winner is picked with
+//       ballots.  After a successful correction the next k-1 k-mers contain corrected bases,
+//       so they are looked up directly, 32 positions per round.
+//
+// Reference functions restated here (Rust; there is no reference kernel):
+//   Corrector::correct, alt_nucs, next_nucs, error_len      src/correct/mod.rs:53-152
+//   Exist::correct_error, Scenario::{get_score,one_more}    src/correct/exist/mod.rs:21-149
+//   ScenarioOne / ScenarioTwo                                src/correct/exist/one.rs:57-71, two.rs:89-325
+//   Graph::correct_error                                     src/correct/graph.rs:44-85
+//   Greedy::correct_error + bio 1.6.0 global alignment       src/correct/greedy.rs:56-173
+//   GapSize::correct_error, ins_sub_correction               src/correct/gap_size.rs:44-108
+#include "internal.h"
+#include "kmer.cuh"
+
+namespace brgpu {
+
+// ------------------------------------------------------------------------------------------
+// phase A
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    solid_bitmap_kernel(const uint8_t *__restrict__ seq, const uint32_t *__restrict__ len,
+                        const uint64_t *__restrict__ slot_off, const uint32_t *__restrict__ word2read,
+                        uint64_t n_words, int k, const uint8_t *__restrict__ bits, uint32_t *__restrict__ bitmap) {
+    const uint64_t mask = kmask(k);
+    for (uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < n_words;
+         w += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t r = __ldg(word2read + w);
+        uint64_t sb = w << 5;
+        uint32_t p0 = (uint32_t)(sb - __ldg(slot_off + r));
+        uint32_t L = __ldg(len + r);
+        uint32_t out = 0;
+        if (p0 < L && L >= (uint32_t)k) {
+            uint64_t prev, cur;
+            load_window(seq, sb, p0, prev, cur);
+            int t_lo = p0 >= (uint32_t)(k - 1) ? 0 : (k - 1 - (int)p0);
+            int t_hi = (L - p0) < 32u ? (int)(L - p0) : 32;
+#pragma unroll
+            for (int t = 0; t < 32; t++) {
+                if (t >= t_lo && t < t_hi) {
+                    if (solid(bits, window_kmer(prev, cur, t, mask), k)) out |= 1u << t;
+                }
+            }
+        }
+        bitmap[w] = out;
+    }
+}
+
+void launch_solid_bitmap(brgpu_ctx *ctx, const Layout &L, const uint8_t *d_seq, const uint32_t *d_len,
+                         const uint8_t *d_bits, int k, uint32_t *d_bitmap, double n_bases_hint) {
+    uint64_t n_words = L.total_slots >> 5;
+    if (!n_words) return;
+    // algorithmic bytes per position: 32 B sector + 1 B ASCII in + 1/8 B bit out
+    ProfScope ps(ctx, "solid_bitmap", n_bases_hint * 33.125);
+    uint64_t need = (n_words + 255) / 256;
+    uint64_t capb = (uint64_t)ctx->sm_count * 8;
+    solid_bitmap_kernel<<<(unsigned)(need < capb ? need : capb), 256, 0, ctx->stream>>>(
+        d_seq, d_len, L.d_slot_off, L.d_word2read, n_words, k, d_bits, d_bitmap);
+}
+
+// ------------------------------------------------------------------------------------------
+// phase B — warp-level machinery.  All `Rd` fields and all scalar state in the scan are
+// warp-uniform unless a comment says "per lane".
+// ------------------------------------------------------------------------------------------
+struct Rd {
+    const uint8_t *in;   // read bytes (slot)
+    uint32_t len;        // input length
+    uint8_t *out;        // output slot
+    uint32_t cap;        // output capacity
+    const uint32_t *bm;  // phase-A bitmap of this read (bit p = solid(k-mer ending at p))
+    const uint8_t *bits; // the solid set
+    int k;
+    uint64_t mask;
+    int lane;
+    uint32_t o;          // bytes produced so far (keeps counting past cap)
+    uint32_t copy_from;  // input bytes [copy_from, i) are still to be copied to out
+    uint8_t *scratch;    // per-warp scratch (Greedy)
+};
+
+// result of correct_error
+struct Corr {
+    bool some;
+    uint32_t n_emit;   // bases emitted
+    uint32_t codes;    // up to 3 emitted 2-bit codes, first base in the highest used pair (Exist)
+    bool in_place;     // bases already written at out[o..] (walk methods); new_kmer is valid
+    uint64_t new_kmer; // rolling k-mer after the emitted bases (walk methods)
+    uint32_t offset;   // read bases consumed
+};
+
+__device__ __forceinline__ void copy_range(Rd &rd, uint32_t from, uint32_t to) {
+    if (to <= from) return;
+    uint32_t n = to - from;
+    for (uint32_t t = rd.lane; t < n; t += 32) {
+        uint32_t dst = rd.o + t;
+        if (dst < rd.cap) rd.out[dst] = rd.in[from + t];
+    }
+    rd.o += n;
+}
+
+__device__ __forceinline__ void flush_copy(Rd &rd, uint32_t upto) {
+    if (upto > rd.len) upto = rd.len;
+    if (upto > rd.copy_from) {
+        copy_range(rd, rd.copy_from, upto);
+        rd.copy_from = upto;
+    }
+}
+
+__device__ __forceinline__ void emit_byte(Rd &rd, uint8_t b) {
+    if (rd.lane == 0 && rd.o < rd.cap) rd.out[rd.o] = b;
+    rd.o += 1;
+}
+
+// k-mer made of the input bases in[p-k+1 ..= p]
+__device__ __forceinline__ uint64_t load_kmer_at(const Rd &rd, uint32_t p) {
+    uint64_t v = 0;
+    if (rd.lane < rd.k) v = (uint64_t)nuc2bit(rd.in[p - (uint32_t)rd.k + 1u + (uint32_t)rd.lane]) << (2 * (rd.k - 1 - rd.lane));
+    return warp_or64(v);
+}
+
+// per lane l: `kmer` after pushing ptr[0..=l]; only lanes l < n (n <= 32) get a defined value
+__device__ __forceinline__ uint64_t push_window(const Rd &rd, uint64_t kmer, const uint8_t *ptr, uint32_t n) {
+    uint64_t c = 0;
+    if ((uint32_t)rd.lane < n) c = (uint64_t)nuc2bit(ptr[rd.lane]) << (2 * (31 - rd.lane));
+    uint64_t W = warp_or64(c);
+    int sh = 2 * (rd.lane + 1);
+    uint64_t hi = sh < 64 ? (kmer << sh) : 0ULL;
+    return (hi | (W >> (2 * (31 - rd.lane)))) & rd.mask;
+}
+
+// `kmer` after pushing ptr[0..n) — scalar loop, any lane may call it on its own data
+__device__ __forceinline__ uint64_t push_seq(uint64_t kmer, const uint8_t *ptr, uint32_t n, uint64_t mask) {
+    for (uint32_t u = 0; u < n; u++) kmer = push(kmer, nuc2bit(ptr[u]), mask);
+    return kmer;
+}
+
+// 4-bit mask of the successors of x that are solid: next_nucs(x) (src/correct/mod.rs:118-128).
+// alt_nucs(y) == succ_mask(y >> 2) with the same push, because push masks the top base away.
+__device__ __forceinline__ uint32_t succ_mask(const Rd &rd, uint64_t x) {
+    bool s = false;
+    if (rd.lane < 4) s = solid(rd.bits, push(x, (uint32_t)rd.lane, rd.mask), rd.k);
+    return __ballot_sync(FULL, s) & 0xfu;
+}
+__device__ __forceinline__ uint32_t alt_mask(const Rd &rd, uint64_t weak) {
+    bool s = false;
+    if (rd.lane < 4) s = solid(rd.bits, replace_last(weak, (uint32_t)rd.lane, rd.mask), rd.k);
+    return __ballot_sync(FULL, s) & 0xfu;
+}
+__device__ __forceinline__ bool uniq(uint32_t m4, uint32_t &a) {
+    a = (uint32_t)(__ffs(m4) - 1);
+    return __popc(m4) == 1;
+}
+
+// First position j in [i, len) with !S[j] && P[j], where S is the phase-A bitmap, P[j] = S[j-1]
+// for j > i and P[i] = previous.  Returns len when there is none.
+__device__ __forceinline__ uint32_t find_transition(const Rd &rd, uint32_t i, bool previous) {
+    uint32_t wbase = i >> 5;
+    const uint32_t n_words = (rd.len + 31) >> 5;
+    uint32_t carry_in = 0;
+    for (;;) {
+        uint32_t wi = wbase + (uint32_t)rd.lane;
+        uint32_t W = wi < n_words ? __ldg(rd.bm + wi) : 0u;
+        uint32_t up = __shfl_up_sync(FULL, W, 1);
+        uint32_t carry = rd.lane ? (up >> 31) : carry_in;
+        uint32_t T = ~W & ((W << 1) | carry);
+        uint32_t posbase = wi << 5;
+        if (posbase + 31 < i) {
+            T = 0;
+        } else if (posbase <= i) {
+            uint32_t sh = i - posbase;
+            T &= (0xffffffffu << sh);
+            T &= ~(1u << sh);
+            if (previous && !((W >> sh) & 1u)) T |= 1u << sh;
+        }
+        if (posbase >= rd.len)
+            T = 0;
+        else if (posbase + 32 > rd.len)
+            T &= (1u << (rd.len - posbase)) - 1u;
+        uint32_t any = __ballot_sync(FULL, T != 0);
+        if (any) {
+            int fl = __ffs(any) - 1;
+            uint32_t Tf = __shfl_sync(FULL, T, fl);
+            return ((wbase + (uint32_t)fl) << 5) + (uint32_t)(__ffs(Tf) - 1);
+        }
+        wbase += 32;
+        if (wbase >= n_words) return rd.len;
+        // continue in the next window: its first position has P = S[pos-1] = top bit of lane 31
+        carry_in = __shfl_sync(FULL, W, 31) >> 31;
+        i = wbase << 5;
+        previous = carry_in != 0;
+    }
+}
+
+// First position p in [from, len) whose phase-A bit is set; len when none.
+__device__ __forceinline__ uint32_t find_solid(const Rd &rd, uint32_t from) {
+    if (from >= rd.len) return rd.len;
+    uint32_t wbase = from >> 5;
+    const uint32_t n_words = (rd.len + 31) >> 5;
+    for (;;) {
+        uint32_t wi = wbase + (uint32_t)rd.lane;
+        uint32_t W = wi < n_words ? __ldg(rd.bm + wi) : 0u;
+        uint32_t posbase = wi << 5;
+        if (posbase + 31 < from)
+            W = 0;
+        else if (posbase <= from)
+            W &= 0xffffffffu << (from - posbase);
+        uint32_t any = __ballot_sync(FULL, W != 0);
+        if (any) {
+            int fl = __ffs(any) - 1;
+            uint32_t Wf = __shfl_sync(FULL, W, fl);
+            uint32_t p = ((wbase + (uint32_t)fl) << 5) + (uint32_t)(__ffs(Wf) - 1);
+            return p < rd.len ? p : rd.len; // bits at positions >= len are never set, but stay safe
+        }
+        wbase += 32;
+        if (wbase >= n_words) return rd.len;
+    }
+}
+
+// error_len (src/correct/mod.rs:130-152) for the weak k-mer `kmer` whose last base is in[i].
+// `dr` = how many of the following pushes still produce k-mers that contain corrected bases
+// (0 in the clean state): those need real lookups, everything after is in the phase-A bitmap.
+// Returns elen; hit_end = the weak run reaches the end of the read (then fck is not solid).
+__device__ __forceinline__ uint32_t error_len(const Rd &rd, uint64_t kmer, uint32_t i, uint32_t dr, bool &hit_end,
+                                              uint64_t &fck) {
+    const uint32_t sublen = rd.len - i;
+    hit_end = false;
+    // j = 1..dr: dirty k-mers (dr <= k-2 < 32, one round)
+    uint32_t nd = dr < sublen - 1 ? dr : sublen - 1; // pushes available: sub[1..sublen-1]
+    if (nd > 0) {
+        uint64_t km = push_window(rd, kmer, rd.in + i + 1, nd);
+        bool s = (uint32_t)rd.lane < nd && solid(rd.bits, km, rd.k);
+        uint32_t m = __ballot_sync(FULL, s);
+        if (m) {
+            int l = __ffs(m) - 1;
+            fck = shfl64(km, l);
+            return (uint32_t)l + 1u;
+        }
+    }
+    if (nd == sublen - 1) { // ran out of read inside the dirty part
+        hit_end = true;
+        fck = 0;
+        return sublen;
+    }
+    uint32_t p = find_solid(rd, i + dr + 1);
+    if (p >= rd.len) {
+        hit_end = true;
+        fck = 0;
+        return sublen;
+    }
+    fck = load_kmer_at(rd, p); // k-mers beyond the dirty part are pure input
+    return p - i;
+}
+
+// ------------------------------------------------------------------------------------------
+// Exist<S>::correct_error (src/correct/exist/mod.rs:120-149) for One (3 scenarios) and Two (13).
+//
+// Rounds of independent lookups instead of the reference's nested calls:
+//   round 1  alt_nucs(kmer)                                   4 lookups
+//   round 2  (Two only) the successor sets every apply() needs 16 lookups:
+//            N0 = next(K0), N1 = next(push(K0,s1)), N2 = next(push(K0,s2)), N0' = next(push(K0,s0))
+//            — every alt_nucs(...) inside two.rs:98-254 reduces to one of these because
+//            add_nuc_to_end masks the oldest base away
+//   round 3  per scenario: get(K), the c confirmations of get_score, and the one_more k-mer
+//            NS * (c + 2) lookups, flattened over the lanes
+// A result needs exactly one surviving scenario, so evaluation order cannot change it.
+// ------------------------------------------------------------------------------------------
+struct Scen {        // per lane: lane s describes scenario s
+    bool valid;      // apply() returned Some (length preconditions + uniqueness)
+    uint64_t K;      // k-mer after apply
+    uint32_t offa;   // apply offset (scoring)
+    uint32_t offc;   // correct offset (advance)
+    uint32_t n_emit; // bases correct() emits
+    uint32_t codes;  // their 2-bit codes, first base highest
+};
+
+__device__ __forceinline__ Scen scen_one(int s, uint64_t K0) {
+    Scen sc;
+    sc.valid = s < 3;
+    sc.K = K0;
+    sc.offa = sc.offc = (uint32_t)(2 - s); // I:2 S:1 D:0 (one.rs:57-71)
+    sc.n_emit = 1;
+    sc.codes = (uint32_t)(K0 & 3);
+    return sc;
+}
+
+__device__ __forceinline__ Scen scen_two(int s, uint64_t K0, uint32_t sublen, const uint32_t sb[4], uint32_t N0,
+                                         uint32_t N1, uint32_t N2, uint32_t N0p, uint64_t mask) {
+    Scen sc;
+    sc.valid = false;
+    sc.K = K0;
+    sc.offa = sc.offc = 0;
+    sc.n_emit = 0;
+    sc.codes = 0;
+    const uint32_t last = (uint32_t)(K0 & 3);
+    uint32_t u0, u1, u2, u0p;
+    const bool q0 = uniq(N0, u0), q1 = uniq(N1, u1), q2 = uniq(N2, u2), q0p = uniq(N0p, u0p);
+    const uint64_t K1 = push(K0, sb[1], mask);
+    switch (s) {
+    case 0: // II  two.rs:96, :260
+        sc.valid = true; sc.offa = 3; sc.offc = 2; sc.n_emit = 1; sc.codes = last; break;
+    case 1: // IS  two.rs:97, :261
+        sc.valid = true; sc.offa = 2; sc.offc = 2; sc.n_emit = 1; sc.codes = last; break;
+    case 2: // SS  two.rs:98-114
+        sc.valid = sublen >= 2 && !((N0 >> sb[1]) & 1) && q0;
+        sc.K = push(K0, u0, mask); sc.offa = 2; sc.offc = 2; sc.n_emit = 2; sc.codes = (last << 2) | u0; break;
+    case 3: // SD  two.rs:115-126
+        sc.valid = sublen >= 1 && q0;
+        sc.K = push(K0, u0, mask); sc.offa = 1; sc.offc = 1; sc.n_emit = 2; sc.codes = (last << 2) | u0; break;
+    case 4: // DD  two.rs:127-134
+        sc.valid = q0;
+        sc.K = push(K0, u0, mask); sc.offa = 0; sc.offc = 0; sc.n_emit = 2; sc.codes = (last << 2) | u0; break;
+    case 5: // ICI two.rs:135-148, :275
+        sc.valid = sublen >= 4 && ((N0 >> sb[3]) & 1);
+        sc.K = push(K0, sb[3], mask); sc.offa = 4; sc.offc = 3; sc.n_emit = 1; sc.codes = last; break;
+    case 6: // ICS two.rs:149-166, :289-301 (correct offset = apply + 1)
+        sc.valid = sublen >= 4 && !((N0 >> sb[1]) & 1) && q0;
+        sc.K = push(K0, u0, mask); sc.offa = 3; sc.offc = 4; sc.n_emit = 2; sc.codes = (last << 2) | u0; break;
+    case 7: // ICD two.rs:167-181, :276-288 (correct offset = apply - 1; K0's alt base is not emitted)
+        sc.valid = sublen >= 4 && q2;
+        sc.K = push(push(K0, sb[2], mask), u2, mask); sc.offa = 3; sc.offc = 2; sc.n_emit = 2;
+        sc.codes = (sb[2] << 2) | u2; break;
+    case 8: // SCI two.rs:182-191
+        sc.valid = sublen >= 4;
+        sc.K = push(K1, sb[3], mask); sc.offa = 4; sc.offc = 4; sc.n_emit = 3;
+        sc.codes = (last << 4) | (sb[1] << 2) | sb[3]; break;
+    case 9: // SCS two.rs:192-215
+        sc.valid = sublen >= 3 && ((N0 >> sb[1]) & 1) && !((N1 >> sb[2]) & 1) && q1;
+        sc.K = push(K1, u1, mask); sc.offa = 3; sc.offc = 3; sc.n_emit = 3;
+        sc.codes = (last << 4) | (sb[1] << 2) | u1; break;
+    case 10: // SCD two.rs:216-230
+        sc.valid = sublen >= 2 && q1;
+        sc.K = push(K1, u1, mask); sc.offa = 2; sc.offc = 2; sc.n_emit = 3;
+        sc.codes = (last << 4) | (sb[1] << 2) | u1; break;
+    case 11: // DCI two.rs:231-240, :323 (`_ => (vec![], 1)`)
+        sc.valid = sublen >= 4;
+        sc.K = push(K1, sb[3], mask); sc.offa = 4; sc.offc = 1; sc.n_emit = 0; sc.codes = 0; break;
+    case 12: // DCD two.rs:241-254
+        sc.valid = sublen >= 2 && q0p;
+        sc.K = push(push(K0, sb[0], mask), u0p, mask); sc.offa = 1; sc.offc = 1; sc.n_emit = 3;
+        sc.codes = (last << 4) | (sb[0] << 2) | u0p; break;
+    default: break;
+    }
+    return sc;
+}
+
+template <int NS>
+__device__ __forceinline__ Corr exist_correct_error(Rd &rd, uint64_t kmer, uint32_t i, uint32_t c) {
+    Corr res;
+    res.some = false;
+    res.in_place = false;
+    res.n_emit = 0;
+    res.codes = 0;
+    res.offset = 0;
+    res.new_kmer = 0;
+
+    uint32_t alt;
+    if (!uniq(alt_mask(rd, kmer), alt)) return res; // exist/mod.rs:121-126
+    const uint64_t K0 = replace_last(kmer, alt, rd.mask);
+    const uint8_t *sub = rd.in + i;
+    const uint32_t sublen = rd.len - i;
+
+    Scen sc;
+    if (NS == 3) {
+        sc = scen_one(rd.lane, K0);
+    } else {
+        uint32_t sb[4];
+#pragma unroll
+        for (int t = 0; t < 4; t++) sb[t] = (uint32_t)t < sublen ? nuc2bit(sub[t]) : 0u;
+        // round 2: the four successor sets
+        bool s = false;
+        if (rd.lane < 16) {
+            int g = rd.lane >> 2;
+            uint64_t base = K0;
+            bool need = true;
+            if (g == 1) { base = push(K0, sb[1], rd.mask); need = sublen >= 2; }
+            if (g == 2) { base = push(K0, sb[2], rd.mask); need = sublen >= 3; }
+            if (g == 3) { base = push(K0, sb[0], rd.mask); }
+            if (need) s = solid(rd.bits, push(base, (uint32_t)(rd.lane & 3), rd.mask), rd.k);
+        }
+        uint32_t m = __ballot_sync(FULL, s);
+        sc = scen_two(rd.lane, K0, sublen, sb, m & 0xf, (m >> 4) & 0xf, (m >> 8) & 0xf, (m >> 12) & 0xf, rd.mask);
+    }
+
+    // round 3: items (s, u), u = 0 .. c+1
+    const uint32_t per = c + 2;
+    const uint32_t Q = (uint32_t)NS * per;
+    uint32_t bad = 0, more = 0; // per lane partial masks over scenarios
+    for (uint32_t q0 = 0; q0 < Q; q0 += 32) {
+        uint32_t q = q0 + (uint32_t)rd.lane;
+        int s = (int)(q / per);
+        uint32_t u = q - (uint32_t)s * per;
+        int src = s < NS ? s : 0;
+        // fetch scenario s from lane s (all lanes take part in the shuffles)
+        bool v = __shfl_sync(FULL, (int)sc.valid, src) != 0;
+        uint64_t K = shfl64(sc.K, src);
+        uint32_t offa = __shfl_sync(FULL, sc.offa, src);
+        uint32_t offc = __shfl_sync(FULL, sc.offc, src);
+        uint32_t ne = __shfl_sync(FULL, sc.n_emit, src);
+        uint32_t codes = __shfl_sync(FULL, sc.codes, src);
+        if (q >= Q || !v) continue;
+        if (offa + c > sublen) { // get_score: `if offset + c > seq.len() return 0` (exist/mod.rs:29-31)
+            bad |= 1u << s;
+            continue;
+        }
+        if (u <= c) {
+            // u = 0: get(K) (exist/mod.rs:23); u = 1..c: the c confirmations (:35-43)
+            uint64_t km = push_seq(K, sub + offa, u, rd.mask);
+            if (!solid(rd.bits, km, rd.k)) bad |= 1u << s;
+        } else {
+            // one_more (exist/mod.rs:49-70): uses correct()'s bases and offset, tests one k-mer
+            if (sublen > c + offc + 1) {
+                uint64_t km = K0 >> 2;
+                for (int e = (int)ne - 1; e >= 0; e--) km = push(km, (codes >> (2 * e)) & 3u, rd.mask);
+                km = push_seq(km, sub + offc, c + 1, rd.mask);
+                if (solid(rd.bits, km, rd.k)) more |= 1u << s;
+            }
+        }
+    }
+    bad = __reduce_or_sync(FULL, bad);
+    more = __reduce_or_sync(FULL, more);
+    uint32_t valid_mask = __ballot_sync(FULL, sc.valid && rd.lane < NS);
+    uint32_t cand = valid_mask & ~bad;
+
+    if (cand == 0) return res;                       // exist/mod.rs:132-134
+    if (__popc(cand) > 1) {                          // :138-148
+        cand &= more;
+        if (__popc(cand) != 1) return res;
+    }
+    int win = __ffs(cand) - 1;
+    res.some = true;
+    res.n_emit = __shfl_sync(FULL, sc.n_emit, win);
+    res.codes = __shfl_sync(FULL, sc.codes, win);
+    res.offset = __shfl_sync(FULL, sc.offc, win);
+    return res;
+}
+
+// ------------------------------------------------------------------------------------------
+// Graph::correct_error (src/correct/graph.rs:44-85).
+//
+// The walk x0 -> x1 -> ... follows the unique solid successor, i.e. it is a deterministic
+// sequence.  The reference keeps an FxHashSet of visited k-mers and fails on the first revisit;
+// for a deterministic sequence "first_correct_kmer is reached before any revisit" is the same
+// as "first_correct_kmer is reached at all" (a value inside the cycle would have been met
+// before the cycle closed), with the one exception x0 == first_correct_kmer, which the
+// reference can only meet as a revisit.  So the visited set is replaced by Brent's cycle
+// detection, which only has to guarantee termination.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ Corr graph_correct_error(Rd &rd, uint64_t kmer, uint32_t i, uint32_t dr) {
+    Corr res;
+    res.some = false;
+    res.in_place = true;
+    res.n_emit = 0;
+    res.codes = 0;
+    res.offset = 0;
+    res.new_kmer = 0;
+
+    bool hit_end;
+    uint64_t fck;
+    uint32_t elen = error_len(rd, kmer, i, dr, hit_end, fck);
+
+    uint32_t alt;
+    if (!uniq(alt_mask(rd, kmer), alt)) return res;
+    // weak run reaches the end of the read: first_correct_kmer is not solid, every walk k-mer is,
+    // so the reference can only end in None
+    if (hit_end) return res;
+    uint64_t x = replace_last(kmer, alt, rd.mask);
+    if (x == fck) return res;
+
+    flush_copy(rd, i);
+    const uint32_t o0 = rd.o;
+    uint32_t n = 0;
+    if (rd.lane == 0 && o0 + n < rd.cap) rd.out[o0 + n] = bit2nuc(alt);
+    n++;
+
+    uint64_t tortoise = x;
+    uint32_t power = 1, lam = 0;
+    for (;;) {
+        uint32_t a;
+        if (!uniq(succ_mask(rd, x), a)) return res; // dead end or branch
+        x = push(x, a, rd.mask);
+        lam++;
+        if (x == tortoise) return res; // cycle that never meets fck
+        if (lam == power) {
+            tortoise = x;
+            power <<= 1;
+            lam = 0;
+        }
+        if (rd.lane == 0 && o0 + n < rd.cap) rd.out[o0 + n] = bit2nuc(a);
+        n++;
+        if (x == fck) break;
+        if (n == 0xfffffff0u) return res; // cannot happen: 2^33 solid k-mers at most
+    }
+    res.some = true;
+    res.n_emit = n;
+    res.new_kmer = x;
+    res.offset = elen + 1;
+    return res;
+}
+
+// ------------------------------------------------------------------------------------------
+// GapSize::ins_sub_correction (src/correct/gap_size.rs:44-89): exactly `gap` unique-successor
+// steps, failing on a revisit.  For the deterministic walk "x0..x_gap are pairwise distinct" is
+// equivalent to "x_gap does not occur among x0..x_{gap-1}" (once a value repeats, every later
+// value is a repeat as well), so the hash set is replaced by one check of the last k-mer
+// against the k-mers of the emitted path, done by all lanes in parallel.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ Corr ins_sub_correction(Rd &rd, uint64_t kmer, uint32_t i, uint32_t gap) {
+    Corr res;
+    res.some = false;
+    res.in_place = true;
+    res.n_emit = 0;
+    res.codes = 0;
+    res.offset = 0;
+    res.new_kmer = 0;
+
+    uint32_t alt;
+    if (!uniq(alt_mask(rd, kmer), alt)) return res;
+    const uint64_t x0 = replace_last(kmer, alt, rd.mask);
+    uint64_t x = x0;
+
+    flush_copy(rd, i);
+    const uint32_t o0 = rd.o;
+    uint32_t n = 0;
+    if (rd.lane == 0 && o0 + n < rd.cap) rd.out[o0 + n] = bit2nuc(alt);
+    n++;
+    for (uint32_t t = 0; t < gap; t++) {
+        uint32_t a;
+        if (!uniq(succ_mask(rd, x), a)) return res;
+        x = push(x, a, rd.mask);
+        if (rd.lane == 0 && o0 + n < rd.cap) rd.out[o0 + n] = bit2nuc(a);
+        n++;
+    }
+    // revisit check: is x (= x_gap) one of x_0 .. x_{gap-1}?  x_t ends with path base t, and
+    // the path bases are out[o0 .. o0+gap].  If the path did not fit in the slot the batch is
+    // re-run with more capacity anyway, so the answer does not matter then.
+    if (gap > 0 && o0 + n <= rd.cap) {
+        __syncwarp();
+        const uint32_t chunk = (gap + 31) / 32; // x_0 .. x_{gap-1}: gap candidates
+        uint32_t t0 = (uint32_t)rd.lane * chunk;
+        uint32_t t1 = t0 + chunk < gap ? t0 + chunk : gap;
+        bool hit = false;
+        if (t0 < t1) {
+            // roll from x0 to x_{t0}: push path bases 1..t0
+            uint64_t y = x0;
+            // jump: only the last k bases matter, start at most k steps before t0
+            uint32_t start = t0 > (uint32_t)rd.k ? t0 - (uint32_t)rd.k : 0;
+            if (start > 0) y = 0;
+            for (uint32_t t = start + 1; t <= t0; t++) y = push(y, nuc2bit(rd.out[o0 + t]), rd.mask);
+            if (start > 0) {
+                // y now holds path bases start+1..t0 (k of them) == x_{t0} because t0 - start == k
+            }
+            for (uint32_t t = t0;;) {
+                if (y == x) hit = true;
+                if (++t >= t1) break;
+                y = push(y, nuc2bit(rd.out[o0 + t]), rd.mask);
+            }
+        }
+        if (__any_sync(FULL, hit)) return res;
+    }
+    res.some = true;
+    res.n_emit = n;
+    res.new_kmer = x;
+    res.offset = n; // offset = local_corr.len() (gap_size.rs:87)
+    return res;
+}
+
+// GapSize::correct_error (src/correct/gap_size.rs:97-108)
+__device__ __forceinline__ Corr gap_size_correct_error(Rd &rd, uint64_t kmer, uint32_t i, uint32_t dr, uint32_t c) {
+    bool hit_end;
+    uint64_t fck;
+    uint32_t elen = error_len(rd, kmer, i, dr, hit_end, fck);
+    if (elen < (uint32_t)rd.k) return graph_correct_error(rd, kmer, i, dr);
+    if (elen == (uint32_t)rd.k) return exist_correct_error<3>(rd, kmer, i, c);
+    return ins_sub_correction(rd, kmer, i, elen - (uint32_t)rd.k);
+}
+
+// ------------------------------------------------------------------------------------------
+// Greedy (src/correct/greedy.rs:56-173).
+//
+// match_alignement runs bio 1.6.0's affine global aligner (gap open -1, extend -1, match +1,
+// mismatch -1) on x = before || read[..i] and y = before || path.  In `global` mode every clip
+// penalty is MIN_SCORE, so no clip state can ever win and the recurrence reduces to the classic
+// three layers with bio's tie rules: extension beats opening only if strictly greater; S takes
+// the diagonal first, then I, then D, each only if strictly greater; an I (or D) cell opened
+// from S stores the S pointer of the cell it came from.  One lane owns up to RMAX consecutive
+// rows and the lanes sweep the columns as a systolic wavefront; the 12-bit traceback cells go
+// to per-warp scratch and the traceback itself is replayed by all lanes uniformly.
+// ------------------------------------------------------------------------------------------
+enum : uint32_t { TB_START = 0, TB_INS = 1, TB_DEL = 2, TB_SUBST = 3, TB_MATCH = 4 };
+enum : uint8_t { OP_MATCH = 0, OP_SUBST = 1, OP_DEL = 2, OP_INS = 3 };
+constexpr int NEG = -1000000; // stands in for MIN_SCORE: always loses against a real score
+constexpr int GREEDY_RMAX = 9; // rows per lane: covers k-1 + 255 + 1 rows
+
+struct GreedyScratch {
+    uint16_t *tb;     // (m+1) x (n+1) traceback cells, row-major with stride n_max+1
+    uint8_t *ops;     // reversed operations
+    uint8_t *x;       // before || read part
+    uint8_t *y;       // before || path
+    uint64_t *viewed; // visited k-mers
+    int32_t *edge;    // 3 x (n_max+1): S, I, sbits of the last row of the lane above (systolic hand-off)
+};
+
+__host__ __device__ inline size_t greedy_dim(int k, int max_search) { return (size_t)(k - 1 + max_search + 2); }
+
+__device__ __forceinline__ GreedyScratch greedy_scratch(uint8_t *base, int k, int max_search) {
+    size_t d = greedy_dim(k, max_search);
+    GreedyScratch g;
+    size_t off = 0;
+    g.viewed = reinterpret_cast<uint64_t *>(base + off);
+    off += ((size_t)max_search + 2) * 8;
+    g.tb = reinterpret_cast<uint16_t *>(base + off);
+    off += d * d * 2;
+    off = (off + 3) & ~(size_t)3;
+    g.edge = reinterpret_cast<int32_t *>(base + off);
+    off += 3 * d * 4;
+    g.ops = base + off;
+    off += 2 * d;
+    g.x = base + off;
+    off += d;
+    g.y = base + off;
+    return g;
+}
+
+size_t scan_scratch_per_warp(const CorrectParams &p) {
+    if (p.method != BRGPU_GREEDY) return 0;
+    size_t d = greedy_dim(p.k, p.max_search);
+    size_t bytes = ((size_t)p.max_search + 2) * 8 + d * d * 2 + 4 + 3 * d * 4 + 2 * d + d + d;
+    return (bytes + 127) & ~(size_t)127;
+}
+
+// Global alignment of x[0..m) vs y[0..n); fills g.ops (reversed) and returns the op count.
+__device__ __forceinline__ uint32_t bio_global(const Rd &rd, const GreedyScratch &g, uint32_t m, uint32_t n,
+                                               uint32_t stride) {
+    const int lane = rd.lane;
+    const uint32_t rows = m + 1; // rows 0..m; row 0 is the boundary
+    const uint32_t R = (rows + 31) / 32; // rows per lane (<= GREEDY_RMAX)
+    const uint32_t r0 = (uint32_t)lane * R; // first row of this lane
+    // per-lane state for its rows at the previous column: S and D; at the current column: S, I
+    int Sp[GREEDY_RMAX], Dp[GREEDY_RMAX];
+    uint32_t sbp[GREEDY_RMAX]; // S-pointer of (row, j-1)
+    // column 0
+#pragma unroll
+    for (int q = 0; q < GREEDY_RMAX; q++) {
+        uint32_t i = r0 + (uint32_t)q;
+        Sp[q] = NEG;
+        Dp[q] = NEG;
+        sbp[q] = TB_START;
+        if ((uint32_t)q < R && i < rows) {
+            if (i == 0) {
+                Sp[q] = 0;
+                g.tb[0] = (uint16_t)((TB_START << 8) | (TB_START << 4) | TB_START);
+            } else {
+                Sp[q] = -1 - (int)i; // gap_open + gap_extend * i
+                sbp[q] = TB_INS;
+                uint32_t ib = i == 1 ? TB_START : TB_INS;
+                g.tb[(size_t)i * stride] = (uint16_t)((TB_INS << 8) | (TB_START << 4) | ib);
+            }
+        }
+    }
+    // systolic sweep: at step t lane l handles column j = t - l + 1 (1..n)
+    // hand-off registers from the lane above: S, I, sbits of its last row at column j and j-1
+    int upS_prev = NEG; // S(r0-1, j-1)
+    // for lane 0, "row above" does not exist; its first row is row 0 (boundary), handled inline
+    if (lane > 0) {
+        uint32_t ia = r0 - 1; // last row of the lane above, column 0
+        upS_prev = ia < rows ? (ia == 0 ? 0 : -1 - (int)ia) : NEG;
+    }
+    int lastS = NEG, lastI = NEG; // this lane's last row at the column it just finished
+    uint32_t lastSb = TB_START;
+    const uint32_t steps = n + 31;
+    for (uint32_t t = 0; t < steps; t++) {
+        // values of the lane above for the column this lane is about to do (it did it last step)
+        int upS = __shfl_up_sync(FULL, lastS, 1);
+        int upI = __shfl_up_sync(FULL, lastI, 1);
+        uint32_t upSb = __shfl_up_sync(FULL, lastSb, 1);
+        int j = (int)t - lane + 1;
+        if (j >= 1 && j <= (int)n && r0 < rows) {
+            const uint8_t yc = g.y[j - 1];
+            int aboveS = upS, aboveI = upI; // (i-1, j)
+            uint32_t aboveSb = upSb;
+            int diagS = upS_prev;           // (i-1, j-1)
+#pragma unroll
+            for (int q = 0; q < GREEDY_RMAX; q++) {
+                uint32_t i = r0 + (uint32_t)q;
+                if ((uint32_t)q < R && i < rows) {
+                    int S, I, D;
+                    uint32_t sb, ib, db;
+                    if (i == 0) { // boundary row: only deletions
+                        D = -1 - j;
+                        S = D;
+                        I = NEG;
+                        sb = TB_DEL;
+                        db = j == 1 ? TB_START : TB_DEL;
+                        ib = TB_START;
+                    } else {
+                        int m_score = diagS + (g.x[i - 1] == yc ? 1 : -1);
+                        int i_ext = aboveI - 1, i_open = aboveS - 2;
+                        if (i_ext > i_open) { I = i_ext; ib = TB_INS; } else { I = i_open; ib = aboveSb; }
+                        int d_ext = Dp[q] - 1, d_open = Sp[q] - 2;
+                        if (d_ext > d_open) { D = d_ext; db = TB_DEL; } else { D = d_open; db = sbp[q]; }
+                        S = m_score;
+                        sb = g.x[i - 1] == yc ? TB_MATCH : TB_SUBST;
+                        if (I > S) { S = I; sb = TB_INS; }
+                        if (D > S) { S = D; sb = TB_DEL; }
+                    }
+                    g.tb[(size_t)i * stride + (uint32_t)j] = (uint16_t)((sb << 8) | (db << 4) | ib);
+                    // next row in this lane sees this cell as "above", and the old Sp as diagonal
+                    diagS = Sp[q];
+                    aboveS = S;
+                    aboveI = I;
+                    aboveSb = sb;
+                    Sp[q] = S;
+                    Dp[q] = D;
+                    sbp[q] = sb;
+                    lastS = S;
+                    lastI = I;
+                    lastSb = sb;
+                }
+            }
+            upS_prev = upS;
+        }
+    }
+    __syncwarp();
+    // traceback (uniform)
+    uint32_t i = m, j = n, nops = 0;
+    uint32_t layer = (g.tb[(size_t)i * stride + j] >> 8) & 0xf;
+    while (layer != TB_START) {
+        uint32_t cell = g.tb[(size_t)i * stride + j];
+        uint32_t next;
+        uint8_t op;
+        if (layer == TB_INS) {
+            op = OP_INS;
+            next = cell & 0xf;
+            i -= 1;
+        } else if (layer == TB_DEL) {
+            op = OP_DEL;
+            next = (cell >> 4) & 0xf;
+            j -= 1;
+        } else {
+            op = layer == TB_MATCH ? OP_MATCH : OP_SUBST;
+            i -= 1;
+            j -= 1;
+            next = (g.tb[(size_t)i * stride + j] >> 8) & 0xf;
+        }
+        if (lane == 0) g.ops[nops] = op;
+        nops++;
+        layer = next;
+    }
+    __syncwarp();
+    return nops;
+}
+
+// Greedy::match_alignement (greedy.rs:56-89) on the reversed op list produced above
+__device__ __forceinline__ bool match_alignement(const GreedyScratch &g, uint32_t nops, uint32_t nbefore, int &off) {
+    int offset = 0;
+    // forward index f <-> reversed index nops-1-f
+    for (uint32_t w = nbefore; w + 1 < nops; w++) {
+        uint8_t op0 = g.ops[nops - 1 - w], op1 = g.ops[nops - 2 - w];
+        if (op0 == OP_DEL)
+            offset -= 1;
+        else if (op0 == OP_INS)
+            offset += 1;
+        if (op0 == OP_MATCH && op1 == OP_MATCH) {
+            int offset_corr = 0;
+            for (uint32_t e = 0; e < nops; e++) { // operations.iter().rev() == reversed list from index 0
+                uint8_t op = g.ops[e];
+                if (op == OP_DEL)
+                    offset_corr -= 1;
+                else if (op == OP_INS)
+                    offset_corr += 1;
+                else
+                    break;
+            }
+            off = offset - offset_corr;
+            return true;
+        }
+    }
+    return false;
+}
+
+__device__ __forceinline__ Corr greedy_correct_error(Rd &rd, uint64_t kmer, uint32_t i, uint32_t max_search,
+                                                     uint32_t nb_validate) {
+    Corr res;
+    res.some = false;
+    res.in_place = true;
+    res.n_emit = 0;
+    res.codes = 0;
+    res.offset = 0;
+    res.new_kmer = 0;
+
+    uint32_t alt;
+    if (!uniq(alt_mask(rd, kmer), alt)) return res; // greedy.rs:130-134
+    const uint8_t *sub = rd.in + i;
+    const uint32_t sublen = rd.len - i;
+    GreedyScratch g = greedy_scratch(rd.scratch, rd.k, (int)max_search);
+    const uint32_t stride = (uint32_t)greedy_dim(rd.k, (int)max_search);
+    const uint32_t nb = (uint32_t)rd.k - 1;
+
+    // before_seq = kmer2seq(kmer >> 2, k-1) (greedy.rs:139-141): upper-case bases of the k-1 prefix
+    if ((uint32_t)rd.lane < nb) {
+        uint8_t b = bit2nuc((uint32_t)((kmer >> (2 * (nb - (uint32_t)rd.lane))) & 3));
+        g.x[rd.lane] = b;
+        g.y[rd.lane] = b;
+    }
+    uint64_t x = replace_last(kmer, alt, rd.mask);
+    uint32_t npath = 0;
+    if (rd.lane == 0) {
+        g.y[nb + npath] = bit2nuc(alt);
+        g.viewed[0] = x;
+    }
+    npath++;
+    uint32_t nviewed = 1;
+    __syncwarp();
+
+    for (uint32_t s = 0; s < max_search; s++) {
+        uint32_t a;
+        if (uniq(succ_mask(rd, x), a)) { // follow_graph (greedy.rs:91-102)
+            x = push(x, a, rd.mask);
+            if (rd.lane == 0) g.y[nb + npath] = bit2nuc(a);
+            npath++;
+        }
+        // viewed_kmer.contains(&kmer) (greedy.rs:154-157)
+        bool seen = false;
+        for (uint32_t e = rd.lane; e < nviewed; e += 32) seen |= g.viewed[e] == x;
+        if (__any_sync(FULL, seen)) return res;
+        if (rd.lane == 0) g.viewed[nviewed] = x;
+        nviewed++;
+        if (sublen < s) return res; // greedy.rs:160-162
+        // x side: before || seq[..s]
+        if ((uint32_t)rd.lane < s) g.x[nb + rd.lane] = sub[rd.lane];
+        for (uint32_t e = 32 + rd.lane; e < s; e += 32) g.x[nb + e] = sub[e];
+        __syncwarp();
+        uint32_t nops = bio_global(rd, g, nb + s, nb + npath, stride);
+        int off;
+        if (match_alignement(g, nops, nb, off)) {
+            // check_next_kmers (greedy.rs:104-117)
+            bool ok = sublen - s >= nb_validate;
+            if (ok) {
+                bool bad = false;
+                for (uint32_t v0 = 0; v0 < nb_validate; v0 += 32) {
+                    uint32_t v = v0 + (uint32_t)rd.lane;
+                    if (v < nb_validate) {
+                        uint64_t km = push_seq(x, sub + s, v + 1, rd.mask);
+                        if (!solid(rd.bits, km, rd.k)) bad = true;
+                    }
+                }
+                ok = !__any_sync(FULL, bad);
+            }
+            if (ok) {
+                long long o = (long long)npath + (long long)off;
+                if (o < 0) o = 0; // unreachable in the reference (would wrap); see SURVEY appendix B.10
+                flush_copy(rd, i);
+                for (uint32_t e = rd.lane; e < npath; e += 32)
+                    if (rd.o + e < rd.cap) rd.out[rd.o + e] = g.y[nb + e];
+                res.some = true;
+                res.n_emit = npath;
+                res.new_kmer = x;
+                res.offset = (uint32_t)o;
+                return res;
+            }
+        }
+    }
+    return res;
+}
+
+// ------------------------------------------------------------------------------------------
+// Corrector::correct (src/correct/mod.rs:53-107) for one read
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ Corr correct_error(Rd &rd, const CorrectParams &p, uint64_t kmer, uint32_t i, uint32_t dr) {
+    switch (p.method) {
+    case BRGPU_ONE: return exist_correct_error<3>(rd, kmer, i, (uint32_t)p.confirm);
+    case BRGPU_TWO: return exist_correct_error<13>(rd, kmer, i, (uint32_t)p.confirm);
+    case BRGPU_GRAPH: return graph_correct_error(rd, kmer, i, dr);
+    case BRGPU_GREEDY: return greedy_correct_error(rd, kmer, i, (uint32_t)p.max_search, (uint32_t)p.confirm);
+    default: return gap_size_correct_error(rd, kmer, i, dr, (uint32_t)p.confirm);
+    }
+}
+
+__device__ __forceinline__ void correct_read(Rd &rd, const CorrectParams &p) {
+    const uint32_t k = (uint32_t)rd.k;
+    rd.o = 0;
+    rd.copy_from = 0;
+    if (rd.len < k) { // mod.rs:56-58
+        flush_copy(rd, rd.len);
+        return;
+    }
+    uint32_t i = k;
+    bool previous = (__ldg(rd.bm + ((k - 1) >> 5)) >> ((k - 1) & 31)) & 1u; // mod.rs:67
+    uint32_t d = 0;    // pushes still to come whose k-mer contains corrected bases
+    uint64_t kmer = 0; // rolling k-mer; only maintained while d > 0 or at an event
+
+    while (i < rd.len) {
+        if (d == 0) {
+            uint32_t j = find_transition(rd, i, previous);
+            if (j >= rd.len) break;
+            i = j;
+            kmer = load_kmer_at(rd, i);
+        } else {
+            uint32_t n = rd.len - i;
+            if (n > d) n = d;
+            if (n > 32) n = 32;
+            uint64_t km = push_window(rd, kmer, rd.in + i, n);
+            bool s = (uint32_t)rd.lane < n && solid(rd.bits, km, rd.k);
+            uint32_t gm = __ballot_sync(FULL, s);
+            uint32_t vm = n == 32 ? 0xffffffffu : ((1u << n) - 1u);
+            uint32_t trig = ~gm & ((gm << 1) | (previous ? 1u : 0u)) & vm; // mod.rs:73
+            if (trig == 0) {
+                kmer = shfl64(km, (int)n - 1);
+                previous = (gm >> (n - 1)) & 1u; // mod.rs:99
+                i += n;
+                d -= n;
+                continue;
+            }
+            uint32_t l = (uint32_t)(__ffs(trig) - 1);
+            kmer = shfl64(km, (int)l);
+            i += l;
+            d -= l + 1;
+        }
+        // solid -> weak transition at input position i; kmer ends with in[i]
+        Corr c = correct_error(rd, p, kmer, i, d);
+        if (!c.some) { // mod.rs:90-96
+            previous = false;
+            i += 1;
+        } else { // mod.rs:74-89
+            flush_copy(rd, i);
+            if (c.in_place) {
+                rd.o += c.n_emit;
+                kmer = c.new_kmer;
+            } else {
+                kmer >>= 2;
+                for (int e = (int)c.n_emit - 1; e >= 0; e--) {
+                    uint32_t code = (c.codes >> (2 * e)) & 3u;
+                    kmer = push(kmer, code, rd.mask);
+                    emit_byte(rd, bit2nuc(code));
+                }
+            }
+            previous = true;
+            i += c.offset;
+            rd.copy_from = i;
+            d = k - 1;
+        }
+    }
+    flush_copy(rd, rd.len);
+}
+
+constexpr int SCAN_WARPS_PER_BLOCK = 4;
+
+__global__ void __launch_bounds__(SCAN_WARPS_PER_BLOCK * 32)
+    scan_kernel(const uint8_t *__restrict__ in, const uint32_t *__restrict__ len_in, uint8_t *__restrict__ out,
+                uint32_t *__restrict__ len_out, const uint64_t *__restrict__ slot_off,
+                const uint32_t *__restrict__ bitmap, const uint32_t *__restrict__ order, uint32_t n_reads,
+                uint32_t *__restrict__ flags, const uint8_t *__restrict__ bits, CorrectParams p, uint8_t *scratch,
+                size_t scratch_per_warp) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    Rd rd;
+    rd.bits = bits;
+    rd.k = p.k;
+    rd.mask = kmask(p.k);
+    rd.lane = lane;
+    rd.scratch = scratch ? scratch + (size_t)warp * scratch_per_warp : nullptr;
+    for (;;) {
+        uint32_t qi = 0;
+        if (lane == 0) qi = atomicAdd(flags + 0, 1u);
+        qi = __shfl_sync(FULL, qi, 0);
+        if (qi >= n_reads) break;
+        const uint32_t r = __ldg(order + qi);
+        const uint64_t base = __ldg(slot_off + r);
+        rd.in = in + base;
+        rd.out = out + base;
+        rd.cap = (uint32_t)(__ldg(slot_off + r + 1) - base);
+        rd.len = __ldg(len_in + r);
+        rd.bm = bitmap + (base >> 5);
+        correct_read(rd, p);
+        __syncwarp();
+        if (lane == 0) {
+            len_out[r] = rd.o;
+            if (rd.o > rd.cap) atomicOr(flags + 1, 1u);
+        }
+    }
+}
+
+int scan_grid_warps(brgpu_ctx *ctx) { return ctx->sm_count * 8 * SCAN_WARPS_PER_BLOCK; }
+
+void launch_scan(brgpu_ctx *ctx, const Layout &L, const uint8_t *d_in, const uint32_t *d_len_in, uint8_t *d_out,
+                 uint32_t *d_len_out, const uint32_t *d_bitmap, const uint8_t *d_bits, const CorrectParams &p,
+                 uint8_t *d_scratch, size_t scratch_per_warp, int n_warps_total, double n_bases_hint) {
+    if (!L.n) return;
+    cudaMemsetAsync(ctx->d_flags, 0, sizeof(uint32_t), ctx->stream); // work-queue cursor
+    static const char *names[5] = {"scan_one", "scan_two", "scan_graph", "scan_greedy", "scan_gap_size"};
+    ProfScope ps(ctx, names[p.method], n_bases_hint * 2.0);
+    uint64_t need_warps = L.n;
+    uint64_t warps = need_warps < (uint64_t)n_warps_total ? need_warps : (uint64_t)n_warps_total;
+    unsigned blocks = (unsigned)((warps + SCAN_WARPS_PER_BLOCK - 1) / SCAN_WARPS_PER_BLOCK);
+    scan_kernel<<<blocks, SCAN_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(d_in, d_len_in, d_out, d_len_out, L.d_slot_off,
+                                                                       d_bitmap, L.d_order, (uint32_t)L.n,
+                                                                       ctx->d_flags, d_bits, p, d_scratch,
+                                                                       scratch_per_warp);
+}
+
+} // namespace brgpu

@@ -1,0 +1,141 @@
+// internal.h — host-side objects behind the opaque handles of include/brgpu.h and the
+// kernel launchers the API layer calls.  Not part of the ABI.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <memory>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/brgpu.h"
+
+namespace brgpu {
+
+struct ProfEntry {
+    std::string name;
+    double ms = 0.0;
+    uint64_t launches = 0;
+    double bytes = 0.0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+};
+
+} // namespace brgpu
+
+struct brgpu_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    bool profiling = false;
+    std::vector<brgpu::ProfEntry> prof;
+    std::vector<cudaEvent_t> event_pool;
+    uint64_t launches = 0;
+    // small device scratch reused by every call
+    uint32_t *d_flags = nullptr; // [0] work-queue cursor, [1] overflow flag, [2..] spare
+    uint64_t *d_hist = nullptr;  // 256 bins
+    uint64_t *h_pinned = nullptr; // 512 x u64 pinned staging for small readbacks
+};
+
+namespace brgpu {
+
+// Where every read lives in the slot layout: read r owns bytes [slot_off[r], slot_off[r+1]),
+// slot_off[r] % 32 == 0, capacity = len + slack so that a corrected read can grow in place.
+struct Layout {
+    brgpu_ctx *ctx = nullptr;
+    uint64_t n = 0;
+    uint64_t total_slots = 0;        // bytes, multiple of 32
+    uint64_t *d_slot_off = nullptr;  // n + 1
+    uint32_t *d_word2read = nullptr; // total_slots / 32
+    uint32_t *d_order = nullptr;     // read ids, longest first (work queue order)
+    ~Layout();
+};
+
+} // namespace brgpu
+
+struct brgpu_reads {
+    brgpu_ctx *ctx = nullptr;
+    std::shared_ptr<brgpu::Layout> layout;
+    uint8_t *d_seq = nullptr;  // total_slots bytes
+    uint32_t *d_len = nullptr; // n
+    std::vector<uint32_t> h_len; // host copy of the lengths (uploaded reads only)
+    uint64_t sum_len = 0;        // sum of lengths at upload (bookkeeping hint afterwards)
+};
+
+struct brgpu_counts {
+    brgpu_ctx *ctx = nullptr;
+    int k = 0;
+    uint64_t n = 0; // 2^(2k-1)
+    uint8_t *d_counts = nullptr;
+};
+
+struct brgpu_set {
+    brgpu_ctx *ctx = nullptr;
+    int k = 0;
+    int abundance = -1;
+    uint64_t n_bytes = 0;
+    uint8_t *d_bits = nullptr;
+    uint64_t hist[256] = {0};
+};
+
+namespace brgpu {
+
+// RAII-less helper: record an error string and return a status
+int fail(brgpu_ctx *ctx, int code, const char *what, cudaError_t e = cudaSuccess);
+
+// profiling hooks around a launch
+void prof_begin(brgpu_ctx *ctx, const char *name, double algo_bytes, bool is_kernel = true);
+void prof_end(brgpu_ctx *ctx);
+
+struct ProfScope {
+    brgpu_ctx *c;
+    ProfScope(brgpu_ctx *ctx, const char *name, double bytes, bool is_kernel = true) : c(ctx) {
+        prof_begin(c, name, bytes, is_kernel);
+    }
+    ~ProfScope() { prof_end(c); }
+};
+
+// ---- layout / relayout kernels (set_kernels.cu) ----
+void launch_fill_word2read(brgpu_ctx *ctx, const Layout &L);
+void launch_scatter_to_slots(brgpu_ctx *ctx, const Layout &L, const uint8_t *d_tight, const uint64_t *d_tight_off,
+                             uint8_t *d_slots);
+void launch_gather_from_slots(brgpu_ctx *ctx, const Layout &L, const uint8_t *d_slots, const uint32_t *d_len,
+                              const uint64_t *d_tight_off, uint8_t *d_tight, bool reverse);
+void launch_reverse_slots(brgpu_ctx *ctx, const Layout &L, const uint8_t *d_in, const uint32_t *d_len, uint8_t *d_out);
+void launch_exclusive_scan_u32(brgpu_ctx *ctx, const uint32_t *d_in, uint64_t n, uint64_t *d_out /* n+1 */,
+                               uint64_t *d_tmp /* >= n/4096 + 2 */);
+
+// ---- part 1 kernels (set_kernels.cu) ----
+void launch_count(brgpu_ctx *ctx, const Layout &L, const uint8_t *d_seq, const uint32_t *d_len, int k,
+                  uint8_t *d_counts, double n_bases_hint);
+// histogram of counts[begin,end) into d_hist (256 x u64, accumulated) and, if d_bits != nullptr,
+// bit i = counts[i] > abundance for the same range.  begin/end multiples of 1024.
+void launch_spectrum_threshold(brgpu_ctx *ctx, const uint8_t *d_counts, uint64_t begin, uint64_t end, uint64_t *d_hist,
+                               uint8_t *d_bits, int abundance);
+void launch_get_batch(brgpu_ctx *ctx, const uint8_t *d_bits, int k, const uint64_t *d_kmers, uint64_t n,
+                      uint8_t *d_out);
+void launch_insert_batch(brgpu_ctx *ctx, uint8_t *d_bits, int k, const uint64_t *d_kmers, uint64_t n);
+void launch_merge_slice(brgpu_ctx *ctx, uint8_t *d_counts, void *const *peers, int n_peers, uint64_t begin,
+                        uint64_t end);
+
+// ---- part 2 kernels (correct_kernels.cu) ----
+struct CorrectParams {
+    int k;
+    int method;
+    int confirm;
+    int max_search;
+};
+// solidity bit of the k-mer ending at every slot position of every read (0 where undefined)
+void launch_solid_bitmap(brgpu_ctx *ctx, const Layout &L, const uint8_t *d_seq, const uint32_t *d_len,
+                         const uint8_t *d_bits, int k, uint32_t *d_bitmap, double n_bases_hint);
+// Corrector::correct over all reads (one warp per read, longest first); writes min(len,cap)
+// bytes per read, the true output length to d_len_out and sets d_flags[1] on overflow.
+void launch_scan(brgpu_ctx *ctx, const Layout &L, const uint8_t *d_in, const uint32_t *d_len_in, uint8_t *d_out,
+                 uint32_t *d_len_out, const uint32_t *d_bitmap, const uint8_t *d_bits, const CorrectParams &p,
+                 uint8_t *d_scratch, size_t scratch_per_warp, int n_warps_total, double n_bases_hint);
+int scan_grid_warps(brgpu_ctx *ctx);
+size_t scan_scratch_per_warp(const CorrectParams &p);
+
+} // namespace brgpu

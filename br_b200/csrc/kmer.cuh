@@ -1,0 +1,106 @@
+// kmer.cuh — 2-bit k-mer arithmetic in registers (device side).
+//
+// Semantics follow cocktail::kmer as br uses it (call sites
+// src/correct/mod.rs:61,71,110-112 and pcon's Solid::get behind src/set/pcon.rs:189):
+//   nuc2bit(b) = (b >> 1) & 3            A=0 C=1 T=2 G=3 (any byte is a nucleotide)
+//   canonical  = whichever of {kmer, revcomp} has even popcount (k odd)
+//   table index = canonical >> 1
+//   bitfield is LSB-first: bit i lives in byte i>>3 at position i&7
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace brgpu {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+__host__ __device__ __forceinline__ uint64_t kmask(int k) { return (1ULL << (2 * k)) - 1ULL; }
+
+__host__ __device__ __forceinline__ uint32_t nuc2bit(uint8_t b) { return (b >> 1) & 3u; }
+
+// 0->A 1->C 2->T 3->G, packed in one constant: 'A'|'C'<<8|'T'<<16|'G'<<24
+__host__ __device__ __forceinline__ uint8_t bit2nuc(uint32_t c) {
+    return (uint8_t)((0x47544341u >> (8 * (c & 3u))) & 0xffu);
+}
+
+// add_nuc_to_end (src/correct/mod.rs:110-112)
+__host__ __device__ __forceinline__ uint64_t push(uint64_t kmer, uint32_t nuc, uint64_t mask) {
+    return ((kmer << 2) & mask) ^ (uint64_t)nuc;
+}
+
+// replace the last base: add_nuc_to_end(kmer >> 2, a, k)
+__host__ __device__ __forceinline__ uint64_t replace_last(uint64_t kmer, uint32_t a, uint64_t mask) {
+    return (((kmer >> 2) << 2) & mask) ^ (uint64_t)a;
+}
+
+__device__ __forceinline__ uint64_t revcomp(uint64_t kmer, int k) {
+    // reverse all 64 bits, swap the two bits inside every group back, complement (xor 10 per
+    // group), then drop the 64-2k low garbage bits.
+    uint64_t r = __brevll(kmer);
+    r = ((r >> 1) & 0x5555555555555555ULL) | ((r & 0x5555555555555555ULL) << 1);
+    r ^= 0xAAAAAAAAAAAAAAAAULL;
+    return r >> (64 - 2 * k);
+}
+
+__device__ __forceinline__ uint64_t canonical_index(uint64_t kmer, int k) {
+    uint64_t c = (__popcll(kmer) & 1) ? revcomp(kmer, k) : kmer;
+    return c >> 1;
+}
+
+// KmerSet::get — one random byte (32 B sector) of the HBM-resident bitfield.
+__device__ __forceinline__ bool solid(const uint8_t *__restrict__ bits, uint64_t kmer, int k) {
+    uint64_t idx = canonical_index(kmer, k);
+    return (__ldg(bits + (idx >> 3)) >> (idx & 7)) & 1;
+}
+
+// Pack the 2-bit codes of 16 ASCII bases held in a uint4 (memory order) into 32 bits, first
+// base in the most significant pair.
+__device__ __forceinline__ uint32_t pack4(uint32_t w) {
+    // w holds 4 bytes b0 (lowest address, bits 0-7) .. b3.  codes = (b>>1)&3
+    uint32_t x = (w >> 1) & 0x03030303u;
+    // want c0<<6 | c1<<4 | c2<<2 | c3
+    return ((x & 0x3u) << 6) | (((x >> 8) & 0x3u) << 4) | (((x >> 16) & 0x3u) << 2) | ((x >> 24) & 0x3u);
+}
+
+__device__ __forceinline__ uint32_t pack16(uint4 v) {
+    return (pack4(v.x) << 24) | (pack4(v.y) << 16) | (pack4(v.z) << 8) | pack4(v.w);
+}
+
+// ------------------------------------------------------------------------------------------
+// The 32-position window every streaming kernel uses: slot word w of a read holds positions
+// p0..p0+31; `cur` packs their 2-bit codes (first base in the top pair), `prev` the 32 before.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_window(const uint8_t *__restrict__ seq, uint64_t slot_byte, uint32_t p0,
+                                            uint64_t &prev, uint64_t &cur) {
+    const uint4 *q = reinterpret_cast<const uint4 *>(seq + slot_byte);
+    uint4 a = __ldg(q), b = __ldg(q + 1);
+    cur = ((uint64_t)pack16(a) << 32) | (uint64_t)pack16(b);
+    prev = 0;
+    if (p0 >= 32) {
+        uint4 c = __ldg(q - 2), d = __ldg(q - 1);
+        prev = ((uint64_t)pack16(c) << 32) | (uint64_t)pack16(d);
+    }
+}
+
+// k-mer ending at window position t (0..31)
+__device__ __forceinline__ uint64_t window_kmer(uint64_t prev, uint64_t cur, int t, uint64_t mask) {
+    int s = 2 * (31 - t);
+    uint64_t v = cur >> s;
+    if (s) v |= prev << (64 - s);
+    return v & mask;
+}
+
+// 64-bit OR-reduction across the warp
+__device__ __forceinline__ uint64_t warp_or64(uint64_t v) {
+    uint32_t lo = __reduce_or_sync(FULL, (uint32_t)v);
+    uint32_t hi = __reduce_or_sync(FULL, (uint32_t)(v >> 32));
+    return ((uint64_t)hi << 32) | lo;
+}
+
+__device__ __forceinline__ uint64_t shfl64(uint64_t v, int src) {
+    uint32_t lo = __shfl_sync(FULL, (uint32_t)v, src);
+    uint32_t hi = __shfl_sync(FULL, (uint32_t)(v >> 32), src);
+    return ((uint64_t)hi << 32) | lo;
+}
+
+} // namespace brgpu

@@ -1,0 +1,456 @@
+// set_kernels.cu — part 1 of br's hot path on sm_100a: k-mer counting into an HBM-resident
+// table of saturating u8 counters, the 256-bin spectrum, the solidity threshold into the dense
+// canonical bitfield, batched KmerSet::get — plus the slot-layout plumbing (scatter/gather/
+// reverse/scan) the correction pass shares.
+//
+// None of this is GEMM-shaped: it is integer hashing and random 32-byte-sector access, so the
+// roofline is HBM and the levers are coalesced vector loads for the streams,
+// many independent random accesses in flight per thread, and grids sized from the SM count.
+//
+// Reference semantics replaced (Rust, not CUDA — there is no reference kernel):
+//   pcon Counter::<u8>::count_fasta      call site src/main.rs:73-74
+//   pcon Spectrum::from_count            call site src/main.rs:93
+//   pcon Solid::from_count               call site src/main.rs:112-114
+//   pcon Solid::get via set::Pcon::get   src/set/pcon.rs:188-191
+#include "internal.h"
+#include "kmer.cuh"
+
+namespace brgpu {
+
+static inline int grid_for(brgpu_ctx *ctx, uint64_t work_items, int block, int max_blocks_per_sm) {
+    uint64_t need = (work_items + (uint64_t)block - 1) / (uint64_t)block;
+    uint64_t cap = (uint64_t)ctx->sm_count * (uint64_t)max_blocks_per_sm;
+    if (need < 1) need = 1;
+    return (int)(need < cap ? need : cap);
+}
+
+// ------------------------------------------------------------------------------------------
+// layout plumbing
+// ------------------------------------------------------------------------------------------
+__global__ void fill_word2read_kernel(const uint64_t *__restrict__ slot_off, uint64_t n_reads, uint64_t n_words,
+                                      uint32_t *__restrict__ word2read) {
+    for (uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < n_words;
+         w += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t pos = w << 5;
+        uint64_t lo = 0, hi = n_reads; // find r with slot_off[r] <= pos < slot_off[r+1]
+        while (hi - lo > 1) {
+            uint64_t mid = (lo + hi) >> 1;
+            if (__ldg(slot_off + mid) <= pos)
+                lo = mid;
+            else
+                hi = mid;
+        }
+        word2read[w] = (uint32_t)lo;
+    }
+}
+
+void launch_fill_word2read(brgpu_ctx *ctx, const Layout &L) {
+    uint64_t n_words = L.total_slots >> 5;
+    if (!n_words) return;
+    ProfScope ps(ctx, "fill_word2read", (double)n_words * 4.0);
+    fill_word2read_kernel<<<grid_for(ctx, n_words, 256, 8), 256, 0, ctx->stream>>>(L.d_slot_off, L.n, n_words,
+                                                                                   L.d_word2read);
+}
+
+// tight (concatenated) host layout -> slot layout; slack bytes are zeroed
+__global__ void scatter_to_slots_kernel(const uint8_t *__restrict__ tight, const uint64_t *__restrict__ tight_off,
+                                        const uint64_t *__restrict__ slot_off, const uint32_t *__restrict__ word2read,
+                                        uint64_t n_quads, uint32_t *__restrict__ slots) {
+    for (uint64_t g = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; g < n_quads;
+         g += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t s = g << 2;
+        uint32_t r = __ldg(word2read + (s >> 5));
+        uint64_t p = s - __ldg(slot_off + r);
+        uint64_t t0 = __ldg(tight_off + r);
+        uint64_t len = __ldg(tight_off + r + 1) - t0;
+        uint32_t v = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (p + j < len) v |= (uint32_t)__ldg(tight + t0 + p + j) << (8 * j);
+        slots[g] = v;
+    }
+}
+
+void launch_scatter_to_slots(brgpu_ctx *ctx, const Layout &L, const uint8_t *d_tight, const uint64_t *d_tight_off,
+                             uint8_t *d_slots) {
+    uint64_t n_quads = L.total_slots >> 2;
+    if (!n_quads) return;
+    ProfScope ps(ctx, "scatter_to_slots", (double)L.total_slots * 2.0);
+    scatter_to_slots_kernel<<<grid_for(ctx, n_quads, 256, 8), 256, 0, ctx->stream>>>(
+        d_tight, d_tight_off, L.d_slot_off, L.d_word2read, n_quads, (uint32_t *)d_slots);
+}
+
+// slot layout -> tight layout (optionally byte-reversing each read)
+__global__ void gather_from_slots_kernel(const uint32_t *__restrict__ slots, const uint32_t *__restrict__ len,
+                                         const uint64_t *__restrict__ slot_off, const uint32_t *__restrict__ word2read,
+                                         const uint64_t *__restrict__ tight_off, uint64_t n_quads,
+                                         uint8_t *__restrict__ tight, int reverse) {
+    for (uint64_t g = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; g < n_quads;
+         g += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t s = g << 2;
+        uint32_t r = __ldg(word2read + (s >> 5));
+        uint64_t p = s - __ldg(slot_off + r);
+        uint64_t L = __ldg(len + r);
+        if (p >= L) continue;
+        uint64_t t0 = __ldg(tight_off + r);
+        uint32_t v = __ldg(slots + g);
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (p + j < L) tight[t0 + (reverse ? (L - 1 - (p + j)) : (p + j))] = (uint8_t)(v >> (8 * j));
+    }
+}
+
+void launch_gather_from_slots(brgpu_ctx *ctx, const Layout &L, const uint8_t *d_slots, const uint32_t *d_len,
+                              const uint64_t *d_tight_off, uint8_t *d_tight, bool reverse) {
+    uint64_t n_quads = L.total_slots >> 2;
+    if (!n_quads) return;
+    ProfScope ps(ctx, "gather_from_slots", (double)L.total_slots * 2.0);
+    gather_from_slots_kernel<<<grid_for(ctx, n_quads, 256, 8), 256, 0, ctx->stream>>>(
+        (const uint32_t *)d_slots, d_len, L.d_slot_off, L.d_word2read, d_tight_off, n_quads, d_tight, reverse ? 1 : 0);
+}
+
+// out[p] = in[len-1-p] inside every slot (the reversed pass of src/lib.rs:49,111 is a plain
+// byte reversal, not a reverse complement)
+__global__ void reverse_slots_kernel(const uint8_t *__restrict__ in, const uint32_t *__restrict__ len,
+                                     const uint64_t *__restrict__ slot_off, const uint32_t *__restrict__ word2read,
+                                     uint64_t n_quads, uint32_t *__restrict__ out) {
+    for (uint64_t g = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; g < n_quads;
+         g += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t s = g << 2;
+        uint32_t r = __ldg(word2read + (s >> 5));
+        uint64_t base = __ldg(slot_off + r);
+        uint64_t p = s - base;
+        uint64_t L = __ldg(len + r);
+        uint32_t v = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (p + j < L) v |= (uint32_t)__ldg(in + base + (L - 1 - (p + j))) << (8 * j);
+        out[g] = v;
+    }
+}
+
+void launch_reverse_slots(brgpu_ctx *ctx, const Layout &L, const uint8_t *d_in, const uint32_t *d_len, uint8_t *d_out) {
+    uint64_t n_quads = L.total_slots >> 2;
+    if (!n_quads) return;
+    ProfScope ps(ctx, "reverse_slots", (double)L.total_slots * 2.0);
+    reverse_slots_kernel<<<grid_for(ctx, n_quads, 256, 8), 256, 0, ctx->stream>>>(d_in, d_len, L.d_slot_off,
+                                                                                  L.d_word2read, n_quads,
+                                                                                  (uint32_t *)d_out);
+}
+
+// ------------------------------------------------------------------------------------------
+// exclusive scan of u32 lengths into u64 offsets (n + 1 outputs).  Three small kernels:
+// per-tile sums, one-block scan of the tile sums, per-tile scan with the tile's base added.
+// ------------------------------------------------------------------------------------------
+constexpr int SCAN_TILE = 4096; // elements per block
+constexpr int SCAN_THREADS = 256;
+
+__device__ __forceinline__ uint64_t block_exclusive_scan(uint64_t v, uint64_t *total, uint64_t *smem /* 32 */) {
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint64_t x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint64_t y = __shfl_up_sync(FULL, x, d);
+        if (lane >= d) x += y;
+    }
+    if (lane == 31) smem[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        uint64_t s = lane < (blockDim.x >> 5) ? smem[lane] : 0;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint64_t y = __shfl_up_sync(FULL, s, d);
+            if (lane >= d) s += y;
+        }
+        smem[lane] = s; // inclusive over warps
+    }
+    __syncthreads();
+    uint64_t warp_base = wid ? smem[wid - 1] : 0;
+    *total = smem[(blockDim.x >> 5) - 1];
+    uint64_t res = warp_base + x - v;
+    __syncthreads();
+    return res;
+}
+
+__global__ void scan_tile_sums_kernel(const uint32_t *__restrict__ in, uint64_t n, uint64_t *__restrict__ tile_sums) {
+    __shared__ uint64_t sm[32];
+    uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE;
+    uint64_t acc = 0;
+    for (int j = threadIdx.x; j < SCAN_TILE; j += SCAN_THREADS)
+        if (base + j < n) acc += in[base + j];
+    uint64_t total;
+    block_exclusive_scan(acc, &total, sm);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+__global__ void scan_tile_bases_kernel(uint64_t *tile_sums, uint64_t n_tiles) {
+    // one block; turns tile sums into exclusive bases in place, total in tile_sums[n_tiles]
+    __shared__ uint64_t sm[32];
+    uint64_t carry = 0;
+    for (uint64_t b = 0; b < n_tiles; b += blockDim.x) {
+        uint64_t idx = b + threadIdx.x;
+        uint64_t v = idx < n_tiles ? tile_sums[idx] : 0;
+        uint64_t total;
+        uint64_t ex = block_exclusive_scan(v, &total, sm);
+        if (idx < n_tiles) tile_sums[idx] = carry + ex;
+        carry += total;
+    }
+    if (threadIdx.x == 0) tile_sums[n_tiles] = carry;
+}
+
+__global__ void scan_apply_kernel(const uint32_t *__restrict__ in, uint64_t n, const uint64_t *__restrict__ tile_bases,
+                                  uint64_t n_tiles, uint64_t *__restrict__ out) {
+    __shared__ uint64_t sm[32];
+    uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE;
+    uint64_t carry = tile_bases[blockIdx.x];
+    constexpr int PER = SCAN_TILE / SCAN_THREADS; // 16 consecutive elements per thread
+    uint64_t first = base + (uint64_t)threadIdx.x * PER;
+    uint32_t v[PER];
+    uint64_t acc = 0;
+#pragma unroll
+    for (int j = 0; j < PER; j++) {
+        v[j] = (first + j < n) ? in[first + j] : 0;
+        acc += v[j];
+    }
+    uint64_t total;
+    uint64_t ex = block_exclusive_scan(acc, &total, sm) + carry;
+#pragma unroll
+    for (int j = 0; j < PER; j++) {
+        if (first + j < n) out[first + j] = ex;
+        ex += v[j];
+    }
+    if (blockIdx.x == n_tiles - 1 && threadIdx.x == 0) out[n] = tile_bases[n_tiles];
+}
+
+void launch_exclusive_scan_u32(brgpu_ctx *ctx, const uint32_t *d_in, uint64_t n, uint64_t *d_out, uint64_t *d_tmp) {
+    if (n == 0) {
+        cudaMemsetAsync(d_out, 0, sizeof(uint64_t), ctx->stream);
+        return;
+    }
+    uint64_t n_tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    ProfScope ps(ctx, "exclusive_scan", (double)n * 12.0);
+    scan_tile_sums_kernel<<<(unsigned)n_tiles, SCAN_THREADS, 0, ctx->stream>>>(d_in, n, d_tmp);
+    scan_tile_bases_kernel<<<1, 1024, 0, ctx->stream>>>(d_tmp, n_tiles);
+    scan_apply_kernel<<<(unsigned)n_tiles, SCAN_THREADS, 0, ctx->stream>>>(d_in, n, d_tmp, n_tiles, d_out);
+    ctx->launches += 2;
+}
+
+// ------------------------------------------------------------------------------------------
+// Counting: one thread per 32 read positions, up to 32 independent random read-modify-writes
+// in flight per thread.  CUDA has no 8-bit atomics, so the saturating increment is a CAS on
+// the aligned 32-bit word that holds the counter; the first attempt guesses the word is still
+// zero, which is true for the large majority of updates at k = 17 (2^33 counters).
+// min(255, n) is order independent, so any exact scheme gives the table the CPU would.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void sat_inc_fixup(uint32_t *w, uint32_t sh, uint32_t old) {
+    const uint32_t one = 1u << sh;
+    while (((old >> sh) & 0xffu) != 0xffu) {
+        uint32_t assumed = old;
+        old = atomicCAS(w, assumed, assumed + one);
+        if (old == assumed) break;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+    count_kernel(const uint8_t *__restrict__ seq, const uint32_t *__restrict__ len,
+                 const uint64_t *__restrict__ slot_off, const uint32_t *__restrict__ word2read, uint64_t n_words, int k,
+                 uint8_t *__restrict__ counts) {
+    const uint64_t mask = kmask(k);
+    for (uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < n_words;
+         w += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t r = __ldg(word2read + w);
+        uint64_t sb = w << 5;
+        uint32_t p0 = (uint32_t)(sb - __ldg(slot_off + r));
+        uint32_t L = __ldg(len + r);
+        if (p0 >= L || L < (uint32_t)k) continue; // slack, or read shorter than k (src/set/pcon.rs:58)
+        uint64_t prev, cur;
+        load_window(seq, sb, p0, prev, cur);
+        int t_lo = p0 >= (uint32_t)(k - 1) ? 0 : (k - 1 - (int)p0);
+        int t_hi = (L - p0) < 32u ? (int)(L - p0) : 32;
+#pragma unroll
+        for (int g = 0; g < 32; g += 8) {
+            uint32_t *wp[8];
+            uint32_t sh[8], old[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                int t = g + j;
+                old[j] = 0;
+                wp[j] = nullptr;
+                sh[j] = 0;
+                if (t >= t_lo && t < t_hi) {
+                    uint64_t idx = canonical_index(window_kmer(prev, cur, t, mask), k);
+                    wp[j] = reinterpret_cast<uint32_t *>(counts + (idx & ~3ULL));
+                    sh[j] = (uint32_t)(idx & 3) * 8u;
+                    old[j] = atomicCAS(wp[j], 0u, 1u << sh[j]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                if (old[j] != 0) sat_inc_fixup(wp[j], sh[j], old[j]);
+        }
+    }
+}
+
+void launch_count(brgpu_ctx *ctx, const Layout &L, const uint8_t *d_seq, const uint32_t *d_len, int k,
+                  uint8_t *d_counts, double n_bases_hint) {
+    uint64_t n_words = L.total_slots >> 5;
+    if (!n_words) return;
+    // algorithmic bytes: 0.25 B/base stream + one 32 B sector read + one 32 B sector
+    // write-back per k-mer.  n_bases_hint ~ number of k-mers (sum len - n(k-1), clamped).
+    ProfScope ps(ctx, "count_kmers", n_bases_hint * 64.25);
+    count_kernel<<<grid_for(ctx, n_words, 256, 8), 256, 0, ctx->stream>>>(d_seq, d_len, L.d_slot_off, L.d_word2read,
+                                                                          n_words, k, d_counts);
+}
+
+// ------------------------------------------------------------------------------------------
+// Spectrum + threshold: one streaming pass over the count table.  Each thread takes 16
+// counters (one 16 B load, lanes contiguous), tallies values 0..3 with byte-SIMD compares in
+// registers (they hold almost all the mass), sends the rest to a shared-memory histogram, and
+// writes 16 bits of the LSB-first bitfield.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t msb_nibble(uint32_t cmp) {
+    // cmp has 0xff/0x00 per byte; gather one bit per byte: byte j -> bit j
+    uint32_t y = (cmp & 0x80808080u) >> 7;
+    return (y | (y >> 7) | (y >> 14) | (y >> 21)) & 0xfu;
+}
+
+__global__ void __launch_bounds__(256)
+    spectrum_threshold_kernel(const uint4 *__restrict__ counts16, uint64_t n16, unsigned long long *__restrict__ hist,
+                              uint16_t *__restrict__ bits16, int abundance) {
+    __shared__ unsigned int sh_hist[256];
+    __shared__ unsigned long long sh_low[4];
+    sh_hist[threadIdx.x] = 0;
+    if (threadIdx.x < 4) sh_low[threadIdx.x] = 0;
+    __syncthreads();
+
+    const uint32_t thr = (uint32_t)abundance * 0x01010101u;
+    uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+    for (uint64_t g = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; g < n16;
+         g += (uint64_t)gridDim.x * blockDim.x) {
+        uint4 v = __ldcs(counts16 + g);
+        uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        uint32_t out = 0;
+        if ((v.x | v.y | v.z | v.w) == 0) {
+            c0 += 16;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                uint32_t z0 = __vcmpeq4(w[j], 0u), z1 = __vcmpeq4(w[j], 0x01010101u);
+                uint32_t z2 = __vcmpeq4(w[j], 0x02020202u), z3 = __vcmpeq4(w[j], 0x03030303u);
+                c0 += __popc(z0) >> 3;
+                c1 += __popc(z1) >> 3;
+                c2 += __popc(z2) >> 3;
+                c3 += __popc(z3) >> 3;
+                uint32_t rest = ~(z0 | z1 | z2 | z3);
+                while (rest) {
+                    int b = (__ffs(rest) - 1) >> 3;
+                    atomicAdd(&sh_hist[(w[j] >> (8 * b)) & 0xffu], 1u);
+                    rest &= ~(0xffu << (8 * b));
+                }
+                if (bits16) out |= msb_nibble(__vcmpgtu4(w[j], thr)) << (4 * j);
+            }
+        }
+        if (bits16) bits16[g] = (uint16_t)out;
+    }
+    c0 = __reduce_add_sync(FULL, c0);
+    c1 = __reduce_add_sync(FULL, c1);
+    c2 = __reduce_add_sync(FULL, c2);
+    c3 = __reduce_add_sync(FULL, c3);
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&sh_low[0], (unsigned long long)c0);
+        atomicAdd(&sh_low[1], (unsigned long long)c1);
+        atomicAdd(&sh_low[2], (unsigned long long)c2);
+        atomicAdd(&sh_low[3], (unsigned long long)c3);
+    }
+    __syncthreads();
+    unsigned long long mine = sh_hist[threadIdx.x];
+    if (threadIdx.x < 4) mine += sh_low[threadIdx.x];
+    if (mine) atomicAdd(hist + threadIdx.x, mine);
+}
+
+void launch_spectrum_threshold(brgpu_ctx *ctx, const uint8_t *d_counts, uint64_t begin, uint64_t end, uint64_t *d_hist,
+                               uint8_t *d_bits, int abundance) {
+    if (end <= begin) return;
+    uint64_t n16 = (end - begin) >> 4;
+    double bytes = (double)(end - begin) * (d_bits ? 1.125 : 1.0);
+    ProfScope ps(ctx, d_bits ? "spectrum_threshold" : "spectrum", bytes);
+    // per-thread u32 tallies stay far below 2^32: >= sm_count*8*256 threads share <= 2^37 counters
+    spectrum_threshold_kernel<<<grid_for(ctx, n16, 256, 8), 256, 0, ctx->stream>>>(
+        reinterpret_cast<const uint4 *>(d_counts + begin), n16, reinterpret_cast<unsigned long long *>(d_hist),
+        d_bits ? reinterpret_cast<uint16_t *>(d_bits + (begin >> 3)) : nullptr, abundance);
+}
+
+// tables smaller than 16 counters (k = 3: 32 counters is fine; k < 3 is rejected by the API)
+
+// ------------------------------------------------------------------------------------------
+// KmerSet::get / Solid::set over batches
+// ------------------------------------------------------------------------------------------
+__global__ void get_batch_kernel(const uint8_t *__restrict__ bits, int k, const uint64_t *__restrict__ kmers, uint64_t n,
+                                 uint8_t *__restrict__ out) {
+    const uint64_t mask = kmask(k);
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        out[i] = solid(bits, __ldg(kmers + i) & mask, k) ? 1 : 0;
+}
+
+void launch_get_batch(brgpu_ctx *ctx, const uint8_t *d_bits, int k, const uint64_t *d_kmers, uint64_t n,
+                      uint8_t *d_out) {
+    if (!n) return;
+    ProfScope ps(ctx, "get_batch", (double)n * 41.0); // 8 B k-mer + 32 B sector + 1 B out
+    get_batch_kernel<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(d_bits, k, d_kmers, n, d_out);
+}
+
+__global__ void insert_batch_kernel(uint32_t *bits32, int k, const uint64_t *__restrict__ kmers, uint64_t n) {
+    const uint64_t mask = kmask(k);
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t idx = canonical_index(__ldg(kmers + i) & mask, k);
+        atomicOr(bits32 + (idx >> 5), 1u << (idx & 31)); // little-endian u32 == LSB-first bytes
+    }
+}
+
+void launch_insert_batch(brgpu_ctx *ctx, uint8_t *d_bits, int k, const uint64_t *d_kmers, uint64_t n) {
+    if (!n) return;
+    ProfScope ps(ctx, "insert_batch", (double)n * 72.0);
+    insert_batch_kernel<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(reinterpret_cast<uint32_t *>(d_bits), k,
+                                                                           d_kmers, n);
+}
+
+// ------------------------------------------------------------------------------------------
+// Multi-GPU merge: this rank's slice of the table += the same slice of every peer's table,
+// read straight out of the peers' HBM over NVLink (the pointers are CUDA-IPC mappings), with a
+// per-byte unsigned saturating add (min(255, sum) is associative and commutative, so the merged
+// slice equals what one GPU counting all reads would hold).
+// ------------------------------------------------------------------------------------------
+constexpr int MAX_PEERS = 15;
+struct PeerPtrs {
+    const uint4 *p[MAX_PEERS];
+};
+
+__global__ void __launch_bounds__(256)
+    merge_slice_kernel(uint4 *__restrict__ mine, PeerPtrs peers, int n_peers, uint64_t n16) {
+    for (uint64_t g = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; g < n16;
+         g += (uint64_t)gridDim.x * blockDim.x) {
+        uint4 a = mine[g];
+        for (int q = 0; q < n_peers; q++) {
+            uint4 b = __ldcs(peers.p[q] + g); // streaming: peer data is read once
+            a.x = __vaddus4(a.x, b.x);
+            a.y = __vaddus4(a.y, b.y);
+            a.z = __vaddus4(a.z, b.z);
+            a.w = __vaddus4(a.w, b.w);
+        }
+        mine[g] = a;
+    }
+}
+
+void launch_merge_slice(brgpu_ctx *ctx, uint8_t *d_counts, void *const *peers, int n_peers, uint64_t begin,
+                        uint64_t end) {
+    if (end <= begin || n_peers <= 0) return;
+    PeerPtrs pp;
+    for (int q = 0; q < MAX_PEERS; q++)
+        pp.p[q] = q < n_peers ? reinterpret_cast<const uint4 *>((const uint8_t *)peers[q] + begin) : nullptr;
+    uint64_t n16 = (end - begin) >> 4;
+    ProfScope ps(ctx, "merge_slice", (double)(end - begin) * (double)(n_peers + 2));
+    merge_slice_kernel<<<grid_for(ctx, n16, 256, 8), 256, 0, ctx->stream>>>(
+        reinterpret_cast<uint4 *>(d_counts + begin), pp, n_peers, n16);
+}
+
+} // namespace brgpu

@@ -1,0 +1,64 @@
+"""Minimal FASTA reader/writer for the host side of run_correction (src/lib.rs:30-31,57-60).
+
+The reference uses noodles-fasta 0.38 (not vendored).  Reader: `>` definition line, sequence =
+the following lines joined.  Writer: definition line verbatim, sequence wrapped at 80 columns
+(noodles' default line base count; recalled, see SURVEY §8c — parity tests compare sequences
+per record, not file bytes).  Input may be gzip (niffler sniffing in the reference).
+"""
+import gzip
+import io
+
+import numpy as np
+
+LINE_BASES = 80
+
+
+def _open(path_or_file):
+    if hasattr(path_or_file, "read"):
+        data = path_or_file.read()
+    else:
+        with open(path_or_file, "rb") as f:
+            data = f.read()
+    if data[:2] == b"\x1f\x8b":
+        data = gzip.decompress(data)
+    return data
+
+
+def read_fasta(path_or_file):
+    """Returns (definitions: list[bytes], seq: uint8 ndarray, offsets: uint64 ndarray)."""
+    data = _open(path_or_file)
+    defs, parts, lens = [], [], []
+    for rec in data.split(b">")[1:]:
+        nl = rec.find(b"\n")
+        if nl < 0:
+            defs.append(rec.rstrip(b"\r"))
+            lens.append(0)
+            continue
+        defs.append(rec[:nl].rstrip(b"\r"))
+        body = rec[nl + 1 :].replace(b"\n", b"").replace(b"\r", b"")
+        parts.append(body)
+        lens.append(len(body))
+    off = np.zeros(len(defs) + 1, dtype=np.uint64)
+    if lens:
+        off[1:] = np.cumsum(np.asarray(lens, dtype=np.uint64))
+    seq = np.frombuffer(b"".join(parts), dtype=np.uint8) if parts else np.empty(0, dtype=np.uint8)
+    return defs, seq, off
+
+
+def iter_chunks(defs, seq, off, chunk_records):
+    """populate_buffer (src/lib.rs:168-188): consecutive chunks of at most `chunk_records`."""
+    n = len(defs)
+    for a in range(0, n, chunk_records):
+        b = min(n, a + chunk_records)
+        yield defs[a:b], seq, off[a : b + 1]
+
+
+def write_fasta(out, defs, seq, off, line_bases=LINE_BASES):
+    buf = io.BytesIO()
+    data = seq.tobytes() if hasattr(seq, "tobytes") else bytes(seq)
+    for i, d in enumerate(defs):
+        buf.write(b">" + d + b"\n")
+        s = data[int(off[i]) : int(off[i + 1])]
+        for p in range(0, len(s), line_bases):
+            buf.write(s[p : p + line_bases] + b"\n")
+    out.write(buf.getvalue())

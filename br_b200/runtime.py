@@ -1,0 +1,126 @@
+"""Context and device-resident record chunks (host side of include/brgpu.h)."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None and a.size else None
+
+
+def _addr(buf):
+    """Host address of a numpy array or a (pinned) torch CPU tensor."""
+    if buf is None:
+        return None
+    if hasattr(buf, "data_ptr"):
+        return C.c_void_p(buf.data_ptr())
+    return buf.ctypes.data_as(C.c_void_p)
+
+
+def as_u8(seq):
+    if isinstance(seq, (bytes, bytearray, memoryview)):
+        return np.frombuffer(bytes(seq), dtype=np.uint8)
+    if hasattr(seq, "data_ptr"):
+        return seq
+    return np.ascontiguousarray(seq, dtype=np.uint8)
+
+
+def as_offsets(offsets):
+    if hasattr(offsets, "data_ptr"):
+        return offsets
+    return np.ascontiguousarray(offsets, dtype=np.uint64)
+
+
+class Context:
+    """One per process per GPU.  `stream` may be a torch.cuda.Stream (or a raw cudaStream_t
+    integer) so that torch events and the library's kernels share one stream."""
+
+    def __init__(self, device=0, stream=None):
+        h = C.c_void_p()
+        raw = None
+        if stream is not None:
+            raw = C.c_void_p(getattr(stream, "cuda_stream", stream))
+        check(lib.brgpu_ctx_create(int(device), raw, C.byref(h)))
+        self._h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.brgpu_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def synchronize(self):
+        check(lib.brgpu_ctx_synchronize(self._h), self._h)
+
+    # --- instrumentation -------------------------------------------------------------------
+    def profile_enable(self, on=True):
+        check(lib.brgpu_profile_enable(self._h, int(on)), self._h)
+
+    def profile_reset(self):
+        check(lib.brgpu_profile_reset(self._h), self._h)
+
+    def profile(self):
+        """{kernel name: {"ms", "launches", "algo_bytes"}} accumulated since the last reset."""
+        out = {}
+        n = lib.brgpu_profile_count(self._h)
+        name = C.create_string_buffer(64)
+        ms, nb, ln = C.c_double(), C.c_double(), C.c_uint64()
+        for i in range(n):
+            check(lib.brgpu_profile_get(self._h, i, name, 64, C.byref(ms), C.byref(ln), C.byref(nb)), self._h)
+            out[name.value.decode()] = {"ms": ms.value, "launches": ln.value, "algo_bytes": nb.value}
+        return out
+
+    @property
+    def launch_count(self):
+        return lib.brgpu_launch_count(self._h)
+
+
+class Reads:
+    """A chunk of records resident in HBM (the 8192-record buffer of src/lib.rs:90, any size)."""
+
+    def __init__(self, ctx, handle):
+        self.ctx = ctx
+        self._h = handle
+
+    @classmethod
+    def upload(cls, ctx, seq, offsets):
+        s, off = as_u8(seq), as_offsets(offsets)
+        n = (off.numel() if hasattr(off, "numel") else off.size) - 1
+        h = C.c_void_p()
+        check(lib.brgpu_reads_upload(ctx._h, _addr(s), _addr(off), n, C.byref(h)), ctx._h)
+        r = cls(ctx, h)
+        r._keep = (s, off)
+        return r
+
+    def free(self):
+        if getattr(self, "_h", None):
+            lib.brgpu_reads_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.free()
+
+    def __len__(self):
+        return lib.brgpu_reads_count(self._h)
+
+    @property
+    def bases(self):
+        return lib.brgpu_reads_bases(self._h)
+
+    def download(self, out=None, out_offsets=None):
+        """Returns (uint8 array of concatenated sequences, uint64 offsets)."""
+        n = len(self)
+        if out_offsets is None:
+            out_offsets = np.empty(n + 1, dtype=np.uint64)
+        if out is None:
+            out = np.empty(max(1, self.bases), dtype=np.uint8)
+        cap = out.numel() if hasattr(out, "numel") else out.size
+        req = C.c_uint64()
+        check(lib.brgpu_reads_download(self._h, _addr(out), cap, _addr(out_offsets), C.byref(req)), self.ctx._h)
+        return out[: req.value], out_offsets

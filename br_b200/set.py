@@ -1,0 +1,200 @@
+"""Host-side mirror of br's `set` module (src/set.rs, src/set/pcon.rs) over the C ABI.
+
+    trait KmerSet: Sync { fn get(&self, kmer: u64) -> bool; fn k(&self) -> u8; }   src/set.rs:17-21
+
+`Pcon` keeps the dense canonical bitfield in HBM.  `get` exists for interface parity and for the
+reference's unit tests; it is a batch of one (a round trip per k-mer), so real callers use
+`get_batch`.  Constructors follow src/set/pcon.rs and the count->solid glue of src/main.rs:72-115.
+"""
+import ctypes as C
+import gzip
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, lib
+from .runtime import Context, Reads, _addr, _ptr, as_offsets, as_u8
+
+
+def nuc2bit(b: int) -> int:
+    return (b >> 1) & 3
+
+
+def seq2bit(seq: bytes) -> int:
+    """cocktail::kmer::seq2bit — host helper for building k-mers to pass to get()/insert()."""
+    kmer = 0
+    for b in seq:
+        kmer = (kmer << 2) | ((b >> 1) & 3)
+    return kmer
+
+
+class KmerSet:
+    """src/set.rs:17-21"""
+
+    def get(self, kmer: int) -> bool:
+        raise NotImplementedError
+
+    def k(self) -> int:
+        raise NotImplementedError
+
+
+class Pcon(KmerSet):
+    """set::Pcon (src/set/pcon.rs:13-196): dense bitfield of 2^(2k-1) canonical k-mers."""
+
+    def __init__(self, ctx: Context, handle):
+        self.ctx = ctx
+        self._h = handle
+        self._mirror = None
+
+    # --- constructors ------------------------------------------------------------------------
+    @classmethod
+    def new(cls, ctx, k):
+        """Pcon::new(pcon::solid::Solid::new(k)) — empty set (src/set/pcon.rs:183)."""
+        h = C.c_void_p()
+        check(lib.brgpu_set_new(ctx._h, k, C.byref(h)), ctx._h)
+        return cls(ctx, h)
+
+    @classmethod
+    def from_pcon_solid(cls, ctx, stream):
+        """src/set/pcon.rs:18-25: a (gzip) `.solid` stream — byte 0 = k, rest = bitfield.
+        Decompression is host I/O (niffler in the reference); the payload goes to the GPU."""
+        data = stream if isinstance(stream, (bytes, bytearray)) else stream.read()
+        if data[:2] == b"\x1f\x8b":
+            data = gzip.decompress(data)
+        buf = np.frombuffer(data, dtype=np.uint8)
+        h = C.c_void_p()
+        check(lib.brgpu_set_from_solid_payload(ctx._h, _ptr(buf), buf.size, C.byref(h)), ctx._h)
+        return cls(ctx, h)
+
+    @classmethod
+    def from_bitfield(cls, ctx, k, bits):
+        b = np.ascontiguousarray(bits, dtype=np.uint8)
+        h = C.c_void_p()
+        check(lib.brgpu_set_from_bitfield(ctx._h, k, _ptr(b), b.size, C.byref(h)), ctx._h)
+        return cls(ctx, h)
+
+    @classmethod
+    def from_reads(cls, ctx, reads, k, abundance=None, abundance_selection=None):
+        """The `fasta` sub-command (src/main.rs:72-115): count, spectrum, threshold, bitfield.
+        `reads` is a device-resident Reads or a (seq, offsets) pair of host buffers.
+        abundance: -a; abundance_selection: None or "first-minimum" (src/cli.rs:227-241)."""
+        k = k - (~(k & 1) & 1)  # Fasta::kmer_size forces k odd (src/cli.rs:277-279)
+        if abundance is not None:
+            sel, ab = _lib.ABUNDANCE_EXPLICIT, int(abundance)  # explicit wins (src/main.rs:96)
+        elif abundance_selection in ("first-minimum", "first_minimum"):
+            sel, ab = _lib.ABUNDANCE_FIRST_MINIMUM, -1
+        elif abundance_selection is None:
+            sel, ab = _lib.ABUNDANCE_EXPLICIT, -1  # -> AbundanceThresholdOrAbundanceMethod
+        else:
+            raise ValueError(f"abundance selection {abundance_selection!r} is not supported yet")
+        h = C.c_void_p()
+        if isinstance(reads, Reads):
+            check(lib.brgpu_set_from_reads(ctx._h, k, ab, sel, reads._h, C.byref(h)), ctx._h)
+        else:
+            s, off = as_u8(reads[0]), as_offsets(reads[1])
+            n = (off.numel() if hasattr(off, "numel") else off.size) - 1
+            check(lib.brgpu_set_from_host_reads(ctx._h, k, ab, sel, _addr(s), _addr(off), n, C.byref(h)), ctx._h)
+        return cls(ctx, h)
+
+    # --- KmerSet --------------------------------------------------------------------------------
+    def k(self):
+        return lib.brgpu_set_k(self._h)
+
+    def get(self, kmer: int) -> bool:
+        """Pcon::get (src/set/pcon.rs:189-191); forward k-mers are canonicalised."""
+        return bool(self.get_batch(np.array([kmer], dtype=np.uint64))[0])
+
+    def get_batch(self, kmers):
+        km = np.ascontiguousarray(kmers, dtype=np.uint64)
+        out = np.empty(km.size, dtype=np.uint8)
+        check(lib.brgpu_set_get_batch(self._h, _ptr(km), km.size, _ptr(out)), self.ctx._h)
+        return out
+
+    def insert(self, kmers):
+        """Solid::set(kmer, true) for a batch (canonicalises, like the reference's tests rely on)."""
+        km = np.ascontiguousarray(np.atleast_1d(kmers), dtype=np.uint64)
+        check(lib.brgpu_set_insert_batch(self._h, _ptr(km), km.size), self.ctx._h)
+
+    def insert_all_kmers(self, seq: bytes):
+        """`for kmer in Tokenizer::new(seq, k) { data.set(kmer, true) }` of the reference's tests."""
+        k = self.k()
+        if len(seq) < k:
+            return
+        mask = (1 << (2 * k)) - 1
+        kmers, km = [], seq2bit(seq[: k - 1])
+        for b in seq[k - 1 :]:
+            km = ((km << 2) & mask) | nuc2bit(b)
+            kmers.append(km)
+        self.insert(np.array(kmers, dtype=np.uint64))
+
+    # --- extras -----------------------------------------------------------------------------------
+    @property
+    def abundance(self):
+        a = lib.brgpu_set_abundance(self._h)
+        return None if a < 0 else a
+
+    def spectrum(self):
+        h = np.zeros(256, dtype=np.uint64)
+        check(lib.brgpu_set_spectrum(self._h, _ptr(h)), self.ctx._h)
+        return h
+
+    def bitfield(self):
+        n = lib.brgpu_set_bitfield_bytes(self._h)
+        out = np.empty(n, dtype=np.uint8)
+        check(lib.brgpu_set_export_bitfield(self._h, _ptr(out), n), self.ctx._h)
+        return out
+
+    def to_solid_payload(self) -> bytes:
+        """The body of a `.solid` file before gzip: u8 k || bitfield."""
+        return bytes([self.k()]) + self.bitfield().tobytes()
+
+    def free(self):
+        if getattr(self, "_h", None):
+            lib.brgpu_set_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.free()
+
+
+class Counter:
+    """pcon::counter::Counter<u8> in HBM (src/main.rs:73-78)."""
+
+    def __init__(self, ctx, k):
+        self.ctx, self.k = ctx, k
+        h = C.c_void_p()
+        check(lib.brgpu_counts_create(ctx._h, k, C.byref(h)), ctx._h)
+        self._h = h
+
+    def count(self, reads: Reads):
+        check(lib.brgpu_counts_add_reads(self._h, reads._h), self.ctx._h)
+
+    def spectrum(self):
+        h = np.zeros(256, dtype=np.uint64)
+        check(lib.brgpu_counts_spectrum(self._h, _ptr(h)), self.ctx._h)
+        return h
+
+    @staticmethod
+    def first_minimum(hist):
+        h = np.ascontiguousarray(hist, dtype=np.uint64)
+        r = lib.brgpu_spectrum_first_minimum(_ptr(h))
+        return None if r < 0 else r
+
+    def raw(self):
+        n = lib.brgpu_counts_len(self._h)
+        out = np.empty(n, dtype=np.uint8)
+        check(lib.brgpu_counts_download(self._h, _ptr(out), n), self.ctx._h)
+        return out
+
+    def to_set(self, abundance):
+        h = C.c_void_p()
+        check(lib.brgpu_set_from_counts(self._h, int(abundance), C.byref(h)), self.ctx._h)
+        return Pcon(self.ctx, h)
+
+    def free(self):
+        if getattr(self, "_h", None):
+            lib.brgpu_counts_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.free()

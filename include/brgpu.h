@@ -1,0 +1,180 @@
+/*
+ * brgpu.h — C ABI of the B200-native hot path of natir/br ("Brutal Rewrite").
+ *
+ * This is the drop-in boundary: the entry points are what a Rust `brgpu-sys` FFI crate
+ * (or any other host) binds to replace, inside br,
+ *   part 1  the k-mer count -> solidity threshold -> canonical bitfield pass
+ *           (src/main.rs:72-115, src/set/pcon.rs, pcon::{counter,spectrum,solid}), and
+ *   part 2  the per-read correction pass
+ *           (src/correct/ modules, the chunk loop of src/lib.rs:72-139).
+ * Every function is `extern "C"`, takes plain pointers and sizes, returns an int status
+ * and never throws, aborts or prints across the boundary (tests/br.rs:30 demands an empty
+ * stderr).  All buffers named `host` below are caller-owned host memory (pinned memory
+ * makes the copies faster, pageable memory works); the library never frees caller memory.
+ * There is NO CPU fallback: without a CUDA device every entry point that needs one fails
+ * with BRGPU_E_NO_DEVICE.
+ *
+ * Supported k: odd, 3 <= k <= 19 (dense bitfield of 2^(2k-1) bits; br's `fasta`
+ * sub-command forces k odd, src/cli.rs:277-279; the parity-canonical form needs it).
+ */
+#ifndef BRGPU_H
+#define BRGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes (replace error::Error / anyhow at the boundary, src/error.rs:12-45) ---- */
+enum {
+    BRGPU_OK = 0,
+    BRGPU_E_INVALID = 1,      /* bad argument (NULL, even k, confirm == 0, unknown method, ...) */
+    BRGPU_E_NO_DEVICE = 2,    /* no usable CUDA device: the product has no CPU path */
+    BRGPU_E_CUDA = 3,         /* a CUDA call failed; see brgpu_last_error */
+    BRGPU_E_NOMEM = 4,        /* host or device allocation failed */
+    BRGPU_E_OVERFLOW = 5,     /* caller's output buffer too small; *required holds the size */
+    BRGPU_E_NO_THRESHOLD = 6, /* Error::ComputeAbundanceThreshold (src/main.rs:97) */
+    BRGPU_E_NEED_ABUNDANCE = 7 /* Error::AbundanceThresholdOrAbundanceMethod (src/main.rs:109) */
+};
+
+/* ---- correction methods: cli::CorrectionMethod in declaration order (src/cli.rs:121-131) ---- */
+enum { BRGPU_ONE = 0, BRGPU_TWO = 1, BRGPU_GRAPH = 2, BRGPU_GREEDY = 3, BRGPU_GAP_SIZE = 4 };
+
+/* ---- abundance selection: cli::AbundanceSelection (src/cli.rs:227-241) ---- */
+enum { BRGPU_ABUNDANCE_EXPLICIT = 0, BRGPU_ABUNDANCE_FIRST_MINIMUM = 1 };
+
+typedef struct brgpu_ctx brgpu_ctx;       /* one per process per GPU: device, stream, scratch */
+typedef struct brgpu_set brgpu_set;       /* Box<dyn KmerSet> (src/set.rs:17-23), device resident */
+typedef struct brgpu_reads brgpu_reads;   /* a chunk of records (src/lib.rs:90), device resident */
+typedef struct brgpu_counts brgpu_counts; /* pcon::counter::Counter<u8>, device resident */
+
+/* ------------------------------------------------------------------------------------------
+ * context
+ * ---------------------------------------------------------------------------------------- */
+/* `cuda_stream` may be NULL (the library creates its own) or an existing cudaStream_t so
+ * that the host's own events/allocator order against the library's work. */
+int brgpu_ctx_create(int device, void *cuda_stream, brgpu_ctx **out);
+void brgpu_ctx_destroy(brgpu_ctx *ctx);
+int brgpu_ctx_synchronize(brgpu_ctx *ctx);
+const char *brgpu_last_error(const brgpu_ctx *ctx);
+const char *brgpu_version(void);
+
+/* ------------------------------------------------------------------------------------------
+ * reads — the record chunk run_correction forms (src/lib.rs:90, populate_buffer :168-188).
+ * `seq` is the concatenation of the sequences (any bytes; nuc2bit is (b>>1)&3),
+ * `offsets` has n_reads+1 entries.
+ * ---------------------------------------------------------------------------------------- */
+int brgpu_reads_upload(brgpu_ctx *ctx, const uint8_t *seq_host, const uint64_t *offsets_host, uint64_t n_reads,
+                       brgpu_reads **out);
+uint64_t brgpu_reads_count(const brgpu_reads *reads);
+uint64_t brgpu_reads_bases(const brgpu_reads *reads); /* sum of lengths (syncs the stream) */
+/* Copy back as concatenated bytes + offsets (n_reads+1).  BRGPU_E_OVERFLOW if seq_cap is too
+ * small; *required (may be NULL) receives the byte count either way. */
+int brgpu_reads_download(brgpu_reads *reads, uint8_t *seq_host, uint64_t seq_cap, uint64_t *offsets_host,
+                         uint64_t *required);
+void brgpu_reads_free(brgpu_reads *reads);
+
+/* ------------------------------------------------------------------------------------------
+ * part 1 — counting and the solid set
+ * ---------------------------------------------------------------------------------------- */
+/* pcon Counter::<u8>::new(k) (src/main.rs:73): 2^(2k-1) zeroed saturating u8 counters in HBM */
+int brgpu_counts_create(brgpu_ctx *ctx, int k, brgpu_counts **out);
+/* Counter::count_fasta (src/main.rs:74): counts[canonical(kmer)>>1] = min(255, +1) for every
+ * k-mer of every read with len >= k.  May be called repeatedly (chunks accumulate). */
+int brgpu_counts_add_reads(brgpu_counts *counts, const brgpu_reads *reads);
+/* Spectrum::from_count (src/main.rs:93): 256-bin histogram over all counters incl. zeros */
+int brgpu_counts_spectrum(brgpu_counts *counts, uint64_t hist_host[256]);
+/* Spectrum::get_threshold(FirstMinimum): returns the threshold or -1 for None */
+int brgpu_spectrum_first_minimum(const uint64_t hist[256]);
+/* Copy the raw table to the host (Counter::raw, src/main.rs:76-78); n must be 2^(2k-1) */
+int brgpu_counts_download(brgpu_counts *counts, uint8_t *out_host, uint64_t n);
+/* device pointer and element count of the table, for multi-GPU merge plumbing */
+void *brgpu_counts_device_ptr(brgpu_counts *counts);
+uint64_t brgpu_counts_len(const brgpu_counts *counts);
+void brgpu_counts_free(brgpu_counts *counts);
+
+/* Solid::from_count (src/main.rs:112-114): bit i = counts[i] > abundance, LSB-first */
+int brgpu_set_from_counts(brgpu_counts *counts, int abundance, brgpu_set **out);
+/* the whole `fasta` sub-command glue (src/main.rs:72-115): count -> spectrum -> threshold ->
+ * bitfield.  selection = BRGPU_ABUNDANCE_EXPLICIT uses `abundance` (>= 0); FIRST_MINIMUM
+ * ignores it.  abundance < 0 with EXPLICIT -> BRGPU_E_NEED_ABUNDANCE. */
+int brgpu_set_from_reads(brgpu_ctx *ctx, int k, int abundance, int selection, const brgpu_reads *reads,
+                         brgpu_set **out);
+/* same, from host buffers (the call the Rust shim makes) */
+int brgpu_set_from_host_reads(brgpu_ctx *ctx, int k, int abundance, int selection, const uint8_t *seq_host,
+                              const uint64_t *offsets_host, uint64_t n_reads, brgpu_set **out);
+/* set::Pcon::new(Solid) (src/set/pcon.rs:183) from a raw bitfield of 2^(2k-1)/8 bytes */
+int brgpu_set_from_bitfield(brgpu_ctx *ctx, int k, const uint8_t *bits_host, uint64_t n_bytes, brgpu_set **out);
+/* set::Pcon::from_pcon_solid (src/set/pcon.rs:18-25) after the host gunzipped the stream:
+ * payload[0] = k, payload[1..] = bitfield */
+int brgpu_set_from_solid_payload(brgpu_ctx *ctx, const uint8_t *payload_host, uint64_t n_bytes, brgpu_set **out);
+/* empty set, Solid::new(k), and Solid::set on a batch of (forward or canonical) k-mers —
+ * what the reference's unit tests build their sets with */
+int brgpu_set_new(brgpu_ctx *ctx, int k, brgpu_set **out);
+int brgpu_set_insert_batch(brgpu_set *set, const uint64_t *kmers_host, uint64_t n);
+
+int brgpu_set_k(const brgpu_set *set);                      /* KmerSet::k */
+int brgpu_set_abundance(const brgpu_set *set);              /* threshold used, -1 if not built from counts */
+uint64_t brgpu_set_bitfield_bytes(const brgpu_set *set);    /* 2^(2k-1)/8 */
+int brgpu_set_export_bitfield(brgpu_set *set, uint8_t *out_host, uint64_t cap);
+/* KmerSet::get over a batch; forward k-mers are canonicalised inside (src/set/pcon.rs:189) */
+int brgpu_set_get_batch(brgpu_set *set, const uint64_t *kmers_host, uint64_t n, uint8_t *out_host);
+/* spectrum seen when the set was built from reads/counts (zeros if not) */
+int brgpu_set_spectrum(const brgpu_set *set, uint64_t hist[256]);
+void *brgpu_set_device_ptr(brgpu_set *set);
+void brgpu_set_free(brgpu_set *set);
+
+/* ------------------------------------------------------------------------------------------
+ * part 2 — correction.  Semantics of one record: src/lib.rs:44-55 — fold `methods` left to
+ * right with Corrector::correct (src/correct/mod.rs:53-107); unless two_side, reverse the
+ * bytes, fold again, reverse back.  Records come back in input order (the serial path's order,
+ * src/lib.rs:21-69).  confirm: -C (One/Two/GapSize `c`, Greedy `nb_validate`, src/lib.rs:149-159),
+ * max_search: -M (Greedy).  confirm must be in 1..=255, max_search in 0..=255.
+ * ---------------------------------------------------------------------------------------- */
+int brgpu_correct_reads(brgpu_ctx *ctx, const brgpu_set *set, const uint8_t *methods, uint64_t n_methods, int confirm,
+                        int max_search, int two_side, const brgpu_reads *in, brgpu_reads **out);
+
+int brgpu_correct_batch(brgpu_ctx *ctx, const brgpu_set *set, const uint8_t *methods, uint64_t n_methods, int confirm,
+                        int max_search, int two_side, const uint8_t *seq_host, const uint64_t *offsets_host,
+                        uint64_t n_reads, uint8_t *out_host, uint64_t out_cap, uint64_t *out_offsets_host,
+                        uint64_t *required);
+
+/* Corrector::correct for a single read and a single method (KAT parity; a Rust
+ * `GpuCorrector: Corrector` would call this). */
+int brgpu_correct_one(brgpu_ctx *ctx, const brgpu_set *set, int method, int confirm, int max_search,
+                      const uint8_t *seq_host, uint64_t len, uint8_t *out_host, uint64_t out_cap, uint64_t *out_len);
+
+/* ------------------------------------------------------------------------------------------
+ * multi-GPU (one process per GPU): merge per-rank count tables over NVLink peer memory.
+ * Each rank exports its table with brgpu_counts_ipc_export, the host exchanges the 64-byte
+ * handles (torch.distributed / MPI / anything), every rank opens its peers' tables and then
+ * calls brgpu_counts_merge_slice: counts[i] = min(255, sum over ranks) on this rank's
+ * 1/world slice of the index space, reading the peers' slices straight over NVLink.
+ * ---------------------------------------------------------------------------------------- */
+int brgpu_counts_ipc_export(brgpu_counts *counts, uint8_t handle_out[64]);
+int brgpu_ipc_open(brgpu_ctx *ctx, const uint8_t handle[64], void **peer_dev_ptr);
+int brgpu_ipc_close(brgpu_ctx *ctx, void *peer_dev_ptr);
+/* saturating-add the peers' [begin,end) slices into this rank's table slice */
+int brgpu_counts_merge_slice(brgpu_counts *counts, void *const *peer_tables, int n_peers, uint64_t begin, uint64_t end);
+/* spectrum / threshold restricted to a slice [begin,end) of the index space; the bitfield
+ * slice is written into set's bitfield at the same bit range (begin, end multiples of 1024) */
+int brgpu_counts_spectrum_slice(brgpu_counts *counts, uint64_t begin, uint64_t end, uint64_t hist_host[256]);
+int brgpu_set_threshold_slice(brgpu_set *set, brgpu_counts *counts, int abundance, uint64_t begin, uint64_t end);
+
+/* ------------------------------------------------------------------------------------------
+ * instrumentation (bench.py): per-kernel CUDA-event timings on the library's stream
+ * ---------------------------------------------------------------------------------------- */
+int brgpu_profile_enable(brgpu_ctx *ctx, int on);
+int brgpu_profile_reset(brgpu_ctx *ctx);
+/* number of distinct kernels seen; i-th entry: name, accumulated ms, launches, algorithmic bytes */
+int brgpu_profile_count(brgpu_ctx *ctx);
+int brgpu_profile_get(brgpu_ctx *ctx, int i, char *name_out, size_t name_cap, double *ms, uint64_t *launches,
+                      double *algo_bytes);
+uint64_t brgpu_launch_count(const brgpu_ctx *ctx); /* kernels launched since ctx creation */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BRGPU_H */

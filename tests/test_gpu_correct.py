@@ -1,0 +1,221 @@
+"""GPU parity, part 2: the correction pass through the C ABI against the CPU oracle —
+the reference's own KATs, every method alone and chained on the reads fixture (config 1 of
+BASELINE.json), and randomised small cases that reach the rare scenario paths.  Byte-exact."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+METHODS = ["one", "two", "graph", "greedy", "gap_size"]
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    import br_b200
+
+    ctx = br_b200.Context(0)
+    yield br_b200, ctx
+    ctx.close()
+
+
+def make_corrector(br, s, c):
+    m = c["method"]
+    if m == "One":
+        return br.One(s, c["confirm"])
+    if m == "Two":
+        return br.Two(s, c["confirm"])
+    if m == "Graph":
+        return br.Graph(s)
+    if m == "Greedy":
+        return br.Greedy(s, c["max_search"], c["nb_validate"])
+    return br.GapSize(s, c["confirm"])
+
+
+def compare_batches(name, got, got_off, exp, exp_off, seq=None, off=None):
+    assert got_off.size == exp_off.size, name
+    bad = []
+    for r in range(exp_off.size - 1):
+        g = got[int(got_off[r]) : int(got_off[r + 1])].tobytes()
+        e = exp[int(exp_off[r]) : int(exp_off[r + 1])].tobytes()
+        if g != e:
+            p = next((i for i in range(min(len(g), len(e))) if g[i] != e[i]), min(len(g), len(e)))
+            bad.append((r, len(g), len(e), p))
+    if bad:
+        r, lg, le, p = bad[0]
+        g = got[int(got_off[r]) : int(got_off[r + 1])].tobytes()
+        e = exp[int(exp_off[r]) : int(exp_off[r + 1])].tobytes()
+        msg = f"{name}: {len(bad)} of {exp_off.size - 1} reads differ; first read {r}: len gpu {lg} vs oracle {le}, first diff at {p}\n"
+        msg += f"  gpu    ...{g[max(0, p - 30) : p + 30]!r}\n  oracle ...{e[max(0, p - 30) : p + 30]!r}"
+        if seq is not None:
+            i = seq[int(off[r]) : int(off[r + 1])].tobytes()
+            msg += f"\n  input  (len {len(i)}) ...{i[max(0, p - 40) : p + 40]!r}"
+        pytest.fail(msg)
+
+
+def test_reference_kats_on_gpu(gpu, oracle, kats):
+    """The 52 active corrector KATs of the reference, through Corrector::correct on the GPU."""
+    br, ctx = gpu
+    for t in kats["correctors"]:
+        s = br.Pcon.new(ctx, t["k"])
+        for q in t["insert_all_kmers_of"]:
+            s.insert_all_kmers(q.encode())
+        if t["insert_kmers"]:
+            s.insert(np.array([oracle.seq2bit(q.encode()) for q in t["insert_kmers"]], dtype=np.uint64))
+        corr = make_corrector(br, s, t["corrector"])
+        assert corr.k() == t["k"]
+        for a in t["asserts"]:
+            got = corr.correct(a["input"].encode()).decode()
+            if t["ignored_upstream"]:
+                # #[ignore]d upstream (their assertion does not hold): pin to the oracle instead
+                os_ = oracle.Solid.from_bitfield(t["k"], s.bitfield())
+                c = t["corrector"]
+                exp = os_.correct(3, a["input"].encode(), confirm=c["nb_validate"], max_search=c["max_search"]).decode()
+                assert got == exp, (t["module"], t["name"])
+            else:
+                assert got == a["expected"], (t["module"], t["name"], a["input"], got)
+
+
+@pytest.fixture(scope="module")
+def fixture_sets(gpu, oracle, fixture_solid_payload):
+    br, ctx = gpu
+    return br.Pcon.from_pcon_solid(ctx, fixture_solid_payload), oracle.Solid.from_solid_payload(fixture_solid_payload)
+
+
+@pytest.mark.parametrize("method", METHODS)
+@pytest.mark.parametrize("two_side", [True, False])
+def test_each_method_on_reads_fixture(gpu, oracle, fixture_reads, fixture_sets, method, two_side):
+    """Config 1 of BASELINE.json (tests/data reads, k = 11) for every method, forward only and
+    with the reversed pass (two_side=False is br's default, src/lib.rs:48)."""
+    br, ctx = gpu
+    seq, off = fixture_reads
+    gs, os_ = fixture_sets
+    from oracle.br_oracle import METHOD_IDS
+
+    exp, exp_off = os_.run_correction([METHOD_IDS[method]], seq, off, confirm=5, max_search=7, two_side=two_side, threads=8)
+    got, got_off = br.correct_batch(br.build_methods([method], gs, 5, 7), seq, off, two_side=two_side)
+    compare_batches(f"{method} two_side={two_side}", got, got_off, exp, exp_off, seq, off)
+
+
+@pytest.mark.parametrize("chain", [["one", "two"], ["graph", "greedy", "gap_size"], METHODS, ["gap_size", "one", "gap_size"]])
+def test_method_chains_on_reads_fixture(gpu, oracle, fixture_reads, fixture_sets, chain):
+    br, ctx = gpu
+    seq, off = fixture_reads
+    gs, os_ = fixture_sets
+    from oracle.br_oracle import METHOD_IDS
+
+    exp, exp_off = os_.run_correction([METHOD_IDS[m] for m in chain], seq, off, threads=8)
+    got, got_off = br.correct_batch(br.build_methods(chain, gs), seq, off)
+    compare_batches("+".join(chain), got, got_off, exp, exp_off, seq, off)
+
+
+def test_device_resident_path_equals_host_path(gpu, fixture_reads, fixture_sets):
+    br, ctx = gpu
+    seq, off = fixture_reads
+    gs, _ = fixture_sets
+    methods = br.build_methods(["one", "gap_size"], gs)
+    a, ao = br.correct_batch(methods, seq, off)
+    out = br.correct_reads(methods, br.Reads.upload(ctx, seq, off))
+    b, bo = out.download()
+    assert np.array_equal(ao, bo) and np.array_equal(a, b)
+
+
+def random_case(rng, k, genome_len, n_reads, error, alphabet=b"ACGT"):
+    from br_b200 import synth
+
+    genome = np.frombuffer(alphabet, dtype=np.uint8)[rng.integers(0, len(alphabet), size=genome_len)]
+    parts = []
+    for _ in range(n_reads):
+        L = int(rng.integers(1, min(genome_len, 400)))
+        st = int(rng.integers(0, genome_len - L + 1))
+        parts.append(synth.mutate(genome[st : st + L], error, rng))
+    off = np.zeros(n_reads + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([p.size for p in parts])
+    return genome, np.concatenate(parts), off
+
+
+@pytest.mark.parametrize("k", [5, 7, 9, 13])
+@pytest.mark.parametrize("confirm,max_search", [(1, 0), (2, 3), (5, 7), (3, 12)])
+def test_randomised_small_cases(gpu, oracle, k, confirm, max_search):
+    """Dense little de Bruijn graphs (small k, high error) reach the branches real data rarely
+    takes: ties broken by one_more, DCI's empty emission, cycles in the walks, dirty windows that
+    trigger again, read ends inside every scenario's look-ahead."""
+    br, ctx = gpu
+    from oracle.br_oracle import METHOD_IDS
+
+    rng = np.random.default_rng(1000 * k + 10 * confirm + max_search)
+    genome, seq, off = random_case(rng, k, genome_len=int(rng.integers(200, 3000)), n_reads=600, error=0.12)
+    gs = br.Pcon.new(ctx, k)
+    gs.insert_all_kmers(genome.tobytes())
+    os_ = oracle.Solid.from_bitfield(k, gs.bitfield())
+    for method in METHODS:
+        exp, exp_off = os_.run_correction([METHOD_IDS[method]], seq, off, confirm=confirm, max_search=max_search, two_side=True, threads=8)
+        got, got_off = br.correct_batch(br.build_methods([method], gs, confirm, max_search), seq, off, two_side=True)
+        compare_batches(f"k={k} c={confirm} M={max_search} {method}", got, got_off, exp, exp_off, seq, off)
+    exp, exp_off = os_.run_correction(list(range(5)), seq, off, confirm=confirm, max_search=max_search, threads=8)
+    got, got_off = br.correct_batch(br.build_methods(METHODS, gs, confirm, max_search), seq, off)
+    compare_batches(f"k={k} c={confirm} M={max_search} chain", got, got_off, exp, exp_off, seq, off)
+
+
+def test_non_acgt_bytes_echo_and_short_reads(gpu, oracle):
+    """Untouched positions echo the original byte, corrected ones are upper-case ACTG; reads
+    shorter than k pass through."""
+    br, ctx = gpu
+    from oracle.br_oracle import METHOD_IDS
+
+    rng = np.random.default_rng(77)
+    genome, seq, off = random_case(rng, 7, 1500, 300, 0.08, alphabet=b"ACGTacgtN")
+    gs = br.Pcon.new(ctx, 7)
+    gs.insert_all_kmers(genome.tobytes())
+    os_ = oracle.Solid.from_bitfield(7, gs.bitfield())
+    for method in METHODS:
+        exp, exp_off = os_.run_correction([METHOD_IDS[method]], seq, off, confirm=2, threads=8)
+        got, got_off = br.correct_batch(br.build_methods([method], gs, 2, 7), seq, off)
+        compare_batches(f"non-ACGT {method}", got, got_off, exp, exp_off, seq, off)
+
+
+def test_graph_path_longer_than_the_slot_triggers_reslot(gpu, oracle):
+    """A deletion of 300 bases repaired by Graph grows the read far beyond len/8 + 64: the
+    library must notice the overflow, re-slot and still return the oracle's bytes."""
+    br, ctx = gpu
+    rng = np.random.default_rng(9)
+    refe = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=800)].tobytes()
+    read = refe[:60] + refe[360:440]
+    k = 11
+    gs = br.Pcon.new(ctx, k)
+    gs.insert_all_kmers(refe)
+    os_ = oracle.Solid.from_bitfield(k, gs.bitfield())
+    exp = os_.correct(2, read)
+    assert len(exp) > len(read) + 200  # the walk really is long
+    assert br.Graph(gs).correct(read) == exp
+    seq = np.frombuffer(read * 3, dtype=np.uint8)
+    off = np.array([0, len(read), 2 * len(read), 3 * len(read)], dtype=np.uint64)
+    got, got_off = br.correct_batch([br.Graph(gs)], seq, off, two_side=True)
+    assert [got[int(got_off[i]) : int(got_off[i + 1])].tobytes() for i in range(3)] == [exp] * 3
+
+
+def test_parameter_validation(gpu, fixture_sets):
+    br, ctx = gpu
+    gs, _ = fixture_sets
+    seq = np.frombuffer(b"ACGTACGTACGTACGT", dtype=np.uint8)
+    off = np.array([0, 16], dtype=np.uint64)
+    with pytest.raises(br.BrgpuError):
+        br.correct_batch([br.One(gs, 0)], seq, off)  # confirm == 0
+    with pytest.raises(br.BrgpuError):
+        br.Pcon.new(ctx, 12)  # even k
+    with pytest.raises(br.BrgpuError):
+        br.Pcon.new(ctx, 21)  # dense bitfield does not fit
+
+
+def test_bio_alignment_on_gpu_matches_oracle_through_greedy(gpu, oracle):
+    """Greedy with a long search exercises alignments with more than 32 rows (several rows per
+    lane in the systolic sweep)."""
+    br, ctx = gpu
+    rng = np.random.default_rng(4242)
+    genome, seq, off = random_case(rng, 13, 4000, 400, 0.10)
+    gs = br.Pcon.new(ctx, 13)
+    gs.insert_all_kmers(genome.tobytes())
+    os_ = oracle.Solid.from_bitfield(13, gs.bitfield())
+    for max_search in (25, 60):
+        exp, exp_off = os_.run_correction([3], seq, off, confirm=2, max_search=max_search, two_side=True, threads=8)
+        got, got_off = br.correct_batch([br.Greedy(gs, max_search, 2)], seq, off, two_side=True)
+        compare_batches(f"greedy M={max_search}", got, got_off, exp, exp_off, seq, off)

@@ -1,0 +1,175 @@
+"""GPU parity, part 1: counting -> spectrum -> threshold -> bitfield and KmerSet::get, through
+the C ABI (br_b200 is a ctypes shim over libbrgpu.so), against the CPU oracle and the
+reference's fixtures.  Bit-exact: this is integer / index work."""
+import hashlib
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    import br_b200
+
+    ctx = br_b200.Context(0)
+    yield br_b200, ctx
+    ctx.close()
+
+
+def all_forward_kmers(seq, off, k):
+    code = ((seq >> 1) & 3).astype(np.uint64)
+    out = []
+    for r in range(off.size - 1):
+        c = code[int(off[r]) : int(off[r + 1])]
+        n = c.size - k + 1
+        if n <= 0:
+            continue
+        f = np.zeros(n, dtype=np.uint64)
+        for t in range(k):
+            f = (f << np.uint64(2)) | c[t : t + n]
+        out.append(f)
+    return np.concatenate(out)
+
+
+def test_set_kats_on_gpu(gpu, oracle, kats):
+    br, ctx = gpu
+    t = kats["set"][0]
+    k, seq = t["k"], t["seq"].encode()
+    s = br.Pcon.new(ctx, k)
+    fwd = np.array([oracle.seq2bit(seq[i : i + k]) for i in range(len(seq) - k + 1)], dtype=np.uint64)
+    cano = np.array([oracle.canonical(int(x), k) for x in fwd], dtype=np.uint64)
+    s.insert(cano)  # pcon.rs:205-216
+    assert s.get_batch(cano).all()
+    assert s.get_batch(fwd).all()  # pcon.rs:218-230: get canonicalises
+    assert not s.get(0)  # pcon.rs:232-242
+    assert s.k() == 11  # pcon.rs:244-254
+    # the same set through the oracle: identical bitfield
+    o = oracle.Solid(k)
+    for x in cano:
+        o.set(int(x))
+    assert np.array_equal(s.bitfield(), o.bits())
+
+
+def test_alt_nucs_kat_via_get(gpu, oracle, kats):
+    br, ctx = gpu
+    h = kats["helpers"][0]
+    s = br.Pcon.new(ctx, h["k"])
+    s.insert(np.array([oracle.seq2bit(q.encode()) for q in h["insert_kmers"]], dtype=np.uint64))
+    km = oracle.seq2bit(h["alt_nucs_of"].encode())
+    mask = (1 << (2 * h["k"])) - 1
+    cands = np.array([(((km >> 2) << 2) & mask) ^ a for a in range(4)], dtype=np.uint64)
+    assert [a for a in range(4) if s.get_batch(cands)[a]] == h["expected"]
+
+
+def test_get_batch_matches_oracle_on_fixture_set(gpu, oracle, fixture_reads, fixture_solid_payload):
+    br, ctx = gpu
+    seq, off = fixture_reads
+    s = br.Pcon.from_pcon_solid(ctx, fixture_solid_payload)
+    o = oracle.Solid.from_solid_payload(fixture_solid_payload)
+    assert s.k() == 11
+    assert s.to_solid_payload() == fixture_solid_payload
+    rng = np.random.default_rng(1)
+    rnd = rng.integers(0, 1 << 22, size=1_000_000, dtype=np.uint64)
+    assert np.array_equal(s.get_batch(rnd), o.get_batch(rnd))
+    km = all_forward_kmers(seq, off, 11)
+    g = s.get_batch(km)
+    assert np.array_equal(g, o.get_batch(km))
+    assert 0.70 < g.mean() < 0.80  # 74.8 % of the forward k-mers are solid
+
+
+def test_count_chain_regenerates_solid_fixture(gpu, oracle, fixture_reads, fixture_solid_payload):
+    """count -> threshold on the reads fixture must give the reference's .solid fixture bit for bit."""
+    br, ctx = gpu
+    seq, off = fixture_reads
+    reads = br.Reads.upload(ctx, seq, off)
+    assert len(reads) == 206 and reads.bases == int(off[-1])
+    c = br.Counter(ctx, 11)
+    c.count(reads)
+    oc = oracle.Counter(11)
+    oc.count(seq, off, threads=4)
+    assert np.array_equal(c.raw(), oc.raw())  # incl. the saturated counters
+    hist = c.spectrum()
+    assert np.array_equal(hist, oc.spectrum())
+    assert list(hist[1:9]) == [442564, 95498, 19526, 4458, 1221, 460, 494, 810]
+    assert br.Counter.first_minimum(hist) == 6
+    s = c.to_set(2)
+    assert s.to_solid_payload() == fixture_solid_payload
+    assert np.array_equal(s.spectrum(), hist)
+    # the one-call form (src/main.rs:72-115), explicit -a and first-minimum
+    s2 = br.Pcon.from_reads(ctx, (seq, off), 11, abundance=2)
+    assert s2.to_solid_payload() == fixture_solid_payload and s2.abundance == 2
+    s3 = br.Pcon.from_reads(ctx, reads, 11, abundance_selection="first-minimum")
+    assert s3.abundance == 6
+    assert np.array_equal(s3.bitfield(), oc.to_solid(6).bits())
+    # even k is decremented like Fasta::kmer_size (src/cli.rs:277-279)
+    assert br.Pcon.from_reads(ctx, reads, 12, abundance=2).k() == 11
+    with pytest.raises(br.BrgpuError) as e:
+        br.Pcon.from_reads(ctx, reads, 11)  # neither -a nor a method (src/main.rs:109)
+    assert e.value.status == 7
+
+
+def test_counter_saturates_at_255(gpu, oracle):
+    br, ctx = gpu
+    seq = np.frombuffer(b"A" * 400 + b"ACGTTGCATGCCGTA" * 40, dtype=np.uint8)
+    off = np.array([0, 400, seq.size], dtype=np.uint64)
+    for k in (3, 5, 9):
+        c = br.Counter(ctx, k)
+        c.count(br.Reads.upload(ctx, seq, off))
+        oc = oracle.Counter(k)
+        oc.count(seq, off)
+        assert np.array_equal(c.raw(), oc.raw())
+        assert int(c.raw()[0]) == 255
+        assert np.array_equal(c.spectrum(), oc.spectrum())
+
+
+def test_ragged_short_and_empty_reads(gpu, oracle):
+    br, ctx = gpu
+    rng = np.random.default_rng(5)
+    lens = [0, 1, 10, 11, 12, 31, 32, 33, 0, 64, 1000, 5, 0]
+    seq = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=sum(lens))]
+    off = np.zeros(len(lens) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum(lens)
+    reads = br.Reads.upload(ctx, seq, off)
+    d, o = reads.download()
+    assert np.array_equal(o, off) and np.array_equal(d, seq)
+    c = br.Counter(ctx, 11)
+    c.count(reads)
+    oc = oracle.Counter(11)
+    oc.count(seq, off)
+    assert np.array_equal(c.raw(), oc.raw())
+    # no reads at all
+    e = br.Reads.upload(ctx, np.empty(0, dtype=np.uint8), np.zeros(1, dtype=np.uint64))
+    d, o = e.download()
+    assert d.size == 0 and list(o) == [0]
+
+
+def test_any_byte_is_a_nucleotide(gpu, oracle):
+    """nuc2bit is (b >> 1) & 3 for every byte: N -> G, lower case like upper case."""
+    br, ctx = gpu
+    seq = np.frombuffer(b"ACGTNNacgtnRYKMacgtACGTNNNNACGTACGTAGCTAGCTAGGGATCGATCGNNNN", dtype=np.uint8)
+    off = np.array([0, seq.size], dtype=np.uint64)
+    c = br.Counter(ctx, 7)
+    c.count(br.Reads.upload(ctx, seq, off))
+    oc = oracle.Counter(7)
+    oc.count(seq, off)
+    assert np.array_equal(c.raw(), oc.raw())
+
+
+def test_k17_count_and_threshold_against_oracle(gpu, oracle):
+    """BASELINE config-2 shape at reduced size: k = 17 (8 GiB table, 1 GiB bitfield)."""
+    br, ctx = gpu
+    from br_b200 import synth
+
+    genome = synth.make_genome(200_000, seed=42)
+    seq, off, _ = synth.make_reads(genome, 20, 0.10, seed=43, mean_len=3000)
+    s = br.Pcon.from_reads(ctx, (seq, off), 17, abundance=2)
+    oc = oracle.Counter(17)
+    oc.count(seq, off, threads=8)
+    assert np.array_equal(s.spectrum(), oc.spectrum(threads=8))
+    ob = oc.to_solid(2, threads=8).bits()
+    gb = s.bitfield()
+    assert hashlib.sha256(gb.tobytes()).digest() == hashlib.sha256(ob.tobytes()).digest()
+    km = all_forward_kmers(seq[: int(off[20])], off[:21], 17)
+    assert np.array_equal(s.get_batch(km), oracle.Solid.from_bitfield(17, ob).get_batch(km))
