@@ -74,6 +74,7 @@ SIGNATURES = {
     "brgpu_profile_count": (C.c_int, [vp]),
     "brgpu_profile_get": (C.c_int, [vp, C.c_int, C.c_char_p, sz, C.POINTER(C.c_double), pu64, C.POINTER(C.c_double)]),
     "brgpu_launch_count": (u64, [vp]),
+    "brgpu_scan_lookups": (u64, [vp]),
 }
 
 
@@ -87,7 +88,7 @@ class BrgpuError(RuntimeError):
 def _load():
     if not _SO.exists():
         raise ImportError(
-            f"{_SO} is missing: build it with `python -m br_b200.build` (nvcc, sm_100a). "
+            f"{_SO} is missing: build it with `python br_b200/build.py` (nvcc, sm_100a). "
             "br_b200 has no CPU or pure-Python fallback."
         )
     lib = C.CDLL(str(_SO))

@@ -101,6 +101,35 @@ static inline uint64_t bits_alloc_bytes(int k) {
     return b < 16 ? 16 : b;
 }
 
+// cudaMalloc-backed allocations that may be exported over CUDA IPC (count table, bitfield)
+static cudaError_t big_alloc(brgpu_ctx *ctx, void **p, uint64_t bytes) {
+    for (size_t i = 0; i < ctx->big_cache.size(); i++)
+        if (ctx->big_cache[i].second == bytes) {
+            *p = ctx->big_cache[i].first;
+            ctx->big_cache.erase(ctx->big_cache.begin() + (long)i);
+            return cudaSuccess;
+        }
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess && !ctx->big_cache.empty()) { // make room and retry once
+        cudaGetLastError();
+        cudaStreamSynchronize(ctx->stream);
+        for (auto &c : ctx->big_cache) cudaFree(c.first);
+        ctx->big_cache.clear();
+        e = cudaMalloc(p, bytes);
+    }
+    return e;
+}
+
+static void big_free(brgpu_ctx *ctx, void *p, uint64_t bytes) {
+    if (!p) return;
+    if (ctx->big_cache.size() < 4) {
+        ctx->big_cache.emplace_back(p, bytes);
+        return;
+    }
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(p);
+}
+
 template <class T> static cudaError_t dalloc(brgpu_ctx *ctx, T **p, uint64_t count) {
     *p = nullptr;
     if (count == 0) count = 1;
@@ -167,6 +196,7 @@ extern "C" void brgpu_ctx_destroy(brgpu_ctx *ctx) {
             cudaEventDestroy(ev.second);
         }
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
+    for (auto &c : ctx->big_cache) cudaFree(c.first);
     if (ctx->d_flags) cudaFree(ctx->d_flags);
     if (ctx->d_hist) cudaFree(ctx->d_hist);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
@@ -384,7 +414,7 @@ extern "C" int brgpu_counts_create(brgpu_ctx *ctx, int k, brgpu_counts **out) {
     c->k = k;
     c->n = table_len(k);
     // plain cudaMalloc: the table is exported over CUDA IPC for the multi-GPU merge
-    cudaError_t e = cudaMalloc((void **)&c->d_counts, c->n < 64 ? 64 : c->n);
+    cudaError_t e = big_alloc(ctx, (void **)&c->d_counts, c->n < 64 ? 64 : c->n);
     if (e != cudaSuccess) {
         delete c;
         return fail(ctx, BRGPU_E_NOMEM, "device allocation (count table)", e);
@@ -400,8 +430,7 @@ extern "C" int brgpu_counts_create(brgpu_ctx *ctx, int k, brgpu_counts **out) {
 extern "C" void brgpu_counts_free(brgpu_counts *c) {
     if (!c) return;
     cudaSetDevice(c->ctx->device);
-    cudaStreamSynchronize(c->ctx->stream);
-    if (c->d_counts) cudaFree(c->d_counts);
+    big_free(c->ctx, c->d_counts, c->n < 64 ? 64 : c->n);
     delete c;
 }
 
@@ -474,7 +503,7 @@ static int set_alloc(brgpu_ctx *ctx, int k, brgpu_set **out) {
     s->ctx = ctx;
     s->k = k;
     s->n_bytes = table_len(k) >> 3;
-    cudaError_t e = cudaMalloc((void **)&s->d_bits, bits_alloc_bytes(k));
+    cudaError_t e = big_alloc(ctx, (void **)&s->d_bits, bits_alloc_bytes(k));
     if (e != cudaSuccess) {
         delete s;
         return fail(ctx, BRGPU_E_NOMEM, "device allocation (bitfield)", e);
@@ -486,8 +515,7 @@ static int set_alloc(brgpu_ctx *ctx, int k, brgpu_set **out) {
 extern "C" void brgpu_set_free(brgpu_set *s) {
     if (!s) return;
     cudaSetDevice(s->ctx->device);
-    cudaStreamSynchronize(s->ctx->stream);
-    if (s->d_bits) cudaFree(s->d_bits);
+    big_free(s->ctx, s->d_bits, bits_alloc_bytes(s->k));
     delete s;
 }
 
@@ -931,3 +959,15 @@ extern "C" int brgpu_profile_get(brgpu_ctx *ctx, int i, char *name_out, size_t n
 }
 
 extern "C" uint64_t brgpu_launch_count(const brgpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" uint64_t brgpu_scan_lookups(brgpu_ctx *ctx) {
+    if (!ctx) return 0;
+    cudaSetDevice(ctx->device);
+    if (cudaMemcpyAsync(ctx->h_pinned, ctx->d_flags + 2, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream) !=
+            cudaSuccess ||
+        cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return ctx->h_pinned[0];
+}

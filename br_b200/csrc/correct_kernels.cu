@@ -47,11 +47,21 @@ __global__ void __launch_bounds__(256)
             load_window(seq, sb, p0, prev, cur);
             int t_lo = p0 >= (uint32_t)(k - 1) ? 0 : (k - 1 - (int)p0);
             int t_hi = (L - p0) < 32u ? (int)(L - p0) : 32;
+            // 4 rounds of 8 independent sector gathers: the byte loads of a round are all issued
+            // before the first one is consumed, so every thread keeps 8 DRAM accesses in flight
 #pragma unroll
-            for (int t = 0; t < 32; t++) {
-                if (t >= t_lo && t < t_hi) {
-                    if (solid(bits, window_kmer(prev, cur, t, mask), k)) out |= 1u << t;
+            for (int g = 0; g < 32; g += 8) {
+                uint64_t idx[8];
+                uint32_t byte[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) idx[j] = canonical_index(window_kmer(prev, cur, g + j, mask), k);
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    byte[j] = 0;
+                    if (g + j >= t_lo && g + j < t_hi) byte[j] = __ldg(bits + (idx[j] >> 3));
                 }
+#pragma unroll
+                for (int j = 0; j < 8; j++) out |= ((byte[j] >> (idx[j] & 7)) & 1u) << (g + j);
             }
         }
         bitmap[w] = out;
@@ -87,7 +97,14 @@ struct Rd {
     uint32_t o;          // bytes produced so far (keeps counting past cap)
     uint32_t copy_from;  // input bytes [copy_from, i) are still to be copied to out
     uint8_t *scratch;    // per-warp scratch (Greedy)
+    mutable uint32_t n_get; // per lane: KmerSet::get calls issued by this lane (bookkeeping)
 };
+
+// KmerSet::get from the scan: one random sector of the bitfield, counted for the roofline report
+__device__ __forceinline__ bool lookup(const Rd &rd, uint64_t kmer) {
+    rd.n_get++;
+    return solid(rd.bits, kmer, rd.k);
+}
 
 // result of correct_error
 struct Corr {
@@ -149,12 +166,12 @@ __device__ __forceinline__ uint64_t push_seq(uint64_t kmer, const uint8_t *ptr, 
 // alt_nucs(y) == succ_mask(y >> 2) with the same push, because push masks the top base away.
 __device__ __forceinline__ uint32_t succ_mask(const Rd &rd, uint64_t x) {
     bool s = false;
-    if (rd.lane < 4) s = solid(rd.bits, push(x, (uint32_t)rd.lane, rd.mask), rd.k);
+    if (rd.lane < 4) s = lookup(rd, push(x, (uint32_t)rd.lane, rd.mask));
     return __ballot_sync(FULL, s) & 0xfu;
 }
 __device__ __forceinline__ uint32_t alt_mask(const Rd &rd, uint64_t weak) {
     bool s = false;
-    if (rd.lane < 4) s = solid(rd.bits, replace_last(weak, (uint32_t)rd.lane, rd.mask), rd.k);
+    if (rd.lane < 4) s = lookup(rd, replace_last(weak, (uint32_t)rd.lane, rd.mask));
     return __ballot_sync(FULL, s) & 0xfu;
 }
 __device__ __forceinline__ bool uniq(uint32_t m4, uint32_t &a) {
@@ -239,7 +256,7 @@ __device__ __forceinline__ uint32_t error_len(const Rd &rd, uint64_t kmer, uint3
     uint32_t nd = dr < sublen - 1 ? dr : sublen - 1; // pushes available: sub[1..sublen-1]
     if (nd > 0) {
         uint64_t km = push_window(rd, kmer, rd.in + i + 1, nd);
-        bool s = (uint32_t)rd.lane < nd && solid(rd.bits, km, rd.k);
+        bool s = (uint32_t)rd.lane < nd && lookup(rd, km);
         uint32_t m = __ballot_sync(FULL, s);
         if (m) {
             int l = __ffs(m) - 1;
@@ -386,7 +403,7 @@ __device__ __forceinline__ Corr exist_correct_error(Rd &rd, uint64_t kmer, uint3
             if (g == 1) { base = push(K0, sb[1], rd.mask); need = sublen >= 2; }
             if (g == 2) { base = push(K0, sb[2], rd.mask); need = sublen >= 3; }
             if (g == 3) { base = push(K0, sb[0], rd.mask); }
-            if (need) s = solid(rd.bits, push(base, (uint32_t)(rd.lane & 3), rd.mask), rd.k);
+            if (need) s = lookup(rd, push(base, (uint32_t)(rd.lane & 3), rd.mask));
         }
         uint32_t m = __ballot_sync(FULL, s);
         sc = scen_two(rd.lane, K0, sublen, sb, m & 0xf, (m >> 4) & 0xf, (m >> 8) & 0xf, (m >> 12) & 0xf, rd.mask);
@@ -416,14 +433,14 @@ __device__ __forceinline__ Corr exist_correct_error(Rd &rd, uint64_t kmer, uint3
         if (u <= c) {
             // u = 0: get(K) (exist/mod.rs:23); u = 1..c: the c confirmations (:35-43)
             uint64_t km = push_seq(K, sub + offa, u, rd.mask);
-            if (!solid(rd.bits, km, rd.k)) bad |= 1u << s;
+            if (!lookup(rd, km)) bad |= 1u << s;
         } else {
             // one_more (exist/mod.rs:49-70): uses correct()'s bases and offset, tests one k-mer
             if (sublen > c + offc + 1) {
                 uint64_t km = K0 >> 2;
                 for (int e = (int)ne - 1; e >= 0; e--) km = push(km, (codes >> (2 * e)) & 3u, rd.mask);
                 km = push_seq(km, sub + offc, c + 1, rd.mask);
-                if (solid(rd.bits, km, rd.k)) more |= 1u << s;
+                if (lookup(rd, km)) more |= 1u << s;
             }
         }
     }
@@ -852,7 +869,7 @@ __device__ __forceinline__ Corr greedy_correct_error(Rd &rd, uint64_t kmer, uint
                     uint32_t v = v0 + (uint32_t)rd.lane;
                     if (v < nb_validate) {
                         uint64_t km = push_seq(x, sub + s, v + 1, rd.mask);
-                        if (!solid(rd.bits, km, rd.k)) bad = true;
+                        if (!lookup(rd, km)) bad = true;
                     }
                 }
                 ok = !__any_sync(FULL, bad);
@@ -911,7 +928,7 @@ __device__ __forceinline__ void correct_read(Rd &rd, const CorrectParams &p) {
             if (n > d) n = d;
             if (n > 32) n = 32;
             uint64_t km = push_window(rd, kmer, rd.in + i, n);
-            bool s = (uint32_t)rd.lane < n && solid(rd.bits, km, rd.k);
+            bool s = (uint32_t)rd.lane < n && lookup(rd, km);
             uint32_t gm = __ballot_sync(FULL, s);
             uint32_t vm = n == 32 ? 0xffffffffu : ((1u << n) - 1u);
             uint32_t trig = ~gm & ((gm << 1) | (previous ? 1u : 0u)) & vm; // mod.rs:73
@@ -970,6 +987,7 @@ __global__ void __launch_bounds__(SCAN_WARPS_PER_BLOCK * 32)
     rd.mask = kmask(p.k);
     rd.lane = lane;
     rd.scratch = scratch ? scratch + (size_t)warp * scratch_per_warp : nullptr;
+    rd.n_get = 0;
     for (;;) {
         uint32_t qi = 0;
         if (lane == 0) qi = atomicAdd(flags + 0, 1u);
@@ -989,6 +1007,8 @@ __global__ void __launch_bounds__(SCAN_WARPS_PER_BLOCK * 32)
             if (rd.o > rd.cap) atomicOr(flags + 1, 1u);
         }
     }
+    uint32_t gets = __reduce_add_sync(FULL, rd.n_get);
+    if (lane == 0 && gets) atomicAdd(reinterpret_cast<unsigned long long *>(flags + 2), (unsigned long long)gets);
 }
 
 int scan_grid_warps(brgpu_ctx *ctx) { return ctx->sm_count * 8 * SCAN_WARPS_PER_BLOCK; }

@@ -37,6 +37,9 @@ struct brgpu_ctx {
     uint32_t *d_flags = nullptr; // [0] work-queue cursor, [1] overflow flag, [2..] spare
     uint64_t *d_hist = nullptr;  // 256 bins
     uint64_t *h_pinned = nullptr; // 512 x u64 pinned staging for small readbacks
+    // freed count tables / bitfields kept for the next call (cudaMalloc of GiBs costs ms and
+    // cudaFree synchronises the device); reuse is ordered by the context's stream
+    std::vector<std::pair<void *, uint64_t>> big_cache;
 };
 
 namespace brgpu {

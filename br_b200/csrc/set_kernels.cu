@@ -335,6 +335,10 @@ __global__ void __launch_bounds__(256)
         } else {
 #pragma unroll
             for (int j = 0; j < 4; j++) {
+                if (w[j] == 0) { // sparse tables: most words next to a hit are still empty
+                    c0 += 4;
+                    continue;
+                }
                 uint32_t z0 = __vcmpeq4(w[j], 0u), z1 = __vcmpeq4(w[j], 0x01010101u);
                 uint32_t z2 = __vcmpeq4(w[j], 0x02020202u), z3 = __vcmpeq4(w[j], 0x03030303u);
                 c0 += __popc(z0) >> 3;

@@ -1,0 +1,159 @@
+"""Multi-GPU plumbing: one process per GPU, reads sharded by record, one exchange step.
+
+Part 1 shards like this: every rank counts its own reads into a private full-size
+table; the index space is cut into `world` slices; rank r merges slice r of all tables with a
+saturating add, reading the peers' slices straight over NVLink (CUDA-IPC mapped peer memory, a
+hand-written kernel — NCCL has no saturating u8 sum); the 256-bin spectra are all-reduced when the
+threshold is data-derived; every rank thresholds its slice and the bitfield slices are
+all-gathered with NCCL so each GPU ends up with the full replicated bitfield.  Part 2 needs no
+communication: each rank corrects its own reads against its replica.
+
+The protocol is written against a small `ops` object so that the same code runs on the GPUs
+(`GpuOps`, C ABI + torch.distributed/NCCL) and in the CPU test-suite (a numpy fake over gloo).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, lib
+
+
+def slice_bounds(n, world, rank):
+    """Slice `rank` of [0, n) cut into `world` 1024-aligned pieces (last one takes the rest)."""
+    per = (n // world) & ~1023
+    if per == 0:
+        return (0, n) if rank == 0 else (n, n)
+    b = per * rank
+    e = n if rank == world - 1 else per * (rank + 1)
+    return b, e
+
+
+def shard_records(offsets, world, rank):
+    """Contiguous record range for `rank`, balanced by bases (prefix sum over lengths)."""
+    off = np.asarray(offsets, dtype=np.uint64)
+    n = off.size - 1
+    total = int(off[-1]) - int(off[0])
+    lo = int(np.searchsorted(off - off[0], np.uint64(total * rank // world), side="left"))
+    hi = int(np.searchsorted(off - off[0], np.uint64(total * (rank + 1) // world), side="left")) if rank < world - 1 else n
+    return min(lo, n), min(hi, n)
+
+
+def build_set_sharded(ops, k, abundance=None, abundance_selection=None):
+    """Runs the exchange protocol; returns whatever `ops.finish()` returns (the replicated set)."""
+    world, rank = ops.world, ops.rank
+    n = 1 << (2 * k - 1)
+    begin, end = slice_bounds(n, world, rank)
+    ops.count_local(k)                       # private table, own shard
+    handles = ops.exchange_handles()         # all-gather of the 64-byte IPC handles
+    ops.barrier()                            # every table is complete before anyone reads it
+    ops.merge_slice(handles, begin, end)     # saturating reduce of slice `rank` over NVLink
+    if abundance is None:
+        if abundance_selection not in ("first-minimum", "first_minimum"):
+            raise ValueError("need an abundance threshold or an abundance method")
+        hist = ops.spectrum_slice(begin, end)
+        hist = ops.all_reduce_sum(hist)      # 2 KiB
+        abundance = ops.first_minimum(hist)
+        if abundance is None:
+            raise RuntimeError("can't compute the abundance threshold")
+    ops.threshold_slice(int(abundance), begin, end)
+    ops.all_gather_bitfield(begin, end)      # NCCL all-gather of the bitfield slices
+    ops.barrier()                            # peers are done reading this rank's table
+    return ops.finish(int(abundance))
+
+
+class _CudaArray:
+    """Zero-copy view of library-owned device memory for torch (__cuda_array_interface__)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+class GpuOps:
+    """The protocol's steps on a real GPU: C ABI for the kernels, torch.distributed for the
+    plumbing (handle exchange, barriers, the tiny all-reduce, the bitfield all-gather)."""
+
+    def __init__(self, ctx, reads, group=None):
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist = torch, dist
+        self.ctx, self.reads, self.group = ctx, reads, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.counter = None
+        self.set = None
+        self._peers = []
+
+    def count_local(self, k):
+        from .set import Counter, Pcon
+
+        self.k = k
+        self.counter = Counter(self.ctx, k)
+        self.counter.count(self.reads)
+        self.set = Pcon.new(self.ctx, k)
+
+    def exchange_handles(self):
+        h = (C.c_uint8 * 64)()
+        check(lib.brgpu_counts_ipc_export(self.counter._h, h), self.ctx._h)
+        mine = self.torch.tensor(list(h), dtype=self.torch.uint8, device=f"cuda:{self.ctx.device}")
+        allh = [self.torch.empty_like(mine) for _ in range(self.world)]
+        self.dist.all_gather(allh, mine, group=self.group)
+        return [bytes(t.cpu().tolist()) for t in allh]
+
+    def barrier(self):
+        self.ctx.synchronize()
+        self.dist.barrier(group=self.group)
+
+    def merge_slice(self, handles, begin, end):
+        ptrs = []
+        for r, hb in enumerate(handles):
+            if r == self.rank:
+                continue
+            p = C.c_void_p()
+            check(lib.brgpu_ipc_open(self.ctx._h, (C.c_uint8 * 64).from_buffer_copy(hb), C.byref(p)), self.ctx._h)
+            ptrs.append(p)
+        self._peers = ptrs
+        arr = (C.c_void_p * max(1, len(ptrs)))(*[p.value for p in ptrs])
+        check(lib.brgpu_counts_merge_slice(self.counter._h, arr, len(ptrs), begin, end), self.ctx._h)
+
+    def spectrum_slice(self, begin, end):
+        h = np.zeros(256, dtype=np.uint64)
+        check(lib.brgpu_counts_spectrum_slice(self.counter._h, begin, end, h.ctypes.data_as(C.c_void_p)), self.ctx._h)
+        return h
+
+    def all_reduce_sum(self, hist):
+        t = self.torch.from_numpy(hist.astype(np.int64)).to(f"cuda:{self.ctx.device}")
+        self.dist.all_reduce(t, group=self.group)
+        return t.cpu().numpy().astype(np.uint64)
+
+    @staticmethod
+    def first_minimum(hist):
+        from .set import Counter
+
+        return Counter.first_minimum(hist)
+
+    def threshold_slice(self, abundance, begin, end):
+        check(lib.brgpu_set_threshold_slice(self.set._h, self.counter._h, abundance, begin, end), self.ctx._h)
+
+    def all_gather_bitfield(self, begin, end):
+        n_bytes = lib.brgpu_set_bitfield_bytes(self.set._h)
+        ptr = lib.brgpu_set_device_ptr(self.set._h)
+        full = self.torch.as_tensor(_CudaArray(ptr, n_bytes), device=f"cuda:{self.ctx.device}")
+        per = (end - begin) // 8
+        if self.world == 1:
+            return
+        bounds = [slice_bounds(1 << (2 * self.k - 1), self.world, r) for r in range(self.world)]
+        if all((e - b) // 8 == per for b, e in bounds):
+            mine = full[begin // 8 : end // 8].clone()
+            self.dist.all_gather_into_tensor(full, mine, group=self.group)
+        else:  # ragged last slice: broadcast slice by slice
+            for r, (b, e) in enumerate(bounds):
+                self.dist.broadcast(full[b // 8 : e // 8], src=self.dist.get_global_rank(self.group, r) if self.group else r,
+                                    group=self.group)
+
+    def finish(self, abundance):
+        for p in self._peers:
+            check(lib.brgpu_ipc_close(self.ctx._h, p), self.ctx._h)
+        self._peers = []
+        self.counter.free()
+        return self.set

@@ -80,6 +80,11 @@ class Context:
     def launch_count(self):
         return lib.brgpu_launch_count(self._h)
 
+    @property
+    def scan_lookups(self):
+        """KmerSet::get calls issued by the correction scans so far (bookkeeping for the roofline)."""
+        return lib.brgpu_scan_lookups(self._h)
+
 
 class Reads:
     """A chunk of records resident in HBM (the 8192-record buffer of src/lib.rs:90, any size)."""

@@ -173,6 +173,9 @@ int brgpu_profile_count(brgpu_ctx *ctx);
 int brgpu_profile_get(brgpu_ctx *ctx, int i, char *name_out, size_t name_cap, double *ms, uint64_t *launches,
                       double *algo_bytes);
 uint64_t brgpu_launch_count(const brgpu_ctx *ctx); /* kernels launched since ctx creation */
+/* KmerSet::get calls issued by the correction scans since ctx creation (excludes the one
+ * lookup per base of the bitmap pass); syncs the stream */
+uint64_t brgpu_scan_lookups(brgpu_ctx *ctx);
 
 #ifdef __cplusplus
 }
