@@ -512,9 +512,52 @@ static int set_alloc(brgpu_ctx *ctx, int k, brgpu_set **out) {
     return BRGPU_OK;
 }
 
+// summary geometry: one bit per 2^shift bitfield bits, at most 32 MiB, only for bitfields that
+// do not fit in L2 anyway (k >= 15)
+static void summary_geometry(int k, int *shift, uint64_t *bytes) {
+    uint64_t n_bytes = table_len(k) >> 3;
+    if (n_bytes <= (8ULL << 20)) {
+        *shift = 0;
+        *bytes = 0;
+        return;
+    }
+    int sh = 5;
+    while (((n_bytes << 3) >> sh) / 8 > (32ULL << 20)) sh++;
+    *shift = sh;
+    *bytes = (((n_bytes << 3) >> sh) + 7) / 8;
+}
+
+// (re)build the occupancy summary if the bitfield changed since the last build
+static int ensure_summary(brgpu_set *s) {
+    brgpu_ctx *ctx = s->ctx;
+    if (s->summary_valid) return BRGPU_OK;
+    int shift;
+    uint64_t bytes;
+    summary_geometry(s->k, &shift, &bytes);
+    if (bytes == 0) {
+        s->summary_valid = true;
+        return BRGPU_OK;
+    }
+    if (!s->d_summary) {
+        cudaError_t e = big_alloc(ctx, (void **)&s->d_summary, bytes);
+        if (e != cudaSuccess) return fail(ctx, BRGPU_E_NOMEM, "device allocation (summary)", e);
+        s->summary_bytes = bytes;
+        s->summary_shift = shift;
+    }
+    launch_build_summary(ctx, s->d_bits, s->n_bytes, shift, s->d_summary);
+    CK(cudaGetLastError());
+    s->summary_valid = true;
+    return BRGPU_OK;
+}
+
+static SetView set_view(const brgpu_set *s) {
+    return SetView{s->d_bits, s->summary_bytes ? s->d_summary : nullptr, s->summary_shift, s->k};
+}
+
 extern "C" void brgpu_set_free(brgpu_set *s) {
     if (!s) return;
     cudaSetDevice(s->ctx->device);
+    if (s->d_summary) big_free(s->ctx, s->d_summary, s->summary_bytes);
     big_free(s->ctx, s->d_bits, bits_alloc_bytes(s->k));
     delete s;
 }
@@ -551,14 +594,116 @@ extern "C" int brgpu_set_from_counts(brgpu_counts *c, int abundance, brgpu_set *
     return BRGPU_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// Bucketed set construction (k >= 15): partition the k-mers by table-index range (2^15 counters
+// per bucket), count every bucket in shared memory, emit spectrum + bitfield + summary.  Same
+// result as the table path, without the table and without a host round trip (set_kernels.cu).
+// ------------------------------------------------------------------------------------------
+static const int BUCKET_BITS_HOST = 15; // must match BUCKET_BITS in set_kernels.cu
+
+static bool bucketed_applicable(int k, const brgpu_reads *reads) {
+    if (k < 15) return false; // small tables are cache resident: the literal path is fine
+    return reads->layout->total_slots < 0xffffffffULL && reads->layout->n > 0; // u32 bucket cursors
+}
+
+static void summary_geometry(int k, int *shift, uint64_t *bytes);
+
+static int set_from_reads_bucketed(brgpu_ctx *ctx, int k, int abundance, int selection, const brgpu_reads *reads,
+                                   brgpu_set **out) {
+    const Layout &L = *reads->layout;
+    const uint64_t n_buckets = table_len(k) >> BUCKET_BITS_HOST;
+    const double n_kmers = (double)reads->sum_len;
+    uint32_t *d_fill = nullptr;
+    uint64_t *d_base = nullptr, *d_tmp = nullptr;
+    uint16_t *d_res = nullptr;
+    brgpu_set *s = nullptr;
+    int st = BRGPU_OK;
+    cudaError_t e = cudaSuccess;
+    auto cleanup = [&]() {
+        if (d_fill) cudaFreeAsync(d_fill, ctx->stream);
+        if (d_base) cudaFreeAsync(d_base, ctx->stream);
+        if (d_tmp) cudaFreeAsync(d_tmp, ctx->stream);
+        if (d_res) cudaFreeAsync(d_res, ctx->stream);
+    };
+    // every k-mer starts at a distinct slot position, so total_slots bounds their number
+    if ((e = dalloc(ctx, &d_fill, n_buckets)) != cudaSuccess || (e = dalloc(ctx, &d_base, n_buckets + 1)) != cudaSuccess ||
+        (e = dalloc(ctx, &d_tmp, n_buckets / 4096 + 4)) != cudaSuccess ||
+        (e = dalloc(ctx, &d_res, L.total_slots)) != cudaSuccess) {
+        cleanup();
+        return fail(ctx, BRGPU_E_NOMEM, "device allocation (bucketed counting)", e);
+    }
+    launch_bucket_partition(ctx, L, reads->d_seq, reads->d_len, k, n_buckets, d_fill, d_base, d_tmp, d_res, n_kmers);
+    st = set_alloc(ctx, k, &s);
+    if (st != BRGPU_OK) {
+        cleanup();
+        return st;
+    }
+    int shift;
+    uint64_t sbytes;
+    summary_geometry(k, &shift, &sbytes);
+    if (sbytes && shift == 5) {
+        e = big_alloc(ctx, (void **)&s->d_summary, sbytes);
+        if (e != cudaSuccess) {
+            cleanup();
+            brgpu_set_free(s);
+            return fail(ctx, BRGPU_E_NOMEM, "device allocation (summary)", e);
+        }
+        s->summary_bytes = sbytes;
+        s->summary_shift = shift;
+    }
+    auto read_hist = [&](uint64_t hist[256]) -> cudaError_t {
+        cudaError_t e2 = cudaMemcpyAsync(ctx->h_pinned, ctx->d_hist, 256 * sizeof(uint64_t), cudaMemcpyDeviceToHost,
+                                         ctx->stream);
+        if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(ctx->stream);
+        if (e2 == cudaSuccess) memcpy(hist, ctx->h_pinned, 256 * sizeof(uint64_t));
+        return e2;
+    };
+    uint64_t hist[256];
+    if (selection == BRGPU_ABUNDANCE_FIRST_MINIMUM) {
+        // the threshold depends on the spectrum: one counting sweep without output first
+        cudaMemsetAsync(ctx->d_hist, 0, 256 * sizeof(uint64_t), ctx->stream);
+        launch_bucket_count(ctx, d_res, d_base, n_buckets, 0, nullptr, nullptr, 0, ctx->d_hist, n_kmers);
+        e = read_hist(hist);
+        if (e == cudaSuccess) {
+            abundance = brgpu_spectrum_first_minimum(hist);
+            if (abundance < 0) st = fail(ctx, BRGPU_E_NO_THRESHOLD, "can't compute the abundance threshold");
+        }
+    }
+    if (e == cudaSuccess && st == BRGPU_OK) {
+        cudaMemsetAsync(ctx->d_hist, 0, 256 * sizeof(uint64_t), ctx->stream);
+        launch_bucket_count(ctx, d_res, d_base, n_buckets, abundance, s->d_bits, s->d_summary, s->summary_shift,
+                            ctx->d_hist, n_kmers);
+        e = read_hist(hist);
+    }
+    if (e == cudaSuccess) e = cudaGetLastError();
+    cleanup();
+    if (e != cudaSuccess) st = fail(ctx, BRGPU_E_CUDA, "bucketed counting", e);
+    if (st != BRGPU_OK) {
+        brgpu_set_free(s);
+        return st;
+    }
+    s->abundance = abundance;
+    s->summary_valid = s->d_summary != nullptr; // written by the counting sweep itself
+    memcpy(s->hist, hist, sizeof(hist));
+    *out = s;
+    return BRGPU_OK;
+}
+
 extern "C" int brgpu_set_from_reads(brgpu_ctx *ctx, int k, int abundance, int selection, const brgpu_reads *reads,
                                     brgpu_set **out) {
     if (!ctx || !out || !reads) return BRGPU_E_INVALID;
     *out = nullptr;
+    if (!k_supported(k)) return fail(ctx, BRGPU_E_INVALID, "k must be odd and in 3..=19");
     if (selection == BRGPU_ABUNDANCE_EXPLICIT && abundance < 0)
         return fail(ctx, BRGPU_E_NEED_ABUNDANCE, "need an abundance threshold or an abundance method");
     if (selection != BRGPU_ABUNDANCE_EXPLICIT && selection != BRGPU_ABUNDANCE_FIRST_MINIMUM)
         return fail(ctx, BRGPU_E_INVALID, "unknown abundance selection");
+    if (selection == BRGPU_ABUNDANCE_EXPLICIT && abundance > 255)
+        return fail(ctx, BRGPU_E_INVALID, "abundance must be in 0..=255");
+    if (reads->ctx != ctx) return fail(ctx, BRGPU_E_INVALID, "reads belong to another context");
+    cudaSetDevice(ctx->device);
+    if (bucketed_applicable(k, reads)) return set_from_reads_bucketed(ctx, k, abundance, selection, reads, out);
+    // table path: Counter::new + count_fasta + Spectrum + Solid::from_count, literally
     brgpu_counts *c = nullptr;
     int st = brgpu_counts_create(ctx, k, &c);
     if (st != BRGPU_OK) return st;
@@ -626,6 +771,7 @@ extern "C" int brgpu_set_insert_batch(brgpu_set *s, const uint64_t *kmers_host, 
     uint64_t *d_k = nullptr;
     CK(dalloc(ctx, &d_k, n));
     CK(cudaMemcpyAsync(d_k, kmers_host, n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    s->summary_valid = false;
     launch_insert_batch(ctx, s->d_bits, s->k, d_k, n);
     cudaFreeAsync(d_k, ctx->stream);
     CK(cudaGetLastError());
@@ -636,7 +782,11 @@ extern "C" int brgpu_set_insert_batch(brgpu_set *s, const uint64_t *kmers_host, 
 extern "C" int brgpu_set_k(const brgpu_set *s) { return s ? s->k : 0; }
 extern "C" int brgpu_set_abundance(const brgpu_set *s) { return s ? s->abundance : -1; }
 extern "C" uint64_t brgpu_set_bitfield_bytes(const brgpu_set *s) { return s ? s->n_bytes : 0; }
-extern "C" void *brgpu_set_device_ptr(brgpu_set *s) { return s ? s->d_bits : nullptr; }
+extern "C" void *brgpu_set_device_ptr(brgpu_set *s) {
+    if (!s) return nullptr;
+    s->summary_valid = false; // the caller may write through the pointer (bitfield all-gather)
+    return s->d_bits;
+}
 
 extern "C" int brgpu_set_export_bitfield(brgpu_set *s, uint8_t *out_host, uint64_t cap) {
     if (!s || !out_host) return BRGPU_E_INVALID;
@@ -695,6 +845,7 @@ static int correct_attempt(brgpu_ctx *ctx, const brgpu_set *set, const uint8_t *
     uint32_t *len[2] = {nullptr, nullptr};
     uint32_t *d_bitmap = nullptr;
     uint8_t *d_scratch = nullptr;
+    ScanWork work;
     cudaError_t e = cudaSuccess;
     auto cleanup = [&]() {
         for (int b = 0; b < 2; b++) {
@@ -703,6 +854,11 @@ static int correct_attempt(brgpu_ctx *ctx, const brgpu_set *set, const uint8_t *
         }
         if (d_bitmap) cudaFreeAsync(d_bitmap, ctx->stream);
         if (d_scratch) cudaFreeAsync(d_scratch, ctx->stream);
+        if (work.d_n_seg) cudaFreeAsync(work.d_n_seg, ctx->stream);
+        if (work.d_seg_first) cudaFreeAsync(work.d_seg_first, ctx->stream);
+        if (work.d_scan_tmp) cudaFreeAsync(work.d_scan_tmp, ctx->stream);
+        if (work.d_seg_out) cudaFreeAsync(work.d_seg_out, ctx->stream);
+        if (work.d_seg_recs) cudaFreeAsync(work.d_seg_recs, ctx->stream);
     };
     size_t scratch_per_warp = 0;
     for (uint64_t i = 0; i < n_methods; i++) {
@@ -716,6 +872,15 @@ static int correct_attempt(brgpu_ctx *ctx, const brgpu_set *set, const uint8_t *
     }
     if (e == cudaSuccess) e = dalloc(ctx, &d_bitmap, L.total_slots >> 5);
     if (e == cudaSuccess && scratch_per_warp) e = dalloc(ctx, &d_scratch, scratch_per_warp * (size_t)n_warps);
+    if (e == cudaSuccess && n_methods) {
+        e = dalloc(ctx, &work.d_n_seg, n);
+        if (e == cudaSuccess) e = dalloc(ctx, &work.d_seg_first, n + 1);
+        if (e == cudaSuccess) e = dalloc(ctx, &work.d_scan_tmp, n / 4096 + 4);
+        if (e == cudaSuccess) e = dalloc(ctx, &work.d_seg_out, (uint64_t)scan_seg_out_bytes(L));
+        uint8_t *recs = nullptr;
+        if (e == cudaSuccess) e = dalloc(ctx, &recs, (uint64_t)scan_seg_rec_bytes(L));
+        work.d_seg_recs = recs;
+    }
     if (e != cudaSuccess) {
         cleanup();
         return fail(ctx, BRGPU_E_NOMEM, "device allocation (correction buffers)", e);
@@ -728,9 +893,9 @@ static int correct_attempt(brgpu_ctx *ctx, const brgpu_set *set, const uint8_t *
     auto run_methods = [&]() {
         for (uint64_t i = 0; i < n_methods; i++) {
             CorrectParams p{set->k, methods[i], confirm, max_search};
-            launch_solid_bitmap(ctx, L, src, src_len, set->d_bits, set->k, d_bitmap, (double)in->sum_len);
-            launch_scan(ctx, L, src, src_len, buf[nxt], len[nxt], d_bitmap, set->d_bits, p, d_scratch, scratch_per_warp,
-                        n_warps, (double)in->sum_len);
+            launch_solid_bitmap(ctx, L, src, src_len, set_view(set), d_bitmap, (double)in->sum_len);
+            launch_scan(ctx, L, src, src_len, buf[nxt], len[nxt], d_bitmap, set_view(set), p, d_scratch,
+                        scratch_per_warp, n_warps, work, (double)in->sum_len);
             src = buf[nxt];
             src_len = len[nxt];
             nxt ^= 1;
@@ -814,6 +979,8 @@ extern "C" int brgpu_correct_reads(brgpu_ctx *ctx, const brgpu_set *set, const u
     int st = validate_methods(ctx, methods, n_methods, confirm, max_search);
     if (st != BRGPU_OK) return st;
     cudaSetDevice(ctx->device);
+    st = ensure_summary(const_cast<brgpu_set *>(set));
+    if (st != BRGPU_OK) return st;
 
     const brgpu_reads *cur = in;
     brgpu_reads *owned = nullptr;
@@ -915,6 +1082,7 @@ extern "C" int brgpu_set_threshold_slice(brgpu_set *s, brgpu_counts *c, int abun
         return fail(ctx, BRGPU_E_INVALID, "slice must be 1024-aligned");
     cudaSetDevice(ctx->device);
     s->abundance = abundance;
+    s->summary_valid = false;
     return run_spectrum(ctx, c->d_counts, begin, end, s->d_bits, abundance, nullptr);
 }
 

@@ -33,7 +33,9 @@ namespace brgpu {
 __global__ void __launch_bounds__(256)
     solid_bitmap_kernel(const uint8_t *__restrict__ seq, const uint32_t *__restrict__ len,
                         const uint64_t *__restrict__ slot_off, const uint32_t *__restrict__ word2read,
-                        uint64_t n_words, int k, const uint8_t *__restrict__ bits, uint32_t *__restrict__ bitmap) {
+                        uint64_t n_words, SolidView set, uint32_t *__restrict__ bitmap) {
+    const int k = set.k;
+    const uint8_t *__restrict__ bits = set.bits;
     const uint64_t mask = kmask(k);
     for (uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < n_words;
          w += (uint64_t)gridDim.x * blockDim.x) {
@@ -47,18 +49,33 @@ __global__ void __launch_bounds__(256)
             load_window(seq, sb, p0, prev, cur);
             int t_lo = p0 >= (uint32_t)(k - 1) ? 0 : (k - 1 - (int)p0);
             int t_hi = (L - p0) < 32u ? (int)(L - p0) : 32;
-            // 4 rounds of 8 independent sector gathers: the byte loads of a round are all issued
-            // before the first one is consumed, so every thread keeps 8 DRAM accesses in flight
+            // 4 rounds of 8 independent gathers: all loads of a round are issued before the first
+            // one is consumed.  Round part 1 asks the L2-resident summary; only k-mers whose block
+            // is occupied go on to the bitfield byte in HBM (part 2).
 #pragma unroll
             for (int g = 0; g < 32; g += 8) {
                 uint64_t idx[8];
                 uint32_t byte[8];
+                bool go[8];
 #pragma unroll
-                for (int j = 0; j < 8; j++) idx[j] = canonical_index(window_kmer(prev, cur, g + j, mask), k);
+                for (int j = 0; j < 8; j++) {
+                    idx[j] = canonical_index(window_kmer(prev, cur, g + j, mask), k);
+                    go[j] = g + j >= t_lo && g + j < t_hi;
+                }
+                if (set.summary) {
+                    uint32_t sw[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        sw[j] = 0;
+                        if (go[j]) sw[j] = __ldg(set.summary + (idx[j] >> (set.shift + 5)));
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; j++) go[j] = (sw[j] >> ((idx[j] >> set.shift) & 31)) & 1u;
+                }
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
                     byte[j] = 0;
-                    if (g + j >= t_lo && g + j < t_hi) byte[j] = __ldg(bits + (idx[j] >> 3));
+                    if (go[j]) byte[j] = __ldg(bits + (idx[j] >> 3));
                 }
 #pragma unroll
                 for (int j = 0; j < 8; j++) out |= ((byte[j] >> (idx[j] & 7)) & 1u) << (g + j);
@@ -69,7 +86,7 @@ __global__ void __launch_bounds__(256)
 }
 
 void launch_solid_bitmap(brgpu_ctx *ctx, const Layout &L, const uint8_t *d_seq, const uint32_t *d_len,
-                         const uint8_t *d_bits, int k, uint32_t *d_bitmap, double n_bases_hint) {
+                         const SetView &set, uint32_t *d_bitmap, double n_bases_hint) {
     uint64_t n_words = L.total_slots >> 5;
     if (!n_words) return;
     // algorithmic bytes per position: 32 B sector + 1 B ASCII in + 1/8 B bit out
@@ -77,7 +94,7 @@ void launch_solid_bitmap(brgpu_ctx *ctx, const Layout &L, const uint8_t *d_seq, 
     uint64_t need = (n_words + 255) / 256;
     uint64_t capb = (uint64_t)ctx->sm_count * 8;
     solid_bitmap_kernel<<<(unsigned)(need < capb ? need : capb), 256, 0, ctx->stream>>>(
-        d_seq, d_len, L.d_slot_off, L.d_word2read, n_words, k, d_bits, d_bitmap);
+        d_seq, d_len, L.d_slot_off, L.d_word2read, n_words, SolidView{set.bits, set.summary, set.shift, set.k}, d_bitmap);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -90,7 +107,7 @@ struct Rd {
     uint8_t *out;        // output slot
     uint32_t cap;        // output capacity
     const uint32_t *bm;  // phase-A bitmap of this read (bit p = solid(k-mer ending at p))
-    const uint8_t *bits; // the solid set
+    SolidView set;       // the solid set (bitfield + L2 summary)
     int k;
     uint64_t mask;
     int lane;
@@ -98,12 +115,54 @@ struct Rd {
     uint32_t copy_from;  // input bytes [copy_from, i) are still to be copied to out
     uint8_t *scratch;    // per-warp scratch (Greedy)
     mutable uint32_t n_get; // per lane: KmerSet::get calls issued by this lane (bookkeeping)
+    // cached 1024-position window of the phase-A bitmap: lane l holds word bm_base + l (per lane)
+    uint32_t bm_w;
+    uint32_t bm_base;    // 0xffffffff: nothing cached
+    // 64 input bases around the current event, 2-bit packed, first base in the top pair of w0;
+    // every lane holds the same copy, so a lane can cut out any sub-sequence with shifts alone
+    uint64_t w0, w1;
+    uint32_t w_origin;   // input position of the first base of the window; 0xffffffff: none
 };
+
+// (Re)load the 64-base window starting at input position `origin`.
+__device__ __forceinline__ void load_win(Rd &rd, uint32_t origin) {
+    uint32_t a = origin + (uint32_t)rd.lane, b = a + 32u;
+    uint64_t c0 = a < rd.len ? (uint64_t)nuc2bit(rd.in[a]) << (2 * (31 - rd.lane)) : 0ULL;
+    uint64_t c1 = b < rd.len ? (uint64_t)nuc2bit(rd.in[b]) << (2 * (31 - rd.lane)) : 0ULL;
+    rd.w0 = warp_or64(c0);
+    rd.w1 = warp_or64(c1);
+    rd.w_origin = origin;
+}
+
+// does the window hold input positions [pos, pos + n)?
+__device__ __forceinline__ bool win_covers(const Rd &rd, uint32_t pos, uint32_t n) {
+    return rd.w_origin != 0xffffffffu && pos >= rd.w_origin && pos + n <= rd.w_origin + 64u;
+}
+
+// the n (<= 32) 2-bit codes of input positions [pos, pos + n), first base most significant
+__device__ __forceinline__ uint64_t win_extract(const Rd &rd, uint32_t pos, uint32_t n) {
+    if (n == 0) return 0ULL;
+    const uint32_t off = pos - rd.w_origin, e = off + n;
+    uint64_t v;
+    if (e <= 32u)
+        v = rd.w0 >> (2 * (32u - e));
+    else if (off >= 32u)
+        v = rd.w1 >> (2 * (64u - e));
+    else
+        v = (rd.w0 << (2 * (e - 32u))) | (rd.w1 >> (2 * (64u - e)));
+    return n >= 32u ? v : (v & ((1ULL << (2 * n)) - 1ULL));
+}
+
+// `kmer` after pushing the input bases [pos, pos + n) taken from the window
+__device__ __forceinline__ uint64_t win_push(const Rd &rd, uint64_t kmer, uint32_t pos, uint32_t n) {
+    uint64_t hi = n < 32u ? (kmer << (2 * n)) : 0ULL;
+    return (hi | win_extract(rd, pos, n)) & rd.mask;
+}
 
 // KmerSet::get from the scan: one random sector of the bitfield, counted for the roofline report
 __device__ __forceinline__ bool lookup(const Rd &rd, uint64_t kmer) {
     rd.n_get++;
-    return solid(rd.bits, kmer, rd.k);
+    return solid(rd.set, kmer);
 }
 
 // result of correct_error
@@ -179,15 +238,28 @@ __device__ __forceinline__ bool uniq(uint32_t m4, uint32_t &a) {
     return __popc(m4) == 1;
 }
 
-// First position j in [i, len) with !S[j] && P[j], where S is the phase-A bitmap, P[j] = S[j-1]
-// for j > i and P[i] = previous.  Returns len when there is none.
-__device__ __forceinline__ uint32_t find_transition(const Rd &rd, uint32_t i, bool previous) {
+// First position j in [i, end) with !S[j] && P[j], where S is the phase-A bitmap, P[j] = S[j-1]
+// for j > i and P[i] = previous.  Returns end when there is none (end <= len).
+__device__ __forceinline__ uint32_t find_transition(Rd &rd, uint32_t i, bool previous, uint32_t end) {
+    if (i >= end) return end;
     uint32_t wbase = i >> 5;
-    const uint32_t n_words = (rd.len + 31) >> 5;
+    const uint32_t n_words = (end + 31) >> 5;
     uint32_t carry_in = 0;
+    // events are ~60 bases apart: the 1024-position window loaded for the previous one usually
+    // still covers this search, so keep it in registers instead of going back to L2
+    bool cached = rd.bm_base != 0xffffffffu && wbase >= rd.bm_base && wbase < rd.bm_base + 32u;
+    if (cached) wbase = rd.bm_base;
     for (;;) {
         uint32_t wi = wbase + (uint32_t)rd.lane;
-        uint32_t W = wi < n_words ? __ldg(rd.bm + wi) : 0u;
+        uint32_t W;
+        if (cached) {
+            W = rd.bm_w;
+            cached = false;
+        } else {
+            W = wi < ((rd.len + 31) >> 5) ? __ldg(rd.bm + wi) : 0u; // cache real words, mask below
+            rd.bm_w = W;
+            rd.bm_base = wbase;
+        }
         uint32_t up = __shfl_up_sync(FULL, W, 1);
         uint32_t carry = rd.lane ? (up >> 31) : carry_in;
         uint32_t T = ~W & ((W << 1) | carry);
@@ -200,10 +272,10 @@ __device__ __forceinline__ uint32_t find_transition(const Rd &rd, uint32_t i, bo
             T &= ~(1u << sh);
             if (previous && !((W >> sh) & 1u)) T |= 1u << sh;
         }
-        if (posbase >= rd.len)
+        if (posbase >= end)
             T = 0;
-        else if (posbase + 32 > rd.len)
-            T &= (1u << (rd.len - posbase)) - 1u;
+        else if (posbase + 32 > end)
+            T &= (1u << (end - posbase)) - 1u;
         uint32_t any = __ballot_sync(FULL, T != 0);
         if (any) {
             int fl = __ffs(any) - 1;
@@ -211,7 +283,7 @@ __device__ __forceinline__ uint32_t find_transition(const Rd &rd, uint32_t i, bo
             return ((wbase + (uint32_t)fl) << 5) + (uint32_t)(__ffs(Tf) - 1);
         }
         wbase += 32;
-        if (wbase >= n_words) return rd.len;
+        if (wbase >= n_words) return end;
         // continue in the next window: its first position has P = S[pos-1] = top bit of lane 31
         carry_in = __shfl_sync(FULL, W, 31) >> 31;
         i = wbase << 5;
@@ -248,7 +320,7 @@ __device__ __forceinline__ uint32_t find_solid(const Rd &rd, uint32_t from) {
 // `dr` = how many of the following pushes still produce k-mers that contain corrected bases
 // (0 in the clean state): those need real lookups, everything after is in the phase-A bitmap.
 // Returns elen; hit_end = the weak run reaches the end of the read (then fck is not solid).
-__device__ __forceinline__ uint32_t error_len(const Rd &rd, uint64_t kmer, uint32_t i, uint32_t dr, bool &hit_end,
+__device__ __forceinline__ uint32_t error_len(Rd &rd, uint64_t kmer, uint32_t i, uint32_t dr, bool &hit_end,
                                               uint64_t &fck) {
     const uint32_t sublen = rd.len - i;
     hit_end = false;
@@ -386,6 +458,12 @@ __device__ __forceinline__ Corr exist_correct_error(Rd &rd, uint64_t kmer, uint3
     const uint64_t K0 = replace_last(kmer, alt, rd.mask);
     const uint8_t *sub = rd.in + i;
     const uint32_t sublen = rd.len - i;
+    // every base a scenario looks at lies in sub[0 .. c + 6): take them from the register window
+    // when it reaches that far (it does for the usual confirm values), else from memory
+    const bool use_win = c <= 30u && win_covers(rd, i, c + 6u);
+    auto sub_push = [&](uint64_t km, uint32_t from, uint32_t n) -> uint64_t {
+        return use_win ? win_push(rd, km, i + from, n) : push_seq(km, sub + from, n, rd.mask);
+    };
 
     Scen sc;
     if (NS == 3) {
@@ -393,7 +471,8 @@ __device__ __forceinline__ Corr exist_correct_error(Rd &rd, uint64_t kmer, uint3
     } else {
         uint32_t sb[4];
 #pragma unroll
-        for (int t = 0; t < 4; t++) sb[t] = (uint32_t)t < sublen ? nuc2bit(sub[t]) : 0u;
+        for (int t = 0; t < 4; t++)
+            sb[t] = (uint32_t)t < sublen ? (use_win ? (uint32_t)win_extract(rd, i + (uint32_t)t, 1) : nuc2bit(sub[t])) : 0u;
         // round 2: the four successor sets
         bool s = false;
         if (rd.lane < 16) {
@@ -417,14 +496,21 @@ __device__ __forceinline__ Corr exist_correct_error(Rd &rd, uint64_t kmer, uint3
         uint32_t q = q0 + (uint32_t)rd.lane;
         int s = (int)(q / per);
         uint32_t u = q - (uint32_t)s * per;
-        int src = s < NS ? s : 0;
-        // fetch scenario s from lane s (all lanes take part in the shuffles)
-        bool v = __shfl_sync(FULL, (int)sc.valid, src) != 0;
-        uint64_t K = shfl64(sc.K, src);
-        uint32_t offa = __shfl_sync(FULL, sc.offa, src);
-        uint32_t offc = __shfl_sync(FULL, sc.offc, src);
-        uint32_t ne = __shfl_sync(FULL, sc.n_emit, src);
-        uint32_t codes = __shfl_sync(FULL, sc.codes, src);
+        bool v;
+        uint64_t K;
+        uint32_t offa, offc, ne, codes;
+        if (NS == 3) { // ScenarioOne is a function of s alone: no need to ask lane s
+            Scen t = scen_one(s, K0);
+            v = t.valid; K = t.K; offa = t.offa; offc = t.offc; ne = t.n_emit; codes = t.codes;
+        } else { // fetch scenario s from lane s (all lanes take part in the shuffles)
+            int src = s < NS ? s : 0;
+            v = __shfl_sync(FULL, (int)sc.valid, src) != 0;
+            K = shfl64(sc.K, src);
+            offa = __shfl_sync(FULL, sc.offa, src);
+            offc = __shfl_sync(FULL, sc.offc, src);
+            ne = __shfl_sync(FULL, sc.n_emit, src);
+            codes = __shfl_sync(FULL, sc.codes, src);
+        }
         if (q >= Q || !v) continue;
         if (offa + c > sublen) { // get_score: `if offset + c > seq.len() return 0` (exist/mod.rs:29-31)
             bad |= 1u << s;
@@ -432,15 +518,13 @@ __device__ __forceinline__ Corr exist_correct_error(Rd &rd, uint64_t kmer, uint3
         }
         if (u <= c) {
             // u = 0: get(K) (exist/mod.rs:23); u = 1..c: the c confirmations (:35-43)
-            uint64_t km = push_seq(K, sub + offa, u, rd.mask);
-            if (!lookup(rd, km)) bad |= 1u << s;
+            if (!lookup(rd, sub_push(K, offa, u))) bad |= 1u << s;
         } else {
             // one_more (exist/mod.rs:49-70): uses correct()'s bases and offset, tests one k-mer
             if (sublen > c + offc + 1) {
                 uint64_t km = K0 >> 2;
                 for (int e = (int)ne - 1; e >= 0; e--) km = push(km, (codes >> (2 * e)) & 3u, rd.mask);
-                km = push_seq(km, sub + offc, c + 1, rd.mask);
-                if (lookup(rd, km)) more |= 1u << s;
+                if (lookup(rd, sub_push(km, offc, c + 1))) more |= 1u << s;
             }
         }
     }
@@ -892,42 +976,110 @@ __device__ __forceinline__ Corr greedy_correct_error(Rd &rd, uint64_t kmer, uint
 }
 
 // ------------------------------------------------------------------------------------------
-// Corrector::correct (src/correct/mod.rs:53-107) for one read
+// Corrector::correct (src/correct/mod.rs:53-107) for one read.  The scan is instantiated per
+// method so that One/Two do not pay for the registers of Greedy's alignment.
 // ------------------------------------------------------------------------------------------
+template <int METHOD>
 __device__ __forceinline__ Corr correct_error(Rd &rd, const CorrectParams &p, uint64_t kmer, uint32_t i, uint32_t dr) {
-    switch (p.method) {
-    case BRGPU_ONE: return exist_correct_error<3>(rd, kmer, i, (uint32_t)p.confirm);
-    case BRGPU_TWO: return exist_correct_error<13>(rd, kmer, i, (uint32_t)p.confirm);
-    case BRGPU_GRAPH: return graph_correct_error(rd, kmer, i, dr);
-    case BRGPU_GREEDY: return greedy_correct_error(rd, kmer, i, (uint32_t)p.max_search, (uint32_t)p.confirm);
-    default: return gap_size_correct_error(rd, kmer, i, dr, (uint32_t)p.confirm);
-    }
+    if (METHOD == BRGPU_ONE) return exist_correct_error<3>(rd, kmer, i, (uint32_t)p.confirm);
+    if (METHOD == BRGPU_TWO) return exist_correct_error<13>(rd, kmer, i, (uint32_t)p.confirm);
+    if (METHOD == BRGPU_GRAPH) return graph_correct_error(rd, kmer, i, dr);
+    if (METHOD == BRGPU_GREEDY)
+        return greedy_correct_error(rd, kmer, i, (uint32_t)p.max_search, (uint32_t)p.confirm);
+    return gap_size_correct_error(rd, kmer, i, dr, (uint32_t)p.confirm);
 }
 
-__device__ __forceinline__ void correct_read(Rd &rd, const CorrectParams &p) {
+// ------------------------------------------------------------------------------------------
+// Segmented, speculative scan.
+//
+// Corrector::correct is sequential inside a read, and one warp walking a 60 kb read from end
+// to end takes as long as the whole rest of the batch (ncu r1g: SMs idle for half of the scan
+// kernel while the longest reads finish).  The state the loop carries is small, though: when
+// the rolling k-mer consists of input bases only (d == 0) and `previous` equals the bitmap bit
+// S[i-1], everything that follows depends only on the position i — call that a *clean visit*.
+// A run started at position q in that state reproduces the sequential run's suffix exactly.
+//
+//   scan_spec_kernel:  every read is cut into segments of SEG positions.  One warp per segment
+//       starts at the segment boundary assuming a clean visit there, corrects up to the first
+//       clean visit at or after the next boundary (q_exit), writes its output to a scratch
+//       region, and records `horizon`: the position of its first successful correction.  Up to
+//       and including `horizon` the run has only copied input bytes (failed corrections echo the
+//       original base), so it is in a clean visit at every position of [start, horizon].
+//   scan_merge_kernel: one warp per read chains the pieces in order.  The sequential run reaches
+//       a clean visit at q (initially q = k).  If q <= horizon of the segment containing q, the
+//       speculative run of that segment is, from q on, exactly what the sequential run would
+//       do: append its output from scratch offset q - start and continue at its q_exit.
+//       Otherwise (the previous piece ran ~k positions past the boundary and this segment
+//       corrected something right at its start: a few percent of the boundaries) the warp
+//       re-runs that one segment from q itself.
+//
+// The result is byte-identical to the sequential scan by construction; the critical path drops
+// from "events of the longest read" to "events of one segment + a copy per segment".
+// ------------------------------------------------------------------------------------------
+constexpr uint32_t SEG = 2048;      // input positions per segment
+constexpr uint32_t SEG_CAP = 3072;  // scratch bytes per segment (overrun + growth)
+constexpr uint32_t NO_HORIZON = 0xffffffffu;
+
+struct SegRec {
+    uint32_t out_len;  // bytes written to the scratch region (may exceed SEG_CAP: then `bad`)
+    uint32_t q_exit;   // first clean visit at or after the nominal end (>= len: read finished)
+    uint32_t horizon;  // position of the first successful correction, NO_HORIZON if none
+    uint32_t bad;      // output did not fit into the scratch region: the piece is unusable
+};
+
+__device__ __forceinline__ bool bm_bit(const Rd &rd, uint32_t p) { return (__ldg(rd.bm + (p >> 5)) >> (p & 31)) & 1u; }
+
+// Run Corrector::correct's loop from a clean visit at `start` until the first clean visit at or
+// after `limit` (or the end of the read).  Output goes to rd.out/rd.o; rd.copy_from must be set
+// by the caller (start, or 0 for the piece that also carries the first k bases).
+template <int METHOD>
+__device__ __forceinline__ void correct_segment(Rd &rd, const CorrectParams &p, uint32_t start, uint32_t limit,
+                                                uint32_t &q_exit, uint32_t &horizon) {
     const uint32_t k = (uint32_t)rd.k;
-    rd.o = 0;
-    rd.copy_from = 0;
-    if (rd.len < k) { // mod.rs:56-58
-        flush_copy(rd, rd.len);
-        return;
-    }
-    uint32_t i = k;
-    bool previous = (__ldg(rd.bm + ((k - 1) >> 5)) >> ((k - 1) & 31)) & 1u; // mod.rs:67
-    uint32_t d = 0;    // pushes still to come whose k-mer contains corrected bases
-    uint64_t kmer = 0; // rolling k-mer; only maintained while d > 0 or at an event
+    rd.bm_base = 0xffffffffu;
+    rd.w_origin = 0xffffffffu;
+    horizon = NO_HORIZON;
+    uint32_t i = start;
+    bool previous = bm_bit(rd, start - 1); // mod.rs:67 for start == k; the clean-visit invariant otherwise
+    bool canon = true;  // d == 0 and previous == S[i-1]
+    uint32_t d = 0;     // pushes still to come whose k-mer contains corrected bases
+    uint64_t kmer = 0;  // rolling k-mer; only maintained while d > 0 or at an event
+    if (limit > rd.len) limit = rd.len;
 
     while (i < rd.len) {
         if (d == 0) {
-            uint32_t j = find_transition(rd, i, previous);
-            if (j >= rd.len) break;
-            i = j;
-            kmer = load_kmer_at(rd, i);
+            if (!canon) {
+                // first position after a dirty window: `previous` is the last dirty lookup, which
+                // need not equal S[i-1].  Look at this one position with the real `previous`.
+                const bool Si = bm_bit(rd, i);
+                if (Si || !previous) { // no event here (mod.rs:99-102): from i+1 on the state is canonical
+                    previous = Si;
+                    i += 1;
+                    canon = true;
+                    continue;
+                }
+            } else {
+                if (i >= limit) break; // clean visit at or after the nominal end
+                uint32_t j = find_transition(rd, i, previous, limit);
+                if (j >= limit) {     // nothing fires before the boundary: clean visit at `limit`
+                    i = limit;
+                    continue;
+                }
+                i = j;
+            }
+            // one cooperative load brings in the k-mer, the bases every scenario looks at and the
+            // bases of the dirty window that follows a correction
+            load_win(rd, i - k + 1);
+            kmer = win_extract(rd, i - k + 1, k);
         } else {
             uint32_t n = rd.len - i;
             if (n > d) n = d;
             if (n > 32) n = 32;
-            uint64_t km = push_window(rd, kmer, rd.in + i, n);
+            uint64_t km;
+            if (win_covers(rd, i, n))
+                km = win_push(rd, kmer, i, (uint32_t)rd.lane + 1u <= n ? (uint32_t)rd.lane + 1u : 0u);
+            else
+                km = push_window(rd, kmer, rd.in + i, n);
             bool s = (uint32_t)rd.lane < n && lookup(rd, km);
             uint32_t gm = __ballot_sync(FULL, s);
             uint32_t vm = n == 32 ? 0xffffffffu : ((1u << n) - 1u);
@@ -937,19 +1089,26 @@ __device__ __forceinline__ void correct_read(Rd &rd, const CorrectParams &p) {
                 previous = (gm >> (n - 1)) & 1u; // mod.rs:99
                 i += n;
                 d -= n;
+                if (d == 0 && i < rd.len) canon = previous == bm_bit(rd, i - 1);
                 continue;
             }
             uint32_t l = (uint32_t)(__ffs(trig) - 1);
             kmer = shfl64(km, (int)l);
             i += l;
             d -= l + 1;
+            // keep the bases the scenarios will look at in the register window
+            if (!win_covers(rd, i, 32u)) load_win(rd, i - k + 1);
         }
         // solid -> weak transition at input position i; kmer ends with in[i]
-        Corr c = correct_error(rd, p, kmer, i, d);
+        Corr c = correct_error<METHOD>(rd, p, kmer, i, d);
         if (!c.some) { // mod.rs:90-96
             previous = false;
             i += 1;
+            // d == 0: S[i-1] is 0 as well when the k-mer was pure input; after a dirty event it is
+            // whatever the bitmap says
+            if (d == 0 && i < rd.len) canon = !bm_bit(rd, i - 1);
         } else { // mod.rs:74-89
+            if (horizon == NO_HORIZON) horizon = i;
             flush_copy(rd, i);
             if (c.in_place) {
                 rd.o += c.n_emit;
@@ -966,23 +1125,105 @@ __device__ __forceinline__ void correct_read(Rd &rd, const CorrectParams &p) {
             i += c.offset;
             rd.copy_from = i;
             d = k - 1;
+            canon = false;
+            if (d == 0 && i < rd.len) canon = previous == bm_bit(rd, i - 1); // k == 1 cannot happen (k >= 3)
         }
     }
-    flush_copy(rd, rd.len);
+    q_exit = i;
+    flush_copy(rd, i < rd.len ? i : rd.len);
 }
 
 constexpr int SCAN_WARPS_PER_BLOCK = 4;
 
+// number of segments of a read
+__host__ __device__ __forceinline__ uint32_t seg_count(uint32_t len, uint32_t k) {
+    if (len <= k) return 1;
+    return (len - k + SEG - 1) / SEG;
+}
+
+__global__ void seg_count_kernel(const uint32_t *__restrict__ len, uint32_t n_reads, uint32_t k,
+                                 uint32_t *__restrict__ n_seg) {
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += gridDim.x * blockDim.x)
+        n_seg[r] = seg_count(len[r], k);
+}
+
+template <int METHOD>
 __global__ void __launch_bounds__(SCAN_WARPS_PER_BLOCK * 32)
-    scan_kernel(const uint8_t *__restrict__ in, const uint32_t *__restrict__ len_in, uint8_t *__restrict__ out,
-                uint32_t *__restrict__ len_out, const uint64_t *__restrict__ slot_off,
-                const uint32_t *__restrict__ bitmap, const uint32_t *__restrict__ order, uint32_t n_reads,
-                uint32_t *__restrict__ flags, const uint8_t *__restrict__ bits, CorrectParams p, uint8_t *scratch,
-                size_t scratch_per_warp) {
+    scan_spec_kernel(const uint8_t *__restrict__ in, const uint32_t *__restrict__ len_in,
+                     const uint64_t *__restrict__ slot_off, const uint32_t *__restrict__ bitmap,
+                     const uint64_t *__restrict__ seg_first, uint32_t n_reads, uint8_t *__restrict__ seg_out,
+                     SegRec *__restrict__ recs, uint32_t *__restrict__ flags, SolidView set, CorrectParams p,
+                     uint8_t *scratch, size_t scratch_per_warp) {
     const int lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     Rd rd;
-    rd.bits = bits;
+    rd.set = set;
+    rd.k = p.k;
+    rd.mask = kmask(p.k);
+    rd.lane = lane;
+    rd.scratch = scratch ? scratch + (size_t)warp * scratch_per_warp : nullptr;
+    rd.n_get = 0;
+    const uint64_t n_seg_total = __ldg(seg_first + n_reads);
+    for (;;) {
+        unsigned long long g = 0;
+        if (lane == 0) g = atomicAdd(reinterpret_cast<unsigned long long *>(flags + 4), 1ULL);
+        g = shfl64(g, 0);
+        if (g >= n_seg_total) break;
+        // read r with seg_first[r] <= g < seg_first[r+1]
+        uint32_t lo = 0, hi = n_reads;
+        while (hi - lo > 1) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (__ldg(seg_first + mid) <= g)
+                lo = mid;
+            else
+                hi = mid;
+        }
+        const uint32_t r = lo;
+        const uint32_t sidx = (uint32_t)(g - __ldg(seg_first + r));
+        const uint64_t base = __ldg(slot_off + r);
+        rd.in = in + base;
+        rd.len = __ldg(len_in + r);
+        rd.bm = bitmap + (base >> 5);
+        rd.out = seg_out + g * SEG_CAP;
+        rd.cap = SEG_CAP;
+        rd.o = 0;
+        SegRec rec;
+        rec.out_len = 0;
+        rec.q_exit = rd.len;
+        rec.horizon = NO_HORIZON;
+        rec.bad = 1;
+        if (rd.len >= (uint32_t)p.k && (rd.len > (uint32_t)p.k || sidx == 0)) {
+            const uint32_t start = (uint32_t)p.k + sidx * SEG;
+            rd.copy_from = sidx == 0 ? 0u : start; // piece 0 carries the first k bases (mod.rs:62-65)
+            if (start < rd.len) {
+                correct_segment<METHOD>(rd, p, start, start + SEG, rec.q_exit, rec.horizon);
+            } else { // len == k: nothing to scan, the piece is the read itself
+                rec.q_exit = rd.len;
+                flush_copy(rd, rd.len);
+            }
+            rec.out_len = rd.o;
+            rec.bad = rd.o > SEG_CAP ? 1u : 0u;
+        }
+        __syncwarp();
+        if (lane == 0) recs[g] = rec;
+    }
+    uint32_t gets = __reduce_add_sync(FULL, rd.n_get);
+    if (lane == 0 && gets) atomicAdd(reinterpret_cast<unsigned long long *>(flags + 2), (unsigned long long)gets);
+}
+
+template <int METHOD>
+__global__ void __launch_bounds__(SCAN_WARPS_PER_BLOCK * 32)
+    scan_merge_kernel(const uint8_t *__restrict__ in, const uint32_t *__restrict__ len_in, uint8_t *__restrict__ out,
+                      uint32_t *__restrict__ len_out, const uint64_t *__restrict__ slot_off,
+                      const uint32_t *__restrict__ bitmap, const uint32_t *__restrict__ order,
+                      const uint64_t *__restrict__ seg_first, uint32_t n_reads, const uint8_t *__restrict__ seg_out,
+                      const SegRec *__restrict__ recs, uint32_t *__restrict__ flags, SolidView set, CorrectParams p,
+                      uint8_t *scratch, size_t scratch_per_warp) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t k = (uint32_t)p.k;
+    Rd rd;
+    rd.set = set;
     rd.k = p.k;
     rd.mask = kmask(p.k);
     rd.lane = lane;
@@ -1000,7 +1241,47 @@ __global__ void __launch_bounds__(SCAN_WARPS_PER_BLOCK * 32)
         rd.cap = (uint32_t)(__ldg(slot_off + r + 1) - base);
         rd.len = __ldg(len_in + r);
         rd.bm = bitmap + (base >> 5);
-        correct_read(rd, p);
+        rd.o = 0;
+        rd.copy_from = 0;
+        if (rd.len < k) { // mod.rs:56-58
+            flush_copy(rd, rd.len);
+        } else {
+            const uint64_t g0 = __ldg(seg_first + r);
+            uint32_t q = k; // the sequential run's first clean visit (mod.rs:60-67)
+            bool first = true;
+            for (;;) {
+                const uint32_t sidx = q < rd.len ? (q - k) / SEG : 0u;
+                if (!first && q >= rd.len) break;
+                const SegRec rec = recs[g0 + sidx];
+                const uint32_t seg_start = k + sidx * SEG;
+                if (!rec.bad && q <= rec.horizon) {
+                    // the speculative run of this segment is in a clean visit at q: splice it in
+                    const uint32_t in0 = sidx == 0 ? 0u : seg_start;     // input position of scratch byte 0
+                    const uint32_t skip = first ? 0u : q - in0;          // 1:1 copy region before q
+                    const uint8_t *src = seg_out + (g0 + sidx) * SEG_CAP + skip;
+                    const uint32_t n = rec.out_len - skip;
+                    for (uint32_t t = lane; t < n; t += 32) {
+                        uint32_t dst = rd.o + t;
+                        if (dst < rd.cap) rd.out[dst] = src[t];
+                    }
+                    rd.o += n;
+                    q = rec.q_exit;
+                } else {
+                    // re-run this segment from the true state
+                    rd.copy_from = first ? 0u : q;
+                    uint32_t q_exit, horizon;
+                    if (q < rd.len) {
+                        correct_segment<METHOD>(rd, p, q, seg_start + SEG, q_exit, horizon);
+                    } else {
+                        q_exit = rd.len;
+                        flush_copy(rd, rd.len);
+                    }
+                    q = q_exit;
+                }
+                first = false;
+                if (q >= rd.len) break;
+            }
+        }
         __syncwarp();
         if (lane == 0) {
             len_out[r] = rd.o;
@@ -1011,22 +1292,82 @@ __global__ void __launch_bounds__(SCAN_WARPS_PER_BLOCK * 32)
     if (lane == 0 && gets) atomicAdd(reinterpret_cast<unsigned long long *>(flags + 2), (unsigned long long)gets);
 }
 
-int scan_grid_warps(brgpu_ctx *ctx) { return ctx->sm_count * 8 * SCAN_WARPS_PER_BLOCK; }
+template <class K> static int occupancy_warps(brgpu_ctx *ctx, K kernel) {
+    int blocks_per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, SCAN_WARPS_PER_BLOCK * 32, 0) !=
+            cudaSuccess ||
+        blocks_per_sm < 1) {
+        cudaGetLastError();
+        blocks_per_sm = 4;
+    }
+    return ctx->sm_count * blocks_per_sm * SCAN_WARPS_PER_BLOCK;
+}
+
+// upper bound on resident warps over all methods (sizes the per-warp scratch)
+int scan_grid_warps(brgpu_ctx *ctx) { return ctx->sm_count * 16 * SCAN_WARPS_PER_BLOCK; }
+
+uint64_t scan_max_segments(const Layout &L) { return L.total_slots / SEG + L.n + 1; }
+size_t scan_seg_out_bytes(const Layout &L) { return (size_t)scan_max_segments(L) * SEG_CAP; }
+size_t scan_seg_rec_bytes(const Layout &L) { return (size_t)scan_max_segments(L) * sizeof(SegRec); }
+
+template <int M>
+static void launch_scan_method(brgpu_ctx *ctx, const Layout &L, const uint8_t *d_in, const uint32_t *d_len_in,
+                               uint8_t *d_out, uint32_t *d_len_out, const uint32_t *d_bitmap, const SolidView &sv,
+                               const CorrectParams &p, uint8_t *d_scratch, size_t scratch_per_warp, int n_warps_total,
+                               const ScanWork &w, double n_bases_hint, const char *spec_name, const char *merge_name) {
+    const unsigned threads = SCAN_WARPS_PER_BLOCK * 32;
+    auto grid_for_warps = [&](uint64_t resident, uint64_t items) {
+        if (resident > (uint64_t)n_warps_total) resident = (uint64_t)n_warps_total;
+        uint64_t warps = items < resident ? items : resident;
+        if (warps < 1) warps = 1;
+        return (unsigned)((warps + SCAN_WARPS_PER_BLOCK - 1) / SCAN_WARPS_PER_BLOCK);
+    };
+    {
+        ProfScope ps(ctx, spec_name, n_bases_hint * 2.0);
+        scan_spec_kernel<M><<<grid_for_warps((uint64_t)occupancy_warps(ctx, scan_spec_kernel<M>), scan_max_segments(L)),
+                              threads, 0, ctx->stream>>>(d_in, d_len_in, L.d_slot_off, d_bitmap, w.d_seg_first,
+                                                         (uint32_t)L.n, w.d_seg_out, (SegRec *)w.d_seg_recs,
+                                                         ctx->d_flags, sv, p, d_scratch, scratch_per_warp);
+    }
+    {
+        ProfScope ps(ctx, merge_name, n_bases_hint * 2.0);
+        scan_merge_kernel<M><<<grid_for_warps((uint64_t)occupancy_warps(ctx, scan_merge_kernel<M>), L.n), threads, 0,
+                               ctx->stream>>>(d_in, d_len_in, d_out, d_len_out, L.d_slot_off, d_bitmap, L.d_order,
+                                              w.d_seg_first, (uint32_t)L.n, w.d_seg_out, (const SegRec *)w.d_seg_recs,
+                                              ctx->d_flags, sv, p, d_scratch, scratch_per_warp);
+    }
+}
 
 void launch_scan(brgpu_ctx *ctx, const Layout &L, const uint8_t *d_in, const uint32_t *d_len_in, uint8_t *d_out,
-                 uint32_t *d_len_out, const uint32_t *d_bitmap, const uint8_t *d_bits, const CorrectParams &p,
-                 uint8_t *d_scratch, size_t scratch_per_warp, int n_warps_total, double n_bases_hint) {
+                 uint32_t *d_len_out, const uint32_t *d_bitmap, const SetView &set, const CorrectParams &p,
+                 uint8_t *d_scratch, size_t scratch_per_warp, int n_warps_total, const ScanWork &w,
+                 double n_bases_hint) {
     if (!L.n) return;
-    cudaMemsetAsync(ctx->d_flags, 0, sizeof(uint32_t), ctx->stream); // work-queue cursor
-    static const char *names[5] = {"scan_one", "scan_two", "scan_graph", "scan_greedy", "scan_gap_size"};
-    ProfScope ps(ctx, names[p.method], n_bases_hint * 2.0);
-    uint64_t need_warps = L.n;
-    uint64_t warps = need_warps < (uint64_t)n_warps_total ? need_warps : (uint64_t)n_warps_total;
-    unsigned blocks = (unsigned)((warps + SCAN_WARPS_PER_BLOCK - 1) / SCAN_WARPS_PER_BLOCK);
-    scan_kernel<<<blocks, SCAN_WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(d_in, d_len_in, d_out, d_len_out, L.d_slot_off,
-                                                                       d_bitmap, L.d_order, (uint32_t)L.n,
-                                                                       ctx->d_flags, d_bits, p, d_scratch,
-                                                                       scratch_per_warp);
+    // work-queue cursors: flags[0] reads (merge), flags[4..5] segments (spec, 64 bit)
+    cudaMemsetAsync(ctx->d_flags, 0, sizeof(uint32_t), ctx->stream);
+    cudaMemsetAsync(ctx->d_flags + 4, 0, 2 * sizeof(uint32_t), ctx->stream);
+    // segments per read -> first segment of every read
+    {
+        ProfScope ps(ctx, "seg_count", (double)L.n * 8.0);
+        unsigned blocks = (unsigned)((L.n + 255) / 256);
+        if (blocks > (unsigned)ctx->sm_count * 8) blocks = (unsigned)ctx->sm_count * 8;
+        seg_count_kernel<<<blocks, 256, 0, ctx->stream>>>(d_len_in, (uint32_t)L.n, (uint32_t)p.k, w.d_n_seg);
+    }
+    launch_exclusive_scan_u32(ctx, w.d_n_seg, L.n, w.d_seg_first, w.d_scan_tmp);
+    const SolidView sv{set.bits, set.summary, set.shift, set.k};
+    static const char *spec_names[5] = {"scan_one", "scan_two", "scan_graph", "scan_greedy", "scan_gap_size"};
+    static const char *merge_names[5] = {"merge_one", "merge_two", "merge_graph", "merge_greedy", "merge_gap_size"};
+#define BRGPU_LAUNCH_SCAN(M)                                                                                           \
+    launch_scan_method<M>(ctx, L, d_in, d_len_in, d_out, d_len_out, d_bitmap, sv, p, d_scratch, scratch_per_warp,      \
+                          n_warps_total, w, n_bases_hint, spec_names[M], merge_names[M])
+    switch (p.method) {
+    case BRGPU_ONE: BRGPU_LAUNCH_SCAN(BRGPU_ONE); break;
+    case BRGPU_TWO: BRGPU_LAUNCH_SCAN(BRGPU_TWO); break;
+    case BRGPU_GRAPH: BRGPU_LAUNCH_SCAN(BRGPU_GRAPH); break;
+    case BRGPU_GREEDY: BRGPU_LAUNCH_SCAN(BRGPU_GREEDY); break;
+    default: BRGPU_LAUNCH_SCAN(BRGPU_GAP_SIZE); break;
+    }
+#undef BRGPU_LAUNCH_SCAN
 }
 
 } // namespace brgpu

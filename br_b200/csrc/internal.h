@@ -81,6 +81,11 @@ struct brgpu_set {
     uint64_t n_bytes = 0;
     uint8_t *d_bits = nullptr;
     uint64_t hist[256] = {0};
+    // L2-resident occupancy summary of d_bits (see SolidView in kmer.cuh); rebuilt lazily
+    uint32_t *d_summary = nullptr;
+    uint64_t summary_bytes = 0;
+    int summary_shift = 0;
+    bool summary_valid = false;
 };
 
 namespace brgpu {
@@ -117,11 +122,29 @@ void launch_count(brgpu_ctx *ctx, const Layout &L, const uint8_t *d_seq, const u
 // bit i = counts[i] > abundance for the same range.  begin/end multiples of 1024.
 void launch_spectrum_threshold(brgpu_ctx *ctx, const uint8_t *d_counts, uint64_t begin, uint64_t end, uint64_t *d_hist,
                                uint8_t *d_bits, int abundance);
+// bucketed counting (see set_kernels.cu)
+void launch_bucket_partition(brgpu_ctx *ctx, const Layout &L, const uint8_t *d_seq, const uint32_t *d_len, int k,
+                             uint64_t n_buckets, uint32_t *d_fill, uint64_t *d_base, uint64_t *d_scan_tmp,
+                             uint16_t *d_residues, double n_kmers);
+void launch_bucket_count(brgpu_ctx *ctx, const uint16_t *d_residues, const uint64_t *d_base, uint64_t n_buckets,
+                         int abundance, uint8_t *d_bits, uint32_t *d_summary, int summary_shift, uint64_t *d_hist,
+                         double n_kmers);
 void launch_get_batch(brgpu_ctx *ctx, const uint8_t *d_bits, int k, const uint64_t *d_kmers, uint64_t n,
                       uint8_t *d_out);
 void launch_insert_batch(brgpu_ctx *ctx, uint8_t *d_bits, int k, const uint64_t *d_kmers, uint64_t n);
 void launch_merge_slice(brgpu_ctx *ctx, uint8_t *d_counts, void *const *peers, int n_peers, uint64_t begin,
                         uint64_t end);
+
+// occupancy summary of a bitfield: one bit per 2^shift bitfield bits
+void launch_build_summary(brgpu_ctx *ctx, const uint8_t *d_bits, uint64_t n_bytes, int shift, uint32_t *d_summary);
+
+// device view of a set for the correction kernels
+struct SetView {
+    const uint8_t *bits;
+    const uint32_t *summary;
+    int shift;
+    int k;
+};
 
 // ---- part 2 kernels (correct_kernels.cu) ----
 struct CorrectParams {
@@ -132,12 +155,24 @@ struct CorrectParams {
 };
 // solidity bit of the k-mer ending at every slot position of every read (0 where undefined)
 void launch_solid_bitmap(brgpu_ctx *ctx, const Layout &L, const uint8_t *d_seq, const uint32_t *d_len,
-                         const uint8_t *d_bits, int k, uint32_t *d_bitmap, double n_bases_hint);
-// Corrector::correct over all reads (one warp per read, longest first); writes min(len,cap)
-// bytes per read, the true output length to d_len_out and sets d_flags[1] on overflow.
+                         const SetView &set, uint32_t *d_bitmap, double n_bases_hint);
+// per-pass work areas of the segmented scan (sized once per correction call)
+struct ScanWork {
+    uint32_t *d_n_seg = nullptr;     // n reads
+    uint64_t *d_seg_first = nullptr; // n + 1
+    uint64_t *d_scan_tmp = nullptr;  // n / 4096 + 4
+    uint8_t *d_seg_out = nullptr;    // scan_seg_out_bytes(L)
+    void *d_seg_recs = nullptr;      // scan_seg_rec_bytes(L)
+};
+uint64_t scan_max_segments(const Layout &L);
+size_t scan_seg_out_bytes(const Layout &L);
+size_t scan_seg_rec_bytes(const Layout &L);
+// Corrector::correct over all reads: speculative per-segment scan + per-read merge; writes
+// min(len,cap) bytes per read, the true output length to d_len_out and sets d_flags[1] on overflow.
 void launch_scan(brgpu_ctx *ctx, const Layout &L, const uint8_t *d_in, const uint32_t *d_len_in, uint8_t *d_out,
-                 uint32_t *d_len_out, const uint32_t *d_bitmap, const uint8_t *d_bits, const CorrectParams &p,
-                 uint8_t *d_scratch, size_t scratch_per_warp, int n_warps_total, double n_bases_hint);
+                 uint32_t *d_len_out, const uint32_t *d_bitmap, const SetView &set, const CorrectParams &p,
+                 uint8_t *d_scratch, size_t scratch_per_warp, int n_warps_total, const ScanWork &w,
+                 double n_bases_hint);
 int scan_grid_warps(brgpu_ctx *ctx);
 size_t scan_scratch_per_warp(const CorrectParams &p);
 

@@ -53,6 +53,28 @@ __device__ __forceinline__ bool solid(const uint8_t *__restrict__ bits, uint64_t
     return (__ldg(bits + (idx >> 3)) >> (idx & 7)) & 1;
 }
 
+// The solid set as the kernels see it: the dense bitfield in HBM plus (for k >= 15) a coarse
+// occupancy summary small enough to stay in L2 — summary bit j is set iff any of the bitfield
+// bits [j << shift, (j + 1) << shift) is.  A random byte of the bitfield costs a DRAM row
+// activation (measured ceiling 43 G/s, profiles/microbench_random_access_r1.txt); a random word
+// of the summary is an L2 hit (285 G/s).  Most k-mers a corrector asks about are weak, and for a
+// sparse set almost all of them fall into empty blocks, so they never leave L2.
+struct SolidView {
+    const uint8_t *bits;
+    const uint32_t *summary; // nullptr: no summary (small k: the bitfield itself is cache resident)
+    int shift;               // log2(bitfield bits per summary bit), >= 5
+    int k;
+};
+
+__device__ __forceinline__ bool solid(const SolidView &v, uint64_t kmer) {
+    uint64_t idx = canonical_index(kmer, v.k);
+    if (v.summary) {
+        uint64_t j = idx >> v.shift;
+        if (!((__ldg(v.summary + (j >> 5)) >> (j & 31)) & 1u)) return false;
+    }
+    return (__ldg(v.bits + (idx >> 3)) >> (idx & 7)) & 1;
+}
+
 // Pack the 2-bit codes of 16 ASCII bases held in a uint4 (memory order) into 32 bits, first
 // base in the most significant pair.
 __device__ __forceinline__ uint32_t pack4(uint32_t w) {

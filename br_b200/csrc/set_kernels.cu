@@ -303,16 +303,307 @@ void launch_count(brgpu_ctx *ctx, const Layout &L, const uint8_t *d_seq, const u
 }
 
 // ------------------------------------------------------------------------------------------
-// Spectrum + threshold: one streaming pass over the count table.  Each thread takes 16
-// counters (one 16 B load, lanes contiguous), tallies values 0..3 with byte-SIMD compares in
-// registers (they hold almost all the mass), sends the rest to a shared-memory histogram, and
-// writes 16 bits of the LSB-first bitfield.
+// Bucketed counting (k >= 15): the same counts without a single random DRAM access.
+//
+// A random read-modify-write of the 2^(2k-1)-byte table costs two DRAM row activations and the
+// whole chip sustains only ~20 G of them per second (profiles/microbench_random_access_r1.txt).
+// So the k-mers are first partitioned by the top bits of their table index into buckets that
+// each cover 2^15 consecutive counters — 16-bit residues, one streaming pass that writes 2 B
+// per k-mer through L2-combined runs — and then every bucket is counted by one thread block in
+// 32 KiB of shared memory (7 blocks per SM hide each other's load latency): zero, saturating u8 increments (CAS on the 32-bit shared word), then
+// one sweep over the slice that feeds the spectrum and emits the slice's 8 KiB of the bitfield
+// and its summary bits with plain coalesced stores.  The full table is never materialised and
+// no atomics ever reach HBM.  The result (spectrum, bitfield) is identical to the table
+// path's by construction: both compute min(255, occurrences) per canonical k-mer.
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t msb_nibble(uint32_t cmp) {
     // cmp has 0xff/0x00 per byte; gather one bit per byte: byte j -> bit j
     uint32_t y = (cmp & 0x80808080u) >> 7;
     return (y | (y >> 7) | (y >> 14) | (y >> 21)) & 0xfu;
 }
+
+// Spectrum tallies + threshold nibble of one 32-bit word holding 4 counters that is known to be
+// non-zero.  Deliberately not inlined: sparse tables make this the rare path, and inlining it
+// eight times into the sweep loops turns the common all-zero case into ~50 predicated
+// instructions per word (ncu: 3.5 G warp instructions for a 1 GiB sweep before this split).
+__device__ __noinline__ uint32_t tally_word(uint32_t w, uint32_t thr, uint32_t &c0, uint32_t &c1, uint32_t &c2,
+                                            uint32_t &c3, unsigned int *sh_hist) {
+    uint32_t z0 = __vcmpeq4(w, 0u), z1 = __vcmpeq4(w, 0x01010101u);
+    uint32_t z2 = __vcmpeq4(w, 0x02020202u), z3 = __vcmpeq4(w, 0x03030303u);
+    c0 += __popc(z0) >> 3;
+    c1 += __popc(z1) >> 3;
+    c2 += __popc(z2) >> 3;
+    c3 += __popc(z3) >> 3;
+    uint32_t rest = ~(z0 | z1 | z2 | z3);
+    while (rest) {
+        int q = (__ffs(rest) - 1) >> 3;
+        atomicAdd(&sh_hist[(w >> (8 * q)) & 0xffu], 1u);
+        rest &= ~(0xffu << (8 * q));
+    }
+    return msb_nibble(__vcmpgtu4(w, thr));
+}
+
+constexpr int BUCKET_BITS = 15;                  // counters per bucket = 2^15 (32 KiB of shared memory)
+constexpr int BUCKET_COUNTERS = 1 << BUCKET_BITS;
+constexpr int BUCKET_THREADS = 256;
+
+template <class F>
+__device__ __forceinline__ void for_each_kmer_index8(const uint8_t *__restrict__ seq, const uint32_t *__restrict__ len,
+                                                     const uint64_t *__restrict__ slot_off,
+                                                     const uint32_t *__restrict__ word2read, uint64_t w, int k,
+                                                     uint64_t mask, F f) {
+    // calls f(idx[8], valid[8]) four times: 8 independent k-mers per call
+    uint32_t r = __ldg(word2read + w);
+    uint64_t sb = w << 5;
+    uint32_t p0 = (uint32_t)(sb - __ldg(slot_off + r));
+    uint32_t L = __ldg(len + r);
+    if (p0 >= L || L < (uint32_t)k) return;
+    uint64_t prev, cur;
+    load_window(seq, sb, p0, prev, cur);
+    int t_lo = p0 >= (uint32_t)(k - 1) ? 0 : (k - 1 - (int)p0);
+    int t_hi = (L - p0) < 32u ? (int)(L - p0) : 32;
+#pragma unroll
+    for (int g = 0; g < 32; g += 8) {
+        uint64_t idx[8];
+        bool ok[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            idx[j] = canonical_index(window_kmer(prev, cur, g + j, mask), k);
+            ok[j] = g + j >= t_lo && g + j < t_hi;
+        }
+        f(idx, ok);
+    }
+}
+
+// pass 1: bucket sizes
+__global__ void __launch_bounds__(256)
+    bucket_hist_kernel(const uint8_t *__restrict__ seq, const uint32_t *__restrict__ len,
+                       const uint64_t *__restrict__ slot_off, const uint32_t *__restrict__ word2read, uint64_t n_words,
+                       int k, uint32_t *__restrict__ fill) {
+    const uint64_t mask = kmask(k);
+    for (uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < n_words;
+         w += (uint64_t)gridDim.x * blockDim.x)
+        for_each_kmer_index8(seq, len, slot_off, word2read, w, k, mask, [&](const uint64_t idx[8], const bool ok[8]) {
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                if (ok[j]) atomicAdd(fill + (idx[j] >> BUCKET_BITS), 1u); // result unused: compiles to RED
+        });
+}
+
+// pass 2: scatter the 16-bit residues; the per-bucket cursors live in L2
+__global__ void __launch_bounds__(256)
+    bucket_scatter_kernel(const uint8_t *__restrict__ seq, const uint32_t *__restrict__ len,
+                          const uint64_t *__restrict__ slot_off, const uint32_t *__restrict__ word2read,
+                          uint64_t n_words, int k, const uint64_t *__restrict__ base, uint32_t *__restrict__ fill,
+                          uint16_t *__restrict__ residues) {
+    const uint64_t mask = kmask(k);
+    for (uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < n_words;
+         w += (uint64_t)gridDim.x * blockDim.x)
+        for_each_kmer_index8(seq, len, slot_off, word2read, w, k, mask, [&](const uint64_t idx[8], const bool ok[8]) {
+            uint64_t pos[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                pos[j] = 0;
+                if (ok[j]) {
+                    uint64_t b = idx[j] >> BUCKET_BITS;
+                    pos[j] = __ldg(base + b) + (uint64_t)atomicAdd(fill + b, 1u);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                if (ok[j]) residues[pos[j]] = (uint16_t)(idx[j] & (BUCKET_COUNTERS - 1));
+        });
+}
+
+// Saturating u8 increment in a (shared-memory) word; returns true iff this call took the counter
+// from 0 to 1, i.e. the caller is the k-mer's first occurrence in the bucket ("owner").
+__device__ __forceinline__ bool sat_inc_owner(uint32_t *wp, uint32_t sh) {
+    const uint32_t one = 1u << sh;
+    uint32_t old = atomicCAS(wp, 0u, one);
+    if (old == 0) return true;
+    for (;;) {
+        uint32_t b = (old >> sh) & 0xffu;
+        if (b == 0xffu) return false;
+        uint32_t assumed = old;
+        old = atomicCAS(wp, assumed, assumed + one);
+        if (old == assumed) return b == 0;
+    }
+}
+
+// pass 3: one block per bucket, counters in shared memory.  Work per bucket is proportional to
+// its k-mers, not to its 2^15 counters: the first occurrence of every distinct k-mer ("owner",
+// known from the CAS that took the counter from 0 to 1) comes back after the block barrier,
+// reads the final count, tallies the spectrum, sets the bit in a 4 KiB shared bitfield slice
+// if count > abundance, and stores 0 to its counter byte — so the slice is clean again for
+// the next bucket without ever being swept.  hist[0] is 2^15 minus the owners.
+constexpr int BUCKET_REG_ROUNDS = 4; // residues kept in registers per thread between the two phases
+
+__global__ void __launch_bounds__(BUCKET_THREADS)
+    bucket_count_kernel(const uint16_t *__restrict__ residues, const uint64_t *__restrict__ base, uint64_t n_buckets,
+                        int abundance, uint32_t *__restrict__ bitfield32, uint32_t *__restrict__ summary32,
+                        int summary_shift, unsigned long long *__restrict__ g_hist) {
+    extern __shared__ uint32_t cnt[];          // BUCKET_COUNTERS / 4 words of u8 counters
+    __shared__ uint32_t sh_bits[BUCKET_COUNTERS / 32]; // the bucket's slice of the bitfield
+    __shared__ unsigned int sh_hist[256];
+    uint8_t *cnt8 = reinterpret_cast<uint8_t *>(cnt);
+    for (int t = threadIdx.x; t < 256; t += BUCKET_THREADS) sh_hist[t] = 0;
+    for (int t = threadIdx.x; t < BUCKET_COUNTERS / 4; t += BUCKET_THREADS) cnt[t] = 0; // once: owners keep it clean
+    uint32_t c1 = 0, c2 = 0, c3 = 0, owners = 0; // per-thread tallies of the values that hold the mass
+    unsigned long long zeros = 0;
+    uint64_t begin = 0, end = 0;
+    if (blockIdx.x < n_buckets) {
+        begin = __ldg(base + blockIdx.x);
+        end = __ldg(base + blockIdx.x + 1);
+    }
+    __syncthreads();
+    for (uint64_t b = blockIdx.x; b < n_buckets; b += gridDim.x) {
+        uint32_t res[BUCKET_REG_ROUNDS];
+#pragma unroll
+        for (int q = 0; q < BUCKET_REG_ROUNDS; q++) {
+            uint64_t j = begin + threadIdx.x + (uint64_t)q * BUCKET_THREADS;
+            res[q] = j < end ? (uint32_t)__ldcs(residues + j) : 0xffffffffu;
+        }
+        // bounds of this block's next bucket: requested now, needed only after the barriers
+        uint64_t nb_begin = 0, nb_end = 0;
+        if (b + gridDim.x < n_buckets) {
+            nb_begin = __ldg(base + b + gridDim.x);
+            nb_end = __ldg(base + b + gridDim.x + 1);
+        }
+        for (int t = threadIdx.x; t < BUCKET_COUNTERS / 32; t += BUCKET_THREADS) sh_bits[t] = 0;
+        // ---- phase 1: saturating increments ----
+        uint32_t own = 0; // bit q: res[q] is an owner
+#pragma unroll
+        for (int q = 0; q < BUCKET_REG_ROUNDS; q++)
+            if (res[q] != 0xffffffffu && sat_inc_owner(cnt + (res[q] >> 2), (res[q] & 3u) * 8u)) own |= 1u << q;
+        const uint64_t rest_begin = begin + (uint64_t)BUCKET_REG_ROUNDS * BUCKET_THREADS;
+        for (uint64_t j = rest_begin + threadIdx.x; j < end; j += BUCKET_THREADS) {
+            uint32_t r = __ldcs(residues + j);
+            sat_inc_owner(cnt + (r >> 2), (r & 3u) * 8u);
+        }
+        __syncthreads();
+        // ---- phase 2: owners read the final count, tally, threshold and clear ----
+#pragma unroll
+        for (int q = 0; q < BUCKET_REG_ROUNDS; q++) {
+            if ((own >> q) & 1u) {
+                const uint32_t r = res[q];
+                const uint32_t c = cnt8[r];
+                cnt8[r] = 0;
+                owners++;
+                if (c == 1) c1++;
+                else if (c == 2) c2++;
+                else if (c == 3) c3++;
+                else atomicAdd(&sh_hist[c], 1u);
+                if (c > (uint32_t)abundance) atomicOr(&sh_bits[r >> 5], 1u << (r & 31));
+            }
+        }
+        // big buckets: the overflow occurrences claim their counter with an atomic swap-to-zero —
+        // after the register-held owners have cleared theirs (block-uniform condition)
+        if (end > rest_begin) __syncthreads();
+        for (uint64_t j = rest_begin + threadIdx.x; j < end; j += BUCKET_THREADS) {
+            const uint32_t r = __ldcs(residues + j);
+            const uint32_t sh = (r & 3u) * 8u;
+            const uint32_t old = atomicAnd(cnt + (r >> 2), ~(0xffu << sh));
+            const uint32_t c = (old >> sh) & 0xffu;
+            if (c) { // not yet claimed by a register-held owner or another overflow occurrence
+                owners++;
+                atomicAdd(&sh_hist[c], 1u);
+                if (c > (uint32_t)abundance) atomicOr(&sh_bits[r >> 5], 1u << (r & 31));
+            }
+        }
+        __syncthreads();
+        // ---- write the slice of the bitfield (+ its summary bits) ----
+        if (bitfield32) {
+            for (int t = threadIdx.x; t < BUCKET_COUNTERS / 32; t += BUCKET_THREADS) {
+                const uint32_t out = sh_bits[t];
+                const uint64_t word = b * (BUCKET_COUNTERS / 32) + (uint64_t)t;
+                bitfield32[word] = out;
+                if (summary32 && summary_shift == 5) { // one summary bit per bitfield word
+                    uint32_t m = __ballot_sync(FULL, out != 0);
+                    if ((threadIdx.x & 31) == 0) summary32[word >> 5] = m;
+                }
+            }
+        }
+        if (threadIdx.x == 0) zeros += BUCKET_COUNTERS;
+        begin = nb_begin;
+        end = nb_end;
+        __syncthreads(); // sh_bits is re-zeroed at the top of the next iteration
+    }
+    // hist[0] = counters nobody touched = all counters of this block's buckets - owners
+    c1 = __reduce_add_sync(FULL, c1);
+    c2 = __reduce_add_sync(FULL, c2);
+    c3 = __reduce_add_sync(FULL, c3);
+    owners = __reduce_add_sync(FULL, owners);
+    __shared__ unsigned long long sh_owners;
+    if (threadIdx.x == 0) sh_owners = 0;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) {
+        if (c1) atomicAdd(&sh_hist[1], c1);
+        if (c2) atomicAdd(&sh_hist[2], c2);
+        if (c3) atomicAdd(&sh_hist[3], c3);
+        if (owners) atomicAdd(&sh_owners, (unsigned long long)owners);
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < 256; t += BUCKET_THREADS)
+        if (t > 0 && sh_hist[t]) atomicAdd(g_hist + t, (unsigned long long)sh_hist[t]);
+    if (threadIdx.x == 0 && zeros >= sh_owners) atomicAdd(g_hist + 0, zeros - sh_owners);
+}
+
+void launch_bucket_partition(brgpu_ctx *ctx, const Layout &L, const uint8_t *d_seq, const uint32_t *d_len, int k,
+                             uint64_t n_buckets, uint32_t *d_fill, uint64_t *d_base, uint64_t *d_scan_tmp,
+                             uint16_t *d_residues, double n_kmers) {
+    uint64_t n_words = L.total_slots >> 5;
+    cudaMemsetAsync(d_fill, 0, n_buckets * sizeof(uint32_t), ctx->stream);
+    {
+        ProfScope ps(ctx, "bucket_hist", n_kmers * 1.0); // ASCII stream in; the bucket counters stay in L2
+        bucket_hist_kernel<<<grid_for(ctx, n_words, 256, 8), 256, 0, ctx->stream>>>(d_seq, d_len, L.d_slot_off,
+                                                                                    L.d_word2read, n_words, k, d_fill);
+    }
+    launch_exclusive_scan_u32(ctx, d_fill, n_buckets, d_base, d_scan_tmp);
+    cudaMemsetAsync(d_fill, 0, n_buckets * sizeof(uint32_t), ctx->stream);
+    {
+        ProfScope ps(ctx, "bucket_scatter", n_kmers * 3.0); // ASCII in + 2 B residue out
+        bucket_scatter_kernel<<<grid_for(ctx, n_words, 256, 8), 256, 0, ctx->stream>>>(
+            d_seq, d_len, L.d_slot_off, L.d_word2read, n_words, k, d_base, d_fill, d_residues);
+    }
+}
+
+int bucket_count_configure() {
+    static bool done = false;
+    if (!done) {
+        cudaFuncSetAttribute(bucket_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BUCKET_COUNTERS);
+        cudaFuncSetAttribute(bucket_count_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
+        done = true;
+    }
+    return BUCKET_COUNTERS;
+}
+
+void launch_bucket_count(brgpu_ctx *ctx, const uint16_t *d_residues, const uint64_t *d_base, uint64_t n_buckets,
+                         int abundance, uint8_t *d_bits, uint32_t *d_summary, int summary_shift, uint64_t *d_hist,
+                         double n_kmers) {
+    const int smem = bucket_count_configure();
+    // 2 B residue in per k-mer + the slice's share of the bitfield out (a sweep that reads the
+    // residues twice for the rare buckets that overflow the register rounds is not counted)
+    ProfScope ps(ctx, "bucket_count", n_kmers * 2.0 + (double)n_buckets * (BUCKET_COUNTERS / 8));
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bucket_count_kernel, BUCKET_THREADS, smem) != cudaSuccess ||
+        per_sm < 1) {
+        cudaGetLastError();
+        per_sm = 1;
+    }
+    uint64_t cap = (uint64_t)ctx->sm_count * (uint64_t)per_sm;
+    unsigned grid = (unsigned)(n_buckets < cap ? n_buckets : cap);
+    bucket_count_kernel<<<grid, BUCKET_THREADS, smem, ctx->stream>>>(
+        d_residues, d_base, n_buckets, abundance, reinterpret_cast<uint32_t *>(d_bits), d_summary, summary_shift,
+        reinterpret_cast<unsigned long long *>(d_hist));
+}
+
+// ------------------------------------------------------------------------------------------
+// Spectrum + threshold: one streaming pass over the count table.  Each thread takes 16
+// counters (one 16 B load, lanes contiguous), tallies values 0..3 with byte-SIMD compares in
+// registers (they hold almost all the mass), sends the rest to a shared-memory histogram, and
+// writes 16 bits of the LSB-first bitfield.
+// ------------------------------------------------------------------------------------------
 
 __global__ void __launch_bounds__(256)
     spectrum_threshold_kernel(const uint4 *__restrict__ counts16, uint64_t n16, unsigned long long *__restrict__ hist,
@@ -335,23 +626,10 @@ __global__ void __launch_bounds__(256)
         } else {
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                if (w[j] == 0) { // sparse tables: most words next to a hit are still empty
+                if (w[j] == 0)
                     c0 += 4;
-                    continue;
-                }
-                uint32_t z0 = __vcmpeq4(w[j], 0u), z1 = __vcmpeq4(w[j], 0x01010101u);
-                uint32_t z2 = __vcmpeq4(w[j], 0x02020202u), z3 = __vcmpeq4(w[j], 0x03030303u);
-                c0 += __popc(z0) >> 3;
-                c1 += __popc(z1) >> 3;
-                c2 += __popc(z2) >> 3;
-                c3 += __popc(z3) >> 3;
-                uint32_t rest = ~(z0 | z1 | z2 | z3);
-                while (rest) {
-                    int b = (__ffs(rest) - 1) >> 3;
-                    atomicAdd(&sh_hist[(w[j] >> (8 * b)) & 0xffu], 1u);
-                    rest &= ~(0xffu << (8 * b));
-                }
-                if (bits16) out |= msb_nibble(__vcmpgtu4(w[j], thr)) << (4 * j);
+                else
+                    out |= tally_word(w[j], thr, c0, c1, c2, c3, sh_hist) << (4 * j);
             }
         }
         if (bits16) bits16[g] = (uint16_t)out;
@@ -416,6 +694,36 @@ void launch_insert_batch(brgpu_ctx *ctx, uint8_t *d_bits, int k, const uint64_t 
     ProfScope ps(ctx, "insert_batch", (double)n * 72.0);
     insert_batch_kernel<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(reinterpret_cast<uint32_t *>(d_bits), k,
                                                                            d_kmers, n);
+}
+
+// ------------------------------------------------------------------------------------------
+// Occupancy summary: summary bit j = OR of the 2^shift bitfield bits of block j.  One warp
+// produces one summary word per iteration (lane l reduces block 32*g + l, ballot packs them).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    build_summary_kernel(const uint32_t *__restrict__ bits32, uint64_t n_words, int words_per_block_log2,
+                         uint32_t *__restrict__ summary, uint64_t n_summary_words) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint64_t wpb = 1ULL << words_per_block_log2;
+    for (uint64_t g = warp; g < n_summary_words; g += n_warps) {
+        uint64_t first = ((g << 5) + (uint64_t)lane) << words_per_block_log2;
+        uint32_t acc = 0;
+        for (uint64_t t = 0; t < wpb; t++)
+            if (first + t < n_words) acc |= __ldcs(bits32 + first + t);
+        uint32_t m = __ballot_sync(FULL, acc != 0);
+        if (lane == 0) summary[g] = m;
+    }
+}
+
+void launch_build_summary(brgpu_ctx *ctx, const uint8_t *d_bits, uint64_t n_bytes, int shift, uint32_t *d_summary) {
+    uint64_t n_words = n_bytes >> 2;
+    uint64_t n_blocks = (n_bytes << 3) >> shift;
+    uint64_t n_summary_words = (n_blocks + 31) >> 5;
+    ProfScope ps(ctx, "build_summary", (double)n_bytes + (double)n_summary_words * 4.0);
+    build_summary_kernel<<<grid_for(ctx, n_summary_words * 32, 256, 8), 256, 0, ctx->stream>>>(
+        reinterpret_cast<const uint32_t *>(d_bits), n_words, shift - 5, d_summary, n_summary_words);
 }
 
 // ------------------------------------------------------------------------------------------

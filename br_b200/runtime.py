@@ -1,5 +1,6 @@
 """Context and device-resident record chunks (host side of include/brgpu.h)."""
 import ctypes as C
+import weakref
 
 import numpy as np
 
@@ -46,9 +47,17 @@ class Context:
         check(lib.brgpu_ctx_create(int(device), raw, C.byref(h)))
         self._h = h
         self.device = int(device)
+        self._children = weakref.WeakSet()  # live Reads / Pcon / Counter handles of this context
+
+    def _adopt(self, child):
+        self._children.add(child)
 
     def close(self):
+        """Frees every handle still alive in this context, then the context itself (the C
+        objects keep a raw pointer to their context, so the order matters)."""
         if getattr(self, "_h", None):
+            for child in list(self._children):
+                child.free()
             lib.brgpu_ctx_destroy(self._h)
             self._h = None
 
@@ -92,6 +101,7 @@ class Reads:
     def __init__(self, ctx, handle):
         self.ctx = ctx
         self._h = handle
+        ctx._adopt(self)
 
     @classmethod
     def upload(cls, ctx, seq, offsets):
@@ -104,9 +114,9 @@ class Reads:
         return r
 
     def free(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and getattr(self.ctx, "_h", None):
             lib.brgpu_reads_free(self._h)
-            self._h = None
+        self._h = None
 
     def __del__(self):
         self.free()

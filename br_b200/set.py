@@ -44,7 +44,7 @@ class Pcon(KmerSet):
     def __init__(self, ctx: Context, handle):
         self.ctx = ctx
         self._h = handle
-        self._mirror = None
+        ctx._adopt(self)
 
     # --- constructors ------------------------------------------------------------------------
     @classmethod
@@ -149,9 +149,9 @@ class Pcon(KmerSet):
         return bytes([self.k()]) + self.bitfield().tobytes()
 
     def free(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and getattr(self.ctx, "_h", None):
             lib.brgpu_set_free(self._h)
-            self._h = None
+        self._h = None
 
     def __del__(self):
         self.free()
@@ -165,6 +165,7 @@ class Counter:
         h = C.c_void_p()
         check(lib.brgpu_counts_create(ctx._h, k, C.byref(h)), ctx._h)
         self._h = h
+        ctx._adopt(self)
 
     def count(self, reads: Reads):
         check(lib.brgpu_counts_add_reads(self._h, reads._h), self.ctx._h)
@@ -192,9 +193,9 @@ class Counter:
         return Pcon(self.ctx, h)
 
     def free(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and getattr(self.ctx, "_h", None):
             lib.brgpu_counts_free(self._h)
-            self._h = None
+        self._h = None
 
     def __del__(self):
         self.free()

@@ -173,3 +173,40 @@ def test_k17_count_and_threshold_against_oracle(gpu, oracle):
     assert hashlib.sha256(gb.tobytes()).digest() == hashlib.sha256(ob.tobytes()).digest()
     km = all_forward_kmers(seq[: int(off[20])], off[:21], 17)
     assert np.array_equal(s.get_batch(km), oracle.Solid.from_bitfield(17, ob).get_batch(km))
+
+
+@pytest.mark.parametrize("k", [15, 17])
+def test_bucketed_and_table_counting_paths_agree(gpu, oracle, k):
+    """Pcon.from_reads takes the bucketed (L2-resident) counting path for k = 15/17, Counter the
+    literal table path; both must give the oracle's spectrum and bitfield, including saturated
+    counters (poly-A), any-byte nucleotides and the data-derived first-minimum threshold."""
+    br, ctx = gpu
+    from br_b200 import synth
+
+    genome = synth.make_genome(150_000, seed=7)
+    seq, off, _ = synth.make_reads(genome, 15, 0.08, seed=8, mean_len=2500)
+    extra = np.frombuffer(b"A" * 3000 + b"ACGTNNNNacgtnnACGT" * 50, dtype=np.uint8)
+    seq = np.concatenate([seq, extra])
+    off = np.concatenate([off, [off[-1] + 3000, off[-1] + extra.size]]).astype(np.uint64)
+    reads = br.Reads.upload(ctx, seq, off)
+    oc = oracle.Counter(k)
+    oc.count(seq, off, threads=8)
+    ohist = oc.spectrum(threads=8)
+    assert int(ohist[255]) >= 1  # the poly-A k-mer saturates
+    c = br.Counter(ctx, k)
+    c.count(reads)
+    assert np.array_equal(c.spectrum(), ohist)
+    for kwargs in ({"abundance": 2}, {"abundance": 0}, {"abundance_selection": "first-minimum"}):
+        s = br.Pcon.from_reads(ctx, reads, k, **kwargs)  # bucketed
+        ab = s.abundance
+        assert np.array_equal(s.spectrum(), ohist), kwargs
+        if "abundance" in kwargs:
+            assert ab == kwargs["abundance"]
+        else:
+            assert ab == oracle.Counter.first_minimum(ohist)
+        t = c.to_set(ab)  # table path
+        gb = s.bitfield()
+        assert hashlib.sha256(gb.tobytes()).digest() == hashlib.sha256(t.bitfield().tobytes()).digest(), kwargs
+        assert hashlib.sha256(gb.tobytes()).digest() == hashlib.sha256(oc.to_solid(ab, threads=8).bits().tobytes()).digest()
+        t.free()
+        s.free()
