@@ -90,6 +90,12 @@ class ClockSampler:
                 stdout=self.tmp, stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
+            return
+        # nvidia-smi's start-up (NVML initialisation) holds driver locks for a second or two; wait
+        # for its first sample so that none of that lands in a timed region
+        t0 = time.time()
+        while time.time() - t0 < 10.0 and os.path.getsize(self.tmp.name) == 0 and self.proc.poll() is None:
+            time.sleep(0.05)
 
     def stop(self):
         if self.proc is not None:

@@ -69,6 +69,11 @@ SIGNATURES = {
     "brgpu_counts_merge_slice": (C.c_int, [vp, vp, C.c_int, u64, u64]),
     "brgpu_counts_spectrum_slice": (C.c_int, [vp, u64, u64, vp]),
     "brgpu_set_threshold_slice": (C.c_int, [vp, vp, C.c_int, u64, u64]),
+    "brgpu_kmers_create": (C.c_int, [vp, C.c_int, vp, pvp]),
+    "brgpu_kmers_buckets": (u64, [vp]),
+    "brgpu_kmers_ipc_export": (C.c_int, [vp, vp]),
+    "brgpu_kmers_count_range": (C.c_int, [vp, vp, vp, C.c_int, u64, u64, C.c_int, vp, vp]),
+    "brgpu_kmers_free": (None, [vp]),
     "brgpu_profile_enable": (C.c_int, [vp, C.c_int]),
     "brgpu_profile_reset": (C.c_int, [vp]),
     "brgpu_profile_count": (C.c_int, [vp]),

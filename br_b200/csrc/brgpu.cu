@@ -608,62 +608,91 @@ static bool bucketed_applicable(int k, const brgpu_reads *reads) {
 
 static void summary_geometry(int k, int *shift, uint64_t *bytes);
 
+// partition the k-mers of `reads` into buckets (hist -> scan -> scatter)
+static int kmers_create(brgpu_ctx *ctx, int k, const brgpu_reads *reads, brgpu_kmers **out) {
+    const Layout &L = *reads->layout;
+    brgpu_kmers *km = new (std::nothrow) brgpu_kmers;
+    if (!km) return fail(ctx, BRGPU_E_NOMEM, "host allocation");
+    km->ctx = ctx;
+    km->k = k;
+    km->n_buckets = table_len(k) >> BUCKET_BITS_HOST;
+    km->capacity = L.total_slots ? L.total_slots : 1; // every k-mer starts at a distinct slot position
+    km->n_kmers_hint = (double)reads->sum_len;
+    uint32_t *d_fill = nullptr;
+    uint64_t *d_tmp = nullptr;
+    cudaError_t e;
+    // residues and offsets are cudaMalloc-backed (exportable over CUDA IPC for the multi-GPU path)
+    if ((e = big_alloc(ctx, (void **)&km->d_res, km->capacity * 2)) != cudaSuccess ||
+        (e = big_alloc(ctx, (void **)&km->d_base, (km->n_buckets + 1) * 8)) != cudaSuccess ||
+        (e = dalloc(ctx, &d_fill, km->n_buckets)) != cudaSuccess ||
+        (e = dalloc(ctx, &d_tmp, km->n_buckets / 4096 + 4)) != cudaSuccess) {
+        if (d_fill) cudaFreeAsync(d_fill, ctx->stream);
+        big_free(ctx, km->d_res, km->capacity * 2);
+        big_free(ctx, km->d_base, (km->n_buckets + 1) * 8);
+        delete km;
+        return fail(ctx, BRGPU_E_NOMEM, "device allocation (bucketed k-mers)", e);
+    }
+    launch_bucket_partition(ctx, L, reads->d_seq, reads->d_len, k, km->n_buckets, d_fill, km->d_base, d_tmp, km->d_res,
+                            km->n_kmers_hint);
+    cudaFreeAsync(d_fill, ctx->stream);
+    cudaFreeAsync(d_tmp, ctx->stream);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        big_free(ctx, km->d_res, km->capacity * 2);
+        big_free(ctx, km->d_base, (km->n_buckets + 1) * 8);
+        delete km;
+        return fail(ctx, BRGPU_E_CUDA, "k-mer partition", e);
+    }
+    *out = km;
+    return BRGPU_OK;
+}
+
+static void kmers_release(brgpu_kmers *km) {
+    if (!km) return;
+    big_free(km->ctx, km->d_res, km->capacity * 2);
+    big_free(km->ctx, km->d_base, (km->n_buckets + 1) * 8);
+    delete km;
+}
+
+static cudaError_t read_hist(brgpu_ctx *ctx, uint64_t hist[256]) {
+    cudaError_t e = cudaMemcpyAsync(ctx->h_pinned, ctx->d_hist, 256 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) memcpy(hist, ctx->h_pinned, 256 * sizeof(uint64_t));
+    return e;
+}
+
 static int set_from_reads_bucketed(brgpu_ctx *ctx, int k, int abundance, int selection, const brgpu_reads *reads,
                                    brgpu_set **out) {
-    const Layout &L = *reads->layout;
-    const uint64_t n_buckets = table_len(k) >> BUCKET_BITS_HOST;
-    const double n_kmers = (double)reads->sum_len;
-    uint32_t *d_fill = nullptr;
-    uint64_t *d_base = nullptr, *d_tmp = nullptr;
-    uint16_t *d_res = nullptr;
+    brgpu_kmers *km = nullptr;
+    int st = kmers_create(ctx, k, reads, &km);
+    if (st != BRGPU_OK) return st;
     brgpu_set *s = nullptr;
-    int st = BRGPU_OK;
-    cudaError_t e = cudaSuccess;
-    auto cleanup = [&]() {
-        if (d_fill) cudaFreeAsync(d_fill, ctx->stream);
-        if (d_base) cudaFreeAsync(d_base, ctx->stream);
-        if (d_tmp) cudaFreeAsync(d_tmp, ctx->stream);
-        if (d_res) cudaFreeAsync(d_res, ctx->stream);
-    };
-    // every k-mer starts at a distinct slot position, so total_slots bounds their number
-    if ((e = dalloc(ctx, &d_fill, n_buckets)) != cudaSuccess || (e = dalloc(ctx, &d_base, n_buckets + 1)) != cudaSuccess ||
-        (e = dalloc(ctx, &d_tmp, n_buckets / 4096 + 4)) != cudaSuccess ||
-        (e = dalloc(ctx, &d_res, L.total_slots)) != cudaSuccess) {
-        cleanup();
-        return fail(ctx, BRGPU_E_NOMEM, "device allocation (bucketed counting)", e);
-    }
-    launch_bucket_partition(ctx, L, reads->d_seq, reads->d_len, k, n_buckets, d_fill, d_base, d_tmp, d_res, n_kmers);
     st = set_alloc(ctx, k, &s);
     if (st != BRGPU_OK) {
-        cleanup();
+        kmers_release(km);
         return st;
     }
+    cudaError_t e = cudaSuccess;
     int shift;
     uint64_t sbytes;
     summary_geometry(k, &shift, &sbytes);
     if (sbytes && shift == 5) {
         e = big_alloc(ctx, (void **)&s->d_summary, sbytes);
         if (e != cudaSuccess) {
-            cleanup();
+            kmers_release(km);
             brgpu_set_free(s);
             return fail(ctx, BRGPU_E_NOMEM, "device allocation (summary)", e);
         }
         s->summary_bytes = sbytes;
         s->summary_shift = shift;
     }
-    auto read_hist = [&](uint64_t hist[256]) -> cudaError_t {
-        cudaError_t e2 = cudaMemcpyAsync(ctx->h_pinned, ctx->d_hist, 256 * sizeof(uint64_t), cudaMemcpyDeviceToHost,
-                                         ctx->stream);
-        if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(ctx->stream);
-        if (e2 == cudaSuccess) memcpy(hist, ctx->h_pinned, 256 * sizeof(uint64_t));
-        return e2;
-    };
     uint64_t hist[256];
     if (selection == BRGPU_ABUNDANCE_FIRST_MINIMUM) {
         // the threshold depends on the spectrum: one counting sweep without output first
         cudaMemsetAsync(ctx->d_hist, 0, 256 * sizeof(uint64_t), ctx->stream);
-        launch_bucket_count(ctx, d_res, d_base, n_buckets, 0, nullptr, nullptr, 0, ctx->d_hist, n_kmers);
-        e = read_hist(hist);
+        launch_bucket_count(ctx, km->d_res, km->d_base, km->n_buckets, 0, nullptr, nullptr, 0, ctx->d_hist,
+                            km->n_kmers_hint);
+        e = read_hist(ctx, hist);
         if (e == cudaSuccess) {
             abundance = brgpu_spectrum_first_minimum(hist);
             if (abundance < 0) st = fail(ctx, BRGPU_E_NO_THRESHOLD, "can't compute the abundance threshold");
@@ -671,12 +700,12 @@ static int set_from_reads_bucketed(brgpu_ctx *ctx, int k, int abundance, int sel
     }
     if (e == cudaSuccess && st == BRGPU_OK) {
         cudaMemsetAsync(ctx->d_hist, 0, 256 * sizeof(uint64_t), ctx->stream);
-        launch_bucket_count(ctx, d_res, d_base, n_buckets, abundance, s->d_bits, s->d_summary, s->summary_shift,
-                            ctx->d_hist, n_kmers);
-        e = read_hist(hist);
+        launch_bucket_count(ctx, km->d_res, km->d_base, km->n_buckets, abundance, s->d_bits, s->d_summary,
+                            s->summary_shift, ctx->d_hist, km->n_kmers_hint);
+        e = read_hist(ctx, hist);
     }
     if (e == cudaSuccess) e = cudaGetLastError();
-    cleanup();
+    kmers_release(km);
     if (e != cudaSuccess) st = fail(ctx, BRGPU_E_CUDA, "bucketed counting", e);
     if (st != BRGPU_OK) {
         brgpu_set_free(s);
@@ -686,6 +715,76 @@ static int set_from_reads_bucketed(brgpu_ctx *ctx, int k, int abundance, int sel
     s->summary_valid = s->d_summary != nullptr; // written by the counting sweep itself
     memcpy(s->hist, hist, sizeof(hist));
     *out = s;
+    return BRGPU_OK;
+}
+
+// ---- multi-GPU building blocks on bucketed k-mers ----
+extern "C" int brgpu_kmers_create(brgpu_ctx *ctx, int k, const brgpu_reads *reads, brgpu_kmers **out) {
+    if (!ctx || !reads || !out) return BRGPU_E_INVALID;
+    *out = nullptr;
+    if (!k_supported(k) || k < 15) return fail(ctx, BRGPU_E_INVALID, "bucketed k-mers need odd k in 15..=19");
+    if (reads->ctx != ctx) return fail(ctx, BRGPU_E_INVALID, "reads belong to another context");
+    if (!bucketed_applicable(k, reads)) return fail(ctx, BRGPU_E_INVALID, "chunk too large for 32-bit bucket cursors");
+    cudaSetDevice(ctx->device);
+    return kmers_create(ctx, k, reads, out);
+}
+
+extern "C" void brgpu_kmers_free(brgpu_kmers *km) {
+    if (!km) return;
+    cudaSetDevice(km->ctx->device);
+    kmers_release(km);
+}
+
+extern "C" uint64_t brgpu_kmers_buckets(const brgpu_kmers *km) { return km ? km->n_buckets : 0; }
+
+extern "C" int brgpu_kmers_ipc_export(brgpu_kmers *km, uint8_t handles_out[128]) {
+    if (!km || !handles_out) return BRGPU_E_INVALID;
+    brgpu_ctx *ctx = km->ctx;
+    cudaSetDevice(ctx->device);
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, km->d_res));
+    memcpy(handles_out, &h, 64);
+    CK(cudaIpcGetMemHandle(&h, km->d_base));
+    memcpy(handles_out + 64, &h, 64);
+    return BRGPU_OK;
+}
+
+extern "C" int brgpu_kmers_count_range(brgpu_kmers *km, void *const *peer_residues, void *const *peer_offsets,
+                                       int n_peers, uint64_t bucket_begin, uint64_t bucket_end, int abundance,
+                                       brgpu_set *set, uint64_t hist_host[256]) {
+    if (!km || !hist_host || (n_peers && (!peer_residues || !peer_offsets))) return BRGPU_E_INVALID;
+    brgpu_ctx *ctx = km->ctx;
+    if (n_peers < 0 || n_peers > 15) return fail(ctx, BRGPU_E_INVALID, "at most 15 peers");
+    if (bucket_begin > bucket_end || bucket_end > km->n_buckets) return fail(ctx, BRGPU_E_INVALID, "bad bucket range");
+    if (set && (set->ctx != ctx || set->k != km->k)) return fail(ctx, BRGPU_E_INVALID, "set does not match");
+    if (set && (abundance < 0 || abundance > 255)) return fail(ctx, BRGPU_E_INVALID, "abundance must be in 0..=255");
+    cudaSetDevice(ctx->device);
+    const uint64_t nb = bucket_end - bucket_begin;
+    // bring the peers' bucket offsets of this range into local memory (8 B per bucket and peer)
+    uint64_t *d_pb = nullptr;
+    if (n_peers) CK(dalloc(ctx, &d_pb, (uint64_t)n_peers * (nb + 1)));
+    const uint16_t *res[16];
+    const uint64_t *base[16];
+    res[0] = km->d_res;
+    base[0] = km->d_base;
+    for (int p = 0; p < n_peers; p++) {
+        uint64_t *dst = d_pb + (uint64_t)p * (nb + 1);
+        CK(cudaMemcpyAsync(dst, (const uint64_t *)peer_offsets[p] + bucket_begin, (nb + 1) * 8, cudaMemcpyDefault,
+                           ctx->stream));
+        res[p + 1] = (const uint16_t *)peer_residues[p];
+        base[p + 1] = dst - bucket_begin; // indexable by absolute bucket id inside the range
+    }
+    CK(cudaMemsetAsync(ctx->d_hist, 0, 256 * sizeof(uint64_t), ctx->stream));
+    if (set) {
+        set->abundance = abundance;
+        set->summary_valid = false;
+    }
+    launch_bucket_count_multi(ctx, res, base, n_peers + 1, bucket_begin, bucket_end, set ? abundance : 0,
+                              set ? set->d_bits : nullptr, ctx->d_hist, km->n_kmers_hint * (double)(n_peers + 1));
+    cudaError_t e = read_hist(ctx, hist_host);
+    if (d_pb) cudaFreeAsync(d_pb, ctx->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ctx, BRGPU_E_CUDA, "sharded bucket counting", e);
     return BRGPU_OK;
 }
 

@@ -175,12 +175,42 @@ struct Corr {
     uint32_t offset;   // read bases consumed
 };
 
+// Warp-cooperative byte copy with arbitrary alignment on both sides: the destination is
+// written as aligned 32-bit words, each assembled from two aligned source words with a funnel
+// shift (128 B per warp step instead of 32).  May read up to 3 bytes beyond src + n inside the
+// last aligned source word; all callers copy out of 32-byte-granular slot / scratch regions.
+__device__ __forceinline__ void warp_copy(uint8_t *dst, const uint8_t *src, uint32_t n, int lane) {
+    if (n < 64) {
+        for (uint32_t t = lane; t < n; t += 32) dst[t] = src[t];
+        return;
+    }
+    const uint32_t head = (uint32_t)((4u - ((uintptr_t)dst & 3u)) & 3u); // bytes until dst is word aligned
+    if ((uint32_t)lane < head) dst[lane] = src[lane];
+    const uint8_t *s0 = src + head;
+    uint32_t *d4 = reinterpret_cast<uint32_t *>(dst + head);
+    const uint32_t n_words = (n - head) >> 2;
+    const uint32_t a = (uint32_t)((uintptr_t)s0 & 3u);
+    const uint32_t *s4 = reinterpret_cast<const uint32_t *>(s0 - a);
+    for (uint32_t w = lane; w < n_words; w += 32) {
+        uint32_t lo = s4[w];
+        uint32_t v = lo;
+        if (a) v = __funnelshift_r(lo, s4[w + 1], 8 * a);
+        d4[w] = v;
+    }
+    const uint32_t done = head + (n_words << 2);
+    if (done + (uint32_t)lane < n) dst[done + lane] = src[done + lane]; // at most 3 tail bytes
+}
+
 __device__ __forceinline__ void copy_range(Rd &rd, uint32_t from, uint32_t to) {
     if (to <= from) return;
     uint32_t n = to - from;
-    for (uint32_t t = rd.lane; t < n; t += 32) {
-        uint32_t dst = rd.o + t;
-        if (dst < rd.cap) rd.out[dst] = rd.in[from + t];
+    if (rd.o + n <= rd.cap) {
+        warp_copy(rd.out + rd.o, rd.in + from, n, rd.lane);
+    } else { // the slot overflows: keep counting, write what fits
+        for (uint32_t t = rd.lane; t < n; t += 32) {
+            uint32_t dst = rd.o + t;
+            if (dst < rd.cap) rd.out[dst] = rd.in[from + t];
+        }
     }
     rd.o += n;
 }
@@ -1148,7 +1178,7 @@ __global__ void seg_count_kernel(const uint32_t *__restrict__ len, uint32_t n_re
 }
 
 template <int METHOD>
-__global__ void __launch_bounds__(SCAN_WARPS_PER_BLOCK * 32)
+__global__ void __launch_bounds__(SCAN_WARPS_PER_BLOCK * 32, (METHOD == BRGPU_ONE || METHOD == BRGPU_TWO) ? 12 : 1)
     scan_spec_kernel(const uint8_t *__restrict__ in, const uint32_t *__restrict__ len_in,
                      const uint64_t *__restrict__ slot_off, const uint32_t *__restrict__ bitmap,
                      const uint64_t *__restrict__ seg_first, uint32_t n_reads, uint8_t *__restrict__ seg_out,
@@ -1260,9 +1290,13 @@ __global__ void __launch_bounds__(SCAN_WARPS_PER_BLOCK * 32)
                     const uint32_t skip = first ? 0u : q - in0;          // 1:1 copy region before q
                     const uint8_t *src = seg_out + (g0 + sidx) * SEG_CAP + skip;
                     const uint32_t n = rec.out_len - skip;
-                    for (uint32_t t = lane; t < n; t += 32) {
-                        uint32_t dst = rd.o + t;
-                        if (dst < rd.cap) rd.out[dst] = src[t];
+                    if (rd.o + n <= rd.cap) {
+                        warp_copy(rd.out + rd.o, src, n, lane);
+                    } else {
+                        for (uint32_t t = lane; t < n; t += 32) {
+                            uint32_t dst = rd.o + t;
+                            if (dst < rd.cap) rd.out[dst] = src[t];
+                        }
                     }
                     rd.o += n;
                     q = rec.q_exit;

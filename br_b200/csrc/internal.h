@@ -74,6 +74,17 @@ struct brgpu_counts {
     uint8_t *d_counts = nullptr;
 };
 
+// a chunk's k-mers partitioned by table-index range: 16-bit residues grouped by index >> 15
+struct brgpu_kmers {
+    brgpu_ctx *ctx = nullptr;
+    int k = 0;
+    uint64_t n_buckets = 0;
+    uint64_t capacity = 0;       // residues allocated (u16 each)
+    uint16_t *d_res = nullptr;   // cudaMalloc'ed: exported over CUDA IPC
+    uint64_t *d_base = nullptr;  // n_buckets + 1, cudaMalloc'ed
+    double n_kmers_hint = 0;
+};
+
 struct brgpu_set {
     brgpu_ctx *ctx = nullptr;
     int k = 0;
@@ -129,6 +140,9 @@ void launch_bucket_partition(brgpu_ctx *ctx, const Layout &L, const uint8_t *d_s
 void launch_bucket_count(brgpu_ctx *ctx, const uint16_t *d_residues, const uint64_t *d_base, uint64_t n_buckets,
                          int abundance, uint8_t *d_bits, uint32_t *d_summary, int summary_shift, uint64_t *d_hist,
                          double n_kmers);
+void launch_bucket_count_multi(brgpu_ctx *ctx, const uint16_t *const *d_res, const uint64_t *const *d_base, int n_src,
+                               uint64_t b0, uint64_t b1, int abundance, uint8_t *d_bits, uint64_t *d_hist,
+                               double n_kmers);
 void launch_get_batch(brgpu_ctx *ctx, const uint8_t *d_bits, int k, const uint64_t *d_kmers, uint64_t n,
                       uint8_t *d_out);
 void launch_insert_batch(brgpu_ctx *ctx, uint8_t *d_bits, int k, const uint64_t *d_kmers, uint64_t n);

@@ -394,20 +394,17 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     bucket_scatter_kernel(const uint8_t *__restrict__ seq, const uint32_t *__restrict__ len,
                           const uint64_t *__restrict__ slot_off, const uint32_t *__restrict__ word2read,
-                          uint64_t n_words, int k, const uint64_t *__restrict__ base, uint32_t *__restrict__ fill,
-                          uint16_t *__restrict__ residues) {
+                          uint64_t n_words, int k, uint32_t *__restrict__ cursor, uint16_t *__restrict__ residues) {
     const uint64_t mask = kmask(k);
     for (uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < n_words;
          w += (uint64_t)gridDim.x * blockDim.x)
         for_each_kmer_index8(seq, len, slot_off, word2read, w, k, mask, [&](const uint64_t idx[8], const bool ok[8]) {
-            uint64_t pos[8];
+            // cursor[b] starts at the bucket's first slot, so one L2 atomic yields the position
+            uint32_t pos[8];
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 pos[j] = 0;
-                if (ok[j]) {
-                    uint64_t b = idx[j] >> BUCKET_BITS;
-                    pos[j] = __ldg(base + b) + (uint64_t)atomicAdd(fill + b, 1u);
-                }
+                if (ok[j]) pos[j] = atomicAdd(cursor + (idx[j] >> BUCKET_BITS), 1u);
             }
 #pragma unroll
             for (int j = 0; j < 8; j++)
@@ -428,6 +425,13 @@ __device__ __forceinline__ bool sat_inc_owner(uint32_t *wp, uint32_t sh) {
         old = atomicCAS(wp, assumed, assumed + one);
         if (old == assumed) return b == 0;
     }
+}
+
+__global__ void bucket_cursor_kernel(const uint64_t *__restrict__ base, uint64_t n_buckets,
+                                     uint32_t *__restrict__ cursor) {
+    for (uint64_t b = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; b < n_buckets;
+         b += (uint64_t)gridDim.x * blockDim.x)
+        cursor[b] = (uint32_t)base[b]; // total k-mers < 2^32 (checked by the caller)
 }
 
 // pass 3: one block per bucket, counters in shared memory.  Work per bucket is proportional to
@@ -548,6 +552,136 @@ __global__ void __launch_bounds__(BUCKET_THREADS)
     if (threadIdx.x == 0 && zeros >= sh_owners) atomicAdd(g_hist + 0, zeros - sh_owners);
 }
 
+// Multi-source variant for the multi-GPU path: the k-mers of bucket b come from this rank's
+// residue array and from the residue arrays of the peer ranks, which are CUDA-IPC mappings of
+// the peers' HBM — the exchange step of the sharded set construction is these loads, over
+// NVLink, fused into the counting kernel (no staging copy, no collective).  Bucket offsets of
+// all sources are local (the peers' slices are copied in beforehand, they are tiny).
+constexpr int BUCKET_MAX_SOURCES = 16;
+struct BucketSources {
+    const uint16_t *res[BUCKET_MAX_SOURCES];
+    const uint64_t *base[BUCKET_MAX_SOURCES]; // indexable by absolute bucket id in [b0, b1]
+    int n;
+};
+
+__global__ void __launch_bounds__(BUCKET_THREADS)
+    bucket_count_multi_kernel(BucketSources src, uint64_t b0, uint64_t b1, int abundance,
+                              uint32_t *__restrict__ bitfield32, unsigned long long *__restrict__ g_hist) {
+    extern __shared__ uint32_t cnt[];
+    __shared__ uint32_t sh_bits[BUCKET_COUNTERS / 32];
+    __shared__ unsigned int sh_hist[256];
+    __shared__ uint64_t sh_beg[BUCKET_MAX_SOURCES];
+    __shared__ uint32_t sh_cum[BUCKET_MAX_SOURCES + 1];
+    __shared__ unsigned long long sh_owners;
+    uint8_t *cnt8 = reinterpret_cast<uint8_t *>(cnt);
+    for (int t = threadIdx.x; t < 256; t += BUCKET_THREADS) sh_hist[t] = 0;
+    for (int t = threadIdx.x; t < BUCKET_COUNTERS / 4; t += BUCKET_THREADS) cnt[t] = 0;
+    if (threadIdx.x == 0) sh_owners = 0;
+    uint32_t owners = 0;
+    unsigned long long zeros = 0;
+    __syncthreads();
+    for (uint64_t b = b0 + blockIdx.x; b < b1; b += gridDim.x) {
+        if (threadIdx.x < src.n) sh_beg[threadIdx.x] = __ldg(src.base[threadIdx.x] + b);
+        if (threadIdx.x == 0) {
+            uint32_t acc = 0;
+            for (int q = 0; q < src.n; q++) {
+                sh_cum[q] = acc;
+                acc += (uint32_t)(__ldg(src.base[q] + b + 1) - __ldg(src.base[q] + b));
+            }
+            sh_cum[src.n] = acc;
+        }
+        for (int t = threadIdx.x; t < BUCKET_COUNTERS / 32; t += BUCKET_THREADS) sh_bits[t] = 0;
+        __syncthreads();
+        const uint32_t total = sh_cum[src.n];
+        auto fetch = [&](uint32_t e) -> uint32_t { // e-th k-mer of the bucket over all sources
+            int q = 0;
+            while (e >= sh_cum[q + 1]) q++;
+            return (uint32_t)__ldcs(src.res[q] + sh_beg[q] + (e - sh_cum[q]));
+        };
+        uint32_t res[BUCKET_REG_ROUNDS];
+        uint32_t own = 0;
+#pragma unroll
+        for (int q = 0; q < BUCKET_REG_ROUNDS; q++) {
+            uint32_t e = threadIdx.x + (uint32_t)q * BUCKET_THREADS;
+            res[q] = e < total ? fetch(e) : 0xffffffffu;
+        }
+#pragma unroll
+        for (int q = 0; q < BUCKET_REG_ROUNDS; q++)
+            if (res[q] != 0xffffffffu && sat_inc_owner(cnt + (res[q] >> 2), (res[q] & 3u) * 8u)) own |= 1u << q;
+        for (uint32_t e = BUCKET_REG_ROUNDS * BUCKET_THREADS + threadIdx.x; e < total; e += BUCKET_THREADS) {
+            uint32_t r = fetch(e);
+            sat_inc_owner(cnt + (r >> 2), (r & 3u) * 8u);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < BUCKET_REG_ROUNDS; q++) {
+            if ((own >> q) & 1u) {
+                const uint32_t r = res[q];
+                const uint32_t c = cnt8[r];
+                cnt8[r] = 0;
+                owners++;
+                atomicAdd(&sh_hist[c], 1u);
+                if (c > (uint32_t)abundance) atomicOr(&sh_bits[r >> 5], 1u << (r & 31));
+            }
+        }
+        if (total > BUCKET_REG_ROUNDS * BUCKET_THREADS) __syncthreads(); // block-uniform
+        for (uint32_t e = BUCKET_REG_ROUNDS * BUCKET_THREADS + threadIdx.x; e < total; e += BUCKET_THREADS) {
+            const uint32_t r = fetch(e);
+            const uint32_t sh = (r & 3u) * 8u;
+            const uint32_t old = atomicAnd(cnt + (r >> 2), ~(0xffu << sh));
+            const uint32_t c = (old >> sh) & 0xffu;
+            if (c) {
+                owners++;
+                atomicAdd(&sh_hist[c], 1u);
+                if (c > (uint32_t)abundance) atomicOr(&sh_bits[r >> 5], 1u << (r & 31));
+            }
+        }
+        __syncthreads();
+        if (bitfield32)
+            for (int t = threadIdx.x; t < BUCKET_COUNTERS / 32; t += BUCKET_THREADS)
+                bitfield32[b * (BUCKET_COUNTERS / 32) + (uint64_t)t] = sh_bits[t];
+        if (threadIdx.x == 0) zeros += BUCKET_COUNTERS;
+        __syncthreads();
+    }
+    owners = __reduce_add_sync(FULL, owners);
+    if ((threadIdx.x & 31) == 0 && owners) atomicAdd(&sh_owners, (unsigned long long)owners);
+    __syncthreads();
+    for (int t = threadIdx.x; t < 256; t += BUCKET_THREADS)
+        if (t > 0 && sh_hist[t]) atomicAdd(g_hist + t, (unsigned long long)sh_hist[t]);
+    if (threadIdx.x == 0 && zeros >= sh_owners) atomicAdd(g_hist + 0, zeros - sh_owners);
+}
+
+void launch_bucket_count_multi(brgpu_ctx *ctx, const uint16_t *const *d_res, const uint64_t *const *d_base, int n_src,
+                               uint64_t b0, uint64_t b1, int abundance, uint8_t *d_bits, uint64_t *d_hist,
+                               double n_kmers) {
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(bucket_count_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BUCKET_COUNTERS);
+        cudaFuncSetAttribute(bucket_count_multi_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
+        configured = true;
+    }
+    if (b1 <= b0) return;
+    BucketSources src;
+    src.n = n_src;
+    for (int q = 0; q < BUCKET_MAX_SOURCES; q++) {
+        src.res[q] = q < n_src ? d_res[q] : nullptr;
+        src.base[q] = q < n_src ? d_base[q] : nullptr;
+    }
+    ProfScope ps(ctx, "bucket_count_multi", n_kmers * 2.0 + (double)(b1 - b0) * (BUCKET_COUNTERS / 8));
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bucket_count_multi_kernel, BUCKET_THREADS,
+                                                      BUCKET_COUNTERS) != cudaSuccess ||
+        per_sm < 1) {
+        cudaGetLastError();
+        per_sm = 1;
+    }
+    uint64_t cap = (uint64_t)ctx->sm_count * (uint64_t)per_sm;
+    uint64_t nb = b1 - b0;
+    bucket_count_multi_kernel<<<(unsigned)(nb < cap ? nb : cap), BUCKET_THREADS, BUCKET_COUNTERS, ctx->stream>>>(
+        src, b0, b1, abundance, reinterpret_cast<uint32_t *>(d_bits), reinterpret_cast<unsigned long long *>(d_hist));
+}
+
 void launch_bucket_partition(brgpu_ctx *ctx, const Layout &L, const uint8_t *d_seq, const uint32_t *d_len, int k,
                              uint64_t n_buckets, uint32_t *d_fill, uint64_t *d_base, uint64_t *d_scan_tmp,
                              uint16_t *d_residues, double n_kmers) {
@@ -559,11 +693,12 @@ void launch_bucket_partition(brgpu_ctx *ctx, const Layout &L, const uint8_t *d_s
                                                                                     L.d_word2read, n_words, k, d_fill);
     }
     launch_exclusive_scan_u32(ctx, d_fill, n_buckets, d_base, d_scan_tmp);
-    cudaMemsetAsync(d_fill, 0, n_buckets * sizeof(uint32_t), ctx->stream);
     {
         ProfScope ps(ctx, "bucket_scatter", n_kmers * 3.0); // ASCII in + 2 B residue out
+        bucket_cursor_kernel<<<grid_for(ctx, n_buckets, 256, 8), 256, 0, ctx->stream>>>(d_base, n_buckets, d_fill);
         bucket_scatter_kernel<<<grid_for(ctx, n_words, 256, 8), 256, 0, ctx->stream>>>(
-            d_seq, d_len, L.d_slot_off, L.d_word2read, n_words, k, d_base, d_fill, d_residues);
+            d_seq, d_len, L.d_slot_off, L.d_word2read, n_words, k, d_fill, d_residues);
+        ctx->launches += 1;
     }
 }
 

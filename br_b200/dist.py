@@ -39,8 +39,57 @@ def shard_records(offsets, world, rank):
     return min(lo, n), min(hi, n)
 
 
+BUCKET_BITS = 15  # table indices per bucket = 2^15 (must match BUCKET_BITS in csrc/set_kernels.cu)
+
+
+def bucket_bounds(n_buckets, world, rank):
+    """Contiguous bucket range owned by `rank` (last rank takes the remainder)."""
+    per = n_buckets // world
+    if per == 0:
+        return (0, n_buckets) if rank == 0 else (n_buckets, n_buckets)
+    return per * rank, (n_buckets if rank == world - 1 else per * (rank + 1))
+
+
+def _pick_abundance(ops, abundance, abundance_selection, spectrum_of_range):
+    if abundance is not None:
+        return int(abundance)
+    if abundance_selection not in ("first-minimum", "first_minimum"):
+        raise ValueError("need an abundance threshold or an abundance method")
+    hist = ops.all_reduce_sum(spectrum_of_range())  # 2 KiB
+    a = ops.first_minimum(hist)
+    if a is None:
+        raise RuntimeError("can't compute the abundance threshold")
+    return int(a)
+
+
 def build_set_sharded(ops, k, abundance=None, abundance_selection=None):
-    """Runs the exchange protocol; returns whatever `ops.finish()` returns (the replicated set)."""
+    """Runs the exchange protocol; returns whatever `ops.finish()` returns (the replicated set).
+
+    k >= 15: no count tables at all.  Every rank partitions its own k-mers into buckets of 2^15
+    table indices, exports the partition, and counts its own bucket range over all ranks'
+    partitions (the peers' residues are read over NVLink inside the counting kernel).
+    k < 15: the literal table protocol (private tables, saturating merge of the owned slice)."""
+    if k >= 15 and getattr(ops, "supports_kmers", False):
+        return _build_from_kmers(ops, k, abundance, abundance_selection)
+    return _build_from_tables(ops, k, abundance, abundance_selection)
+
+
+def _build_from_kmers(ops, k, abundance, abundance_selection):
+    world, rank = ops.world, ops.rank
+    n_buckets = 1 << (2 * k - 1 - BUCKET_BITS)
+    b0, b1 = bucket_bounds(n_buckets, world, rank)
+    ops.partition_local(k)                   # bucket_hist -> scan -> bucket_scatter on the own shard
+    handles = ops.exchange_kmer_handles()    # all-gather of the IPC handles
+    ops.barrier()                            # every partition is complete before anyone reads it
+    ops.open_peers(handles)
+    abundance = _pick_abundance(ops, abundance, abundance_selection, lambda: ops.count_range(b0, b1, None))
+    ops.count_range(b0, b1, abundance)       # count + threshold the owned range (peer loads over NVLink)
+    ops.all_gather_bitfield(b0 << BUCKET_BITS, b1 << BUCKET_BITS, 1 << (2 * k - 1))
+    ops.barrier()                            # peers are done reading this rank's partition
+    return ops.finish(abundance)
+
+
+def _build_from_tables(ops, k, abundance, abundance_selection):
     world, rank = ops.world, ops.rank
     n = 1 << (2 * k - 1)
     begin, end = slice_bounds(n, world, rank)
@@ -48,18 +97,11 @@ def build_set_sharded(ops, k, abundance=None, abundance_selection=None):
     handles = ops.exchange_handles()         # all-gather of the 64-byte IPC handles
     ops.barrier()                            # every table is complete before anyone reads it
     ops.merge_slice(handles, begin, end)     # saturating reduce of slice `rank` over NVLink
-    if abundance is None:
-        if abundance_selection not in ("first-minimum", "first_minimum"):
-            raise ValueError("need an abundance threshold or an abundance method")
-        hist = ops.spectrum_slice(begin, end)
-        hist = ops.all_reduce_sum(hist)      # 2 KiB
-        abundance = ops.first_minimum(hist)
-        if abundance is None:
-            raise RuntimeError("can't compute the abundance threshold")
-    ops.threshold_slice(int(abundance), begin, end)
-    ops.all_gather_bitfield(begin, end)      # NCCL all-gather of the bitfield slices
+    abundance = _pick_abundance(ops, abundance, abundance_selection, lambda: ops.spectrum_slice(begin, end))
+    ops.threshold_slice(abundance, begin, end)
+    ops.all_gather_bitfield(begin, end, n)   # NCCL all-gather of the bitfield slices
     ops.barrier()                            # peers are done reading this rank's table
-    return ops.finish(int(abundance))
+    return ops.finish(abundance)
 
 
 class _CudaArray:
@@ -81,8 +123,57 @@ class GpuOps:
         self.ctx, self.reads, self.group = ctx, reads, group
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.counter = None
+        self.kmers = None
         self.set = None
         self._peers = []
+        self.supports_kmers = True
+
+    # ---- bucketed k-mer protocol (k >= 15) ----
+    def partition_local(self, k):
+        from .set import Pcon
+
+        self.k = k
+        h = C.c_void_p()
+        check(lib.brgpu_kmers_create(self.ctx._h, k, self.reads._h, C.byref(h)), self.ctx._h)
+        self.kmers = h
+        self.set = Pcon.new(self.ctx, k)
+
+    def exchange_kmer_handles(self):
+        h = (C.c_uint8 * 128)()
+        check(lib.brgpu_kmers_ipc_export(self.kmers, h), self.ctx._h)
+        mine = self.torch.tensor(list(h), dtype=self.torch.uint8, device=f"cuda:{self.ctx.device}")
+        allh = [self.torch.empty_like(mine) for _ in range(self.world)]
+        self.dist.all_gather(allh, mine, group=self.group)
+        return [bytes(t.cpu().tolist()) for t in allh]
+
+    def _ipc_open_cached(self, handle: bytes):
+        """cudaIpcOpenMemHandle costs milliseconds (and so does closing); the library reuses its big
+        buffers from call to call, so the peers' handles repeat — keep the mappings per context."""
+        cache = self.ctx.__dict__.setdefault("_ipc_cache", {})
+        p = cache.get(handle)
+        if p is None:
+            p = C.c_void_p()
+            check(lib.brgpu_ipc_open(self.ctx._h, (C.c_uint8 * 64).from_buffer_copy(handle), C.byref(p)), self.ctx._h)
+            cache[handle] = p
+        return p
+
+    def open_peers(self, handles):
+        self._peer_res, self._peer_off = [], []
+        for r, hb in enumerate(handles):
+            if r == self.rank:
+                continue
+            self._peer_res.append(self._ipc_open_cached(hb[:64]))
+            self._peer_off.append(self._ipc_open_cached(hb[64:]))
+
+    def count_range(self, b0, b1, abundance):
+        n = len(self._peer_res)
+        res = (C.c_void_p * max(1, n))(*[p.value for p in self._peer_res])
+        off = (C.c_void_p * max(1, n))(*[p.value for p in self._peer_off])
+        hist = np.zeros(256, dtype=np.uint64)
+        check(lib.brgpu_kmers_count_range(self.kmers, res, off, n, b0, b1, -1 if abundance is None else int(abundance),
+                                          None if abundance is None else self.set._h,
+                                          hist.ctypes.data_as(C.c_void_p)), self.ctx._h)
+        return hist
 
     def count_local(self, k):
         from .set import Counter, Pcon
@@ -135,14 +226,18 @@ class GpuOps:
     def threshold_slice(self, abundance, begin, end):
         check(lib.brgpu_set_threshold_slice(self.set._h, self.counter._h, abundance, begin, end), self.ctx._h)
 
-    def all_gather_bitfield(self, begin, end):
+    def all_gather_bitfield(self, begin, end, n_bits):
+        """[begin, end) is this rank's bit range; ranks own consecutive ranges in rank order."""
         n_bytes = lib.brgpu_set_bitfield_bytes(self.set._h)
         ptr = lib.brgpu_set_device_ptr(self.set._h)
         full = self.torch.as_tensor(_CudaArray(ptr, n_bytes), device=f"cuda:{self.ctx.device}")
         per = (end - begin) // 8
         if self.world == 1:
             return
-        bounds = [slice_bounds(1 << (2 * self.k - 1), self.world, r) for r in range(self.world)]
+        mine = self.torch.tensor([begin, end], dtype=self.torch.int64, device=f"cuda:{self.ctx.device}")
+        allb = [self.torch.empty_like(mine) for _ in range(self.world)]
+        self.dist.all_gather(allb, mine, group=self.group)
+        bounds = [tuple(int(x) for x in t.cpu().tolist()) for t in allb]
         if all((e - b) // 8 == per for b, e in bounds):
             mine = full[begin // 8 : end // 8].clone()
             self.dist.all_gather_into_tensor(full, mine, group=self.group)
@@ -155,5 +250,9 @@ class GpuOps:
         for p in self._peers:
             check(lib.brgpu_ipc_close(self.ctx._h, p), self.ctx._h)
         self._peers = []
-        self.counter.free()
+        if self.counter is not None:
+            self.counter.free()
+        if self.kmers is not None:
+            lib.brgpu_kmers_free(self.kmers)
+            self.kmers = None
         return self.set

@@ -58,6 +58,8 @@ class Context:
         if getattr(self, "_h", None):
             for child in list(self._children):
                 child.free()
+            for p in self.__dict__.pop("_ipc_cache", {}).values():  # peer mappings kept by br_b200.dist
+                lib.brgpu_ipc_close(self._h, p)
             lib.brgpu_ctx_destroy(self._h)
             self._h = None
 

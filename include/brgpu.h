@@ -49,6 +49,7 @@ typedef struct brgpu_ctx brgpu_ctx;       /* one per process per GPU: device, st
 typedef struct brgpu_set brgpu_set;       /* Box<dyn KmerSet> (src/set.rs:17-23), device resident */
 typedef struct brgpu_reads brgpu_reads;   /* a chunk of records (src/lib.rs:90), device resident */
 typedef struct brgpu_counts brgpu_counts; /* pcon::counter::Counter<u8>, device resident */
+typedef struct brgpu_kmers brgpu_kmers;   /* a chunk's canonical k-mers, partitioned by table-index range */
 
 /* ------------------------------------------------------------------------------------------
  * context
@@ -162,6 +163,23 @@ int brgpu_counts_merge_slice(brgpu_counts *counts, void *const *peer_tables, int
  * slice is written into set's bitfield at the same bit range (begin, end multiples of 1024) */
 int brgpu_counts_spectrum_slice(brgpu_counts *counts, uint64_t begin, uint64_t end, uint64_t hist_host[256]);
 int brgpu_set_threshold_slice(brgpu_set *set, brgpu_counts *counts, int abundance, uint64_t begin, uint64_t end);
+
+/* Sharded set construction without count tables (the default multi-GPU path, k >= 15).
+ * brgpu_kmers_create partitions a chunk's canonical k-mers into buckets of 2^15 consecutive
+ * table indices (16-bit residues).  Every rank exports its partition (two CUDA-IPC handles:
+ * residues, bucket offsets), owns a contiguous bucket range, and brgpu_kmers_count_range counts
+ * that range over its own and all peers' partitions — the peers' residues are read straight
+ * out of their HBM over NVLink inside the counting kernel.  The spectrum of the range is
+ * returned (sum it over ranks); if `set` is given the range is thresholded into set's bitfield
+ * (bits [bucket_begin << 15, bucket_end << 15)); the host then all-gathers the bitfield slices
+ * through brgpu_set_device_ptr. */
+int brgpu_kmers_create(brgpu_ctx *ctx, int k, const brgpu_reads *reads, brgpu_kmers **out);
+uint64_t brgpu_kmers_buckets(const brgpu_kmers *kmers);
+int brgpu_kmers_ipc_export(brgpu_kmers *kmers, uint8_t handles_out[128]); /* [0..64) residues, [64..128) offsets */
+int brgpu_kmers_count_range(brgpu_kmers *kmers, void *const *peer_residues, void *const *peer_offsets, int n_peers,
+                            uint64_t bucket_begin, uint64_t bucket_end, int abundance, brgpu_set *set,
+                            uint64_t hist_host[256]);
+void brgpu_kmers_free(brgpu_kmers *kmers);
 
 /* ------------------------------------------------------------------------------------------
  * instrumentation (bench.py): per-kernel CUDA-event timings on the library's stream

