@@ -229,7 +229,7 @@ def test_segment_scratch_overflow_falls_back_to_the_merge_warp(gpu, oracle):
     br, ctx = gpu
     rng = np.random.default_rng(12)
     refe = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=12000)].tobytes()
-    k = 13
+    k = 15  # 4^13 is small enough that a 4000-step walk through 24 000 solid 13-mers meets a branch
     gs = br.Pcon.new(ctx, k)
     gs.insert_all_kmers(refe)
     os_ = oracle.Solid.from_bitfield(k, gs.bitfield())
@@ -244,6 +244,5 @@ def test_segment_scratch_overflow_falls_back_to_the_merge_warp(gpu, oracle):
         exp, exp_off = os_.run_correction([mid], seq, off, confirm=3, max_search=7, threads=4)
         got, got_off = br.correct_batch(br.build_methods([method], gs, 3, 7), seq, off)
         compare_batches(f"segments {method}", got, got_off, exp, exp_off, seq, off)
-    assert int(exp_off[1] - exp_off[0]) != 400 or True
     e0 = os_.correct(2, reads[0])
     assert len(e0) > len(reads[0]) + 3500  # the Graph walk really is longer than a scratch region
