@@ -32,6 +32,8 @@ SIGNATURES = {
     "brgpu_ctx_synchronize": (C.c_int, [vp]),
     "brgpu_last_error": (C.c_char_p, [vp]),
     "brgpu_version": (C.c_char_p, []),
+    "brgpu_host_alloc": (C.c_int, [vp, sz, pvp]),
+    "brgpu_host_free": (None, [vp, vp]),
     "brgpu_reads_upload": (C.c_int, [vp, vp, vp, u64, pvp]),
     "brgpu_reads_count": (u64, [vp]),
     "brgpu_reads_bases": (u64, [vp]),

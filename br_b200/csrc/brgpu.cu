@@ -213,6 +213,21 @@ extern "C" int brgpu_ctx_synchronize(brgpu_ctx *ctx) {
 
 extern "C" const char *brgpu_last_error(const brgpu_ctx *ctx) { return ctx ? ctx->err.c_str() : "no context"; }
 
+extern "C" int brgpu_host_alloc(brgpu_ctx *ctx, size_t bytes, void **out) {
+    if (!ctx || !out) return BRGPU_E_INVALID;
+    *out = nullptr;
+    cudaSetDevice(ctx->device);
+    cudaError_t e = cudaMallocHost(out, bytes ? bytes : 1);
+    if (e != cudaSuccess) return fail(ctx, BRGPU_E_NOMEM, "pinned host allocation", e);
+    return BRGPU_OK;
+}
+
+extern "C" void brgpu_host_free(brgpu_ctx *ctx, void *p) {
+    if (!ctx || !p) return;
+    cudaSetDevice(ctx->device);
+    cudaFreeHost(p);
+}
+
 // ------------------------------------------------------------------------------------------
 // reads
 // ------------------------------------------------------------------------------------------

@@ -1,0 +1,432 @@
+// br.hpp — C++ host side of the hot path, mirroring br's own interface over the C ABI.
+//
+// br is Rust and this image has no Rust toolchain, so the host layer above include/brgpu.h is
+// written in C++ with the reference's names, argument meaning and error behaviour:
+//
+//   br::set::KmerSet { get(kmer) -> bool, k() -> u8 }                    src/set.rs:17-23
+//   br::set::Pcon    { from_pcon_solid, from_fasta, from_count, new_ }   src/set/pcon.rs:13-196,
+//                                                                        count2solid src/main.rs:87-115
+//   br::correct::Corrector { valid_kmer, k, correct }                    src/correct/mod.rs:44-108
+//   br::correct::{One, Two, Graph, Greedy, GapSize}                      src/correct/*.rs
+//   br::build_methods(params, solid, confirm, max_search)                src/lib.rs:141-164
+//   br::run_correction(inputs, outputs, methods, two_side, buffer_len)   src/lib.rs:72-139
+//
+// Nothing in this file computes a correction or a count on the CPU: every call lands in
+// libbrgpu.so.  Without a CUDA device Context's constructor throws (BRGPU_E_NO_DEVICE).
+// Corrector::correct_error is not exposed: on the GPU it only exists inside the scan kernels.
+#pragma once
+#include <zlib.h>
+
+#include <cstdint>
+#include <cstring>
+#include <future>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/brgpu.h"
+#include "fasta.hpp"
+
+namespace br {
+
+// error::Error (src/error.rs:12-45) carried as the ABI status + message
+struct Error : std::runtime_error {
+    int status;
+    Error(int st, const std::string &what) : std::runtime_error(what), status(st) {}
+};
+
+inline const char *status_text(int st) {
+    switch (st) {
+    case BRGPU_E_INVALID: return "invalid argument";
+    case BRGPU_E_NO_DEVICE: return "no CUDA device (brgpu has no CPU path)";
+    case BRGPU_E_CUDA: return "CUDA error";
+    case BRGPU_E_NOMEM: return "out of memory";
+    case BRGPU_E_OVERFLOW: return "output buffer too small";
+    case BRGPU_E_NO_THRESHOLD: return "Can't compute the abundance threshold";                  // src/error.rs:32-33
+    case BRGPU_E_NEED_ABUNDANCE: return "You must provide an abundance threshold or a method";  // src/error.rs:36-37
+    default: return "unknown status";
+    }
+}
+
+class Context {
+  public:
+    explicit Context(int device = 0) {
+        int st = brgpu_ctx_create(device, nullptr, &h_);
+        if (st != BRGPU_OK) throw Error(st, status_text(st));
+    }
+    Context(const Context &) = delete;
+    Context &operator=(const Context &) = delete;
+    ~Context() { brgpu_ctx_destroy(h_); }
+    brgpu_ctx *handle() const { return h_; }
+    void check(int st) const {
+        if (st == BRGPU_OK) return;
+        std::string msg = status_text(st);
+        const char *d = brgpu_last_error(h_);
+        if (d && *d) msg += std::string(" (") + d + ")";
+        throw Error(st, msg);
+    }
+
+  private:
+    brgpu_ctx *h_ = nullptr;
+};
+
+// page-locked host buffer (brgpu_host_alloc): what the chunk loop stages records in
+class PinnedBuffer {
+  public:
+    explicit PinnedBuffer(const Context &ctx) : ctx_(&ctx) {}
+    PinnedBuffer(const PinnedBuffer &) = delete;
+    PinnedBuffer &operator=(const PinnedBuffer &) = delete;
+    ~PinnedBuffer() { brgpu_host_free(ctx_->handle(), p_); }
+    uint8_t *reserve(size_t bytes) {
+        if (bytes > cap_) {
+            brgpu_host_free(ctx_->handle(), p_);
+            p_ = nullptr;
+            cap_ = 0;
+            size_t want = bytes + bytes / 4 + 4096;
+            void *q = nullptr;
+            ctx_->check(brgpu_host_alloc(ctx_->handle(), want, &q));
+            p_ = q;
+            cap_ = want;
+        }
+        return static_cast<uint8_t *>(p_);
+    }
+    uint8_t *data() const { return static_cast<uint8_t *>(p_); }
+    size_t capacity() const { return cap_; }
+
+  private:
+    const Context *ctx_;
+    void *p_ = nullptr;
+    size_t cap_ = 0;
+};
+
+namespace kmer {
+// cocktail::kmer as br uses it — host helpers for building k-mers to hand to
+// KmerSet::get / Pcon::set, and for Pcon::get's index into the host mirror of the bitfield.
+inline uint64_t nuc2bit(uint8_t b) { return (b >> 1) & 3u; }
+inline uint64_t seq2bit(const uint8_t *s, size_t n) {
+    uint64_t v = 0;
+    for (size_t i = 0; i < n; i++) v = (v << 2) | nuc2bit(s[i]);
+    return v;
+}
+inline uint64_t revcomp(uint64_t kmer, int k) {
+    uint64_t r = 0;
+    for (int i = 0; i < k; i++) {
+        r = (r << 2) | ((kmer & 3u) ^ 2u);
+        kmer >>= 2;
+    }
+    return r;
+}
+inline uint64_t canonical(uint64_t kmer, int k) { // parity-canonical: the form with an even popcount
+    return (__builtin_popcountll(kmer) & 1) ? revcomp(kmer, k) : kmer;
+}
+} // namespace kmer
+
+namespace set {
+
+// src/set.rs:17-21
+class KmerSet {
+  public:
+    virtual ~KmerSet() = default;
+    virtual bool get(uint64_t kmer) const = 0;
+    virtual uint8_t k() const = 0;
+};
+
+// cli::AbundanceSelection (src/cli.rs:227-241) as far as the ABI implements it
+enum class AbundanceSelection { None, FirstMinimum };
+
+// set::Pcon (src/set/pcon.rs:13-196): the dense canonical bitfield, resident in HBM
+class Pcon : public KmerSet {
+  public:
+    Pcon(const Context &ctx, brgpu_set *h) : ctx_(&ctx), h_(h) {}
+    Pcon(const Pcon &) = delete;
+    Pcon &operator=(const Pcon &) = delete;
+    ~Pcon() override { brgpu_set_free(h_); }
+
+    // Pcon::new(pcon::solid::Solid::new(k)) — empty set (src/set/pcon.rs:183)
+    static std::unique_ptr<Pcon> new_(const Context &ctx, int k) {
+        brgpu_set *h = nullptr;
+        ctx.check(brgpu_set_new(ctx.handle(), k, &h));
+        return std::make_unique<Pcon>(ctx, h);
+    }
+
+    // Pcon::from_pcon_solid (src/set/pcon.rs:18-25): (gzip) stream, byte 0 = k, rest = bitfield.
+    // Decompression is host I/O (niffler in the reference); the payload goes to the GPU.
+    static std::unique_ptr<Pcon> from_pcon_solid(const Context &ctx, const std::string &path) {
+        gzFile gz = gzopen(path.c_str(), "rb");
+        if (!gz) throw std::runtime_error("can't open " + path);
+        std::vector<uint8_t> payload;
+        std::vector<uint8_t> buf(1u << 20);
+        int n;
+        while ((n = gzread(gz, buf.data(), (unsigned)buf.size())) > 0) payload.insert(payload.end(), buf.begin(), buf.begin() + n);
+        gzclose(gz);
+        if (n < 0) throw std::runtime_error("read error in " + path);
+        brgpu_set *h = nullptr;
+        ctx.check(brgpu_set_from_solid_payload(ctx.handle(), payload.data(), payload.size(), &h));
+        return std::make_unique<Pcon>(ctx, h);
+    }
+
+    // the `fasta` sub-command (src/main.rs:72-115): Counter::new(k) + count_fasta + count2solid.
+    // abundance < 0 means "not given" (Option::None); an explicit abundance wins (src/main.rs:96).
+    static std::unique_ptr<Pcon> from_count(const Context &ctx, const fasta::Chunk &reads, int k, int abundance,
+                                            AbundanceSelection selection) {
+        k = k - (!(k & 1) & 1); // Fasta::kmer_size forces k odd (src/cli.rs:277-279)
+        int sel = BRGPU_ABUNDANCE_EXPLICIT;
+        if (abundance < 0 && selection == AbundanceSelection::FirstMinimum) sel = BRGPU_ABUNDANCE_FIRST_MINIMUM;
+        brgpu_set *h = nullptr;
+        ctx.check(brgpu_set_from_host_reads(ctx.handle(), k, abundance, sel, reads.seq.data(), reads.offsets.data(),
+                                            reads.size(), &h));
+        return std::make_unique<Pcon>(ctx, h);
+    }
+
+    // Pcon::from_fasta (src/set/pcon.rs:47-112): presence-only set of every canonical k-mer of the
+    // records with len >= k — the counting pass with threshold `count > 0`.
+    static std::unique_ptr<Pcon> from_fasta(const Context &ctx, const fasta::Chunk &reads, int k) {
+        brgpu_set *h = nullptr;
+        ctx.check(brgpu_set_from_host_reads(ctx.handle(), k, 0, BRGPU_ABUNDANCE_EXPLICIT, reads.seq.data(),
+                                            reads.offsets.data(), reads.size(), &h));
+        return std::make_unique<Pcon>(ctx, h);
+    }
+
+    // KmerSet
+    uint8_t k() const override { return (uint8_t)brgpu_set_k(h_); }
+    // Pcon::get (src/set/pcon.rs:189-191), forward k-mers accepted.  Served from a host mirror of
+    // the bitfield (exported once): a GPU round trip per k-mer would be useless.  Batches go
+    // through get_batch.
+    bool get(uint64_t kmer) const override {
+        if (mirror_.empty()) mirror_ = bitfield();
+        const int kk = k();
+        const uint64_t mask = (kk < 32) ? ((1ULL << (2 * kk)) - 1ULL) : ~0ULL;
+        const uint64_t idx = kmer::canonical(kmer & mask, kk) >> 1;
+        return (mirror_[idx >> 3] >> (idx & 7)) & 1;
+    }
+    std::vector<uint8_t> get_batch(const std::vector<uint64_t> &kmers) const {
+        std::vector<uint8_t> out(kmers.size());
+        ctx_->check(brgpu_set_get_batch(h_, kmers.data(), kmers.size(), out.data()));
+        return out;
+    }
+    // Solid::set(kmer, true) on a batch (canonicalises, like the reference's unit tests rely on)
+    void set(const std::vector<uint64_t> &kmers) {
+        ctx_->check(brgpu_set_insert_batch(h_, kmers.data(), kmers.size()));
+        mirror_.clear();
+    }
+    // `for kmer in Tokenizer::new(seq, k) { data.set(kmer, true) }` of the reference's tests
+    void set_all_kmers(const std::string &seq) {
+        const int kk = k();
+        if ((int)seq.size() < kk) return;
+        const uint64_t mask = (1ULL << (2 * kk)) - 1ULL;
+        std::vector<uint64_t> kmers;
+        uint64_t v = kmer::seq2bit((const uint8_t *)seq.data(), (size_t)kk - 1);
+        for (size_t i = (size_t)kk - 1; i < seq.size(); i++) {
+            v = ((v << 2) & mask) | kmer::nuc2bit((uint8_t)seq[i]);
+            kmers.push_back(v);
+        }
+        set(kmers);
+    }
+
+    int abundance() const { return brgpu_set_abundance(h_); }
+    std::vector<uint64_t> spectrum() const {
+        std::vector<uint64_t> h(256);
+        ctx_->check(brgpu_set_spectrum(h_, h.data()));
+        return h;
+    }
+    std::vector<uint8_t> bitfield() const {
+        std::vector<uint8_t> out(brgpu_set_bitfield_bytes(h_));
+        ctx_->check(brgpu_set_export_bitfield(h_, out.data(), out.size()));
+        return out;
+    }
+    // pcon's `.solid` container: gzip(u8 k || bitfield) — what from_pcon_solid reads back
+    void write_solid(const std::string &path) const {
+        std::vector<uint8_t> bits = bitfield();
+        gzFile gz = gzopen(path.c_str(), "wb6");
+        if (!gz) throw std::runtime_error("can't create " + path);
+        uint8_t kk = k();
+        bool ok = gzwrite(gz, &kk, 1) == 1;
+        for (size_t p = 0; ok && p < bits.size();) {
+            unsigned n = (unsigned)std::min<size_t>(bits.size() - p, 1u << 30);
+            ok = gzwrite(gz, bits.data() + p, n) == (int)n;
+            p += n;
+        }
+        ok = (gzclose(gz) == Z_OK) && ok;
+        if (!ok) throw std::runtime_error("write error in " + path);
+    }
+
+    brgpu_set *handle() const { return h_; }
+    const Context &context() const { return *ctx_; }
+
+  private:
+    const Context *ctx_;
+    brgpu_set *h_;
+    mutable std::vector<uint8_t> mirror_;
+};
+
+} // namespace set
+
+namespace cli {
+// cli::CorrectionMethod in declaration order (src/cli.rs:11-17) == the ABI's method ids
+enum class CorrectionMethod : uint8_t { One = BRGPU_ONE, Two = BRGPU_TWO, Graph = BRGPU_GRAPH, Greedy = BRGPU_GREEDY, GapSize = BRGPU_GAP_SIZE };
+} // namespace cli
+
+namespace correct {
+
+// src/correct/mod.rs:44-108.  A corrector is a (method, parameters, set) description; the scan
+// itself runs in libbrgpu.so.  correct() is the unit-test entry point (one read per call);
+// run_correction hands whole chunks to the library.
+class Corrector {
+  public:
+    virtual ~Corrector() = default;
+    const set::Pcon &valid_kmer() const { return *set_; }
+    uint8_t k() const { return set_->k(); }
+    cli::CorrectionMethod method() const { return method_; }
+    int confirm() const { return confirm_; }
+    int max_search() const { return max_search_; }
+
+    std::vector<uint8_t> correct(const uint8_t *seq, size_t len) const {
+        std::vector<uint8_t> out(2 * len + 256);
+        for (;;) {
+            uint64_t n = 0;
+            int st = brgpu_correct_one(set_->context().handle(), set_->handle(), (int)method_, confirm_, max_search_, seq,
+                                       len, out.data(), out.size(), &n);
+            if (st == BRGPU_E_OVERFLOW && n > out.size()) {
+                out.resize(n);
+                continue;
+            }
+            set_->context().check(st);
+            out.resize(n);
+            return out;
+        }
+    }
+    std::vector<uint8_t> correct(const std::string &seq) const { return correct((const uint8_t *)seq.data(), seq.size()); }
+
+  protected:
+    Corrector(const set::Pcon &s, cli::CorrectionMethod m, int confirm, int max_search)
+        : set_(&s), method_(m), confirm_(confirm), max_search_(max_search) {}
+
+  private:
+    const set::Pcon *set_;
+    cli::CorrectionMethod method_;
+    int confirm_, max_search_;
+};
+
+struct One : Corrector { // src/correct/exist/one.rs:74
+    One(const set::Pcon &s, uint8_t c) : Corrector(s, cli::CorrectionMethod::One, c, 7) {}
+};
+struct Two : Corrector { // src/correct/exist/two.rs:328
+    Two(const set::Pcon &s, uint8_t c) : Corrector(s, cli::CorrectionMethod::Two, c, 7) {}
+};
+struct Graph : Corrector { // src/correct/graph.rs:29-37
+    explicit Graph(const set::Pcon &s) : Corrector(s, cli::CorrectionMethod::Graph, 5, 7) {}
+};
+struct Greedy : Corrector { // src/correct/greedy.rs:41-54
+    Greedy(const set::Pcon &s, uint8_t max_search, uint8_t nb_validate)
+        : Corrector(s, cli::CorrectionMethod::Greedy, nb_validate, max_search) {}
+};
+struct GapSize : Corrector { // src/correct/gap_size.rs:29-42
+    GapSize(const set::Pcon &s, uint8_t c) : Corrector(s, cli::CorrectionMethod::GapSize, c, 7) {}
+};
+
+} // namespace correct
+
+using Methods = std::vector<std::unique_ptr<correct::Corrector>>;
+
+// src/lib.rs:141-164 — same argument mapping
+inline Methods build_methods(const std::vector<cli::CorrectionMethod> &params, const set::Pcon &solid, uint8_t confirm,
+                             uint8_t max_search) {
+    Methods methods;
+    for (auto m : params) {
+        switch (m) {
+        case cli::CorrectionMethod::One: methods.emplace_back(new correct::One(solid, confirm)); break;
+        case cli::CorrectionMethod::Two: methods.emplace_back(new correct::Two(solid, confirm)); break;
+        case cli::CorrectionMethod::Graph: methods.emplace_back(new correct::Graph(solid)); break;
+        case cli::CorrectionMethod::Greedy: methods.emplace_back(new correct::Greedy(solid, max_search, confirm)); break;
+        case cli::CorrectionMethod::GapSize: methods.emplace_back(new correct::GapSize(solid, confirm)); break;
+        }
+    }
+    return methods;
+}
+
+// the per-chunk body of run_correction (src/lib.rs:93-128) in one library call
+struct Corrected {
+    std::vector<uint8_t> seq;
+    std::vector<uint64_t> offsets;
+};
+
+inline void correct_chunk(const Methods &methods, bool two_side, const fasta::Chunk &in, Corrected &out) {
+    const size_t n = in.size();
+    out.offsets.assign(n + 1, 0);
+    if (methods.empty()) { // fold over no method: records pass through
+        out.seq = in.seq;
+        out.offsets = in.offsets;
+        return;
+    }
+    const set::Pcon &solid = methods[0]->valid_kmer();
+    std::vector<uint8_t> ids;
+    int confirm = 5, max_search = 7;
+    for (auto &m : methods) {
+        ids.push_back((uint8_t)m->method());
+        if (m->method() != cli::CorrectionMethod::Graph) confirm = m->confirm();
+        if (m->method() == cli::CorrectionMethod::Greedy) max_search = m->max_search();
+    }
+    const size_t total = in.seq.size();
+    out.seq.resize(total + total / 8 + 64 * n + 64);
+    for (;;) {
+        uint64_t need = 0;
+        int st = brgpu_correct_batch(solid.context().handle(), solid.handle(), ids.data(), ids.size(), confirm, max_search,
+                                     two_side ? 1 : 0, in.seq.data(), in.offsets.data(), n, out.seq.data(),
+                                     out.seq.size(), out.offsets.data(), &need);
+        if (st == BRGPU_E_OVERFLOW && need > out.seq.size()) {
+            out.seq.resize(need);
+            continue;
+        }
+        solid.context().check(st);
+        out.seq.resize(need);
+        return;
+    }
+}
+
+constexpr size_t CHUNK_RECORDS = 8192; // hard-coded in src/lib.rs:90
+
+// src/lib.rs:72-139: for each (input, output) pair read FASTA records, correct them chunk by
+// chunk (8192 records), write FASTA in input order (the serial path's order, src/lib.rs:21-69).
+// `record_buffer_len` is accepted and, like in the reference, only a capacity hint.  The parse of
+// chunk c+1 and the formatting of chunk c-1 run on host threads while the GPU corrects chunk c.
+inline void run_correction(const std::vector<std::string> &inputs, const std::vector<std::string> &outputs,
+                           const Methods &methods, bool two_side, uint64_t record_buffer_len = CHUNK_RECORDS) {
+    (void)record_buffer_len;
+    const size_t pairs = inputs.size() < outputs.size() ? inputs.size() : outputs.size(); // zip (src/lib.rs:79)
+    for (size_t p = 0; p < pairs; p++) {
+        fasta::Reader reader(inputs[p]);
+        fasta::Writer writer(outputs[p]);
+        fasta::Chunk chunks[2];
+        Corrected results[2];
+        std::vector<std::string> written_defs[2];
+        auto read_into = [&reader](fasta::Chunk *c) {
+            c->clear();
+            return reader.read_chunk(*c, CHUNK_RECORDS);
+        };
+        std::future<bool> next = std::async(std::launch::async, read_into, &chunks[0]);
+        std::shared_future<void> writes[2]; // writes[b]: the write that still reads results[b]
+        for (int cur = 0;; cur ^= 1) {
+            const bool more = next.get();
+            fasta::Chunk &c = chunks[cur];
+            if (more) next = std::async(std::launch::async, read_into, &chunks[cur ^ 1]);
+            if (c.size()) {
+                if (writes[cur].valid()) writes[cur].wait(); // results[cur] is free again
+                correct_chunk(methods, two_side, c, results[cur]);
+                written_defs[cur].swap(c.definitions);
+                Corrected *r = &results[cur];
+                std::vector<std::string> *d = &written_defs[cur];
+                std::shared_future<void> before = writes[cur ^ 1]; // keep the records in input order
+                writes[cur] = std::async(std::launch::async, [&writer, r, d, before]() {
+                                  if (before.valid()) before.wait();
+                                  writer.write(*d, r->seq.data(), r->offsets.data());
+                              }).share();
+            }
+            if (!more) break;
+        }
+        for (auto &w : writes)
+            if (w.valid()) w.get();
+    }
+}
+
+} // namespace br

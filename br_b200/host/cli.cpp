@@ -1,0 +1,202 @@
+// brgpu-cli — br's command line (src/cli.rs, src/main.rs:17-58) in front of libbrgpu.so.
+//
+//   brgpu-cli [-i IN..] [-o OUT..] [-s] [-c METHOD..] [-C CONFIRM] [-M MAX_SEARCH] [-b N] [-t N] [-d DEVICE] [-q] [-v..]
+//             fasta -i READS.. -k K [-a N] [first-minimum]            src/main.rs:72-85
+//           | solid -i FILE -f solid|fasta [-k K]                      src/main.rs:117-145
+//           | large-kmer -i FILE -f fasta -k K   (odd K <= 19 only: the dense set; src/main.rs:147-163)
+//           | count ...                          (rejected: no fixture pins pcon's count-file format)
+//
+// Same flag names, defaults and quirks as the reference: -s *disables* the
+// reversed pass; -b is accepted and does not change the 8192-record chunk; `fasta -k` decrements an
+// even k; omitting both -a and a selection method is an error; nothing is printed on success
+// (tests/br.rs:28-30 demands an empty stderr).  -t is accepted and ignored (the GPU is the pool).
+// One extra sub-command, `echo`, copies records through the FASTA reader and writer without
+// touching the GPU (I/O self-check).  `--write-solid PATH` additionally stores the set it built.
+#include <cstdio>
+#include <cstdlib>
+#include <iostream>
+#include <string>
+#include <vector>
+
+#include "br.hpp"
+
+namespace {
+
+struct Args {
+    std::vector<std::string> inputs, outputs;
+    bool two_side = false;
+    std::vector<br::cli::CorrectionMethod> corrections;
+    bool corrections_given = false;
+    int confirm = 5, max_search = 7; // src/cli.rs:135-142
+    uint64_t record_buffer = 8192;
+    int device = 0;
+    std::string write_solid;
+    // sub-command
+    std::string sub;
+    std::vector<std::string> sub_inputs;
+    int k = -1;
+    int abundance = -1;
+    std::string selection;
+    std::string format;
+};
+
+[[noreturn]] void usage_error(const std::string &msg) {
+    std::fprintf(stderr, "error: %s\n", msg.c_str());
+    std::exit(2);
+}
+
+bool is_sub(const std::string &s) {
+    return s == "fasta" || s == "solid" || s == "large-kmer" || s == "count" || s == "echo";
+}
+
+br::cli::CorrectionMethod parse_method(const std::string &s) { // clap ValueEnum: kebab-case
+    if (s == "one") return br::cli::CorrectionMethod::One;
+    if (s == "two") return br::cli::CorrectionMethod::Two;
+    if (s == "graph") return br::cli::CorrectionMethod::Graph;
+    if (s == "greedy") return br::cli::CorrectionMethod::Greedy;
+    if (s == "gap-size" || s == "gap_size") return br::cli::CorrectionMethod::GapSize;
+    usage_error("invalid value '" + s + "' for '--corrections': one, two, graph, greedy, gap-size");
+}
+
+long parse_int(const std::string &flag, const std::string &v, long lo, long hi) {
+    char *end = nullptr;
+    long x = std::strtol(v.c_str(), &end, 10);
+    if (v.empty() || *end || x < lo || x > hi) usage_error("invalid value '" + v + "' for '" + flag + "'");
+    return x;
+}
+
+Args parse(int argc, char **argv) {
+    Args a;
+    int i = 1;
+    auto value = [&](const std::string &flag) -> std::string {
+        if (i + 1 >= argc) usage_error("a value is required for '" + flag + "'");
+        return argv[++i];
+    };
+    // a multi-valued option takes every following token up to the next option / sub-command
+    auto values = [&](const std::string &flag, std::vector<std::string> &dst, bool stop_at_sub) {
+        size_t before = dst.size();
+        while (i + 1 < argc && argv[i + 1][0] != '-' && !(stop_at_sub && is_sub(argv[i + 1]))) dst.push_back(argv[++i]);
+        if (dst.size() == before) usage_error("a value is required for '" + flag + "'");
+    };
+    for (; i < argc; i++) {
+        std::string t = argv[i];
+        if (is_sub(t)) {
+            a.sub = t;
+            i++;
+            break;
+        }
+        if (t == "-i" || t == "--inputs") values(t, a.inputs, true);
+        else if (t == "-o" || t == "--outputs") values(t, a.outputs, true);
+        else if (t == "-s" || t == "--two-side") a.two_side = true;
+        else if (t == "-c" || t == "--corrections") {
+            std::vector<std::string> ms;
+            values(t, ms, true);
+            for (auto &m : ms) a.corrections.push_back(parse_method(m));
+            a.corrections_given = true;
+        } else if (t == "-C" || t == "--confirm") a.confirm = (int)parse_int(t, value(t), 0, 255);
+        else if (t == "-M" || t == "--max-search") a.max_search = (int)parse_int(t, value(t), 0, 255);
+        else if (t == "-b" || t == "--record_buffer") a.record_buffer = (uint64_t)parse_int(t, value(t), 0, 1L << 40);
+        else if (t == "-t" || t == "--threads") (void)parse_int(t, value(t), 0, 1 << 20);
+        else if (t == "-d" || t == "--device") a.device = (int)parse_int(t, value(t), 0, 1023);
+        else if (t == "--write-solid") a.write_solid = value(t);
+        else if (t == "-q" || t == "--quiet") {}
+        else if (t.rfind("-v", 0) == 0 || t == "--verbosity") {}
+        else if (t == "-T" || t == "--timestamp") (void)value(t);
+        else usage_error("unexpected argument '" + t + "'");
+    }
+    if (a.sub.empty()) usage_error("a sub-command is required: fasta, solid, large-kmer, count");
+    for (; i < argc; i++) {
+        std::string t = argv[i];
+        if (t == "-i" || t == "--inputs" || t == "--input") values(t, a.sub_inputs, false);
+        else if (t == "-k" || t == "--kmer-size") a.k = (int)parse_int(t, value(t), 1, 255);
+        else if (t == "-a" || t == "--abundance") a.abundance = (int)parse_int(t, value(t), 0, 255);
+        else if (t == "-f" || t == "--format") a.format = value(t);
+        else if (t == "first-minimum") a.selection = t;
+        else if (t == "rarefaction" || t == "percent-most" || t == "percent-least") {
+            a.selection = t;
+            (void)value(t);
+        } else usage_error("unexpected argument '" + t + "' for '" + a.sub + "'");
+    }
+    if (!a.corrections_given) // src/cli.rs:121-131
+        a.corrections = {br::cli::CorrectionMethod::One, br::cli::CorrectionMethod::Two, br::cli::CorrectionMethod::Graph,
+                         br::cli::CorrectionMethod::Greedy, br::cli::CorrectionMethod::GapSize};
+    if (a.inputs.empty()) a.inputs.push_back("-");   // default stdin  (src/cli.rs:80-81)
+    if (a.outputs.empty()) a.outputs.push_back("-"); // default stdout (src/cli.rs:99-103)
+    return a;
+}
+
+// Fasta::inputs / Solid::input: every file chained into one record stream (src/cli.rs:265-274)
+void read_all(const std::vector<std::string> &paths, br::fasta::Chunk &all) {
+    for (auto &p : paths) {
+        br::fasta::Reader r(p);
+        while (r.read_chunk(all, 1u << 20)) {}
+    }
+}
+
+std::unique_ptr<br::set::Pcon> build_set(const br::Context &ctx, const Args &a) {
+    using br::set::AbundanceSelection;
+    using br::set::Pcon;
+    if (a.sub_inputs.empty()) usage_error("the following required arguments were not provided: --inputs");
+    if (a.sub == "fasta") { // src/main.rs:72-85
+        if (a.k < 0) usage_error("the following required arguments were not provided: --kmer-size");
+        AbundanceSelection sel = AbundanceSelection::None;
+        if (a.selection == "first-minimum") sel = AbundanceSelection::FirstMinimum;
+        else if (!a.selection.empty() && a.abundance < 0)
+            throw std::runtime_error("abundance selection '" + a.selection + "' is not supported by brgpu (use -a or first-minimum)");
+        br::fasta::Chunk reads;
+        read_all(a.sub_inputs, reads);
+        return Pcon::from_count(ctx, reads, a.k, a.abundance, sel);
+    }
+    if (a.sub == "solid") { // src/main.rs:117-145
+        if (a.format == "solid") return Pcon::from_pcon_solid(ctx, a.sub_inputs[0]);
+        if (a.format == "fasta") {
+            if (a.k < 0) throw std::runtime_error("Solid input in this format require a kmer size"); // Error::SolidRequireKmerSize
+            br::fasta::Chunk reads;
+            read_all({a.sub_inputs[0]}, reads);
+            return Pcon::from_fasta(ctx, reads, a.k);
+        }
+        usage_error("invalid value '" + a.format + "' for '--format': solid, fasta");
+    }
+    if (a.sub == "large-kmer") { // src/main.rs:147-163: set::Hash == presence-only set of canonical k-mers
+        if (a.k < 0) usage_error("the following required arguments were not provided: --kmer-size");
+        if (a.format != "fasta") usage_error("invalid value '" + a.format + "' for '--format': fasta");
+        if (!(a.k & 1) || a.k > 19)
+            throw std::runtime_error("large-kmer: brgpu holds the set as a dense bitfield, odd k <= 19 only");
+        br::fasta::Chunk reads;
+        read_all({a.sub_inputs[0]}, reads);
+        return Pcon::from_fasta(ctx, reads, a.k);
+    }
+    throw std::runtime_error("sub-command '" + a.sub + "' is not supported by brgpu (pcon's count-file format is not pinned by any fixture)");
+}
+
+} // namespace
+
+int main(int argc, char **argv) {
+    Args a = parse(argc, argv);
+    try {
+        if (a.sub == "echo") { // FASTA reader -> writer, no GPU
+            const size_t pairs = std::min(a.inputs.size(), a.outputs.size());
+            for (size_t p = 0; p < pairs; p++) {
+                br::fasta::Reader r(a.inputs[p]);
+                br::fasta::Writer w(a.outputs[p]);
+                br::fasta::Chunk c;
+                bool more = true;
+                while (more) {
+                    c.clear();
+                    more = r.read_chunk(c, br::CHUNK_RECORDS);
+                    w.write(c.definitions, c.seq.data(), c.offsets.data());
+                }
+            }
+            return 0;
+        }
+        br::Context ctx(a.device);
+        std::unique_ptr<br::set::Pcon> kmer_set = build_set(ctx, a);
+        if (!a.write_solid.empty()) kmer_set->write_solid(a.write_solid);
+        br::Methods methods = br::build_methods(a.corrections, *kmer_set, (uint8_t)a.confirm, (uint8_t)a.max_search);
+        br::run_correction(a.inputs, a.outputs, methods, a.two_side, a.record_buffer);
+    } catch (const std::exception &e) {
+        std::fprintf(stderr, "Error: %s\n", e.what()); // anyhow's top-level report
+        return 1;
+    }
+    return 0;
+}

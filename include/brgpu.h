@@ -62,6 +62,11 @@ int brgpu_ctx_synchronize(brgpu_ctx *ctx);
 const char *brgpu_last_error(const brgpu_ctx *ctx);
 const char *brgpu_version(void);
 
+/* Page-locked host memory for the buffers handed to the calls below (optional: pageable
+ * memory works, pinned memory lets the copies run at PCIe speed and overlap with kernels). */
+int brgpu_host_alloc(brgpu_ctx *ctx, size_t bytes, void **out);
+void brgpu_host_free(brgpu_ctx *ctx, void *p);
+
 /* ------------------------------------------------------------------------------------------
  * reads — the record chunk run_correction forms (src/lib.rs:90, populate_buffer :168-188).
  * `seq` is the concatenation of the sequences (any bytes; nuc2bit is (b>>1)&3),

@@ -1,0 +1,213 @@
+"""The C++ host side (br_b200/host/br.hpp: br's own set / corrector / run_correction interface over
+the C ABI) and its command line `brgpu-cli` (br's flags, src/cli.rs).
+
+CPU tests: the FASTA reader/writer pair (stands in for noodles-fasta, src/lib.rs:30-31,57-60), the
+argument contract and the loud failure without a GPU.  GPU tests mirror the reference's integration
+tests (tests/br.rs:8-59: `fasta ... first-minimum` and `solid -f solid` must succeed with an empty
+stderr) and go further: the corrected FASTA is compared record by record with the oracle, and the
+reference's unit KATs are replayed through the C++ classes.
+"""
+import gzip
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT, parse_fasta
+
+CLI = ROOT / "br_b200" / "brgpu-cli"
+KAT = ROOT / "br_b200" / "brgpu-kat"
+
+
+@pytest.fixture(scope="module", autouse=True)
+def built():
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("brgpu_build", ROOT / "br_b200" / "build.py")
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    b.build()
+    assert CLI.exists() and KAT.exists()
+
+
+def run(args, **kw):
+    return subprocess.run([str(CLI), *map(str, args)], capture_output=True, timeout=600, **kw)
+
+
+def records(path):
+    data = open(path, "rb").read()
+    if data[:2] == b"\x1f\x8b":
+        data = gzip.decompress(data)
+    return parse_fasta(data)
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU
+# ---------------------------------------------------------------------------------------------
+def test_echo_round_trips_the_reference_fixture(tmp_path):
+    out = tmp_path / "echo.fa"
+    r = run(["-i", GOLDEN / "br_reads.fa.gz", "-o", out, "echo"])
+    assert r.returncode == 0 and r.stderr == b"" and r.stdout == b""
+    n0, s0, o0 = records(GOLDEN / "br_reads.fa.gz")
+    n1, s1, o1 = records(out)
+    assert n0 == n1 and np.array_equal(s0, s1) and np.array_equal(o0, o1)
+    lines = [l for l in open(out, "rb").read().split(b"\n") if l and not l.startswith(b">")]
+    assert max(map(len, lines)) == 80  # noodles' default line width
+
+
+def test_reader_handles_wrapped_crlf_empty_and_unterminated_records(tmp_path):
+    src = tmp_path / "in.fa"
+    src.write_bytes(b"\n>r1 desc with spaces\r\nACGT\r\nAC\r\n>empty\n>r3\nNNNNacgt\n\nTT\n>last\nGG")
+    out = tmp_path / "out.fa"
+    r = run(["-i", src, "-o", out, "echo"])
+    assert r.returncode == 0 and r.stderr == b""
+    assert out.read_bytes() == b">r1 desc with spaces\nACGTAC\n>empty\n>r3\nNNNNacgtTT\n>last\nGG\n"
+
+
+def test_echo_reads_stdin_and_writes_stdout():
+    r = run(["echo"], input=b">a\nAC\nGT\n")
+    assert r.returncode == 0 and r.stdout == b">a\nACGT\n" and r.stderr == b""
+
+
+def test_inputs_and_outputs_are_zipped_pairwise(tmp_path):
+    a, b = tmp_path / "a.fa", tmp_path / "b.fa"
+    a.write_bytes(b">a\nAAAA\n")
+    b.write_bytes(b">b\nCCCC\n")
+    oa, ob = tmp_path / "oa.fa", tmp_path / "ob.fa"
+    r = run(["-i", a, b, "-o", oa, ob, "echo"])  # src/lib.rs:79: inputs.zip(outputs)
+    assert r.returncode == 0
+    assert oa.read_bytes() == b">a\nAAAA\n" and ob.read_bytes() == b">b\nCCCC\n"
+    r = run(["-i", a, "-i", b, "-o", oa, "-o", ob, "echo"])
+    assert r.returncode == 0 and ob.read_bytes() == b">b\nCCCC\n"
+
+
+def test_argument_contract():
+    assert run([]).returncode == 2  # a sub-command is required
+    assert run(["-c", "three", "echo"]).returncode == 2
+    assert run(["--bogus", "echo"]).returncode == 2
+    assert run(["-C", "300", "echo"]).returncode == 2  # confirm is a u8
+
+
+@pytest.mark.skipif("__import__('torch').cuda.is_available()")
+def test_without_a_gpu_the_cli_fails_loudly(tmp_path):
+    r = run(["-i", GOLDEN / "br_reads.fa.gz", "-o", tmp_path / "o.fa", "solid", "-i", GOLDEN / "br_reads.k11.a2.solid",
+             "-f", "solid"])
+    assert r.returncode == 1 and b"no CUDA device" in r.stderr
+    assert not (tmp_path / "o.fa").exists() or (tmp_path / "o.fa").stat().st_size == 0
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU
+# ---------------------------------------------------------------------------------------------
+def oracle_corrected(oracle, payload, methods, seq, off, confirm=5, max_search=7, two_side=False):
+    solid = oracle.Solid.from_solid_payload(payload)
+    ids = [oracle.METHOD_IDS[m] for m in methods]
+    return solid.run_correction(ids, seq, off, confirm=confirm, max_search=max_search, two_side=two_side, threads=8)
+
+
+def assert_same_records(path, names, exp, exp_off):
+    n1, s1, o1 = records(path)
+    assert n1 == names
+    assert np.array_equal(o1, exp_off), "corrected lengths differ from the oracle"
+    assert np.array_equal(s1, exp), "corrected bases differ from the oracle"
+
+
+@pytest.mark.gpu
+def test_solid_subcommand_like_tests_br_rs(tmp_path, oracle, fixture_reads, fixture_solid_payload):
+    """tests/br.rs:35-59 (`solid -i raw.k11.a2.solid -f solid`), default method chain and flags."""
+    out = tmp_path / "corr.fasta"
+    r = run(["-i", GOLDEN / "br_reads.fa.gz", "-o", out, "-t", "4", "solid", "-i", GOLDEN / "br_reads.k11.a2.solid",
+             "-f", "solid"])
+    assert r.returncode == 0 and r.stderr == b"", r.stderr
+    names, _, _ = records(GOLDEN / "br_reads.fa.gz")
+    seq, off = fixture_reads
+    exp, exp_off = oracle_corrected(oracle, fixture_solid_payload, ["one", "two", "graph", "greedy", "gap_size"], seq, off)
+    assert_same_records(out, names, exp, exp_off)
+
+
+@pytest.mark.gpu
+def test_fasta_subcommand_config1(tmp_path, oracle, fixture_reads, fixture_solid_payload):
+    """BASELINE.json configs[0]: the reference's reads, k = 11, method one — `fasta -k 11 -a 2` must
+    rebuild the `.solid` fixture (checked through --write-solid) and correct like the oracle."""
+    out, solid_out = tmp_path / "corr.fasta", tmp_path / "set.solid"
+    r = run(["-i", GOLDEN / "br_reads.fa.gz", "-o", out, "-c", "one", "--write-solid", solid_out, "fasta", "-i",
+             GOLDEN / "br_reads.fa.gz", "-k", "11", "-a", "2"])
+    assert r.returncode == 0 and r.stderr == b"", r.stderr
+    assert gzip.open(solid_out).read() == fixture_solid_payload
+    names, _, _ = records(GOLDEN / "br_reads.fa.gz")
+    seq, off = fixture_reads
+    exp, exp_off = oracle_corrected(oracle, fixture_solid_payload, ["one"], seq, off)
+    assert_same_records(out, names, exp, exp_off)
+
+
+@pytest.mark.gpu
+def test_fasta_first_minimum_two_side_and_even_k(tmp_path, oracle, fixture_reads):
+    """tests/br.rs:8-33 (`fasta -k 11 first-minimum`), here with -k 12 (decremented to 11,
+    src/cli.rs:277-279), -s (no reversed pass) and -C 3."""
+    out = tmp_path / "corr.fasta"
+    r = run(["-i", GOLDEN / "br_reads.fa.gz", "-o", out, "-s", "-c", "two", "gap-size", "-C", "3", "fasta", "-i",
+             GOLDEN / "br_reads.fa.gz", "-k", "12", "first-minimum"])
+    assert r.returncode == 0 and r.stderr == b"", r.stderr
+    seq, off = fixture_reads
+    c = oracle.Counter(11)
+    c.count(seq, off, threads=8)
+    thr = oracle.Counter.first_minimum(c.spectrum(8))
+    solid = c.to_solid(thr, 8)
+    exp, exp_off = solid.run_correction([oracle.METHOD_IDS["two"], oracle.METHOD_IDS["gap_size"]], seq, off, confirm=3,
+                                        max_search=7, two_side=True, threads=8)
+    names, _, _ = records(GOLDEN / "br_reads.fa.gz")
+    assert_same_records(out, names, exp, exp_off)
+
+
+@pytest.mark.gpu
+def test_missing_abundance_is_the_reference_error(tmp_path):
+    r = run(["-i", GOLDEN / "br_reads.fa.gz", "-o", tmp_path / "o.fa", "fasta", "-i", GOLDEN / "br_reads.fa.gz", "-k", "11"])
+    assert r.returncode == 1 and b"abundance" in r.stderr  # Error::AbundanceThresholdOrAbundanceMethod
+
+
+@pytest.mark.gpu
+def test_solid_from_fasta_is_presence_only(tmp_path, oracle, fixture_reads):
+    """`solid -f fasta -k 11` = set::Pcon::from_fasta (src/set/pcon.rs:47-112): every canonical
+    k-mer of the file is in the set."""
+    solid_out = tmp_path / "presence.solid"
+    small = tmp_path / "small.fa"
+    small.write_bytes(b">x\nACGTTGCA\n")
+    r = run(["-i", small, "-o", tmp_path / "o.fa", "-c", "one", "--write-solid", solid_out, "solid", "-i",
+             GOLDEN / "br_reads.fa.gz", "-f", "fasta", "-k", "11"])
+    assert r.returncode == 0 and r.stderr == b"", r.stderr
+    seq, off = fixture_reads
+    c = oracle.Counter(11)
+    c.count(seq, off, threads=8)
+    payload = gzip.open(solid_out).read()
+    assert payload[0] == 11
+    assert np.array_equal(np.frombuffer(payload[1:], dtype=np.uint8), c.to_solid(0, 8).bits())
+
+
+@pytest.mark.gpu
+def test_reference_unit_kats_through_the_cpp_interface(kats):
+    """The reference's #[test] vectors (tests/golden/kats.json) replayed through br::set::Pcon and
+    br::correct::{One,Two,Graph,Greedy,GapSize} of br.hpp."""
+    lines = []
+    n = 0
+    for c in kats["correctors"]:
+        if c["ignored_upstream"]:
+            continue
+        cor = c["corrector"]
+        confirm = cor.get("confirm", cor.get("nb_validate", 2))
+        lines.append(f"KAT {c['module']}::{c['name']} {c['k']} {cor['method']} {confirm} {cor.get('max_search', 7)}")
+        lines += [f"ALL {s}" for s in c["insert_all_kmers_of"]] + [f"KMER {s}" for s in c["insert_kmers"]]
+        lines += [f"CASE {a['input']} {a['expected']}" for a in c["asserts"]]
+        lines.append("END")
+        n += 1
+    for s in kats["set"]:  # src/set/pcon.rs:198-255: forward and canonical k-mers are present, get(0) is false
+        k, seq = s["k"], s["seq"]
+        lines.append(f"KAT set::pcon {k} One 2 7")
+        lines.append(f"ALL {seq}")
+        lines += [f"GET {seq[i:i + k]} 1" for i in range(len(seq) - k + 1)]
+        lines.append(f"GET {'A' * k} 0")
+        lines.append("END")
+    r = subprocess.run([str(KAT)], input="\n".join(lines).encode(), capture_output=True, timeout=600)
+    sys.stdout.write(r.stdout.decode())
+    assert r.returncode == 0, r.stdout.decode() + r.stderr.decode()
+    assert f"{n + len(kats['set'])} KATs".encode() in r.stdout
