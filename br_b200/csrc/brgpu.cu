@@ -6,6 +6,7 @@
 // computes needs a CUDA device and reports BRGPU_E_NO_DEVICE / BRGPU_E_CUDA otherwise.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -18,6 +19,8 @@ using namespace brgpu;
         cudaError_t e__ = (call);                                                                                      \
         if (e__ != cudaSuccess) return fail(ctx, BRGPU_E_CUDA, #call, e__);                                            \
     } while (0)
+
+static inline void dfree(brgpu_ctx *ctx, void *p); // caching allocator, below
 
 namespace brgpu {
 
@@ -87,9 +90,9 @@ static void prof_resolve(brgpu_ctx *ctx) {
 Layout::~Layout() {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    if (d_slot_off) cudaFreeAsync(d_slot_off, ctx->stream);
-    if (d_word2read) cudaFreeAsync(d_word2read, ctx->stream);
-    if (d_order) cudaFreeAsync(d_order, ctx->stream);
+    if (d_slot_off) dfree(ctx, d_slot_off);
+    if (d_word2read) dfree(ctx, d_word2read);
+    if (d_order) dfree(ctx, d_order);
 }
 
 } // namespace brgpu
@@ -101,40 +104,76 @@ static inline uint64_t bits_alloc_bytes(int k) {
     return b < 16 ? 16 : b;
 }
 
-// cudaMalloc-backed allocations that may be exported over CUDA IPC (count table, bitfield)
-static cudaError_t big_alloc(brgpu_ctx *ctx, void **p, uint64_t bytes) {
-    for (size_t i = 0; i < ctx->big_cache.size(); i++)
-        if (ctx->big_cache[i].second == bytes) {
-            *p = ctx->big_cache[i].first;
-            ctx->big_cache.erase(ctx->big_cache.begin() + (long)i);
-            return cudaSuccess;
-        }
+// ------------------------------------------------------------------------------------------
+// Device memory: a context-owned caching allocator over plain cudaMalloc.
+//
+// Every buffer the library uses — handles' payloads and call-scoped temporaries alike — comes
+// from here.  The context runs on ONE stream, so a block that is freed may be handed out again
+// at once: the kernels that still read it were enqueued before the kernels that will write it.
+// No events, no synchronisation on the hot path.  Blocks are found by best fit without
+// splitting (a request takes the smallest cached block that is at most 25 % + 1 MiB larger), so
+// a loop over same-shaped chunks reaches a steady state after its first iteration and calls
+// cudaMalloc never again.  cudaMallocAsync's pool is deliberately not used: without device-wide
+// synchronisation between calls it showed sporadic 50-1500 ms stalls on large blocks
+// (profiles/e2e_stalls_r1.txt).  Blocks are cudaMalloc-backed, hence exportable over CUDA IPC.
+// ------------------------------------------------------------------------------------------
+static const uint64_t POOL_TRIM_BYTES = 48ULL << 30; // cached-but-unused bytes above which the cache is flushed
+
+static void pool_flush(brgpu_ctx *ctx) {
+    if (ctx->pool_free.empty()) return;
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &b : ctx->pool_free) cudaFree(b.first);
+    ctx->pool_free.clear();
+    ctx->pool_free_bytes = 0;
+}
+
+static cudaError_t pool_alloc(brgpu_ctx *ctx, void **p, uint64_t bytes) {
+    *p = nullptr;
+    bytes = (bytes + 511) & ~511ULL;
+    if (bytes == 0) bytes = 512;
+    size_t best = (size_t)-1;
+    const uint64_t limit = bytes + bytes / 4 + (1ULL << 20);
+    for (size_t i = 0; i < ctx->pool_free.size(); i++) {
+        const uint64_t b = ctx->pool_free[i].second;
+        if (b >= bytes && b <= limit && (best == (size_t)-1 || b < ctx->pool_free[best].second)) best = i;
+    }
+    if (best != (size_t)-1) {
+        *p = ctx->pool_free[best].first;
+        ctx->pool_live[*p] = ctx->pool_free[best].second;
+        ctx->pool_free_bytes -= ctx->pool_free[best].second;
+        ctx->pool_free[best] = ctx->pool_free.back();
+        ctx->pool_free.pop_back();
+        return cudaSuccess;
+    }
     cudaError_t e = cudaMalloc(p, bytes);
-    if (e != cudaSuccess && !ctx->big_cache.empty()) { // make room and retry once
+    if (e != cudaSuccess && !ctx->pool_free.empty()) { // make room and retry once
         cudaGetLastError();
-        cudaStreamSynchronize(ctx->stream);
-        for (auto &c : ctx->big_cache) cudaFree(c.first);
-        ctx->big_cache.clear();
+        pool_flush(ctx);
         e = cudaMalloc(p, bytes);
     }
+    if (e == cudaSuccess) ctx->pool_live[*p] = bytes;
     return e;
 }
 
-static void big_free(brgpu_ctx *ctx, void *p, uint64_t bytes) {
+static void pool_release(brgpu_ctx *ctx, void *p) {
     if (!p) return;
-    if (ctx->big_cache.size() < 4) {
-        ctx->big_cache.emplace_back(p, bytes);
-        return;
-    }
-    cudaStreamSynchronize(ctx->stream);
-    cudaFree(p);
+    auto it = ctx->pool_live.find(p);
+    if (it == ctx->pool_live.end()) return; // not ours (never happens)
+    ctx->pool_free.emplace_back(p, it->second);
+    ctx->pool_free_bytes += it->second;
+    ctx->pool_live.erase(it);
+    if (ctx->pool_free_bytes > POOL_TRIM_BYTES) pool_flush(ctx);
 }
 
+// count tables, bitfields, k-mer partitions (sizes recur exactly from call to call)
+static cudaError_t big_alloc(brgpu_ctx *ctx, void **p, uint64_t bytes) { return pool_alloc(ctx, p, bytes); }
+static void big_free(brgpu_ctx *ctx, void *p, uint64_t) { pool_release(ctx, p); }
+
 template <class T> static cudaError_t dalloc(brgpu_ctx *ctx, T **p, uint64_t count) {
-    *p = nullptr;
     if (count == 0) count = 1;
-    return cudaMallocAsync((void **)p, count * sizeof(T), ctx->stream);
+    return pool_alloc(ctx, (void **)p, count * sizeof(T));
 }
+static inline void dfree(brgpu_ctx *ctx, void *p) { pool_release(ctx, p); }
 
 // ------------------------------------------------------------------------------------------
 // context
@@ -168,12 +207,6 @@ extern "C" int brgpu_ctx_create(int device, void *cuda_stream, brgpu_ctx **out) 
         }
         ctx->own_stream = true;
     }
-    // keep freed temporaries in the stream-ordered pool instead of returning them to the driver
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-        uint64_t thr = ~0ULL;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-    }
     if (cudaMalloc((void **)&ctx->d_flags, 16 * sizeof(uint32_t)) != cudaSuccess ||
         cudaMalloc((void **)&ctx->d_hist, 256 * sizeof(uint64_t)) != cudaSuccess ||
         cudaMallocHost((void **)&ctx->h_pinned, 512 * sizeof(uint64_t)) != cudaSuccess) {
@@ -196,7 +229,8 @@ extern "C" void brgpu_ctx_destroy(brgpu_ctx *ctx) {
             cudaEventDestroy(ev.second);
         }
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
-    for (auto &c : ctx->big_cache) cudaFree(c.first);
+    for (auto &b : ctx->pool_free) cudaFree(b.first);
+    for (auto &b : ctx->pool_live) cudaFree(b.first);
     if (ctx->d_flags) cudaFree(ctx->d_flags);
     if (ctx->d_hist) cudaFree(ctx->d_hist);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
@@ -284,8 +318,8 @@ static void reads_release(brgpu_reads *r) {
     if (!r) return;
     if (r->ctx) {
         cudaSetDevice(r->ctx->device);
-        if (r->d_seq) cudaFreeAsync(r->d_seq, r->ctx->stream);
-        if (r->d_len) cudaFreeAsync(r->d_len, r->ctx->stream);
+        if (r->d_seq) dfree(r->ctx, r->d_seq);
+        if (r->d_len) dfree(r->ctx, r->d_len);
     }
     delete r;
 }
@@ -329,7 +363,7 @@ static int reads_from_tight(brgpu_ctx *ctx, const uint8_t *seq, bool seq_on_devi
         d_src = seq + base0;
     } else {
         if ((e = dalloc(ctx, &d_tight, total)) != cudaSuccess) {
-            cudaFreeAsync(d_toff, ctx->stream);
+            dfree(ctx, d_toff);
             reads_release(R);
             return fail(ctx, BRGPU_E_NOMEM, "device allocation (staging)", e);
         }
@@ -339,8 +373,8 @@ static int reads_from_tight(brgpu_ctx *ctx, const uint8_t *seq, bool seq_on_devi
     cudaMemcpyAsync(d_toff, rel.data(), (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream);
     if (n) cudaMemcpyAsync(R->d_len, h_len.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
     launch_scatter_to_slots(ctx, L, d_src, d_toff, R->d_seq);
-    if (d_tight) cudaFreeAsync(d_tight, ctx->stream);
-    cudaFreeAsync(d_toff, ctx->stream);
+    if (d_tight) dfree(ctx, d_tight);
+    dfree(ctx, d_toff);
     e = cudaGetLastError();
     if (e != cudaSuccess) {
         reads_release(R);
@@ -370,7 +404,7 @@ static int reads_tight_offsets(brgpu_reads *R, uint64_t **d_toff_out, uint64_t *
     CK(dalloc(ctx, &d_toff, n + 1));
     CK(dalloc(ctx, &d_tmp, n / 4096 + 4));
     launch_exclusive_scan_u32(ctx, R->d_len, n, d_toff, d_tmp);
-    cudaFreeAsync(d_tmp, ctx->stream);
+    dfree(ctx, d_tmp);
     CK(cudaMemcpyAsync(ctx->h_pinned, d_toff + n, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     *total = ctx->h_pinned[0];
@@ -384,7 +418,7 @@ extern "C" uint64_t brgpu_reads_bases(const brgpu_reads *reads) {
     cudaSetDevice(R->ctx->device);
     uint64_t *d_toff = nullptr, total = 0;
     if (reads_tight_offsets(R, &d_toff, &total) != BRGPU_OK) return 0;
-    cudaFreeAsync(d_toff, R->ctx->stream);
+    dfree(R->ctx, d_toff);
     return total;
 }
 
@@ -399,7 +433,7 @@ extern "C" int brgpu_reads_download(brgpu_reads *reads, uint8_t *seq_host, uint6
     if (st != BRGPU_OK) return st;
     if (required) *required = total;
     if (total > seq_cap || (!seq_host && total) || !offsets_host) {
-        cudaFreeAsync(d_toff, ctx->stream);
+        dfree(ctx, d_toff);
         return fail(ctx, total > seq_cap ? BRGPU_E_OVERFLOW : BRGPU_E_INVALID, "output buffer too small");
     }
     uint8_t *d_tight = nullptr;
@@ -407,8 +441,8 @@ extern "C" int brgpu_reads_download(brgpu_reads *reads, uint8_t *seq_host, uint6
     launch_gather_from_slots(ctx, L, reads->d_seq, reads->d_len, d_toff, d_tight, false);
     if (total) CK(cudaMemcpyAsync(seq_host, d_tight, total, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(offsets_host, d_toff, (L.n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
-    cudaFreeAsync(d_tight, ctx->stream);
-    cudaFreeAsync(d_toff, ctx->stream);
+    dfree(ctx, d_tight);
+    dfree(ctx, d_toff);
     CK(cudaStreamSynchronize(ctx->stream));
     return BRGPU_OK;
 }
@@ -527,8 +561,8 @@ static int set_alloc(brgpu_ctx *ctx, int k, brgpu_set **out) {
     return BRGPU_OK;
 }
 
-// summary geometry: one bit per 2^shift bitfield bits, at most 32 MiB, only for bitfields that
-// do not fit in L2 anyway (k >= 15)
+// summary geometry: one bit per 2^shift bitfield bits (shift >= 6: one bit per 64-bit block), at
+// most 32 MiB, only for bitfields that do not fit in L2 anyway (k >= 15)
 static void summary_geometry(int k, int *shift, uint64_t *bytes) {
     uint64_t n_bytes = table_len(k) >> 3;
     if (n_bytes <= (8ULL << 20)) {
@@ -536,16 +570,86 @@ static void summary_geometry(int k, int *shift, uint64_t *bytes) {
         *bytes = 0;
         return;
     }
-    int sh = 5;
+    int sh = 6;
     while (((n_bytes << 3) >> sh) / 8 > (32ULL << 20)) sh++;
     *shift = sh;
     *bytes = (((n_bytes << 3) >> sh) + 7) / 8;
 }
 
-// (re)build the occupancy summary if the bitfield changed since the last build
+// The rank-compacted copy pays off while its blocks stay L2 resident next to the 8 B-per-group
+// directory (B200: 126 MB of L2): at most this many bytes of occupied blocks.
+static const uint64_t COMPACT_MAX_BLOCK_BYTES = 64ULL << 20;
+
+static void compact_release(brgpu_set *s) {
+    if (s->d_dir) big_free(s->ctx, s->d_dir, s->dir_bytes);
+    if (s->d_blocks) big_free(s->ctx, s->d_blocks, s->blocks_bytes);
+    s->d_dir = nullptr;
+    s->d_blocks = nullptr;
+    s->dir_bytes = s->blocks_bytes = 0;
+    s->compact_valid = false;
+}
+
+// Build the rank directory + compacted blocks from a valid shift-6 summary.  One host round trip
+// (the number of occupied blocks sizes the allocation); callers that synchronise anyway pass the
+// already-known count.
+static int build_compact(brgpu_set *s) {
+    brgpu_ctx *ctx = s->ctx;
+    compact_release(s);
+    if (!s->d_summary || s->summary_shift != 6) return BRGPU_OK;
+    if (const char *off = getenv("BRGPU_NO_COMPACT")) // test hook: keep lookups on summary + bitfield
+        if (*off && *off != '0') return BRGPU_OK;
+    const uint64_t n_words = s->summary_bytes >> 2;
+    uint32_t *d_pop = nullptr;
+    uint64_t *d_rank = nullptr, *d_tmp = nullptr;
+    cudaError_t e = dalloc(ctx, &d_pop, n_words);
+    if (e == cudaSuccess) e = dalloc(ctx, &d_rank, n_words + 1);
+    if (e == cudaSuccess) e = dalloc(ctx, &d_tmp, n_words / 4096 + 4);
+    auto drop = [&]() {
+        if (d_pop) dfree(ctx, d_pop);
+        if (d_rank) dfree(ctx, d_rank);
+        if (d_tmp) dfree(ctx, d_tmp);
+    };
+    if (e != cudaSuccess) {
+        drop();
+        return fail(ctx, BRGPU_E_NOMEM, "device allocation (rank directory)", e);
+    }
+    launch_summary_rank(ctx, s->d_summary, n_words, d_pop, d_rank, d_tmp);
+    e = cudaMemcpyAsync(ctx->h_pinned + 300, d_rank + n_words, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        drop();
+        return fail(ctx, BRGPU_E_CUDA, "rank directory", e);
+    }
+    s->n_occupied = ctx->h_pinned[300];
+    if (s->n_occupied * 8 <= COMPACT_MAX_BLOCK_BYTES) {
+        // round the allocation up so that sets of similar size reuse the cached block
+        const uint64_t bbytes = ((s->n_occupied * 8 + (8ULL << 20)) >> 23) << 23;
+        e = big_alloc(ctx, &s->d_dir, n_words * 8);
+        if (e == cudaSuccess) {
+            s->dir_bytes = n_words * 8;
+            e = big_alloc(ctx, (void **)&s->d_blocks, bbytes);
+            if (e == cudaSuccess) s->blocks_bytes = bbytes;
+        }
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            compact_release(s); // not fatal: lookups fall back to summary + bitfield
+        } else {
+            launch_compact_blocks(ctx, s->d_summary, d_rank, s->d_bits, n_words, s->d_dir, s->d_blocks);
+            s->compact_valid = true;
+        }
+    }
+    drop();
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ctx, BRGPU_E_CUDA, "compacted blocks", e);
+    return BRGPU_OK;
+}
+
+// (re)build the occupancy summary (and the rank-compacted copy) if the bitfield changed since
+// the last build
 static int ensure_summary(brgpu_set *s) {
     brgpu_ctx *ctx = s->ctx;
     if (s->summary_valid) return BRGPU_OK;
+    compact_release(s);
     int shift;
     uint64_t bytes;
     summary_geometry(s->k, &shift, &bytes);
@@ -562,16 +666,22 @@ static int ensure_summary(brgpu_set *s) {
     launch_build_summary(ctx, s->d_bits, s->n_bytes, shift, s->d_summary);
     CK(cudaGetLastError());
     s->summary_valid = true;
-    return BRGPU_OK;
+    return build_compact(s);
 }
 
 static SetView set_view(const brgpu_set *s) {
-    return SetView{s->d_bits, s->summary_bytes ? s->d_summary : nullptr, s->summary_shift, s->k};
+    SetView v{s->d_bits, s->summary_bytes ? s->d_summary : nullptr, s->summary_shift, s->k};
+    if (s->compact_valid) {
+        v.dir = s->d_dir;
+        v.blocks = s->d_blocks;
+    }
+    return v;
 }
 
 extern "C" void brgpu_set_free(brgpu_set *s) {
     if (!s) return;
     cudaSetDevice(s->ctx->device);
+    compact_release(s);
     if (s->d_summary) big_free(s->ctx, s->d_summary, s->summary_bytes);
     big_free(s->ctx, s->d_bits, bits_alloc_bytes(s->k));
     delete s;
@@ -641,7 +751,7 @@ static int kmers_create(brgpu_ctx *ctx, int k, const brgpu_reads *reads, brgpu_k
         (e = big_alloc(ctx, (void **)&km->d_base, (km->n_buckets + 1) * 8)) != cudaSuccess ||
         (e = dalloc(ctx, &d_fill, km->n_buckets)) != cudaSuccess ||
         (e = dalloc(ctx, &d_tmp, km->n_buckets / 4096 + 4)) != cudaSuccess) {
-        if (d_fill) cudaFreeAsync(d_fill, ctx->stream);
+        if (d_fill) dfree(ctx, d_fill);
         big_free(ctx, km->d_res, km->capacity * 2);
         big_free(ctx, km->d_base, (km->n_buckets + 1) * 8);
         delete km;
@@ -649,8 +759,8 @@ static int kmers_create(brgpu_ctx *ctx, int k, const brgpu_reads *reads, brgpu_k
     }
     launch_bucket_partition(ctx, L, reads->d_seq, reads->d_len, k, km->n_buckets, d_fill, km->d_base, d_tmp, km->d_res,
                             km->n_kmers_hint);
-    cudaFreeAsync(d_fill, ctx->stream);
-    cudaFreeAsync(d_tmp, ctx->stream);
+    dfree(ctx, d_fill);
+    dfree(ctx, d_tmp);
     e = cudaGetLastError();
     if (e != cudaSuccess) {
         big_free(ctx, km->d_res, km->capacity * 2);
@@ -691,7 +801,7 @@ static int set_from_reads_bucketed(brgpu_ctx *ctx, int k, int abundance, int sel
     int shift;
     uint64_t sbytes;
     summary_geometry(k, &shift, &sbytes);
-    if (sbytes && shift == 5) {
+    if (sbytes && shift == 6) {
         e = big_alloc(ctx, (void **)&s->d_summary, sbytes);
         if (e != cudaSuccess) {
             kmers_release(km);
@@ -729,6 +839,13 @@ static int set_from_reads_bucketed(brgpu_ctx *ctx, int k, int abundance, int sel
     s->abundance = abundance;
     s->summary_valid = s->d_summary != nullptr; // written by the counting sweep itself
     memcpy(s->hist, hist, sizeof(hist));
+    if (s->summary_valid) {
+        st = build_compact(s);
+        if (st != BRGPU_OK) {
+            brgpu_set_free(s);
+            return st;
+        }
+    }
     *out = s;
     return BRGPU_OK;
 }
@@ -797,7 +914,7 @@ extern "C" int brgpu_kmers_count_range(brgpu_kmers *km, void *const *peer_residu
     launch_bucket_count_multi(ctx, res, base, n_peers + 1, bucket_begin, bucket_end, set ? abundance : 0,
                               set ? set->d_bits : nullptr, ctx->d_hist, km->n_kmers_hint * (double)(n_peers + 1));
     cudaError_t e = read_hist(ctx, hist_host);
-    if (d_pb) cudaFreeAsync(d_pb, ctx->stream);
+    if (d_pb) dfree(ctx, d_pb);
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) return fail(ctx, BRGPU_E_CUDA, "sharded bucket counting", e);
     return BRGPU_OK;
@@ -887,7 +1004,7 @@ extern "C" int brgpu_set_insert_batch(brgpu_set *s, const uint64_t *kmers_host, 
     CK(cudaMemcpyAsync(d_k, kmers_host, n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
     s->summary_valid = false;
     launch_insert_batch(ctx, s->d_bits, s->k, d_k, n);
-    cudaFreeAsync(d_k, ctx->stream);
+    dfree(ctx, d_k);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(ctx->stream));
     return BRGPU_OK;
@@ -924,8 +1041,8 @@ extern "C" int brgpu_set_get_batch(brgpu_set *s, const uint64_t *kmers_host, uin
     CK(cudaMemcpyAsync(d_k, kmers_host, n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
     launch_get_batch(ctx, s->d_bits, s->k, d_k, n, d_o);
     CK(cudaMemcpyAsync(out_host, d_o, n, cudaMemcpyDeviceToHost, ctx->stream));
-    cudaFreeAsync(d_k, ctx->stream);
-    cudaFreeAsync(d_o, ctx->stream);
+    dfree(ctx, d_k);
+    dfree(ctx, d_o);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(ctx->stream));
     return BRGPU_OK;
@@ -963,16 +1080,16 @@ static int correct_attempt(brgpu_ctx *ctx, const brgpu_set *set, const uint8_t *
     cudaError_t e = cudaSuccess;
     auto cleanup = [&]() {
         for (int b = 0; b < 2; b++) {
-            if (buf[b]) cudaFreeAsync(buf[b], ctx->stream);
-            if (len[b]) cudaFreeAsync(len[b], ctx->stream);
+            if (buf[b]) dfree(ctx, buf[b]);
+            if (len[b]) dfree(ctx, len[b]);
         }
-        if (d_bitmap) cudaFreeAsync(d_bitmap, ctx->stream);
-        if (d_scratch) cudaFreeAsync(d_scratch, ctx->stream);
-        if (work.d_n_seg) cudaFreeAsync(work.d_n_seg, ctx->stream);
-        if (work.d_seg_first) cudaFreeAsync(work.d_seg_first, ctx->stream);
-        if (work.d_scan_tmp) cudaFreeAsync(work.d_scan_tmp, ctx->stream);
-        if (work.d_seg_out) cudaFreeAsync(work.d_seg_out, ctx->stream);
-        if (work.d_seg_recs) cudaFreeAsync(work.d_seg_recs, ctx->stream);
+        if (d_bitmap) dfree(ctx, d_bitmap);
+        if (d_scratch) dfree(ctx, d_scratch);
+        if (work.d_n_seg) dfree(ctx, work.d_n_seg);
+        if (work.d_seg_first) dfree(ctx, work.d_seg_first);
+        if (work.d_scan_tmp) dfree(ctx, work.d_scan_tmp);
+        if (work.d_seg_out) dfree(ctx, work.d_seg_out);
+        if (work.d_seg_recs) dfree(ctx, work.d_seg_recs);
     };
     size_t scratch_per_warp = 0;
     for (uint64_t i = 0; i < n_methods; i++) {
@@ -1080,8 +1197,8 @@ static int reads_reslot(brgpu_reads *in, unsigned slack_extra, brgpu_reads **out
     CK(cudaMemcpyAsync(h_off.data(), d_toff, (n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     st = reads_from_tight(ctx, d_tight, true, h_off.data(), n, slack_extra, out);
-    cudaFreeAsync(d_tight, ctx->stream);
-    cudaFreeAsync(d_toff, ctx->stream);
+    dfree(ctx, d_tight);
+    dfree(ctx, d_toff);
     return st;
 }
 

@@ -62,6 +62,25 @@ __global__ void __launch_bounds__(256)
                     idx[j] = canonical_index(window_kmer(prev, cur, g + j, mask), k);
                     go[j] = g + j >= t_lo && g + j < t_hi;
                 }
+                if (set.dir) {
+                    // rank-compacted set: directory entry (8 B, L2), then the occupied block (8 B)
+                    uint2 e[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        e[j] = make_uint2(0u, 0u);
+                        if (go[j]) e[j] = __ldg(set.dir + (idx[j] >> 11));
+                    }
+                    uint64_t blk[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const uint32_t b = (uint32_t)(idx[j] >> 6) & 31u;
+                        blk[j] = 0;
+                        if ((e[j].x >> b) & 1u) blk[j] = __ldg(set.blocks + (e[j].y + __popc(e[j].x & ((1u << b) - 1u))));
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; j++) out |= (uint32_t)((blk[j] >> (idx[j] & 63)) & 1ULL) << (g + j);
+                    continue;
+                }
                 if (set.summary) {
                     uint32_t sw[8];
 #pragma unroll
@@ -94,7 +113,7 @@ void launch_solid_bitmap(brgpu_ctx *ctx, const Layout &L, const uint8_t *d_seq, 
     uint64_t need = (n_words + 255) / 256;
     uint64_t capb = (uint64_t)ctx->sm_count * 8;
     solid_bitmap_kernel<<<(unsigned)(need < capb ? need : capb), 256, 0, ctx->stream>>>(
-        d_seq, d_len, L.d_slot_off, L.d_word2read, n_words, SolidView{set.bits, set.summary, set.shift, set.k}, d_bitmap);
+        d_seq, d_len, L.d_slot_off, L.d_word2read, n_words, SolidView{set.bits, set.summary, set.shift, set.k, (const uint2 *)set.dir, set.blocks}, d_bitmap);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1388,7 +1407,7 @@ void launch_scan(brgpu_ctx *ctx, const Layout &L, const uint8_t *d_in, const uin
         seg_count_kernel<<<blocks, 256, 0, ctx->stream>>>(d_len_in, (uint32_t)L.n, (uint32_t)p.k, w.d_n_seg);
     }
     launch_exclusive_scan_u32(ctx, w.d_n_seg, L.n, w.d_seg_first, w.d_scan_tmp);
-    const SolidView sv{set.bits, set.summary, set.shift, set.k};
+    const SolidView sv{set.bits, set.summary, set.shift, set.k, (const uint2 *)set.dir, set.blocks};
     static const char *spec_names[5] = {"scan_one", "scan_two", "scan_graph", "scan_greedy", "scan_gap_size"};
     static const char *merge_names[5] = {"merge_one", "merge_two", "merge_graph", "merge_greedy", "merge_gap_size"};
 #define BRGPU_LAUNCH_SCAN(M)                                                                                           \

@@ -6,6 +6,7 @@
 #include <cstdint>
 #include <memory>
 #include <string>
+#include <unordered_map>
 #include <utility>
 #include <vector>
 
@@ -37,9 +38,10 @@ struct brgpu_ctx {
     uint32_t *d_flags = nullptr; // [0] work-queue cursor, [1] overflow flag, [2..] spare
     uint64_t *d_hist = nullptr;  // 256 bins
     uint64_t *h_pinned = nullptr; // 512 x u64 pinned staging for small readbacks
-    // freed count tables / bitfields kept for the next call (cudaMalloc of GiBs costs ms and
-    // cudaFree synchronises the device); reuse is ordered by the context's stream
-    std::vector<std::pair<void *, uint64_t>> big_cache;
+    // caching device allocator (brgpu.cu): blocks handed out (ptr -> bytes) and cached free blocks
+    std::unordered_map<void *, uint64_t> pool_live;
+    std::vector<std::pair<void *, uint64_t>> pool_free;
+    uint64_t pool_free_bytes = 0;
 };
 
 namespace brgpu {
@@ -97,6 +99,13 @@ struct brgpu_set {
     uint64_t summary_bytes = 0;
     int summary_shift = 0;
     bool summary_valid = false;
+    // rank-compacted copy of a sparse bitfield (see SolidView in kmer.cuh); rebuilt with the summary
+    void *d_dir = nullptr;       // uint2 per summary word
+    uint64_t dir_bytes = 0;
+    uint64_t *d_blocks = nullptr;
+    uint64_t blocks_bytes = 0;   // allocation size
+    uint64_t n_occupied = 0;     // occupied 64-bit blocks
+    bool compact_valid = false;  // d_dir/d_blocks describe the current bitfield
 };
 
 namespace brgpu {
@@ -151,6 +160,12 @@ void launch_merge_slice(brgpu_ctx *ctx, uint8_t *d_counts, void *const *peers, i
 
 // occupancy summary of a bitfield: one bit per 2^shift bitfield bits
 void launch_build_summary(brgpu_ctx *ctx, const uint8_t *d_bits, uint64_t n_bytes, int shift, uint32_t *d_summary);
+// rank directory over a shift-6 summary: d_pop[g] = popc(summary[g]), d_rank = exclusive scan (n + 1)
+void launch_summary_rank(brgpu_ctx *ctx, const uint32_t *d_summary, uint64_t n_words, uint32_t *d_pop, uint64_t *d_rank,
+                         uint64_t *d_scan_tmp);
+// dir[g] = {summary[g], rank[g]}; blocks[rank[g] + i] = i-th occupied 64-bit block of group g
+void launch_compact_blocks(brgpu_ctx *ctx, const uint32_t *d_summary, const uint64_t *d_rank, const uint8_t *d_bits,
+                           uint64_t n_words, void *d_dir, uint64_t *d_blocks);
 
 // device view of a set for the correction kernels
 struct SetView {
@@ -158,6 +173,8 @@ struct SetView {
     const uint32_t *summary;
     int shift;
     int k;
+    const void *dir = nullptr;        // uint2 *
+    const uint64_t *blocks = nullptr;
 };
 
 // ---- part 2 kernels (correct_kernels.cu) ----

@@ -447,8 +447,9 @@ __global__ void __launch_bounds__(BUCKET_THREADS)
                         int abundance, uint32_t *__restrict__ bitfield32, uint32_t *__restrict__ summary32,
                         int summary_shift, unsigned long long *__restrict__ g_hist) {
     extern __shared__ uint32_t cnt[];          // BUCKET_COUNTERS / 4 words of u8 counters
-    __shared__ uint32_t sh_bits[BUCKET_COUNTERS / 32]; // the bucket's slice of the bitfield
+    __shared__ uint64_t sh_bits64[BUCKET_COUNTERS / 64]; // the bucket's slice of the bitfield
     __shared__ unsigned int sh_hist[256];
+    uint32_t *sh_bits = reinterpret_cast<uint32_t *>(sh_bits64);
     uint8_t *cnt8 = reinterpret_cast<uint8_t *>(cnt);
     for (int t = threadIdx.x; t < 256; t += BUCKET_THREADS) sh_hist[t] = 0;
     for (int t = threadIdx.x; t < BUCKET_COUNTERS / 4; t += BUCKET_THREADS) cnt[t] = 0; // once: owners keep it clean
@@ -517,13 +518,14 @@ __global__ void __launch_bounds__(BUCKET_THREADS)
         __syncthreads();
         // ---- write the slice of the bitfield (+ its summary bits) ----
         if (bitfield32) {
-            for (int t = threadIdx.x; t < BUCKET_COUNTERS / 32; t += BUCKET_THREADS) {
-                const uint32_t out = sh_bits[t];
-                const uint64_t word = b * (BUCKET_COUNTERS / 32) + (uint64_t)t;
-                bitfield32[word] = out;
-                if (summary32 && summary_shift == 5) { // one summary bit per bitfield word
+            uint64_t *bitfield64 = reinterpret_cast<uint64_t *>(bitfield32);
+            for (int t = threadIdx.x; t < BUCKET_COUNTERS / 64; t += BUCKET_THREADS) {
+                const uint64_t out = sh_bits64[t];
+                const uint64_t block = b * (BUCKET_COUNTERS / 64) + (uint64_t)t;
+                bitfield64[block] = out;
+                if (summary32 && summary_shift == 6) { // one summary bit per 64-bit block
                     uint32_t m = __ballot_sync(FULL, out != 0);
-                    if ((threadIdx.x & 31) == 0) summary32[word >> 5] = m;
+                    if ((threadIdx.x & 31) == 0) summary32[block >> 5] = m;
                 }
             }
         }
@@ -859,6 +861,52 @@ void launch_build_summary(brgpu_ctx *ctx, const uint8_t *d_bits, uint64_t n_byte
     ProfScope ps(ctx, "build_summary", (double)n_bytes + (double)n_summary_words * 4.0);
     build_summary_kernel<<<grid_for(ctx, n_summary_words * 32, 256, 8), 256, 0, ctx->stream>>>(
         reinterpret_cast<const uint32_t *>(d_bits), n_words, shift - 5, d_summary, n_summary_words);
+}
+
+// ------------------------------------------------------------------------------------------
+// Rank-compacted copy of a sparse bitfield (SolidView::dir / blocks in kmer.cuh).  Input: the
+// shift-6 summary (one bit per 64-bit block).  popc per summary word -> exclusive scan = rank of
+// the first block of every group; then every group copies its occupied blocks, in order, to
+// blocks[rank ...] and stores {occupancy, rank} next to each other so that a lookup needs one
+// 8-byte load to know whether and where.  Only occupied blocks are read from the bitfield.
+// ------------------------------------------------------------------------------------------
+__global__ void summary_popc_kernel(const uint32_t *__restrict__ summary, uint64_t n_words, uint32_t *__restrict__ pop) {
+    for (uint64_t g = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; g < n_words;
+         g += (uint64_t)gridDim.x * blockDim.x)
+        pop[g] = (uint32_t)__popc(summary[g]);
+}
+
+void launch_summary_rank(brgpu_ctx *ctx, const uint32_t *d_summary, uint64_t n_words, uint32_t *d_pop, uint64_t *d_rank,
+                         uint64_t *d_scan_tmp) {
+    {
+        ProfScope ps(ctx, "summary_popc", (double)n_words * 8.0);
+        summary_popc_kernel<<<grid_for(ctx, n_words, 256, 8), 256, 0, ctx->stream>>>(d_summary, n_words, d_pop);
+    }
+    launch_exclusive_scan_u32(ctx, d_pop, n_words, d_rank, d_scan_tmp);
+}
+
+__global__ void __launch_bounds__(256)
+    compact_blocks_kernel(const uint32_t *__restrict__ summary, const uint64_t *__restrict__ rank,
+                          const uint64_t *__restrict__ bits64, uint64_t n_words, uint2 *__restrict__ dir,
+                          uint64_t *__restrict__ blocks) {
+    for (uint64_t g = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; g < n_words;
+         g += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t occ = summary[g];
+        uint64_t r = rank[g];
+        dir[g] = make_uint2(occ, (uint32_t)r);
+        while (occ) {
+            const int i = __ffs(occ) - 1;
+            blocks[r++] = __ldcs(bits64 + (g << 5) + (uint64_t)i);
+            occ &= occ - 1;
+        }
+    }
+}
+
+void launch_compact_blocks(brgpu_ctx *ctx, const uint32_t *d_summary, const uint64_t *d_rank, const uint8_t *d_bits,
+                           uint64_t n_words, void *d_dir, uint64_t *d_blocks) {
+    ProfScope ps(ctx, "compact_blocks", (double)n_words * 20.0);
+    compact_blocks_kernel<<<grid_for(ctx, n_words, 256, 8), 256, 0, ctx->stream>>>(
+        d_summary, d_rank, reinterpret_cast<const uint64_t *>(d_bits), n_words, reinterpret_cast<uint2 *>(d_dir), d_blocks);
 }
 
 // ------------------------------------------------------------------------------------------

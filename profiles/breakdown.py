@@ -31,6 +31,9 @@ def main():
     ap.add_argument("--k", type=int, default=17)
     ap.add_argument("--methods", nargs="+", default=["one", "two"])
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--e2e-steps", type=int, default=6)
+    ap.add_argument("--no-step-sync", action="store_true", help="no device synchronisation between e2e steps (as in bench.py)")
+    ap.add_argument("--smi", action="store_true", help="poll nvidia-smi every 200 ms during the e2e loop, like bench.py")
     a = ap.parse_args()
 
     stream = torch.cuda.Stream()
@@ -93,7 +96,13 @@ def main():
         for key in ("reads", "solid", "out"):
             state.pop(key).free()
         torch.cuda.synchronize()
-        for it in range(6):
+        smi = None
+        if a.smi:
+            import subprocess
+            smi = subprocess.Popen(["nvidia-smi", "--query-gpu=clocks.sm,clocks_event_reasons.active", "--format=csv,noheader",
+                                    "-lms", "200", "-i", "0"], stdout=subprocess.DEVNULL)
+            time.sleep(2.0)
+        for it in range(a.e2e_steps):
             t = [time.perf_counter()]
             reads = br_b200.Reads.upload(ctx, h_seq, h_off)
             t.append(time.perf_counter())
@@ -107,11 +116,15 @@ def main():
             solid.free()
             reads.free()
             t.append(time.perf_counter())
-            torch.cuda.synchronize()
+            if not a.no_step_sync:
+                torch.cuda.synchronize()
             t.append(time.perf_counter())
             d = [(t[j + 1] - t[j]) * 1e3 for j in range(len(t) - 1)]
-            print("e2e step %d: upload %.2f  set %.2f  correct %.2f  download %.2f  free %.2f  sync %.2f  total %.2f ms"
-                  % (it, *d, (t[-1] - t[0]) * 1e3))
+            if a.e2e_steps <= 8 or (t[-1] - t[0]) * 1e3 > 30.0:
+                print("e2e step %d: upload %.2f  set %.2f  correct %.2f  download %.2f  free %.2f  sync %.2f  total %.2f ms"
+                      % (it, *d, (t[-1] - t[0]) * 1e3))
+        if smi is not None:
+            smi.terminate()
         state["reads"] = br_b200.Reads.upload(ctx, h_seq, h_off)
         state["solid"] = br_b200.Pcon.from_reads(ctx, state["reads"], a.k, abundance=2)
 

@@ -246,3 +246,33 @@ def test_segment_scratch_overflow_falls_back_to_the_merge_warp(gpu, oracle):
         compare_batches(f"segments {method}", got, got_off, exp, exp_off, seq, off)
     e0 = os_.correct(2, reads[0])
     assert len(e0) > len(reads[0]) + 3500  # the Graph walk really is longer than a scratch region
+
+
+@pytest.mark.parametrize("k", [15, 17])
+def test_large_k_sets_correct_like_the_oracle_on_every_lookup_path(gpu, oracle, k, monkeypatch):
+    """k = 15 / 17 (BASELINE configs 2-5): the set is looked up through the rank-compacted copy
+    (directory + occupied 64-bit blocks) when it is sparse, through summary + bitfield otherwise.
+    Both paths, for a set built by counting and for the same set loaded as a bitfield, must give
+    the oracle's bytes for all five methods chained with the reversed pass."""
+    br, ctx = gpu
+    from br_b200 import synth
+
+    genome = synth.make_genome(60_000, seed=5)
+    seq, off, _ = synth.make_reads(genome, 25, 0.08, seed=6, mean_len=3000)
+    oc = oracle.Counter(k)
+    oc.count(seq, off, threads=8)
+    osolid = oc.to_solid(2, threads=8)
+    ids = [oracle.METHOD_IDS[m] for m in METHODS]
+    exp, exp_off = osolid.run_correction(ids, seq, off, confirm=4, max_search=7, threads=8)
+    changed = int((np.diff(exp_off.astype(np.int64)) != np.diff(off.astype(np.int64))).sum())
+    assert changed > 10  # the chain really edits reads
+    for no_compact in ("0", "1"):
+        monkeypatch.setenv("BRGPU_NO_COMPACT", no_compact)
+        counted = br.Pcon.from_reads(ctx, (seq, off), k, abundance=2)
+        assert np.array_equal(counted.bitfield(), osolid.bits())
+        loaded = br.Pcon.from_bitfield(ctx, k, osolid.bits())
+        for name, s in (("counted", counted), ("loaded", loaded)):
+            got, got_off = br.correct_batch(br.build_methods(METHODS, s, 4, 7), seq, off)
+            compare_batches(f"k={k} {name} no_compact={no_compact}", got, got_off, exp, exp_off, seq, off)
+        counted.free()
+        loaded.free()
