@@ -75,6 +75,8 @@ SIGNATURES = {
     "brgpu_kmers_buckets": (u64, [vp]),
     "brgpu_kmers_ipc_export": (C.c_int, [vp, vp]),
     "brgpu_kmers_count_range": (C.c_int, [vp, vp, vp, C.c_int, u64, u64, C.c_int, vp, vp]),
+    "brgpu_kmers_offsets_at": (C.c_int, [vp, vp, u64, vp]),
+    "brgpu_kmers_count_range_staged": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, u64, u64, C.c_int, vp, vp]),
     "brgpu_kmers_free": (None, [vp]),
     "brgpu_profile_enable": (C.c_int, [vp, C.c_int]),
     "brgpu_profile_reset": (C.c_int, [vp]),

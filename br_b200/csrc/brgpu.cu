@@ -881,9 +881,9 @@ extern "C" int brgpu_kmers_ipc_export(brgpu_kmers *km, uint8_t handles_out[128])
     return BRGPU_OK;
 }
 
-extern "C" int brgpu_kmers_count_range(brgpu_kmers *km, void *const *peer_residues, void *const *peer_offsets,
-                                       int n_peers, uint64_t bucket_begin, uint64_t bucket_end, int abundance,
-                                       brgpu_set *set, uint64_t hist_host[256]) {
+static int kmers_count_range(brgpu_kmers *km, void *const *peer_residues, void *const *peer_offsets,
+                             const uint64_t *peer_first, const uint64_t *peer_last, int n_peers, uint64_t bucket_begin,
+                             uint64_t bucket_end, int abundance, brgpu_set *set, uint64_t hist_host[256]) {
     if (!km || !hist_host || (n_peers && (!peer_residues || !peer_offsets))) return BRGPU_E_INVALID;
     brgpu_ctx *ctx = km->ctx;
     if (n_peers < 0 || n_peers > 15) return fail(ctx, BRGPU_E_INVALID, "at most 15 peers");
@@ -895,16 +895,45 @@ extern "C" int brgpu_kmers_count_range(brgpu_kmers *km, void *const *peer_residu
     // bring the peers' bucket offsets of this range into local memory (8 B per bucket and peer)
     uint64_t *d_pb = nullptr;
     if (n_peers) CK(dalloc(ctx, &d_pb, (uint64_t)n_peers * (nb + 1)));
+    // staged variant: the peers' residues of the range as well, one bulk copy per peer
+    uint16_t *d_stage = nullptr;
+    if (n_peers && peer_first) {
+        uint64_t total = 0;
+        for (int p = 0; p < n_peers; p++) {
+            if (peer_last[p] < peer_first[p]) {
+                dfree(ctx, d_pb);
+                return fail(ctx, BRGPU_E_INVALID, "bad peer residue range");
+            }
+            total += peer_last[p] - peer_first[p];
+        }
+        cudaError_t e = dalloc(ctx, &d_stage, total + 1);
+        if (e != cudaSuccess) {
+            dfree(ctx, d_pb);
+            return fail(ctx, BRGPU_E_NOMEM, "device allocation (peer residues)", e);
+        }
+    }
     const uint16_t *res[16];
     const uint64_t *base[16];
     res[0] = km->d_res;
     base[0] = km->d_base;
+    uint64_t staged = 0;
     for (int p = 0; p < n_peers; p++) {
         uint64_t *dst = d_pb + (uint64_t)p * (nb + 1);
         CK(cudaMemcpyAsync(dst, (const uint64_t *)peer_offsets[p] + bucket_begin, (nb + 1) * 8, cudaMemcpyDefault,
                            ctx->stream));
-        res[p + 1] = (const uint16_t *)peer_residues[p];
         base[p + 1] = dst - bucket_begin; // indexable by absolute bucket id inside the range
+        if (d_stage) {
+            const uint64_t n = peer_last[p] - peer_first[p];
+            ProfScope ps(ctx, "peer_residue_copy", (double)n * 2.0, false);
+            if (n)
+                CK(cudaMemcpyAsync(d_stage + staged, (const uint16_t *)peer_residues[p] + peer_first[p], n * 2,
+                                   cudaMemcpyDefault, ctx->stream));
+            // the kernel indexes a source by the peer's absolute residue offsets
+            res[p + 1] = d_stage + staged - peer_first[p];
+            staged += n;
+        } else {
+            res[p + 1] = (const uint16_t *)peer_residues[p];
+        }
     }
     CK(cudaMemsetAsync(ctx->d_hist, 0, 256 * sizeof(uint64_t), ctx->stream));
     if (set) {
@@ -915,8 +944,40 @@ extern "C" int brgpu_kmers_count_range(brgpu_kmers *km, void *const *peer_residu
                               set ? set->d_bits : nullptr, ctx->d_hist, km->n_kmers_hint * (double)(n_peers + 1));
     cudaError_t e = read_hist(ctx, hist_host);
     if (d_pb) dfree(ctx, d_pb);
+    if (d_stage) dfree(ctx, d_stage);
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) return fail(ctx, BRGPU_E_CUDA, "sharded bucket counting", e);
+    return BRGPU_OK;
+}
+
+extern "C" int brgpu_kmers_count_range(brgpu_kmers *km, void *const *peer_residues, void *const *peer_offsets,
+                                       int n_peers, uint64_t bucket_begin, uint64_t bucket_end, int abundance,
+                                       brgpu_set *set, uint64_t hist_host[256]) {
+    return kmers_count_range(km, peer_residues, peer_offsets, nullptr, nullptr, n_peers, bucket_begin, bucket_end,
+                             abundance, set, hist_host);
+}
+
+extern "C" int brgpu_kmers_count_range_staged(brgpu_kmers *km, void *const *peer_residues, void *const *peer_offsets,
+                                              const uint64_t *peer_first, const uint64_t *peer_last, int n_peers,
+                                              uint64_t bucket_begin, uint64_t bucket_end, int abundance,
+                                              brgpu_set *set, uint64_t hist_host[256]) {
+    if (n_peers && (!peer_first || !peer_last)) return BRGPU_E_INVALID;
+    return kmers_count_range(km, peer_residues, peer_offsets, peer_first, peer_last, n_peers, bucket_begin, bucket_end,
+                             abundance, set, hist_host);
+}
+
+extern "C" int brgpu_kmers_offsets_at(brgpu_kmers *km, const uint64_t *buckets_host, uint64_t n, uint64_t *offsets_host) {
+    if (!km || (n && (!buckets_host || !offsets_host))) return BRGPU_E_INVALID;
+    brgpu_ctx *ctx = km->ctx;
+    if (n > 256) return fail(ctx, BRGPU_E_INVALID, "at most 256 boundaries per call");
+    cudaSetDevice(ctx->device);
+    for (uint64_t i = 0; i < n; i++) {
+        if (buckets_host[i] > km->n_buckets) return fail(ctx, BRGPU_E_INVALID, "bucket id out of range");
+        CK(cudaMemcpyAsync(ctx->h_pinned + i, km->d_base + buckets_host[i], sizeof(uint64_t), cudaMemcpyDeviceToHost,
+                           ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (uint64_t i = 0; i < n; i++) offsets_host[i] = ctx->h_pinned[i];
     return BRGPU_OK;
 }
 

@@ -210,7 +210,20 @@ __device__ __forceinline__ void warp_copy(uint8_t *dst, const uint8_t *src, uint
     const uint32_t n_words = (n - head) >> 2;
     const uint32_t a = (uint32_t)((uintptr_t)s0 & 3u);
     const uint32_t *s4 = reinterpret_cast<const uint32_t *>(s0 - a);
-    for (uint32_t w = lane; w < n_words; w += 32) {
+    // four independent load pairs in flight per lane: a 2 KiB piece is 4 round trips, not 16 (the
+    // merge of the longest read is a chain of such copies and sets the kernel's tail)
+    uint32_t w = lane;
+    for (; w + 96 < n_words; w += 128) {
+        uint32_t lo[4], hi[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            lo[u] = s4[w + 32 * u];
+            hi[u] = a ? s4[w + 32 * u + 1] : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) d4[w + 32 * u] = a ? __funnelshift_r(lo[u], hi[u], 8 * a) : lo[u];
+    }
+    for (; w < n_words; w += 32) {
         uint32_t lo = s4[w];
         uint32_t v = lo;
         if (a) v = __funnelshift_r(lo, s4[w + 1], 8 * a);
@@ -537,50 +550,66 @@ __device__ __forceinline__ Corr exist_correct_error(Rd &rd, uint64_t kmer, uint3
         sc = scen_two(rd.lane, K0, sublen, sb, m & 0xf, (m >> 4) & 0xf, (m >> 8) & 0xf, (m >> 12) & 0xf, rd.mask);
     }
 
-    // round 3: items (s, u), u = 0 .. c+1
-    const uint32_t per = c + 2;
-    const uint32_t Q = (uint32_t)NS * per;
     uint32_t bad = 0, more = 0; // per lane partial masks over scenarios
-    for (uint32_t q0 = 0; q0 < Q; q0 += 32) {
-        uint32_t q = q0 + (uint32_t)rd.lane;
-        int s = (int)(q / per);
-        uint32_t u = q - (uint32_t)s * per;
-        bool v;
-        uint64_t K;
-        uint32_t offa, offc, ne, codes;
-        if (NS == 3) { // ScenarioOne is a function of s alone: no need to ask lane s
-            Scen t = scen_one(s, K0);
-            v = t.valid; K = t.K; offa = t.offa; offc = t.offc; ne = t.n_emit; codes = t.codes;
-        } else { // fetch scenario s from lane s (all lanes take part in the shuffles)
-            int src = s < NS ? s : 0;
-            v = __shfl_sync(FULL, (int)sc.valid, src) != 0;
-            K = shfl64(sc.K, src);
-            offa = __shfl_sync(FULL, sc.offa, src);
-            offc = __shfl_sync(FULL, sc.offc, src);
-            ne = __shfl_sync(FULL, sc.n_emit, src);
-            codes = __shfl_sync(FULL, sc.codes, src);
-        }
-        if (q >= Q || !v) continue;
-        if (offa + c > sublen) { // get_score: `if offset + c > seq.len() return 0` (exist/mod.rs:29-31)
-            bad |= 1u << s;
-            continue;
-        }
-        if (u <= c) {
-            // u = 0: get(K) (exist/mod.rs:23); u = 1..c: the c confirmations (:35-43)
-            if (!lookup(rd, sub_push(K, offa, u))) bad |= 1u << s;
-        } else {
-            // one_more (exist/mod.rs:49-70): uses correct()'s bases and offset, tests one k-mer
-            if (sublen > c + offc + 1) {
-                uint64_t km = K0 >> 2;
-                for (int e = (int)ne - 1; e >= 0; e--) km = push(km, (codes >> (2 * e)) & 3u, rd.mask);
-                if (lookup(rd, sub_push(km, offc, c + 1))) more |= 1u << s;
+    const uint32_t valid_mask = __ballot_sync(FULL, sc.valid && rd.lane < NS);
+    // get_score's length test: `if offset + c > seq.len() return 0` (exist/mod.rs:29-31)
+    const uint32_t short_mask = __ballot_sync(FULL, sc.valid && rd.lane < NS && sc.offa + c > sublen);
+    uint32_t cand;
+    if (NS == 3) {
+        // round 3, One: items (s, u), u = 0 .. c+1, all at once (3 * (c + 2) lookups, one round for
+        // the usual confirm values)
+        const uint32_t per = c + 2;
+        const uint32_t Q = (uint32_t)NS * per;
+        for (uint32_t q0 = 0; q0 < Q; q0 += 32) {
+            uint32_t q = q0 + (uint32_t)rd.lane;
+            int s = (int)(q / per);
+            uint32_t u = q - (uint32_t)s * per;
+            Scen t = scen_one(s, K0); // ScenarioOne is a function of s alone: no need to ask lane s
+            if (q >= Q || ((short_mask >> s) & 1u)) continue;
+            if (u <= c) {
+                // u = 0: get(K) (exist/mod.rs:23); u = 1..c: the c confirmations (:35-43)
+                if (!lookup(rd, sub_push(t.K, t.offa, u))) bad |= 1u << s;
+            } else if (sublen > c + t.offc + 1) {
+                // one_more (exist/mod.rs:49-70): uses correct()'s bases and offset, tests one k-mer
+                uint64_t km = push(K0 >> 2, t.codes & 3u, rd.mask);
+                if (lookup(rd, sub_push(km, t.offc, c + 1))) more |= 1u << s;
             }
         }
+        bad = __reduce_or_sync(FULL, bad);
+        more = __reduce_or_sync(FULL, more);
+        cand = valid_mask & ~short_mask & ~bad;
+    } else {
+        // Two: most of the 13 scenarios die on get(K), so the rounds are taken one after the other
+        // and only survivors go on — 13 + 5 * survivors lookups instead of 13 * 7.
+        // round 3a: get(K) of every valid scenario (exist/mod.rs:23), lane s asks for scenario s
+        bool alive = sc.valid && rd.lane < NS && !((short_mask >> rd.lane) & 1u);
+        if (alive) alive = lookup(rd, sc.K);
+        cand = __ballot_sync(FULL, alive);
+        // round 3b: the c confirmations (:35-43) of the survivors, item (r-th survivor, u = 1..c)
+        const uint32_t n_alive = (uint32_t)__popc(cand);
+        const uint32_t Q = n_alive * c;
+        for (uint32_t q0 = 0; q0 < Q; q0 += 32) {
+            const uint32_t q = q0 + (uint32_t)rd.lane;
+            const uint32_t r = q / c, u = q - r * c + 1u;
+            const int s = q < Q ? (int)__fns(cand, 0u, (int)r + 1) : 0;
+            const uint64_t K = shfl64(sc.K, s); // all lanes take part in the shuffles
+            const uint32_t offa = __shfl_sync(FULL, sc.offa, s);
+            if (q < Q && !lookup(rd, sub_push(K, offa, u))) bad |= 1u << s;
+        }
+        cand &= ~__reduce_or_sync(FULL, bad);
+        // round 3c, only on a tie: one_more (exist/mod.rs:49-70) of the tied scenarios
+        if (__popc(cand) > 1) {
+            bool m = false;
+            if ((cand >> rd.lane) & 1u) {
+                if (sublen > c + sc.offc + 1) {
+                    uint64_t km = K0 >> 2;
+                    for (int e = (int)sc.n_emit - 1; e >= 0; e--) km = push(km, (sc.codes >> (2 * e)) & 3u, rd.mask);
+                    m = lookup(rd, sub_push(km, sc.offc, c + 1));
+                }
+            }
+            more = __ballot_sync(FULL, m);
+        }
     }
-    bad = __reduce_or_sync(FULL, bad);
-    more = __reduce_or_sync(FULL, more);
-    uint32_t valid_mask = __ballot_sync(FULL, sc.valid && rd.lane < NS);
-    uint32_t cand = valid_mask & ~bad;
 
     if (cand == 0) return res;                       // exist/mod.rs:132-134
     if (__popc(cand) > 1) {                          // :138-148

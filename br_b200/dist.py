@@ -83,8 +83,9 @@ def _build_from_kmers(ops, k, abundance, abundance_selection):
     ops.barrier()                            # every partition is complete before anyone reads it
     ops.open_peers(handles)
     abundance = _pick_abundance(ops, abundance, abundance_selection, lambda: ops.count_range(b0, b1, None))
-    ops.count_range(b0, b1, abundance)       # count + threshold the owned range (peer loads over NVLink)
-    ops.all_gather_bitfield(b0 << BUCKET_BITS, b1 << BUCKET_BITS, 1 << (2 * k - 1))
+    ops.count_range(b0, b1, abundance)       # count + threshold the owned range (peer data over NVLink)
+    bounds = [tuple(x << BUCKET_BITS for x in bucket_bounds(n_buckets, world, r)) for r in range(world)]
+    ops.all_gather_bitfield(b0 << BUCKET_BITS, b1 << BUCKET_BITS, 1 << (2 * k - 1), bounds)
     ops.barrier()                            # peers are done reading this rank's partition
     return ops.finish(abundance)
 
@@ -99,7 +100,7 @@ def _build_from_tables(ops, k, abundance, abundance_selection):
     ops.merge_slice(handles, begin, end)     # saturating reduce of slice `rank` over NVLink
     abundance = _pick_abundance(ops, abundance, abundance_selection, lambda: ops.spectrum_slice(begin, end))
     ops.threshold_slice(abundance, begin, end)
-    ops.all_gather_bitfield(begin, end, n)   # NCCL all-gather of the bitfield slices
+    ops.all_gather_bitfield(begin, end, n, [slice_bounds(n, world, r) for r in range(world)])  # NCCL all-gather
     ops.barrier()                            # peers are done reading this rank's table
     return ops.finish(abundance)
 
@@ -139,12 +140,21 @@ class GpuOps:
         self.set = Pcon.new(self.ctx, k)
 
     def exchange_kmer_handles(self):
+        """All-gather of: the two CUDA-IPC handles (residues, bucket offsets) and this rank's residue
+        offsets at every rank's bucket boundaries (so that the owner of a bucket range knows which
+        contiguous piece of this rank's residues it needs)."""
         h = (C.c_uint8 * 128)()
         check(lib.brgpu_kmers_ipc_export(self.kmers, h), self.ctx._h)
-        mine = self.torch.tensor(list(h), dtype=self.torch.uint8, device=f"cuda:{self.ctx.device}")
+        n_buckets = lib.brgpu_kmers_buckets(self.kmers)
+        cuts = np.array([bucket_bounds(n_buckets, self.world, r)[0] for r in range(self.world)] + [n_buckets], dtype=np.uint64)
+        offs = np.zeros(cuts.size, dtype=np.uint64)
+        check(lib.brgpu_kmers_offsets_at(self.kmers, cuts.ctypes.data_as(C.c_void_p), cuts.size,
+                                         offs.ctypes.data_as(C.c_void_p)), self.ctx._h)
+        payload = bytes(h) + offs.tobytes()
+        mine = self.torch.frombuffer(bytearray(payload), dtype=self.torch.uint8).to(f"cuda:{self.ctx.device}")
         allh = [self.torch.empty_like(mine) for _ in range(self.world)]
         self.dist.all_gather(allh, mine, group=self.group)
-        return [bytes(t.cpu().tolist()) for t in allh]
+        return [t.cpu().numpy().tobytes() for t in allh]
 
     def _ipc_open_cached(self, handle: bytes):
         """cudaIpcOpenMemHandle costs milliseconds (and so does closing); the library reuses its big
@@ -158,21 +168,27 @@ class GpuOps:
         return p
 
     def open_peers(self, handles):
-        self._peer_res, self._peer_off = [], []
+        self._peer_res, self._peer_off, self._peer_first, self._peer_last = [], [], [], []
         for r, hb in enumerate(handles):
             if r == self.rank:
                 continue
             self._peer_res.append(self._ipc_open_cached(hb[:64]))
-            self._peer_off.append(self._ipc_open_cached(hb[64:]))
+            self._peer_off.append(self._ipc_open_cached(hb[64:128]))
+            cuts = np.frombuffer(hb[128:], dtype=np.uint64)  # peer r's residue offsets at the rank boundaries
+            self._peer_first.append(int(cuts[self.rank]))
+            self._peer_last.append(int(cuts[self.rank + 1]))
 
     def count_range(self, b0, b1, abundance):
         n = len(self._peer_res)
         res = (C.c_void_p * max(1, n))(*[p.value for p in self._peer_res])
         off = (C.c_void_p * max(1, n))(*[p.value for p in self._peer_off])
+        first = (C.c_uint64 * max(1, n))(*self._peer_first)
+        last = (C.c_uint64 * max(1, n))(*self._peer_last)
         hist = np.zeros(256, dtype=np.uint64)
-        check(lib.brgpu_kmers_count_range(self.kmers, res, off, n, b0, b1, -1 if abundance is None else int(abundance),
-                                          None if abundance is None else self.set._h,
-                                          hist.ctypes.data_as(C.c_void_p)), self.ctx._h)
+        check(lib.brgpu_kmers_count_range_staged(self.kmers, res, off, first, last, n, b0, b1,
+                                                 -1 if abundance is None else int(abundance),
+                                                 None if abundance is None else self.set._h,
+                                                 hist.ctypes.data_as(C.c_void_p)), self.ctx._h)
         return hist
 
     def count_local(self, k):
@@ -226,21 +242,24 @@ class GpuOps:
     def threshold_slice(self, abundance, begin, end):
         check(lib.brgpu_set_threshold_slice(self.set._h, self.counter._h, abundance, begin, end), self.ctx._h)
 
-    def all_gather_bitfield(self, begin, end, n_bits):
-        """[begin, end) is this rank's bit range; ranks own consecutive ranges in rank order."""
+    def all_gather_bitfield(self, begin, end, n_bits, bounds=None):
+        """[begin, end) is this rank's bit range; `bounds` lists every rank's range in rank order."""
         n_bytes = lib.brgpu_set_bitfield_bytes(self.set._h)
         ptr = lib.brgpu_set_device_ptr(self.set._h)
         full = self.torch.as_tensor(_CudaArray(ptr, n_bytes), device=f"cuda:{self.ctx.device}")
         per = (end - begin) // 8
         if self.world == 1:
             return
-        mine = self.torch.tensor([begin, end], dtype=self.torch.int64, device=f"cuda:{self.ctx.device}")
-        allb = [self.torch.empty_like(mine) for _ in range(self.world)]
-        self.dist.all_gather(allb, mine, group=self.group)
-        bounds = [tuple(int(x) for x in t.cpu().tolist()) for t in allb]
-        if all((e - b) // 8 == per for b, e in bounds):
-            mine = full[begin // 8 : end // 8].clone()
-            self.dist.all_gather_into_tensor(full, mine, group=self.group)
+        if bounds is None:
+            mine = self.torch.tensor([begin, end], dtype=self.torch.int64, device=f"cuda:{self.ctx.device}")
+            allb = [self.torch.empty_like(mine) for _ in range(self.world)]
+            self.dist.all_gather(allb, mine, group=self.group)
+            bounds = [tuple(int(x) for x in t.cpu().tolist()) for t in allb]
+        # the library's stream produced the slice; NCCL runs on torch's current stream
+        self.ctx.synchronize()
+        if all((e - b) // 8 == per for b, e in bounds) and per * self.world == n_bytes:
+            # in place: rank r's slice already sits at offset r * per of the output
+            self.dist.all_gather_into_tensor(full, full[begin // 8 : end // 8], group=self.group)
         else:  # ragged last slice: broadcast slice by slice
             for r, (b, e) in enumerate(bounds):
                 self.dist.broadcast(full[b // 8 : e // 8], src=self.dist.get_global_rank(self.group, r) if self.group else r,

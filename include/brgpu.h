@@ -184,6 +184,18 @@ int brgpu_kmers_ipc_export(brgpu_kmers *kmers, uint8_t handles_out[128]); /* [0.
 int brgpu_kmers_count_range(brgpu_kmers *kmers, void *const *peer_residues, void *const *peer_offsets, int n_peers,
                             uint64_t bucket_begin, uint64_t bucket_end, int abundance, brgpu_set *set,
                             uint64_t hist_host[256]);
+/* Offsets (in k-mers) at which the given buckets start inside this rank's partition: the rank
+ * that owns bucket range [b0, b1) needs residues [offset(b0), offset(b1)) of every peer.  The host
+ * exchanges these along with the IPC handles. */
+int brgpu_kmers_offsets_at(brgpu_kmers *kmers, const uint64_t *buckets_host, uint64_t n, uint64_t *offsets_host);
+/* brgpu_kmers_count_range with the peers' residues of the range — [peer_first[p], peer_last[p]) of
+ * peer p's residue array, contiguous because buckets are stored in order — first pulled into local
+ * HBM by bulk peer-to-peer copies over NVLink (full-bandwidth transfers instead of ~1 KB remote
+ * loads per bucket and peer), then counted from local memory. */
+int brgpu_kmers_count_range_staged(brgpu_kmers *kmers, void *const *peer_residues, void *const *peer_offsets,
+                                   const uint64_t *peer_first, const uint64_t *peer_last, int n_peers,
+                                   uint64_t bucket_begin, uint64_t bucket_end, int abundance, brgpu_set *set,
+                                   uint64_t hist_host[256]);
 void brgpu_kmers_free(brgpu_kmers *kmers);
 
 /* ------------------------------------------------------------------------------------------

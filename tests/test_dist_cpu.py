@@ -75,11 +75,10 @@ class NumpyOps:
     def threshold_slice(self, abundance, begin, end):
         self.bits[begin // 8 : end // 8] = np.packbits(self.table[begin:end] > abundance, bitorder="little")
 
-    def all_gather_bitfield(self, begin, end, n_bits):
-        mine = torch.tensor([begin, end], dtype=torch.int64)
-        allb = [torch.empty_like(mine) for _ in range(self.world)]
-        self.tdist.all_gather(allb, mine)
-        for r, (b, e) in enumerate(tuple(int(x) for x in t.tolist()) for t in allb):
+    def all_gather_bitfield(self, begin, end, n_bits, bounds=None):
+        assert bounds is not None and tuple(bounds[self.rank]) == (begin, end)
+        assert bounds[0][0] == 0 and bounds[-1][1] == n_bits
+        for r, (b, e) in enumerate(bounds):
             t = torch.from_numpy(self.bits[b // 8 : e // 8].copy())
             self.tdist.broadcast(t, src=r)
             self.bits[b // 8 : e // 8] = t.numpy()
