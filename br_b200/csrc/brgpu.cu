@@ -743,24 +743,31 @@ static int kmers_create(brgpu_ctx *ctx, int k, const brgpu_reads *reads, brgpu_k
     km->n_buckets = table_len(k) >> BUCKET_BITS_HOST;
     km->capacity = L.total_slots ? L.total_slots : 1; // every k-mer starts at a distinct slot position
     km->n_kmers_hint = (double)reads->sum_len;
-    uint32_t *d_fill = nullptr;
-    uint64_t *d_tmp = nullptr;
+    uint32_t *d_fill = nullptr, *d_coarse_kmers = nullptr;
+    uint64_t *d_tmp = nullptr, *d_coarse_base = nullptr;
     cudaError_t e;
+    const bool two_level = bucket_partition_two_level(km->n_buckets) && !getenv("BRGPU_ONE_LEVEL_PARTITION");
     // residues and offsets are cudaMalloc-backed (exportable over CUDA IPC for the multi-GPU path)
     if ((e = big_alloc(ctx, (void **)&km->d_res, km->capacity * 2)) != cudaSuccess ||
         (e = big_alloc(ctx, (void **)&km->d_base, (km->n_buckets + 1) * 8)) != cudaSuccess ||
-        (e = dalloc(ctx, &d_fill, km->n_buckets)) != cudaSuccess ||
-        (e = dalloc(ctx, &d_tmp, km->n_buckets / 4096 + 4)) != cudaSuccess) {
+        (e = dalloc(ctx, &d_fill, km->n_buckets < 1024 ? 1024 : km->n_buckets)) != cudaSuccess ||
+        (e = dalloc(ctx, &d_tmp, km->n_buckets / 4096 + 4)) != cudaSuccess ||
+        (two_level && ((e = dalloc(ctx, &d_coarse_kmers, km->capacity)) != cudaSuccess ||
+                       (e = dalloc(ctx, &d_coarse_base, 1024)) != cudaSuccess))) {
         if (d_fill) dfree(ctx, d_fill);
+        if (d_tmp) dfree(ctx, d_tmp);
+        if (d_coarse_kmers) dfree(ctx, d_coarse_kmers);
         big_free(ctx, km->d_res, km->capacity * 2);
         big_free(ctx, km->d_base, (km->n_buckets + 1) * 8);
         delete km;
         return fail(ctx, BRGPU_E_NOMEM, "device allocation (bucketed k-mers)", e);
     }
     launch_bucket_partition(ctx, L, reads->d_seq, reads->d_len, k, km->n_buckets, d_fill, km->d_base, d_tmp, km->d_res,
-                            km->n_kmers_hint);
+                            d_coarse_kmers, d_coarse_base, km->n_kmers_hint);
     dfree(ctx, d_fill);
     dfree(ctx, d_tmp);
+    if (d_coarse_kmers) dfree(ctx, d_coarse_kmers);
+    if (d_coarse_base) dfree(ctx, d_coarse_base);
     e = cudaGetLastError();
     if (e != cudaSuccess) {
         big_free(ctx, km->d_res, km->capacity * 2);

@@ -143,9 +143,12 @@ void launch_count(brgpu_ctx *ctx, const Layout &L, const uint8_t *d_seq, const u
 void launch_spectrum_threshold(brgpu_ctx *ctx, const uint8_t *d_counts, uint64_t begin, uint64_t end, uint64_t *d_hist,
                                uint8_t *d_bits, int abundance);
 // bucketed counting (see set_kernels.cu)
+// d_coarse_kmers (u32 per k-mer) + d_coarse_base (u64 x 513): scratch of the two-level partition;
+// nullptr (or more than 2^18 buckets) selects the one-level partition.  d_fill: max(n_buckets, 1024) words.
+bool bucket_partition_two_level(uint64_t n_buckets);
 void launch_bucket_partition(brgpu_ctx *ctx, const Layout &L, const uint8_t *d_seq, const uint32_t *d_len, int k,
                              uint64_t n_buckets, uint32_t *d_fill, uint64_t *d_base, uint64_t *d_scan_tmp,
-                             uint16_t *d_residues, double n_kmers);
+                             uint16_t *d_residues, uint32_t *d_coarse_kmers, uint64_t *d_coarse_base, double n_kmers);
 void launch_bucket_count(brgpu_ctx *ctx, const uint16_t *d_residues, const uint64_t *d_base, uint64_t n_buckets,
                          int abundance, uint8_t *d_bits, uint32_t *d_summary, int summary_shift, uint64_t *d_hist,
                          double n_kmers);

@@ -684,10 +684,260 @@ void launch_bucket_count_multi(brgpu_ctx *ctx, const uint16_t *const *d_res, con
         src, b0, b1, abundance, reinterpret_cast<uint32_t *>(d_bits), reinterpret_cast<unsigned long long *>(d_hist));
 }
 
+// ------------------------------------------------------------------------------------------
+// Two-level partition (k <= 17: at most 2^18 buckets).  The one-level scheme above pays one L2
+// atomic per k-mer twice (sizes, then cursors: 138 M `red` + 138 M `atom` on the E. coli config,
+// 0.8 + 1.9 ms) because with 2^18 destinations nothing can be combined inside a block.  Splitting
+// the 18 bucket bits 9 + 9 makes both levels block-local problems:
+//   coarse_hist     per-block shared-memory histogram over the 512 coarse buckets, one global add
+//                   per block and bucket;
+//   coarse_scatter  a block takes a tile of 8192 k-mers, ranks them inside the tile with shared-
+//                   memory atomics, reserves each coarse bucket's run with one global atomic per
+//                   tile and bucket (512 instead of 8192), stages the tile sorted by bucket in
+//                   shared memory and writes it out as contiguous runs (u32: index bits below the
+//                   coarse bits);
+//   fine_partition  one block per coarse bucket (1 MB of k-mers): shared histogram over its 512
+//                   fine buckets, scan, scatter of the 15-bit residues into bucket order — also
+//                   produces the bucket offsets.
+// The output (residues grouped by bucket, bucket offsets) is exactly what bucket_scatter produces,
+// up to the order inside a bucket, which counting does not see.
+// ------------------------------------------------------------------------------------------
+constexpr int CP_THREADS = 256;
+constexpr int CP_MAX_COARSE = 512;
+constexpr int CP_TILE_KMERS = CP_THREADS * 32;
+
+__global__ void __launch_bounds__(CP_THREADS)
+    coarse_hist_kernel(const uint8_t *__restrict__ seq, const uint32_t *__restrict__ len,
+                       const uint64_t *__restrict__ slot_off, const uint32_t *__restrict__ word2read, uint64_t n_words,
+                       int k, int coarse_shift, uint32_t *__restrict__ g_hist) {
+    __shared__ uint32_t sh_cnt[CP_MAX_COARSE];
+    for (int t = threadIdx.x; t < CP_MAX_COARSE; t += CP_THREADS) sh_cnt[t] = 0;
+    __syncthreads();
+    const uint64_t mask = kmask(k);
+    for (uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < n_words;
+         w += (uint64_t)gridDim.x * blockDim.x)
+        for_each_kmer_index8(seq, len, slot_off, word2read, w, k, mask, [&](const uint64_t idx[8], const bool ok[8]) {
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                if (ok[j]) atomicAdd(&sh_cnt[idx[j] >> coarse_shift], 1u);
+        });
+    __syncthreads();
+    for (int t = threadIdx.x; t < CP_MAX_COARSE; t += CP_THREADS)
+        if (sh_cnt[t]) atomicAdd(g_hist + t, sh_cnt[t]);
+}
+
+__global__ void __launch_bounds__(CP_THREADS)
+    coarse_scatter_kernel(const uint8_t *__restrict__ seq, const uint32_t *__restrict__ len,
+                          const uint64_t *__restrict__ slot_off, const uint32_t *__restrict__ word2read,
+                          uint64_t n_words, int k, int coarse_shift, int n_coarse, uint32_t *__restrict__ cursor,
+                          uint32_t *__restrict__ out) {
+    __shared__ uint32_t sh_cnt[CP_MAX_COARSE];
+    __shared__ uint32_t sh_off[CP_MAX_COARSE];
+    __shared__ uint32_t sh_gbase[CP_MAX_COARSE];
+    __shared__ uint64_t sh_scan[32];
+    __shared__ uint32_t stage[CP_TILE_KMERS];
+    const uint64_t mask = kmask(k);
+    const uint32_t rem_mask = (1u << coarse_shift) - 1u;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t n_tiles = (n_words + CP_THREADS - 1) / CP_THREADS;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint64_t w = tile * CP_THREADS + threadIdx.x;
+        for (int t = threadIdx.x; t < CP_MAX_COARSE; t += CP_THREADS) sh_cnt[t] = 0;
+        // this thread's word: 32 positions of one read
+        uint64_t prev = 0, cur = 0;
+        int t_lo = 0, t_hi = 0;
+        if (w < n_words) {
+            const uint32_t r = __ldg(word2read + w);
+            const uint64_t sb = w << 5;
+            const uint32_t p0 = (uint32_t)(sb - __ldg(slot_off + r));
+            const uint32_t L = __ldg(len + r);
+            if (p0 < L && L >= (uint32_t)k) {
+                load_window(seq, sb, p0, prev, cur);
+                t_lo = p0 >= (uint32_t)(k - 1) ? 0 : (k - 1 - (int)p0);
+                t_hi = (L - p0) < 32u ? (int)(L - p0) : 32;
+            }
+        }
+        __syncthreads();
+        // the 32 table indices of this thread, computed once: low words in registers, bit 32 in `hi`
+        // (an index has 2k - 1 <= 33 bits); pass 1: how many k-mers go to every coarse bucket
+        uint32_t lo[32];
+        uint32_t hi = 0, okm = 0;
+#pragma unroll
+        for (int t = 0; t < 32; t++) {
+            const uint64_t idx = canonical_index(window_kmer(prev, cur, t, mask), k);
+            lo[t] = (uint32_t)idx;
+            hi |= (uint32_t)(idx >> 32) << t;
+            if (t >= t_lo && t < t_hi) {
+                okm |= 1u << t;
+                atomicAdd(&sh_cnt[idx >> coarse_shift], 1u);
+            }
+        }
+        __syncthreads();
+        // exclusive scan over the buckets (two per thread) = where each bucket's run starts in the
+        // staging area; one global atomic per bucket reserves the run in the output
+        {
+            const uint32_t a = sh_cnt[2 * threadIdx.x], b = sh_cnt[2 * threadIdx.x + 1];
+            uint64_t total;
+            const uint32_t ex = (uint32_t)block_exclusive_scan((uint64_t)(a + b), &total, sh_scan);
+            sh_off[2 * threadIdx.x] = ex;
+            sh_off[2 * threadIdx.x + 1] = ex + a;
+            if (a) sh_gbase[2 * threadIdx.x] = atomicAdd(cursor + 2 * threadIdx.x, a);
+            if (b) sh_gbase[2 * threadIdx.x + 1] = atomicAdd(cursor + 2 * threadIdx.x + 1, b);
+            sh_cnt[2 * threadIdx.x] = 0;
+            sh_cnt[2 * threadIdx.x + 1] = 0;
+        }
+        __syncthreads();
+        // pass 2: rank inside the bucket's run, stage (8 independent shared atomics in flight)
+#pragma unroll
+        for (int g = 0; g < 32; g += 8) {
+            uint32_t c[8], r[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const uint64_t idx = ((uint64_t)((hi >> (g + j)) & 1u) << 32) | lo[g + j];
+                c[j] = (uint32_t)(idx >> coarse_shift);
+                r[j] = 0;
+                if ((okm >> (g + j)) & 1u) r[j] = atomicAdd(&sh_cnt[c[j]], 1u);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                if ((okm >> (g + j)) & 1u) stage[sh_off[c[j]] + r[j]] = lo[g + j] & rem_mask;
+        }
+        __syncthreads();
+        // write the runs: a warp per bucket, lanes over the run
+        for (int c = warp; c < n_coarse; c += CP_THREADS / 32) {
+            const uint32_t n = sh_cnt[c], o = sh_off[c], g = sh_gbase[c];
+            for (uint32_t e = lane; e < n; e += 32) out[g + e] = stage[o + e];
+        }
+        __syncthreads();
+    }
+}
+
+constexpr int FP_THREADS = 512;
+constexpr int FP_ILP = 8;                         // independent loads in flight per thread
+constexpr int FP_TILE = FP_THREADS * FP_ILP;      // k-mers staged per round (4096)
+
+// One block owns one coarse bucket.  Pass A: histogram over its fine buckets -> bucket offsets.
+// Pass B: tiles of 4096 k-mers are ranked per fine bucket with shared-memory atomics, staged in
+// bucket order and written as runs (a run = the tile's k-mers of one fine bucket, ~8 residues =
+// one 16 B piece of a sector) — scattering the 2-byte residues one by one costs an L2 write
+// transaction per k-mer and was 3x slower.
+__global__ void __launch_bounds__(FP_THREADS)
+    fine_partition_kernel(const uint32_t *__restrict__ coarse_kmers, const uint64_t *__restrict__ coarse_base,
+                          int n_coarse, int fine_bits, uint64_t *__restrict__ base, uint16_t *__restrict__ residues) {
+    __shared__ uint32_t sh_cnt[CP_MAX_COARSE];  // pass A: bucket sizes; pass B: ranks inside the tile
+    __shared__ uint32_t sh_off[CP_MAX_COARSE];  // pass B: start of the bucket's run in the staging area
+    __shared__ uint32_t sh_cur[CP_MAX_COARSE];  // k-mers of the bucket already written (relative to begin)
+    __shared__ uint64_t sh_scan[32];
+    __shared__ uint16_t stage[FP_TILE];
+    const int n_fine = 1 << fine_bits;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int c = blockIdx.x; c < n_coarse; c += gridDim.x) {
+        const uint64_t begin = __ldg(coarse_base + c), end = __ldg(coarse_base + c + 1);
+        for (int t = threadIdx.x; t < CP_MAX_COARSE; t += FP_THREADS) sh_cnt[t] = 0;
+        __syncthreads();
+        for (uint64_t e0 = begin; e0 < end; e0 += FP_TILE) {
+            uint32_t v[FP_ILP];
+#pragma unroll
+            for (int u = 0; u < FP_ILP; u++) {
+                const uint64_t e = e0 + (uint64_t)u * FP_THREADS + threadIdx.x;
+                v[u] = e < end ? __ldg(coarse_kmers + e) : 0xffffffffu;
+            }
+#pragma unroll
+            for (int u = 0; u < FP_ILP; u++)
+                if (v[u] != 0xffffffffu) atomicAdd(&sh_cnt[v[u] >> BUCKET_BITS], 1u);
+        }
+        __syncthreads();
+        {
+            const uint32_t a = threadIdx.x < (unsigned)n_fine ? sh_cnt[threadIdx.x] : 0u;
+            uint64_t total;
+            const uint32_t ex = (uint32_t)block_exclusive_scan((uint64_t)a, &total, sh_scan);
+            if (threadIdx.x < (unsigned)n_fine) {
+                sh_cur[threadIdx.x] = ex;
+                base[(uint64_t)c * n_fine + threadIdx.x] = begin + ex;
+            }
+            if (c == n_coarse - 1 && threadIdx.x == 0) base[(uint64_t)n_coarse * n_fine] = end;
+        }
+        for (uint64_t e0 = begin; e0 < end; e0 += FP_TILE) {
+            if (threadIdx.x < CP_MAX_COARSE) sh_cnt[threadIdx.x] = 0;
+            uint32_t v[FP_ILP], r[FP_ILP];
+#pragma unroll
+            for (int u = 0; u < FP_ILP; u++) {
+                const uint64_t e = e0 + (uint64_t)u * FP_THREADS + threadIdx.x;
+                v[u] = e < end ? __ldcs(coarse_kmers + e) : 0xffffffffu; // second and last read
+            }
+            __syncthreads(); // counters zeroed (and sh_cur of the previous tile updated)
+#pragma unroll
+            for (int u = 0; u < FP_ILP; u++) {
+                r[u] = 0;
+                if (v[u] != 0xffffffffu) r[u] = atomicAdd(&sh_cnt[v[u] >> BUCKET_BITS], 1u);
+            }
+            __syncthreads();
+            {
+                const uint32_t a = threadIdx.x < (unsigned)n_fine ? sh_cnt[threadIdx.x] : 0u;
+                uint64_t total;
+                const uint32_t ex = (uint32_t)block_exclusive_scan((uint64_t)a, &total, sh_scan);
+                if (threadIdx.x < (unsigned)n_fine) sh_off[threadIdx.x] = ex;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int u = 0; u < FP_ILP; u++)
+                if (v[u] != 0xffffffffu) stage[sh_off[v[u] >> BUCKET_BITS] + r[u]] = (uint16_t)(v[u] & (BUCKET_COUNTERS - 1));
+            __syncthreads();
+            // runs: half a warp per bucket, 16 buckets x 2 per warp round
+            for (int f = warp * 2 + (lane >> 4); f < n_fine; f += (FP_THREADS / 32) * 2) {
+                const uint32_t n = sh_cnt[f], o = sh_off[f];
+                const uint64_t g = begin + sh_cur[f];
+                for (uint32_t e = lane & 15; e < n; e += 16) residues[g + e] = stage[o + e];
+            }
+            __syncthreads();
+            if (threadIdx.x < (unsigned)n_fine) sh_cur[threadIdx.x] += sh_cnt[threadIdx.x];
+        }
+        __syncthreads();
+    }
+}
+
+bool bucket_partition_two_level(uint64_t n_buckets) { return n_buckets >= 4 && n_buckets <= (uint64_t)CP_MAX_COARSE * CP_MAX_COARSE; }
+
 void launch_bucket_partition(brgpu_ctx *ctx, const Layout &L, const uint8_t *d_seq, const uint32_t *d_len, int k,
                              uint64_t n_buckets, uint32_t *d_fill, uint64_t *d_base, uint64_t *d_scan_tmp,
-                             uint16_t *d_residues, double n_kmers) {
+                             uint16_t *d_residues, uint32_t *d_coarse_kmers, uint64_t *d_coarse_base, double n_kmers) {
     uint64_t n_words = L.total_slots >> 5;
+    if (d_coarse_kmers && bucket_partition_two_level(n_buckets)) {
+        int nb_bits = 0;
+        while ((1ULL << nb_bits) < n_buckets) nb_bits++;
+        const int coarse_bits = (nb_bits + 1) / 2, fine_bits = nb_bits - coarse_bits;
+        const int n_coarse = 1 << coarse_bits;
+        const int coarse_shift = fine_bits + BUCKET_BITS;
+        uint32_t *d_hist = d_fill, *d_cursor = d_fill + CP_MAX_COARSE; // d_fill holds n_buckets >= 2 * 512 words... or fewer
+        cudaMemsetAsync(d_fill, 0, 2 * CP_MAX_COARSE * sizeof(uint32_t), ctx->stream);
+        {
+            ProfScope ps(ctx, "coarse_hist", n_kmers * 1.0); // ASCII stream in
+            coarse_hist_kernel<<<grid_for(ctx, n_words, CP_THREADS, 8), CP_THREADS, 0, ctx->stream>>>(
+                d_seq, d_len, L.d_slot_off, L.d_word2read, n_words, k, coarse_shift, d_hist);
+        }
+        launch_exclusive_scan_u32(ctx, d_hist, (uint64_t)n_coarse, d_coarse_base, d_scan_tmp);
+        {
+            ProfScope ps(ctx, "coarse_scatter", n_kmers * 5.0); // ASCII in + 4 B out
+            bucket_cursor_kernel<<<1, 512, 0, ctx->stream>>>(d_coarse_base, (uint64_t)n_coarse, d_cursor);
+            const uint64_t n_tiles = (n_words + CP_THREADS - 1) / CP_THREADS;
+            int per_sm = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, coarse_scatter_kernel, CP_THREADS, 0) != cudaSuccess ||
+                per_sm < 1) {
+                cudaGetLastError();
+                per_sm = 1;
+            }
+            const uint64_t cap = (uint64_t)ctx->sm_count * (uint64_t)per_sm;
+            coarse_scatter_kernel<<<(unsigned)(n_tiles < cap ? n_tiles : cap), CP_THREADS, 0, ctx->stream>>>(
+                d_seq, d_len, L.d_slot_off, L.d_word2read, n_words, k, coarse_shift, n_coarse, d_cursor, d_coarse_kmers);
+            ctx->launches += 1;
+        }
+        {
+            ProfScope ps(ctx, "fine_partition", n_kmers * 6.0); // 4 B in + 2 B out
+            fine_partition_kernel<<<n_coarse, FP_THREADS, 0, ctx->stream>>>(d_coarse_kmers, d_coarse_base, n_coarse, fine_bits,
+                                                                            d_base, d_residues);
+        }
+        return;
+    }
     cudaMemsetAsync(d_fill, 0, n_buckets * sizeof(uint32_t), ctx->stream);
     {
         ProfScope ps(ctx, "bucket_hist", n_kmers * 1.0); // ASCII stream in; the bucket counters stay in L2

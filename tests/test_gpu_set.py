@@ -175,12 +175,17 @@ def test_k17_count_and_threshold_against_oracle(gpu, oracle):
     assert np.array_equal(s.get_batch(km), oracle.Solid.from_bitfield(17, ob).get_batch(km))
 
 
+@pytest.mark.parametrize("one_level", [False, True])
 @pytest.mark.parametrize("k", [15, 17])
-def test_bucketed_and_table_counting_paths_agree(gpu, oracle, k):
-    """Pcon.from_reads takes the bucketed (L2-resident) counting path for k = 15/17, Counter the
-    literal table path; both must give the oracle's spectrum and bitfield, including saturated
-    counters (poly-A), any-byte nucleotides and the data-derived first-minimum threshold."""
+def test_bucketed_and_table_counting_paths_agree(gpu, oracle, k, one_level, monkeypatch):
+    """Pcon.from_reads takes the bucketed counting path for k = 15/17 (two-level shared-memory
+    partition, or the one-level partition with L2 atomics that k = 19 uses), Counter the literal
+    table path; all must give the oracle's spectrum and bitfield, including saturated counters
+    (poly-A: every k-mer of a tile in one bucket), any-byte nucleotides and the data-derived
+    first-minimum threshold."""
     br, ctx = gpu
+    if one_level:
+        monkeypatch.setenv("BRGPU_ONE_LEVEL_PARTITION", "1")
     from br_b200 import synth
 
     genome = synth.make_genome(150_000, seed=7)
