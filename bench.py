@@ -403,6 +403,17 @@ def run_ours(args, world, rank, local_rank):
                          "algo_bytes_per_launch": ab, "achieved_gbs": round(gbs, 1), "frac_of_hbm": round(gbs / peak, 4)}
     dominant = max(prof, key=lambda k_: prof[k_]["ms"])
     dk = kernels[dominant]
+    # DRAM traffic per launch from the committed `ncu --set full` capture (profiles/summarize.py)
+    traffic, traffic_src = None, None
+    tp = ROOT / "profiles" / "traffic.json"
+    if tp.exists():
+        tj = json.loads(tp.read_text())
+        traffic_src = tj.get("source")
+        for name, kk in kernels.items():
+            if name in tj["kernels"]:
+                kk["dram_bytes_per_launch_ncu"] = tj["kernels"][name]["dram_bytes_per_launch"]
+        if dominant in tj["kernels"]:
+            traffic = tj["kernels"][dominant]["dram_bytes_per_launch"]
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -421,7 +432,8 @@ def run_ours(args, world, rank, local_rank):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"kernel": dominant, "bound": "hbm", "achieved": dk["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                     "frac": dk["frac_of_hbm"], "traffic": None, "peak_source": peak_src,
+                     "frac": dk["frac_of_hbm"], "traffic": traffic, "traffic_source": traffic_src,
+                     "algorithmic_bytes_per_launch": dk["algo_bytes_per_launch"], "peak_source": peak_src,
                      "scan_lookups_per_step": lookups},
         "kernels": kernels,
         "ms_per_step_with_kernel_events": ms_prof / args.steps,

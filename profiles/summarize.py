@@ -64,3 +64,42 @@ if rep.exists():
                 if m in idx and d[idx[m]] not in ("", "n/a"):
                     f.write(f"  {m:78s} {d[idx[m]]:>18s} {units[idx[m]]}\n")
     print("wrote", out_dir / f"ncu_{tag}.txt")
+
+    # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) under bench.py's kernel
+    # names -> profiles/traffic.json, which bench.py reports as roofline.traffic
+    import json
+    import re
+
+    def bench_name(kernel):
+        m = re.match(r"(?:void )?(?:brgpu::)?(\w+?)(?:_kernel)?(?:<(?:\(int\))?(\d)>)?$", kernel.strip())
+        if not m:
+            return kernel
+        base, meth = m.group(1), m.group(2)
+        methods = ["one", "two", "graph", "greedy", "gap_size"]
+        if base == "scan_spec" and meth is not None:
+            return "scan_" + methods[int(meth)]
+        if base == "scan_merge" and meth is not None:
+            return "merge_" + methods[int(meth)]
+        return base
+
+    def to_bytes(val, unit):
+        v = float(val.replace(",", ""))
+        return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}.get(unit, 1)
+
+    acc = collections.OrderedDict()
+    for d in data:
+        name = bench_name(d[idx["Kernel Name"]].split("(")[0])
+        rd = to_bytes(d[idx["dram__bytes_read.sum"]], units[idx["dram__bytes_read.sum"]])
+        wr = to_bytes(d[idx["dram__bytes_write.sum"]], units[idx["dram__bytes_write.sum"]])
+        ms = float(d[idx["gpu__time_duration.sum"]].replace(",", "")) * {"us": 1e-3, "ms": 1.0, "ns": 1e-6, "s": 1e3}.get(
+            units[idx["gpu__time_duration.sum"]], 1.0)
+        a = acc.setdefault(name, {"launches": 0, "dram_bytes": 0.0, "ms": 0.0})
+        a["launches"] += 1
+        a["dram_bytes"] += rd + wr
+        a["ms"] += ms
+    traffic = {"source": f"ncu --set full --clock-control none ({rep.name}); mean over the captured launches of one step",
+               "kernels": {n: {"dram_bytes_per_launch": round(a["dram_bytes"] / a["launches"]),
+                               "launches_captured": a["launches"], "ms_per_launch_under_ncu": round(a["ms"] / a["launches"], 4)}
+                           for n, a in acc.items()}}
+    (out_dir / "traffic.json").write_text(json.dumps(traffic, indent=1) + "\n")
+    print("wrote", out_dir / "traffic.json")
