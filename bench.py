@@ -224,6 +224,9 @@ def run_ours(args, world, rank, local_rank):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; br_b200 has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    from br_b200.runtime import bind_to_gpu_numa_node
+
+    numa_node = bind_to_gpu_numa_node(local_rank) if world > 1 else None  # before any pinned allocation
     tdist = None
     if world > 1:
         import torch.distributed as tdist
@@ -421,7 +424,7 @@ def run_ours(args, world, rank, local_rank):
         "config": {"workload": workload_name(world, args.genome_per_gpu), "reads_per_gpu": n_reads,
                    "bases_per_gpu": n_bases, "kmers_per_gpu": n_kmers,
                    "l2": "inputs larger than L2 (8 GiB count table, 1 GiB bitfield, >=138 MB reads per GPU); no flush",
-                   "parallelism": f"reads sharded over {world} GPU(s)"},
+                   "parallelism": f"reads sharded over {world} GPU(s)", "rank0_numa_node": numa_node},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                 "warmup_ms_per_step": [round(x, 2) for x in e2e_warm_ms],
                 "host_clock_ms_per_step": e2e_step_ms, "lanes": len(lanes),
@@ -460,10 +463,15 @@ def main():
     ap.add_argument("--genome-per-gpu", type=int, default=GENOME_PER_GPU,
                     help="genome bases per GPU (default: the 4.6 Mb of BASELINE.json configs[1]); smaller values are "
                          "for smoke runs only and are not the benchmark")
+    ap.add_argument("--methods", nargs="+", default=None,
+                    help="method chain (default: one two = BASELINE.json configs[1]; `graph greedy gap_size` = configs[2])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e-pipeline", action="store_true", help="e2e steps one at a time on a single context")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
+    if args.methods:
+        global METHODS
+        METHODS = [m.replace("-", "_") for m in args.methods]
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

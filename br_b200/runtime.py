@@ -35,6 +35,45 @@ def as_offsets(offsets):
     return np.ascontiguousarray(offsets, dtype=np.uint64)
 
 
+def bind_to_gpu_numa_node(device=0):
+    """Pin this process to the CPUs of the NUMA node the GPU hangs off, so that the pinned host
+    buffers it allocates afterwards (first touch) and its PCIe copies stay on that socket.  With
+    one process per GPU this keeps 8 ranks from pushing their uploads and downloads across the
+    inter-socket link.  Returns the node id, or None when the topology is not visible (containers
+    often hide it); never raises."""
+    import os
+
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        try:
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            index = int(vis.split(",")[device]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else device
+            bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        finally:
+            pynvml.nvmlShutdown()
+        if isinstance(bus, bytes):
+            bus = bus.decode()
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:  # NVML prints an 8-digit domain, sysfs a 4-digit one
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:  # noqa: BLE001 - topology probing is best effort by design
+        return None
+
+
 class Context:
     """One per process per GPU.  `stream` may be a torch.cuda.Stream (or a raw cudaStream_t
     integer) so that torch events and the library's kernels share one stream."""
