@@ -30,11 +30,14 @@ namespace brgpu {
 // ------------------------------------------------------------------------------------------
 // phase A
 // ------------------------------------------------------------------------------------------
+// KT: compile-time k (0 = take it from the set).  k = 17 is the size every BASELINE config uses;
+// with a constant k the 64-bit shifts and masks of the k-mer arithmetic become immediates.
+template <int KT>
 __global__ void __launch_bounds__(256)
     solid_bitmap_kernel(const uint8_t *__restrict__ seq, const uint32_t *__restrict__ len,
                         const uint64_t *__restrict__ slot_off, const uint32_t *__restrict__ word2read,
                         uint64_t n_words, SolidView set, uint32_t *__restrict__ bitmap) {
-    const int k = set.k;
+    const int k = KT ? KT : set.k;
     const uint8_t *__restrict__ bits = set.bits;
     const uint64_t mask = kmask(k);
     for (uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < n_words;
@@ -112,8 +115,12 @@ void launch_solid_bitmap(brgpu_ctx *ctx, const Layout &L, const uint8_t *d_seq, 
     ProfScope ps(ctx, "solid_bitmap", n_bases_hint * 33.125);
     uint64_t need = (n_words + 255) / 256;
     uint64_t capb = (uint64_t)ctx->sm_count * 8;
-    solid_bitmap_kernel<<<(unsigned)(need < capb ? need : capb), 256, 0, ctx->stream>>>(
-        d_seq, d_len, L.d_slot_off, L.d_word2read, n_words, SolidView{set.bits, set.summary, set.shift, set.k, (const uint2 *)set.dir, set.blocks}, d_bitmap);
+    const SolidView sv{set.bits, set.summary, set.shift, set.k, (const uint2 *)set.dir, set.blocks};
+    const unsigned grid = (unsigned)(need < capb ? need : capb);
+    if (set.k == 17)
+        solid_bitmap_kernel<17><<<grid, 256, 0, ctx->stream>>>(d_seq, d_len, L.d_slot_off, L.d_word2read, n_words, sv, d_bitmap);
+    else
+        solid_bitmap_kernel<0><<<grid, 256, 0, ctx->stream>>>(d_seq, d_len, L.d_slot_off, L.d_word2read, n_words, sv, d_bitmap);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1225,7 +1232,7 @@ __global__ void seg_count_kernel(const uint32_t *__restrict__ len, uint32_t n_re
         n_seg[r] = seg_count(len[r], k);
 }
 
-template <int METHOD>
+template <int METHOD, int KT>
 __global__ void __launch_bounds__(SCAN_WARPS_PER_BLOCK * 32, (METHOD == BRGPU_ONE || METHOD == BRGPU_TWO) ? 12 : 1)
     scan_spec_kernel(const uint8_t *__restrict__ in, const uint32_t *__restrict__ len_in,
                      const uint64_t *__restrict__ slot_off, const uint32_t *__restrict__ bitmap,
@@ -1235,7 +1242,9 @@ __global__ void __launch_bounds__(SCAN_WARPS_PER_BLOCK * 32, (METHOD == BRGPU_ON
     const int lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     Rd rd;
+    if (KT) p.k = KT; // compile-time k: the k-mer arithmetic below folds to immediates
     rd.set = set;
+    rd.set.k = p.k;
     rd.k = p.k;
     rd.mask = kmask(p.k);
     rd.lane = lane;
@@ -1289,7 +1298,7 @@ __global__ void __launch_bounds__(SCAN_WARPS_PER_BLOCK * 32, (METHOD == BRGPU_ON
     if (lane == 0 && gets) atomicAdd(reinterpret_cast<unsigned long long *>(flags + 2), (unsigned long long)gets);
 }
 
-template <int METHOD>
+template <int METHOD, int KT>
 __global__ void __launch_bounds__(SCAN_WARPS_PER_BLOCK * 32)
     scan_merge_kernel(const uint8_t *__restrict__ in, const uint32_t *__restrict__ len_in, uint8_t *__restrict__ out,
                       uint32_t *__restrict__ len_out, const uint64_t *__restrict__ slot_off,
@@ -1299,9 +1308,11 @@ __global__ void __launch_bounds__(SCAN_WARPS_PER_BLOCK * 32)
                       uint8_t *scratch, size_t scratch_per_warp) {
     const int lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (KT) p.k = KT; // compile-time k: the k-mer arithmetic below folds to immediates
     const uint32_t k = (uint32_t)p.k;
     Rd rd;
     rd.set = set;
+    rd.set.k = p.k;
     rd.k = p.k;
     rd.mask = kmask(p.k);
     rd.lane = lane;
@@ -1392,7 +1403,7 @@ uint64_t scan_max_segments(const Layout &L) { return L.total_slots / SEG + L.n +
 size_t scan_seg_out_bytes(const Layout &L) { return (size_t)scan_max_segments(L) * SEG_CAP; }
 size_t scan_seg_rec_bytes(const Layout &L) { return (size_t)scan_max_segments(L) * sizeof(SegRec); }
 
-template <int M>
+template <int M, int KT>
 static void launch_scan_method(brgpu_ctx *ctx, const Layout &L, const uint8_t *d_in, const uint32_t *d_len_in,
                                uint8_t *d_out, uint32_t *d_len_out, const uint32_t *d_bitmap, const SolidView &sv,
                                const CorrectParams &p, uint8_t *d_scratch, size_t scratch_per_warp, int n_warps_total,
@@ -1406,14 +1417,14 @@ static void launch_scan_method(brgpu_ctx *ctx, const Layout &L, const uint8_t *d
     };
     {
         ProfScope ps(ctx, spec_name, n_bases_hint * 2.0);
-        scan_spec_kernel<M><<<grid_for_warps((uint64_t)occupancy_warps(ctx, scan_spec_kernel<M>), scan_max_segments(L)),
+        scan_spec_kernel<M, KT><<<grid_for_warps((uint64_t)occupancy_warps(ctx, scan_spec_kernel<M, KT>), scan_max_segments(L)),
                               threads, 0, ctx->stream>>>(d_in, d_len_in, L.d_slot_off, d_bitmap, w.d_seg_first,
                                                          (uint32_t)L.n, w.d_seg_out, (SegRec *)w.d_seg_recs,
                                                          ctx->d_flags, sv, p, d_scratch, scratch_per_warp);
     }
     {
         ProfScope ps(ctx, merge_name, n_bases_hint * 2.0);
-        scan_merge_kernel<M><<<grid_for_warps((uint64_t)occupancy_warps(ctx, scan_merge_kernel<M>), L.n), threads, 0,
+        scan_merge_kernel<M, KT><<<grid_for_warps((uint64_t)occupancy_warps(ctx, scan_merge_kernel<M, KT>), L.n), threads, 0,
                                ctx->stream>>>(d_in, d_len_in, d_out, d_len_out, L.d_slot_off, d_bitmap, L.d_order,
                                               w.d_seg_first, (uint32_t)L.n, w.d_seg_out, (const SegRec *)w.d_seg_recs,
                                               ctx->d_flags, sv, p, d_scratch, scratch_per_warp);
@@ -1440,8 +1451,14 @@ void launch_scan(brgpu_ctx *ctx, const Layout &L, const uint8_t *d_in, const uin
     static const char *spec_names[5] = {"scan_one", "scan_two", "scan_graph", "scan_greedy", "scan_gap_size"};
     static const char *merge_names[5] = {"merge_one", "merge_two", "merge_graph", "merge_greedy", "merge_gap_size"};
 #define BRGPU_LAUNCH_SCAN(M)                                                                                           \
-    launch_scan_method<M>(ctx, L, d_in, d_len_in, d_out, d_len_out, d_bitmap, sv, p, d_scratch, scratch_per_warp,      \
-                          n_warps_total, w, n_bases_hint, spec_names[M], merge_names[M])
+    do {                                                                                                               \
+        if (p.k == 17)                                                                                                 \
+            launch_scan_method<M, 17>(ctx, L, d_in, d_len_in, d_out, d_len_out, d_bitmap, sv, p, d_scratch,           \
+                                      scratch_per_warp, n_warps_total, w, n_bases_hint, spec_names[M], merge_names[M]); \
+        else                                                                                                           \
+            launch_scan_method<M, 0>(ctx, L, d_in, d_len_in, d_out, d_len_out, d_bitmap, sv, p, d_scratch,            \
+                                     scratch_per_warp, n_warps_total, w, n_bases_hint, spec_names[M], merge_names[M]);  \
+    } while (0)
     switch (p.method) {
     case BRGPU_ONE: BRGPU_LAUNCH_SCAN(BRGPU_ONE); break;
     case BRGPU_TWO: BRGPU_LAUNCH_SCAN(BRGPU_TWO); break;

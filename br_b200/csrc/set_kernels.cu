@@ -706,10 +706,15 @@ constexpr int CP_THREADS = 256;
 constexpr int CP_MAX_COARSE = 512;
 constexpr int CP_TILE_KMERS = CP_THREADS * 32;
 
+// KT: compile-time k (0 = runtime): with k = 17 (every BASELINE config) the shifts and masks of the
+// k-mer arithmetic are immediates
+template <int KT>
 __global__ void __launch_bounds__(CP_THREADS)
     coarse_hist_kernel(const uint8_t *__restrict__ seq, const uint32_t *__restrict__ len,
                        const uint64_t *__restrict__ slot_off, const uint32_t *__restrict__ word2read, uint64_t n_words,
-                       int k, int coarse_shift, uint32_t *__restrict__ g_hist) {
+                       int k_, int coarse_shift_, uint32_t *__restrict__ g_hist) {
+    const int k = KT ? KT : k_;
+    const int coarse_shift = KT == 17 ? 24 : coarse_shift_;
     __shared__ uint32_t sh_cnt[CP_MAX_COARSE];
     for (int t = threadIdx.x; t < CP_MAX_COARSE; t += CP_THREADS) sh_cnt[t] = 0;
     __syncthreads();
@@ -726,11 +731,14 @@ __global__ void __launch_bounds__(CP_THREADS)
         if (sh_cnt[t]) atomicAdd(g_hist + t, sh_cnt[t]);
 }
 
+template <int KT>
 __global__ void __launch_bounds__(CP_THREADS)
     coarse_scatter_kernel(const uint8_t *__restrict__ seq, const uint32_t *__restrict__ len,
                           const uint64_t *__restrict__ slot_off, const uint32_t *__restrict__ word2read,
-                          uint64_t n_words, int k, int coarse_shift, int n_coarse, uint32_t *__restrict__ cursor,
+                          uint64_t n_words, int k_, int coarse_shift_, int n_coarse, uint32_t *__restrict__ cursor,
                           uint32_t *__restrict__ out) {
+    const int k = KT ? KT : k_;
+    const int coarse_shift = KT == 17 ? 24 : coarse_shift_; // k = 17: 18 bucket bits split 9 + 9, 9 + 15 below
     __shared__ uint32_t sh_cnt[CP_MAX_COARSE];
     __shared__ uint32_t sh_off[CP_MAX_COARSE];
     __shared__ uint32_t sh_gbase[CP_MAX_COARSE];
@@ -912,8 +920,12 @@ void launch_bucket_partition(brgpu_ctx *ctx, const Layout &L, const uint8_t *d_s
         cudaMemsetAsync(d_fill, 0, 2 * CP_MAX_COARSE * sizeof(uint32_t), ctx->stream);
         {
             ProfScope ps(ctx, "coarse_hist", n_kmers * 1.0); // ASCII stream in
-            coarse_hist_kernel<<<grid_for(ctx, n_words, CP_THREADS, 8), CP_THREADS, 0, ctx->stream>>>(
-                d_seq, d_len, L.d_slot_off, L.d_word2read, n_words, k, coarse_shift, d_hist);
+            if (k == 17)
+                coarse_hist_kernel<17><<<grid_for(ctx, n_words, CP_THREADS, 8), CP_THREADS, 0, ctx->stream>>>(
+                    d_seq, d_len, L.d_slot_off, L.d_word2read, n_words, k, coarse_shift, d_hist);
+            else
+                coarse_hist_kernel<0><<<grid_for(ctx, n_words, CP_THREADS, 8), CP_THREADS, 0, ctx->stream>>>(
+                    d_seq, d_len, L.d_slot_off, L.d_word2read, n_words, k, coarse_shift, d_hist);
         }
         launch_exclusive_scan_u32(ctx, d_hist, (uint64_t)n_coarse, d_coarse_base, d_scan_tmp);
         {
@@ -921,14 +933,19 @@ void launch_bucket_partition(brgpu_ctx *ctx, const Layout &L, const uint8_t *d_s
             bucket_cursor_kernel<<<1, 512, 0, ctx->stream>>>(d_coarse_base, (uint64_t)n_coarse, d_cursor);
             const uint64_t n_tiles = (n_words + CP_THREADS - 1) / CP_THREADS;
             int per_sm = 0;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, coarse_scatter_kernel, CP_THREADS, 0) != cudaSuccess ||
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, coarse_scatter_kernel<17>, CP_THREADS, 0) != cudaSuccess ||
                 per_sm < 1) {
                 cudaGetLastError();
                 per_sm = 1;
             }
             const uint64_t cap = (uint64_t)ctx->sm_count * (uint64_t)per_sm;
-            coarse_scatter_kernel<<<(unsigned)(n_tiles < cap ? n_tiles : cap), CP_THREADS, 0, ctx->stream>>>(
-                d_seq, d_len, L.d_slot_off, L.d_word2read, n_words, k, coarse_shift, n_coarse, d_cursor, d_coarse_kmers);
+            const unsigned grid = (unsigned)(n_tiles < cap ? n_tiles : cap);
+            if (k == 17)
+                coarse_scatter_kernel<17><<<grid, CP_THREADS, 0, ctx->stream>>>(d_seq, d_len, L.d_slot_off, L.d_word2read, n_words,
+                                                                                k, coarse_shift, n_coarse, d_cursor, d_coarse_kmers);
+            else
+                coarse_scatter_kernel<0><<<grid, CP_THREADS, 0, ctx->stream>>>(d_seq, d_len, L.d_slot_off, L.d_word2read, n_words,
+                                                                               k, coarse_shift, n_coarse, d_cursor, d_coarse_kmers);
             ctx->launches += 1;
         }
         {
