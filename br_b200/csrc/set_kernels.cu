@@ -743,10 +743,11 @@ __global__ void __launch_bounds__(CP_THREADS)
     __shared__ uint32_t sh_off[CP_MAX_COARSE];
     __shared__ uint32_t sh_gbase[CP_MAX_COARSE];
     __shared__ uint64_t sh_scan[32];
-    __shared__ uint32_t stage[CP_TILE_KMERS];
+    __shared__ uint32_t sh_total;
+    extern __shared__ uint32_t stage[];                 // CP_TILE_KMERS values, then CP_TILE_KMERS destinations
+    uint32_t *stage_dst = stage + CP_TILE_KMERS;
     const uint64_t mask = kmask(k);
     const uint32_t rem_mask = (1u << coarse_shift) - 1u;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint64_t n_tiles = (n_words + CP_THREADS - 1) / CP_THREADS;
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const uint64_t w = tile * CP_THREADS + threadIdx.x;
@@ -787,6 +788,7 @@ __global__ void __launch_bounds__(CP_THREADS)
             const uint32_t a = sh_cnt[2 * threadIdx.x], b = sh_cnt[2 * threadIdx.x + 1];
             uint64_t total;
             const uint32_t ex = (uint32_t)block_exclusive_scan((uint64_t)(a + b), &total, sh_scan);
+            if (threadIdx.x == 0) sh_total = (uint32_t)total;
             sh_off[2 * threadIdx.x] = ex;
             sh_off[2 * threadIdx.x + 1] = ex + a;
             if (a) sh_gbase[2 * threadIdx.x] = atomicAdd(cursor + 2 * threadIdx.x, a);
@@ -808,14 +810,16 @@ __global__ void __launch_bounds__(CP_THREADS)
             }
 #pragma unroll
             for (int j = 0; j < 8; j++)
-                if ((okm >> (g + j)) & 1u) stage[sh_off[c[j]] + r[j]] = lo[g + j] & rem_mask;
+                if ((okm >> (g + j)) & 1u) {
+                    const uint32_t p = sh_off[c[j]] + r[j];
+                    stage[p] = lo[g + j] & rem_mask;
+                    stage_dst[p] = sh_gbase[c[j]] + r[j];
+                }
         }
         __syncthreads();
-        // write the runs: a warp per bucket, lanes over the run
-        for (int c = warp; c < n_coarse; c += CP_THREADS / 32) {
-            const uint32_t n = sh_cnt[c], o = sh_off[c], g = sh_gbase[c];
-            for (uint32_t e = lane; e < n; e += 32) out[g + e] = stage[o + e];
-        }
+        // write-out: staged position j goes to stage_dst[j]; neighbours in a bucket's run are
+        // neighbours in the output, so the stores of a warp fall into a few 64 B runs
+        for (uint32_t j = threadIdx.x; j < sh_total; j += CP_THREADS) out[stage_dst[j]] = stage[j];
         __syncthreads();
     }
 }
@@ -837,8 +841,9 @@ __global__ void __launch_bounds__(FP_THREADS)
     __shared__ uint32_t sh_cur[CP_MAX_COARSE];  // k-mers of the bucket already written (relative to begin)
     __shared__ uint64_t sh_scan[32];
     __shared__ uint16_t stage[FP_TILE];
+    __shared__ uint32_t stage_dst[FP_TILE];      // destination (relative to `begin`) of every staged residue
+    __shared__ uint32_t sh_total;
     const int n_fine = 1 << fine_bits;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int c = blockIdx.x; c < n_coarse; c += gridDim.x) {
         const uint64_t begin = __ldg(coarse_base + c), end = __ldg(coarse_base + c + 1);
         for (int t = threadIdx.x; t < CP_MAX_COARSE; t += FP_THREADS) sh_cnt[t] = 0;
@@ -885,18 +890,20 @@ __global__ void __launch_bounds__(FP_THREADS)
                 uint64_t total;
                 const uint32_t ex = (uint32_t)block_exclusive_scan((uint64_t)a, &total, sh_scan);
                 if (threadIdx.x < (unsigned)n_fine) sh_off[threadIdx.x] = ex;
+                if (threadIdx.x == 0) sh_total = (uint32_t)total;
             }
             __syncthreads();
 #pragma unroll
             for (int u = 0; u < FP_ILP; u++)
-                if (v[u] != 0xffffffffu) stage[sh_off[v[u] >> BUCKET_BITS] + r[u]] = (uint16_t)(v[u] & (BUCKET_COUNTERS - 1));
+                if (v[u] != 0xffffffffu) {
+                    const uint32_t f = v[u] >> BUCKET_BITS;
+                    const uint32_t p = sh_off[f] + r[u];
+                    stage[p] = (uint16_t)(v[u] & (BUCKET_COUNTERS - 1));
+                    stage_dst[p] = sh_cur[f] + r[u];
+                }
             __syncthreads();
-            // runs: half a warp per bucket, 16 buckets x 2 per warp round
-            for (int f = warp * 2 + (lane >> 4); f < n_fine; f += (FP_THREADS / 32) * 2) {
-                const uint32_t n = sh_cnt[f], o = sh_off[f];
-                const uint64_t g = begin + sh_cur[f];
-                for (uint32_t e = lane & 15; e < n; e += 16) residues[g + e] = stage[o + e];
-            }
+            // staged position j goes to begin + stage_dst[j]: runs of ~8 consecutive residues
+            for (uint32_t j = threadIdx.x; j < sh_total; j += FP_THREADS) residues[begin + stage_dst[j]] = stage[j];
             __syncthreads();
             if (threadIdx.x < (unsigned)n_fine) sh_cur[threadIdx.x] += sh_cnt[threadIdx.x];
         }
@@ -933,7 +940,14 @@ void launch_bucket_partition(brgpu_ctx *ctx, const Layout &L, const uint8_t *d_s
             bucket_cursor_kernel<<<1, 512, 0, ctx->stream>>>(d_coarse_base, (uint64_t)n_coarse, d_cursor);
             const uint64_t n_tiles = (n_words + CP_THREADS - 1) / CP_THREADS;
             int per_sm = 0;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, coarse_scatter_kernel<17>, CP_THREADS, 0) != cudaSuccess ||
+            const size_t cs_smem = 2 * CP_TILE_KMERS * sizeof(uint32_t);
+            static bool cs_configured = false;
+            if (!cs_configured) {
+                cudaFuncSetAttribute(coarse_scatter_kernel<17>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs_smem);
+                cudaFuncSetAttribute(coarse_scatter_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs_smem);
+                cs_configured = true;
+            }
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, coarse_scatter_kernel<17>, CP_THREADS, cs_smem) != cudaSuccess ||
                 per_sm < 1) {
                 cudaGetLastError();
                 per_sm = 1;
@@ -941,10 +955,10 @@ void launch_bucket_partition(brgpu_ctx *ctx, const Layout &L, const uint8_t *d_s
             const uint64_t cap = (uint64_t)ctx->sm_count * (uint64_t)per_sm;
             const unsigned grid = (unsigned)(n_tiles < cap ? n_tiles : cap);
             if (k == 17)
-                coarse_scatter_kernel<17><<<grid, CP_THREADS, 0, ctx->stream>>>(d_seq, d_len, L.d_slot_off, L.d_word2read, n_words,
+                coarse_scatter_kernel<17><<<grid, CP_THREADS, cs_smem, ctx->stream>>>(d_seq, d_len, L.d_slot_off, L.d_word2read, n_words,
                                                                                 k, coarse_shift, n_coarse, d_cursor, d_coarse_kmers);
             else
-                coarse_scatter_kernel<0><<<grid, CP_THREADS, 0, ctx->stream>>>(d_seq, d_len, L.d_slot_off, L.d_word2read, n_words,
+                coarse_scatter_kernel<0><<<grid, CP_THREADS, cs_smem, ctx->stream>>>(d_seq, d_len, L.d_slot_off, L.d_word2read, n_words,
                                                                                k, coarse_shift, n_coarse, d_cursor, d_coarse_kmers);
             ctx->launches += 1;
         }
