@@ -1158,6 +1158,7 @@ static int correct_attempt(brgpu_ctx *ctx, const brgpu_set *set, const uint8_t *
         if (work.d_scan_tmp) dfree(ctx, work.d_scan_tmp);
         if (work.d_seg_out) dfree(ctx, work.d_seg_out);
         if (work.d_seg_recs) dfree(ctx, work.d_seg_recs);
+        if (work.d_changed) dfree(ctx, work.d_changed);
     };
     size_t scratch_per_warp = 0;
     for (uint64_t i = 0; i < n_methods; i++) {
@@ -1179,6 +1180,7 @@ static int correct_attempt(brgpu_ctx *ctx, const brgpu_set *set, const uint8_t *
         uint8_t *recs = nullptr;
         if (e == cudaSuccess) e = dalloc(ctx, &recs, (uint64_t)scan_seg_rec_bytes(L));
         work.d_seg_recs = recs;
+        if (e == cudaSuccess) e = dalloc(ctx, &work.d_changed, n);
     }
     if (e != cudaSuccess) {
         cleanup();
@@ -1192,7 +1194,9 @@ static int correct_attempt(brgpu_ctx *ctx, const brgpu_set *set, const uint8_t *
     auto run_methods = [&]() {
         for (uint64_t i = 0; i < n_methods; i++) {
             CorrectParams p{set->k, methods[i], confirm, max_search};
-            launch_solid_bitmap(ctx, L, src, src_len, set_view(set), d_bitmap, (double)in->sum_len);
+            // after a method of the same orientation only the reads it edited need new bitmap words
+            launch_solid_bitmap(ctx, L, src, src_len, set_view(set), d_bitmap, i > 0 ? work.d_changed : nullptr,
+                                (double)in->sum_len);
             launch_scan(ctx, L, src, src_len, buf[nxt], len[nxt], d_bitmap, set_view(set), p, d_scratch,
                         scratch_per_warp, n_warps, work, (double)in->sum_len);
             src = buf[nxt];

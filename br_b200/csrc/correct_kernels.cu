@@ -36,13 +36,16 @@ template <int KT>
 __global__ void __launch_bounds__(256)
     solid_bitmap_kernel(const uint8_t *__restrict__ seq, const uint32_t *__restrict__ len,
                         const uint64_t *__restrict__ slot_off, const uint32_t *__restrict__ word2read,
-                        uint64_t n_words, SolidView set, uint32_t *__restrict__ bitmap) {
+                        uint64_t n_words, SolidView set, uint32_t *__restrict__ bitmap,
+                        const uint8_t *__restrict__ changed) {
     const int k = KT ? KT : set.k;
     const uint8_t *__restrict__ bits = set.bits;
     const uint64_t mask = kmask(k);
     for (uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < n_words;
          w += (uint64_t)gridDim.x * blockDim.x) {
         uint32_t r = __ldg(word2read + w);
+        // the previous method left this read as it was: its bitmap words are still valid
+        if (changed && !__ldg(changed + r)) continue;
         uint64_t sb = w << 5;
         uint32_t p0 = (uint32_t)(sb - __ldg(slot_off + r));
         uint32_t L = __ldg(len + r);
@@ -108,7 +111,7 @@ __global__ void __launch_bounds__(256)
 }
 
 void launch_solid_bitmap(brgpu_ctx *ctx, const Layout &L, const uint8_t *d_seq, const uint32_t *d_len,
-                         const SetView &set, uint32_t *d_bitmap, double n_bases_hint) {
+                         const SetView &set, uint32_t *d_bitmap, const uint8_t *d_changed, double n_bases_hint) {
     uint64_t n_words = L.total_slots >> 5;
     if (!n_words) return;
     // algorithmic bytes per position: 32 B sector + 1 B ASCII in + 1/8 B bit out
@@ -118,9 +121,9 @@ void launch_solid_bitmap(brgpu_ctx *ctx, const Layout &L, const uint8_t *d_seq, 
     const SolidView sv{set.bits, set.summary, set.shift, set.k, (const uint2 *)set.dir, set.blocks};
     const unsigned grid = (unsigned)(need < capb ? need : capb);
     if (set.k == 17)
-        solid_bitmap_kernel<17><<<grid, 256, 0, ctx->stream>>>(d_seq, d_len, L.d_slot_off, L.d_word2read, n_words, sv, d_bitmap);
+        solid_bitmap_kernel<17><<<grid, 256, 0, ctx->stream>>>(d_seq, d_len, L.d_slot_off, L.d_word2read, n_words, sv, d_bitmap, d_changed);
     else
-        solid_bitmap_kernel<0><<<grid, 256, 0, ctx->stream>>>(d_seq, d_len, L.d_slot_off, L.d_word2read, n_words, sv, d_bitmap);
+        solid_bitmap_kernel<0><<<grid, 256, 0, ctx->stream>>>(d_seq, d_len, L.d_slot_off, L.d_word2read, n_words, sv, d_bitmap, d_changed);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1305,7 +1308,7 @@ __global__ void __launch_bounds__(SCAN_WARPS_PER_BLOCK * 32)
                       const uint32_t *__restrict__ bitmap, const uint32_t *__restrict__ order,
                       const uint64_t *__restrict__ seg_first, uint32_t n_reads, const uint8_t *__restrict__ seg_out,
                       const SegRec *__restrict__ recs, uint32_t *__restrict__ flags, SolidView set, CorrectParams p,
-                      uint8_t *scratch, size_t scratch_per_warp) {
+                      uint8_t *scratch, size_t scratch_per_warp, uint8_t *__restrict__ changed) {
     const int lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (KT) p.k = KT; // compile-time k: the k-mer arithmetic below folds to immediates
@@ -1332,6 +1335,7 @@ __global__ void __launch_bounds__(SCAN_WARPS_PER_BLOCK * 32)
         rd.bm = bitmap + (base >> 5);
         rd.o = 0;
         rd.copy_from = 0;
+        bool edited = false; // a correction succeeded somewhere in this read
         if (rd.len < k) { // mod.rs:56-58
             flush_copy(rd, rd.len);
         } else {
@@ -1359,12 +1363,14 @@ __global__ void __launch_bounds__(SCAN_WARPS_PER_BLOCK * 32)
                     }
                     rd.o += n;
                     q = rec.q_exit;
+                    edited |= rec.horizon != NO_HORIZON; // q <= horizon: the correction is inside the spliced part
                 } else {
                     // re-run this segment from the true state
                     rd.copy_from = first ? 0u : q;
                     uint32_t q_exit, horizon;
                     if (q < rd.len) {
                         correct_segment<METHOD>(rd, p, q, seg_start + SEG, q_exit, horizon);
+                        edited |= horizon != NO_HORIZON;
                     } else {
                         q_exit = rd.len;
                         flush_copy(rd, rd.len);
@@ -1378,6 +1384,7 @@ __global__ void __launch_bounds__(SCAN_WARPS_PER_BLOCK * 32)
         __syncwarp();
         if (lane == 0) {
             len_out[r] = rd.o;
+            changed[r] = edited ? 1 : 0;
             if (rd.o > rd.cap) atomicOr(flags + 1, 1u);
         }
     }
@@ -1427,7 +1434,7 @@ static void launch_scan_method(brgpu_ctx *ctx, const Layout &L, const uint8_t *d
         scan_merge_kernel<M, KT><<<grid_for_warps((uint64_t)occupancy_warps(ctx, scan_merge_kernel<M, KT>), L.n), threads, 0,
                                ctx->stream>>>(d_in, d_len_in, d_out, d_len_out, L.d_slot_off, d_bitmap, L.d_order,
                                               w.d_seg_first, (uint32_t)L.n, w.d_seg_out, (const SegRec *)w.d_seg_recs,
-                                              ctx->d_flags, sv, p, d_scratch, scratch_per_warp);
+                                              ctx->d_flags, sv, p, d_scratch, scratch_per_warp, w.d_changed);
     }
 }
 

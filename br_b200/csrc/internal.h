@@ -187,9 +187,10 @@ struct CorrectParams {
     int confirm;
     int max_search;
 };
-// solidity bit of the k-mer ending at every slot position of every read (0 where undefined)
+// solidity bit of the k-mer ending at every slot position of every read (0 where undefined);
+// d_changed != nullptr: only for the reads it marks, the others keep the words already in d_bitmap
 void launch_solid_bitmap(brgpu_ctx *ctx, const Layout &L, const uint8_t *d_seq, const uint32_t *d_len,
-                         const SetView &set, uint32_t *d_bitmap, double n_bases_hint);
+                         const SetView &set, uint32_t *d_bitmap, const uint8_t *d_changed, double n_bases_hint);
 // per-pass work areas of the segmented scan (sized once per correction call)
 struct ScanWork {
     uint32_t *d_n_seg = nullptr;     // n reads
@@ -197,6 +198,7 @@ struct ScanWork {
     uint64_t *d_scan_tmp = nullptr;  // n / 4096 + 4
     uint8_t *d_seg_out = nullptr;    // scan_seg_out_bytes(L)
     void *d_seg_recs = nullptr;      // scan_seg_rec_bytes(L)
+    uint8_t *d_changed = nullptr;    // n reads: 1 iff the pass edited the read (the next pass's bitmap skips the others)
 };
 uint64_t scan_max_segments(const Layout &L);
 size_t scan_seg_out_bytes(const Layout &L);
