@@ -34,6 +34,14 @@ __host__ __device__ __forceinline__ uint64_t replace_last(uint64_t kmer, uint32_
 }
 
 __device__ __forceinline__ uint64_t revcomp(uint64_t kmer, int k) {
+    if (k == 17) {
+        // 34 bits: the low word of the result is the reversed-and-swapped image of bits 2..33, the
+        // two top bits are the first base complemented — 32-bit operations only
+        const uint32_t x = __brev((uint32_t)(kmer >> 2));
+        const uint32_t lo = (((x >> 1) & 0x55555555u) | ((x << 1) & 0xAAAAAAAAu)) ^ 0xAAAAAAAAu;
+        const uint32_t hi = ((uint32_t)kmer & 3u) ^ 2u;
+        return ((uint64_t)hi << 32) | lo;
+    }
     // reverse all 64 bits, swap the two bits inside every group back, complement (xor 10 per
     // group), then drop the 64-2k low garbage bits.
     uint64_t r = __brevll(kmer);
