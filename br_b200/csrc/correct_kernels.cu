@@ -1026,6 +1026,22 @@ __device__ __forceinline__ Corr greedy_correct_error(Rd &rd, uint64_t kmer, uint
         if (rd.lane == 0) g.viewed[nviewed] = x;
         nviewed++;
         if (sublen < s) return res; // greedy.rs:160-162
+        // The reference evaluates match_alignement first and check_next_kmers second
+        // (greedy.rs:163-165); both are pure and a result needs both, so the cheap one (nb_validate
+        // lookups, greedy.rs:104-117) goes first and the alignment runs only when it can matter.
+        bool ok = sublen - s >= nb_validate;
+        if (ok) {
+            bool bad = false;
+            for (uint32_t v0 = 0; v0 < nb_validate; v0 += 32) {
+                uint32_t v = v0 + (uint32_t)rd.lane;
+                if (v < nb_validate) {
+                    uint64_t km = push_seq(x, sub + s, v + 1, rd.mask);
+                    if (!lookup(rd, km)) bad = true;
+                }
+            }
+            ok = !__any_sync(FULL, bad);
+        }
+        if (!ok) continue;
         // x side: before || seq[..s]
         if ((uint32_t)rd.lane < s) g.x[nb + rd.lane] = sub[rd.lane];
         for (uint32_t e = 32 + rd.lane; e < s; e += 32) g.x[nb + e] = sub[e];
@@ -1033,31 +1049,16 @@ __device__ __forceinline__ Corr greedy_correct_error(Rd &rd, uint64_t kmer, uint
         uint32_t nops = bio_global(rd, g, nb + s, nb + npath, stride);
         int off;
         if (match_alignement(g, nops, nb, off)) {
-            // check_next_kmers (greedy.rs:104-117)
-            bool ok = sublen - s >= nb_validate;
-            if (ok) {
-                bool bad = false;
-                for (uint32_t v0 = 0; v0 < nb_validate; v0 += 32) {
-                    uint32_t v = v0 + (uint32_t)rd.lane;
-                    if (v < nb_validate) {
-                        uint64_t km = push_seq(x, sub + s, v + 1, rd.mask);
-                        if (!lookup(rd, km)) bad = true;
-                    }
-                }
-                ok = !__any_sync(FULL, bad);
-            }
-            if (ok) {
-                long long o = (long long)npath + (long long)off;
-                if (o < 0) o = 0; // unreachable in the reference (would wrap); see SURVEY appendix B.10
-                flush_copy(rd, i);
-                for (uint32_t e = rd.lane; e < npath; e += 32)
-                    if (rd.o + e < rd.cap) rd.out[rd.o + e] = g.y[nb + e];
-                res.some = true;
-                res.n_emit = npath;
-                res.new_kmer = x;
-                res.offset = (uint32_t)o;
-                return res;
-            }
+            long long o = (long long)npath + (long long)off;
+            if (o < 0) o = 0; // unreachable in the reference (would wrap); see SURVEY appendix B.10
+            flush_copy(rd, i);
+            for (uint32_t e = rd.lane; e < npath; e += 32)
+                if (rd.o + e < rd.cap) rd.out[rd.o + e] = g.y[nb + e];
+            res.some = true;
+            res.n_emit = npath;
+            res.new_kmer = x;
+            res.offset = (uint32_t)o;
+            return res;
         }
     }
     return res;
