@@ -22,6 +22,8 @@
 //   Graph::correct_error                                     src/correct/graph.rs:44-85
 //   Greedy::correct_error + bio 1.6.0 global alignment       src/correct/greedy.rs:56-173
 //   GapSize::correct_error, ins_sub_correction               src/correct/gap_size.rs:44-108
+#include <cstdlib>
+
 #include "internal.h"
 #include "kmer.cuh"
 
@@ -164,12 +166,12 @@ __device__ __forceinline__ void load_win(Rd &rd, uint32_t origin) {
 }
 
 // does the window hold input positions [pos, pos + n)?
-__device__ __forceinline__ bool win_covers(const Rd &rd, uint32_t pos, uint32_t n) {
+template <class R> __device__ __forceinline__ bool win_covers(const R &rd, uint32_t pos, uint32_t n) {
     return rd.w_origin != 0xffffffffu && pos >= rd.w_origin && pos + n <= rd.w_origin + 64u;
 }
 
 // the n (<= 32) 2-bit codes of input positions [pos, pos + n), first base most significant
-__device__ __forceinline__ uint64_t win_extract(const Rd &rd, uint32_t pos, uint32_t n) {
+template <class R> __device__ __forceinline__ uint64_t win_extract(const R &rd, uint32_t pos, uint32_t n) {
     if (n == 0) return 0ULL;
     const uint32_t off = pos - rd.w_origin, e = off + n;
     uint64_t v;
@@ -183,7 +185,7 @@ __device__ __forceinline__ uint64_t win_extract(const Rd &rd, uint32_t pos, uint
 }
 
 // `kmer` after pushing the input bases [pos, pos + n) taken from the window
-__device__ __forceinline__ uint64_t win_push(const Rd &rd, uint64_t kmer, uint32_t pos, uint32_t n) {
+template <class R> __device__ __forceinline__ uint64_t win_push(const R &rd, uint64_t kmer, uint32_t pos, uint32_t n) {
     uint64_t hi = n < 32u ? (kmer << (2 * n)) : 0ULL;
     return (hi | win_extract(rd, pos, n)) & rd.mask;
 }
@@ -1393,6 +1395,633 @@ __global__ void __launch_bounds__(SCAN_WARPS_PER_BLOCK * 32)
     if (lane == 0 && gets) atomicAdd(reinterpret_cast<unsigned long long *>(flags + 2), (unsigned long long)gets);
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Four segments per warp (One / Two).
+//
+// A warp that owns one segment runs ~700 warp instructions per event with most lanes idle:
+// the alternatives take 4 lanes, One's scenario items 21, the dirty window 16, and everything
+// between the lookup rounds is scalar bookkeeping; once the lookups had moved into L2 the forward
+// scans were bound by instruction issue (profiles/ncu_r1q.txt).  Here a warp is four groups of 8
+// lanes; a group owns a segment and walks it exactly like correct_segment does (same state, same
+// order, so the pieces and records are interchangeable), and the four groups step through their
+// events together: find the next event, load the window, alternatives, scenario rounds, apply.
+// Collectives use the group's lane mask, so a group may leave a phase early (no unique
+// alternative, end of segment) and rejoins the others at the next structured merge point.
+// ------------------------------------------------------------------------------------------
+struct G8 {
+    // lane geometry
+    int gl;           // lane inside the group (0..7)
+    uint32_t gbase;   // first lane of the group inside the warp
+    uint32_t gmask;   // lanes of the group
+    // segment (uniform inside the group)
+    const uint8_t *in;
+    uint32_t len;
+    uint8_t *out;
+    const uint32_t *bm;
+    uint32_t o, copy_from;
+    uint64_t mask;
+    int k;
+    uint64_t w0, w1;
+    uint32_t w_origin;
+    uint32_t n_get; // per lane
+};
+
+__device__ __forceinline__ uint32_t g_ballot(const G8 &g, bool p) { return (__ballot_sync(g.gmask, p) >> g.gbase) & 0xffu; }
+__device__ __forceinline__ uint32_t g_shfl(const G8 &g, uint32_t v, int src) { return __shfl_sync(g.gmask, v, src, 8); }
+__device__ __forceinline__ uint64_t g_shfl64(const G8 &g, uint64_t v, int src) {
+    uint32_t lo = __shfl_sync(g.gmask, (uint32_t)v, src, 8);
+    uint32_t hi = __shfl_sync(g.gmask, (uint32_t)(v >> 32), src, 8);
+    return ((uint64_t)hi << 32) | lo;
+}
+__device__ __forceinline__ uint32_t g_or(const G8 &g, uint32_t v) {
+    v |= __shfl_xor_sync(g.gmask, v, 1, 8);
+    v |= __shfl_xor_sync(g.gmask, v, 2, 8);
+    v |= __shfl_xor_sync(g.gmask, v, 4, 8);
+    return v;
+}
+__device__ __forceinline__ bool g_lookup(G8 &g, const SolidView &set, uint64_t kmer) {
+    g.n_get++;
+    return solid(set, kmer);
+}
+// N lookups per lane with all their loads in flight together: first the N directory words (or
+// summary words), then the N blocks (or bitfield bytes) of those that are occupied.  A lane's
+// rounds are latency chains of L2 round trips, so batching is what keeps 8-lane groups from
+// paying one round trip per 8 items.
+template <int N>
+__device__ __forceinline__ void g_lookup_n(G8 &g, const SolidView &set, const uint64_t (&km)[N], const bool (&want)[N],
+                                           bool (&out)[N]) {
+    uint64_t idx[N];
+#pragma unroll
+    for (int t = 0; t < N; t++) {
+        idx[t] = canonical_index(km[t], set.k);
+        if (want[t]) g.n_get++;
+    }
+    if (set.dir) {
+        uint2 e[N];
+#pragma unroll
+        for (int t = 0; t < N; t++) {
+            e[t] = make_uint2(0u, 0u);
+            if (want[t]) e[t] = __ldg(set.dir + (idx[t] >> 11));
+        }
+        uint64_t blk[N];
+#pragma unroll
+        for (int t = 0; t < N; t++) {
+            const uint32_t b = (uint32_t)(idx[t] >> 6) & 31u;
+            blk[t] = 0;
+            if ((e[t].x >> b) & 1u) blk[t] = __ldg(set.blocks + (e[t].y + __popc(e[t].x & ((1u << b) - 1u))));
+        }
+#pragma unroll
+        for (int t = 0; t < N; t++) out[t] = (blk[t] >> (idx[t] & 63)) & 1ULL;
+        return;
+    }
+    bool go[N];
+#pragma unroll
+    for (int t = 0; t < N; t++) go[t] = want[t];
+    if (set.summary) {
+        uint32_t sw[N];
+#pragma unroll
+        for (int t = 0; t < N; t++) {
+            sw[t] = 0;
+            if (go[t]) sw[t] = __ldg(set.summary + (idx[t] >> (set.shift + 5)));
+        }
+#pragma unroll
+        for (int t = 0; t < N; t++) go[t] = (sw[t] >> ((idx[t] >> set.shift) & 31)) & 1u;
+    }
+    uint32_t byte[N];
+#pragma unroll
+    for (int t = 0; t < N; t++) {
+        byte[t] = 0;
+        if (go[t]) byte[t] = __ldg(set.bits + (idx[t] >> 3));
+    }
+#pragma unroll
+    for (int t = 0; t < N; t++) out[t] = (byte[t] >> (idx[t] & 7)) & 1u;
+}
+
+__device__ __forceinline__ bool g_bm_bit(const G8 &g, uint32_t p) { return (__ldg(g.bm + (p >> 5)) >> (p & 31)) & 1u; }
+
+// 64 input bases from `origin` on, packed into (w0, w1) on every lane of the group: lane l reads
+// bytes [8l, 8l + 8) with three aligned word loads and a funnel shift, packs them to 16 bits, and
+// a 3-step butterfly concatenates the eight pieces.  Codes of positions >= len are zero.
+__device__ __forceinline__ void g_load_win(G8 &g, uint32_t origin) {
+    const uint8_t *p = g.in + origin + 8u * (uint32_t)g.gl;
+    const uint32_t a = (uint32_t)((uintptr_t)p & 3u);
+    const uint32_t *q = reinterpret_cast<const uint32_t *>(p - a);
+    const uint32_t x0 = __ldg(q), x1 = __ldg(q + 1), x2 = a ? __ldg(q + 2) : 0u;
+    const uint32_t b0 = __funnelshift_r(x0, x1, 8 * a), b1 = __funnelshift_r(x1, x2, 8 * a);
+    uint32_t v16 = (pack4(b0) << 8) | pack4(b1);
+    const uint32_t first = origin + 8u * (uint32_t)g.gl;
+    const uint32_t nv = first >= g.len ? 0u : (g.len - first < 8u ? g.len - first : 8u);
+    v16 &= (0xffffu << (16u - 2u * nv)) & 0xffffu;
+    const uint32_t o16 = __shfl_xor_sync(g.gmask, v16, 1, 8);
+    const uint32_t t32 = (g.gl & 1) ? ((o16 << 16) | v16) : ((v16 << 16) | o16);
+    const uint32_t o32 = __shfl_xor_sync(g.gmask, t32, 2, 8);
+    const uint64_t t64 = (g.gl & 2) ? (((uint64_t)o32 << 32) | t32) : (((uint64_t)t32 << 32) | o32);
+    const uint32_t olo = __shfl_xor_sync(g.gmask, (uint32_t)t64, 4, 8);
+    const uint32_t ohi = __shfl_xor_sync(g.gmask, (uint32_t)(t64 >> 32), 4, 8);
+    const uint64_t o64 = ((uint64_t)ohi << 32) | olo;
+    g.w0 = (g.gl & 4) ? o64 : t64;
+    g.w1 = (g.gl & 4) ? t64 : o64;
+    g.w_origin = origin;
+}
+
+// group copy, arbitrary alignment on both sides (see warp_copy); 8 lanes, two word pairs in flight
+__device__ __forceinline__ void g_copy(uint8_t *dst, const uint8_t *src, uint32_t n, int gl) {
+    if (n < 16) {
+        for (uint32_t t = gl; t < n; t += 8) dst[t] = src[t];
+        return;
+    }
+    const uint32_t head = (uint32_t)((4u - ((uintptr_t)dst & 3u)) & 3u);
+    if ((uint32_t)gl < head) dst[gl] = src[gl];
+    const uint8_t *s0 = src + head;
+    uint32_t *d4 = reinterpret_cast<uint32_t *>(dst + head);
+    const uint32_t n_words = (n - head) >> 2;
+    const uint32_t a = (uint32_t)((uintptr_t)s0 & 3u);
+    const uint32_t *s4 = reinterpret_cast<const uint32_t *>(s0 - a);
+    uint32_t w = gl;
+    for (; w + 8 < n_words; w += 16) {
+        const uint32_t l0 = s4[w], l1 = s4[w + 8];
+        const uint32_t h0 = a ? s4[w + 1] : 0u, h1 = a ? s4[w + 9] : 0u;
+        d4[w] = a ? __funnelshift_r(l0, h0, 8 * a) : l0;
+        d4[w + 8] = a ? __funnelshift_r(l1, h1, 8 * a) : l1;
+    }
+    for (; w < n_words; w += 8) {
+        const uint32_t lo = s4[w];
+        d4[w] = a ? __funnelshift_r(lo, s4[w + 1], 8 * a) : lo;
+    }
+    const uint32_t done = head + (n_words << 2);
+    if (done + (uint32_t)gl < n) dst[done + gl] = src[done + gl];
+}
+
+__device__ __forceinline__ void g_flush_copy(G8 &g, uint32_t upto) {
+    if (upto > g.len) upto = g.len;
+    if (upto <= g.copy_from) return;
+    const uint32_t n = upto - g.copy_from;
+    if (g.o + n <= SEG_CAP) {
+        g_copy(g.out + g.o, g.in + g.copy_from, n, g.gl);
+    } else { // the scratch region overflows: keep counting, write what fits (the piece is marked bad)
+        for (uint32_t t = g.gl; t < n; t += 8)
+            if (g.o + t < SEG_CAP) g.out[g.o + t] = g.in[g.copy_from + t];
+    }
+    g.o += n;
+    g.copy_from = upto;
+}
+
+// find_transition for a group: 256 bitmap positions per step
+__device__ __forceinline__ uint32_t g_find_transition(const G8 &g, uint32_t i, bool previous, uint32_t end) {
+    if (i >= end) return end;
+    uint32_t wbase = i >> 5;
+    const uint32_t n_words = (end + 31) >> 5;
+    const uint32_t n_words_read = (g.len + 31) >> 5;
+    uint32_t carry_in = 0;
+    for (;;) {
+        const uint32_t wi = wbase + (uint32_t)g.gl;
+        const uint32_t W = wi < n_words_read ? __ldg(g.bm + wi) : 0u;
+        const uint32_t up = __shfl_up_sync(g.gmask, W, 1, 8);
+        const uint32_t carry = g.gl ? (up >> 31) : carry_in;
+        uint32_t T = ~W & ((W << 1) | carry);
+        const uint32_t posbase = wi << 5;
+        if (posbase + 31 < i) {
+            T = 0;
+        } else if (posbase <= i) {
+            const uint32_t sh = i - posbase;
+            T &= (0xffffffffu << sh);
+            T &= ~(1u << sh);
+            if (previous && !((W >> sh) & 1u)) T |= 1u << sh;
+        }
+        if (posbase >= end)
+            T = 0;
+        else if (posbase + 32 > end)
+            T &= (1u << (end - posbase)) - 1u;
+        const uint32_t any = g_ballot(g, T != 0);
+        if (any) {
+            const int fl = __ffs(any) - 1;
+            const uint32_t Tf = g_shfl(g, T, fl);
+            return ((wbase + (uint32_t)fl) << 5) + (uint32_t)(__ffs(Tf) - 1);
+        }
+        wbase += 8;
+        if (wbase >= n_words) return end;
+        carry_in = g_shfl(g, W, 7) >> 31;
+        i = wbase << 5;
+        previous = carry_in != 0;
+    }
+}
+
+// Exist<S>::correct_error for a group (see exist_correct_error for the 32-lane version and the
+// references into exist/mod.rs, one.rs, two.rs): same rounds, 8 items per round.
+template <int NS>
+__device__ __forceinline__ Corr g_exist_correct_error(G8 &g, const SolidView &set, uint64_t kmer, uint32_t i, uint32_t c) {
+    Corr res;
+    res.some = false;
+    res.in_place = false;
+    res.n_emit = 0;
+    res.codes = 0;
+    res.offset = 0;
+    res.new_kmer = 0;
+    const uint64_t mask = g.mask;
+
+    bool sa = false;
+    if (g.gl < 4) sa = g_lookup(g, set, replace_last(kmer, (uint32_t)g.gl, mask));
+    uint32_t alt;
+    if (!uniq(g_ballot(g, sa) & 0xfu, alt)) return res; // exist/mod.rs:121-126
+    const uint64_t K0 = replace_last(kmer, alt, mask);
+    const uint8_t *sub = g.in + i;
+    const uint32_t sublen = g.len - i;
+    const bool use_win = c <= 30u && win_covers(g, i, c + 6u);
+    auto sub_push = [&](uint64_t km, uint32_t from, uint32_t n) -> uint64_t {
+        return use_win ? win_push(g, km, i + from, n) : push_seq(km, sub + from, n, mask);
+    };
+
+    uint32_t bad = 0, more = 0, cand;
+    Scen win;
+    if (NS == 3) {
+        uint32_t short_mask = 0;
+#pragma unroll
+        for (int s = 0; s < 3; s++)
+            if (scen_one(s, K0).offa + c > sublen) short_mask |= 1u << s;
+        const uint32_t per = c + 2, Q = 3u * per;
+        if (Q <= 24u) {
+            // the usual confirm values: three items per lane, their lookups in flight together
+            uint64_t km[3];
+            bool want[3], hit[3], is_more[3];
+            int sc_of[3];
+#pragma unroll
+            for (int h = 0; h < 3; h++) {
+                const uint32_t q = (uint32_t)g.gl + 8u * (uint32_t)h;
+                const int s = (int)(q / per);
+                const uint32_t u = q - (uint32_t)s * per;
+                const Scen t = scen_one(s, K0);
+                sc_of[h] = s;
+                want[h] = q < Q && !((short_mask >> s) & 1u);
+                is_more[h] = u > c;
+                km[h] = 0;
+                if (want[h]) {
+                    if (u <= c) {
+                        km[h] = sub_push(t.K, t.offa, u);
+                    } else if (sublen > c + t.offc + 1) {
+                        km[h] = sub_push(push(K0 >> 2, t.codes & 3u, mask), t.offc, c + 1);
+                    } else {
+                        want[h] = false; // one_more is false without a lookup (exist/mod.rs:52)
+                    }
+                }
+            }
+            g_lookup_n<3>(g, set, km, want, hit);
+#pragma unroll
+            for (int h = 0; h < 3; h++) {
+                if (!want[h]) continue;
+                if (is_more[h]) {
+                    if (hit[h]) more |= 1u << sc_of[h];
+                } else if (!hit[h]) {
+                    bad |= 1u << sc_of[h];
+                }
+            }
+        } else {
+            for (uint32_t q0 = 0; q0 < Q; q0 += 8) {
+                const uint32_t q = q0 + (uint32_t)g.gl;
+                const int s = (int)(q / per);
+                const uint32_t u = q - (uint32_t)s * per;
+                const Scen t = scen_one(s, K0);
+                if (q >= Q || ((short_mask >> s) & 1u)) continue;
+                if (u <= c) {
+                    if (!g_lookup(g, set, sub_push(t.K, t.offa, u))) bad |= 1u << s;
+                } else if (sublen > c + t.offc + 1) {
+                    const uint64_t km = push(K0 >> 2, t.codes & 3u, mask);
+                    if (g_lookup(g, set, sub_push(km, t.offc, c + 1))) more |= 1u << s;
+                }
+            }
+        }
+        bad = g_or(g, bad);
+        more = g_or(g, more);
+        cand = 7u & ~short_mask & ~bad;
+        if (cand == 0) return res;
+        if (__popc(cand) > 1) {
+            cand &= more;
+            if (__popc(cand) != 1) return res;
+        }
+        win = scen_one(__ffs(cand) - 1, K0);
+    } else {
+        uint32_t sb[4];
+#pragma unroll
+        for (int t = 0; t < 4; t++)
+            sb[t] = (uint32_t)t < sublen ? (use_win ? (uint32_t)win_extract(g, i + (uint32_t)t, 1) : nuc2bit(sub[t])) : 0u;
+        // round 2: the four successor sets, 16 lookups = two per lane, in flight together
+        uint32_t m16 = 0;
+        {
+            uint64_t km[2];
+            bool want[2], hit[2];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int it = g.gl + 8 * h, grp = it >> 2;
+                uint64_t base = K0;
+                want[h] = true;
+                if (grp == 1) { base = push(K0, sb[1], mask); want[h] = sublen >= 2; }
+                if (grp == 2) { base = push(K0, sb[2], mask); want[h] = sublen >= 3; }
+                if (grp == 3) { base = push(K0, sb[0], mask); }
+                km[h] = push(base, (uint32_t)(it & 3), mask);
+            }
+            g_lookup_n<2>(g, set, km, want, hit);
+#pragma unroll
+            for (int h = 0; h < 2; h++) m16 |= g_ballot(g, want[h] && hit[h]) << (8 * h);
+        }
+        const uint32_t N0 = m16 & 0xf, N1 = (m16 >> 4) & 0xf, N2 = (m16 >> 8) & 0xf, N0p = (m16 >> 12) & 0xf;
+        // round 3a: get(K) of every valid scenario that is long enough, two scenarios per lane
+        cand = 0;
+        {
+            uint64_t km[2];
+            bool want[2], hit[2];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int s = g.gl + 8 * h;
+                want[h] = false;
+                km[h] = 0;
+                if (s < NS) {
+                    const Scen t = scen_two(s, K0, sublen, sb, N0, N1, N2, N0p, mask);
+                    want[h] = t.valid && !(t.offa + c > sublen);
+                    km[h] = t.K;
+                }
+            }
+            g_lookup_n<2>(g, set, km, want, hit);
+#pragma unroll
+            for (int h = 0; h < 2; h++) cand |= g_ballot(g, want[h] && hit[h]) << (8 * h);
+        }
+        // round 3b: the c confirmations of the survivors
+        const uint32_t Q = (uint32_t)__popc(cand) * c;
+        if (Q <= 24u) {
+            uint64_t km[3];
+            bool want[3], hit[3];
+            int sc_of[3];
+#pragma unroll
+            for (int h = 0; h < 3; h++) {
+                const uint32_t q = (uint32_t)g.gl + 8u * (uint32_t)h;
+                want[h] = q < Q;
+                km[h] = 0;
+                sc_of[h] = 0;
+                if (want[h]) {
+                    const uint32_t r = q / c, u = q - r * c + 1u;
+                    const int s = (int)__fns(cand, 0u, (int)r + 1);
+                    const Scen t = scen_two(s, K0, sublen, sb, N0, N1, N2, N0p, mask);
+                    sc_of[h] = s;
+                    km[h] = sub_push(t.K, t.offa, u);
+                }
+            }
+            g_lookup_n<3>(g, set, km, want, hit);
+#pragma unroll
+            for (int h = 0; h < 3; h++)
+                if (want[h] && !hit[h]) bad |= 1u << sc_of[h];
+        } else {
+            for (uint32_t q0 = 0; q0 < Q; q0 += 8) {
+                const uint32_t q = q0 + (uint32_t)g.gl;
+                if (q < Q) {
+                    const uint32_t r = q / c, u = q - r * c + 1u;
+                    const int s = (int)__fns(cand, 0u, (int)r + 1);
+                    const Scen t = scen_two(s, K0, sublen, sb, N0, N1, N2, N0p, mask);
+                    if (!g_lookup(g, set, sub_push(t.K, t.offa, u))) bad |= 1u << s;
+                }
+            }
+        }
+        cand &= ~g_or(g, bad);
+        if (cand == 0) return res;
+        // round 3c, only on a tie: one_more of the tied scenarios
+        if (__popc(cand) > 1) {
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int s = g.gl + 8 * h;
+                bool m = false;
+                if (s < NS && ((cand >> s) & 1u)) {
+                    const Scen t = scen_two(s, K0, sublen, sb, N0, N1, N2, N0p, mask);
+                    if (sublen > c + t.offc + 1) {
+                        uint64_t km = K0 >> 2;
+                        for (int e = (int)t.n_emit - 1; e >= 0; e--) km = push(km, (t.codes >> (2 * e)) & 3u, mask);
+                        m = g_lookup(g, set, sub_push(km, t.offc, c + 1));
+                    }
+                }
+                more |= g_ballot(g, m) << (8 * h);
+            }
+            cand &= more;
+            if (__popc(cand) != 1) return res;
+        }
+        win = scen_two(__ffs(cand) - 1, K0, sublen, sb, N0, N1, N2, N0p, mask);
+    }
+    res.some = true;
+    res.n_emit = win.n_emit;
+    res.codes = win.codes;
+    res.offset = win.offc;
+    return res;
+}
+
+template <int METHOD, int KT>
+__global__ void __launch_bounds__(SCAN_WARPS_PER_BLOCK * 32, 8)
+    scan_spec8_kernel(const uint8_t *__restrict__ in, const uint32_t *__restrict__ len_in,
+                      const uint64_t *__restrict__ slot_off, const uint32_t *__restrict__ bitmap,
+                      const uint64_t *__restrict__ seg_first, uint32_t n_reads, uint8_t *__restrict__ seg_out,
+                      SegRec *__restrict__ recs, uint32_t *__restrict__ flags, SolidView set, CorrectParams p) {
+    constexpr int NS = METHOD == BRGPU_ONE ? 3 : 13;
+    if (KT) p.k = KT;
+    set.k = p.k;
+    const uint32_t k = (uint32_t)p.k, c = (uint32_t)p.confirm;
+    G8 g;
+    g.gl = threadIdx.x & 7;
+    g.gbase = threadIdx.x & 24;
+    g.gmask = 0xffu << g.gbase;
+    g.mask = kmask(p.k);
+    g.k = p.k;
+    g.n_get = 0;
+    g.in = in;
+    g.out = seg_out;
+    g.bm = bitmap;
+    g.len = 0;
+    g.o = g.copy_from = 0;
+    g.w0 = g.w1 = 0;
+    g.w_origin = 0xffffffffu;
+    const uint64_t n_seg_total = __ldg(seg_first + n_reads);
+
+    // state of the group's piece (correct_segment's locals), uniform inside the group
+    bool active = false, exhausted = false;
+    unsigned long long sg = 0;
+    uint32_t i = 0, limit = 0, d = 0, horizon = NO_HORIZON;
+    bool previous = false, canon = true;
+    uint64_t kmer = 0;
+
+    // One trip of this loop = every group of the warp handles one event of its piece: the four
+    // groups advance to their next events in lockstep rounds, then process them side by side.
+    // The warp-wide votes at the loop heads re-converge the groups.
+    for (;;) {
+        // ---- an idle group takes a segment
+        if (!active && !exhausted) {
+            if (g.gl == 0) sg = atomicAdd(reinterpret_cast<unsigned long long *>(flags + 4), 1ULL);
+            sg = g_shfl64(g, sg, 0);
+            if (sg >= n_seg_total) {
+                exhausted = true;
+            } else {
+                uint32_t lo = 0, hi = n_reads;
+                while (hi - lo > 1) {
+                    uint32_t mid = (lo + hi) >> 1;
+                    if (__ldg(seg_first + mid) <= sg)
+                        lo = mid;
+                    else
+                        hi = mid;
+                }
+                const uint32_t r = lo;
+                const uint32_t sidx = (uint32_t)(sg - __ldg(seg_first + r));
+                const uint64_t base = __ldg(slot_off + r);
+                g.in = in + base;
+                g.len = __ldg(len_in + r);
+                g.bm = bitmap + (base >> 5);
+                g.out = seg_out + sg * SEG_CAP;
+                g.o = 0;
+                g.w_origin = 0xffffffffu;
+                const uint32_t start = k + sidx * SEG;
+                if (g.len >= k && (g.len > k || sidx == 0) && start < g.len) {
+                    g.copy_from = sidx == 0 ? 0u : start; // piece 0 carries the first k bases (mod.rs:62-65)
+                    i = start;
+                    limit = start + SEG < g.len ? start + SEG : g.len;
+                    previous = g_bm_bit(g, start - 1);
+                    canon = true;
+                    d = 0;
+                    kmer = 0;
+                    horizon = NO_HORIZON;
+                    active = true;
+                } else {
+                    // nothing to scan: a piece of a read shorter than k (unusable, the merge copies
+                    // the read), or the read of exactly k bases (the piece is the read itself)
+                    SegRec rec;
+                    rec.out_len = 0;
+                    rec.q_exit = g.len;
+                    rec.horizon = NO_HORIZON;
+                    rec.bad = 1;
+                    if (g.len >= k && (g.len > k || sidx == 0)) {
+                        g.copy_from = 0;
+                        g_flush_copy(g, g.len);
+                        rec.out_len = g.o;
+                        rec.bad = g.o > SEG_CAP ? 1u : 0u;
+                    }
+                    __syncwarp(g.gmask);
+                    if (g.gl == 0) recs[sg] = rec;
+                }
+            }
+        }
+        if (__all_sync(FULL, !active && exhausted)) break;
+
+        // ---- advance every active group to its next event (or to the end of its piece)
+        bool at_event = false, clean_event = false, done = false;
+        bool adv = active;
+        while (__any_sync(FULL, adv)) {
+            if (adv && i >= g.len) {
+                done = true;
+                adv = false;
+            }
+            if (adv && d > 0) { // k-mers that still contain corrected bases: real lookups, 16 per round
+                uint32_t n = g.len - i;
+                if (n > d) n = d;
+                if (n > 16) n = 16;
+                if (!win_covers(g, i, n)) g_load_win(g, i >= k - 1 ? i - k + 1 : 0u);
+                const bool in0 = (uint32_t)g.gl < n, in1 = (uint32_t)g.gl + 8u < n;
+                const uint64_t km0 = win_push(g, kmer, i, in0 ? (uint32_t)g.gl + 1u : 0u);
+                const uint64_t km1 = win_push(g, kmer, i, in1 ? (uint32_t)g.gl + 9u : 0u);
+                const uint64_t kmd[2] = {km0, km1};
+                const bool wantd[2] = {in0, in1};
+                bool hitd[2];
+                g_lookup_n<2>(g, set, kmd, wantd, hitd);
+                const uint32_t gm = g_ballot(g, in0 && hitd[0]) | (g_ballot(g, in1 && hitd[1]) << 8);
+                const uint32_t vm = (1u << n) - 1u;
+                const uint32_t trig = ~gm & ((gm << 1) | (previous ? 1u : 0u)) & vm; // mod.rs:73
+                if (trig == 0) {
+                    const uint32_t last = n - 1;
+                    kmer = g_shfl64(g, last < 8 ? km0 : km1, (int)(last & 7));
+                    previous = (gm >> last) & 1u; // mod.rs:99
+                    i += n;
+                    d -= n;
+                    if (d == 0 && i < g.len) canon = previous == g_bm_bit(g, i - 1);
+                } else {
+                    const uint32_t l = (uint32_t)(__ffs(trig) - 1);
+                    kmer = g_shfl64(g, l < 8 ? km0 : km1, (int)(l & 7));
+                    i += l;
+                    d -= l + 1;
+                    if (!win_covers(g, i, 32u)) g_load_win(g, i - k + 1);
+                    at_event = true;
+                    adv = false;
+                }
+            }
+            if (adv && i >= g.len) {
+                done = true;
+                adv = false;
+            }
+            if (adv && d == 0 && !canon) {
+                // first position after a dirty window: `previous` is the last dirty lookup
+                const bool Si = g_bm_bit(g, i);
+                if (Si || !previous) { // no event here (mod.rs:99-102)
+                    previous = Si;
+                    i += 1;
+                    canon = true;
+                } else {
+                    at_event = clean_event = true;
+                    adv = false;
+                }
+            }
+            if (adv && i >= g.len) {
+                done = true;
+                adv = false;
+            }
+            if (adv && d == 0 && canon) {
+                uint32_t j = limit;
+                if (i < limit) j = g_find_transition(g, i, previous, limit);
+                if (j >= limit) { // clean visit at or after the nominal end
+                    if (i < limit) i = limit;
+                    done = true;
+                } else {
+                    i = j;
+                    at_event = clean_event = true;
+                }
+                adv = false;
+            }
+        }
+
+        // ---- pieces that ended
+        if (done) {
+            SegRec rec;
+            rec.q_exit = i;
+            g_flush_copy(g, i < g.len ? i : g.len);
+            rec.horizon = horizon;
+            rec.out_len = g.o;
+            rec.bad = g.o > SEG_CAP ? 1u : 0u;
+            __syncwarp(g.gmask);
+            if (g.gl == 0) recs[sg] = rec;
+            active = false;
+        }
+
+        // ---- events: solid -> weak transition at input position i; kmer ends with in[i]
+        if (at_event) {
+            if (clean_event) {
+                g_load_win(g, i - k + 1);
+                kmer = win_extract(g, i - k + 1, k);
+            }
+            const Corr cr = g_exist_correct_error<NS>(g, set, kmer, i, c);
+            if (!cr.some) { // mod.rs:90-96
+                previous = false;
+                i += 1;
+                if (d == 0 && i < g.len) canon = !g_bm_bit(g, i - 1);
+            } else { // mod.rs:74-89
+                if (horizon == NO_HORIZON) horizon = i;
+                g_flush_copy(g, i);
+                kmer >>= 2;
+                for (int e = (int)cr.n_emit - 1; e >= 0; e--) {
+                    const uint32_t code = (cr.codes >> (2 * e)) & 3u;
+                    kmer = push(kmer, code, g.mask);
+                    if (g.gl == 0 && g.o < SEG_CAP) g.out[g.o] = bit2nuc(code);
+                    g.o += 1;
+                }
+                previous = true;
+                i += cr.offset;
+                g.copy_from = i;
+                d = k - 1;
+                canon = false;
+            }
+        }
+    }
+    uint32_t gets = __reduce_add_sync(FULL, g.n_get);
+    if ((threadIdx.x & 31) == 0 && gets) atomicAdd(reinterpret_cast<unsigned long long *>(flags + 2), (unsigned long long)gets);
+}
+
 template <class K> static int occupancy_warps(brgpu_ctx *ctx, K kernel) {
     int blocks_per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, SCAN_WARPS_PER_BLOCK * 32, 0) !=
@@ -1425,10 +2054,25 @@ static void launch_scan_method(brgpu_ctx *ctx, const Layout &L, const uint8_t *d
     };
     {
         ProfScope ps(ctx, spec_name, n_bases_hint * 2.0);
-        scan_spec_kernel<M, KT><<<grid_for_warps((uint64_t)occupancy_warps(ctx, scan_spec_kernel<M, KT>), scan_max_segments(L)),
-                              threads, 0, ctx->stream>>>(d_in, d_len_in, L.d_slot_off, d_bitmap, w.d_seg_first,
-                                                         (uint32_t)L.n, w.d_seg_out, (SegRec *)w.d_seg_recs,
-                                                         ctx->d_flags, sv, p, d_scratch, scratch_per_warp);
+        // One runs four segments per warp (1.67 -> 1.44 ms per launch on the E. coli config); for Two
+        // the same scheme measured slower than a warp per segment (its rounds are already lane-filling:
+        // 2.37 vs 1.72 ms), so it is off unless asked for.  BRGPU_SCAN=warp|groups overrides (A/B, tests).
+        const char *mode = getenv("BRGPU_SCAN");
+        const bool force_warp = mode && mode[0] == 'w', force_groups = mode && mode[0] == 'g';
+        if ((M == BRGPU_ONE && !force_warp) || (M == BRGPU_TWO && force_groups)) {
+            // four segments per warp: a quarter of the warps for the same number of segments in flight
+            constexpr int MG = (M == BRGPU_ONE || M == BRGPU_TWO) ? M : BRGPU_ONE;
+            const uint64_t groups = scan_max_segments(L);
+            scan_spec8_kernel<MG, KT><<<grid_for_warps((uint64_t)occupancy_warps(ctx, scan_spec8_kernel<MG, KT>), (groups + 3) / 4),
+                                        threads, 0, ctx->stream>>>(d_in, d_len_in, L.d_slot_off, d_bitmap, w.d_seg_first,
+                                                                   (uint32_t)L.n, w.d_seg_out, (SegRec *)w.d_seg_recs,
+                                                                   ctx->d_flags, sv, p);
+        } else {
+            scan_spec_kernel<M, KT><<<grid_for_warps((uint64_t)occupancy_warps(ctx, scan_spec_kernel<M, KT>), scan_max_segments(L)),
+                                      threads, 0, ctx->stream>>>(d_in, d_len_in, L.d_slot_off, d_bitmap, w.d_seg_first,
+                                                                 (uint32_t)L.n, w.d_seg_out, (SegRec *)w.d_seg_recs,
+                                                                 ctx->d_flags, sv, p, d_scratch, scratch_per_warp);
+        }
     }
     {
         ProfScope ps(ctx, merge_name, n_bases_hint * 2.0);

@@ -276,3 +276,27 @@ def test_large_k_sets_correct_like_the_oracle_on_every_lookup_path(gpu, oracle, 
             compare_batches(f"k={k} {name} no_compact={no_compact}", got, got_off, exp, exp_off, seq, off)
         counted.free()
         loaded.free()
+
+
+@pytest.mark.parametrize("mode", ["warp", "groups"])
+def test_both_scan_kernels_give_the_oracle_bytes(gpu, oracle, fixture_sets, fixture_reads, mode, monkeypatch):
+    """One and Two exist as a warp-per-segment kernel and as a four-segments-per-warp kernel
+    (8-lane groups); the library picks per method.  Both must reproduce the oracle on the
+    reference's reads (chained, reversed pass on) and on a dense random case."""
+    br, ctx = gpu
+    monkeypatch.setenv("BRGPU_SCAN", mode)
+    gs, os_ = fixture_sets
+    seq, off = fixture_reads
+    ids = [oracle.METHOD_IDS[m] for m in ("one", "two")]
+    exp, exp_off = os_.run_correction(ids, seq, off, confirm=5, max_search=7, threads=8)
+    got, got_off = br.correct_batch(br.build_methods(["one", "two"], gs, 5, 7), seq, off)
+    compare_batches(f"fixture one+two ({mode})", got, got_off, exp, exp_off, seq, off)
+    rng = np.random.default_rng(99)
+    genome, rseq, roff = random_case(rng, 9, 3000, 300, 0.12)
+    rs = br.Pcon.new(ctx, 9)
+    rs.insert_all_kmers(genome.tobytes())
+    ro = oracle.Solid.from_bitfield(9, rs.bitfield())
+    for c in (2, 7):  # 7: more than 24 scenario items, the unbatched rounds
+        exp, exp_off = ro.run_correction(ids, rseq, roff, confirm=c, max_search=7, threads=8)
+        got, got_off = br.correct_batch(br.build_methods(["one", "two"], rs, c, 7), rseq, roff)
+        compare_batches(f"random one+two c={c} ({mode})", got, got_off, exp, exp_off, rseq, roff)
