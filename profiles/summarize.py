@@ -11,9 +11,13 @@ import subprocess
 import sys
 from pathlib import Path
 
+import os
+
 ROOT = Path(__file__).resolve().parent.parent
 tag = sys.argv[1]
-out_dir = ROOT / "profiles"
+# SUMMARY_OUT: where the summaries go (default profiles/; on the GPU box gpurun_out/, so that only
+# the small text files travel back); NCU_REP_DIR: where prof_<tag>.ncu-rep lives
+out_dir = Path(os.environ.get("SUMMARY_OUT", ROOT / "profiles"))
 
 METRICS = [
     "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__sectors_read.sum",
@@ -50,7 +54,7 @@ if launch_csv.exists():
             f.write(f"{n:34s} {c:8d} {v / 1e6:10.3f} {v / 1e6 / c:10.4f} {v / tot:7.1%}\n")
     print((out_dir / f"launches_{tag}.txt").read_text())
 
-rep = ROOT / "gpurun_out" / f"prof_{tag}.ncu-rep"
+rep = Path(os.environ.get("NCU_REP_DIR", ROOT / "gpurun_out")) / f"prof_{tag}.ncu-rep"
 if rep.exists():
     raw = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
@@ -71,15 +75,17 @@ if rep.exists():
     import re
 
     def bench_name(kernel):
-        m = re.match(r"(?:void )?(?:brgpu::)?(\w+?)(?:_kernel)?(?:<(?:\(int\))?(\d)>)?$", kernel.strip())
+        """ncu's kernel name -> the name bench.py reports (scan_spec8_kernel<0, 17> -> scan_one ...)."""
+        m = re.match(r"(?:void )?(?:brgpu::)?(\w+?)(?:_kernel)?(?:<([^>]*)>)?$", kernel.strip())
         if not m:
             return kernel
-        base, meth = m.group(1), m.group(2)
+        base = m.group(1)
+        args = [a.strip().replace("(int)", "") for a in (m.group(2) or "").split(",") if a.strip()]
         methods = ["one", "two", "graph", "greedy", "gap_size"]
-        if base == "scan_spec" and meth is not None:
-            return "scan_" + methods[int(meth)]
-        if base == "scan_merge" and meth is not None:
-            return "merge_" + methods[int(meth)]
+        if base in ("scan_spec", "scan_spec8") and args:
+            return "scan_" + methods[int(args[0])]
+        if base == "scan_merge" and args:
+            return "merge_" + methods[int(args[0])]
         return base
 
     def to_bytes(val, unit):
