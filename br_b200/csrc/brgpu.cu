@@ -576,9 +576,11 @@ static void summary_geometry(int k, int *shift, uint64_t *bytes) {
     *bytes = (((n_bytes << 3) >> sh) + 7) / 8;
 }
 
-// The rank-compacted copy pays off while its blocks stay L2 resident next to the 8 B-per-group
-// directory (B200: 126 MB of L2): at most this many bytes of occupied blocks.
-static const uint64_t COMPACT_MAX_BLOCK_BYTES = 64ULL << 20;
+// The rank-compacted copy pays off most while directory + blocks stay L2 resident (B200: 126 MB;
+// E. coli config 32 + 37 MB).  Beyond that a positive lookup still costs one DRAM access — as it
+// does in the bitfield — but into an array 3-30x smaller, with the directory answering every
+// negative lookup from L2, so it is built as long as the blocks take less than half the bitfield.
+static uint64_t compact_max_block_bytes(const brgpu_set *s) { return s->n_bytes / 2; }
 
 static void compact_release(brgpu_set *s) {
     if (s->d_dir) big_free(s->ctx, s->d_dir, s->dir_bytes);
@@ -621,7 +623,7 @@ static int build_compact(brgpu_set *s) {
         return fail(ctx, BRGPU_E_CUDA, "rank directory", e);
     }
     s->n_occupied = ctx->h_pinned[300];
-    if (s->n_occupied * 8 <= COMPACT_MAX_BLOCK_BYTES) {
+    if (s->n_occupied * 8 <= compact_max_block_bytes(s)) {
         // round the allocation up so that sets of similar size reuse the cached block
         const uint64_t bbytes = ((s->n_occupied * 8 + (8ULL << 20)) >> 23) << 23;
         e = big_alloc(ctx, &s->d_dir, n_words * 8);
@@ -634,7 +636,7 @@ static int build_compact(brgpu_set *s) {
             cudaGetLastError();
             compact_release(s); // not fatal: lookups fall back to summary + bitfield
         } else {
-            launch_compact_blocks(ctx, s->d_summary, d_rank, s->d_bits, n_words, s->d_dir, s->d_blocks);
+            launch_compact_blocks(ctx, s->d_summary, d_rank, s->d_bits, n_words, s->n_occupied, s->d_dir, s->d_blocks);
             s->compact_valid = true;
         }
     }

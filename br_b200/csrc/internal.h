@@ -168,7 +168,7 @@ void launch_summary_rank(brgpu_ctx *ctx, const uint32_t *d_summary, uint64_t n_w
                          uint64_t *d_scan_tmp);
 // dir[g] = {summary[g], rank[g]}; blocks[rank[g] + i] = i-th occupied 64-bit block of group g
 void launch_compact_blocks(brgpu_ctx *ctx, const uint32_t *d_summary, const uint64_t *d_rank, const uint8_t *d_bits,
-                           uint64_t n_words, void *d_dir, uint64_t *d_blocks);
+                           uint64_t n_words, uint64_t n_occupied, void *d_dir, uint64_t *d_blocks);
 
 // device view of a set for the correction kernels
 struct SetView {

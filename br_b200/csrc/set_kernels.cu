@@ -1183,11 +1183,36 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// Streaming variant for sets that occupy more than a few percent of their blocks: a warp takes one
+// group (32 blocks = one coalesced 256 B load), lanes with a non-empty block store it at
+// rank + (number of occupied blocks before theirs).  Reads the whole bitfield once, at HBM speed.
+__global__ void __launch_bounds__(256)
+    compact_blocks_stream_kernel(const uint32_t *__restrict__ summary, const uint64_t *__restrict__ rank,
+                                 const uint64_t *__restrict__ bits64, uint64_t n_words, uint2 *__restrict__ dir,
+                                 uint64_t *__restrict__ blocks) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t g = warp; g < n_words; g += n_warps) {
+        const uint64_t blk = __ldcs(bits64 + (g << 5) + (uint64_t)lane);
+        const uint32_t occ = __ldg(summary + g);
+        const uint64_t r = __ldg(rank + g);
+        if (lane == 0) dir[g] = make_uint2(occ, (uint32_t)r);
+        if ((occ >> lane) & 1u) blocks[r + (uint64_t)__popc(occ & ((1u << lane) - 1u))] = blk;
+    }
+}
+
 void launch_compact_blocks(brgpu_ctx *ctx, const uint32_t *d_summary, const uint64_t *d_rank, const uint8_t *d_bits,
-                           uint64_t n_words, void *d_dir, uint64_t *d_blocks) {
-    ProfScope ps(ctx, "compact_blocks", (double)n_words * 20.0);
-    compact_blocks_kernel<<<grid_for(ctx, n_words, 256, 8), 256, 0, ctx->stream>>>(
-        d_summary, d_rank, reinterpret_cast<const uint64_t *>(d_bits), n_words, reinterpret_cast<uint2 *>(d_dir), d_blocks);
+                           uint64_t n_words, uint64_t n_occupied, void *d_dir, uint64_t *d_blocks) {
+    const bool sparse = n_occupied * 16 < n_words * 32; // fewer than 1 block in 16 occupied: read only those
+    ProfScope ps(ctx, "compact_blocks", sparse ? (double)n_words * 20.0 + (double)n_occupied * 16.0
+                                                : (double)n_words * 268.0 + (double)n_occupied * 8.0);
+    if (sparse)
+        compact_blocks_kernel<<<grid_for(ctx, n_words, 256, 8), 256, 0, ctx->stream>>>(
+            d_summary, d_rank, reinterpret_cast<const uint64_t *>(d_bits), n_words, reinterpret_cast<uint2 *>(d_dir), d_blocks);
+    else
+        compact_blocks_stream_kernel<<<grid_for(ctx, n_words * 32, 256, 8), 256, 0, ctx->stream>>>(
+            d_summary, d_rank, reinterpret_cast<const uint64_t *>(d_bits), n_words, reinterpret_cast<uint2 *>(d_dir), d_blocks);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -276,6 +276,20 @@ def test_large_k_sets_correct_like_the_oracle_on_every_lookup_path(gpu, oracle, 
             compare_batches(f"k={k} {name} no_compact={no_compact}", got, got_off, exp, exp_off, seq, off)
         counted.free()
         loaded.free()
+    # a denser set (17 % of the 64-bit blocks occupied): the rank-compacted copy is built by the
+    # streaming kernel instead of the sparse one
+    monkeypatch.setenv("BRGPU_NO_COMPACT", "0")
+    rng = np.random.default_rng(k)
+    dense_bits = osolid.bits().copy()
+    pos = rng.integers(0, dense_bits.size * 8, size=int(dense_bits.size * 8 * 0.003), dtype=np.int64)
+    np.bitwise_or.at(dense_bits, pos >> 3, (1 << (pos & 7)).astype(np.uint8))
+    dsolid = oracle.Solid.from_bitfield(k, dense_bits)
+    sub = off[:41]
+    exp, exp_off = dsolid.run_correction(ids, seq, sub, confirm=4, max_search=7, threads=8)
+    dense = br.Pcon.from_bitfield(ctx, k, dense_bits)
+    got, got_off = br.correct_batch(br.build_methods(METHODS, dense, 4, 7), seq, sub)
+    compare_batches(f"k={k} dense set", got, got_off, exp, exp_off, seq, sub)
+    dense.free()
 
 
 @pytest.mark.parametrize("mode", ["warp", "groups"])
