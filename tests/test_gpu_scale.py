@@ -2,8 +2,8 @@
 properties over the whole result plus exact oracle comparison on a random sample of reads.
 
 The case is one GPU's shard of configs[3] (100 Mb genome, 50x reads at 12 % error, k = 17, sharded
-over 8 GPUs => 625 Mbases per GPU): more reads than the benchmark config, a solid set that no
-longer fits in L2 (the lookups take the summary + bitfield path) and count tables in the billions.
+over 8 GPUs => 625 Mbases per GPU): more reads than the benchmark config, a solid set whose
+rank-compacted copy no longer fits in L2, and counter totals in the hundreds of millions.
 """
 import numpy as np
 import pytest
