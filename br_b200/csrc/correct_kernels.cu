@@ -600,10 +600,16 @@ __device__ __forceinline__ Corr exist_correct_error(Rd &rd, uint64_t kmer, uint3
         // round 3b: the c confirmations (:35-43) of the survivors, item (r-th survivor, u = 1..c)
         const uint32_t n_alive = (uint32_t)__popc(cand);
         const uint32_t Q = n_alive * c;
+        // survivor r is scenario ids[r] (4 bits each): every surviving lane contributes its id at its
+        // rank among the survivors (cheaper than one __fns per item, which is a software loop)
+        uint64_t ids = 0;
+        if (alive) ids = (uint64_t)rd.lane << (4 * __popc(cand & ((1u << rd.lane) - 1u)));
+        ids = warp_or64(ids);
+        const uint32_t inv_c = c > 1 ? 0xffffffffu / c + 1u : 0u; // q / c by multiplication (q < 2^16)
         for (uint32_t q0 = 0; q0 < Q; q0 += 32) {
             const uint32_t q = q0 + (uint32_t)rd.lane;
-            const uint32_t r = q / c, u = q - r * c + 1u;
-            const int s = q < Q ? (int)__fns(cand, 0u, (int)r + 1) : 0;
+            const uint32_t r = c > 1 ? __umulhi(q, inv_c) : q, u = q - r * c + 1u;
+            const int s = q < Q ? (int)((ids >> (4 * r)) & 0xfu) : 0;
             const uint64_t K = shfl64(sc.K, s); // all lanes take part in the shuffles
             const uint32_t offa = __shfl_sync(FULL, sc.offa, s);
             if (q < Q && !lookup(rd, sub_push(K, offa, u))) bad |= 1u << s;
@@ -1645,10 +1651,11 @@ __device__ __forceinline__ Corr g_exist_correct_error(G8 &g, const SolidView &se
             uint64_t km[3];
             bool want[3], hit[3], is_more[3];
             int sc_of[3];
+            const uint32_t inv_per = 0xffffffffu / per + 1u; // q / per by multiplication (per >= 3, q < 24)
 #pragma unroll
             for (int h = 0; h < 3; h++) {
                 const uint32_t q = (uint32_t)g.gl + 8u * (uint32_t)h;
-                const int s = (int)(q / per);
+                const int s = (int)__umulhi(q, inv_per);
                 const uint32_t u = q - (uint32_t)s * per;
                 const Scen t = scen_one(s, K0);
                 sc_of[h] = s;
