@@ -544,9 +544,14 @@ __device__ __forceinline__ Corr exist_correct_error(Rd &rd, uint64_t kmer, uint3
         sc = scen_one(rd.lane, K0);
     } else {
         uint32_t sb[4];
+        if (use_win) { // one cut for the four bases; codes of positions >= len are zero in the window
+            const uint32_t four = (uint32_t)win_extract(rd, i, 4);
 #pragma unroll
-        for (int t = 0; t < 4; t++)
-            sb[t] = (uint32_t)t < sublen ? (use_win ? (uint32_t)win_extract(rd, i + (uint32_t)t, 1) : nuc2bit(sub[t])) : 0u;
+            for (int t = 0; t < 4; t++) sb[t] = (four >> (2 * (3 - t))) & 3u;
+        } else {
+#pragma unroll
+            for (int t = 0; t < 4; t++) sb[t] = (uint32_t)t < sublen ? nuc2bit(sub[t]) : 0u;
+        }
         // round 2: the four successor sets
         bool s = false;
         if (rd.lane < 16) {
@@ -1124,6 +1129,15 @@ struct SegRec {
     uint32_t bad;      // output did not fit into the scratch region: the piece is unusable
 };
 
+// What the merge warp decided for a spliced piece: the copy itself is done afterwards by
+// scan_splice_kernel, all pieces in parallel (a merge warp that copied its pieces one after the
+// other made the longest read the tail of the kernel).
+struct SegCopy {
+    uint64_t dst;   // byte offset in the output slot buffer
+    uint32_t skip;  // bytes of the piece's scratch region to skip
+    uint32_t n;     // bytes to copy (0: nothing — the segment was re-run, or never reached)
+};
+
 __device__ __forceinline__ bool bm_bit(const Rd &rd, uint32_t p) { return (__ldg(rd.bm + (p >> 5)) >> (p & 31)) & 1u; }
 
 // Run Corrector::correct's loop from a clean visit at `start` until the first clean visit at or
@@ -1317,7 +1331,8 @@ __global__ void __launch_bounds__(SCAN_WARPS_PER_BLOCK * 32)
                       const uint32_t *__restrict__ bitmap, const uint32_t *__restrict__ order,
                       const uint64_t *__restrict__ seg_first, uint32_t n_reads, const uint8_t *__restrict__ seg_out,
                       const SegRec *__restrict__ recs, uint32_t *__restrict__ flags, SolidView set, CorrectParams p,
-                      uint8_t *scratch, size_t scratch_per_warp, uint8_t *__restrict__ changed) {
+                      uint8_t *scratch, size_t scratch_per_warp, uint8_t *__restrict__ changed,
+                      SegCopy *__restrict__ copies) {
     const int lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (KT) p.k = KT; // compile-time k: the k-mer arithmetic below folds to immediates
@@ -1360,15 +1375,13 @@ __global__ void __launch_bounds__(SCAN_WARPS_PER_BLOCK * 32)
                     // the speculative run of this segment is in a clean visit at q: splice it in
                     const uint32_t in0 = sidx == 0 ? 0u : seg_start;     // input position of scratch byte 0
                     const uint32_t skip = first ? 0u : q - in0;          // 1:1 copy region before q
-                    const uint8_t *src = seg_out + (g0 + sidx) * SEG_CAP + skip;
                     const uint32_t n = rec.out_len - skip;
-                    if (rd.o + n <= rd.cap) {
-                        warp_copy(rd.out + rd.o, src, n, lane);
-                    } else {
-                        for (uint32_t t = lane; t < n; t += 32) {
-                            uint32_t dst = rd.o + t;
-                            if (dst < rd.cap) rd.out[dst] = src[t];
-                        }
+                    if (lane == 0) { // the bytes are moved by scan_splice_kernel; what fits if the slot overflows
+                        SegCopy cp;
+                        cp.dst = base + rd.o;
+                        cp.skip = skip;
+                        cp.n = rd.o >= rd.cap ? 0u : (rd.o + n <= rd.cap ? n : rd.cap - rd.o);
+                        copies[g0 + sidx] = cp;
                     }
                     rd.o += n;
                     q = rec.q_exit;
@@ -1708,9 +1721,14 @@ __device__ __forceinline__ Corr g_exist_correct_error(G8 &g, const SolidView &se
         win = scen_one(__ffs(cand) - 1, K0);
     } else {
         uint32_t sb[4];
+        if (use_win) {
+            const uint32_t four = (uint32_t)win_extract(g, i, 4);
 #pragma unroll
-        for (int t = 0; t < 4; t++)
-            sb[t] = (uint32_t)t < sublen ? (use_win ? (uint32_t)win_extract(g, i + (uint32_t)t, 1) : nuc2bit(sub[t])) : 0u;
+            for (int t = 0; t < 4; t++) sb[t] = (four >> (2 * (3 - t))) & 3u;
+        } else {
+#pragma unroll
+            for (int t = 0; t < 4; t++) sb[t] = (uint32_t)t < sublen ? nuc2bit(sub[t]) : 0u;
+        }
         // round 2: the four successor sets, 16 lookups = two per lane, in flight together
         uint32_t m16 = 0;
         {
@@ -2029,6 +2047,19 @@ __global__ void __launch_bounds__(SCAN_WARPS_PER_BLOCK * 32, 8)
     if ((threadIdx.x & 31) == 0 && gets) atomicAdd(reinterpret_cast<unsigned long long *>(flags + 2), (unsigned long long)gets);
 }
 
+// one warp per spliced piece: scratch region -> its place in the output slot
+__global__ void __launch_bounds__(256)
+    scan_splice_kernel(const SegCopy *__restrict__ copies, uint64_t n_seg, const uint8_t *__restrict__ seg_out,
+                       uint8_t *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t g = warp; g < n_seg; g += n_warps) {
+        const SegCopy cp = copies[g];
+        if (cp.n) warp_copy(out + cp.dst, seg_out + g * SEG_CAP + cp.skip, cp.n, lane);
+    }
+}
+
 template <class K> static int occupancy_warps(brgpu_ctx *ctx, K kernel) {
     int blocks_per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, SCAN_WARPS_PER_BLOCK * 32, 0) !=
@@ -2045,7 +2076,7 @@ int scan_grid_warps(brgpu_ctx *ctx) { return ctx->sm_count * 16 * SCAN_WARPS_PER
 
 uint64_t scan_max_segments(const Layout &L) { return L.total_slots / SEG + L.n + 1; }
 size_t scan_seg_out_bytes(const Layout &L) { return (size_t)scan_max_segments(L) * SEG_CAP; }
-size_t scan_seg_rec_bytes(const Layout &L) { return (size_t)scan_max_segments(L) * sizeof(SegRec); }
+size_t scan_seg_rec_bytes(const Layout &L) { return (size_t)scan_max_segments(L) * (sizeof(SegRec) + sizeof(SegCopy)); }
 
 template <int M, int KT>
 static void launch_scan_method(brgpu_ctx *ctx, const Layout &L, const uint8_t *d_in, const uint32_t *d_len_in,
@@ -2081,12 +2112,19 @@ static void launch_scan_method(brgpu_ctx *ctx, const Layout &L, const uint8_t *d
                                                                  ctx->d_flags, sv, p, d_scratch, scratch_per_warp);
         }
     }
+    SegCopy *d_copies = reinterpret_cast<SegCopy *>((uint8_t *)w.d_seg_recs + scan_max_segments(L) * sizeof(SegRec));
+    cudaMemsetAsync(d_copies, 0, scan_max_segments(L) * sizeof(SegCopy), ctx->stream);
     {
         ProfScope ps(ctx, merge_name, n_bases_hint * 2.0);
         scan_merge_kernel<M, KT><<<grid_for_warps((uint64_t)occupancy_warps(ctx, scan_merge_kernel<M, KT>), L.n), threads, 0,
                                ctx->stream>>>(d_in, d_len_in, d_out, d_len_out, L.d_slot_off, d_bitmap, L.d_order,
                                               w.d_seg_first, (uint32_t)L.n, w.d_seg_out, (const SegRec *)w.d_seg_recs,
-                                              ctx->d_flags, sv, p, d_scratch, scratch_per_warp, w.d_changed);
+                                              ctx->d_flags, sv, p, d_scratch, scratch_per_warp, w.d_changed, d_copies);
+        // all spliced pieces at once (the merge warps only decided where they go)
+        const uint64_t n_seg = scan_max_segments(L);
+        uint64_t blocks = (n_seg + 7) / 8, cap = (uint64_t)ctx->sm_count * 8;
+        scan_splice_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, ctx->stream>>>(d_copies, n_seg, w.d_seg_out, d_out);
+        ctx->launches += 1;
     }
 }
 
