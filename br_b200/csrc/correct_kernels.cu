@@ -1526,11 +1526,18 @@ __device__ __forceinline__ void g_load_win(G8 &g, uint32_t origin) {
     const uint8_t *p = g.in + origin + 8u * (uint32_t)g.gl;
     const uint32_t a = (uint32_t)((uintptr_t)p & 3u);
     const uint32_t *q = reinterpret_cast<const uint32_t *>(p - a);
-    const uint32_t x0 = __ldg(q), x1 = __ldg(q + 1), x2 = a ? __ldg(q + 2) : 0u;
-    const uint32_t b0 = __funnelshift_r(x0, x1, 8 * a), b1 = __funnelshift_r(x1, x2, 8 * a);
-    uint32_t v16 = (pack4(b0) << 8) | pack4(b1);
     const uint32_t first = origin + 8u * (uint32_t)g.gl;
     const uint32_t nv = first >= g.len ? 0u : (g.len - first < 8u ? g.len - first : 8u);
+    // a lane whose 8 bytes start inside the read touches at most 11 bytes past its first one, all
+    // inside the slot's slack (>= 64 bytes); lanes past the end of the read do not load at all
+    uint32_t x0 = 0, x1 = 0, x2 = 0;
+    if (nv) {
+        x0 = __ldg(q);
+        x1 = __ldg(q + 1);
+        if (a) x2 = __ldg(q + 2);
+    }
+    const uint32_t b0 = __funnelshift_r(x0, x1, 8 * a), b1 = __funnelshift_r(x1, x2, 8 * a);
+    uint32_t v16 = (pack4(b0) << 8) | pack4(b1);
     v16 &= (0xffffu << (16u - 2u * nv)) & 0xffffu;
     const uint32_t o16 = __shfl_xor_sync(g.gmask, v16, 1, 8);
     const uint32_t t32 = (g.gl & 1) ? ((o16 << 16) | v16) : ((v16 << 16) | o16);
@@ -2075,7 +2082,7 @@ template <class K> static int occupancy_warps(brgpu_ctx *ctx, K kernel) {
 int scan_grid_warps(brgpu_ctx *ctx) { return ctx->sm_count * 16 * SCAN_WARPS_PER_BLOCK; }
 
 uint64_t scan_max_segments(const Layout &L) { return L.total_slots / SEG + L.n + 1; }
-size_t scan_seg_out_bytes(const Layout &L) { return (size_t)scan_max_segments(L) * SEG_CAP; }
+size_t scan_seg_out_bytes(const Layout &L) { return (size_t)scan_max_segments(L) * SEG_CAP + 64; } // + slack: warp_copy reads whole source words
 size_t scan_seg_rec_bytes(const Layout &L) { return (size_t)scan_max_segments(L) * (sizeof(SegRec) + sizeof(SegCopy)); }
 
 template <int M, int KT>
