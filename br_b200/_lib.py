@@ -10,7 +10,7 @@ _SO = Path(__file__).resolve().parent / "libbrgpu.so"
 
 OK, E_INVALID, E_NO_DEVICE, E_CUDA, E_NOMEM, E_OVERFLOW, E_NO_THRESHOLD, E_NEED_ABUNDANCE = range(8)
 ONE, TWO, GRAPH, GREEDY, GAP_SIZE = range(5)
-ABUNDANCE_EXPLICIT, ABUNDANCE_FIRST_MINIMUM = 0, 1
+ABUNDANCE_EXPLICIT, ABUNDANCE_FIRST_MINIMUM, ABUNDANCE_RAREFACTION, ABUNDANCE_PERCENT_AT_MOST, ABUNDANCE_PERCENT_AT_LEAST = range(5)
 
 _STATUS = {
     E_INVALID: "invalid argument",
@@ -43,6 +43,7 @@ SIGNATURES = {
     "brgpu_counts_add_reads": (C.c_int, [vp, vp]),
     "brgpu_counts_spectrum": (C.c_int, [vp, vp]),
     "brgpu_spectrum_first_minimum": (C.c_int, [vp]),
+    "brgpu_spectrum_threshold": (C.c_int, [vp, C.c_int, C.c_double]),
     "brgpu_counts_download": (C.c_int, [vp, vp, u64]),
     "brgpu_counts_device_ptr": (vp, [vp]),
     "brgpu_counts_len": (u64, [vp]),
@@ -50,6 +51,8 @@ SIGNATURES = {
     "brgpu_set_from_counts": (C.c_int, [vp, C.c_int, pvp]),
     "brgpu_set_from_reads": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, pvp]),
     "brgpu_set_from_host_reads": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, vp, u64, pvp]),
+    "brgpu_set_from_reads_ex": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_double, vp, pvp]),
+    "brgpu_set_from_host_reads_ex": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_double, vp, vp, u64, pvp]),
     "brgpu_set_from_bitfield": (C.c_int, [vp, C.c_int, vp, u64, pvp]),
     "brgpu_set_from_solid_payload": (C.c_int, [vp, vp, u64, pvp]),
     "brgpu_set_new": (C.c_int, [vp, C.c_int, pvp]),

@@ -536,6 +536,35 @@ extern "C" int brgpu_spectrum_first_minimum(const uint64_t hist[256]) {
     return -1;
 }
 
+// pcon Spectrum::get_threshold for the percent-driven methods (recalled from pcon @0184ae77, which
+// is not vendored; no reference test pins them — see DESIGN.md §3):
+//   Rarefaction(limit):    first bin whose count / running sum of index * count is below limit
+//   PercentAtLeast(p):     first bin at which the running share of index * count exceeds p
+//   PercentAtMost(p):      the bin before that one
+extern "C" int brgpu_spectrum_threshold(const uint64_t hist[256], int selection, double percent) {
+    if (!hist) return -1;
+    if (selection == BRGPU_ABUNDANCE_FIRST_MINIMUM) return brgpu_spectrum_first_minimum(hist);
+    if (selection == BRGPU_ABUNDANCE_RAREFACTION) {
+        uint64_t running = 0;
+        for (int i = 0; i < 256; i++) {
+            running += (uint64_t)i * hist[i];
+            if ((double)hist[i] / (double)running < percent) return i;
+        }
+        return -1;
+    }
+    if (selection == BRGPU_ABUNDANCE_PERCENT_AT_MOST || selection == BRGPU_ABUNDANCE_PERCENT_AT_LEAST) {
+        uint64_t total = 0, running = 0;
+        for (int i = 0; i < 256; i++) total += (uint64_t)i * hist[i];
+        for (int i = 0; i < 256; i++) {
+            running += (uint64_t)i * hist[i];
+            if ((double)running / (double)total > percent)
+                return selection == BRGPU_ABUNDANCE_PERCENT_AT_LEAST ? i : (i > 0 ? i - 1 : -1);
+        }
+        return -1;
+    }
+    return -1;
+}
+
 extern "C" int brgpu_counts_download(brgpu_counts *c, uint8_t *out_host, uint64_t n) {
     if (!c || !out_host) return BRGPU_E_INVALID;
     brgpu_ctx *ctx = c->ctx;
@@ -795,8 +824,8 @@ static cudaError_t read_hist(brgpu_ctx *ctx, uint64_t hist[256]) {
     return e;
 }
 
-static int set_from_reads_bucketed(brgpu_ctx *ctx, int k, int abundance, int selection, const brgpu_reads *reads,
-                                   brgpu_set **out) {
+static int set_from_reads_bucketed(brgpu_ctx *ctx, int k, int abundance, int selection, double percent,
+                                   const brgpu_reads *reads, brgpu_set **out) {
     brgpu_kmers *km = nullptr;
     int st = kmers_create(ctx, k, reads, &km);
     if (st != BRGPU_OK) return st;
@@ -821,14 +850,14 @@ static int set_from_reads_bucketed(brgpu_ctx *ctx, int k, int abundance, int sel
         s->summary_shift = shift;
     }
     uint64_t hist[256];
-    if (selection == BRGPU_ABUNDANCE_FIRST_MINIMUM) {
+    if (selection != BRGPU_ABUNDANCE_EXPLICIT) {
         // the threshold depends on the spectrum: one counting sweep without output first
         cudaMemsetAsync(ctx->d_hist, 0, 256 * sizeof(uint64_t), ctx->stream);
         launch_bucket_count(ctx, km->d_res, km->d_base, km->n_buckets, 0, nullptr, nullptr, 0, ctx->d_hist,
                             km->n_kmers_hint);
         e = read_hist(ctx, hist);
         if (e == cudaSuccess) {
-            abundance = brgpu_spectrum_first_minimum(hist);
+            abundance = brgpu_spectrum_threshold(hist, selection, percent);
             if (abundance < 0) st = fail(ctx, BRGPU_E_NO_THRESHOLD, "can't compute the abundance threshold");
         }
     }
@@ -990,31 +1019,31 @@ extern "C" int brgpu_kmers_offsets_at(brgpu_kmers *km, const uint64_t *buckets_h
     return BRGPU_OK;
 }
 
-extern "C" int brgpu_set_from_reads(brgpu_ctx *ctx, int k, int abundance, int selection, const brgpu_reads *reads,
-                                    brgpu_set **out) {
+extern "C" int brgpu_set_from_reads_ex(brgpu_ctx *ctx, int k, int abundance, int selection, double percent,
+                                       const brgpu_reads *reads, brgpu_set **out) {
     if (!ctx || !out || !reads) return BRGPU_E_INVALID;
     *out = nullptr;
     if (!k_supported(k)) return fail(ctx, BRGPU_E_INVALID, "k must be odd and in 3..=19");
     if (selection == BRGPU_ABUNDANCE_EXPLICIT && abundance < 0)
         return fail(ctx, BRGPU_E_NEED_ABUNDANCE, "need an abundance threshold or an abundance method");
-    if (selection != BRGPU_ABUNDANCE_EXPLICIT && selection != BRGPU_ABUNDANCE_FIRST_MINIMUM)
+    if (selection < BRGPU_ABUNDANCE_EXPLICIT || selection > BRGPU_ABUNDANCE_PERCENT_AT_LEAST)
         return fail(ctx, BRGPU_E_INVALID, "unknown abundance selection");
     if (selection == BRGPU_ABUNDANCE_EXPLICIT && abundance > 255)
         return fail(ctx, BRGPU_E_INVALID, "abundance must be in 0..=255");
     if (reads->ctx != ctx) return fail(ctx, BRGPU_E_INVALID, "reads belong to another context");
     cudaSetDevice(ctx->device);
-    if (bucketed_applicable(k, reads)) return set_from_reads_bucketed(ctx, k, abundance, selection, reads, out);
+    if (bucketed_applicable(k, reads)) return set_from_reads_bucketed(ctx, k, abundance, selection, percent, reads, out);
     // table path: Counter::new + count_fasta + Spectrum + Solid::from_count, literally
     brgpu_counts *c = nullptr;
     int st = brgpu_counts_create(ctx, k, &c);
     if (st != BRGPU_OK) return st;
     st = brgpu_counts_add_reads(c, reads);
     if (st == BRGPU_OK) {
-        if (selection == BRGPU_ABUNDANCE_FIRST_MINIMUM) {
+        if (selection != BRGPU_ABUNDANCE_EXPLICIT) {
             uint64_t hist[256];
             st = brgpu_counts_spectrum(c, hist);
             if (st == BRGPU_OK) {
-                abundance = brgpu_spectrum_first_minimum(hist);
+                abundance = brgpu_spectrum_threshold(hist, selection, percent);
                 if (abundance < 0) st = fail(ctx, BRGPU_E_NO_THRESHOLD, "can't compute the abundance threshold");
             }
         }
@@ -1024,17 +1053,28 @@ extern "C" int brgpu_set_from_reads(brgpu_ctx *ctx, int k, int abundance, int se
     return st;
 }
 
-extern "C" int brgpu_set_from_host_reads(brgpu_ctx *ctx, int k, int abundance, int selection, const uint8_t *seq_host,
-                                         const uint64_t *offsets_host, uint64_t n_reads, brgpu_set **out) {
+extern "C" int brgpu_set_from_reads(brgpu_ctx *ctx, int k, int abundance, int selection, const brgpu_reads *reads,
+                                    brgpu_set **out) {
+    return brgpu_set_from_reads_ex(ctx, k, abundance, selection, 0.0, reads, out);
+}
+
+extern "C" int brgpu_set_from_host_reads_ex(brgpu_ctx *ctx, int k, int abundance, int selection, double percent,
+                                            const uint8_t *seq_host, const uint64_t *offsets_host, uint64_t n_reads,
+                                            brgpu_set **out) {
     if (!ctx || !out) return BRGPU_E_INVALID;
     *out = nullptr;
     if (!k_supported(k)) return fail(ctx, BRGPU_E_INVALID, "k must be odd and in 3..=19");
     brgpu_reads *R = nullptr;
     int st = brgpu_reads_upload(ctx, seq_host, offsets_host, n_reads, &R);
     if (st != BRGPU_OK) return st;
-    st = brgpu_set_from_reads(ctx, k, abundance, selection, R, out);
+    st = brgpu_set_from_reads_ex(ctx, k, abundance, selection, percent, R, out);
     brgpu_reads_free(R);
     return st;
+}
+
+extern "C" int brgpu_set_from_host_reads(brgpu_ctx *ctx, int k, int abundance, int selection, const uint8_t *seq_host,
+                                         const uint64_t *offsets_host, uint64_t n_reads, brgpu_set **out) {
+    return brgpu_set_from_host_reads_ex(ctx, k, abundance, selection, 0.0, seq_host, offsets_host, n_reads, out);
 }
 
 extern "C" int brgpu_set_from_bitfield(brgpu_ctx *ctx, int k, const uint8_t *bits_host, uint64_t n_bytes,

@@ -50,19 +50,22 @@ def bucket_bounds(n_buckets, world, rank):
     return per * rank, (n_buckets if rank == world - 1 else per * (rank + 1))
 
 
-def _pick_abundance(ops, abundance, abundance_selection, spectrum_of_range):
+def _pick_abundance(ops, abundance, abundance_selection, spectrum_of_range, percent=0.0):
     if abundance is not None:
         return int(abundance)
-    if abundance_selection not in ("first-minimum", "first_minimum"):
+    if abundance_selection is None:
         raise ValueError("need an abundance threshold or an abundance method")
     hist = ops.all_reduce_sum(spectrum_of_range())  # 2 KiB
-    a = ops.first_minimum(hist)
+    if abundance_selection in ("first-minimum", "first_minimum"):
+        a = ops.first_minimum(hist)
+    else:
+        a = ops.spectrum_threshold(hist, abundance_selection, percent)
     if a is None:
         raise RuntimeError("can't compute the abundance threshold")
     return int(a)
 
 
-def build_set_sharded(ops, k, abundance=None, abundance_selection=None):
+def build_set_sharded(ops, k, abundance=None, abundance_selection=None, percent=0.0):
     """Runs the exchange protocol; returns whatever `ops.finish()` returns (the replicated set).
 
     k >= 15: no count tables at all.  Every rank partitions its own k-mers into buckets of 2^15
@@ -70,11 +73,11 @@ def build_set_sharded(ops, k, abundance=None, abundance_selection=None):
     partitions (the peers' residues are read over NVLink inside the counting kernel).
     k < 15: the literal table protocol (private tables, saturating merge of the owned slice)."""
     if k >= 15 and getattr(ops, "supports_kmers", False):
-        return _build_from_kmers(ops, k, abundance, abundance_selection)
-    return _build_from_tables(ops, k, abundance, abundance_selection)
+        return _build_from_kmers(ops, k, abundance, abundance_selection, percent)
+    return _build_from_tables(ops, k, abundance, abundance_selection, percent)
 
 
-def _build_from_kmers(ops, k, abundance, abundance_selection):
+def _build_from_kmers(ops, k, abundance, abundance_selection, percent=0.0):
     world, rank = ops.world, ops.rank
     n_buckets = 1 << (2 * k - 1 - BUCKET_BITS)
     b0, b1 = bucket_bounds(n_buckets, world, rank)
@@ -82,7 +85,7 @@ def _build_from_kmers(ops, k, abundance, abundance_selection):
     handles = ops.exchange_kmer_handles()    # all-gather of the IPC handles
     ops.barrier()                            # every partition is complete before anyone reads it
     ops.open_peers(handles)
-    abundance = _pick_abundance(ops, abundance, abundance_selection, lambda: ops.count_range(b0, b1, None))
+    abundance = _pick_abundance(ops, abundance, abundance_selection, lambda: ops.count_range(b0, b1, None), percent)
     ops.count_range(b0, b1, abundance)       # count + threshold the owned range (peer data over NVLink)
     bounds = [tuple(x << BUCKET_BITS for x in bucket_bounds(n_buckets, world, r)) for r in range(world)]
     ops.all_gather_bitfield(b0 << BUCKET_BITS, b1 << BUCKET_BITS, 1 << (2 * k - 1), bounds)
@@ -90,7 +93,7 @@ def _build_from_kmers(ops, k, abundance, abundance_selection):
     return ops.finish(abundance)
 
 
-def _build_from_tables(ops, k, abundance, abundance_selection):
+def _build_from_tables(ops, k, abundance, abundance_selection, percent=0.0):
     world, rank = ops.world, ops.rank
     n = 1 << (2 * k - 1)
     begin, end = slice_bounds(n, world, rank)
@@ -98,7 +101,7 @@ def _build_from_tables(ops, k, abundance, abundance_selection):
     handles = ops.exchange_handles()         # all-gather of the 64-byte IPC handles
     ops.barrier()                            # every table is complete before anyone reads it
     ops.merge_slice(handles, begin, end)     # saturating reduce of slice `rank` over NVLink
-    abundance = _pick_abundance(ops, abundance, abundance_selection, lambda: ops.spectrum_slice(begin, end))
+    abundance = _pick_abundance(ops, abundance, abundance_selection, lambda: ops.spectrum_slice(begin, end), percent)
     ops.threshold_slice(abundance, begin, end)
     ops.all_gather_bitfield(begin, end, n, [slice_bounds(n, world, r) for r in range(world)])  # NCCL all-gather
     ops.barrier()                            # peers are done reading this rank's table
@@ -238,6 +241,12 @@ class GpuOps:
         from .set import Counter
 
         return Counter.first_minimum(hist)
+
+    @staticmethod
+    def spectrum_threshold(hist, abundance_selection, percent):
+        from .set import spectrum_threshold
+
+        return spectrum_threshold(hist, abundance_selection, percent)
 
     def threshold_slice(self, abundance, begin, end):
         check(lib.brgpu_set_threshold_slice(self.set._h, self.counter._h, abundance, begin, end), self.ctx._h)

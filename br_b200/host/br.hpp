@@ -132,8 +132,8 @@ class KmerSet {
     virtual uint8_t k() const = 0;
 };
 
-// cli::AbundanceSelection (src/cli.rs:227-241) as far as the ABI implements it
-enum class AbundanceSelection { None, FirstMinimum };
+// cli::AbundanceSelection (src/cli.rs:227-241); None = no method given
+enum class AbundanceSelection { None, FirstMinimum, Rarefaction, PercentMost, PercentLeast };
 
 // set::Pcon (src/set/pcon.rs:13-196): the dense canonical bitfield, resident in HBM
 class Pcon : public KmerSet {
@@ -169,13 +169,21 @@ class Pcon : public KmerSet {
     // the `fasta` sub-command (src/main.rs:72-115): Counter::new(k) + count_fasta + count2solid.
     // abundance < 0 means "not given" (Option::None); an explicit abundance wins (src/main.rs:96).
     static std::unique_ptr<Pcon> from_count(const Context &ctx, const fasta::Chunk &reads, int k, int abundance,
-                                            AbundanceSelection selection) {
+                                            AbundanceSelection selection, double percent = 0.0) {
         k = k - (!(k & 1) & 1); // Fasta::kmer_size forces k odd (src/cli.rs:277-279)
         int sel = BRGPU_ABUNDANCE_EXPLICIT;
-        if (abundance < 0 && selection == AbundanceSelection::FirstMinimum) sel = BRGPU_ABUNDANCE_FIRST_MINIMUM;
+        if (abundance < 0) { // count2solid's match (src/main.rs:95-110): an explicit abundance wins
+            switch (selection) {
+            case AbundanceSelection::FirstMinimum: sel = BRGPU_ABUNDANCE_FIRST_MINIMUM; break;
+            case AbundanceSelection::Rarefaction: sel = BRGPU_ABUNDANCE_RAREFACTION; break;
+            case AbundanceSelection::PercentMost: sel = BRGPU_ABUNDANCE_PERCENT_AT_MOST; break;
+            case AbundanceSelection::PercentLeast: sel = BRGPU_ABUNDANCE_PERCENT_AT_LEAST; break;
+            case AbundanceSelection::None: break;
+            }
+        }
         brgpu_set *h = nullptr;
-        ctx.check(brgpu_set_from_host_reads(ctx.handle(), k, abundance, sel, reads.seq.data(), reads.offsets.data(),
-                                            reads.size(), &h));
+        ctx.check(brgpu_set_from_host_reads_ex(ctx.handle(), k, abundance, sel, percent, reads.seq.data(),
+                                               reads.offsets.data(), reads.size(), &h));
         return std::make_unique<Pcon>(ctx, h);
     }
 

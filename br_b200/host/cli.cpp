@@ -1,7 +1,7 @@
 // brgpu-cli — br's command line (src/cli.rs, src/main.rs:17-58) in front of libbrgpu.so.
 //
 //   brgpu-cli [-i IN..] [-o OUT..] [-s] [-c METHOD..] [-C CONFIRM] [-M MAX_SEARCH] [-b N] [-t N] [-d DEVICE] [-q] [-v..]
-//             fasta -i READS.. -k K [-a N] [first-minimum]            src/main.rs:72-85
+//             fasta -i READS.. -k K [-a N] [first-minimum | rarefaction P | percent-most P | percent-least P]   src/main.rs:72-115
 //           | solid -i FILE -f solid|fasta [-k K]                      src/main.rs:117-145
 //           | large-kmer -i FILE -f fasta -k K   (odd K <= 19 only: the dense set; src/main.rs:147-163)
 //           | count ...                          (rejected: no fixture pins pcon's count-file format)
@@ -37,6 +37,7 @@ struct Args {
     int k = -1;
     int abundance = -1;
     std::string selection;
+    double percent = 0.0;
     std::string format;
 };
 
@@ -114,7 +115,10 @@ Args parse(int argc, char **argv) {
         else if (t == "first-minimum") a.selection = t;
         else if (t == "rarefaction" || t == "percent-most" || t == "percent-least") {
             a.selection = t;
-            (void)value(t);
+            const std::string v = value(t);
+            char *end = nullptr;
+            a.percent = std::strtod(v.c_str(), &end);
+            if (v.empty() || *end) usage_error("invalid value '" + v + "' for '<PERCENT>'");
         } else usage_error("unexpected argument '" + t + "' for '" + a.sub + "'");
     }
     if (!a.corrections_given) // src/cli.rs:121-131
@@ -141,11 +145,12 @@ std::unique_ptr<br::set::Pcon> build_set(const br::Context &ctx, const Args &a) 
         if (a.k < 0) usage_error("the following required arguments were not provided: --kmer-size");
         AbundanceSelection sel = AbundanceSelection::None;
         if (a.selection == "first-minimum") sel = AbundanceSelection::FirstMinimum;
-        else if (!a.selection.empty() && a.abundance < 0)
-            throw std::runtime_error("abundance selection '" + a.selection + "' is not supported by brgpu (use -a or first-minimum)");
+        else if (a.selection == "rarefaction") sel = AbundanceSelection::Rarefaction;
+        else if (a.selection == "percent-most") sel = AbundanceSelection::PercentMost;
+        else if (a.selection == "percent-least") sel = AbundanceSelection::PercentLeast;
         br::fasta::Chunk reads;
         read_all(a.sub_inputs, reads);
-        return Pcon::from_count(ctx, reads, a.k, a.abundance, sel);
+        return Pcon::from_count(ctx, reads, a.k, a.abundance, sel, a.percent);
     }
     if (a.sub == "solid") { // src/main.rs:117-145
         if (a.format == "solid") return Pcon::from_pcon_solid(ctx, a.sub_inputs[0]);

@@ -28,6 +28,33 @@ def seq2bit(seq: bytes) -> int:
     return kmer
 
 
+SELECTIONS = {
+    "first-minimum": _lib.ABUNDANCE_FIRST_MINIMUM, "first_minimum": _lib.ABUNDANCE_FIRST_MINIMUM,
+    "rarefaction": _lib.ABUNDANCE_RAREFACTION,
+    "percent-most": _lib.ABUNDANCE_PERCENT_AT_MOST, "percent_most": _lib.ABUNDANCE_PERCENT_AT_MOST,
+    "percent-least": _lib.ABUNDANCE_PERCENT_AT_LEAST, "percent_least": _lib.ABUNDANCE_PERCENT_AT_LEAST,
+}
+
+
+def selection_code(abundance, abundance_selection):
+    """(selection, abundance) for the ABI: an explicit abundance wins (src/main.rs:96); neither an
+    abundance nor a method is Error::AbundanceThresholdOrAbundanceMethod (:109)."""
+    if abundance is not None:
+        return _lib.ABUNDANCE_EXPLICIT, int(abundance)
+    if abundance_selection is None:
+        return _lib.ABUNDANCE_EXPLICIT, -1
+    if abundance_selection not in SELECTIONS:
+        raise ValueError(f"unknown abundance selection {abundance_selection!r}")
+    return SELECTIONS[abundance_selection], -1
+
+
+def spectrum_threshold(hist, abundance_selection, percent=0.0):
+    """pcon Spectrum::get_threshold on a 256-bin histogram; None when there is no threshold."""
+    h = np.ascontiguousarray(hist, dtype=np.uint64)
+    r = lib.brgpu_spectrum_threshold(_ptr(h), SELECTIONS[abundance_selection], float(percent))
+    return None if r < 0 else r
+
+
 class KmerSet:
     """src/set.rs:17-21"""
 
@@ -74,26 +101,21 @@ class Pcon(KmerSet):
         return cls(ctx, h)
 
     @classmethod
-    def from_reads(cls, ctx, reads, k, abundance=None, abundance_selection=None):
+    def from_reads(cls, ctx, reads, k, abundance=None, abundance_selection=None, percent=0.0):
         """The `fasta` sub-command (src/main.rs:72-115): count, spectrum, threshold, bitfield.
         `reads` is a device-resident Reads or a (seq, offsets) pair of host buffers.
-        abundance: -a; abundance_selection: None or "first-minimum" (src/cli.rs:227-241)."""
+        abundance: -a; abundance_selection: None, "first-minimum", or "rarefaction" /
+        "percent-most" / "percent-least" with `percent` (src/cli.rs:227-241)."""
         k = k - (~(k & 1) & 1)  # Fasta::kmer_size forces k odd (src/cli.rs:277-279)
-        if abundance is not None:
-            sel, ab = _lib.ABUNDANCE_EXPLICIT, int(abundance)  # explicit wins (src/main.rs:96)
-        elif abundance_selection in ("first-minimum", "first_minimum"):
-            sel, ab = _lib.ABUNDANCE_FIRST_MINIMUM, -1
-        elif abundance_selection is None:
-            sel, ab = _lib.ABUNDANCE_EXPLICIT, -1  # -> AbundanceThresholdOrAbundanceMethod
-        else:
-            raise ValueError(f"abundance selection {abundance_selection!r} is not supported yet")
+        sel, ab = selection_code(abundance, abundance_selection)
         h = C.c_void_p()
         if isinstance(reads, Reads):
-            check(lib.brgpu_set_from_reads(ctx._h, k, ab, sel, reads._h, C.byref(h)), ctx._h)
+            check(lib.brgpu_set_from_reads_ex(ctx._h, k, ab, sel, float(percent), reads._h, C.byref(h)), ctx._h)
         else:
             s, off = as_u8(reads[0]), as_offsets(reads[1])
             n = (off.numel() if hasattr(off, "numel") else off.size) - 1
-            check(lib.brgpu_set_from_host_reads(ctx._h, k, ab, sel, _addr(s), _addr(off), n, C.byref(h)), ctx._h)
+            check(lib.brgpu_set_from_host_reads_ex(ctx._h, k, ab, sel, float(percent), _addr(s), _addr(off), n, C.byref(h)),
+                  ctx._h)
         return cls(ctx, h)
 
     # --- KmerSet --------------------------------------------------------------------------------

@@ -42,8 +42,16 @@ enum {
 /* ---- correction methods: cli::CorrectionMethod in declaration order (src/cli.rs:121-131) ---- */
 enum { BRGPU_ONE = 0, BRGPU_TWO = 1, BRGPU_GRAPH = 2, BRGPU_GREEDY = 3, BRGPU_GAP_SIZE = 4 };
 
-/* ---- abundance selection: cli::AbundanceSelection (src/cli.rs:227-241) ---- */
-enum { BRGPU_ABUNDANCE_EXPLICIT = 0, BRGPU_ABUNDANCE_FIRST_MINIMUM = 1 };
+/* ---- abundance selection: cli::AbundanceSelection (src/cli.rs:227-241) and the pcon
+ * ThresholdMethod each maps to (src/main.rs:97-108): FirstMinimum, Rarefaction{percent},
+ * PercentMost{percent} -> PercentAtMost, PercentLeast{percent} -> PercentAtLeast ---- */
+enum {
+    BRGPU_ABUNDANCE_EXPLICIT = 0,
+    BRGPU_ABUNDANCE_FIRST_MINIMUM = 1,
+    BRGPU_ABUNDANCE_RAREFACTION = 2,
+    BRGPU_ABUNDANCE_PERCENT_AT_MOST = 3,
+    BRGPU_ABUNDANCE_PERCENT_AT_LEAST = 4
+};
 
 typedef struct brgpu_ctx brgpu_ctx;       /* one per process per GPU: device, stream, scratch */
 typedef struct brgpu_set brgpu_set;       /* Box<dyn KmerSet> (src/set.rs:17-23), device resident */
@@ -94,6 +102,9 @@ int brgpu_counts_add_reads(brgpu_counts *counts, const brgpu_reads *reads);
 int brgpu_counts_spectrum(brgpu_counts *counts, uint64_t hist_host[256]);
 /* Spectrum::get_threshold(FirstMinimum): returns the threshold or -1 for None */
 int brgpu_spectrum_first_minimum(const uint64_t hist[256]);
+/* Spectrum::get_threshold(method, percent) for any BRGPU_ABUNDANCE_* method but EXPLICIT
+ * (src/main.rs:95-108); -1 for None.  Host arithmetic on the 256 bins the GPU produced. */
+int brgpu_spectrum_threshold(const uint64_t hist[256], int selection, double percent);
 /* Copy the raw table to the host (Counter::raw, src/main.rs:76-78); n must be 2^(2k-1) */
 int brgpu_counts_download(brgpu_counts *counts, uint8_t *out_host, uint64_t n);
 /* device pointer and element count of the table, for multi-GPU merge plumbing */
@@ -108,6 +119,12 @@ int brgpu_set_from_counts(brgpu_counts *counts, int abundance, brgpu_set **out);
  * ignores it.  abundance < 0 with EXPLICIT -> BRGPU_E_NEED_ABUNDANCE. */
 int brgpu_set_from_reads(brgpu_ctx *ctx, int k, int abundance, int selection, const brgpu_reads *reads,
                          brgpu_set **out);
+/* same with the percent argument of Rarefaction / PercentAtMost / PercentAtLeast */
+int brgpu_set_from_reads_ex(brgpu_ctx *ctx, int k, int abundance, int selection, double percent,
+                            const brgpu_reads *reads, brgpu_set **out);
+int brgpu_set_from_host_reads_ex(brgpu_ctx *ctx, int k, int abundance, int selection, double percent,
+                                 const uint8_t *seq_host, const uint64_t *offsets_host, uint64_t n_reads,
+                                 brgpu_set **out);
 /* same, from host buffers (the call the Rust shim makes) */
 int brgpu_set_from_host_reads(brgpu_ctx *ctx, int k, int abundance, int selection, const uint8_t *seq_host,
                               const uint64_t *offsets_host, uint64_t n_reads, brgpu_set **out);

@@ -1068,6 +1068,37 @@ int bro_first_minimum(const uint64_t hist[256]) {
     return -1;
 }
 
+/* pcon Spectrum::get_threshold for the three percent-driven methods br can ask for
+ * (src/main.rs:100-108: Rarefaction, PercentAtLeast, PercentAtMost).  pcon @0184ae77 is not
+ * vendored and no reference test calls these: restated from the published source as recalled —
+ * PARITY UNPINNED.
+ *   rarefaction(limit):     walk the bins with the running sum of index * count; first bin whose
+ *                           count / running sum drops below limit
+ *   percent_at_least(p):    first bin at which the running share of index * count exceeds p
+ *   percent_at_most(p):     the bin before that one
+ * method: 2 rarefaction, 3 percent_at_most, 4 percent_at_least; returns -1 for None. */
+int bro_spectrum_threshold(const uint64_t hist[256], int method, double percent) {
+    if (method == 2) {
+        uint64_t cumulative = 0;
+        for (int i = 0; i < 256; i++) {
+            cumulative += (uint64_t)i * hist[i];
+            if ((double)hist[i] / (double)cumulative < percent) return i;
+        }
+        return -1;
+    }
+    if (method == 3 || method == 4) {
+        uint64_t total = 0;
+        for (int i = 0; i < 256; i++) total += (uint64_t)i * hist[i];
+        uint64_t cumulative = 0;
+        for (int i = 0; i < 256; i++) {
+            cumulative += (uint64_t)i * hist[i];
+            if ((double)cumulative / (double)total > percent) return method == 4 ? i : (i > 0 ? i - 1 : -1);
+        }
+        return -1;
+    }
+    return -1;
+}
+
 /* pcon Solid::from_count: bit[i] = counts[i] > abundance (src/main.rs:112-114; fixture `a2` == count>=3) */
 bro_set *bro_solid_from_count(const bro_counter *c, int abundance, int threads) {
     bro_set *s = bro_set_new(c->k);

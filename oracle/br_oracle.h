@@ -61,6 +61,7 @@ void bro_counter_count(bro_counter *, const uint8_t *seq, const uint64_t *offset
 const uint8_t *bro_counter_raw(const bro_counter *, size_t *n);
 void bro_spectrum(const bro_counter *, uint64_t hist[256], int threads);
 int bro_first_minimum(const uint64_t hist[256]);                         /* -1 == None */
+int bro_spectrum_threshold(const uint64_t hist[256], int method, double percent); /* 2 rarefaction, 3 at most, 4 at least */
 bro_set *bro_solid_from_count(const bro_counter *, int abundance, int threads);
 
 /* ---- correct module ---- */

@@ -55,6 +55,7 @@ def _load():
     sig("bro_counter_raw", vp, vp, C.POINTER(sz))
     sig("bro_spectrum", None, vp, vp, C.c_int)
     sig("bro_first_minimum", C.c_int, vp)
+    sig("bro_spectrum_threshold", C.c_int, vp, C.c_int, C.c_double)
     sig("bro_solid_from_count", vp, vp, C.c_int, C.c_int)
     sig("bro_alt_nucs", C.c_int, vp, C.c_uint64, vp)
     sig("bro_next_nucs", C.c_int, vp, C.c_uint64, vp)
@@ -241,6 +242,14 @@ class Counter:
     def first_minimum(hist):
         h = np.ascontiguousarray(hist, dtype=np.uint64)
         r = lib().bro_first_minimum(_ptr(h))
+        return None if r < 0 else r
+
+    @staticmethod
+    def spectrum_threshold(hist, method, percent):
+        """method: "rarefaction" | "percent-most" | "percent-least" (src/cli.rs:227-241)."""
+        h = np.ascontiguousarray(hist, dtype=np.uint64)
+        code = {"rarefaction": 2, "percent-most": 3, "percent-least": 4}[method]
+        r = lib().bro_spectrum_threshold(_ptr(h), code, float(percent))
         return None if r < 0 else r
 
     def to_solid(self, abundance, threads=1):

@@ -102,3 +102,24 @@ def test_bench_reference_arm_line_shape(monkeypatch, capsys):
     assert line["e2e"] == {"value": line["value"], "unit": "bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     for key in ("metric", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "config"):
         assert key in line
+
+
+def test_spectrum_threshold_is_host_arithmetic_and_matches_the_oracle():
+    """brgpu_spectrum_threshold needs no device; library and oracle restate pcon's pickers
+    independently and must agree, on the reference fixture's spectrum and on random ones."""
+    import numpy as np
+
+    from br_b200 import set as bset
+    from oracle import br_oracle as o
+
+    o.build()
+    fixture = np.zeros(256, dtype=np.uint64)
+    fixture[1:9] = [442564, 95498, 19526, 4458, 1221, 460, 494, 810]  # SURVEY section 8c: raw.fasta at k = 11
+    fixture[0] = (1 << 21) - int(fixture.sum())
+    assert bset.spectrum_threshold(fixture, "first-minimum") == 6
+    rng = np.random.default_rng(1)
+    cases = [fixture] + [(rng.integers(0, 10**6, 256) * (rng.random(256) < 0.4)).astype(np.uint64) for _ in range(200)]
+    for h in cases:
+        for m in ("rarefaction", "percent-most", "percent-least"):
+            for p in (0.001, 0.05, 0.5, 0.99, 1.5):
+                assert bset.spectrum_threshold(h, m, p) == o.Counter.spectrum_threshold(h, m, p), (m, p)

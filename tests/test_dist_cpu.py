@@ -72,6 +72,12 @@ class NumpyOps:
                 return i
         return None
 
+    @staticmethod
+    def spectrum_threshold(hist, abundance_selection, percent):
+        from oracle import br_oracle as o
+
+        return o.Counter.spectrum_threshold(hist, abundance_selection, percent)
+
     def threshold_slice(self, abundance, begin, end):
         self.bits[begin // 8 : end // 8] = np.packbits(self.table[begin:end] > abundance, bitorder="little")
 
@@ -139,15 +145,17 @@ def _worker(rank, world, port, k, selection, q):
         ops = NumpyOps(seq[int(sub[0]) : int(sub[-1])], sub - sub[0], rank, world)
         if selection == "explicit":
             ab, bits = dist.build_set_sharded(ops, k, abundance=2)
-        else:
+        elif selection == "first-minimum":
             ab, bits = dist.build_set_sharded(ops, k, abundance_selection="first-minimum")
+        else:
+            ab, bits = dist.build_set_sharded(ops, k, abundance_selection=selection, percent=0.2)
         q.put((rank, lo, hi, ab, bits.tobytes()))
     finally:
         tdist.destroy_process_group()
 
 
 @pytest.mark.parametrize("k", [9, 15])  # 9: table protocol, 15: bucketed k-mer protocol
-@pytest.mark.parametrize("selection", ["explicit", "first-minimum"])
+@pytest.mark.parametrize("selection", ["explicit", "first-minimum", "percent-least"])
 def test_sharded_set_equals_single_process(selection, k):
     import torch.multiprocessing as mp
 
@@ -157,7 +165,7 @@ def test_sharded_set_equals_single_process(selection, k):
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + (os.getpid() % 2000) + (0 if selection == "explicit" else 1) + (0 if k == 9 else 2)
+    port = 29500 + (os.getpid() % 2000) + {"explicit": 0, "first-minimum": 1, "percent-least": 4}[selection] + (0 if k == 9 else 2)
     procs = [ctx.Process(target=_worker, args=(r, world, port, k, selection, q)) for r in range(world)]
     for p in procs:
         p.start()
@@ -170,7 +178,12 @@ def test_sharded_set_equals_single_process(selection, k):
     seq, off, _ = synth.make_reads(genome, 20, 0.05, seed=43, mean_len=400, min_len=50)
     c = o.Counter(k)
     c.count(seq, off)
-    ab = 2 if selection == "explicit" else o.Counter.first_minimum(c.spectrum())
+    if selection == "explicit":
+        ab = 2
+    elif selection == "first-minimum":
+        ab = o.Counter.first_minimum(c.spectrum())
+    else:
+        ab = o.Counter.spectrum_threshold(c.spectrum(), selection, 0.2)
     expect = c.to_solid(ab).bits().tobytes()
     results.sort()
     # shards are contiguous, cover every record once, and every rank ends with the full bitfield

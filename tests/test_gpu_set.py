@@ -215,3 +215,27 @@ def test_bucketed_and_table_counting_paths_agree(gpu, oracle, k, one_level, monk
         assert hashlib.sha256(gb.tobytes()).digest() == hashlib.sha256(oc.to_solid(ab, threads=8).bits().tobytes()).digest()
         t.free()
         s.free()
+
+
+@pytest.mark.parametrize("k", [11, 15])
+def test_percent_driven_abundance_methods(gpu, oracle, k):
+    """`rarefaction P`, `percent-most P`, `percent-least P` (src/cli.rs:227-241, src/main.rs:100-108):
+    the threshold comes from the spectrum; table path (k = 11) and bucketed path (k = 15).  The
+    pickers themselves are restated from pcon as recalled (parity unpinned)."""
+    br, ctx = gpu
+    from br_b200 import synth
+
+    genome = synth.make_genome(50_000, seed=3)
+    seq, off, _ = synth.make_reads(genome, 20, 0.08, seed=4, mean_len=2000)
+    oc = oracle.Counter(k)
+    oc.count(seq, off, threads=8)
+    ohist = oc.spectrum(threads=8)
+    for method, percent in (("rarefaction", 0.3), ("percent-most", 0.6), ("percent-least", 0.25), ("percent-least", 0.6)):
+        want = oracle.Counter.spectrum_threshold(ohist, method, percent)
+        assert want is not None and want < 40, (method, want)
+        s = br.Pcon.from_reads(ctx, (seq, off), k, abundance_selection=method, percent=percent)
+        assert s.abundance == want, (method, s.abundance, want)
+        assert np.array_equal(s.bitfield(), oc.to_solid(want, threads=8).bits())
+        s.free()
+    with pytest.raises(br.BrgpuError):  # an impossible share has no threshold: Error::ComputeAbundanceThreshold
+        br.Pcon.from_reads(ctx, (seq, off), k, abundance_selection="percent-least", percent=2.0)

@@ -211,3 +211,18 @@ def test_reference_unit_kats_through_the_cpp_interface(kats):
     sys.stdout.write(r.stdout.decode())
     assert r.returncode == 0, r.stdout.decode() + r.stderr.decode()
     assert f"{n + len(kats['set'])} KATs".encode() in r.stdout
+
+
+@pytest.mark.gpu
+def test_fasta_percent_least_through_the_cli(tmp_path, oracle, fixture_reads):
+    """`fasta -k 11 percent-least 0.3`: the abundance sub-sub-command with its percent argument."""
+    out, solid_out = tmp_path / "corr.fasta", tmp_path / "set.solid"
+    r = run(["-i", GOLDEN / "br_reads.fa.gz", "-o", out, "-c", "one", "--write-solid", solid_out, "fasta", "-i",
+             GOLDEN / "br_reads.fa.gz", "-k", "11", "percent-least", "0.3"])
+    assert r.returncode == 0 and r.stderr == b"", r.stderr
+    seq, off = fixture_reads
+    c = oracle.Counter(11)
+    c.count(seq, off, threads=8)
+    thr = oracle.Counter.spectrum_threshold(c.spectrum(8), "percent-least", 0.3)
+    payload = gzip.open(solid_out).read()
+    assert np.array_equal(np.frombuffer(payload[1:], dtype=np.uint8), c.to_solid(thr, 8).bits())
