@@ -261,16 +261,21 @@ def run_ours(args, world, rank, local_rank):
         out.free()
         solid.free()
 
-    # e2e lanes.  A lane is a context (its own stream) with its own pinned output buffers; a step
-    # runs start to finish on one lane: upload -> set -> correct -> download, all through the
-    # host-buffer API.  At N = 1 two lanes are driven by two host threads and the steps alternate
-    # between them, so one step's PCIe copies overlap the other step's kernels (every step still
-    # uploads its inputs and downloads its result inside the timed region).  At N > 1 the set
-    # construction contains collectives, which must be issued in one order per rank: one lane.
+    # e2e: every step uploads its inputs from pinned host memory and downloads its result inside
+    # the timed region, through the host-buffer API.  At N = 1 the steps are pipelined — by
+    # default on one context whose copy stream carries step i+1's upload and step i-1's download
+    # while step i's kernels run (`stream`); alternatively on several contexts driven by host
+    # threads (`lanes`).  At N > 1 the set construction contains collectives, which must be issued
+    # in one order per rank: one step at a time (`serial`).
+    e2e_mode = "serial" if (world > 1 or args.no_e2e_pipeline) else args.e2e_mode
+    out_bufs = [(h_out, h_out_off)]
+    if e2e_mode == "stream":
+        out_bufs.append((torch.empty_like(h_out).pin_memory(), torch.empty_like(h_out_off).pin_memory()))
     lanes = [(ctx, h_out, h_out_off)]
-    if world == 1 and not args.no_e2e_pipeline:
-        ctx2 = br_b200.Context(local_rank, stream=torch.cuda.Stream())
-        lanes.append((ctx2, torch.empty_like(h_out).pin_memory(), torch.empty_like(h_out_off).pin_memory()))
+    if e2e_mode == "lanes":
+        for _ in range(max(1, args.e2e_lanes) - 1):
+            cx = br_b200.Context(local_rank, stream=torch.cuda.Stream())
+            lanes.append((cx, torch.empty_like(h_out).pin_memory(), torch.empty_like(h_out_off).pin_memory()))
 
     def step_e2e(lane=0):
         c, o, oo = lanes[lane]
@@ -284,8 +289,42 @@ def run_ours(args, world, rank, local_rank):
         reads.free()
         return nbytes
 
+    def run_e2e_stream(n_steps, stamps=None):
+        """n_steps e2e steps on ONE context with the asynchronous staging calls: step i+1's reads go
+        up and step i-1's result comes down on the context's copy stream while step i's kernels run.
+        Every step still uploads its own inputs and downloads its own result."""
+        c = ctx
+        res = 0
+        nxt = br_b200.Reads.upload_async(c, h_seq, h_off)
+        prev = None
+        t0 = time.perf_counter()
+        for i in range(n_steps):
+            cur = nxt
+            if i + 1 < n_steps:
+                nxt = br_b200.Reads.upload_async(c, h_seq, h_off)           # H2D of the next step
+            if prev is not None:
+                res = max(res, prev.download_async(*out_bufs[(i - 1) % 2]))  # D2H of the previous step
+            solid = build_set(cur, c)
+            out = br_b200.correct_reads(br_b200.build_methods(METHODS, solid, CONFIRM, MAX_SEARCH), cur)
+            solid.free()
+            cur.free()
+            if prev is not None:
+                prev.download_wait()
+                prev.free()
+            prev = out
+            if stamps is not None:
+                t1 = time.perf_counter()
+                stamps.append(round((t1 - t0) * 1e3, 2))
+                t0 = t1
+        res = max(res, prev.download_async(*out_bufs[(n_steps - 1) % 2]))
+        prev.download_wait()
+        prev.free()
+        return res
+
     def run_e2e(n_steps, stamps=None):
         """n_steps e2e steps spread over the lanes; returns the D2H bytes of one step."""
+        if e2e_mode == "stream":
+            return run_e2e_stream(n_steps, stamps)
         res = [0] * len(lanes)
 
         def work(lane, n):
@@ -367,9 +406,10 @@ def run_ours(args, world, rank, local_rank):
         for it in range(max(3, args.warmup) + 12):
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            d2h = max(d2h, run_e2e(len(lanes)))
+            n_warm = 4 if e2e_mode == "stream" else len(lanes)
+            d2h = max(d2h, run_e2e(n_warm))
             torch.cuda.synchronize()
-            e2e_warm_ms.append((time.perf_counter() - t0) * 1e3 / len(lanes))
+            e2e_warm_ms.append((time.perf_counter() - t0) * 1e3 / n_warm)
             stable = it + 1 >= max(3, args.warmup) and abs(e2e_warm_ms[-1] - e2e_warm_ms[-2]) <= 0.03 * e2e_warm_ms[-1]
             if tdist is not None:  # the step contains collectives: every rank must take the same decision
                 t = torch.tensor([1 if stable else 0], dtype=torch.int32, device=f"cuda:{local_rank}")
@@ -427,9 +467,12 @@ def run_ours(args, world, rank, local_rank):
                    "parallelism": f"reads sharded over {world} GPU(s)", "rank0_numa_node": numa_node},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                 "warmup_ms_per_step": [round(x, 2) for x in e2e_warm_ms],
-                "host_clock_ms_per_step": e2e_step_ms, "lanes": len(lanes),
-                "pipeline": ("%d contexts (streams) driven by %d host threads, steps alternate between them" % (len(lanes), len(lanes)))
-                if len(lanes) > 1 else "one step at a time",
+                "host_clock_ms_per_step": e2e_step_ms, "mode": e2e_mode,
+                "pipeline": {"stream": "one context; step i+1's upload and step i-1's download run on its copy stream "
+                                       "(brgpu_reads_upload_async / _download_async) while step i's kernels run",
+                             "lanes": "%d contexts (streams) driven by %d host threads, steps alternate between them"
+                                      % (len(lanes), len(lanes)),
+                             "serial": "one step at a time"}[e2e_mode],
                 "h2d_bytes_per_step": int(h_seq.numel() + 8 * h_off.numel()),
                 "d2h_bytes_per_step": int(d2h + 8 * (n_reads + 1))},
         "gpu_launches": int(launches),
@@ -467,6 +510,10 @@ def main():
                     help="method chain (default: one two = BASELINE.json configs[1]; `graph greedy gap_size` = configs[2])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e-pipeline", action="store_true", help="e2e steps one at a time on a single context")
+    ap.add_argument("--e2e-mode", choices=["stream", "lanes", "serial"], default="stream",
+                    help="e2e pipeline at N = 1: `stream` = one context, copies of the neighbouring steps on its copy "
+                         "stream (default); `lanes` = several contexts driven by host threads; `serial` = one step at a time")
+    ap.add_argument("--e2e-lanes", type=int, default=2, help="contexts / host threads of the `lanes` e2e mode")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.methods:

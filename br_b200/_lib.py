@@ -39,6 +39,9 @@ SIGNATURES = {
     "brgpu_reads_bases": (u64, [vp]),
     "brgpu_reads_download": (C.c_int, [vp, vp, u64, vp, pu64]),
     "brgpu_reads_free": (None, [vp]),
+    "brgpu_reads_upload_async": (C.c_int, [vp, vp, vp, u64, pvp]),
+    "brgpu_reads_download_async": (C.c_int, [vp, vp, u64, vp, pu64]),
+    "brgpu_reads_download_wait": (C.c_int, [vp]),
     "brgpu_counts_create": (C.c_int, [vp, C.c_int, pvp]),
     "brgpu_counts_add_reads": (C.c_int, [vp, vp]),
     "brgpu_counts_spectrum": (C.c_int, [vp, vp]),

@@ -207,9 +207,15 @@ extern "C" int brgpu_ctx_create(int device, void *cuda_stream, brgpu_ctx **out) 
         }
         ctx->own_stream = true;
     }
+    if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_fence, cudaEventDisableTiming) != cudaSuccess) {
+        cudaGetLastError();
+        brgpu_ctx_destroy(ctx);
+        return BRGPU_E_CUDA;
+    }
     if (cudaMalloc((void **)&ctx->d_flags, 16 * sizeof(uint32_t)) != cudaSuccess ||
         cudaMalloc((void **)&ctx->d_hist, 256 * sizeof(uint64_t)) != cudaSuccess ||
-        cudaMallocHost((void **)&ctx->h_pinned, 512 * sizeof(uint64_t)) != cudaSuccess) {
+        cudaHostAlloc((void **)&ctx->h_pinned, 512 * sizeof(uint64_t), cudaHostAllocMapped) != cudaSuccess) {
         cudaGetLastError();
         brgpu_ctx_destroy(ctx);
         return BRGPU_E_NOMEM;
@@ -223,6 +229,11 @@ extern "C" void brgpu_ctx_destroy(brgpu_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->copy_stream) {
+        cudaStreamSynchronize(ctx->copy_stream);
+        cudaStreamDestroy(ctx->copy_stream);
+    }
+    if (ctx->ev_fence) cudaEventDestroy(ctx->ev_fence);
     for (auto &p : ctx->prof)
         for (auto &ev : p.pending) {
             cudaEventDestroy(ev.first);
@@ -314,10 +325,37 @@ static int make_layout(brgpu_ctx *ctx, const uint32_t *h_len, uint64_t n, unsign
     return BRGPU_OK;
 }
 
+// A consumer of reads that may still be uploading on the copy stream: order the compute stream
+// after the upload and hand the upload's temporaries back to the allocator (everything enqueued
+// from here on, on either stream, runs after the upload).
+static void reads_ready(const brgpu_reads *cr) {
+    brgpu_reads *r = const_cast<brgpu_reads *>(cr);
+    if (!r || !r->ready) return;
+    cudaStreamWaitEvent(r->ctx->stream, r->ready, 0);
+    // later uploads reuse these blocks on the copy stream: they are fenced behind the compute stream
+    for (void *p : r->deferred) dfree(r->ctx, p);
+    r->deferred.clear();
+    cudaEventDestroy(r->ready);
+    r->ready = nullptr;
+}
+
 static void reads_release(brgpu_reads *r) {
     if (!r) return;
     if (r->ctx) {
         cudaSetDevice(r->ctx->device);
+        if (r->ready) { // never consumed: wait on the host before the buffers go back to the cache
+            cudaEventSynchronize(r->ready);
+            cudaEventDestroy(r->ready);
+            r->ready = nullptr;
+        }
+        if (r->dl_done) {
+            cudaEventSynchronize(r->dl_done);
+            cudaEventDestroy(r->dl_done);
+            r->dl_done = nullptr;
+        }
+        for (void *p : r->deferred) dfree(r->ctx, p);
+        if (r->dl_tight) dfree(r->ctx, r->dl_tight);
+        if (r->dl_toff) dfree(r->ctx, r->dl_toff);
         if (r->d_seq) dfree(r->ctx, r->d_seq);
         if (r->d_len) dfree(r->ctx, r->d_len);
     }
@@ -326,7 +364,7 @@ static void reads_release(brgpu_reads *r) {
 
 // upload from a tight device or host buffer into a fresh slot layout
 static int reads_from_tight(brgpu_ctx *ctx, const uint8_t *seq, bool seq_on_device, const uint64_t *h_off, uint64_t n,
-                            unsigned slack_extra, brgpu_reads **out) {
+                            unsigned slack_extra, brgpu_reads **out, bool defer_frees = false) {
     std::vector<uint32_t> h_len(n);
     for (uint64_t r = 0; r < n; r++) {
         if (h_off[r + 1] < h_off[r]) return fail(ctx, BRGPU_E_INVALID, "offsets must be non-decreasing");
@@ -367,14 +405,21 @@ static int reads_from_tight(brgpu_ctx *ctx, const uint8_t *seq, bool seq_on_devi
             reads_release(R);
             return fail(ctx, BRGPU_E_NOMEM, "device allocation (staging)", e);
         }
-        if (total) cudaMemcpyAsync(d_tight, seq + base0, total, cudaMemcpyHostToDevice, ctx->stream);
         d_src = d_tight;
     }
+    // the small pageable arrays first (the runtime drains the stream before it stages them), the
+    // big pinned copy after them, so that it is the only thing the caller may have to wait for
     cudaMemcpyAsync(d_toff, rel.data(), (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream);
     if (n) cudaMemcpyAsync(R->d_len, h_len.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (d_tight && total) cudaMemcpyAsync(d_tight, seq + base0, total, cudaMemcpyHostToDevice, ctx->stream);
     launch_scatter_to_slots(ctx, L, d_src, d_toff, R->d_seq);
-    if (d_tight) dfree(ctx, d_tight);
-    dfree(ctx, d_toff);
+    if (defer_frees) { // the copy stream still uses them: released by the first consumer (reads_ready)
+        if (d_tight) R->deferred.push_back(d_tight);
+        R->deferred.push_back(d_toff);
+    } else {
+        if (d_tight) dfree(ctx, d_tight);
+        dfree(ctx, d_toff);
+    }
     e = cudaGetLastError();
     if (e != cudaSuccess) {
         reads_release(R);
@@ -405,7 +450,7 @@ static int reads_tight_offsets(brgpu_reads *R, uint64_t **d_toff_out, uint64_t *
     CK(dalloc(ctx, &d_tmp, n / 4096 + 4));
     launch_exclusive_scan_u32(ctx, R->d_len, n, d_toff, d_tmp);
     dfree(ctx, d_tmp);
-    CK(cudaMemcpyAsync(ctx->h_pinned, d_toff + n, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    launch_readback(ctx, ctx->h_pinned, d_toff + n, sizeof(uint64_t));
     CK(cudaStreamSynchronize(ctx->stream));
     *total = ctx->h_pinned[0];
     *d_toff_out = d_toff;
@@ -416,6 +461,7 @@ extern "C" uint64_t brgpu_reads_bases(const brgpu_reads *reads) {
     if (!reads) return 0;
     brgpu_reads *R = const_cast<brgpu_reads *>(reads);
     cudaSetDevice(R->ctx->device);
+    reads_ready(R);
     uint64_t *d_toff = nullptr, total = 0;
     if (reads_tight_offsets(R, &d_toff, &total) != BRGPU_OK) return 0;
     dfree(R->ctx, d_toff);
@@ -427,6 +473,7 @@ extern "C" int brgpu_reads_download(brgpu_reads *reads, uint8_t *seq_host, uint6
     if (!reads) return BRGPU_E_INVALID;
     brgpu_ctx *ctx = reads->ctx;
     cudaSetDevice(ctx->device);
+    reads_ready(reads);
     const Layout &L = *reads->layout;
     uint64_t *d_toff = nullptr, total = 0;
     int st = reads_tight_offsets(reads, &d_toff, &total);
@@ -448,6 +495,93 @@ extern "C" int brgpu_reads_download(brgpu_reads *reads, uint8_t *seq_host, uint6
 }
 
 extern "C" void brgpu_reads_free(brgpu_reads *reads) { reads_release(reads); }
+
+// ------------------------------------------------------------------------------------------
+// Asynchronous staging.  The context owns a second stream; an upload enqueued there runs while
+// the kernels of the previous chunk do, a download while the kernels of the next one do.  The
+// allocator hands blocks from one stream's past to the other stream's future, so every hand-over
+// is fenced: an upload starts behind everything the compute stream has been given so far, its
+// temporaries return to the cache only when a consumer has put the compute stream behind the
+// upload, and a download's buffers return after the host has seen it finish.
+// ------------------------------------------------------------------------------------------
+extern "C" int brgpu_reads_upload_async(brgpu_ctx *ctx, const uint8_t *seq_host, const uint64_t *offsets_host,
+                                        uint64_t n_reads, brgpu_reads **out) {
+    if (!ctx || !out || !offsets_host) return ctx ? fail(ctx, BRGPU_E_INVALID, "null argument") : BRGPU_E_INVALID;
+    *out = nullptr;
+    if (!seq_host && n_reads && offsets_host[n_reads] != offsets_host[0])
+        return fail(ctx, BRGPU_E_INVALID, "null sequence buffer");
+    cudaSetDevice(ctx->device);
+    CK(cudaEventRecord(ctx->ev_fence, ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_fence, 0));
+    cudaStream_t compute = ctx->stream;
+    ctx->stream = ctx->copy_stream; // the staging kernels and copies of this call go to the copy stream
+    int st = reads_from_tight(ctx, seq_host, false, offsets_host, n_reads, 0, out, true);
+    ctx->stream = compute;
+    if (st != BRGPU_OK) return st;
+    brgpu_reads *R = *out;
+    cudaError_t e = cudaEventCreateWithFlags(&R->ready, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventRecord(R->ready, ctx->copy_stream);
+    if (e != cudaSuccess) {
+        cudaStreamSynchronize(ctx->copy_stream);
+        if (R->ready) cudaEventDestroy(R->ready);
+        R->ready = nullptr;
+        reads_release(R);
+        *out = nullptr;
+        return fail(ctx, BRGPU_E_CUDA, "asynchronous upload", e);
+    }
+    return BRGPU_OK;
+}
+
+extern "C" int brgpu_reads_download_async(brgpu_reads *reads, uint8_t *seq_host, uint64_t seq_cap,
+                                          uint64_t *offsets_host, uint64_t *required) {
+    if (!reads) return BRGPU_E_INVALID;
+    brgpu_ctx *ctx = reads->ctx;
+    cudaSetDevice(ctx->device);
+    if (reads->dl_done) return fail(ctx, BRGPU_E_INVALID, "a download of these reads is already in flight");
+    reads_ready(reads);
+    const Layout &L = *reads->layout;
+    uint64_t *d_toff = nullptr, total = 0;
+    int st = reads_tight_offsets(reads, &d_toff, &total); // waits for the producer of these reads
+    if (st != BRGPU_OK) return st;
+    if (required) *required = total;
+    if (total > seq_cap || (!seq_host && total) || !offsets_host) {
+        dfree(ctx, d_toff);
+        return fail(ctx, total > seq_cap ? BRGPU_E_OVERFLOW : BRGPU_E_INVALID, "output buffer too small");
+    }
+    uint8_t *d_tight = nullptr;
+    cudaError_t e = dalloc(ctx, &d_tight, total);
+    if (e != cudaSuccess) {
+        dfree(ctx, d_toff);
+        return fail(ctx, BRGPU_E_NOMEM, "device allocation (download staging)", e);
+    }
+    launch_gather_from_slots(ctx, L, reads->d_seq, reads->d_len, d_toff, d_tight, false);
+    e = cudaEventRecord(ctx->ev_fence, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_fence, 0);
+    if (e == cudaSuccess && total) e = cudaMemcpyAsync(seq_host, d_tight, total, cudaMemcpyDeviceToHost, ctx->copy_stream);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(offsets_host, d_toff, (L.n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->copy_stream);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&reads->dl_done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventRecord(reads->dl_done, ctx->copy_stream);
+    reads->dl_tight = d_tight;
+    reads->dl_toff = d_toff;
+    if (e != cudaSuccess) return fail(ctx, BRGPU_E_CUDA, "asynchronous download", e);
+    return BRGPU_OK;
+}
+
+extern "C" int brgpu_reads_download_wait(brgpu_reads *reads) {
+    if (!reads) return BRGPU_E_INVALID;
+    brgpu_ctx *ctx = reads->ctx;
+    cudaSetDevice(ctx->device);
+    if (!reads->dl_done) return BRGPU_OK;
+    cudaError_t e = cudaEventSynchronize(reads->dl_done);
+    cudaEventDestroy(reads->dl_done);
+    reads->dl_done = nullptr;
+    dfree(ctx, reads->dl_tight);
+    dfree(ctx, reads->dl_toff);
+    reads->dl_tight = reads->dl_toff = nullptr;
+    if (e != cudaSuccess) return fail(ctx, BRGPU_E_CUDA, "asynchronous download", e);
+    return BRGPU_OK;
+}
 
 // ------------------------------------------------------------------------------------------
 // part 1
@@ -491,6 +625,7 @@ extern "C" int brgpu_counts_add_reads(brgpu_counts *c, const brgpu_reads *reads)
     brgpu_ctx *ctx = c->ctx;
     if (reads->ctx != ctx) return fail(ctx, BRGPU_E_INVALID, "reads belong to another context");
     cudaSetDevice(ctx->device);
+    reads_ready(reads);
     const Layout &L = *reads->layout;
     // k-mer count for the roofline bookkeeping (exact for uploaded reads)
     double n_kmers = 0;
@@ -507,7 +642,7 @@ static int run_spectrum(brgpu_ctx *ctx, const uint8_t *d_counts, uint64_t begin,
     launch_spectrum_threshold(ctx, d_counts, begin, end, ctx->d_hist, d_bits, abundance);
     CK(cudaGetLastError());
     if (hist) {
-        CK(cudaMemcpyAsync(ctx->h_pinned, ctx->d_hist, 256 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        launch_readback(ctx, ctx->h_pinned, ctx->d_hist, 256 * sizeof(uint64_t));
         CK(cudaStreamSynchronize(ctx->stream));
         memcpy(hist, ctx->h_pinned, 256 * sizeof(uint64_t));
     }
@@ -645,7 +780,8 @@ static int build_compact(brgpu_set *s) {
         return fail(ctx, BRGPU_E_NOMEM, "device allocation (rank directory)", e);
     }
     launch_summary_rank(ctx, s->d_summary, n_words, d_pop, d_rank, d_tmp);
-    e = cudaMemcpyAsync(ctx->h_pinned + 300, d_rank + n_words, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
+    launch_readback(ctx, ctx->h_pinned + 300, d_rank + n_words, sizeof(uint64_t));
+    e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) {
         drop();
@@ -818,7 +954,8 @@ static void kmers_release(brgpu_kmers *km) {
 }
 
 static cudaError_t read_hist(brgpu_ctx *ctx, uint64_t hist[256]) {
-    cudaError_t e = cudaMemcpyAsync(ctx->h_pinned, ctx->d_hist, 256 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream);
+    launch_readback(ctx, ctx->h_pinned, ctx->d_hist, 256 * sizeof(uint64_t));
+    cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e == cudaSuccess) memcpy(hist, ctx->h_pinned, 256 * sizeof(uint64_t));
     return e;
@@ -896,6 +1033,7 @@ extern "C" int brgpu_kmers_create(brgpu_ctx *ctx, int k, const brgpu_reads *read
     if (reads->ctx != ctx) return fail(ctx, BRGPU_E_INVALID, "reads belong to another context");
     if (!bucketed_applicable(k, reads)) return fail(ctx, BRGPU_E_INVALID, "chunk too large for 32-bit bucket cursors");
     cudaSetDevice(ctx->device);
+    reads_ready(reads);
     return kmers_create(ctx, k, reads, out);
 }
 
@@ -1011,8 +1149,7 @@ extern "C" int brgpu_kmers_offsets_at(brgpu_kmers *km, const uint64_t *buckets_h
     cudaSetDevice(ctx->device);
     for (uint64_t i = 0; i < n; i++) {
         if (buckets_host[i] > km->n_buckets) return fail(ctx, BRGPU_E_INVALID, "bucket id out of range");
-        CK(cudaMemcpyAsync(ctx->h_pinned + i, km->d_base + buckets_host[i], sizeof(uint64_t), cudaMemcpyDeviceToHost,
-                           ctx->stream));
+        launch_readback(ctx, ctx->h_pinned + i, km->d_base + buckets_host[i], sizeof(uint64_t));
     }
     CK(cudaStreamSynchronize(ctx->stream));
     for (uint64_t i = 0; i < n; i++) offsets_host[i] = ctx->h_pinned[i];
@@ -1032,6 +1169,7 @@ extern "C" int brgpu_set_from_reads_ex(brgpu_ctx *ctx, int k, int abundance, int
         return fail(ctx, BRGPU_E_INVALID, "abundance must be in 0..=255");
     if (reads->ctx != ctx) return fail(ctx, BRGPU_E_INVALID, "reads belong to another context");
     cudaSetDevice(ctx->device);
+    reads_ready(reads);
     if (bucketed_applicable(k, reads)) return set_from_reads_bucketed(ctx, k, abundance, selection, percent, reads, out);
     // table path: Counter::new + count_fasta + Spectrum + Solid::from_count, literally
     brgpu_counts *c = nullptr;
@@ -1268,7 +1406,8 @@ static int correct_attempt(brgpu_ctx *ctx, const brgpu_set *set, const uint8_t *
     }
     e = cudaGetLastError();
     if (e == cudaSuccess)
-        e = cudaMemcpyAsync(ctx->h_pinned, ctx->d_flags + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
+        launch_readback(ctx, ctx->h_pinned, ctx->d_flags + 1, sizeof(uint32_t));
+        e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) {
         cleanup();
@@ -1324,6 +1463,7 @@ extern "C" int brgpu_correct_reads(brgpu_ctx *ctx, const brgpu_set *set, const u
     int st = validate_methods(ctx, methods, n_methods, confirm, max_search);
     if (st != BRGPU_OK) return st;
     cudaSetDevice(ctx->device);
+    reads_ready(in);
     st = ensure_summary(const_cast<brgpu_set *>(set));
     if (st != BRGPU_OK) return st;
 
@@ -1476,9 +1616,8 @@ extern "C" uint64_t brgpu_launch_count(const brgpu_ctx *ctx) { return ctx ? ctx-
 extern "C" uint64_t brgpu_scan_lookups(brgpu_ctx *ctx) {
     if (!ctx) return 0;
     cudaSetDevice(ctx->device);
-    if (cudaMemcpyAsync(ctx->h_pinned, ctx->d_flags + 2, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream) !=
-            cudaSuccess ||
-        cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+    launch_readback(ctx, ctx->h_pinned, ctx->d_flags + 2, sizeof(uint64_t));
+    if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
         cudaGetLastError();
         return 0;
     }

@@ -29,6 +29,10 @@ struct brgpu_ctx {
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    // second stream for the asynchronous host<->device staging calls (brgpu_reads_upload_async /
+    // _download_async): copies of the neighbouring chunks run while this chunk's kernels do
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_fence = nullptr; // orders the two streams against each other
     std::string err;
     bool profiling = false;
     std::vector<brgpu::ProfEntry> prof;
@@ -67,6 +71,11 @@ struct brgpu_reads {
     uint32_t *d_len = nullptr; // n
     std::vector<uint32_t> h_len; // host copy of the lengths (uploaded reads only)
     uint64_t sum_len = 0;        // sum of lengths at upload (bookkeeping hint afterwards)
+    // asynchronous staging (copy stream)
+    cudaEvent_t ready = nullptr;     // upload in flight: consumers make the compute stream wait for it
+    std::vector<void *> deferred;    // upload temporaries, released once a consumer has ordered itself after `ready`
+    cudaEvent_t dl_done = nullptr;   // download in flight
+    void *dl_tight = nullptr, *dl_toff = nullptr;
 };
 
 struct brgpu_counts {
@@ -124,6 +133,10 @@ struct ProfScope {
     }
     ~ProfScope() { prof_end(c); }
 };
+
+// small device -> host results through mapped pinned memory (h_mapped_dst inside ctx->h_pinned); the
+// caller synchronises the stream before reading.  bytes: multiple of 4
+void launch_readback(brgpu_ctx *ctx, void *h_mapped_dst, const void *d_src, size_t bytes);
 
 // ---- layout / relayout kernels (set_kernels.cu) ----
 void launch_fill_word2read(brgpu_ctx *ctx, const Layout &L);

@@ -154,6 +154,31 @@ class Reads:
         r._keep = (s, off)
         return r
 
+    @classmethod
+    def upload_async(cls, ctx, seq, offsets):
+        """Upload on the context's copy stream; returns at once.  Pass pinned buffers and leave them
+        alone until a call that takes the reads has returned."""
+        s, off = as_u8(seq), as_offsets(offsets)
+        n = (off.numel() if hasattr(off, "numel") else off.size) - 1
+        h = C.c_void_p()
+        check(lib.brgpu_reads_upload_async(ctx._h, _addr(s), _addr(off), n, C.byref(h)), ctx._h)
+        r = cls(ctx, h)
+        r._keep = (s, off)
+        return r
+
+    def download_async(self, out, out_offsets):
+        """Enqueue the copy back on the copy stream; returns the byte count.  `download_wait()`
+        blocks until `out[:count]` and `out_offsets` are filled."""
+        cap = out.numel() if hasattr(out, "numel") else out.size
+        req = C.c_uint64()
+        check(lib.brgpu_reads_download_async(self._h, _addr(out), cap, _addr(out_offsets), C.byref(req)), self.ctx._h)
+        self._dl = (out, out_offsets)
+        return int(req.value)
+
+    def download_wait(self):
+        check(lib.brgpu_reads_download_wait(self._h), self.ctx._h)
+        self._dl = None
+
     def free(self):
         if getattr(self, "_h", None) and getattr(self.ctx, "_h", None):
             lib.brgpu_reads_free(self._h)

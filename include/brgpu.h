@@ -89,6 +89,18 @@ uint64_t brgpu_reads_bases(const brgpu_reads *reads); /* sum of lengths (syncs t
 int brgpu_reads_download(brgpu_reads *reads, uint8_t *seq_host, uint64_t seq_cap, uint64_t *offsets_host,
                          uint64_t *required);
 void brgpu_reads_free(brgpu_reads *reads);
+/* Asynchronous staging for pipelined chunks (what a host loop over run_correction's chunks,
+ * src/lib.rs:86-136, uses to hide PCIe behind the kernels): the context owns a copy stream;
+ * brgpu_reads_upload_async returns at once and any later call that takes the reads waits for the
+ * copy on the device; brgpu_reads_download_async enqueues the copy back (the call that produced
+ * `reads` must have returned) and brgpu_reads_download_wait blocks until the bytes are in the
+ * host buffers.  Host buffers should come from brgpu_host_alloc (pageable memory makes the copies
+ * synchronous) and must not be touched between the call and the wait / the first consumer. */
+int brgpu_reads_upload_async(brgpu_ctx *ctx, const uint8_t *seq_host, const uint64_t *offsets_host, uint64_t n_reads,
+                             brgpu_reads **out);
+int brgpu_reads_download_async(brgpu_reads *reads, uint8_t *seq_host, uint64_t seq_cap, uint64_t *offsets_host,
+                               uint64_t *required);
+int brgpu_reads_download_wait(brgpu_reads *reads);
 
 /* ------------------------------------------------------------------------------------------
  * part 1 — counting and the solid set

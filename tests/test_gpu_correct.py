@@ -314,3 +314,57 @@ def test_both_scan_kernels_give_the_oracle_bytes(gpu, oracle, fixture_sets, fixt
         exp, exp_off = ro.run_correction(ids, rseq, roff, confirm=c, max_search=7, threads=8)
         got, got_off = br.correct_batch(br.build_methods(["one", "two"], rs, c, 7), rseq, roff)
         compare_batches(f"random one+two c={c} ({mode})", got, got_off, exp, exp_off, rseq, roff)
+
+
+def test_async_staging_pipeline_matches_the_synchronous_calls(gpu, fixture_sets, fixture_reads):
+    """brgpu_reads_upload_async / _download_async / _download_wait: chunk c+1 goes up and chunk c-1
+    comes down on the copy stream while chunk c is corrected.  Three rounds over the same buffers
+    so that the allocator recycles blocks between the two streams; the bytes must equal what the
+    synchronous calls return."""
+    import torch
+
+    br, ctx = gpu
+    gs, _ = fixture_sets
+    seq, off = fixture_reads
+    n = off.size - 1
+    cuts = [0, 40, 41, 100, 160, n]  # uneven chunks, one of a single read
+    methods = br.build_methods(["one", "two", "gap_size"], gs, 4, 7)
+    chunks, expected = [], []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        cseq = torch.from_numpy(seq[int(off[a]) : int(off[b])].copy()).pin_memory()
+        coff = torch.from_numpy((off[a : b + 1] - off[a]).astype(np.int64)).pin_memory()
+        chunks.append((cseq, coff))
+        expected.append(br.correct_batch(methods, cseq.numpy(), coff.numpy().astype(np.uint64)))
+    cap = int(max(c[0].numel() for c in chunks) * 2 + 4096)
+    bufs = [(torch.empty(cap, dtype=torch.uint8).pin_memory(), torch.empty(n + 1, dtype=torch.int64).pin_memory())
+            for _ in range(2)]
+
+    def check(i, count, buf):
+        exp, exp_off = expected[i]
+        m = chunks[i][1].numel()
+        got_off = buf[1][:m].numpy().astype(np.uint64)
+        assert count == exp.size and np.array_equal(got_off, exp_off), f"chunk {i}: offsets differ"
+        assert np.array_equal(buf[0][:count].numpy(), exp), f"chunk {i}: bytes differ"
+
+    for _ in range(3):
+        nxt = br.Reads.upload_async(ctx, *chunks[0])
+        prev = None  # (index, corrected reads, byte count)
+        for i in range(len(chunks)):
+            cur = nxt
+            if i + 1 < len(chunks):
+                nxt = br.Reads.upload_async(ctx, *chunks[i + 1])
+            if prev is not None:
+                prev = (prev[0], prev[1], prev[1].download_async(*bufs[prev[0] % 2]))
+            out = br.correct_reads(methods, cur)
+            if prev is not None:
+                prev[1].download_wait()
+                check(prev[0], prev[2], bufs[prev[0] % 2])
+                prev[1].free()
+            cur.free()
+            prev = (i, out, None)
+        count = prev[1].download_async(*bufs[prev[0] % 2])
+        prev[1].download_wait()
+        check(prev[0], count, bufs[prev[0] % 2])
+        prev[1].free()
+    # an upload that nobody consumes is still released cleanly
+    br.Reads.upload_async(ctx, *chunks[0]).free()
