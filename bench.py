@@ -262,12 +262,14 @@ def run_ours(args, world, rank, local_rank):
         solid.free()
 
     # e2e: every step uploads its inputs from pinned host memory and downloads its result inside
-    # the timed region, through the host-buffer API.  At N = 1 the steps are pipelined — by
-    # default on one context whose copy stream carries step i+1's upload and step i-1's download
-    # while step i's kernels run (`stream`); alternatively on several contexts driven by host
-    # threads (`lanes`).  At N > 1 the set construction contains collectives, which must be issued
-    # in one order per rank: one step at a time (`serial`).
-    e2e_mode = "serial" if (world > 1 or args.no_e2e_pipeline) else args.e2e_mode
+    # the timed region, through the host-buffer API.  The steps are pipelined — by default on one
+    # context whose copy stream carries step i+1's upload and step i-1's download while step i's
+    # kernels run (`stream`; one host thread, so the collectives of the sharded set construction
+    # keep one order per rank); at N = 1 alternatively on several contexts driven by host threads
+    # (`lanes`); `serial` = one step at a time.
+    e2e_mode = "serial" if args.no_e2e_pipeline else args.e2e_mode
+    if world > 1 and e2e_mode == "lanes":
+        e2e_mode = "stream"  # host threads would issue the collectives of two steps in no fixed order
     out_bufs = [(h_out, h_out_off)]
     if e2e_mode == "stream":
         out_bufs.append((torch.empty_like(h_out).pin_memory(), torch.empty_like(h_out_off).pin_memory()))

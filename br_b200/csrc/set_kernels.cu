@@ -150,6 +150,7 @@ __global__ void readback_kernel(uint32_t *__restrict__ host_mapped, const uint32
 }
 
 void launch_readback(brgpu_ctx *ctx, void *h_mapped_dst, const void *d_src, size_t bytes) {
+    ctx->launches++;
     readback_kernel<<<1, 256, 0, ctx->stream>>>(reinterpret_cast<uint32_t *>(h_mapped_dst),
                                                 reinterpret_cast<const uint32_t *>(d_src), (int)(bytes / 4));
 }
