@@ -355,7 +355,7 @@ inline Methods build_methods(const std::vector<cli::CorrectionMethod> &params, c
 
 // the per-chunk body of run_correction (src/lib.rs:93-128) in one library call
 struct Corrected {
-    std::vector<uint8_t> seq;
+    fasta::Bytes seq; // not value-initialised on resize: the library fills it
     std::vector<uint64_t> offsets;
 };
 

@@ -12,7 +12,9 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <new>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -22,11 +24,70 @@ namespace fasta {
 
 constexpr size_t LINE_BASES = 80;
 
+// Growable byte buffer without value initialisation (std::vector<uint8_t>::resize zero-fills, which
+// doubles the memory traffic of a parser that only appends).
+class Bytes {
+  public:
+    Bytes() = default;
+    Bytes(const Bytes &o) { append(o.p_, o.n_); }
+    Bytes &operator=(const Bytes &o) {
+        if (this != &o) {
+            n_ = 0;
+            append(o.p_, o.n_);
+        }
+        return *this;
+    }
+    Bytes(Bytes &&o) noexcept : p_(o.p_), n_(o.n_), cap_(o.cap_) { o.p_ = nullptr, o.n_ = o.cap_ = 0; }
+    Bytes &operator=(Bytes &&o) noexcept {
+        if (this != &o) {
+            std::free(p_);
+            p_ = o.p_, n_ = o.n_, cap_ = o.cap_;
+            o.p_ = nullptr, o.n_ = o.cap_ = 0;
+        }
+        return *this;
+    }
+    ~Bytes() { std::free(p_); }
+    uint8_t *data() { return p_; }
+    const uint8_t *data() const { return p_; }
+    size_t size() const { return n_; }
+    bool empty() const { return n_ == 0; }
+    void clear() { n_ = 0; }
+    void reserve(size_t cap) {
+        if (cap <= cap_) return;
+        size_t want = cap_ ? cap_ : (size_t)1 << 16;
+        while (want < cap) want += want / 2 + 4096;
+        void *q = std::realloc(p_, want);
+        if (!q) throw std::bad_alloc();
+        p_ = static_cast<uint8_t *>(q);
+        cap_ = want;
+    }
+    void resize(size_t n) { // new bytes are NOT initialised
+        reserve(n);
+        n_ = n;
+    }
+    void append(const void *src, size_t n) {
+        if (!n) return;
+        reserve(n_ + n);
+        std::memcpy(p_ + n_, src, n);
+        n_ += n;
+    }
+    void push_back(uint8_t b) {
+        reserve(n_ + 1);
+        p_[n_++] = b;
+    }
+    uint8_t back() const { return p_[n_ - 1]; }
+    void pop_back() { n_--; }
+
+  private:
+    uint8_t *p_ = nullptr;
+    size_t n_ = 0, cap_ = 0;
+};
+
 // One buffer of records (populate_buffer, src/lib.rs:168-188): sequences concatenated, with
 // prefix-sum offsets — exactly what brgpu_correct_batch / brgpu_reads_upload take.
 struct Chunk {
     std::vector<std::string> definitions; // without the leading '>' and the line end
-    std::vector<uint8_t> seq;
+    Bytes seq;
     std::vector<uint64_t> offsets{0};
     size_t size() const { return definitions.size(); }
     void clear() {
@@ -82,14 +143,14 @@ class Reader {
         if (pos_ == end_ && !fill()) return -1;
         return (unsigned char)buf_[pos_];
     }
-    // appends the rest of the current line (without the line end) to dst
-    template <class Sink> void take_line(Sink &dst) {
+    // the rest of the current line (without the line end) -> dst (a std::string: definition lines)
+    void take_line(std::string &dst) {
         for (;;) {
             if (pos_ == end_ && !fill()) break;
             const char *p = buf_.data() + pos_;
             const char *nl = (const char *)memchr(p, '\n', end_ - pos_);
             size_t n = nl ? (size_t)(nl - p) : end_ - pos_;
-            dst.insert(dst.end(), p, p + n);
+            dst.append(p, n);
             pos_ += n;
             if (nl) {
                 pos_++;
@@ -97,6 +158,29 @@ class Reader {
             }
         }
         if (!dst.empty() && dst.back() == '\r') dst.pop_back();
+    }
+    // all sequence lines up to the next '>' (or the end of the stream) -> dst, line ends dropped:
+    // one memchr and one memcpy per line, straight out of the read buffer
+    void take_sequence(Bytes &dst) {
+        bool line_start = true;
+        size_t line_len = 0; // bytes of the current line already appended (a line may span two buffer fills)
+        for (;;) {
+            if (pos_ == end_ && !fill()) return;
+            const char *p = buf_.data() + pos_;
+            if (line_start && *p == '>') return;
+            const char *nl = (const char *)memchr(p, '\n', end_ - pos_);
+            size_t n = nl ? (size_t)(nl - p) : end_ - pos_;
+            dst.append(p, n);
+            pos_ += n;
+            line_len += n;
+            line_start = false;
+            if (nl) {
+                pos_++;
+                if (line_len && dst.back() == '\r') dst.pop_back();
+                line_start = true;
+                line_len = 0;
+            }
+        }
     }
     bool next_record(Chunk &out) {
         // skip anything before the first '>' (blank lines)
@@ -110,11 +194,7 @@ class Reader {
         std::string def;
         take_line(def);
         out.definitions.push_back(std::move(def));
-        while ((c = peek()) >= 0 && c != '>') {
-            size_t before = out.seq.size();
-            take_line(out.seq);
-            (void)before;
-        }
+        take_sequence(out.seq);
         out.offsets.push_back(out.seq.size());
         return true;
     }
@@ -135,7 +215,7 @@ class Writer {
             own_ = true;
         }
         if (!f_) throw std::runtime_error("can't create " + path);
-        setvbuf(f_, nullptr, _IOFBF, 1u << 22);
+        setvbuf(f_, nullptr, _IONBF, 0); // one fwrite per chunk: no second copy through stdio's buffer
     }
     Writer(const Writer &) = delete;
     Writer &operator=(const Writer &) = delete;
@@ -148,27 +228,34 @@ class Writer {
 
     // one chunk: definitions[i] with seq[offsets[i], offsets[i+1])
     void write(const std::vector<std::string> &definitions, const uint8_t *seq, const uint64_t *offsets) {
-        line_.clear();
+        size_t total = 0;
         for (size_t i = 0; i < definitions.size(); i++) {
-            line_.push_back('>');
-            line_.insert(line_.end(), definitions[i].begin(), definitions[i].end());
-            line_.push_back('\n');
+            const size_t n = (size_t)(offsets[i + 1] - offsets[i]);
+            total += 2 + definitions[i].size() + n + (n + LINE_BASES - 1) / LINE_BASES;
+        }
+        line_.resize(total);
+        uint8_t *w = line_.data();
+        for (size_t i = 0; i < definitions.size(); i++) {
+            *w++ = '>';
+            std::memcpy(w, definitions[i].data(), definitions[i].size());
+            w += definitions[i].size();
+            *w++ = '\n';
             const uint8_t *s = seq + offsets[i];
             const size_t n = (size_t)(offsets[i + 1] - offsets[i]);
             for (size_t p = 0; p < n; p += LINE_BASES) {
-                size_t m = n - p < LINE_BASES ? n - p : LINE_BASES;
-                line_.insert(line_.end(), s + p, s + p + m);
-                line_.push_back('\n');
+                const size_t m = n - p < LINE_BASES ? n - p : LINE_BASES;
+                std::memcpy(w, s + p, m);
+                w += m;
+                *w++ = '\n';
             }
         }
-        if (!line_.empty() && fwrite(line_.data(), 1, line_.size(), f_) != line_.size())
-            throw std::runtime_error("write error in FASTA output");
+        if (total && fwrite(line_.data(), 1, total, f_) != total) throw std::runtime_error("write error in FASTA output");
     }
 
   private:
     FILE *f_ = nullptr;
     bool own_ = false;
-    std::vector<char> line_;
+    Bytes line_;
 };
 
 } // namespace fasta
