@@ -65,6 +65,39 @@ def test_reader_handles_wrapped_crlf_empty_and_unterminated_records(tmp_path):
     assert out.read_bytes() == b">r1 desc with spaces\nACGTAC\n>empty\n>r3\nNNNNacgtTT\n>last\nGG\n"
 
 
+def test_reader_on_random_framings_and_buffer_boundaries(tmp_path):
+    """Random line widths, LF / CRLF, blank lines, records of 0..5000 bases, and a CRLF pair that
+    straddles the reader's 4 MiB buffer: the C++ reader must see the same records as the Python
+    parser, and the writer must re-wrap them at 80 columns."""
+    rng = np.random.default_rng(5)
+    recs, blob = [], bytearray()
+    for i in range(300):
+        n = int(rng.integers(0, 5000))
+        seq = bytes(np.frombuffer(b"ACGTNacgt", dtype=np.uint8)[rng.integers(0, 9, size=n)])
+        recs.append((b"r%d some description" % i, seq))
+        eol = b"\r\n" if i % 3 == 0 else b"\n"
+        blob += b">" + recs[-1][0] + eol
+        w = int(rng.integers(1, 200))
+        for p in range(0, n, w):
+            blob += seq[p : p + w] + eol
+        if i % 7 == 0:
+            blob += b"\n"
+    # one long CRLF-terminated line whose "\r" is the last byte of the first 4 MiB and "\n" the first of the next
+    pad = (1 << 22) - 1 - (len(blob) + len(b">edge\r\n")) % (1 << 22)
+    big = bytes(np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=pad)])
+    recs.append((b"edge", big + b"GATTACA"))
+    blob += b">edge\r\n" + big
+    cr = len(blob)
+    blob += b"\r\n" + b"GATTACA\r\n"
+    assert (cr + 1) % (1 << 22) == 0 and blob[cr : cr + 2] == b"\r\n"
+    src, out = tmp_path / "in.fa", tmp_path / "out.fa"
+    src.write_bytes(bytes(blob))
+    r = run(["-i", src, "-o", out, "echo"])
+    assert r.returncode == 0 and r.stderr == b""
+    expect = b"".join(b">" + d + b"\n" + b"".join(s[p : p + 80] + b"\n" for p in range(0, len(s), 80)) for d, s in recs)
+    assert out.read_bytes() == expect
+
+
 def test_echo_reads_stdin_and_writes_stdout():
     r = run(["echo"], input=b">a\nAC\nGT\n")
     assert r.returncode == 0 and r.stdout == b">a\nACGT\n" and r.stderr == b""
