@@ -239,3 +239,58 @@ def test_percent_driven_abundance_methods(gpu, oracle, k):
         s.free()
     with pytest.raises(br.BrgpuError):  # an impossible share has no threshold: Error::ComputeAbundanceThreshold
         br.Pcon.from_reads(ctx, (seq, off), k, abundance_selection="percent-least", percent=2.0)
+
+
+def test_k19_counting_and_correction_without_the_dense_oracle(gpu):
+    """k = 19 is the largest supported k (16 GiB bitfield; the oracle's dense table would need 128 GiB
+    of host memory, so it cannot replay this).  Counting (one-level partition: 2^22 buckets) is
+    checked against numpy's own canonical-k-mer counts; correction against a known answer by
+    construction: isolated substitutions in reads of a random genome, set = all genome k-mers, must
+    be repaired back to the genome by `one` (38-bit k-mer arithmetic end to end)."""
+    br, ctx = gpu
+    from kmer_numpy import numpy_canonical_indices
+
+    from br_b200 import synth
+
+    k = 19
+    rng = np.random.default_rng(19)
+    genome = synth.make_genome(30_000, seed=19)
+    seq, off, _ = synth.make_reads(genome, 12, 0.05, seed=20, mean_len=1500, min_len=200)
+    idx = numpy_canonical_indices(seq, off, k)
+    uniq, counts = np.unique(idx, return_counts=True)
+    s = br.Pcon.from_reads(ctx, (seq, off), k, abundance=2)
+    hist = s.spectrum()
+    want = np.bincount(np.minimum(counts, 255), minlength=256).astype(np.uint64)
+    want[0] = (1 << (2 * k - 1)) - uniq.size
+    assert np.array_equal(hist, want)
+    # every k-mer of the reads: solid iff its canonical form occurs more than twice; plus random k-mers (absent)
+    km = all_forward_kmers(seq[: int(off[40])], off[:41], k)
+    kidx = numpy_canonical_indices(seq[: int(off[40])], off[:41], k)
+    solid_idx = set(uniq[counts > 2].tolist())
+    assert np.array_equal(s.get_batch(km), np.array([i in solid_idx for i in kidx.tolist()], dtype=np.uint8))
+    assert not s.get_batch(rng.integers(0, 1 << 38, size=5000, dtype=np.int64).astype(np.uint64)).any()
+    s.free()
+
+    g = br.Pcon.new(ctx, k)
+    g.insert_all_kmers(genome.tobytes())
+    truth, reads = [], []
+    for _ in range(150):
+        L = int(rng.integers(400, 2500))
+        st = int(rng.integers(0, genome.size - L))
+        t = genome[st : st + L].copy()
+        r = t.copy()
+        for p in range(60, L - 60, 97):  # substitutions further apart than 2k
+            r[p] = np.frombuffer(b"ACGT", dtype=np.uint8)[(np.searchsorted(np.frombuffer(b"ACGT", dtype=np.uint8), r[p]) + 1 + p % 3) & 3]
+        truth.append(t)
+        reads.append(r)
+    rseq = np.concatenate(reads)
+    roff = np.zeros(len(reads) + 1, dtype=np.uint64)
+    roff[1:] = np.cumsum([r.size for r in reads])
+    got, got_off = br.correct_batch(br.build_methods(["one"], g, 5, 7), rseq, roff)
+    assert np.array_equal(got_off, roff)  # substitutions never change a length
+    exact = sum(np.array_equal(got[int(roff[i]) : int(roff[i + 1])], truth[i]) for i in range(len(reads)))
+    assert exact >= 145, exact  # a repair can be ambiguous by chance; nearly all reads must come back exactly
+    same, _ = br.correct_batch(br.build_methods(["one", "two", "graph", "greedy", "gap_size"], g, 5, 7),
+                               np.concatenate(truth), roff)
+    assert np.array_equal(same, np.concatenate(truth))  # error-free reads are left alone by every method
+    g.free()
