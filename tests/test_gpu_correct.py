@@ -368,3 +368,37 @@ def test_async_staging_pipeline_matches_the_synchronous_calls(gpu, fixture_sets,
         prev[1].free()
     # an upload that nobody consumes is still released cleanly
     br.Reads.upload_async(ctx, *chunks[0]).free()
+
+
+def test_output_capacity_contract(gpu, fixture_sets, fixture_reads):
+    """Caller-owned output buffers (include/brgpu.h, ownership row of SURVEY section 8b): too small a
+    buffer is BRGPU_E_OVERFLOW with the needed size in *required, nothing is written past the
+    capacity, and a second call with that size succeeds."""
+    import ctypes as C
+
+    from br_b200 import _lib
+    from br_b200.runtime import _ptr
+
+    br, ctx = gpu
+    gs, _ = fixture_sets
+    seq, off = fixture_reads
+    sub = np.ascontiguousarray(off[:21])
+    ids = np.array([_lib.ONE, _lib.TWO], dtype=np.uint8)
+    exp, exp_off = br.correct_batch(br.build_methods(["one", "two"], gs, 5, 7), seq, sub)
+    small = np.full(1000 + 16, 0xEE, dtype=np.uint8)
+    out_off = np.zeros(sub.size, dtype=np.uint64)
+    req = C.c_uint64()
+    st = _lib.lib.brgpu_correct_batch(ctx._h, gs._h, _ptr(ids), ids.size, 5, 7, 0, _ptr(seq), _ptr(sub), sub.size - 1,
+                                      _ptr(small), 1000, _ptr(out_off), C.byref(req))
+    assert st == _lib.E_OVERFLOW and req.value == exp.size
+    assert (small[1000:] == 0xEE).all()
+    big = np.empty(req.value, dtype=np.uint8)
+    st = _lib.lib.brgpu_correct_batch(ctx._h, gs._h, _ptr(ids), ids.size, 5, 7, 0, _ptr(seq), _ptr(sub), sub.size - 1,
+                                      _ptr(big), big.size, _ptr(out_off), C.byref(req))
+    assert st == _lib.OK and np.array_equal(big, exp) and np.array_equal(out_off, exp_off)
+    # Corrector::correct for one read through brgpu_correct_one
+    read = np.ascontiguousarray(seq[int(off[3]) : int(off[4])])
+    n = C.c_uint64()
+    tiny = np.empty(10, dtype=np.uint8)
+    st = _lib.lib.brgpu_correct_one(ctx._h, gs._h, _lib.ONE, 5, 7, _ptr(read), read.size, _ptr(tiny), tiny.size, C.byref(n))
+    assert st == _lib.E_OVERFLOW and n.value > 10
