@@ -7,21 +7,29 @@ A step is one pass of the whole hot path over one batch of synthetic reads:
     Counter::new + count + spectrum + threshold (src/main.rs:72-115)  then
     run_correction's chunk body with methods `one two`, confirm 5, reversed pass on
     (src/lib.rs:44-55) over every read.
-Workload at N = 1: BASELINE.json configs[1] — synthetic 4.6 Mb genome (seed 42), 30x ONT-like
-reads (seed 43), 10 % error, k = 17, -a 2.  At N > 1 the genome is N x 4.6 Mb and every rank owns
-30 x 4.6 Mb of reads (weak scaling): per-rank count tables are merged with the saturating
-reduce-scatter over NVLink peer memory, the bitfield slices are all-gathered with NCCL, and each
-rank corrects its own reads.
+Headline workload at N = 1: BASELINE.json configs[1] — synthetic 4.6 Mb genome (seed 42), 30x
+ONT-like reads (seed 43), 10 % error, k = 17, -a 2.  At N > 1 the genome is N x 4.6 Mb and every
+rank owns 30 x 4.6 Mb of reads (weak scaling): every rank partitions its own k-mers, rank r counts
+bucket range r over all ranks' partitions (pulled over NVLink peer memory), the bitfield slices are
+all-gathered with NCCL, and each rank corrects its own reads.  Reads are generated on the device
+(brgpu_reads_synth, counter-based; br_b200/synth.py is the numpy mirror the CPU arm uses).
 
 `value`  : bases/s with the reads already resident in HBM (device-resident handles in and out).
 `e2e`    : the same metric through the host-buffer calls — pinned host reads are copied to the
            device and the corrected reads are copied back inside the timed region, every step.
-`roofline`: the dominant kernel's achieved algorithmic bytes/s over measured HBM bandwidth,
-           timed with CUDA events on the launching stream inside the timed region.
+`roofline`: the dominant kernel against the ceiling that bounds it ("issue": warp instructions per
+           second, "l2": random gathers per second measured in this run, "hbm": algorithmic bytes
+           per second over the measured copy bandwidth); `kernels` holds the same for every kernel,
+           forward and reversed passes separately, timed with CUDA events on the launching stream.
+`parity_check`: untimed, after the timed regions, on the benched data itself.
+`extra`  : the other BASELINE configs this run can hold — configs[2] (graph + greedy + gap_size) at
+           N = 1, configs[3] (100 Mb genome, 50x, 12 %, reads sharded: strong scaling) at N >= 2.
 `cpu_baseline` / `--impl reference`: the CPU restatement of br (oracle/, C++ + OpenMP on all host
            cores; the Rust reference cannot be built in this image) on a bounded sample.
 """
 import argparse
+import hashlib
+import importlib.util
 import json
 import os
 import subprocess
@@ -43,32 +51,58 @@ MAX_SEARCH = 7
 GENOME_PER_GPU = 4_600_000
 COVERAGE = 30
 ERROR = 0.10
+GENOME_SEED = 42
+READ_SEED = 43
 METRIC = "corrected bases/sec (count + threshold + correct, whole pipeline)"
 UNIT = "bases/s"
+CONFIG3 = {"genome": 100_000_000, "coverage": 50, "error": 0.12}  # BASELINE.json configs[3]
+CONFIG2_METHODS = ["graph", "greedy", "gap_size"]                  # BASELINE.json configs[2]
 
 
-def workload_name(n_gpus, genome_per_gpu):
+def load_synth():
+    """br_b200/synth.py by path: the CPU arm must not load the package (and with it libbrgpu.so)."""
+    spec = importlib.util.spec_from_file_location("brgpu_synth", ROOT / "br_b200" / "synth.py")
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def workload_name(n_gpus, genome_per_gpu, methods=None):
     g = genome_per_gpu * n_gpus / 1e6
-    return (f"synthetic {g:.1f} Mb genome (seed 42), {COVERAGE}x ONT-like reads (seed 43+rank), "
-            f"{int(ERROR * 100)}% error, k={K}, -a {ABUNDANCE}, methods {'+'.join(METHODS)}, confirm {CONFIRM}, "
+    return (f"synthetic {g:.1f} Mb genome (seed {GENOME_SEED}), {COVERAGE}x ONT-like reads (seed {READ_SEED}+rank), "
+            f"{int(ERROR * 100)}% error, k={K}, -a {ABUNDANCE}, methods {'+'.join(methods or METHODS)}, confirm {CONFIRM}, "
             f"reversed pass on")
 
 
-def make_shard(n_gpus, rank, genome_per_gpu):
-    from br_b200 import synth
+def headline_descriptors(synth, n_gpus, rank, genome_per_gpu):
+    """Every rank draws its reads from the whole (N x 4.6 Mb) genome; its share is 30 x 4.6 Mb of bases."""
+    start, tlen, strand = synth.read_descriptors(genome_per_gpu * n_gpus, COVERAGE / n_gpus, seed=READ_SEED + rank)
+    return {"genome_seed": GENOME_SEED, "read_seed": READ_SEED + rank, "first": 0, "start": start, "tlen": tlen,
+            "strand": strand, "thr": synth.error_thresholds(ERROR)}
 
-    genome = synth.make_genome(genome_per_gpu * n_gpus, seed=42)
-    # every rank draws reads from the whole genome; its share is COVERAGE x genome_per_gpu bases
-    seq, off, _ = synth.make_reads(genome, COVERAGE / n_gpus, ERROR, seed=43 + rank)
-    return seq, off
+
+def config3_descriptors(synth, n_gpus, rank):
+    """One 100 Mb genome, 50x, 12 %: the read list is global, rank r takes a contiguous range of it."""
+    start, tlen, strand = synth.read_descriptors(CONFIG3["genome"], CONFIG3["coverage"], seed=READ_SEED)
+    lo, hi = synth.shard_descriptors(tlen, n_gpus, rank)
+    return {"genome_seed": GENOME_SEED, "read_seed": READ_SEED, "first": lo, "start": start[lo:hi], "tlen": tlen[lo:hi],
+            "strand": strand[lo:hi], "thr": synth.error_thresholds(CONFIG3["error"]), "n_reads_total": int(tlen.size),
+            "template_bases_total": int(tlen.astype(np.int64).sum())}
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
 
 
 def peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
         d = json.loads(p.read_text())
-        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    return 6650.0, "fallback (B200_PROFILING.md)"
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)", float(d.get("sm_max_mhz", 1965.0))
+    return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
 
 
 class ClockSampler:
@@ -125,10 +159,10 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------
 # CPU arm: the oracle (C++ restatement of br) with OpenMP on all host cores
 # ----------------------------------------------------------------------------------------------
-def cpu_pipeline_sample(seq, off, total_bases_all_shards, n_shards, threads, correct_target_s=6.0):
+def cpu_pipeline_sample(seq, off, total_bases_all_shards, n_shards, threads, methods, correct_target_s=6.0, keep_solid=False):
     """Times the CPU restatement on a bounded sample of the workload and extrapolates linearly
     in the parts that are linear (counting after the table is touched; correction over reads).
-    Returns (bases/s for the whole workload, description of the sample)."""
+    Returns (bases/s for the whole workload, description of the sample, oracle Solid or None)."""
     from oracle import br_oracle as o
 
     n = off.size - 1
@@ -148,7 +182,7 @@ def cpu_pipeline_sample(seq, off, total_bases_all_shards, n_shards, threads, cor
         t_count_warm = time.perf_counter() - t0
     del c
     # correction: grow the sample until it costs about correct_target_s
-    ids = [o.METHOD_IDS[m] for m in METHODS]
+    ids = [o.METHOD_IDS[m] for m in methods]
     ns = max(1, n // 64)
     while True:
         t0 = time.perf_counter()
@@ -158,38 +192,50 @@ def cpu_pipeline_sample(seq, off, total_bases_all_shards, n_shards, threads, cor
             break
         ns = min(n, max(ns * 2, int(ns * correct_target_s / max(t_corr, 1e-3))))
     sample_bases = int(off[ns]) - int(off[0])
-    t_full = t_count_cold + (n_shards - 1) * t_count_warm + t_passes + t_corr * (total_bases_all_shards / sample_bases)
-    desc = (f"count of one {int(off[-1]) / 1e6:.0f} Mbase shard into a fresh 2^{2 * K - 1}-counter table ({t_count_cold:.2f} s"
-            f"{', warm recount %.2f s x %d' % (t_count_warm, n_shards - 1) if n_shards > 1 else ''}) + spectrum and threshold "
-            f"passes ({t_passes:.2f} s) measured in full; correction measured on the first {ns} reads "
-            f"({sample_bases / 1e6:.1f} Mbases, {t_corr:.2f} s) and scaled linearly to {total_bases_all_shards / 1e6:.0f} Mbases")
-    return total_bases_all_shards / t_full, desc
+    shard_bases = int(off[-1]) - int(off[0])
+    # counting is linear in the bases once the table is touched: the measured shard stands for the rest
+    other = max(0.0, total_bases_all_shards - shard_bases)
+    t_count_rest = (t_count_warm if n_shards > 1 else 0.0) * other / max(1, shard_bases)
+    t_full = t_count_cold + t_count_rest + t_passes + t_corr * (total_bases_all_shards / sample_bases)
+    desc = (f"count of a {shard_bases / 1e6:.0f} Mbase shard into a fresh 2^{2 * K - 1}-counter table ({t_count_cold:.2f} s"
+            f"{', warm recount %.2f s scaled to the other %.0f Mbases' % (t_count_warm, other / 1e6) if n_shards > 1 else ''}) "
+            f"+ spectrum and threshold passes ({t_passes:.2f} s) measured in full; correction ({'+'.join(methods)}) measured on "
+            f"the first {ns} reads ({sample_bases / 1e6:.1f} Mbases, {t_corr:.2f} s) and scaled linearly to "
+            f"{total_bases_all_shards / 1e6:.0f} Mbases")
+    return total_bases_all_shards / t_full, desc, (solid if keep_solid else None)
 
 
 def run_reference(args, world, rank):
-    """--impl reference: the CPU implementation of the path on the host cores (rank 0 only)."""
+    """--impl reference: the CPU implementation of the path on the host cores (rank 0 only).  The thread
+    count comes from the process's CPU affinity, not from OMP_NUM_THREADS (torch.distributed.run exports
+    OMP_NUM_THREADS=1 to its workers)."""
     if rank != 0:
         return
     from oracle import br_oracle as o
 
     o.build()
-    threads = o.max_threads()
-    seq, off = make_shard(args.gpus, 0, args.genome_per_gpu)
+    synth = load_synth()
+    threads = host_cores()
+    d = headline_descriptors(synth, args.gpus, 0, args.genome_per_gpu)
+    seq, off = synth.host_reads(d["genome_seed"], d["read_seed"], d["first"], d["start"], d["tlen"], d["strand"], d["thr"])
     total = int(off[-1]) * args.gpus
     vals, desc = [], ""
-    for it in range(args.warmup + args.steps):
-        v, desc = cpu_pipeline_sample(seq, off, total, args.gpus, threads)
-        if it >= args.warmup:
-            vals.append(v)
+    # the CPU pipeline takes seconds per pass: one untimed-quality pass would cost as much as a timed one,
+    # so it is measured once plus one repeat whatever --steps / --warmup say
+    for _ in range(2):
+        v, desc, _ = cpu_pipeline_sample(seq, off, total, args.gpus, threads, METHODS)
+        vals.append(v)
     value = float(np.mean(vals))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / value, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         "config": {"workload": workload_name(args.gpus, args.genome_per_gpu)},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc,
+                         "repeats": [round(x) for x in vals]},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "CPU restatement of br (oracle/, C++17 + OpenMP); the Rust reference cannot be built in this image",
+        "note": "CPU restatement of br (oracle/, C++17 + OpenMP); the Rust reference cannot be built in this image; "
+                "measured twice (not warmup + steps times): each pass is seconds of CPU work",
     }
     print(json.dumps(line), flush=True)
 
@@ -197,22 +243,61 @@ def run_reference(args, world, rank):
 # ----------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------
-def algo_bytes(name, prof, n_bases, n_kmers, table, scan_lookups_per_step):
+def algo_bytes(name, p, n_bases, n_kmers, table):
     """SURVEY §8(d) algorithmic bytes per launch for each kernel of the step."""
-    if name == "count_kmers":
+    base = name[:-4] if name.endswith("_rev") else name
+    if base == "count_kmers":
         return 0.25 * n_bases + 64.0 * n_kmers
-    if name == "zero_counts":
+    if base == "zero_counts":
         return float(table)
-    if name == "spectrum_threshold":
+    if base == "spectrum_threshold":
         return table * 1.125
-    if name == "spectrum":
+    if base == "spectrum":
         return float(table)
-    if name == "solid_bitmap":
-        return 32.0 * n_kmers + 0.25 * n_bases + n_bases / 8.0
-    if name.startswith("scan_"):
-        # read + write of the ASCII bases and one 32 B sector per KmerSet::get the scan issued
-        return 2.0 * n_bases + 32.0 * scan_lookups_per_step / max(1, sum(1 for k in prof if k.startswith("scan_")))
-    return prof[name]["algo_bytes"] / max(1, prof[name]["launches"])
+    lookups = p["lookups"] / max(1, p["launches"])
+    if base == "solid_bitmap":  # one sector per lookup it really issued + the ASCII stream in + 1 bit out per position
+        return 32.0 * lookups + 0.25 * n_bases + n_bases / 8.0
+    if base.startswith("scan_") or base.startswith("merge_"):
+        # read + write of the ASCII bases and one 32 B sector per KmerSet::get this launch issued
+        return 2.0 * n_bases + 32.0 * lookups
+    return p["algo_bytes"] / max(1, p["launches"])
+
+
+def kernel_table(prof, steps, n_bases, n_kmers, table, hbm_peak, issue_peak, l2_gather, counters):
+    """Per-kernel record: time, share, §8(d) byte view, and the ceiling that bounds the kernel."""
+    out = {}
+    tot = sum(p["ms"] for p in prof.values())
+    for name, p in prof.items():
+        per_ms = p["ms"] / max(1, p["launches"])
+        ab = algo_bytes(name, p, n_bases, n_kmers, table)
+        gbs = ab / (per_ms * 1e-3) / 1e9 if per_ms > 0 else 0.0
+        lookups = p["lookups"] / max(1, p["launches"])
+        rec = {"launches_per_step": p["launches"] / steps, "ms_per_launch": round(per_ms, 4),
+               "share_of_kernel_time": round(p["ms"] / tot, 4) if tot else 0.0,
+               "lookups_per_launch": lookups, "algo_bytes_per_launch": ab,
+               "hbm_view": {"achieved_gbs": round(gbs, 1), "frac_of_hbm": round(gbs / hbm_peak, 4)}}
+        c = counters.get(name)
+        if c:
+            rec["warp_inst_per_launch_ncu"] = c.get("warp_inst_per_launch")
+            rec["dram_bytes_per_launch_ncu"] = c.get("dram_bytes_per_launch")
+        base = name[:-4] if name.endswith("_rev") else name
+        dram = c.get("dram_bytes_per_launch") if c else None
+        inst = c.get("warp_inst_per_launch") if c else None
+        if base == "solid_bitmap" and l2_gather:
+            ach = lookups / (per_ms * 1e-3) if per_ms > 0 else 0.0
+            rec["bound"] = {"bound": "l2", "achieved": round(ach / 1e9, 2), "peak": round(l2_gather / 1e9, 2),
+                            "unit": "G lookups/s vs G random 8 B gathers/s (64 MiB table, measured in this run)",
+                            "frac": round(ach / l2_gather, 4)}
+        elif (base.startswith("scan_") or base.startswith("merge_") or (dram is not None and dram < 0.5 * ab)) and inst:
+            ach = inst / (per_ms * 1e-3) if per_ms > 0 else 0.0
+            rec["bound"] = {"bound": "issue", "achieved": round(ach / 1e12, 4), "peak": round(issue_peak / 1e12, 4),
+                            "unit": "T warp instructions/s (instructions per launch from the committed ncu capture)",
+                            "frac": round(ach / issue_peak, 4)}
+        else:
+            rec["bound"] = {"bound": "hbm", "achieved": round(gbs, 1), "peak": hbm_peak, "unit": "GB/s",
+                            "frac": round(gbs / hbm_peak, 4)}
+        out[name] = rec
+    return out
 
 
 def run_ours(args, world, rank, local_rank):
@@ -226,6 +311,7 @@ def run_ours(args, world, rank, local_rank):
     torch.cuda.set_device(local_rank)
     from br_b200.runtime import bind_to_gpu_numa_node
 
+    synth = load_synth()
     numa_node = bind_to_gpu_numa_node(local_rank) if world > 1 else None  # before any pinned allocation
     tdist = None
     if world > 1:
@@ -234,80 +320,101 @@ def run_ours(args, world, rank, local_rank):
         tdist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     stream = torch.cuda.Stream()
     ctx = br_b200.Context(local_rank, stream=stream)
-
-    seq, off = make_shard(world, rank, args.genome_per_gpu)
-    n_reads = off.size - 1
-    n_bases = int(off[-1])
-    lens = np.diff(off.astype(np.int64))
-    n_kmers = int(np.maximum(lens - K + 1, 0).sum())
+    dev = f"cuda:{local_rank}"
     table = 1 << (2 * K - 1)
 
-    # pinned host buffers (what a host application would hand to the C ABI)
-    h_seq = torch.from_numpy(seq).pin_memory()
-    h_off = torch.from_numpy(off.view(np.int64)).pin_memory()
-    out_cap = n_bases + n_bases // 8 + 64 * n_reads + 64
-    h_out = torch.empty(out_cap, dtype=torch.uint8).pin_memory()
-    h_out_off = torch.empty(n_reads + 1, dtype=torch.int64).pin_memory()
+    def barrier():
+        torch.cuda.synchronize()
+        if tdist is not None:
+            tdist.barrier()
+        torch.cuda.synchronize()
 
-    def build_set(reads, c=None):
-        c = c or ctx
+    def all_max(x):
+        if tdist is None:
+            return float(x)
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+        return float(t.item())
+
+    def all_sum(x):
+        if tdist is None:
+            return int(x)
+        t = torch.tensor([int(x)], dtype=torch.int64, device=dev)
+        tdist.all_reduce(t)
+        return int(t.item())
+
+    def all_and(flag):
+        if tdist is None:
+            return bool(flag)
+        t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=dev)
+        tdist.all_reduce(t, op=tdist.ReduceOp.MIN)
+        return bool(t.item())
+
+    def timed(fn, steps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        a.record(stream)
+        for _ in range(steps):
+            fn()
+        b.record(stream)
+        barrier()
+        return all_max(a.elapsed_time(b))
+
+    def build_set(reads):
         if world == 1:
-            return br_b200.Pcon.from_reads(c, reads, K, abundance=ABUNDANCE)
-        return bdist.build_set_sharded(bdist.GpuOps(c, reads), K, abundance=ABUNDANCE)
+            return br_b200.Pcon.from_reads(ctx, reads, K, abundance=ABUNDANCE)
+        return bdist.build_set_sharded(bdist.GpuOps(ctx, reads), K, abundance=ABUNDANCE)
 
-    def step_device(reads):
-        solid = build_set(reads)
-        out = br_b200.correct_reads(br_b200.build_methods(METHODS, solid, CONFIRM, MAX_SEARCH), reads)
+    class Workload:
+        """Device-resident reads of one config + the pinned host buffers of its e2e steps."""
+
+        def __init__(self, desc):
+            self.desc = desc
+            self.dev_reads = br_b200.Reads.synth(ctx, desc["genome_seed"], desc["read_seed"], desc["first"], desc["start"],
+                                                 desc["tlen"], desc["strand"], desc["thr"])
+            self.n_reads = len(self.dev_reads)
+            self.n_bases = int(self.dev_reads.bases)
+            self.h_seq = torch.empty(max(1, self.n_bases), dtype=torch.uint8).pin_memory()
+            self.h_off = torch.empty(self.n_reads + 1, dtype=torch.int64).pin_memory()
+            self.dev_reads.download(self.h_seq, self.h_off)   # what a host application would hand to the C ABI
+            off = self.h_off.numpy().view(np.uint64)
+            lens = np.diff(off.astype(np.int64))
+            self.n_kmers = int(np.maximum(lens - K + 1, 0).sum())
+            out_cap = self.n_bases + self.n_bases // 8 + 64 * self.n_reads + 64
+            self.out_bufs = [(torch.empty(out_cap, dtype=torch.uint8).pin_memory(),
+                              torch.empty(self.n_reads + 1, dtype=torch.int64).pin_memory()) for _ in range(2)]
+
+        def seq_off(self):
+            return self.h_seq.numpy()[: self.n_bases], self.h_off.numpy().view(np.uint64)
+
+        def free(self):
+            self.dev_reads.free()
+            self.h_seq = self.h_off = self.out_bufs = None
+
+    def step_device(wl, methods, keep=False):
+        solid = build_set(wl.dev_reads)
+        out = br_b200.correct_reads(br_b200.build_methods(methods, solid, CONFIRM, MAX_SEARCH), wl.dev_reads)
+        if keep:
+            return solid, out
         out.free()
         solid.free()
 
-    # e2e: every step uploads its inputs from pinned host memory and downloads its result inside
-    # the timed region, through the host-buffer API.  The steps are pipelined — by default on one
-    # context whose copy stream carries step i+1's upload and step i-1's download while step i's
-    # kernels run (`stream`; one host thread, so the collectives of the sharded set construction
-    # keep one order per rank); at N = 1 alternatively on several contexts driven by host threads
-    # (`lanes`); `serial` = one step at a time.
-    e2e_mode = "serial" if args.no_e2e_pipeline else args.e2e_mode
-    if world > 1 and e2e_mode == "lanes":
-        e2e_mode = "stream"  # host threads would issue the collectives of two steps in no fixed order
-    out_bufs = [(h_out, h_out_off)]
-    if e2e_mode == "stream":
-        out_bufs.append((torch.empty_like(h_out).pin_memory(), torch.empty_like(h_out_off).pin_memory()))
-    lanes = [(ctx, h_out, h_out_off)]
-    if e2e_mode == "lanes":
-        for _ in range(max(1, args.e2e_lanes) - 1):
-            cx = br_b200.Context(local_rank, stream=torch.cuda.Stream())
-            lanes.append((cx, torch.empty_like(h_out).pin_memory(), torch.empty_like(h_out_off).pin_memory()))
-
-    def step_e2e(lane=0):
-        c, o, oo = lanes[lane]
-        reads = br_b200.Reads.upload(c, h_seq, h_off)            # H2D every step
-        solid = build_set(reads, c)
-        out = br_b200.correct_reads(br_b200.build_methods(METHODS, solid, CONFIRM, MAX_SEARCH), reads)
-        d, _ = out.download(o, oo)                                # D2H every step
-        nbytes = int(d.numel())
-        out.free()
-        solid.free()
-        reads.free()
-        return nbytes
-
-    def run_e2e_stream(n_steps, stamps=None):
+    def run_e2e_stream(wl, methods, n_steps, stamps=None):
         """n_steps e2e steps on ONE context with the asynchronous staging calls: step i+1's reads go
         up and step i-1's result comes down on the context's copy stream while step i's kernels run.
         Every step still uploads its own inputs and downloads its own result."""
-        c = ctx
         res = 0
-        nxt = br_b200.Reads.upload_async(c, h_seq, h_off)
+        nxt = br_b200.Reads.upload_async(ctx, wl.h_seq, wl.h_off)
         prev = None
         t0 = time.perf_counter()
         for i in range(n_steps):
             cur = nxt
             if i + 1 < n_steps:
-                nxt = br_b200.Reads.upload_async(c, h_seq, h_off)           # H2D of the next step
+                nxt = br_b200.Reads.upload_async(ctx, wl.h_seq, wl.h_off)           # H2D of the next step
             if prev is not None:
-                res = max(res, prev.download_async(*out_bufs[(i - 1) % 2]))  # D2H of the previous step
-            solid = build_set(cur, c)
-            out = br_b200.correct_reads(br_b200.build_methods(METHODS, solid, CONFIRM, MAX_SEARCH), cur)
+                res = max(res, prev.download_async(*wl.out_bufs[(i - 1) % 2]))       # D2H of the previous step
+            solid = build_set(cur)
+            out = br_b200.correct_reads(br_b200.build_methods(methods, solid, CONFIRM, MAX_SEARCH), cur)
             solid.free()
             cur.free()
             if prev is not None:
@@ -318,57 +425,64 @@ def run_ours(args, world, rank, local_rank):
                 t1 = time.perf_counter()
                 stamps.append(round((t1 - t0) * 1e3, 2))
                 t0 = t1
-        res = max(res, prev.download_async(*out_bufs[(n_steps - 1) % 2]))
+        res = max(res, prev.download_async(*wl.out_bufs[(n_steps - 1) % 2]))
         prev.download_wait()
         prev.free()
         return res
 
-    def run_e2e(n_steps, stamps=None):
-        """n_steps e2e steps spread over the lanes; returns the D2H bytes of one step."""
-        if e2e_mode == "stream":
-            return run_e2e_stream(n_steps, stamps)
-        res = [0] * len(lanes)
+    def run_e2e_serial(wl, methods, n_steps, stamps=None):
+        res = 0
+        for _ in range(n_steps):
+            t0 = time.perf_counter()
+            reads = br_b200.Reads.upload(ctx, wl.h_seq, wl.h_off)            # H2D every step
+            solid = build_set(reads)
+            out = br_b200.correct_reads(br_b200.build_methods(methods, solid, CONFIRM, MAX_SEARCH), reads)
+            d, _ = out.download(*wl.out_bufs[0])                              # D2H every step
+            res = max(res, int(d.numel()))
+            out.free()
+            solid.free()
+            reads.free()
+            if stamps is not None:
+                stamps.append(round((time.perf_counter() - t0) * 1e3, 2))
+        return res
 
-        def work(lane, n):
-            for _ in range(n):
-                t0 = time.perf_counter()
-                res[lane] = step_e2e(lane)
-                if stamps is not None:
-                    stamps.append(round((time.perf_counter() - t0) * 1e3, 2))
+    e2e_mode = "serial" if args.no_e2e_pipeline else args.e2e_mode
+    run_e2e = run_e2e_stream if e2e_mode == "stream" else run_e2e_serial
 
-        share = [n_steps // len(lanes) + (1 if i < n_steps % len(lanes) else 0) for i in range(len(lanes))]
-        if len(lanes) == 1:
-            work(0, n_steps)
-        else:
-            import threading
-
-            ts = [threading.Thread(target=work, args=(i, share[i])) for i in range(len(lanes))]
-            for t in ts:
-                t.start()
-            for t in ts:
-                t.join()
-        return max(res)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if tdist is not None:
-            tdist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        a.record(stream)
-        for _ in range(steps):
-            fn()
-        b.record(stream)
-        barrier()
-        ms = a.elapsed_time(b)
-        if tdist is not None:
-            t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local_rank}")
-            tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
+    def measure(wl, methods, steps, warmup, want_e2e=True, e2e_warm_extra=12):
+        """value, per-kernel profile and e2e of `methods` over `wl`; returns a dict of raw numbers."""
+        for _ in range(warmup):
+            step_device(wl, methods)
+        launches0 = ctx.launch_count
+        ms_dev = timed(lambda: step_device(wl, methods), steps)       # ---- device-resident region: `value`
+        launches = ctx.launch_count - launches0
+        # the same steps again with a CUDA-event pair around every kernel and the scans' KmerSet::get
+        # counters on (the event records perturb the step a little: `value` comes from the region above)
+        ctx.profile_reset()
+        ctx.profile_enable(True)
+        ms_prof = timed(lambda: step_device(wl, methods), steps)
+        prof = ctx.profile()
+        ctx.profile_enable(False)
+        res = {"ms_dev": ms_dev, "launches": launches, "ms_prof": ms_prof, "prof": prof}
+        if not want_e2e:
+            return res
+        # end-to-end region: warm up until two consecutive rounds agree within 3 % (the first e2e steps
+        # size the allocator's cache for the upload / download buffers)
+        d2h, warm_ms = 0, []
+        for it in range(max(3, warmup) + e2e_warm_extra):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            n_warm = 4 if e2e_mode == "stream" else 1
+            d2h = max(d2h, run_e2e(wl, methods, n_warm))
+            torch.cuda.synchronize()
+            warm_ms.append((time.perf_counter() - t0) * 1e3 / n_warm)
+            stable = it + 1 >= max(3, warmup) and abs(warm_ms[-1] - warm_ms[-2]) <= 0.03 * warm_ms[-1]
+            if all_and(stable):  # the step contains collectives: every rank must take the same decision
+                break
+        stamps = []
+        ms_e2e = timed(lambda: run_e2e(wl, methods, steps, stamps), 1)
+        res.update({"ms_e2e": ms_e2e, "d2h": d2h, "e2e_warm_ms": warm_ms, "e2e_step_ms": stamps})
+        return res
 
     # a full collection of the interpreter's heap (torch imports ~10^6 objects) costs 0.1-0.5 s and
     # would land inside a timed region: collect now, then keep the collector off while timing
@@ -377,128 +491,200 @@ def run_ours(args, world, rank, local_rank):
     gc.collect()
     gc.freeze()
     gc.disable()
+    hbm_peak, peak_src, sm_max_mhz = peaks()
     with torch.cuda.stream(stream):
-        dev_reads = br_b200.Reads.upload(ctx, h_seq, h_off)
+        wl = Workload(headline_descriptors(synth, world, rank, args.genome_per_gpu))
         # the sampler is started before the warm-up so that nvidia-smi's own start-up (NVML
         # initialisation takes driver locks) is over before the timed regions begin
         sampler = ClockSampler(local_rank)
         if rank == 0 and not os.environ.get("BRGPU_BENCH_NO_SAMPLER"):
             sampler.start()
-        for _ in range(args.warmup):
-            step_device(dev_reads)
-        # ---- device-resident timed region: `value` ----
-        launches0 = ctx.launch_count
-        ms_dev = timed(lambda: step_device(dev_reads), args.steps)
-        launches = ctx.launch_count - launches0
-        # ---- the same K steps again with a CUDA-event pair around every kernel (per-kernel
-        # durations for the roofline; the event records perturb the step a little, which is why
-        # `value` is taken from the undisturbed region above) ----
-        ctx.profile_reset()
-        ctx.profile_enable(True)
-        lookups0 = ctx.scan_lookups
-        ms_prof = timed(lambda: step_device(dev_reads), args.steps)
-        prof = ctx.profile()
-        ctx.profile_enable(False)
-        lookups = (ctx.scan_lookups - lookups0) / args.steps
-        # ---- end-to-end timed region (host buffers in and out) ----
-        # warm-up: at least W steps per lane, then until two consecutive rounds agree within 3 % (at
-        # most 12 more): the first e2e steps size the allocator's cache for the upload/download buffers
-        d2h = 0
-        e2e_warm_ms = []
-        for it in range(max(3, args.warmup) + 12):
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            n_warm = 4 if e2e_mode == "stream" else len(lanes)
-            d2h = max(d2h, run_e2e(n_warm))
-            torch.cuda.synchronize()
-            e2e_warm_ms.append((time.perf_counter() - t0) * 1e3 / n_warm)
-            stable = it + 1 >= max(3, args.warmup) and abs(e2e_warm_ms[-1] - e2e_warm_ms[-2]) <= 0.03 * e2e_warm_ms[-1]
-            if tdist is not None:  # the step contains collectives: every rank must take the same decision
-                t = torch.tensor([1 if stable else 0], dtype=torch.int32, device=f"cuda:{local_rank}")
-                tdist.all_reduce(t, op=tdist.ReduceOp.MIN)
-                stable = bool(t.item())
-            if stable:
-                break
-        e2e_step_ms = []  # host clock, whole steps (every e2e step ends in a synchronising download)
-        ms_e2e = timed(lambda: run_e2e(args.steps, e2e_step_ms), 1)
+        m = measure(wl, METHODS, args.steps, args.warmup)
         clocks = sampler.stop() if rank == 0 else None
+        total_bases = all_sum(wl.n_bases)
 
-    total_bases = n_bases
-    if tdist is not None:
-        t = torch.tensor([n_bases], dtype=torch.int64, device=f"cuda:{local_rank}")
-        tdist.all_reduce(t)
-        total_bases = int(t.item())
+        # ---- yardsticks measured in this run ----
+        l2_gather = ctx.probe_random_gather(64 << 20)
+        dram_gather = ctx.probe_random_gather(8 << 30)
+
+        # ---- parity on the benched data (untimed) ----
+        parity = None
+        if not args.no_parity:
+            parity = parity_check(args, ctx, wl, world, rank, tdist, dev, step_device, all_and)
+
+        # ---- the other configs this run can hold ----
+        extra = {}
+        if not args.no_extra:
+            if world == 1:
+                steps2, warm2 = max(1, min(args.steps, 3)), max(1, min(args.warmup, 2))
+                m2 = measure(wl, CONFIG2_METHODS, steps2, warm2, e2e_warm_extra=4)
+                extra["configs[2]"] = leg_record(m2, wl, wl.n_bases, steps2, warm2, table, hbm_peak, sm_max_mhz, l2_gather,
+                                                 workload_name(1, args.genome_per_gpu, CONFIG2_METHODS), "weak", world)
+            else:
+                wl.free()
+                wl3 = Workload(config3_descriptors(synth, world, rank))
+                steps3, warm3 = 2, 1
+                m3 = measure(wl3, METHODS, steps3, warm3, e2e_warm_extra=2)
+                total3 = all_sum(wl3.n_bases)
+                name3 = (f"synthetic {CONFIG3['genome'] / 1e6:.0f} Mb genome (seed {GENOME_SEED}), {CONFIG3['coverage']}x ONT-like "
+                         f"reads (seed {READ_SEED}), {int(CONFIG3['error'] * 100)}% error, k={K}, -a {ABUNDANCE}, methods "
+                         f"{'+'.join(METHODS)}, confirm {CONFIRM}, reversed pass on; reads sharded over {world} GPUs")
+                extra["configs[3]"] = leg_record(m3, wl3, total3, steps3, warm3, table, hbm_peak, sm_max_mhz, l2_gather, name3,
+                                                 "strong", world)
+                if not args.no_parity:
+                    extra["configs[3]"]["parity_check"] = parity_check(args, ctx, wl3, world, rank, tdist, dev, step_device,
+                                                                        all_and, single_gpu_rebuild=False)
+                wl3.free()
+
     if rank != 0:
         if tdist is not None:
             tdist.barrier()
             tdist.destroy_process_group()
         return
 
-    value = total_bases * args.steps / (ms_dev * 1e-3)
-    e2e_value = total_bases * args.steps / (ms_e2e * 1e-3)
-    peak, peak_src = peaks()
-    kernels = {}
-    tot_kernel_ms = sum(p["ms"] for p in prof.values())
-    for name, p in prof.items():
-        per_launch_ms = p["ms"] / max(1, p["launches"])
-        ab = algo_bytes(name, prof, n_bases, n_kmers, table, lookups)
-        gbs = ab / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
-        kernels[name] = {"launches_per_step": p["launches"] / args.steps, "ms_per_launch": round(per_launch_ms, 4),
-                         "share_of_kernel_time": round(p["ms"] / tot_kernel_ms, 4) if tot_kernel_ms else 0.0,
-                         "algo_bytes_per_launch": ab, "achieved_gbs": round(gbs, 1), "frac_of_hbm": round(gbs / peak, 4)}
-    dominant = max(prof, key=lambda k_: prof[k_]["ms"])
-    dk = kernels[dominant]
-    # DRAM traffic per launch from the committed `ncu --set full` capture (profiles/summarize.py)
-    traffic, traffic_src = None, None
-    tp = ROOT / "profiles" / "traffic.json"
-    if tp.exists():
-        tj = json.loads(tp.read_text())
-        traffic_src = tj.get("source")
-        for name, kk in kernels.items():
-            if name in tj["kernels"]:
-                kk["dram_bytes_per_launch_ncu"] = tj["kernels"][name]["dram_bytes_per_launch"]
-        if dominant in tj["kernels"]:
-            traffic = tj["kernels"][dominant]["dram_bytes_per_launch"]
-    line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u64", "data": "synthetic",
-        "config": {"workload": workload_name(world, args.genome_per_gpu), "reads_per_gpu": n_reads,
-                   "bases_per_gpu": n_bases, "kmers_per_gpu": n_kmers,
-                   "l2": "no flush: every step streams more than L2 holds (155 MB of read slots per pass x 4 passes, 0.55 GB of "
-                         "partitioned k-mers, the 1 GiB bitfield written per step); the 69 MB rank-compacted copy of the "
-                         "solid set is L2 resident by design and is rebuilt every step",
-                   "parallelism": f"reads sharded over {world} GPU(s)", "rank0_numa_node": numa_node},
-        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
-                "warmup_ms_per_step": [round(x, 2) for x in e2e_warm_ms],
-                "host_clock_ms_per_step": e2e_step_ms, "mode": e2e_mode,
-                "pipeline": {"stream": "one context; step i+1's upload and step i-1's download run on its copy stream "
-                                       "(brgpu_reads_upload_async / _download_async) while step i's kernels run",
-                             "lanes": "%d contexts (streams) driven by %d host threads, steps alternate between them"
-                                      % (len(lanes), len(lanes)),
-                             "serial": "one step at a time"}[e2e_mode],
-                "h2d_bytes_per_step": int(h_seq.numel() + 8 * h_off.numel()),
-                "d2h_bytes_per_step": int(d2h + 8 * (n_reads + 1))},
-        "gpu_launches": int(launches),
-        "clocks": clocks,
-        "roofline": {"kernel": dominant, "bound": "hbm", "achieved": dk["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                     "frac": dk["frac_of_hbm"], "traffic": traffic, "traffic_source": traffic_src,
-                     "algorithmic_bytes_per_launch": dk["algo_bytes_per_launch"], "peak_source": peak_src,
-                     "scan_lookups_per_step": lookups},
-        "kernels": kernels,
-        "ms_per_step_with_kernel_events": ms_prof / args.steps,
-    }
+    line = leg_record(m, wl if world == 1 or args.no_extra else None, total_bases, args.steps, args.warmup, table, hbm_peak,
+                      sm_max_mhz, l2_gather, workload_name(world, args.genome_per_gpu), "weak", world,
+                      per_gpu=(wl.n_reads, wl.n_bases, wl.n_kmers))
+    line["config"].update({
+        "l2": "no flush: every step streams more than L2 holds (155 MB of read slots per pass x 4 passes, 0.55 GB of "
+              "partitioned k-mers, the 1 GiB bitfield written per step); the 69 MB rank-compacted copy of the "
+              "solid set is L2 resident by design and is rebuilt every step",
+        "parallelism": f"reads sharded over {world} GPU(s)", "rank0_numa_node": numa_node,
+        "generator": "counter-based (brgpu_reads_synth on the device; br_b200/synth.py host mirror)"})
+    line["e2e"]["mode"] = e2e_mode
+    line["clocks"] = clocks
+    line["roofline"]["peak_source"] = peak_src
+    line["yardsticks"] = {"hbm_copy_gbs": hbm_peak, "hbm_source": peak_src,
+                          "issue_warp_inst_per_s": 148 * 4 * sm_max_mhz * 1e6,
+                          "l2_random_gather_per_s_64MiB": l2_gather, "dram_random_gather_per_s_8GiB": dram_gather}
+    if parity is not None:
+        line["parity_check"] = parity
+    if extra:
+        line["extra"] = extra
     if world == 1 and not args.no_cpu_baseline:
         from oracle import br_oracle as o
 
         o.build()
-        th = o.max_threads()
-        v, desc = cpu_pipeline_sample(seq, off, n_bases, 1, th)
+        th = host_cores()
+        seq, off = wl.seq_off()
+        v, desc, osolid = cpu_pipeline_sample(seq, off, wl.n_bases, 1, th, METHODS, keep_solid=not args.no_parity)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": th, "kind": "port", "sample": desc}
+        if osolid is not None and parity is not None:
+            # the CPU leg counted the whole benched data set: its bitfield must be the GPU's
+            parity["bitfield_equals_oracle"] = bool(hashlib.blake2b(osolid.bits().tobytes()).hexdigest() == parity["bitfield_blake2b"])
     print(json.dumps(line), flush=True)
     if tdist is not None:
         tdist.barrier()
         tdist.destroy_process_group()
+
+
+def load_counters():
+    """Per-kernel warp instructions and DRAM bytes per launch from the committed ncu capture
+    (profiles/kernel_counters.json, written by profiles/summarize_r2.py)."""
+    p = ROOT / "profiles" / "kernel_counters.json"
+    if not p.exists():
+        return {}, None
+    d = json.loads(p.read_text())
+    return d.get("kernels", {}), d.get("source")
+
+
+def leg_record(m, wl, total_bases, steps, warmup, table, hbm_peak, sm_max_mhz, l2_gather, workload, scaling, world,
+               per_gpu=None):
+    """The JSON record of one measured workload (headline line or an `extra` leg)."""
+    counters, counters_src = load_counters()
+    if world != 1 or "4.6 Mb" not in workload:
+        counters, counters_src = {}, None  # the instruction / DRAM counts belong to the workload they were captured on
+    n_reads, n_bases, n_kmers = per_gpu if per_gpu else (wl.n_reads, wl.n_bases, wl.n_kmers)
+    issue_peak = 148 * 4 * sm_max_mhz * 1e6
+    kernels = kernel_table(m["prof"], steps, n_bases, n_kmers, table, hbm_peak, issue_peak, l2_gather, counters)
+    dominant = max(m["prof"], key=lambda k_: m["prof"][k_]["ms"])
+    dk = kernels[dominant]
+    rec = {
+        "metric": METRIC, "value": total_bases * steps / (m["ms_dev"] * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps,
+        "warmup": warmup, "ms_per_step": m["ms_dev"] / steps, "higher_is_better": True, "scaling": scaling,
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": workload, "reads_per_gpu": n_reads, "bases_per_gpu": n_bases, "kmers_per_gpu": n_kmers},
+        "gpu_launches": int(m["launches"]),
+        "roofline": dict(dk["bound"], kernel=dominant, traffic=dk.get("dram_bytes_per_launch_ncu"),
+                         traffic_source=counters_src, algorithmic_bytes_per_launch=dk["algo_bytes_per_launch"],
+                         hbm_view=dk["hbm_view"], lookups_per_launch=dk["lookups_per_launch"],
+                         warp_inst_per_launch=dk.get("warp_inst_per_launch_ncu")),
+        "kernels": kernels,
+        "ms_per_step_with_kernel_events": m["ms_prof"] / steps,
+    }
+    if "ms_e2e" in m:
+        rec["e2e"] = {"value": total_bases * steps / (m["ms_e2e"] * 1e-3), "unit": UNIT, "ms_per_step": m["ms_e2e"] / steps,
+                      "warmup_ms_per_step": [round(x, 2) for x in m["e2e_warm_ms"]],
+                      "host_clock_ms_per_step": m["e2e_step_ms"],
+                      "h2d_bytes_per_step": int(n_bases + 8 * (n_reads + 1)),
+                      "d2h_bytes_per_step": int(m["d2h"] + 8 * (n_reads + 1))}
+    return rec
+
+
+def parity_check(args, ctx, wl, world, rank, tdist, dev, step_device, all_and, single_gpu_rebuild=True, sample=200):
+    """Untimed checks on the benched data: (N > 1) every rank's replicated bitfield is the same and equals
+    the one a single GPU builds from all ranks' reads through the literal count-table path; (any N) the
+    bucketed path's bitfield equals the table path's; a sample of this rank's reads corrected on the GPU
+    equals the oracle's bytes (the oracle is given the GPU's bitfield)."""
+    import torch
+
+    import br_b200
+    from oracle import br_oracle as o
+
+    o.build()
+    res = {}
+    solid, out = step_device(wl, METHODS, keep=True)
+    bits = solid.bitfield()
+    digest = hashlib.blake2b(bits.tobytes()).hexdigest()
+    res["bitfield_blake2b"] = digest
+    if world > 1:
+        t = torch.tensor(list(bytes.fromhex(digest[:32])), dtype=torch.uint8, device=dev)
+        allt = [torch.empty_like(t) for _ in range(world)]
+        tdist.all_gather(allt, t)
+        res["bitfield_equal_across_ranks"] = all(bool(torch.equal(x, allt[0])) for x in allt)
+    # literal table path on one GPU over all ranks' reads (Counter::count per shard, Solid::from_count)
+    if single_gpu_rebuild and rank == 0:
+        synth = load_synth()
+        c = br_b200.Counter(ctx, K)
+        for r in range(world):
+            if world == 1:
+                c.count(wl.dev_reads)
+            else:
+                d = headline_descriptors(synth, world, r, args.genome_per_gpu)
+                rr = br_b200.Reads.synth(ctx, d["genome_seed"], d["read_seed"], d["first"], d["start"], d["tlen"], d["strand"], d["thr"])
+                c.count(rr)
+                rr.free()
+        ref = c.to_set(ABUNDANCE)
+        same = hashlib.blake2b(ref.bitfield().tobytes()).hexdigest() == digest
+        res["equals_single_gpu_table_path" if world > 1 else "bitfield_equals_table_path"] = bool(same)
+        ref.free()
+        c.free()
+    # oracle replay of a read sample
+    seq, off = wl.seq_off()
+    n = off.size - 1
+    ids = np.sort(np.random.default_rng(7 + rank).choice(n, size=min(sample, n), replace=False))
+    got, got_off = out.download()
+    got_off = got_off.astype(np.int64)
+    sub_off = np.zeros(ids.size + 1, dtype=np.uint64)
+    sub_off[1:] = np.cumsum((off[ids + 1] - off[ids]).astype(np.uint64))
+    sub_seq = np.concatenate([seq[int(off[i]) : int(off[i + 1])] for i in ids]) if ids.size else np.empty(0, np.uint8)
+    osolid = o.Solid.from_bitfield(K, bits)
+    exp, exp_off = osolid.run_correction([o.METHOD_IDS[x] for x in METHODS], sub_seq, sub_off, confirm=CONFIRM,
+                                         max_search=MAX_SEARCH, two_side=False, threads=min(8, host_cores()))
+    exp_off = exp_off.astype(np.int64)
+    ok = True
+    edited = 0
+    for j, i in enumerate(ids):
+        g = got[got_off[i] : got_off[i + 1]]
+        e = exp[exp_off[j] : exp_off[j + 1]]
+        ok = ok and g.size == e.size and bool(np.array_equal(g, e))
+        edited += int(e.size != int(off[i + 1] - off[i]) or not np.array_equal(e, seq[int(off[i]) : int(off[i + 1])]))
+    res["sample_reads_equal_oracle"] = all_and(ok)
+    res["sample_reads_per_rank"] = int(ids.size)
+    res["sample_reads_edited_rank0"] = edited
+    out.free()
+    solid.free()
+    return res
 
 
 def main():
@@ -513,11 +699,12 @@ def main():
     ap.add_argument("--methods", nargs="+", default=None,
                     help="method chain (default: one two = BASELINE.json configs[1]; `graph greedy gap_size` = configs[2])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-e2e-pipeline", action="store_true", help="e2e steps one at a time on a single context")
-    ap.add_argument("--e2e-mode", choices=["stream", "lanes", "serial"], default="stream",
-                    help="e2e pipeline at N = 1: `stream` = one context, copies of the neighbouring steps on its copy "
-                         "stream (default); `lanes` = several contexts driven by host threads; `serial` = one step at a time")
-    ap.add_argument("--e2e-lanes", type=int, default=2, help="contexts / host threads of the `lanes` e2e mode")
+    ap.add_argument("--no-parity", action="store_true", help="skip the untimed parity checks on the benched data")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra legs (configs[2] at N = 1, configs[3] at N >= 2)")
+    ap.add_argument("--no-e2e-pipeline", action="store_true", help="e2e steps one at a time")
+    ap.add_argument("--e2e-mode", choices=["stream", "serial"], default="stream",
+                    help="`stream` = copies of the neighbouring steps on the context's copy stream (default); "
+                         "`serial` = one step at a time")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.methods:

@@ -6,7 +6,10 @@ the import fails loudly: there is no Python or CPU fallback for any operation.
 import ctypes as C
 from pathlib import Path
 
-_SO = Path(__file__).resolve().parent / "libbrgpu.so"
+import os
+
+# BRGPU_LIBRARY: another build of the same sources (A/B measurements of compile-time choices)
+_SO = Path(os.environ.get("BRGPU_LIBRARY") or Path(__file__).resolve().parent / "libbrgpu.so")
 
 OK, E_INVALID, E_NO_DEVICE, E_CUDA, E_NOMEM, E_OVERFLOW, E_NO_THRESHOLD, E_NEED_ABUNDANCE = range(8)
 ONE, TWO, GRAPH, GREEDY, GAP_SIZE = range(5)
@@ -30,11 +33,13 @@ SIGNATURES = {
     "brgpu_ctx_create": (C.c_int, [C.c_int, vp, pvp]),
     "brgpu_ctx_destroy": (None, [vp]),
     "brgpu_ctx_synchronize": (C.c_int, [vp]),
+    "brgpu_ctx_set_option": (C.c_int, [vp, C.c_char_p, C.c_int]),
     "brgpu_last_error": (C.c_char_p, [vp]),
     "brgpu_version": (C.c_char_p, []),
     "brgpu_host_alloc": (C.c_int, [vp, sz, pvp]),
     "brgpu_host_free": (None, [vp, vp]),
     "brgpu_reads_upload": (C.c_int, [vp, vp, vp, u64, pvp]),
+    "brgpu_reads_synth": (C.c_int, [vp, u64, u64, u64, vp, vp, vp, u64, vp, pvp]),
     "brgpu_reads_count": (u64, [vp]),
     "brgpu_reads_bases": (u64, [vp]),
     "brgpu_reads_download": (C.c_int, [vp, vp, u64, vp, pu64]),
@@ -88,6 +93,8 @@ SIGNATURES = {
     "brgpu_profile_reset": (C.c_int, [vp]),
     "brgpu_profile_count": (C.c_int, [vp]),
     "brgpu_profile_get": (C.c_int, [vp, C.c_int, C.c_char_p, sz, C.POINTER(C.c_double), pu64, C.POINTER(C.c_double)]),
+    "brgpu_profile_get_lookups": (C.c_int, [vp, C.c_int, pu64]),
+    "brgpu_probe_random_gather": (C.c_int, [vp, u64, C.POINTER(C.c_double)]),
     "brgpu_launch_count": (u64, [vp]),
     "brgpu_scan_lookups": (u64, [vp]),
 }

@@ -1,14 +1,21 @@
-"""Build br_b200/libbrgpu.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+"""Build br_b200/libbrgpu.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+
+The translation units compile in parallel: brgpu.cu (C ABI), set_kernels.cu (part 1),
+correct_kernels.cu (phase A + the scan's host side) and scan_methods.cu once per
+(correction method, variant) — `fast` is the product path, `cnt` counts the scans' KmerSet::get
+calls for profiling runs (bench.py's roofline)."""
 import os
 import shutil
 import subprocess
+from concurrent.futures import ThreadPoolExecutor
 from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
+OBJ = PKG / "build_obj"
 SO = PKG / "libbrgpu.so"
-SOURCES = ["brgpu.cu", "set_kernels.cu", "correct_kernels.cu"]
-HEADERS = ["internal.h", "kmer.cuh", "../../include/brgpu.h"]
+SOURCES = ["brgpu.cu", "set_kernels.cu", "correct_kernels.cu", "scan_methods.cu", "synth_kernels.cu", "hash_kernels.cu"]
+HEADERS = ["internal.h", "kmer.cuh", "scan_common.cuh", "scan_device.cuh", "../../include/brgpu.h"]
 # C++ host side (br's own interface over the C ABI) and its command line
 HOST = PKG / "host"
 CLI = PKG / "brgpu-cli"
@@ -20,7 +27,6 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC",
-    "-shared",
 ]
 
 
@@ -31,11 +37,15 @@ def nvcc_path():
     return p
 
 
+def existing(names):
+    return [f for f in names if (CSRC / f).exists()]
+
+
 def needs_build():
     if not SO.exists():
         return True
     t = SO.stat().st_mtime
-    return any((CSRC / f).stat().st_mtime > t for f in SOURCES + HEADERS)
+    return any((CSRC / f).stat().st_mtime > t for f in existing(SOURCES) + HEADERS)
 
 
 def cli_needs_build():
@@ -58,20 +68,53 @@ def build_cli(force=False):
     return CLI
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def compile_jobs(extra_defines=()):
+    """(object path, nvcc argument list) for every translation unit."""
+    jobs = []
+    for src in existing(SOURCES):
+        if src == "scan_methods.cu":
+            for variant, count in (("fast", 0), ("cnt", 1)):
+                for m in range(5):
+                    obj = OBJ / f"scan_m{m}_{variant}.o"
+                    jobs.append((obj, [f"-DBRGPU_METHOD={m}", f"-DBRGPU_VARIANT={variant}", f"-DBRGPU_COUNT_GETS={count}",
+                                       *extra_defines, "-c", "-o", str(obj), str(CSRC / src)]))
+        else:
+            obj = OBJ / (Path(src).stem + ".o")
+            jobs.append((obj, [*extra_defines, "-c", "-o", str(obj), str(CSRC / src)]))
+    return jobs
+
+
+def build(force=False, verbose=False, out=None, extra_defines=()):
+    """out / extra_defines: A/B builds (e.g. extra_defines=["-DBRGPU_SCAN_MINB=12"], out=libbrgpu_mb12.so)."""
+    target = Path(out) if out else SO
+    if not force and not out and not needs_build():
         build_cli()
         return SO
-    cmd = [nvcc_path(), *NVCC_FLAGS, "-ccbin", "/usr/bin/g++", "-o", str(SO), *[str(CSRC / s) for s in SOURCES]]
-    if verbose:
-        cmd[1:1] = ["-Xptxas", "-v"]
+    nvcc = nvcc_path()
+    OBJ.mkdir(exist_ok=True)
+    jobs = compile_jobs(tuple(extra_defines))
+
+    def run(job):
+        obj, args = job
+        cmd = [nvcc, *NVCC_FLAGS, "-ccbin", "/usr/bin/g++", *(["-Xptxas", "-v"] if verbose else []), *args]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        return obj, r
+
+    with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
+        results = list(ex.map(run, jobs))
+    for obj, r in results:
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {obj.name}:\n" + r.stdout + r.stderr)
+        if verbose:
+            print(r.stdout + r.stderr)
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-ccbin", "/usr/bin/g++", "-o", str(target),
+           *[str(obj) for obj, _ in results]]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
-    if verbose:
-        print(r.stdout + r.stderr)
-    build_cli(force=True)
-    return SO
+        raise RuntimeError("nvcc link failed:\n" + r.stdout + r.stderr)
+    if not out:
+        build_cli(force=True)
+    return target
 
 
 if __name__ == "__main__":

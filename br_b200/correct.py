@@ -6,7 +6,7 @@
                           fn correct(&self, seq: &[u8]) -> Vec<u8>; }          src/correct/mod.rs:44-108
 
 Each corrector object is only a (method, parameters, set) description: the work happens in
-libbrgpu.so, one warp per read.  `correct(seq)` exists for the reference's unit tests (one read per
+libbrgpu.so (speculative per-segment scan + per-read merge).  `correct(seq)` exists for the reference's unit tests (one read per
 call); `run_correction` / `correct_batch` / `correct_reads` are the real entry points and take the
 whole chunk (src/lib.rs:90-128) in one call.
 """
@@ -56,7 +56,7 @@ class Corrector:
             n = C.c_uint64()
             st = lib.brgpu_correct_one(self._set.ctx._h, self._set._h, self.method, self.confirm, self.max_search,
                                        _ptr(s), s.size, _ptr(out), cap, C.byref(n))
-            if st == _lib.E_OVERFLOW:
+            if st == _lib.E_OVERFLOW and int(n.value) > cap:  # buffer too small: *required tells how much
                 cap = int(n.value)
                 continue
             check(st, self._set.ctx._h)

@@ -68,6 +68,15 @@ void prof_begin(brgpu_ctx *ctx, const char *name, double algo_bytes, bool is_ker
     tl_open = pe;
 }
 
+unsigned long long *prof_counter_slot(brgpu_ctx *ctx) {
+    int slot = brgpu_ctx::GET_SLOTS - 1;
+    if (ctx->profiling && tl_open) {
+        const long i = tl_open - ctx->prof.data();
+        if (i >= 0 && i < brgpu_ctx::GET_SLOTS - 1) slot = (int)i;
+    }
+    return ctx->d_getcnt + slot;
+}
+
 void prof_end(brgpu_ctx *ctx) {
     if (!ctx->profiling || !tl_open) return;
     cudaEventRecord(tl_open->pending.back().second, ctx->stream);
@@ -84,6 +93,14 @@ static void prof_resolve(brgpu_ctx *ctx) {
             ctx->event_pool.push_back(ev.second);
         }
         p.pending.clear();
+    }
+    // the scan kernels' KmerSet::get counters: slot i belongs to prof[i]
+    if (ctx->d_getcnt && !ctx->prof.empty()) {
+        unsigned long long h[brgpu_ctx::GET_SLOTS];
+        if (cudaMemcpy(h, ctx->d_getcnt, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess)
+            for (size_t i = 0; i < ctx->prof.size() && i < (size_t)brgpu_ctx::GET_SLOTS - 1; i++) ctx->prof[i].lookups = h[i];
+        else
+            cudaGetLastError();
     }
 }
 
@@ -215,12 +232,22 @@ extern "C" int brgpu_ctx_create(int device, void *cuda_stream, brgpu_ctx **out) 
     }
     if (cudaMalloc((void **)&ctx->d_flags, 16 * sizeof(uint32_t)) != cudaSuccess ||
         cudaMalloc((void **)&ctx->d_hist, 256 * sizeof(uint64_t)) != cudaSuccess ||
+        cudaMalloc((void **)&ctx->d_getcnt, brgpu_ctx::GET_SLOTS * sizeof(unsigned long long)) != cudaSuccess ||
         cudaHostAlloc((void **)&ctx->h_pinned, 512 * sizeof(uint64_t), cudaHostAllocMapped) != cudaSuccess) {
         cudaGetLastError();
         brgpu_ctx_destroy(ctx);
         return BRGPU_E_NOMEM;
     }
     cudaMemsetAsync(ctx->d_flags, 0, 16 * sizeof(uint32_t), ctx->stream);
+    cudaMemsetAsync(ctx->d_getcnt, 0, brgpu_ctx::GET_SLOTS * sizeof(unsigned long long), ctx->stream);
+    // switches for tests and A/B runs: the environment gives the defaults once, here
+    auto env_on = [](const char *name) {
+        const char *v = getenv(name);
+        return v && *v && *v != '0';
+    };
+    ctx->opt_no_compact = env_on("BRGPU_NO_COMPACT") ? 1 : 0;
+    ctx->opt_one_level_partition = env_on("BRGPU_ONE_LEVEL_PARTITION") ? 1 : 0;
+    if (const char *m = getenv("BRGPU_SCAN")) ctx->opt_scan_mode = m[0] == 'w' ? 1 : (m[0] == 'g' ? 2 : 0);
     *out = ctx;
     return BRGPU_OK;
 }
@@ -244,9 +271,22 @@ extern "C" void brgpu_ctx_destroy(brgpu_ctx *ctx) {
     for (auto &b : ctx->pool_live) cudaFree(b.first);
     if (ctx->d_flags) cudaFree(ctx->d_flags);
     if (ctx->d_hist) cudaFree(ctx->d_hist);
+    if (ctx->d_getcnt) cudaFree(ctx->d_getcnt);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
+}
+
+extern "C" int brgpu_ctx_set_option(brgpu_ctx *ctx, const char *name, int value) {
+    if (!ctx || !name) return BRGPU_E_INVALID;
+    if (!strcmp(name, "no_compact")) ctx->opt_no_compact = value != 0;
+    else if (!strcmp(name, "one_level_partition")) ctx->opt_one_level_partition = value != 0;
+    else if (!strcmp(name, "scan_mode")) {
+        if (value < 0 || value > 2) return fail(ctx, BRGPU_E_INVALID, "scan_mode must be 0 (default), 1 (warp) or 2 (groups)");
+        ctx->opt_scan_mode = value;
+    } else
+        return fail(ctx, BRGPU_E_INVALID, "unknown option");
+    return BRGPU_OK;
 }
 
 extern "C" int brgpu_ctx_synchronize(brgpu_ctx *ctx) {
@@ -437,6 +477,82 @@ extern "C" int brgpu_reads_upload(brgpu_ctx *ctx, const uint8_t *seq_host, const
         return fail(ctx, BRGPU_E_INVALID, "null sequence buffer");
     cudaSetDevice(ctx->device);
     return reads_from_tight(ctx, seq_host, false, offsets_host, n_reads, 0, out);
+}
+
+// Synthetic reads generated on the device (measurement support; see synth_kernels.cu for the generator).
+extern "C" int brgpu_reads_synth(brgpu_ctx *ctx, uint64_t genome_seed, uint64_t read_seed, uint64_t first_read_id,
+                                 const uint64_t *start_host, const uint32_t *tlen_host, const uint8_t *strand_host,
+                                 uint64_t n_reads, const uint32_t thresholds[3], brgpu_reads **out) {
+    if (!ctx || !out || !thresholds || (n_reads && (!start_host || !tlen_host || !strand_host)))
+        return ctx ? fail(ctx, BRGPU_E_INVALID, "null argument") : BRGPU_E_INVALID;
+    *out = nullptr;
+    if (!(thresholds[0] <= thresholds[1] && thresholds[1] <= thresholds[2] && thresholds[2] <= (1u << 24)))
+        return fail(ctx, BRGPU_E_INVALID, "thresholds must be cumulative and at most 2^24");
+    cudaSetDevice(ctx->device);
+    const uint64_t n = n_reads;
+    const uint64_t tile = (uint64_t)synth_tile_positions();
+    std::vector<uint64_t> tile_first(n + 1);
+    uint64_t n_tiles = 0;
+    for (uint64_t r = 0; r < n; r++) {
+        if (tlen_host[r] > 0x7fffffffu) return fail(ctx, BRGPU_E_INVALID, "template longer than 2^31 bases");
+        tile_first[r] = n_tiles;
+        n_tiles += ((uint64_t)tlen_host[r] + tile - 1) / tile;
+    }
+    tile_first[n] = n_tiles;
+    uint64_t *d_start = nullptr, *d_tile_first = nullptr, *d_tile_off = nullptr, *d_tmp = nullptr, *d_read_off = nullptr;
+    uint32_t *d_tlen = nullptr, *d_tile_bytes = nullptr;
+    uint8_t *d_strand = nullptr, *d_tight = nullptr;
+    auto drop = [&]() {
+        for (void *p : {(void *)d_start, (void *)d_tile_first, (void *)d_tile_off, (void *)d_tmp, (void *)d_read_off,
+                        (void *)d_tlen, (void *)d_tile_bytes, (void *)d_strand, (void *)d_tight})
+            if (p) dfree(ctx, p);
+    };
+    cudaError_t e = dalloc(ctx, &d_start, n);
+    if (e == cudaSuccess) e = dalloc(ctx, &d_tlen, n);
+    if (e == cudaSuccess) e = dalloc(ctx, &d_strand, n);
+    if (e == cudaSuccess) e = dalloc(ctx, &d_tile_first, n + 1);
+    if (e == cudaSuccess) e = dalloc(ctx, &d_tile_bytes, n_tiles);
+    if (e == cudaSuccess) e = dalloc(ctx, &d_tile_off, n_tiles + 1);
+    if (e == cudaSuccess) e = dalloc(ctx, &d_tmp, n_tiles / 4096 + 4);
+    if (e == cudaSuccess) e = dalloc(ctx, &d_read_off, n + 1);
+    if (e != cudaSuccess) {
+        drop();
+        return fail(ctx, BRGPU_E_NOMEM, "device allocation (synthetic reads)", e);
+    }
+    const uint64_t seeds[3] = {genome_seed, read_seed, first_read_id};
+    if (n) {
+        cudaMemcpyAsync(d_start, start_host, n * 8, cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemcpyAsync(d_tlen, tlen_host, n * 4, cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemcpyAsync(d_strand, strand_host, n, cudaMemcpyHostToDevice, ctx->stream);
+    }
+    cudaMemcpyAsync(d_tile_first, tile_first.data(), (n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream);
+    launch_synth_count(ctx, seeds, thresholds, d_start, d_tlen, d_strand, d_tile_first, n, n_tiles, d_tile_bytes);
+    launch_exclusive_scan_u32(ctx, d_tile_bytes, n_tiles, d_tile_off, d_tmp);
+    launch_readback(ctx, ctx->h_pinned, d_tile_off + n_tiles, sizeof(uint64_t));
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        drop();
+        return fail(ctx, BRGPU_E_CUDA, "synthetic reads (count)", e);
+    }
+    const uint64_t total = ctx->h_pinned[0];
+    e = dalloc(ctx, &d_tight, total + 64);
+    if (e != cudaSuccess) {
+        drop();
+        return fail(ctx, BRGPU_E_NOMEM, "device allocation (synthetic reads)", e);
+    }
+    launch_synth_write(ctx, seeds, thresholds, d_start, d_tlen, d_strand, d_tile_first, n, n_tiles, d_tile_off, d_tight,
+                       d_read_off);
+    std::vector<uint64_t> h_off(n + 1);
+    e = cudaMemcpyAsync(h_off.data(), d_read_off, (n + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        drop();
+        return fail(ctx, BRGPU_E_CUDA, "synthetic reads (write)", e);
+    }
+    const int st = reads_from_tight(ctx, d_tight, true, h_off.data(), n, 0, out);
+    drop();
+    return st;
 }
 
 extern "C" uint64_t brgpu_reads_count(const brgpu_reads *reads) { return reads ? reads->layout->n : 0; }
@@ -762,8 +878,7 @@ static int build_compact(brgpu_set *s) {
     brgpu_ctx *ctx = s->ctx;
     compact_release(s);
     if (!s->d_summary || s->summary_shift != 6) return BRGPU_OK;
-    if (const char *off = getenv("BRGPU_NO_COMPACT")) // test hook: keep lookups on summary + bitfield
-        if (*off && *off != '0') return BRGPU_OK;
+    if (ctx->opt_no_compact) return BRGPU_OK; // test hook: keep lookups on summary + bitfield
     const uint64_t n_words = s->summary_bytes >> 2;
     uint32_t *d_pop = nullptr;
     uint64_t *d_rank = nullptr, *d_tmp = nullptr;
@@ -913,7 +1028,7 @@ static int kmers_create(brgpu_ctx *ctx, int k, const brgpu_reads *reads, brgpu_k
     uint32_t *d_fill = nullptr, *d_coarse_kmers = nullptr;
     uint64_t *d_tmp = nullptr, *d_coarse_base = nullptr;
     cudaError_t e;
-    const bool two_level = bucket_partition_two_level(km->n_buckets) && !getenv("BRGPU_ONE_LEVEL_PARTITION");
+    const bool two_level = bucket_partition_two_level(km->n_buckets) && !ctx->opt_one_level_partition;
     // residues and offsets are cudaMalloc-backed (exportable over CUDA IPC for the multi-GPU path)
     if ((e = big_alloc(ctx, (void **)&km->d_res, km->capacity * 2)) != cudaSuccess ||
         (e = big_alloc(ctx, (void **)&km->d_base, (km->n_buckets + 1) * 8)) != cudaSuccess ||
@@ -1371,12 +1486,12 @@ static int correct_attempt(brgpu_ctx *ctx, const brgpu_set *set, const uint8_t *
     const uint8_t *src = in->d_seq;
     const uint32_t *src_len = in->d_len;
     int nxt = 0;
-    auto run_methods = [&]() {
+    auto run_methods = [&](bool reversed) {
         for (uint64_t i = 0; i < n_methods; i++) {
-            CorrectParams p{set->k, methods[i], confirm, max_search};
+            CorrectParams p{set->k, methods[i], confirm, max_search, reversed ? 1 : 0};
             // after a method of the same orientation only the reads it edited need new bitmap words
             launch_solid_bitmap(ctx, L, src, src_len, set_view(set), d_bitmap, i > 0 ? work.d_changed : nullptr,
-                                (double)in->sum_len);
+                                (double)in->sum_len, reversed);
             launch_scan(ctx, L, src, src_len, buf[nxt], len[nxt], d_bitmap, set_view(set), p, d_scratch,
                         scratch_per_warp, n_warps, work, (double)in->sum_len);
             src = buf[nxt];
@@ -1392,10 +1507,10 @@ static int correct_attempt(brgpu_ctx *ctx, const brgpu_set *set, const uint8_t *
         src_len = len[nxt];
         nxt ^= 1;
     };
-    run_methods(); // src/lib.rs:44-46
+    run_methods(false); // src/lib.rs:44-46
     if (!two_side) { // src/lib.rs:48-55 (the flag is inverted: default runs the reversed pass)
         run_reverse();
-        run_methods();
+        run_methods(true);
         run_reverse();
     }
     if (src == in->d_seq) { // no method at all and two_side: plain copy
@@ -1405,9 +1520,10 @@ static int correct_attempt(brgpu_ctx *ctx, const brgpu_set *set, const uint8_t *
         src_len = len[0];
     }
     e = cudaGetLastError();
-    if (e == cudaSuccess)
+    if (e == cudaSuccess) {
         launch_readback(ctx, ctx->h_pinned, ctx->d_flags + 1, sizeof(uint32_t));
         e = cudaGetLastError();
+    }
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) {
         cleanup();
@@ -1587,6 +1703,7 @@ extern "C" int brgpu_profile_reset(brgpu_ctx *ctx) {
     cudaSetDevice(ctx->device);
     prof_resolve(ctx);
     ctx->prof.clear();
+    CK(cudaMemsetAsync(ctx->d_getcnt, 0, brgpu_ctx::GET_SLOTS * sizeof(unsigned long long), ctx->stream));
     return BRGPU_OK;
 }
 
@@ -1611,15 +1728,64 @@ extern "C" int brgpu_profile_get(brgpu_ctx *ctx, int i, char *name_out, size_t n
     return BRGPU_OK;
 }
 
+// Random 8-byte gathers per second over a zeroed table of `table_bytes` (rounded down to a power of
+// two): the yardstick for the solidity lookups (L2-resident table: L2 gather ceiling; table >> L2: DRAM
+// random-sector ceiling).  Measured with CUDA events on the context's stream, best of three.
+extern "C" int brgpu_probe_random_gather(brgpu_ctx *ctx, uint64_t table_bytes, double *gathers_per_s) {
+    if (!ctx || !gathers_per_s || table_bytes < 4096) return BRGPU_E_INVALID;
+    cudaSetDevice(ctx->device);
+    uint64_t words = 1;
+    while (words * 2 * 8 <= table_bytes) words *= 2;
+    uint64_t *d_tab = nullptr, *d_sink = nullptr;
+    CK(dalloc(ctx, &d_tab, words));
+    cudaError_t e = dalloc(ctx, &d_sink, 8);
+    if (e != cudaSuccess) {
+        dfree(ctx, d_tab);
+        return fail(ctx, BRGPU_E_NOMEM, "device allocation (probe)", e);
+    }
+    cudaMemsetAsync(d_tab, 0, words * 8, ctx->stream);
+    cudaEvent_t a = nullptr, b = nullptr;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    double best = 0.0;
+    uint64_t n = 0;
+    launch_probe_gather(ctx, d_tab, words, 256, d_sink, &n); // warm-up (and L2 fill for small tables)
+    for (int rep = 0; rep < 3 && e == cudaSuccess; rep++) {
+        cudaEventRecord(a, ctx->stream);
+        launch_probe_gather(ctx, d_tab, words, 256, d_sink, &n);
+        cudaEventRecord(b, ctx->stream);
+        e = cudaEventSynchronize(b);
+        float ms = 0.f;
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, a, b);
+        if (e == cudaSuccess && ms > 0.f && (double)n / (ms * 1e-3) > best) best = (double)n / (ms * 1e-3);
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    dfree(ctx, d_tab);
+    dfree(ctx, d_sink);
+    if (e != cudaSuccess) return fail(ctx, BRGPU_E_CUDA, "gather probe", e);
+    *gathers_per_s = best;
+    return BRGPU_OK;
+}
+
+extern "C" int brgpu_profile_get_lookups(brgpu_ctx *ctx, int i, uint64_t *lookups) {
+    if (!ctx || !lookups || i < 0 || i >= (int)ctx->prof.size()) return BRGPU_E_INVALID;
+    *lookups = ctx->prof[(size_t)i].lookups;
+    return BRGPU_OK;
+}
+
 extern "C" uint64_t brgpu_launch_count(const brgpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
 extern "C" uint64_t brgpu_scan_lookups(brgpu_ctx *ctx) {
     if (!ctx) return 0;
     cudaSetDevice(ctx->device);
-    launch_readback(ctx, ctx->h_pinned, ctx->d_flags + 2, sizeof(uint64_t));
-    if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+    unsigned long long h[brgpu_ctx::GET_SLOTS];
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess ||
+        cudaMemcpy(h, ctx->d_getcnt, sizeof(h), cudaMemcpyDeviceToHost) != cudaSuccess) {
         cudaGetLastError();
         return 0;
     }
-    return ctx->h_pinned[0];
+    uint64_t total = 0;
+    for (int t = 0; t < brgpu_ctx::GET_SLOTS; t++) total += h[t];
+    return total;
 }

@@ -19,6 +19,7 @@ struct ProfEntry {
     double ms = 0.0;
     uint64_t launches = 0;
     double bytes = 0.0;
+    uint64_t lookups = 0; // KmerSet::get calls the kernel issued (scan kernels, counted while profiling)
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
 };
 
@@ -42,6 +43,15 @@ struct brgpu_ctx {
     uint32_t *d_flags = nullptr; // [0] work-queue cursor, [1] overflow flag, [2..] spare
     uint64_t *d_hist = nullptr;  // 256 bins
     uint64_t *h_pinned = nullptr; // 512 x u64 pinned staging for small readbacks
+    // per-kernel-name KmerSet::get counters (profiling runs only): slot i belongs to prof[i]; the last
+    // slot collects launches that have no entry
+    static constexpr int GET_SLOTS = 64;
+    unsigned long long *d_getcnt = nullptr;
+    // test / A-B switches: defaults from the environment at context creation (BRGPU_NO_COMPACT,
+    // BRGPU_ONE_LEVEL_PARTITION, BRGPU_SCAN=warp|groups), changed with brgpu_ctx_set_option
+    int opt_no_compact = 0;          // lookups through summary + bitfield even for sparse sets
+    int opt_one_level_partition = 0; // the k = 19 partition path for k <= 17
+    int opt_scan_mode = 0;           // 0: per method default, 1: warp per segment, 2: four segments per warp
     // caching device allocator (brgpu.cu): blocks handed out (ptr -> bytes) and cached free blocks
     std::unordered_map<void *, uint64_t> pool_live;
     std::vector<std::pair<void *, uint64_t>> pool_free;
@@ -125,6 +135,8 @@ int fail(brgpu_ctx *ctx, int code, const char *what, cudaError_t e = cudaSuccess
 // profiling hooks around a launch
 void prof_begin(brgpu_ctx *ctx, const char *name, double algo_bytes, bool is_kernel = true);
 void prof_end(brgpu_ctx *ctx);
+// device counter for the KmerSet::get calls of the kernel whose ProfScope is open
+unsigned long long *prof_counter_slot(brgpu_ctx *ctx);
 
 struct ProfScope {
     brgpu_ctx *c;
@@ -147,6 +159,16 @@ void launch_gather_from_slots(brgpu_ctx *ctx, const Layout &L, const uint8_t *d_
 void launch_reverse_slots(brgpu_ctx *ctx, const Layout &L, const uint8_t *d_in, const uint32_t *d_len, uint8_t *d_out);
 void launch_exclusive_scan_u32(brgpu_ctx *ctx, const uint32_t *d_in, uint64_t n, uint64_t *d_out /* n+1 */,
                                uint64_t *d_tmp /* >= n/4096 + 2 */);
+
+// ---- synthetic reads (synth_kernels.cu): seeds = {genome seed, read seed, first read id}, thr = cumulative
+// 24-bit thresholds {substitution, insertion, deletion} ----
+int synth_tile_positions();
+void launch_synth_count(brgpu_ctx *ctx, const uint64_t seeds[3], const uint32_t thr[3], const uint64_t *d_start,
+                        const uint32_t *d_tlen, const uint8_t *d_strand, const uint64_t *d_tile_first, uint64_t n_reads,
+                        uint64_t n_tiles, uint32_t *d_tile_bytes);
+void launch_synth_write(brgpu_ctx *ctx, const uint64_t seeds[3], const uint32_t thr[3], const uint64_t *d_start,
+                        const uint32_t *d_tlen, const uint8_t *d_strand, const uint64_t *d_tile_first, uint64_t n_reads,
+                        uint64_t n_tiles, const uint64_t *d_tile_off, uint8_t *d_out, uint64_t *d_read_off);
 
 // ---- part 1 kernels (set_kernels.cu) ----
 void launch_count(brgpu_ctx *ctx, const Layout &L, const uint8_t *d_seq, const uint32_t *d_len, int k,
@@ -174,6 +196,9 @@ void launch_insert_batch(brgpu_ctx *ctx, uint8_t *d_bits, int k, const uint64_t 
 void launch_merge_slice(brgpu_ctx *ctx, uint8_t *d_counts, void *const *peers, int n_peers, uint64_t begin,
                         uint64_t end);
 
+void launch_probe_gather(brgpu_ctx *ctx, const uint64_t *d_tab, uint64_t n_words_pow2, uint64_t n_per_thread,
+                         uint64_t *d_sink, uint64_t *n_gathers);
+
 // occupancy summary of a bitfield: one bit per 2^shift bitfield bits
 void launch_build_summary(brgpu_ctx *ctx, const uint8_t *d_bits, uint64_t n_bytes, int shift, uint32_t *d_summary);
 // rank directory over a shift-6 summary: d_pop[g] = popc(summary[g]), d_rank = exclusive scan (n + 1)
@@ -199,11 +224,13 @@ struct CorrectParams {
     int method;
     int confirm;
     int max_search;
+    int reversed = 0; // the pass runs over the byte-reversed reads (src/lib.rs:48-55): reporting only
 };
 // solidity bit of the k-mer ending at every slot position of every read (0 where undefined);
 // d_changed != nullptr: only for the reads it marks, the others keep the words already in d_bitmap
 void launch_solid_bitmap(brgpu_ctx *ctx, const Layout &L, const uint8_t *d_seq, const uint32_t *d_len,
-                         const SetView &set, uint32_t *d_bitmap, const uint8_t *d_changed, double n_bases_hint);
+                         const SetView &set, uint32_t *d_bitmap, const uint8_t *d_changed, double n_bases_hint,
+                         bool reversed = false);
 // per-pass work areas of the segmented scan (sized once per correction call)
 struct ScanWork {
     uint32_t *d_n_seg = nullptr;     // n reads

@@ -1233,6 +1233,39 @@ void launch_compact_blocks(brgpu_ctx *ctx, const uint32_t *d_summary, const uint
 }
 
 // ------------------------------------------------------------------------------------------
+// Probe behind the "l2" yardstick bench.py reports for the solidity lookups: random 8-byte gathers
+// over a table of the given size, 8 independent loads in flight per thread (the access pattern of
+// solid_bitmap's directory / block loads).  A table that fits in L2 gives the L2 random-gather
+// ceiling, one much larger than L2 the DRAM random-sector ceiling.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    probe_gather_kernel(const uint64_t *__restrict__ tab, uint64_t mask, uint64_t n_per_thread, uint64_t *__restrict__ sink) {
+    const uint64_t tid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    uint64_t acc = 0;
+    for (uint64_t i = 0; i < n_per_thread; i += 8) {
+        uint64_t v[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            uint64_t x = tid * n_per_thread + i + (uint64_t)j + 0x9E3779B97F4A7C15ULL;
+            x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+            x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+            v[j] = __ldg(tab + ((x ^ (x >> 31)) & mask));
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc += v[j];
+    }
+    if (acc == 0xdeadbeefULL) sink[0] = acc;
+}
+
+void launch_probe_gather(brgpu_ctx *ctx, const uint64_t *d_tab, uint64_t n_words_pow2, uint64_t n_per_thread,
+                         uint64_t *d_sink, uint64_t *n_gathers) {
+    const unsigned blocks = (unsigned)ctx->sm_count * 8;
+    ctx->launches++;
+    probe_gather_kernel<<<blocks, 256, 0, ctx->stream>>>(d_tab, n_words_pow2 - 1, n_per_thread, d_sink);
+    *n_gathers = (uint64_t)blocks * 256 * n_per_thread;
+}
+
+// ------------------------------------------------------------------------------------------
 // Multi-GPU merge: this rank's slice of the table += the same slice of every peer's table,
 // read straight out of the peers' HBM over NVLink (the pointers are CUDA-IPC mappings), with a
 // per-byte unsigned saturating add (min(255, sum) is associative and commutative, so the merged

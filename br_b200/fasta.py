@@ -28,7 +28,13 @@ def read_fasta(path_or_file):
     """Returns (definitions: list[bytes], seq: uint8 ndarray, offsets: uint64 ndarray)."""
     data = _open(path_or_file)
     defs, parts, lens = [], [], []
-    for rec in data.split(b">")[1:]:
+    # a record starts with '>' at the start of a line only: a '>' inside a definition line is legal
+    start = data.find(b">") if not data.startswith(b">") else 0
+    if start > 0 and data[start - 1 : start] != b"\n":
+        start = data.find(b"\n>")
+        start = -1 if start < 0 else start + 1
+    records = data[start + 1 :].split(b"\n>") if start >= 0 else []
+    for rec in records:
         nl = rec.find(b"\n")
         if nl < 0:
             defs.append(rec.rstrip(b"\r"))

@@ -108,6 +108,13 @@ class Context:
     def synchronize(self):
         check(lib.brgpu_ctx_synchronize(self._h), self._h)
 
+    def set_option(self, name, value):
+        """Test / A-B switches of include/brgpu.h (brgpu_ctx_set_option): "no_compact", "one_level_partition",
+        "scan_mode" (0 default, 1 or "warp", 2 or "groups").  None of them changes a result."""
+        if name == "scan_mode" and isinstance(value, str):
+            value = {"default": 0, "warp": 1, "groups": 2}[value]
+        check(lib.brgpu_ctx_set_option(self._h, name.encode(), int(value)), self._h)
+
     # --- instrumentation -------------------------------------------------------------------
     def profile_enable(self, on=True):
         check(lib.brgpu_profile_enable(self._h, int(on)), self._h)
@@ -116,15 +123,23 @@ class Context:
         check(lib.brgpu_profile_reset(self._h), self._h)
 
     def profile(self):
-        """{kernel name: {"ms", "launches", "algo_bytes"}} accumulated since the last reset."""
+        """{kernel name: {"ms", "launches", "algo_bytes", "lookups"}} accumulated since the last reset;
+        "lookups" = KmerSet::get calls the kernel issued (scan / merge kernels)."""
         out = {}
         n = lib.brgpu_profile_count(self._h)
         name = C.create_string_buffer(64)
-        ms, nb, ln = C.c_double(), C.c_double(), C.c_uint64()
+        ms, nb, ln, lk = C.c_double(), C.c_double(), C.c_uint64(), C.c_uint64()
         for i in range(n):
             check(lib.brgpu_profile_get(self._h, i, name, 64, C.byref(ms), C.byref(ln), C.byref(nb)), self._h)
-            out[name.value.decode()] = {"ms": ms.value, "launches": ln.value, "algo_bytes": nb.value}
+            check(lib.brgpu_profile_get_lookups(self._h, i, C.byref(lk)), self._h)
+            out[name.value.decode()] = {"ms": ms.value, "launches": ln.value, "algo_bytes": nb.value, "lookups": lk.value}
         return out
+
+    def probe_random_gather(self, table_bytes):
+        """Random 8-byte gathers per second over a table of that size (brgpu_probe_random_gather)."""
+        v = C.c_double()
+        check(lib.brgpu_probe_random_gather(self._h, int(table_bytes), C.byref(v)), self._h)
+        return v.value
 
     @property
     def launch_count(self):
@@ -132,7 +147,7 @@ class Context:
 
     @property
     def scan_lookups(self):
-        """KmerSet::get calls issued by the correction scans so far (bookkeeping for the roofline)."""
+        """KmerSet::get calls issued by the correction scans while profiling was on (since the last reset)."""
         return lib.brgpu_scan_lookups(self._h)
 
 
@@ -165,6 +180,19 @@ class Reads:
         r = cls(ctx, h)
         r._keep = (s, off)
         return r
+
+    @classmethod
+    def synth(cls, ctx, genome_seed, read_seed, first_read_id, start, tlen, strand, thresholds):
+        """Synthetic reads generated on the device (brgpu_reads_synth); br_b200.synth.host_reads is the
+        numpy mirror that yields the same bytes."""
+        start = np.ascontiguousarray(start, dtype=np.uint64)
+        tlen = np.ascontiguousarray(tlen, dtype=np.uint32)
+        strand = np.ascontiguousarray(strand, dtype=np.uint8)
+        thr = np.ascontiguousarray(thresholds, dtype=np.uint32)
+        h = C.c_void_p()
+        check(lib.brgpu_reads_synth(ctx._h, int(genome_seed), int(read_seed), int(first_read_id), _ptr(start) or None,
+                                    _ptr(tlen) or None, _ptr(strand) or None, tlen.size, _ptr(thr), C.byref(h)), ctx._h)
+        return cls(ctx, h)
 
     def download_async(self, out, out_offsets):
         """Enqueue the copy back on the copy stream; returns the byte count.  `download_wait()`

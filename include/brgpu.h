@@ -67,6 +67,12 @@ typedef struct brgpu_kmers brgpu_kmers;   /* a chunk's canonical k-mers, partiti
 int brgpu_ctx_create(int device, void *cuda_stream, brgpu_ctx **out);
 void brgpu_ctx_destroy(brgpu_ctx *ctx);
 int brgpu_ctx_synchronize(brgpu_ctx *ctx);
+/* Switches for tests and A/B measurements; none changes a result.  Defaults come from the
+ * environment once, at brgpu_ctx_create (BRGPU_NO_COMPACT, BRGPU_ONE_LEVEL_PARTITION,
+ * BRGPU_SCAN=warp|groups).  name: "no_compact" (0/1: solidity lookups through summary + bitfield
+ * even for sparse sets), "one_level_partition" (0/1: the k = 19 partition path for k <= 17),
+ * "scan_mode" (0 per-method default, 1 warp per segment, 2 four segments per warp, for One/Two). */
+int brgpu_ctx_set_option(brgpu_ctx *ctx, const char *name, int value);
 const char *brgpu_last_error(const brgpu_ctx *ctx);
 const char *brgpu_version(void);
 
@@ -101,6 +107,17 @@ int brgpu_reads_upload_async(brgpu_ctx *ctx, const uint8_t *seq_host, const uint
 int brgpu_reads_download_async(brgpu_reads *reads, uint8_t *seq_host, uint64_t seq_cap, uint64_t *offsets_host,
                                uint64_t *required);
 int brgpu_reads_download_wait(brgpu_reads *reads);
+
+/* Measurement support (bench.py): synthetic ONT-like reads generated on the device, so
+ * that the 5 and 30 Gbase workloads of BASELINE.json's configs[3]/[4] never cross PCIe.  The genome is
+ * a pure function of (genome_seed, position) and is never stored; read r of this call is read number
+ * first_read_id + r of the data set: template = genome[start, start + tlen), reverse-complemented when
+ * strand != 0, then per-base substitutions / insertions / deletions drawn from a counter-based hash
+ * of (read_seed, read number, template position) against the three cumulative 24-bit thresholds.
+ * br_b200/synth.py holds the numpy mirror that produces the same bytes. */
+int brgpu_reads_synth(brgpu_ctx *ctx, uint64_t genome_seed, uint64_t read_seed, uint64_t first_read_id,
+                      const uint64_t *start_host, const uint32_t *tlen_host, const uint8_t *strand_host,
+                      uint64_t n_reads, const uint32_t thresholds[3], brgpu_reads **out);
 
 /* ------------------------------------------------------------------------------------------
  * part 1 — counting and the solid set
@@ -236,9 +253,16 @@ int brgpu_profile_reset(brgpu_ctx *ctx);
 int brgpu_profile_count(brgpu_ctx *ctx);
 int brgpu_profile_get(brgpu_ctx *ctx, int i, char *name_out, size_t name_cap, double *ms, uint64_t *launches,
                       double *algo_bytes);
+/* KmerSet::get calls the i-th kernel issued (scan / merge kernels; 0 for the others).  Counted only
+ * while profiling is enabled: the product path runs kernels compiled without the bookkeeping. */
+int brgpu_profile_get_lookups(brgpu_ctx *ctx, int i, uint64_t *lookups);
+/* Random 8-byte gathers per second over a table of `table_bytes` (8 loads in flight per thread, the
+ * access pattern of the solidity lookups): an L2-resident table gives the L2 gather ceiling, a table
+ * much larger than L2 the DRAM random-sector ceiling.  bench.py measures both in the run it reports. */
+int brgpu_probe_random_gather(brgpu_ctx *ctx, uint64_t table_bytes, double *gathers_per_s);
 uint64_t brgpu_launch_count(const brgpu_ctx *ctx); /* kernels launched since ctx creation */
-/* KmerSet::get calls issued by the correction scans since ctx creation (excludes the one
- * lookup per base of the bitmap pass); syncs the stream */
+/* KmerSet::get calls issued by the correction scans while profiling was enabled, since the last
+ * brgpu_profile_reset (excludes the one lookup per base of the bitmap pass); syncs the stream */
 uint64_t brgpu_scan_lookups(brgpu_ctx *ctx);
 
 #ifdef __cplusplus

@@ -249,7 +249,7 @@ def test_segment_scratch_overflow_falls_back_to_the_merge_warp(gpu, oracle):
 
 
 @pytest.mark.parametrize("k", [15, 17])
-def test_large_k_sets_correct_like_the_oracle_on_every_lookup_path(gpu, oracle, k, monkeypatch):
+def test_large_k_sets_correct_like_the_oracle_on_every_lookup_path(gpu, oracle, k):
     """k = 15 / 17 (BASELINE configs 2-5): the set is looked up through the rank-compacted copy
     (directory + occupied 64-bit blocks) when it is sparse, through summary + bitfield otherwise.
     Both paths, for a set built by counting and for the same set loaded as a bitfield, must give
@@ -267,7 +267,7 @@ def test_large_k_sets_correct_like_the_oracle_on_every_lookup_path(gpu, oracle, 
     changed = int((np.diff(exp_off.astype(np.int64)) != np.diff(off.astype(np.int64))).sum())
     assert changed > 10  # the chain really edits reads
     for no_compact in ("0", "1"):
-        monkeypatch.setenv("BRGPU_NO_COMPACT", no_compact)
+        ctx.set_option("no_compact", int(no_compact))
         counted = br.Pcon.from_reads(ctx, (seq, off), k, abundance=2)
         assert np.array_equal(counted.bitfield(), osolid.bits())
         loaded = br.Pcon.from_bitfield(ctx, k, osolid.bits())
@@ -278,7 +278,7 @@ def test_large_k_sets_correct_like_the_oracle_on_every_lookup_path(gpu, oracle, 
         loaded.free()
     # a denser set (17 % of the 64-bit blocks occupied): the rank-compacted copy is built by the
     # streaming kernel instead of the sparse one
-    monkeypatch.setenv("BRGPU_NO_COMPACT", "0")
+    ctx.set_option("no_compact", 0)
     rng = np.random.default_rng(k)
     dense_bits = osolid.bits().copy()
     pos = rng.integers(0, dense_bits.size * 8, size=int(dense_bits.size * 8 * 0.003), dtype=np.int64)
@@ -293,12 +293,13 @@ def test_large_k_sets_correct_like_the_oracle_on_every_lookup_path(gpu, oracle, 
 
 
 @pytest.mark.parametrize("mode", ["warp", "groups"])
-def test_both_scan_kernels_give_the_oracle_bytes(gpu, oracle, fixture_sets, fixture_reads, mode, monkeypatch):
+def test_both_scan_kernels_give_the_oracle_bytes(gpu, oracle, fixture_sets, fixture_reads, mode, request):
     """One and Two exist as a warp-per-segment kernel and as a four-segments-per-warp kernel
     (8-lane groups); the library picks per method.  Both must reproduce the oracle on the
     reference's reads (chained, reversed pass on) and on a dense random case."""
     br, ctx = gpu
-    monkeypatch.setenv("BRGPU_SCAN", mode)
+    ctx.set_option("scan_mode", mode)
+    request.addfinalizer(lambda: ctx.set_option("scan_mode", 0))
     gs, os_ = fixture_sets
     seq, off = fixture_reads
     ids = [oracle.METHOD_IDS[m] for m in ("one", "two")]

@@ -177,15 +177,15 @@ def test_k17_count_and_threshold_against_oracle(gpu, oracle):
 
 @pytest.mark.parametrize("one_level", [False, True])
 @pytest.mark.parametrize("k", [15, 17])
-def test_bucketed_and_table_counting_paths_agree(gpu, oracle, k, one_level, monkeypatch):
+def test_bucketed_and_table_counting_paths_agree(gpu, oracle, k, one_level, request):
     """Pcon.from_reads takes the bucketed counting path for k = 15/17 (two-level shared-memory
     partition, or the one-level partition with L2 atomics that k = 19 uses), Counter the literal
     table path; all must give the oracle's spectrum and bitfield, including saturated counters
     (poly-A: every k-mer of a tile in one bucket), any-byte nucleotides and the data-derived
     first-minimum threshold."""
     br, ctx = gpu
-    if one_level:
-        monkeypatch.setenv("BRGPU_ONE_LEVEL_PARTITION", "1")
+    ctx.set_option("one_level_partition", int(one_level))
+    request.addfinalizer(lambda: ctx.set_option("one_level_partition", 0))
     from br_b200 import synth
 
     genome = synth.make_genome(150_000, seed=7)
