@@ -10,9 +10,9 @@ from .correct import (
     Corrector, GapSize, Graph, Greedy, One, Two, build_methods, correct_batch, correct_reads, run_correction,
 )
 from .runtime import Context, Reads
-from .set import Counter, KmerSet, Pcon, seq2bit
+from .set import Counter, Hash, KmerSet, Pcon, seq2bit
 
 __all__ = [
-    "BrgpuError", "Context", "Reads", "Counter", "KmerSet", "Pcon", "seq2bit", "Corrector", "One", "Two", "Graph",
+    "BrgpuError", "Context", "Reads", "Counter", "Hash", "KmerSet", "Pcon", "seq2bit", "Corrector", "One", "Two", "Graph",
     "Greedy", "GapSize", "build_methods", "correct_batch", "correct_reads", "run_correction",
 ]

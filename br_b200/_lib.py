@@ -65,6 +65,12 @@ SIGNATURES = {
     "brgpu_set_from_solid_payload": (C.c_int, [vp, vp, u64, pvp]),
     "brgpu_set_new": (C.c_int, [vp, C.c_int, pvp]),
     "brgpu_set_insert_batch": (C.c_int, [vp, vp, u64]),
+    "brgpu_set_hash_new": (C.c_int, [vp, C.c_int, u64, pvp]),
+    "brgpu_set_hash_add_reads": (C.c_int, [vp, vp]),
+    "brgpu_set_hash_from_reads": (C.c_int, [vp, C.c_int, vp, pvp]),
+    "brgpu_set_hash_from_host_reads": (C.c_int, [vp, C.c_int, vp, vp, u64, pvp]),
+    "brgpu_set_is_hash": (C.c_int, [vp]),
+    "brgpu_set_hash_size": (u64, [vp]),
     "brgpu_set_k": (C.c_int, [vp]),
     "brgpu_set_abundance": (C.c_int, [vp]),
     "brgpu_set_bitfield_bytes": (u64, [vp]),
@@ -88,6 +94,8 @@ SIGNATURES = {
     "brgpu_kmers_count_range": (C.c_int, [vp, vp, vp, C.c_int, u64, u64, C.c_int, vp, vp]),
     "brgpu_kmers_offsets_at": (C.c_int, [vp, vp, u64, vp]),
     "brgpu_kmers_count_range_staged": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, u64, u64, C.c_int, vp, vp]),
+    "brgpu_kmers_count_parts": (C.c_int, [vp, vp, C.c_int, vp, vp, vp, vp, C.c_int, u64, u64, C.c_int, vp, vp]),
+    "brgpu_set_from_kmers": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_double, pvp]),
     "brgpu_kmers_free": (None, [vp]),
     "brgpu_profile_enable": (C.c_int, [vp, C.c_int]),
     "brgpu_profile_reset": (C.c_int, [vp]),

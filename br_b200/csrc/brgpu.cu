@@ -930,7 +930,7 @@ static int build_compact(brgpu_set *s) {
 // the last build
 static int ensure_summary(brgpu_set *s) {
     brgpu_ctx *ctx = s->ctx;
-    if (s->summary_valid) return BRGPU_OK;
+    if (s->is_hash || s->summary_valid) return BRGPU_OK;
     compact_release(s);
     int shift;
     uint64_t bytes;
@@ -953,6 +953,11 @@ static int ensure_summary(brgpu_set *s) {
 
 static SetView set_view(const brgpu_set *s) {
     SetView v{s->d_bits, s->summary_bytes ? s->d_summary : nullptr, s->summary_shift, s->k};
+    if (s->is_hash) {
+        v.hash = s->d_hash;
+        v.hash_mask = s->hash_slots - 1;
+        return v;
+    }
     if (s->compact_valid) {
         v.dir = s->d_dir;
         v.blocks = s->d_blocks;
@@ -965,7 +970,8 @@ extern "C" void brgpu_set_free(brgpu_set *s) {
     cudaSetDevice(s->ctx->device);
     compact_release(s);
     if (s->d_summary) big_free(s->ctx, s->d_summary, s->summary_bytes);
-    big_free(s->ctx, s->d_bits, bits_alloc_bytes(s->k));
+    if (s->d_bits) big_free(s->ctx, s->d_bits, bits_alloc_bytes(s->k));
+    if (s->d_hash) big_free(s->ctx, s->d_hash, s->hash_slots * 8);
     delete s;
 }
 
@@ -1172,89 +1178,175 @@ extern "C" int brgpu_kmers_ipc_export(brgpu_kmers *km, uint8_t handles_out[128])
     return BRGPU_OK;
 }
 
-static int kmers_count_range(brgpu_kmers *km, void *const *peer_residues, void *const *peer_offsets,
-                             const uint64_t *peer_first, const uint64_t *peer_last, int n_peers, uint64_t bucket_begin,
-                             uint64_t bucket_end, int abundance, brgpu_set *set, uint64_t hist_host[256]) {
-    if (!km || !hist_host || (n_peers && (!peer_residues || !peer_offsets))) return BRGPU_E_INVALID;
-    brgpu_ctx *ctx = km->ctx;
-    if (n_peers < 0 || n_peers > 15) return fail(ctx, BRGPU_E_INVALID, "at most 15 peers");
-    if (bucket_begin > bucket_end || bucket_end > km->n_buckets) return fail(ctx, BRGPU_E_INVALID, "bad bucket range");
-    if (set && (set->ctx != ctx || set->k != km->k)) return fail(ctx, BRGPU_E_INVALID, "set does not match");
+// Count bucket range [bucket_begin, bucket_end) over any number of partitions: `local` partitions of
+// this context (one per chunk of reads) and peer partitions given as device pointers (CUDA-IPC or
+// peer-access mappings).  With peer_first/peer_last the peers' residues of the range are first pulled
+// into local HBM by one bulk copy per peer; without, the kernel reads them remotely.
+static int kmers_count_parts(brgpu_ctx *ctx, brgpu_kmers *const *local, int n_local, void *const *peer_residues,
+                             void *const *peer_offsets, const uint64_t *peer_first, const uint64_t *peer_last, int n_peers,
+                             uint64_t bucket_begin, uint64_t bucket_end, int abundance, brgpu_set *set, bool emit_summary,
+                             uint64_t hist_host[256]) {
+    if (!ctx || !local || n_local < 1 || !hist_host || (n_peers && (!peer_residues || !peer_offsets))) return BRGPU_E_INVALID;
+    if (n_peers < 0 || n_local + n_peers > BRGPU_MAX_KMER_SOURCES)
+        return fail(ctx, BRGPU_E_INVALID, "at most 64 k-mer partitions (local chunks + peers) per count");
+    const int k = local[0]->k;
+    const uint64_t n_buckets = local[0]->n_buckets;
+    double n_kmers = 0;
+    for (int q = 0; q < n_local; q++) {
+        if (!local[q] || local[q]->ctx != ctx || local[q]->k != k) return fail(ctx, BRGPU_E_INVALID, "partitions do not match");
+        n_kmers += local[q]->n_kmers_hint;
+    }
+    if (bucket_begin > bucket_end || bucket_end > n_buckets) return fail(ctx, BRGPU_E_INVALID, "bad bucket range");
+    if (set && (set->ctx != ctx || set->k != k || set->is_hash)) return fail(ctx, BRGPU_E_INVALID, "set does not match");
     if (set && (abundance < 0 || abundance > 255)) return fail(ctx, BRGPU_E_INVALID, "abundance must be in 0..=255");
     cudaSetDevice(ctx->device);
     const uint64_t nb = bucket_end - bucket_begin;
-    // bring the peers' bucket offsets of this range into local memory (8 B per bucket and peer)
-    uint64_t *d_pb = nullptr;
-    if (n_peers) CK(dalloc(ctx, &d_pb, (uint64_t)n_peers * (nb + 1)));
-    // staged variant: the peers' residues of the range as well, one bulk copy per peer
-    uint16_t *d_stage = nullptr;
-    if (n_peers && peer_first) {
+    uint64_t *d_pb = nullptr;    // the peers' bucket offsets of this range (8 B per bucket and peer)
+    uint16_t *d_stage = nullptr; // staged variant: the peers' residues of the range
+    auto drop = [&]() {
+        if (d_pb) dfree(ctx, d_pb);
+        if (d_stage) dfree(ctx, d_stage);
+    };
+    cudaError_t e = cudaSuccess;
+    if (n_peers) e = dalloc(ctx, &d_pb, (uint64_t)n_peers * (nb + 1));
+    if (e == cudaSuccess && n_peers && peer_first) {
         uint64_t total = 0;
         for (int p = 0; p < n_peers; p++) {
             if (peer_last[p] < peer_first[p]) {
-                dfree(ctx, d_pb);
+                drop();
                 return fail(ctx, BRGPU_E_INVALID, "bad peer residue range");
             }
             total += peer_last[p] - peer_first[p];
         }
-        cudaError_t e = dalloc(ctx, &d_stage, total + 1);
-        if (e != cudaSuccess) {
-            dfree(ctx, d_pb);
-            return fail(ctx, BRGPU_E_NOMEM, "device allocation (peer residues)", e);
-        }
+        e = dalloc(ctx, &d_stage, total + 1);
     }
-    const uint16_t *res[16];
-    const uint64_t *base[16];
-    res[0] = km->d_res;
-    base[0] = km->d_base;
+    if (e != cudaSuccess) {
+        drop();
+        return fail(ctx, BRGPU_E_NOMEM, "device allocation (peer residues)", e);
+    }
+    const uint16_t *res[BRGPU_MAX_KMER_SOURCES];
+    const uint64_t *base[BRGPU_MAX_KMER_SOURCES];
+    for (int q = 0; q < n_local; q++) {
+        res[q] = local[q]->d_res;
+        base[q] = local[q]->d_base;
+    }
     uint64_t staged = 0;
-    for (int p = 0; p < n_peers; p++) {
+    for (int p = 0; p < n_peers && e == cudaSuccess; p++) {
         uint64_t *dst = d_pb + (uint64_t)p * (nb + 1);
-        CK(cudaMemcpyAsync(dst, (const uint64_t *)peer_offsets[p] + bucket_begin, (nb + 1) * 8, cudaMemcpyDefault,
-                           ctx->stream));
-        base[p + 1] = dst - bucket_begin; // indexable by absolute bucket id inside the range
+        e = cudaMemcpyAsync(dst, (const uint64_t *)peer_offsets[p] + bucket_begin, (nb + 1) * 8, cudaMemcpyDefault, ctx->stream);
+        base[n_local + p] = dst - bucket_begin; // indexable by absolute bucket id inside the range
         if (d_stage) {
             const uint64_t n = peer_last[p] - peer_first[p];
             ProfScope ps(ctx, "peer_residue_copy", (double)n * 2.0, false);
-            if (n)
-                CK(cudaMemcpyAsync(d_stage + staged, (const uint16_t *)peer_residues[p] + peer_first[p], n * 2,
-                                   cudaMemcpyDefault, ctx->stream));
-            // the kernel indexes a source by the peer's absolute residue offsets
-            res[p + 1] = d_stage + staged - peer_first[p];
+            if (n && e == cudaSuccess)
+                e = cudaMemcpyAsync(d_stage + staged, (const uint16_t *)peer_residues[p] + peer_first[p], n * 2,
+                                    cudaMemcpyDefault, ctx->stream);
+            res[n_local + p] = d_stage + staged - peer_first[p]; // the kernel indexes by the peer's absolute offsets
             staged += n;
         } else {
-            res[p + 1] = (const uint16_t *)peer_residues[p];
+            res[n_local + p] = (const uint16_t *)peer_residues[p];
         }
     }
-    CK(cudaMemsetAsync(ctx->d_hist, 0, 256 * sizeof(uint64_t), ctx->stream));
+    if (e == cudaSuccess) e = cudaMemsetAsync(ctx->d_hist, 0, 256 * sizeof(uint64_t), ctx->stream);
+    if (e != cudaSuccess) {
+        drop();
+        return fail(ctx, BRGPU_E_CUDA, "sharded bucket counting (staging)", e);
+    }
     if (set) {
         set->abundance = abundance;
         set->summary_valid = false;
     }
-    launch_bucket_count_multi(ctx, res, base, n_peers + 1, bucket_begin, bucket_end, set ? abundance : 0,
-                              set ? set->d_bits : nullptr, ctx->d_hist, km->n_kmers_hint * (double)(n_peers + 1));
-    cudaError_t e = read_hist(ctx, hist_host);
-    if (d_pb) dfree(ctx, d_pb);
-    if (d_stage) dfree(ctx, d_stage);
+    launch_bucket_count_multi(ctx, res, base, n_local + n_peers, bucket_begin, bucket_end, set ? abundance : 0,
+                              set ? set->d_bits : nullptr, set && emit_summary ? set->d_summary : nullptr, ctx->d_hist,
+                              n_kmers * (double)(n_local + n_peers) / (double)n_local);
+    e = read_hist(ctx, hist_host);
+    drop();
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) return fail(ctx, BRGPU_E_CUDA, "sharded bucket counting", e);
     return BRGPU_OK;
 }
 
+extern "C" int brgpu_kmers_count_parts(brgpu_ctx *ctx, brgpu_kmers *const *local, int n_local, void *const *peer_residues,
+                                       void *const *peer_offsets, const uint64_t *peer_first, const uint64_t *peer_last,
+                                       int n_peers, uint64_t bucket_begin, uint64_t bucket_end, int abundance, brgpu_set *set,
+                                       uint64_t hist_host[256]) {
+    return kmers_count_parts(ctx, local, n_local, peer_residues, peer_offsets, peer_first, peer_last, n_peers, bucket_begin,
+                             bucket_end, abundance, set, false, hist_host);
+}
+
 extern "C" int brgpu_kmers_count_range(brgpu_kmers *km, void *const *peer_residues, void *const *peer_offsets,
                                        int n_peers, uint64_t bucket_begin, uint64_t bucket_end, int abundance,
                                        brgpu_set *set, uint64_t hist_host[256]) {
-    return kmers_count_range(km, peer_residues, peer_offsets, nullptr, nullptr, n_peers, bucket_begin, bucket_end,
-                             abundance, set, hist_host);
+    if (!km) return BRGPU_E_INVALID;
+    return kmers_count_parts(km->ctx, &km, 1, peer_residues, peer_offsets, nullptr, nullptr, n_peers, bucket_begin, bucket_end,
+                             abundance, set, false, hist_host);
 }
 
 extern "C" int brgpu_kmers_count_range_staged(brgpu_kmers *km, void *const *peer_residues, void *const *peer_offsets,
                                               const uint64_t *peer_first, const uint64_t *peer_last, int n_peers,
                                               uint64_t bucket_begin, uint64_t bucket_end, int abundance,
                                               brgpu_set *set, uint64_t hist_host[256]) {
-    if (n_peers && (!peer_first || !peer_last)) return BRGPU_E_INVALID;
-    return kmers_count_range(km, peer_residues, peer_offsets, peer_first, peer_last, n_peers, bucket_begin, bucket_end,
-                             abundance, set, hist_host);
+    if (!km || (n_peers && (!peer_first || !peer_last))) return BRGPU_E_INVALID;
+    return kmers_count_parts(km->ctx, &km, 1, peer_residues, peer_offsets, peer_first, peer_last, n_peers, bucket_begin,
+                             bucket_end, abundance, set, false, hist_host);
+}
+
+// The `fasta` sub-command over a stream of chunks (src/main.rs:72-78: count_fasta(inputs, 8192) reads the
+// records chunk by chunk): every chunk was partitioned on its own (brgpu_kmers_create, 2 B per k-mer kept),
+// the chunk's reads are gone; the buckets are counted over all partitions at once.  Same spectrum and
+// bitfield as one call over all the reads: min(255, occurrences) per canonical k-mer either way.
+extern "C" int brgpu_set_from_kmers(brgpu_ctx *ctx, brgpu_kmers *const *parts, int n_parts, int abundance, int selection,
+                                    double percent, brgpu_set **out) {
+    if (!ctx || !out || !parts || n_parts < 1) return ctx ? fail(ctx, BRGPU_E_INVALID, "null argument") : BRGPU_E_INVALID;
+    *out = nullptr;
+    if (n_parts > BRGPU_MAX_KMER_SOURCES) return fail(ctx, BRGPU_E_INVALID, "at most 64 k-mer partitions per set");
+    if (selection == BRGPU_ABUNDANCE_EXPLICIT && abundance < 0)
+        return fail(ctx, BRGPU_E_NEED_ABUNDANCE, "need an abundance threshold or an abundance method");
+    if (selection < BRGPU_ABUNDANCE_EXPLICIT || selection > BRGPU_ABUNDANCE_PERCENT_AT_LEAST)
+        return fail(ctx, BRGPU_E_INVALID, "unknown abundance selection");
+    if (selection == BRGPU_ABUNDANCE_EXPLICIT && abundance > 255) return fail(ctx, BRGPU_E_INVALID, "abundance must be in 0..=255");
+    for (int q = 0; q < n_parts; q++)
+        if (!parts[q] || parts[q]->ctx != ctx || parts[q]->k != parts[0]->k) return fail(ctx, BRGPU_E_INVALID, "partitions do not match");
+    cudaSetDevice(ctx->device);
+    const int k = parts[0]->k;
+    const uint64_t n_buckets = parts[0]->n_buckets;
+    uint64_t hist[256];
+    int st = BRGPU_OK;
+    if (selection != BRGPU_ABUNDANCE_EXPLICIT) { // the threshold depends on the spectrum: one counting sweep without output
+        st = kmers_count_parts(ctx, parts, n_parts, nullptr, nullptr, nullptr, nullptr, 0, 0, n_buckets, 0, nullptr, false, hist);
+        if (st != BRGPU_OK) return st;
+        abundance = brgpu_spectrum_threshold(hist, selection, percent);
+        if (abundance < 0) return fail(ctx, BRGPU_E_NO_THRESHOLD, "can't compute the abundance threshold");
+    }
+    brgpu_set *s = nullptr;
+    st = set_alloc(ctx, k, &s);
+    if (st != BRGPU_OK) return st;
+    int shift;
+    uint64_t sbytes;
+    summary_geometry(k, &shift, &sbytes);
+    if (sbytes && shift == 6) {
+        cudaError_t e = big_alloc(ctx, (void **)&s->d_summary, sbytes);
+        if (e != cudaSuccess) {
+            brgpu_set_free(s);
+            return fail(ctx, BRGPU_E_NOMEM, "device allocation (summary)", e);
+        }
+        s->summary_bytes = sbytes;
+        s->summary_shift = shift;
+    }
+    st = kmers_count_parts(ctx, parts, n_parts, nullptr, nullptr, nullptr, nullptr, 0, 0, n_buckets, abundance, s,
+                           s->d_summary != nullptr, hist);
+    if (st == BRGPU_OK) {
+        s->abundance = abundance;
+        s->summary_valid = s->d_summary != nullptr; // written by the counting sweep itself
+        memcpy(s->hist, hist, sizeof(hist));
+        if (s->summary_valid) st = build_compact(s);
+    }
+    if (st != BRGPU_OK) {
+        brgpu_set_free(s);
+        return st;
+    }
+    *out = s;
+    return BRGPU_OK;
 }
 
 extern "C" int brgpu_kmers_offsets_at(brgpu_kmers *km, const uint64_t *buckets_host, uint64_t n, uint64_t *offsets_host) {
@@ -1357,11 +1449,161 @@ extern "C" int brgpu_set_from_solid_payload(brgpu_ctx *ctx, const uint8_t *paylo
     return brgpu_set_from_bitfield(ctx, (int)payload_host[0], payload_host + 1, n_bytes - 1, out);
 }
 
+// ------------------------------------------------------------------------------------------
+// set::Hash (src/set/hash.rs): the solid set for k-mers too large for a bitfield — an open-addressing
+// table of canonical k-mers (hash_kernels.cu) behind the same handle type, so that every call that
+// takes a set (get_batch, insert_batch, the correction calls) works on either kind.
+// ------------------------------------------------------------------------------------------
+static inline bool hash_k_supported(int k) { return k >= 3 && k <= 31; } // mask(k) exists for k < 32 (src/correct/mod.rs:26-42)
+
+static uint64_t hash_slots_for(uint64_t keys) { // load factor <= 1/2
+    uint64_t s = 1024;
+    while (s < 2 * keys) s <<= 1;
+    return s;
+}
+
+static int hash_alloc(brgpu_ctx *ctx, int k, uint64_t expected_keys, brgpu_set **out) {
+    brgpu_set *s = new (std::nothrow) brgpu_set;
+    if (!s) return fail(ctx, BRGPU_E_NOMEM, "host allocation");
+    s->ctx = ctx;
+    s->k = k;
+    s->is_hash = true;
+    s->hash_slots = hash_slots_for(expected_keys);
+    cudaError_t e = big_alloc(ctx, (void **)&s->d_hash, s->hash_slots * 8);
+    if (e != cudaSuccess) {
+        delete s;
+        return fail(ctx, BRGPU_E_NOMEM, "device allocation (hash set)", e);
+    }
+    cudaMemsetAsync(s->d_hash, 0xff, s->hash_slots * 8, ctx->stream);
+    *out = s;
+    return BRGPU_OK;
+}
+
+// distinct-key counter: d_getcnt's last slot is free while no profile scope is open; use a private word
+static int hash_read_size(brgpu_set *s, unsigned long long *d_cnt) {
+    brgpu_ctx *ctx = s->ctx;
+    launch_readback(ctx, ctx->h_pinned + 310, d_cnt, sizeof(uint64_t));
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) return fail(ctx, BRGPU_E_CUDA, "hash set insertion", e);
+    s->hash_size += ctx->h_pinned[310];
+    return BRGPU_OK;
+}
+
+// make room for `more` additional keys: rehash into a table twice (or more) the size
+static int hash_reserve(brgpu_set *s, uint64_t more) {
+    brgpu_ctx *ctx = s->ctx;
+    if (2 * (s->hash_size + more) <= s->hash_slots) return BRGPU_OK;
+    const uint64_t slots = hash_slots_for(s->hash_size + more);
+    uint64_t *d_new = nullptr;
+    unsigned long long *d_cnt = nullptr;
+    cudaError_t e = big_alloc(ctx, (void **)&d_new, slots * 8);
+    if (e == cudaSuccess) e = dalloc(ctx, &d_cnt, 1);
+    if (e != cudaSuccess) {
+        if (d_new) big_free(ctx, d_new, slots * 8);
+        return fail(ctx, BRGPU_E_NOMEM, "device allocation (hash set growth)", e);
+    }
+    cudaMemsetAsync(d_new, 0xff, slots * 8, ctx->stream);
+    cudaMemsetAsync(d_cnt, 0, 8, ctx->stream);
+    launch_hash_insert_keys(ctx, s->d_hash, s->hash_slots, s->k, false, d_new, slots, d_cnt);
+    big_free(ctx, s->d_hash, s->hash_slots * 8);
+    dfree(ctx, d_cnt);
+    s->d_hash = d_new;
+    s->hash_slots = slots;
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ctx, BRGPU_E_CUDA, "hash set growth", e);
+    return BRGPU_OK;
+}
+
+static int hash_insert_host_keys(brgpu_set *s, const uint64_t *kmers_host, uint64_t n) {
+    brgpu_ctx *ctx = s->ctx;
+    int st = hash_reserve(s, n);
+    if (st != BRGPU_OK) return st;
+    uint64_t *d_k = nullptr;
+    unsigned long long *d_cnt = nullptr;
+    CK(dalloc(ctx, &d_k, n));
+    cudaError_t e = dalloc(ctx, &d_cnt, 1);
+    if (e != cudaSuccess) {
+        dfree(ctx, d_k);
+        return fail(ctx, BRGPU_E_NOMEM, "device allocation (hash set)", e);
+    }
+    cudaMemcpyAsync(d_k, kmers_host, n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemsetAsync(d_cnt, 0, 8, ctx->stream);
+    launch_hash_insert_keys(ctx, d_k, n, s->k, true, s->d_hash, s->hash_slots, d_cnt);
+    st = hash_read_size(s, d_cnt);
+    dfree(ctx, d_k);
+    dfree(ctx, d_cnt);
+    return st;
+}
+
+// Hash { set: FxHashSet::default(), k } — an empty set::Hash; expected_kmers sizes the first table
+extern "C" int brgpu_set_hash_new(brgpu_ctx *ctx, int k, uint64_t expected_kmers, brgpu_set **out) {
+    if (!ctx || !out) return BRGPU_E_INVALID;
+    *out = nullptr;
+    if (!hash_k_supported(k)) return fail(ctx, BRGPU_E_INVALID, "hash sets hold k-mers with 3 <= k <= 31");
+    cudaSetDevice(ctx->device);
+    return hash_alloc(ctx, k, expected_kmers, out);
+}
+
+// Hash::from_fasta over one more chunk of records (src/set/hash.rs:41-60): every canonical k-mer of every
+// record with len >= k; presence only.  May be called repeatedly (the set grows as needed).
+extern "C" int brgpu_set_hash_add_reads(brgpu_set *s, const brgpu_reads *reads) {
+    if (!s || !reads) return BRGPU_E_INVALID;
+    brgpu_ctx *ctx = s->ctx;
+    if (!s->is_hash) return fail(ctx, BRGPU_E_INVALID, "not a hash set");
+    if (reads->ctx != ctx) return fail(ctx, BRGPU_E_INVALID, "reads belong to another context");
+    cudaSetDevice(ctx->device);
+    reads_ready(reads);
+    double n_kmers = 0;
+    for (uint32_t l : reads->h_len)
+        if (l >= (uint32_t)s->k) n_kmers += (double)(l - (uint32_t)s->k + 1);
+    if (reads->h_len.empty()) n_kmers = (double)reads->sum_len;
+    int st = hash_reserve(s, (uint64_t)n_kmers);
+    if (st != BRGPU_OK) return st;
+    unsigned long long *d_cnt = nullptr;
+    CK(dalloc(ctx, &d_cnt, 1));
+    cudaMemsetAsync(d_cnt, 0, 8, ctx->stream);
+    launch_hash_insert_reads(ctx, *reads->layout, reads->d_seq, reads->d_len, s->k, s->d_hash, s->hash_slots, d_cnt, n_kmers);
+    st = hash_read_size(s, d_cnt);
+    dfree(ctx, d_cnt);
+    return st;
+}
+
+extern "C" int brgpu_set_hash_from_reads(brgpu_ctx *ctx, int k, const brgpu_reads *reads, brgpu_set **out) {
+    if (!ctx || !reads || !out) return BRGPU_E_INVALID;
+    *out = nullptr;
+    if (!hash_k_supported(k)) return fail(ctx, BRGPU_E_INVALID, "hash sets hold k-mers with 3 <= k <= 31");
+    cudaSetDevice(ctx->device);
+    brgpu_set *s = nullptr;
+    int st = hash_alloc(ctx, k, reads->sum_len, &s);
+    if (st != BRGPU_OK) return st;
+    st = brgpu_set_hash_add_reads(s, reads);
+    if (st != BRGPU_OK) {
+        brgpu_set_free(s);
+        return st;
+    }
+    *out = s;
+    return BRGPU_OK;
+}
+
+extern "C" int brgpu_set_hash_from_host_reads(brgpu_ctx *ctx, int k, const uint8_t *seq_host, const uint64_t *offsets_host,
+                                              uint64_t n_reads, brgpu_set **out) {
+    if (!ctx || !out) return BRGPU_E_INVALID;
+    *out = nullptr;
+    brgpu_reads *R = nullptr;
+    int st = brgpu_reads_upload(ctx, seq_host, offsets_host, n_reads, &R);
+    if (st != BRGPU_OK) return st;
+    st = brgpu_set_hash_from_reads(ctx, k, R, out);
+    brgpu_reads_free(R);
+    return st;
+}
+
 extern "C" int brgpu_set_insert_batch(brgpu_set *s, const uint64_t *kmers_host, uint64_t n) {
     if (!s || (!kmers_host && n)) return BRGPU_E_INVALID;
     brgpu_ctx *ctx = s->ctx;
     cudaSetDevice(ctx->device);
     if (!n) return BRGPU_OK;
+    if (s->is_hash) return hash_insert_host_keys(s, kmers_host, n);
     uint64_t *d_k = nullptr;
     CK(dalloc(ctx, &d_k, n));
     CK(cudaMemcpyAsync(d_k, kmers_host, n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
@@ -1375,9 +1617,12 @@ extern "C" int brgpu_set_insert_batch(brgpu_set *s, const uint64_t *kmers_host, 
 
 extern "C" int brgpu_set_k(const brgpu_set *s) { return s ? s->k : 0; }
 extern "C" int brgpu_set_abundance(const brgpu_set *s) { return s ? s->abundance : -1; }
-extern "C" uint64_t brgpu_set_bitfield_bytes(const brgpu_set *s) { return s ? s->n_bytes : 0; }
+extern "C" uint64_t brgpu_set_bitfield_bytes(const brgpu_set *s) { return s && !s->is_hash ? s->n_bytes : 0; }
+extern "C" int brgpu_set_is_hash(const brgpu_set *s) { return s && s->is_hash ? 1 : 0; }
+extern "C" uint64_t brgpu_set_hash_size(const brgpu_set *s) { return s && s->is_hash ? s->hash_size : 0; }
 extern "C" void *brgpu_set_device_ptr(brgpu_set *s) {
     if (!s) return nullptr;
+    if (s->is_hash) return s->d_hash;
     s->summary_valid = false; // the caller may write through the pointer (bitfield all-gather)
     return s->d_bits;
 }
@@ -1385,6 +1630,7 @@ extern "C" void *brgpu_set_device_ptr(brgpu_set *s) {
 extern "C" int brgpu_set_export_bitfield(brgpu_set *s, uint8_t *out_host, uint64_t cap) {
     if (!s || !out_host) return BRGPU_E_INVALID;
     brgpu_ctx *ctx = s->ctx;
+    if (s->is_hash) return fail(ctx, BRGPU_E_INVALID, "a hash set has no bitfield");
     if (cap < s->n_bytes) return fail(ctx, BRGPU_E_OVERFLOW, "output buffer too small");
     cudaSetDevice(ctx->device);
     CK(cudaMemcpyAsync(out_host, s->d_bits, s->n_bytes, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1402,7 +1648,10 @@ extern "C" int brgpu_set_get_batch(brgpu_set *s, const uint64_t *kmers_host, uin
     CK(dalloc(ctx, &d_k, n));
     CK(dalloc(ctx, &d_o, n));
     CK(cudaMemcpyAsync(d_k, kmers_host, n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
-    launch_get_batch(ctx, s->d_bits, s->k, d_k, n, d_o);
+    if (s->is_hash)
+        launch_get_batch_view(ctx, set_view(s), d_k, n, d_o);
+    else
+        launch_get_batch(ctx, s->d_bits, s->k, d_k, n, d_o);
     CK(cudaMemcpyAsync(out_host, d_o, n, cudaMemcpyDeviceToHost, ctx->stream));
     dfree(ctx, d_k);
     dfree(ctx, d_o);
@@ -1677,7 +1926,7 @@ extern "C" int brgpu_counts_merge_slice(brgpu_counts *c, void *const *peer_table
 extern "C" int brgpu_set_threshold_slice(brgpu_set *s, brgpu_counts *c, int abundance, uint64_t begin, uint64_t end) {
     if (!s || !c) return BRGPU_E_INVALID;
     brgpu_ctx *ctx = s->ctx;
-    if (c->ctx != ctx || c->k != s->k) return fail(ctx, BRGPU_E_INVALID, "set and counts do not match");
+    if (c->ctx != ctx || c->k != s->k || s->is_hash) return fail(ctx, BRGPU_E_INVALID, "set and counts do not match");
     if (abundance < 0 || abundance > 255) return fail(ctx, BRGPU_E_INVALID, "abundance must be in 0..=255");
     if (begin > end || end > c->n || (begin & 1023) || ((end & 1023) && end != c->n))
         return fail(ctx, BRGPU_E_INVALID, "slice must be 1024-aligned");

@@ -75,6 +75,13 @@ __global__ void __launch_bounds__(256)
                     idx[j] = canonical_index(window_kmer(prev, cur, g + j, mask), k);
                     go[j] = g + j >= t_lo && g + j < t_hi;
                 }
+                if (set.hash) { // set::Hash: probe the table (k > 19: no dense form exists)
+#pragma unroll
+                    for (int j = 0; j < 8; j++)
+                        if (go[j] && hash_contains(set.hash, set.hash_mask, canonical_kmer(window_kmer(prev, cur, g + j, mask), k)))
+                            out |= 1u << (g + j);
+                    continue;
+                }
                 if (set.dir) {
                     // rank-compacted set: directory entry (8 B, L2), then the occupied block (8 B)
                     uint2 e[8];
@@ -130,7 +137,7 @@ void launch_solid_bitmap(brgpu_ctx *ctx, const Layout &L, const uint8_t *d_seq, 
     ProfScope ps(ctx, reversed ? "solid_bitmap_rev" : "solid_bitmap", n_bases_hint * 33.125);
     uint64_t need = (n_words + 255) / 256;
     uint64_t capb = (uint64_t)ctx->sm_count * 8;
-    const SolidView sv{set.bits, set.summary, set.shift, set.k, (const uint2 *)set.dir, set.blocks};
+    const SolidView sv = solid_view(set);
     const unsigned grid = (unsigned)(need < capb ? need : capb);
     unsigned long long *gc = ctx->profiling ? prof_counter_slot(ctx) : nullptr;
     if (set.k == 17)
@@ -196,7 +203,7 @@ void launch_scan(brgpu_ctx *ctx, const Layout &L, const uint8_t *d_in, const uin
         seg_count_kernel<<<blocks, 256, 0, ctx->stream>>>(d_len_in, (uint32_t)L.n, (uint32_t)p.k, w.d_n_seg);
     }
     launch_exclusive_scan_u32(ctx, w.d_n_seg, L.n, w.d_seg_first, w.d_scan_tmp);
-    const SolidView sv{set.bits, set.summary, set.shift, set.k, (const uint2 *)set.dir, set.blocks};
+    const SolidView sv = solid_view(set);
     // kernel names carry the orientation: the reversed pass sees almost no events (the forward pass
     // repaired them), so averaging the two hides what a launch costs
     static const char *spec_names[2][5] = {{"scan_one", "scan_two", "scan_graph", "scan_greedy", "scan_gap_size"},

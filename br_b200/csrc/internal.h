@@ -125,6 +125,11 @@ struct brgpu_set {
     uint64_t blocks_bytes = 0;   // allocation size
     uint64_t n_occupied = 0;     // occupied 64-bit blocks
     bool compact_valid = false;  // d_dir/d_blocks describe the current bitfield
+    // set::Hash (src/set/hash.rs): open-addressing table of canonical k-mers instead of a bitfield
+    bool is_hash = false;
+    uint64_t *d_hash = nullptr;
+    uint64_t hash_slots = 0;     // power of two
+    uint64_t hash_size = 0;      // distinct k-mers held
 };
 
 namespace brgpu {
@@ -188,8 +193,9 @@ void launch_bucket_count(brgpu_ctx *ctx, const uint16_t *d_residues, const uint6
                          int abundance, uint8_t *d_bits, uint32_t *d_summary, int summary_shift, uint64_t *d_hist,
                          double n_kmers);
 void launch_bucket_count_multi(brgpu_ctx *ctx, const uint16_t *const *d_res, const uint64_t *const *d_base, int n_src,
-                               uint64_t b0, uint64_t b1, int abundance, uint8_t *d_bits, uint64_t *d_hist,
-                               double n_kmers);
+                               uint64_t b0, uint64_t b1, int abundance, uint8_t *d_bits, uint32_t *d_summary,
+                               uint64_t *d_hist, double n_kmers);
+constexpr int BRGPU_MAX_KMER_SOURCES = 64; // == BUCKET_MAX_SOURCES in set_kernels.cu
 void launch_get_batch(brgpu_ctx *ctx, const uint8_t *d_bits, int k, const uint64_t *d_kmers, uint64_t n,
                       uint8_t *d_out);
 void launch_insert_batch(brgpu_ctx *ctx, uint8_t *d_bits, int k, const uint64_t *d_kmers, uint64_t n);
@@ -216,7 +222,16 @@ struct SetView {
     int k;
     const void *dir = nullptr;        // uint2 *
     const uint64_t *blocks = nullptr;
+    const uint64_t *hash = nullptr;   // set::Hash table (then everything above is unused)
+    uint64_t hash_mask = 0;
 };
+
+// ---- set::Hash (hash_kernels.cu) ----
+void launch_hash_insert_reads(brgpu_ctx *ctx, const Layout &L, const uint8_t *d_seq, const uint32_t *d_len, int k,
+                              uint64_t *d_table, uint64_t n_slots, unsigned long long *d_distinct, double n_kmers);
+void launch_hash_insert_keys(brgpu_ctx *ctx, const uint64_t *d_keys, uint64_t n, int k, bool canonicalise,
+                             uint64_t *d_table, uint64_t n_slots, unsigned long long *d_distinct);
+void launch_get_batch_view(brgpu_ctx *ctx, const SetView &set, const uint64_t *d_kmers, uint64_t n, uint8_t *d_out);
 
 // ---- part 2 kernels (correct_kernels.cu) ----
 struct CorrectParams {

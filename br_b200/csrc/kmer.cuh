@@ -55,6 +55,20 @@ __device__ __forceinline__ uint64_t canonical_index(uint64_t kmer, int k) {
     return c >> 1;
 }
 
+// cocktail::kmer::canonical for any k <= 31 (set::Hash stores the canonical k-mer itself, src/set/hash.rs:179)
+__device__ __forceinline__ uint64_t canonical_kmer(uint64_t kmer, int k) {
+    return (__popcll(kmer) & 1) ? revcomp(kmer, k) : kmer;
+}
+
+// set::Hash on the device (hash_kernels.cu): open addressing, linear probing, empty = all ones
+constexpr uint64_t HASH_EMPTY = ~0ULL;
+__host__ __device__ __forceinline__ uint64_t hash_mix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ULL;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+    return x ^ (x >> 31);
+}
+
 // KmerSet::get — one random byte (32 B sector) of the HBM-resident bitfield.
 __device__ __forceinline__ bool solid(const uint8_t *__restrict__ bits, uint64_t kmer, int k) {
     uint64_t idx = canonical_index(kmer, k);
@@ -79,9 +93,28 @@ struct SolidView {
     // arrays together are 69 MB and stay in L2, where the bitfield costs a DRAM access per hit.
     const uint2 *dir;
     const uint64_t *blocks;
+    // set::Hash (nullptr: a dense set): table of canonical k-mers, hash_mask = slots - 1
+    const uint64_t *hash;
+    uint64_t hash_mask;
 };
 
+// host side: the kernels' view of a brgpu::SetView (internal.h)
+template <class SV> inline SolidView solid_view(const SV &s) {
+    return SolidView{s.bits, s.summary, s.shift, s.k, (const uint2 *)s.dir, s.blocks, s.hash, s.hash_mask};
+}
+
+__device__ __forceinline__ bool hash_contains(const uint64_t *__restrict__ table, uint64_t slot_mask, uint64_t key) {
+    uint64_t h = hash_mix64(key) & slot_mask;
+    for (;;) {
+        const uint64_t e = __ldg(table + h);
+        if (e == key) return true;
+        if (e == HASH_EMPTY) return false;
+        h = (h + 1) & slot_mask;
+    }
+}
+
 __device__ __forceinline__ bool solid(const SolidView &v, uint64_t kmer) {
+    if (v.hash) return hash_contains(v.hash, v.hash_mask, canonical_kmer(kmer, v.k)); // src/set/hash.rs:179-181
     uint64_t idx = canonical_index(kmer, v.k);
     if (v.dir) {
         const uint64_t j = idx >> 6;

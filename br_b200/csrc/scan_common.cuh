@@ -76,6 +76,9 @@ __host__ __device__ __forceinline__ uint32_t seg_count(uint32_t len, uint32_t k)
 
 
 
+#ifndef BRGPU_SCAN8_MINB
+#define BRGPU_SCAN8_MINB 8 // the same for the four-segments-per-warp kernels
+#endif
 #ifndef BRGPU_SCAN_MINB
 #define BRGPU_SCAN_MINB 8 // resident blocks per SM the One/Two warp-per-segment kernels are compiled for (64 registers)
 #endif

@@ -1317,6 +1317,16 @@ __device__ __forceinline__ bool g_lookup(G8 &g, const SolidView &set, uint64_t k
 template <int N>
 __device__ __forceinline__ void g_lookup_n(G8 &g, const SolidView &set, const uint64_t (&km)[N], const bool (&want)[N],
                                            bool (&out)[N]) {
+    if (set.hash) { // set::Hash: probe the table, one item after the other
+#pragma unroll
+        for (int t = 0; t < N; t++) {
+#if BRGPU_COUNT_GETS
+            if (want[t]) g.n_get++;
+#endif
+            out[t] = want[t] && hash_contains(set.hash, set.hash_mask, canonical_kmer(km[t], set.k));
+        }
+        return;
+    }
     uint64_t idx[N];
 #pragma unroll
     for (int t = 0; t < N; t++) {
@@ -1691,7 +1701,7 @@ __device__ __forceinline__ Corr g_exist_correct_error(G8 &g, const SolidView &se
 }
 
 template <int METHOD, int KT>
-__global__ void __launch_bounds__(SCAN_WARPS_PER_BLOCK * 32, 8)
+__global__ void __launch_bounds__(SCAN_WARPS_PER_BLOCK * 32, BRGPU_SCAN8_MINB)
     scan_spec8_kernel(const uint8_t *__restrict__ in, const uint32_t *__restrict__ len_in,
                       const uint64_t *__restrict__ slot_off, const uint32_t *__restrict__ bitmap,
                       const uint64_t *__restrict__ seg_first, uint32_t n_reads, uint8_t *__restrict__ seg_out,

@@ -576,7 +576,7 @@ __global__ void __launch_bounds__(BUCKET_THREADS)
 // the peers' HBM — the exchange step of the sharded set construction is these loads, over
 // NVLink, fused into the counting kernel (no staging copy, no collective).  Bucket offsets of
 // all sources are local (the peers' slices are copied in beforehand, they are tiny).
-constexpr int BUCKET_MAX_SOURCES = 16;
+constexpr int BUCKET_MAX_SOURCES = 64; // local partitions (one per chunk of reads) + peer partitions
 struct BucketSources {
     const uint16_t *res[BUCKET_MAX_SOURCES];
     const uint64_t *base[BUCKET_MAX_SOURCES]; // indexable by absolute bucket id in [b0, b1]
@@ -585,12 +585,15 @@ struct BucketSources {
 
 __global__ void __launch_bounds__(BUCKET_THREADS)
     bucket_count_multi_kernel(BucketSources src, uint64_t b0, uint64_t b1, int abundance,
-                              uint32_t *__restrict__ bitfield32, unsigned long long *__restrict__ g_hist) {
+                              uint32_t *__restrict__ bitfield32, uint32_t *__restrict__ summary32,
+                              unsigned long long *__restrict__ g_hist) {
     extern __shared__ uint32_t cnt[];
-    __shared__ uint32_t sh_bits[BUCKET_COUNTERS / 32];
+    __shared__ uint64_t sh_bits64[BUCKET_COUNTERS / 64];
     __shared__ unsigned int sh_hist[256];
     __shared__ uint64_t sh_beg[BUCKET_MAX_SOURCES];
+    __shared__ uint32_t sh_len[BUCKET_MAX_SOURCES];
     __shared__ uint32_t sh_cum[BUCKET_MAX_SOURCES + 1];
+    uint32_t *sh_bits = reinterpret_cast<uint32_t *>(sh_bits64);
     __shared__ unsigned long long sh_owners;
     uint8_t *cnt8 = reinterpret_cast<uint8_t *>(cnt);
     for (int t = threadIdx.x; t < 256; t += BUCKET_THREADS) sh_hist[t] = 0;
@@ -600,16 +603,21 @@ __global__ void __launch_bounds__(BUCKET_THREADS)
     unsigned long long zeros = 0;
     __syncthreads();
     for (uint64_t b = b0 + blockIdx.x; b < b1; b += gridDim.x) {
-        if (threadIdx.x < src.n) sh_beg[threadIdx.x] = __ldg(src.base[threadIdx.x] + b);
+        if (threadIdx.x < src.n) { // every source's piece of this bucket: one thread per source
+            const uint64_t beg = __ldg(src.base[threadIdx.x] + b);
+            sh_beg[threadIdx.x] = beg;
+            sh_len[threadIdx.x] = (uint32_t)(__ldg(src.base[threadIdx.x] + b + 1) - beg);
+        }
+        for (int t = threadIdx.x; t < BUCKET_COUNTERS / 32; t += BUCKET_THREADS) sh_bits[t] = 0;
+        __syncthreads();
         if (threadIdx.x == 0) {
             uint32_t acc = 0;
             for (int q = 0; q < src.n; q++) {
                 sh_cum[q] = acc;
-                acc += (uint32_t)(__ldg(src.base[q] + b + 1) - __ldg(src.base[q] + b));
+                acc += sh_len[q];
             }
             sh_cum[src.n] = acc;
         }
-        for (int t = threadIdx.x; t < BUCKET_COUNTERS / 32; t += BUCKET_THREADS) sh_bits[t] = 0;
         __syncthreads();
         const uint32_t total = sh_cum[src.n];
         auto fetch = [&](uint32_t e) -> uint32_t { // e-th k-mer of the bucket over all sources
@@ -656,9 +664,18 @@ __global__ void __launch_bounds__(BUCKET_THREADS)
             }
         }
         __syncthreads();
-        if (bitfield32)
-            for (int t = threadIdx.x; t < BUCKET_COUNTERS / 32; t += BUCKET_THREADS)
-                bitfield32[b * (BUCKET_COUNTERS / 32) + (uint64_t)t] = sh_bits[t];
+        if (bitfield32) {
+            uint64_t *bitfield64 = reinterpret_cast<uint64_t *>(bitfield32);
+            for (int t = threadIdx.x; t < BUCKET_COUNTERS / 64; t += BUCKET_THREADS) {
+                const uint64_t out = sh_bits64[t];
+                const uint64_t block = b * (BUCKET_COUNTERS / 64) + (uint64_t)t;
+                bitfield64[block] = out;
+                if (summary32) { // one summary bit per 64-bit block (shift 6)
+                    const uint32_t m = __ballot_sync(FULL, out != 0);
+                    if ((threadIdx.x & 31) == 0) summary32[block >> 5] = m;
+                }
+            }
+        }
         if (threadIdx.x == 0) zeros += BUCKET_COUNTERS;
         __syncthreads();
     }
@@ -671,8 +688,8 @@ __global__ void __launch_bounds__(BUCKET_THREADS)
 }
 
 void launch_bucket_count_multi(brgpu_ctx *ctx, const uint16_t *const *d_res, const uint64_t *const *d_base, int n_src,
-                               uint64_t b0, uint64_t b1, int abundance, uint8_t *d_bits, uint64_t *d_hist,
-                               double n_kmers) {
+                               uint64_t b0, uint64_t b1, int abundance, uint8_t *d_bits, uint32_t *d_summary,
+                               uint64_t *d_hist, double n_kmers) {
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(bucket_count_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BUCKET_COUNTERS);
@@ -698,7 +715,7 @@ void launch_bucket_count_multi(brgpu_ctx *ctx, const uint16_t *const *d_res, con
     uint64_t cap = (uint64_t)ctx->sm_count * (uint64_t)per_sm;
     uint64_t nb = b1 - b0;
     bucket_count_multi_kernel<<<(unsigned)(nb < cap ? nb : cap), BUCKET_THREADS, BUCKET_COUNTERS, ctx->stream>>>(
-        src, b0, b1, abundance, reinterpret_cast<uint32_t *>(d_bits), reinterpret_cast<unsigned long long *>(d_hist));
+        src, b0, b1, abundance, reinterpret_cast<uint32_t *>(d_bits), d_summary, reinterpret_cast<unsigned long long *>(d_hist));
 }
 
 // ------------------------------------------------------------------------------------------

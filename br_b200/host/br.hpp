@@ -135,13 +135,48 @@ class KmerSet {
 // cli::AbundanceSelection (src/cli.rs:227-241); None = no method given
 enum class AbundanceSelection { None, FirstMinimum, Rarefaction, PercentMost, PercentLeast };
 
-// set::Pcon (src/set/pcon.rs:13-196): the dense canonical bitfield, resident in HBM
-class Pcon : public KmerSet {
+// what the two device-resident sets share: the handle every corrector and batch call takes
+class DeviceSet : public KmerSet {
   public:
-    Pcon(const Context &ctx, brgpu_set *h) : ctx_(&ctx), h_(h) {}
-    Pcon(const Pcon &) = delete;
-    Pcon &operator=(const Pcon &) = delete;
-    ~Pcon() override { brgpu_set_free(h_); }
+    DeviceSet(const Context &ctx, brgpu_set *h) : ctx_(&ctx), h_(h) {}
+    DeviceSet(const DeviceSet &) = delete;
+    DeviceSet &operator=(const DeviceSet &) = delete;
+    ~DeviceSet() override { brgpu_set_free(h_); }
+    uint8_t k() const override { return (uint8_t)brgpu_set_k(h_); }
+    std::vector<uint8_t> get_batch(const std::vector<uint64_t> &kmers) const {
+        std::vector<uint8_t> out(kmers.size());
+        ctx_->check(brgpu_set_get_batch(h_, kmers.data(), kmers.size(), out.data()));
+        return out;
+    }
+    brgpu_set *handle() const { return h_; }
+    const Context &context() const { return *ctx_; }
+
+  protected:
+    const Context *ctx_;
+    brgpu_set *h_;
+};
+
+// upload chunk after chunk: `each(chunk)` is called once per chunk of at most `chunk_bases` bases
+template <class F> inline void for_each_chunk(const std::vector<std::string> &paths, size_t chunk_bases, F each) {
+    fasta::Chunk c;
+    for (auto &p : paths) {
+        fasta::Reader r(p);
+        bool more = true;
+        while (more) {
+            more = r.read_chunk(c, 8192); // appends
+            if (c.seq.size() >= chunk_bases) {
+                each(c);
+                c.clear();
+            }
+        }
+    }
+    if (c.size()) each(c);
+}
+
+// set::Pcon (src/set/pcon.rs:13-196): the dense canonical bitfield, resident in HBM
+class Pcon : public DeviceSet {
+  public:
+    Pcon(const Context &ctx, brgpu_set *h) : DeviceSet(ctx, h) {}
 
     // Pcon::new(pcon::solid::Solid::new(k)) — empty set (src/set/pcon.rs:183)
     static std::unique_ptr<Pcon> new_(const Context &ctx, int k) {
@@ -196,8 +231,79 @@ class Pcon : public KmerSet {
         return std::make_unique<Pcon>(ctx, h);
     }
 
-    // KmerSet
-    uint8_t k() const override { return (uint8_t)brgpu_set_k(h_); }
+    // The same over a stream of files (src/main.rs:72-78: count_fasta(inputs, 8192) reads the records chunk by
+    // chunk): chunks of ~chunk_bases bases are uploaded, partitioned by table-index range and dropped; the set
+    // is counted over all partitions at once.  Neither the host nor the device ever holds all the reads.
+    static std::unique_ptr<Pcon> from_count_stream(const Context &ctx, const std::vector<std::string> &paths, int k,
+                                                   int abundance, AbundanceSelection selection, double percent = 0.0,
+                                                   size_t chunk_bases = 1u << 30) {
+        k = k - (!(k & 1) & 1);
+        int sel = BRGPU_ABUNDANCE_EXPLICIT;
+        if (abundance < 0) {
+            switch (selection) {
+            case AbundanceSelection::FirstMinimum: sel = BRGPU_ABUNDANCE_FIRST_MINIMUM; break;
+            case AbundanceSelection::Rarefaction: sel = BRGPU_ABUNDANCE_RAREFACTION; break;
+            case AbundanceSelection::PercentMost: sel = BRGPU_ABUNDANCE_PERCENT_AT_MOST; break;
+            case AbundanceSelection::PercentLeast: sel = BRGPU_ABUNDANCE_PERCENT_AT_LEAST; break;
+            case AbundanceSelection::None: break;
+            }
+        }
+        brgpu_set *h = nullptr;
+        if (k < 15) { // small tables: the literal counter accumulates chunk by chunk
+            brgpu_counts *c = nullptr;
+            ctx.check(brgpu_counts_create(ctx.handle(), k, &c));
+            try {
+                for_each_chunk(paths, chunk_bases, [&](const fasta::Chunk &ch) {
+                    brgpu_reads *r = nullptr;
+                    ctx.check(brgpu_reads_upload(ctx.handle(), ch.seq.data(), ch.offsets.data(), ch.size(), &r));
+                    int st = brgpu_counts_add_reads(c, r);
+                    brgpu_reads_free(r);
+                    ctx.check(st);
+                });
+                if (abundance < 0) {
+                    if (sel == BRGPU_ABUNDANCE_EXPLICIT) ctx.check(BRGPU_E_NEED_ABUNDANCE);
+                    uint64_t hist[256];
+                    ctx.check(brgpu_counts_spectrum(c, hist));
+                    abundance = brgpu_spectrum_threshold(hist, sel, percent);
+                    if (abundance < 0) ctx.check(BRGPU_E_NO_THRESHOLD);
+                }
+                ctx.check(brgpu_set_from_counts(c, abundance, &h));
+            } catch (...) {
+                brgpu_counts_free(c);
+                throw;
+            }
+            brgpu_counts_free(c);
+            return std::make_unique<Pcon>(ctx, h);
+        }
+        std::vector<brgpu_kmers *> parts;
+        auto drop = [&]() {
+            for (auto p : parts) brgpu_kmers_free(p);
+        };
+        try {
+            for_each_chunk(paths, chunk_bases, [&](const fasta::Chunk &ch) {
+                brgpu_reads *r = nullptr;
+                ctx.check(brgpu_reads_upload(ctx.handle(), ch.seq.data(), ch.offsets.data(), ch.size(), &r));
+                brgpu_kmers *km = nullptr;
+                int st = brgpu_kmers_create(ctx.handle(), k, r, &km);
+                brgpu_reads_free(r);
+                ctx.check(st);
+                parts.push_back(km);
+            });
+            if (parts.empty()) { // no record at all: an empty chunk still gives the (all-zero) spectrum and set
+                fasta::Chunk none;
+                none.offsets.assign(1, 0);
+                drop();
+                return from_count(ctx, none, k, abundance, selection, percent);
+            }
+            ctx.check(brgpu_set_from_kmers(ctx.handle(), parts.data(), (int)parts.size(), abundance, sel, percent, &h));
+        } catch (...) {
+            drop();
+            throw;
+        }
+        drop();
+        return std::make_unique<Pcon>(ctx, h);
+    }
+
     // Pcon::get (src/set/pcon.rs:189-191), forward k-mers accepted.  Served from a host mirror of
     // the bitfield (exported once): a GPU round trip per k-mer would be useless.  Batches go
     // through get_batch.
@@ -207,11 +313,6 @@ class Pcon : public KmerSet {
         const uint64_t mask = (kk < 32) ? ((1ULL << (2 * kk)) - 1ULL) : ~0ULL;
         const uint64_t idx = kmer::canonical(kmer & mask, kk) >> 1;
         return (mirror_[idx >> 3] >> (idx & 7)) & 1;
-    }
-    std::vector<uint8_t> get_batch(const std::vector<uint64_t> &kmers) const {
-        std::vector<uint8_t> out(kmers.size());
-        ctx_->check(brgpu_set_get_batch(h_, kmers.data(), kmers.size(), out.data()));
-        return out;
     }
     // Solid::set(kmer, true) on a batch (canonicalises, like the reference's unit tests rely on)
     void set(const std::vector<uint64_t> &kmers) {
@@ -259,13 +360,42 @@ class Pcon : public KmerSet {
         if (!ok) throw std::runtime_error("write error in " + path);
     }
 
-    brgpu_set *handle() const { return h_; }
-    const Context &context() const { return *ctx_; }
-
   private:
-    const Context *ctx_;
-    brgpu_set *h_;
     mutable std::vector<uint8_t> mirror_;
+};
+
+// set::Hash (src/set/hash.rs:14-186): canonical k-mers of any k <= 31 in a device hash table — the set
+// behind the `large-kmer` sub-command (src/main.rs:147-163)
+class Hash : public DeviceSet {
+  public:
+    Hash(const Context &ctx, brgpu_set *h) : DeviceSet(ctx, h) {}
+
+    // Hash::from_fasta (src/set/hash.rs:41-100): presence of every canonical k-mer of every record with
+    // len >= k, read chunk by chunk like the reference's 8192-record loop
+    static std::unique_ptr<Hash> from_fasta(const Context &ctx, const std::vector<std::string> &paths, int k,
+                                            size_t chunk_bases = 1u << 28) {
+        brgpu_set *h = nullptr;
+        ctx.check(brgpu_set_hash_new(ctx.handle(), k, 1u << 20, &h));
+        auto out = std::make_unique<Hash>(ctx, h);
+        for_each_chunk(paths, chunk_bases, [&](const fasta::Chunk &ch) {
+            brgpu_reads *r = nullptr;
+            ctx.check(brgpu_reads_upload(ctx.handle(), ch.seq.data(), ch.offsets.data(), ch.size(), &r));
+            int st = brgpu_set_hash_add_reads(h, r);
+            brgpu_reads_free(r);
+            ctx.check(st);
+        });
+        return out;
+    }
+    // an empty Hash and insertion of (forward or canonical) k-mers, for the unit KATs
+    static std::unique_ptr<Hash> new_(const Context &ctx, int k) {
+        brgpu_set *h = nullptr;
+        ctx.check(brgpu_set_hash_new(ctx.handle(), k, 0, &h));
+        return std::make_unique<Hash>(ctx, h);
+    }
+    void insert(const std::vector<uint64_t> &kmers) { ctx_->check(brgpu_set_insert_batch(h_, kmers.data(), kmers.size())); }
+    // Hash::get (src/set/hash.rs:179-181); one k-mer per call is a GPU round trip: tests only
+    bool get(uint64_t kmer) const override { return get_batch({kmer})[0] != 0; }
+    uint64_t size() const { return brgpu_set_hash_size(h_); }
 };
 
 } // namespace set
@@ -283,7 +413,7 @@ namespace correct {
 class Corrector {
   public:
     virtual ~Corrector() = default;
-    const set::Pcon &valid_kmer() const { return *set_; }
+    const set::DeviceSet &valid_kmer() const { return *set_; }
     uint8_t k() const { return set_->k(); }
     cli::CorrectionMethod method() const { return method_; }
     int confirm() const { return confirm_; }
@@ -307,30 +437,30 @@ class Corrector {
     std::vector<uint8_t> correct(const std::string &seq) const { return correct((const uint8_t *)seq.data(), seq.size()); }
 
   protected:
-    Corrector(const set::Pcon &s, cli::CorrectionMethod m, int confirm, int max_search)
+    Corrector(const set::DeviceSet &s, cli::CorrectionMethod m, int confirm, int max_search)
         : set_(&s), method_(m), confirm_(confirm), max_search_(max_search) {}
 
   private:
-    const set::Pcon *set_;
+    const set::DeviceSet *set_;
     cli::CorrectionMethod method_;
     int confirm_, max_search_;
 };
 
 struct One : Corrector { // src/correct/exist/one.rs:74
-    One(const set::Pcon &s, uint8_t c) : Corrector(s, cli::CorrectionMethod::One, c, 7) {}
+    One(const set::DeviceSet &s, uint8_t c) : Corrector(s, cli::CorrectionMethod::One, c, 7) {}
 };
 struct Two : Corrector { // src/correct/exist/two.rs:328
-    Two(const set::Pcon &s, uint8_t c) : Corrector(s, cli::CorrectionMethod::Two, c, 7) {}
+    Two(const set::DeviceSet &s, uint8_t c) : Corrector(s, cli::CorrectionMethod::Two, c, 7) {}
 };
 struct Graph : Corrector { // src/correct/graph.rs:29-37
-    explicit Graph(const set::Pcon &s) : Corrector(s, cli::CorrectionMethod::Graph, 5, 7) {}
+    explicit Graph(const set::DeviceSet &s) : Corrector(s, cli::CorrectionMethod::Graph, 5, 7) {}
 };
 struct Greedy : Corrector { // src/correct/greedy.rs:41-54
-    Greedy(const set::Pcon &s, uint8_t max_search, uint8_t nb_validate)
+    Greedy(const set::DeviceSet &s, uint8_t max_search, uint8_t nb_validate)
         : Corrector(s, cli::CorrectionMethod::Greedy, nb_validate, max_search) {}
 };
 struct GapSize : Corrector { // src/correct/gap_size.rs:29-42
-    GapSize(const set::Pcon &s, uint8_t c) : Corrector(s, cli::CorrectionMethod::GapSize, c, 7) {}
+    GapSize(const set::DeviceSet &s, uint8_t c) : Corrector(s, cli::CorrectionMethod::GapSize, c, 7) {}
 };
 
 } // namespace correct
@@ -338,7 +468,7 @@ struct GapSize : Corrector { // src/correct/gap_size.rs:29-42
 using Methods = std::vector<std::unique_ptr<correct::Corrector>>;
 
 // src/lib.rs:141-164 — same argument mapping
-inline Methods build_methods(const std::vector<cli::CorrectionMethod> &params, const set::Pcon &solid, uint8_t confirm,
+inline Methods build_methods(const std::vector<cli::CorrectionMethod> &params, const set::DeviceSet &solid, uint8_t confirm,
                              uint8_t max_search) {
     Methods methods;
     for (auto m : params) {
@@ -367,14 +497,25 @@ inline void correct_chunk(const Methods &methods, bool two_side, const fasta::Ch
         out.offsets = in.offsets;
         return;
     }
-    const set::Pcon &solid = methods[0]->valid_kmer();
+    const set::DeviceSet &solid = methods[0]->valid_kmer();
     std::vector<uint8_t> ids;
-    int confirm = 5, max_search = 7;
+    // the C ABI takes one (confirm, max_search) pair for the chain, as br's command line does (build_methods
+    // passes one -C and one -M, src/lib.rs:141-164); a hand-built chain that disagrees is refused
+    int confirm = -1, max_search = -1;
     for (auto &m : methods) {
         ids.push_back((uint8_t)m->method());
-        if (m->method() != cli::CorrectionMethod::Graph) confirm = m->confirm();
-        if (m->method() == cli::CorrectionMethod::Greedy) max_search = m->max_search();
+        if (&m->valid_kmer() != &solid) throw std::invalid_argument("all methods of a chain must share the set");
+        if (m->method() != cli::CorrectionMethod::Graph) {
+            if (confirm >= 0 && confirm != m->confirm()) throw std::invalid_argument("all methods of a chain must share confirm");
+            confirm = m->confirm();
+        }
+        if (m->method() == cli::CorrectionMethod::Greedy) {
+            if (max_search >= 0 && max_search != m->max_search()) throw std::invalid_argument("all Greedy methods of a chain must share max_search");
+            max_search = m->max_search();
+        }
     }
+    if (confirm < 0) confirm = 5;
+    if (max_search < 0) max_search = 7;
     const size_t total = in.seq.size();
     out.seq.resize(total + total / 8 + 64 * n + 64);
     for (;;) {

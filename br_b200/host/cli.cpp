@@ -3,7 +3,7 @@
 //   brgpu-cli [-i IN..] [-o OUT..] [-s] [-c METHOD..] [-C CONFIRM] [-M MAX_SEARCH] [-b N] [-t N] [-d DEVICE] [-q] [-v..]
 //             fasta -i READS.. -k K [-a N] [first-minimum | rarefaction P | percent-most P | percent-least P]   src/main.rs:72-115
 //           | solid -i FILE -f solid|fasta [-k K]                      src/main.rs:117-145
-//           | large-kmer -i FILE -f fasta -k K   (odd K <= 19 only: the dense set; src/main.rs:147-163)
+//           | large-kmer -i FILE -f fasta -k K   (set::Hash, 3 <= K <= 31; src/main.rs:147-163)
 //           | count ...                          (rejected: no fixture pins pcon's count-file format)
 //
 // Same flag names, defaults and quirks as the reference: -s *disables* the
@@ -31,6 +31,7 @@ struct Args {
     uint64_t record_buffer = 8192;
     int device = 0;
     std::string write_solid;
+    size_t chunk_bases = 1u << 30; // bases per chunk while the set is built (the reads are streamed, not held)
     // sub-command
     std::string sub;
     std::vector<std::string> sub_inputs;
@@ -100,6 +101,7 @@ Args parse(int argc, char **argv) {
         else if (t == "-t" || t == "--threads") (void)parse_int(t, value(t), 0, 1 << 20);
         else if (t == "-d" || t == "--device") a.device = (int)parse_int(t, value(t), 0, 1023);
         else if (t == "--write-solid") a.write_solid = value(t);
+        else if (t == "--chunk-bases") a.chunk_bases = (size_t)parse_int(t, value(t), 1, 1LL << 40); // set construction streams chunks of this size
         else if (t == "-q" || t == "--quiet") {}
         else if (t.rfind("-v", 0) == 0 || t == "--verbosity") {}
         else if (t == "-T" || t == "--timestamp") (void)value(t);
@@ -137,7 +139,7 @@ void read_all(const std::vector<std::string> &paths, br::fasta::Chunk &all) {
     }
 }
 
-std::unique_ptr<br::set::Pcon> build_set(const br::Context &ctx, const Args &a) {
+std::unique_ptr<br::set::DeviceSet> build_set(const br::Context &ctx, const Args &a) {
     using br::set::AbundanceSelection;
     using br::set::Pcon;
     if (a.sub_inputs.empty()) usage_error("the following required arguments were not provided: --inputs");
@@ -148,9 +150,8 @@ std::unique_ptr<br::set::Pcon> build_set(const br::Context &ctx, const Args &a) 
         else if (a.selection == "rarefaction") sel = AbundanceSelection::Rarefaction;
         else if (a.selection == "percent-most") sel = AbundanceSelection::PercentMost;
         else if (a.selection == "percent-least") sel = AbundanceSelection::PercentLeast;
-        br::fasta::Chunk reads;
-        read_all(a.sub_inputs, reads);
-        return Pcon::from_count(ctx, reads, a.k, a.abundance, sel, a.percent);
+        // count_fasta(inputs, 8192) streams the records (src/main.rs:74): so does this, 1 Gbase per chunk
+        return Pcon::from_count_stream(ctx, a.sub_inputs, a.k, a.abundance, sel, a.percent, a.chunk_bases);
     }
     if (a.sub == "solid") { // src/main.rs:117-145
         if (a.format == "solid") return Pcon::from_pcon_solid(ctx, a.sub_inputs[0]);
@@ -165,11 +166,8 @@ std::unique_ptr<br::set::Pcon> build_set(const br::Context &ctx, const Args &a) 
     if (a.sub == "large-kmer") { // src/main.rs:147-163: set::Hash == presence-only set of canonical k-mers
         if (a.k < 0) usage_error("the following required arguments were not provided: --kmer-size");
         if (a.format != "fasta") usage_error("invalid value '" + a.format + "' for '--format': fasta");
-        if (!(a.k & 1) || a.k > 19)
-            throw std::runtime_error("large-kmer: brgpu holds the set as a dense bitfield, odd k <= 19 only");
-        br::fasta::Chunk reads;
-        read_all({a.sub_inputs[0]}, reads);
-        return Pcon::from_fasta(ctx, reads, a.k);
+        if (a.k < 3 || a.k > 31) throw std::runtime_error("large-kmer: k must be in 3..=31 (k-mers are 2-bit packed in 64 bits)");
+        return br::set::Hash::from_fasta(ctx, {a.sub_inputs[0]}, a.k, a.chunk_bases);
     }
     throw std::runtime_error("sub-command '" + a.sub + "' is not supported by brgpu (pcon's count-file format is not pinned by any fixture)");
 }
@@ -195,8 +193,12 @@ int main(int argc, char **argv) {
             return 0;
         }
         br::Context ctx(a.device);
-        std::unique_ptr<br::set::Pcon> kmer_set = build_set(ctx, a);
-        if (!a.write_solid.empty()) kmer_set->write_solid(a.write_solid);
+        std::unique_ptr<br::set::DeviceSet> kmer_set = build_set(ctx, a);
+        if (!a.write_solid.empty()) {
+            auto *dense = dynamic_cast<br::set::Pcon *>(kmer_set.get());
+            if (!dense) throw std::runtime_error("--write-solid needs a dense set (fasta / solid sub-commands)");
+            dense->write_solid(a.write_solid);
+        }
         br::Methods methods = br::build_methods(a.corrections, *kmer_set, (uint8_t)a.confirm, (uint8_t)a.max_search);
         br::run_correction(a.inputs, a.outputs, methods, a.two_side, a.record_buffer);
     } catch (const std::exception &e) {

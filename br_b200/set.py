@@ -118,6 +118,48 @@ class Pcon(KmerSet):
                   ctx._h)
         return cls(ctx, h)
 
+    @classmethod
+    def from_chunks(cls, ctx, chunks, k, abundance=None, abundance_selection=None, percent=0.0):
+        """The `fasta` sub-command over a stream of record chunks (count_fasta(inputs, 8192) reads chunk by
+        chunk, src/main.rs:72-78): every chunk — a Reads or a (seq, offsets) pair — is partitioned on its
+        own and dropped; the set is counted over all partitions at once (brgpu_set_from_kmers).  Same result
+        as from_reads over the concatenation; peak device memory is 2 B per k-mer plus one chunk."""
+        k = k - (~(k & 1) & 1)
+        sel, ab = selection_code(abundance, abundance_selection)
+        if k < 15:  # small tables: the literal counter accumulates chunk by chunk
+            c = Counter(ctx, k)
+            for ch in chunks:
+                r = ch if isinstance(ch, Reads) else Reads.upload(ctx, *ch)
+                c.count(r)
+                if r is not ch:
+                    r.free()
+            if ab < 0:
+                if sel == _lib.ABUNDANCE_EXPLICIT:
+                    raise _lib.BrgpuError(_lib.E_NEED_ABUNDANCE)
+                a = spectrum_threshold(c.spectrum(), abundance_selection, percent)
+                if a is None:
+                    raise _lib.BrgpuError(_lib.E_NO_THRESHOLD)
+                ab = a
+            s = c.to_set(ab)
+            c.free()
+            return s
+        parts = []
+        try:
+            for ch in chunks:
+                r = ch if isinstance(ch, Reads) else Reads.upload(ctx, *ch)
+                h = C.c_void_p()
+                check(lib.brgpu_kmers_create(ctx._h, k, r._h, C.byref(h)), ctx._h)
+                parts.append(h)
+                if r is not ch:
+                    r.free()
+            arr = (C.c_void_p * max(1, len(parts)))(*[p.value for p in parts])
+            out = C.c_void_p()
+            check(lib.brgpu_set_from_kmers(ctx._h, arr, len(parts), ab, sel, float(percent), C.byref(out)), ctx._h)
+        finally:
+            for p in parts:
+                lib.brgpu_kmers_free(p)
+        return cls(ctx, out)
+
     # --- KmerSet --------------------------------------------------------------------------------
     def k(self):
         return lib.brgpu_set_k(self._h)
@@ -177,6 +219,48 @@ class Pcon(KmerSet):
 
     def __del__(self):
         self.free()
+
+
+class Hash(Pcon):
+    """set::Hash (src/set/hash.rs:14-186): the set behind br's `large-kmer` sub-command — canonical
+    k-mers of any k <= 31 in a device hash table.  Same KmerSet surface as Pcon (get, get_batch, k,
+    insert, insert_all_kmers) and accepted by every corrector; it has no bitfield or spectrum."""
+
+    @classmethod
+    def new(cls, ctx, k, expected_kmers=0):
+        h = C.c_void_p()
+        check(lib.brgpu_set_hash_new(ctx._h, k, int(expected_kmers), C.byref(h)), ctx._h)
+        return cls(ctx, h)
+
+    @classmethod
+    def from_reads(cls, ctx, reads, k):
+        """Hash::from_fasta (src/set/hash.rs:41-100): presence of every canonical k-mer of every record
+        with len >= k.  `reads` is a device-resident Reads or a (seq, offsets) pair of host buffers."""
+        h = C.c_void_p()
+        if isinstance(reads, Reads):
+            check(lib.brgpu_set_hash_from_reads(ctx._h, k, reads._h, C.byref(h)), ctx._h)
+        else:
+            s, off = as_u8(reads[0]), as_offsets(reads[1])
+            n = (off.numel() if hasattr(off, "numel") else off.size) - 1
+            check(lib.brgpu_set_hash_from_host_reads(ctx._h, k, _addr(s), _addr(off), n, C.byref(h)), ctx._h)
+        return cls(ctx, h)
+
+    def add_reads(self, reads: Reads):
+        """One more chunk of records (the 8192-record loop of src/set/hash.rs:76-97)."""
+        check(lib.brgpu_set_hash_add_reads(self._h, reads._h), self.ctx._h)
+
+    def __len__(self):
+        return lib.brgpu_set_hash_size(self._h)
+
+    @property
+    def abundance(self):
+        return None
+
+    def spectrum(self):
+        raise TypeError("set::Hash is presence-only: it has no spectrum")
+
+    def bitfield(self):
+        raise TypeError("set::Hash has no bitfield")
 
 
 class Counter:

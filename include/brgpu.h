@@ -14,8 +14,9 @@
  * There is NO CPU fallback: without a CUDA device every entry point that needs one fails
  * with BRGPU_E_NO_DEVICE.
  *
- * Supported k: odd, 3 <= k <= 19 (dense bitfield of 2^(2k-1) bits; br's `fasta`
- * sub-command forces k odd, src/cli.rs:277-279; the parity-canonical form needs it).
+ * Supported k: odd, 3 <= k <= 19 for the dense bitfield of 2^(2k-1) bits (set::Pcon; br's `fasta`
+ * sub-command forces k odd, src/cli.rs:277-279; the parity-canonical form needs it), and
+ * 3 <= k <= 31 for the hash set (set::Hash, br's `large-kmer` sub-command).
  */
 #ifndef BRGPU_H
 #define BRGPU_H
@@ -167,6 +168,21 @@ int brgpu_set_from_solid_payload(brgpu_ctx *ctx, const uint8_t *payload_host, ui
 int brgpu_set_new(brgpu_ctx *ctx, int k, brgpu_set **out);
 int brgpu_set_insert_batch(brgpu_set *set, const uint64_t *kmers_host, uint64_t n);
 
+/* set::Hash (src/set/hash.rs:14-186, wired at src/main.rs:147-163: the `large-kmer` sub-command): the
+ * solid set for k-mers too large for a dense bitfield — 3 <= k <= 31, any parity — as a device hash
+ * table of canonical k-mers behind the same handle type: brgpu_set_k / _get_batch / _insert_batch /
+ * _free and all the correction calls take it; the bitfield calls return BRGPU_E_INVALID for it.
+ * _hash_new = an empty Hash (expected_kmers sizes the first table; it grows on demand),
+ * _hash_add_reads = Hash::from_fasta's loop over one chunk of records (presence only: every canonical
+ * k-mer of every record with len >= k, src/set/hash.rs:52-57); may be called once per chunk. */
+int brgpu_set_hash_new(brgpu_ctx *ctx, int k, uint64_t expected_kmers, brgpu_set **out);
+int brgpu_set_hash_add_reads(brgpu_set *set, const brgpu_reads *reads);
+int brgpu_set_hash_from_reads(brgpu_ctx *ctx, int k, const brgpu_reads *reads, brgpu_set **out);
+int brgpu_set_hash_from_host_reads(brgpu_ctx *ctx, int k, const uint8_t *seq_host, const uint64_t *offsets_host,
+                                   uint64_t n_reads, brgpu_set **out);
+int brgpu_set_is_hash(const brgpu_set *set);
+uint64_t brgpu_set_hash_size(const brgpu_set *set);         /* distinct canonical k-mers held */
+
 int brgpu_set_k(const brgpu_set *set);                      /* KmerSet::k */
 int brgpu_set_abundance(const brgpu_set *set);              /* threshold used, -1 if not built from counts */
 uint64_t brgpu_set_bitfield_bytes(const brgpu_set *set);    /* 2^(2k-1)/8 */
@@ -242,6 +258,20 @@ int brgpu_kmers_count_range_staged(brgpu_kmers *kmers, void *const *peer_residue
                                    const uint64_t *peer_first, const uint64_t *peer_last, int n_peers,
                                    uint64_t bucket_begin, uint64_t bucket_end, int abundance, brgpu_set *set,
                                    uint64_t hist_host[256]);
+/* The general form: bucket range over `n_local` partitions of this context (one per chunk of reads —
+ * a GPU whose shard does not fit one chunk holds several) plus `n_peers` peer partitions; peer_first /
+ * peer_last may be NULL (remote loads instead of staged copies).  n_local + n_peers <= 64. */
+int brgpu_kmers_count_parts(brgpu_ctx *ctx, brgpu_kmers *const *local, int n_local, void *const *peer_residues,
+                            void *const *peer_offsets, const uint64_t *peer_first, const uint64_t *peer_last, int n_peers,
+                            uint64_t bucket_begin, uint64_t bucket_end, int abundance, brgpu_set *set,
+                            uint64_t hist_host[256]);
+/* The `fasta` sub-command over a stream of chunks (src/main.rs:72-78, count_fasta(inputs, 8192) reads the
+ * records chunk by chunk): upload a chunk, brgpu_kmers_create, free the chunk, repeat; then build the set
+ * from all partitions at once.  Peak device memory is 2 B per k-mer of the input plus one chunk, and the
+ * result equals brgpu_set_from_reads over all the reads.  k >= 15 (smaller k: brgpu_counts_add_reads per
+ * chunk + brgpu_counts_spectrum + brgpu_set_from_counts, whose table is at most 128 MiB).  n_parts <= 64. */
+int brgpu_set_from_kmers(brgpu_ctx *ctx, brgpu_kmers *const *parts, int n_parts, int abundance, int selection,
+                         double percent, brgpu_set **out);
 void brgpu_kmers_free(brgpu_kmers *kmers);
 
 /* ------------------------------------------------------------------------------------------

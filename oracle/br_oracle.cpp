@@ -82,11 +82,23 @@ static inline uint64_t add_nuc_to_end(uint64_t kmer, uint64_t nuc, int k) {
 struct bro_set {
     int k;
     Bytes bits;
+    /* set::Hash (src/set/hash.rs:14-17, :178-186): FxHashSet<u64> of canonical k-mers behind the same
+     * KmerSet::get; only membership matters, so any exact set is equivalent.  Null for set::Pcon. */
+    std::unordered_set<uint64_t> *hash = nullptr;
+    ~bro_set() { delete hash; }
     inline bool get(uint64_t kmer) const {
+        if (hash) return hash->count(canonical(kmer, k)) != 0; /* src/set/hash.rs:179-181 */
         uint64_t idx = canonical(kmer, k) >> 1;
         return (bits[idx >> 3] >> (idx & 7)) & 1;
     }
     inline void set(uint64_t kmer, bool v) {
+        if (hash) {
+            if (v)
+                hash->insert(canonical(kmer, k));
+            else
+                hash->erase(canonical(kmer, k));
+            return;
+        }
         uint64_t idx = canonical(kmer, k) >> 1;
         if (v)
             bits[idx >> 3] |= (uint8_t)(1u << (idx & 7));
@@ -971,6 +983,28 @@ bro_set *bro_set_from_bitfield(int k, const uint8_t *bits, size_t n) {
     memcpy(s->bits.data(), bits, n);
     return s;
 }
+/* set::Hash — empty, then Hash::from_fasta's loop over records (src/set/hash.rs:41-60): every
+ * canonical k-mer of every record with len >= k */
+bro_set *bro_hash_new(int k) {
+    bro_set *s = new bro_set;
+    s->k = k;
+    s->hash = new std::unordered_set<uint64_t>();
+    return s;
+}
+void bro_hash_add_reads(bro_set *s, const uint8_t *seq, const uint64_t *offsets, size_t n_reads) {
+    const size_t k = (size_t)s->k;
+    for (size_t r = 0; r < n_reads; r++) {
+        const uint8_t *p = seq + offsets[r];
+        const size_t len = (size_t)(offsets[r + 1] - offsets[r]);
+        if (len < k) continue; /* src/set/hash.rs:52 */
+        uint64_t kmer = seq2bit(p, k - 1);
+        for (size_t i = k - 1; i < len; i++) { /* cocktail::tokenizer::Canonical */
+            kmer = add_nuc_to_end(kmer, nuc2bit(p[i]), s->k);
+            s->hash->insert(canonical(kmer, s->k));
+        }
+    }
+}
+size_t bro_hash_size(const bro_set *s) { return s->hash ? s->hash->size() : 0; }
 void bro_set_free(bro_set *s) { delete s; }
 int bro_set_k(const bro_set *s) { return s->k; }
 void bro_set_set(bro_set *s, uint64_t kmer, int value) { s->set(kmer, value != 0); }

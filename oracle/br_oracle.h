@@ -44,6 +44,10 @@ uint64_t bro_canonical(uint64_t kmer, int k);
 typedef struct bro_set bro_set;
 bro_set *bro_set_new(int k);                                            /* Solid::new */
 bro_set *bro_set_from_bitfield(int k, const uint8_t *bits, size_t n);   /* body of a .solid payload */
+/* set::Hash (src/set/hash.rs): the same handle type, backed by an exact hash set of canonical k-mers */
+bro_set *bro_hash_new(int k);
+void bro_hash_add_reads(bro_set *, const uint8_t *seq, const uint64_t *offsets, size_t n_reads); /* Hash::from_fasta */
+size_t bro_hash_size(const bro_set *);
 void bro_set_free(bro_set *);
 int bro_set_k(const bro_set *);
 void bro_set_set(bro_set *, uint64_t kmer, int value);                  /* Solid::set (canonicalises) */

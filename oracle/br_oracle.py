@@ -42,6 +42,9 @@ def _load():
     sig("bro_canonical", C.c_uint64, C.c_uint64, C.c_int)
     sig("bro_set_new", vp, C.c_int)
     sig("bro_set_from_bitfield", vp, C.c_int, vp, sz)
+    sig("bro_hash_new", vp, C.c_int)
+    sig("bro_hash_add_reads", None, vp, vp, vp, sz)
+    sig("bro_hash_size", sz, vp)
     sig("bro_set_free", None, vp)
     sig("bro_set_k", C.c_int, vp)
     sig("bro_set_set", None, vp, C.c_uint64, C.c_int)
@@ -207,6 +210,32 @@ class Solid:
         finally:
             lib().bro_result_free(h)
         return d, o
+
+
+class Hash(Solid):
+    """set::Hash (src/set/hash.rs): exact set of canonical k-mers behind the same KmerSet::get, any
+    k <= 31.  Everything `Solid` offers except the bitfield works on it (correct, run_correction, ...)."""
+
+    def __init__(self, k):
+        super().__init__(_handle=lib().bro_hash_new(k))
+
+    @classmethod
+    def from_reads(cls, k, seq, offsets):
+        """Hash::from_fasta (src/set/hash.rs:41-60) over records given as (seq, offsets)."""
+        h = cls(k)
+        h.add_reads(seq, offsets)
+        return h
+
+    def add_reads(self, seq, offsets):
+        s = _u8(seq)
+        off = np.ascontiguousarray(offsets, dtype=np.uint64)
+        lib().bro_hash_add_reads(self._h, _ptr(s), _ptr(off), off.size - 1)
+
+    def __len__(self):
+        return lib().bro_hash_size(self._h)
+
+    def bits(self):
+        raise TypeError("set::Hash has no bitfield")
 
 
 class Counter:

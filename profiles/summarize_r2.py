@@ -42,8 +42,10 @@ def parse(path):
 
 
 def bench_name(fn, state):
-    base = re.sub(r"^(brgpu::)?((fast|cnt)::)?", "", fn.split("(")[0])
+    base = re.sub(r"^(void )?(brgpu::)?((fast|cnt)::)?", "", fn.split("(")[0].strip())
     m = re.match(r"(\w+?)(<(.*)>)?$", base)
+    if not m:
+        return None, False
     name, targs = m.group(1), (m.group(3) or "")
     rev = "_rev" if state["reversals"] % 2 else ""
     if name == "reverse_slots_kernel":

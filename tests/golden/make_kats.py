@@ -207,6 +207,20 @@ def main():
         }
     )
 
+    # src/set/hash.rs:185-242 — the same four KATs through Hash::from_fasta (FILE = ">1\n" + sequence)
+    src = (REF / "set/hash.rs").read_text()
+    m = re.search(r'static FILE: &\[u8\] = b"([^"]*)"', src)
+    fasta = m.group(1).encode().decode("unicode_escape")
+    assert fasta.startswith(">1\n")
+    out["hash_set"] = [
+        {
+            "source": "src/set/hash.rs:189",
+            "k": 11,
+            "seq": fasta.split("\n", 1)[1].replace("\n", ""),
+            "checks": ["canonical_kmers_present", "forward_kmers_present", "get(0)==false", "k()==11"],
+        }
+    ]
+
     n = len(out["correctors"])
     per = {}
     for t in out["correctors"]:

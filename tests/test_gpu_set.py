@@ -294,3 +294,39 @@ def test_k19_counting_and_correction_without_the_dense_oracle(gpu):
                                np.concatenate(truth), roff)
     assert np.array_equal(same, np.concatenate(truth))  # error-free reads are left alone by every method
     g.free()
+
+
+@pytest.mark.parametrize("k", [13, 15, 17])
+def test_set_built_from_a_stream_of_chunks_equals_the_one_shot_set(gpu, oracle, k):
+    """brgpu_set_from_kmers (k >= 15: one partition per chunk, counted together) and the accumulating
+    counter (k < 15): spectrum, threshold and bitfield equal those of one call over all the reads, for
+    an explicit abundance and for first-minimum, with uneven chunks incl. one of a single short read."""
+    br, ctx = gpu
+    from br_b200 import synth
+
+    genome = synth.make_genome(120_000, seed=21)
+    seq, off, _ = synth.make_reads(genome, 18, 0.08, seed=22, mean_len=2500)
+    seq = np.concatenate([seq, np.frombuffer(b"ACGTA", dtype=np.uint8)])
+    off = np.concatenate([off, [off[-1] + 5]]).astype(np.uint64)
+    n = off.size - 1
+    cuts = [0, n // 7, n // 7 + 1, n // 2, n - 1, n]
+    chunks = [(seq, off[a : b + 1]) for a, b in zip(cuts[:-1], cuts[1:])]
+    oc = oracle.Counter(k)
+    oc.count(seq, off, threads=8)
+    ohist = oc.spectrum(threads=8)
+    for kwargs in ({"abundance": 2}, {"abundance_selection": "first-minimum"}):
+        whole = br.Pcon.from_reads(ctx, (seq, off), k, **kwargs)
+        streamed = br.Pcon.from_chunks(ctx, chunks, k, **kwargs)
+        assert streamed.abundance == whole.abundance
+        if k >= 15:
+            assert np.array_equal(streamed.spectrum(), ohist)
+        a = streamed.bitfield()
+        assert np.array_equal(a, whole.bitfield())
+        assert np.array_equal(a, oc.to_solid(whole.abundance, threads=8).bits())
+        # the streamed set corrects like the one-shot one (its summary / compacted copy came from the multi-source kernel)
+        sub = off[:60]
+        g1, o1 = br.correct_batch(br.build_methods(["one", "two"], streamed, 4, 7), seq, sub)
+        g2, o2 = br.correct_batch(br.build_methods(["one", "two"], whole, 4, 7), seq, sub)
+        assert np.array_equal(o1, o2) and np.array_equal(g1, g2)
+        whole.free()
+        streamed.free()

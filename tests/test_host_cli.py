@@ -259,3 +259,62 @@ def test_fasta_percent_least_through_the_cli(tmp_path, oracle, fixture_reads):
     thr = oracle.Counter.spectrum_threshold(c.spectrum(8), "percent-least", 0.3)
     payload = gzip.open(solid_out).read()
     assert np.array_equal(np.frombuffer(payload[1:], dtype=np.uint8), c.to_solid(thr, 8).bits())
+
+
+@pytest.mark.gpu
+def test_large_kmer_subcommand_like_tests_br_rs(tmp_path, oracle, fixture_reads):
+    """tests/br.rs:61-87 (`large-kmer -i FILE -f fasta -k 31`): set::Hash of every canonical 31-mer of
+    the file (the reference's raw.k31.fasta is not shipped, so the reads themselves serve as the k-mer
+    source), default method chain; also k = 21 with a tiny --chunk-bases so that the hash set is filled
+    chunk by chunk and grows.  The corrected records must equal the oracle's."""
+    seq, off = fixture_reads
+    names, _, _ = records(GOLDEN / "br_reads.fa.gz")
+    for k, extra in ((31, []), (21, ["--chunk-bases", "300000"])):
+        out = tmp_path / f"corr{k}.fasta"
+        r = run(["-i", GOLDEN / "br_reads.fa.gz", "-o", out, "-t", "4", *extra, "large-kmer", "-i", GOLDEN / "br_reads.fa.gz",
+                 "-f", "fasta", "-k", str(k)])
+        assert r.returncode == 0 and r.stderr == b"", r.stderr
+        oh = oracle.Hash.from_reads(k, seq, off)
+        ids = [oracle.METHOD_IDS[m] for m in ("one", "two", "graph", "greedy", "gap_size")]
+        exp, exp_off = oh.run_correction(ids, seq, off, confirm=5, max_search=7, threads=8)
+        assert_same_records(out, names, exp, exp_off)
+    r = run(["-i", GOLDEN / "br_reads.fa.gz", "-o", tmp_path / "o.fa", "large-kmer", "-i", GOLDEN / "br_reads.fa.gz", "-f",
+             "fasta", "-k", "33"])
+    assert r.returncode == 1 and b"3..=31" in r.stderr
+
+
+@pytest.mark.gpu
+def test_fasta_subcommand_streams_its_input_in_chunks(tmp_path, oracle, fixture_reads, fixture_solid_payload):
+    """count_fasta(inputs, 8192) reads the records chunk by chunk (src/main.rs:74).  The CLI streams too:
+    with --chunk-bases 200000 the 2.5 Mbase fixture becomes 13 partitions (k = 15: the bucketed path;
+    k = 11: the counter accumulates), two input files are chained, and the set equals the one-shot one."""
+    seq, off = fixture_reads
+    half = tmp_path / "half.fa"
+    data = gzip.open(GOLDEN / "br_reads.fa.gz").read()
+    cut = data.find(b"\n>", len(data) // 2) + 1
+    half.write_bytes(data[:cut])
+    rest = tmp_path / "rest.fa"
+    rest.write_bytes(data[cut:])
+    for k in (11, 15):
+        solid_out = tmp_path / f"set{k}.solid"
+        r = run(["-i", GOLDEN / "br_reads.fa.gz", "-o", tmp_path / "o.fa", "-c", "one", "--write-solid", solid_out,
+                 "--chunk-bases", "200000", "fasta", "-i", half, rest, "-k", str(k), "-a", "2"])
+        assert r.returncode == 0 and r.stderr == b"", r.stderr
+        payload = gzip.open(solid_out).read()
+        if k == 11:
+            assert payload == fixture_solid_payload
+        else:
+            c = oracle.Counter(k)
+            c.count(seq, off, threads=8)
+            assert payload[0] == k and np.array_equal(np.frombuffer(payload[1:], dtype=np.uint8), c.to_solid(2, 8).bits())
+    # first-minimum over chunks: the spectrum pass runs over all partitions
+    out = tmp_path / "fm.fa"
+    r = run(["-i", GOLDEN / "br_reads.fa.gz", "-o", out, "-c", "one", "--chunk-bases", "500000", "fasta", "-i",
+             GOLDEN / "br_reads.fa.gz", "-k", "15", "first-minimum"])
+    assert r.returncode == 0 and r.stderr == b"", r.stderr
+    c = oracle.Counter(15)
+    c.count(seq, off, threads=8)
+    solid = c.to_solid(oracle.Counter.first_minimum(c.spectrum(8)), 8)
+    exp, exp_off = solid.run_correction([oracle.METHOD_IDS["one"]], seq, off, confirm=5, threads=8)
+    names, _, _ = records(GOLDEN / "br_reads.fa.gz")
+    assert_same_records(out, names, exp, exp_off)

@@ -82,6 +82,43 @@ def test_set_kats(oracle, kats):
     assert s.k == 11  # pcon.rs:244-254
 
 
+def test_hash_set_kats(oracle, kats):
+    """src/set/hash.rs:185-242: canonical / forward / absence / k through Hash::from_fasta."""
+    t = kats["hash_set"][0]
+    k, seq = t["k"], t["seq"].encode()
+    h = oracle.Hash.from_reads(k, np.frombuffer(seq, dtype=np.uint8), np.array([0, len(seq)], dtype=np.uint64))
+    fwd = [oracle.seq2bit(seq[i : i + k]) for i in range(len(seq) - k + 1)]
+    assert all(h.get(oracle.canonical(km, k)) for km in fwd)  # hash.rs:192-205
+    assert all(h.get(km) for km in fwd)  # hash.rs:207-219
+    assert not h.get(0)  # hash.rs:221-230
+    assert h.k == 11  # hash.rs:232-241
+    assert len(h) == len({oracle.canonical(km, k) for km in fwd})
+
+
+def test_hash_set_answers_like_the_dense_set(oracle, fixture_reads):
+    """set::Hash and set::Pcon are two containers for the same membership function (odd k): built from
+    the same reads they answer every get alike, so every corrector does the same on either."""
+    seq, off = fixture_reads
+    k = 11
+    sub = off[:31]
+    c = oracle.Counter(k)
+    c.count(seq, sub, threads=4)
+    dense = c.to_solid(0, threads=4)  # presence: count > 0
+    h = oracle.Hash.from_reads(k, seq, sub)
+    rng = np.random.default_rng(1)
+    km = rng.integers(0, 1 << (2 * k), size=20000, dtype=np.uint64)
+    assert np.array_equal(dense.get_batch(km), h.get_batch(km))
+    ids = [oracle.ONE, oracle.TWO, oracle.GRAPH, oracle.GREEDY, oracle.GAP_SIZE]
+    a, ao = dense.run_correction(ids, seq, off[40:61], confirm=3, threads=4)
+    b, bo = h.run_correction(ids, seq, off[40:61], confirm=3, threads=4)
+    assert np.array_equal(ao, bo) and np.array_equal(a, b)
+    # short records are skipped (src/set/hash.rs:52), even k works (large-kmer takes k as given)
+    tiny = oracle.Hash.from_reads(21, np.frombuffer(b"ACGT" * 5, dtype=np.uint8), np.array([0, 20], dtype=np.uint64))
+    assert len(tiny) == 0
+    even = oracle.Hash.from_reads(20, np.frombuffer(b"ACGTTGCAAGGCTTAACCGGTTACA", dtype=np.uint8), np.array([0, 25], dtype=np.uint64))
+    assert len(even) > 0 and even.get(oracle.seq2bit(b"ACGTTGCAAGGCTTAACCGG"))
+
+
 def test_kmer_primitives(oracle):
     assert [oracle.lib().bro_nuc2bit(c) for c in b"ACTGactgN"] == [0, 1, 2, 3, 0, 1, 2, 3, 3]
     assert bytes(oracle.lib().bro_bit2nuc(i) for i in range(4)) == b"ACTG"
