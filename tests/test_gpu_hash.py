@@ -78,7 +78,7 @@ def test_hash_membership_matches_the_oracle(gpu, oracle, k):
                              km ^ np.uint64(1), (km >> np.uint64(2)) | (np.uint64(3) << np.uint64(2 * k - 2)),
                              rng.integers(0, mask, size=2000, dtype=np.uint64), np.array([0, mask], dtype=np.uint64)])
     exp = oh.get_batch(probes)
-    assert 0.2 < exp.mean() < 0.9
+    assert exp[: km.size].all() and not exp[-2000:].all()  # the k-mers of the reads are in (even k: not always their reverse complements)
     assert np.array_equal(gh.get_batch(probes), exp)
     assert np.array_equal(g2.get_batch(probes), exp)
     for h in (gh, g2, r1, r2):
