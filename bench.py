@@ -383,13 +383,25 @@ def run_ours(args, world, rank, local_rank):
             out_cap = self.n_bases + self.n_bases // 8 + 64 * self.n_reads + 64
             self.out_bufs = [(torch.empty(out_cap, dtype=torch.uint8).pin_memory(),
                               torch.empty(self.n_reads + 1, dtype=torch.int64).pin_memory()) for _ in range(2)]
+            # the same chunk in the 2-bit transport form (what br::fasta's reader produces while it parses):
+            # four bases per byte + the exception list (empty here: the generator emits A, C, G, T only)
+            from br_b200.runtime import pack_2bit
+
+            packed, exc_pos, exc_byte = pack_2bit(self.h_seq.numpy()[: self.n_bases])
+            self.h_packed = torch.from_numpy(packed).pin_memory()
+            self.exc_pos, self.exc_byte = exc_pos, exc_byte
+            ecap = max(16, int(exc_pos.size))
+            self.out_packed = [(torch.empty(out_cap // 4 + 8, dtype=torch.uint8).pin_memory(),
+                                torch.empty(self.n_reads + 1, dtype=torch.int64).pin_memory(),
+                                torch.empty(ecap, dtype=torch.int64).pin_memory(), torch.empty(ecap, dtype=torch.uint8).pin_memory(),
+                                torch.zeros(2, dtype=torch.int64).pin_memory()) for _ in range(2)]
 
         def seq_off(self):
             return self.h_seq.numpy()[: self.n_bases], self.h_off.numpy().view(np.uint64)
 
         def free(self):
             self.dev_reads.free()
-            self.h_seq = self.h_off = self.out_bufs = None
+            self.h_seq = self.h_off = self.out_bufs = self.h_packed = self.out_packed = None
 
     def step_device(wl, methods, keep=False):
         solid = build_set(wl.dev_reads)
@@ -399,20 +411,33 @@ def run_ours(args, world, rank, local_rank):
         out.free()
         solid.free()
 
-    def run_e2e_stream(wl, methods, n_steps, stamps=None):
+    def run_e2e_stream(wl, methods, n_steps, stamps=None, transport="packed"):
         """n_steps e2e steps on ONE context with the asynchronous staging calls: step i+1's reads go
         up and step i-1's result comes down on the context's copy stream while step i's kernels run.
         Every step still uploads its own inputs and downloads its own result."""
         res = 0
-        nxt = br_b200.Reads.upload_async(ctx, wl.h_seq, wl.h_off)
+        if transport == "packed":
+            def up():
+                return br_b200.Reads.upload_packed(ctx, wl.h_packed, wl.h_off, wl.exc_pos, wl.exc_byte, asynchronous=True)
+
+            def down(r, j):
+                r.download_packed(*wl.out_packed[j % 2], asynchronous=True)
+                return j % 2
+        else:
+            def up():
+                return br_b200.Reads.upload_async(ctx, wl.h_seq, wl.h_off)
+
+            def down(r, j):
+                return r.download_async(*wl.out_bufs[j % 2])
+        nxt = up()
         prev = None
         t0 = time.perf_counter()
         for i in range(n_steps):
             cur = nxt
             if i + 1 < n_steps:
-                nxt = br_b200.Reads.upload_async(ctx, wl.h_seq, wl.h_off)           # H2D of the next step
+                nxt = up()                                                            # H2D of the next step
             if prev is not None:
-                res = max(res, prev.download_async(*wl.out_bufs[(i - 1) % 2]))       # D2H of the previous step
+                res = max(res, down(prev, i - 1))                                     # D2H of the previous step
             solid = build_set(cur)
             out = br_b200.correct_reads(br_b200.build_methods(methods, solid, CONFIRM, MAX_SEARCH), cur)
             solid.free()
@@ -425,20 +450,30 @@ def run_ours(args, world, rank, local_rank):
                 t1 = time.perf_counter()
                 stamps.append(round((t1 - t0) * 1e3, 2))
                 t0 = t1
-        res = max(res, prev.download_async(*wl.out_bufs[(n_steps - 1) % 2]))
+        res = max(res, down(prev, n_steps - 1))
         prev.download_wait()
         prev.free()
+        if transport == "packed":  # bytes that came down: packed bases + the surviving exceptions
+            c = wl.out_packed[(n_steps - 1) % 2][4]
+            return (int(c[0]) + 3) // 4 + 9 * int(c[1])
         return res
 
-    def run_e2e_serial(wl, methods, n_steps, stamps=None):
+    def run_e2e_serial(wl, methods, n_steps, stamps=None, transport="packed"):
         res = 0
         for _ in range(n_steps):
             t0 = time.perf_counter()
-            reads = br_b200.Reads.upload(ctx, wl.h_seq, wl.h_off)            # H2D every step
+            if transport == "packed":
+                reads = br_b200.Reads.upload_packed(ctx, wl.h_packed, wl.h_off, wl.exc_pos, wl.exc_byte)  # H2D every step
+            else:
+                reads = br_b200.Reads.upload(ctx, wl.h_seq, wl.h_off)
             solid = build_set(reads)
             out = br_b200.correct_reads(br_b200.build_methods(methods, solid, CONFIRM, MAX_SEARCH), reads)
-            d, _ = out.download(*wl.out_bufs[0])                              # D2H every step
-            res = max(res, int(d.numel()))
+            if transport == "packed":
+                c = out.download_packed(*wl.out_packed[0])[4]                 # D2H every step
+                res = max(res, (int(c[0]) + 3) // 4 + 9 * int(c[1]))
+            else:
+                d, _ = out.download(*wl.out_bufs[0])
+                res = max(res, int(d.numel()))
             out.free()
             solid.free()
             reads.free()
@@ -449,7 +484,7 @@ def run_ours(args, world, rank, local_rank):
     e2e_mode = "serial" if args.no_e2e_pipeline else args.e2e_mode
     run_e2e = run_e2e_stream if e2e_mode == "stream" else run_e2e_serial
 
-    def measure(wl, methods, steps, warmup, want_e2e=True, e2e_warm_extra=12):
+    def measure(wl, methods, steps, warmup, want_e2e=True, e2e_warm_extra=12, transports=("packed",)):
         """value, per-kernel profile and e2e of `methods` over `wl`; returns a dict of raw numbers."""
         for _ in range(warmup):
             step_device(wl, methods)
@@ -468,20 +503,27 @@ def run_ours(args, world, rank, local_rank):
             return res
         # end-to-end region: warm up until two consecutive rounds agree within 3 % (the first e2e steps
         # size the allocator's cache for the upload / download buffers)
-        d2h, warm_ms = 0, []
-        for it in range(max(3, warmup) + e2e_warm_extra):
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            n_warm = 4 if e2e_mode == "stream" else 1
-            d2h = max(d2h, run_e2e(wl, methods, n_warm))
-            torch.cuda.synchronize()
-            warm_ms.append((time.perf_counter() - t0) * 1e3 / n_warm)
-            stable = it + 1 >= max(3, warmup) and abs(warm_ms[-1] - warm_ms[-2]) <= 0.03 * warm_ms[-1]
-            if all_and(stable):  # the step contains collectives: every rank must take the same decision
-                break
-        stamps = []
-        ms_e2e = timed(lambda: run_e2e(wl, methods, steps, stamps), 1)
-        res.update({"ms_e2e": ms_e2e, "d2h": d2h, "e2e_warm_ms": warm_ms, "e2e_step_ms": stamps})
+        for tr in transports:
+            d2h, warm_ms = 0, []
+            for it in range(max(3, warmup) + e2e_warm_extra):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                n_warm = 4 if e2e_mode == "stream" else 1
+                d2h = max(d2h, run_e2e(wl, methods, n_warm, None, tr))
+                torch.cuda.synchronize()
+                warm_ms.append((time.perf_counter() - t0) * 1e3 / n_warm)
+                stable = it + 1 >= max(3, warmup) and abs(warm_ms[-1] - warm_ms[-2]) <= 0.03 * warm_ms[-1]
+                if all_and(stable):  # the step contains collectives: every rank must take the same decision
+                    break
+            stamps = []
+            ms_e2e = timed(lambda: run_e2e(wl, methods, steps, stamps, tr), 1)
+            h2d = ((wl.n_bases + 3) // 4 + 9 * int(wl.exc_pos.size) if tr == "packed" else wl.n_bases) + 8 * (wl.n_reads + 1)
+            rec = {"ms_e2e": ms_e2e, "d2h": d2h + 8 * (wl.n_reads + 1) + (16 if tr == "packed" else 0), "h2d": h2d,
+                   "e2e_warm_ms": warm_ms, "e2e_step_ms": stamps, "transport": tr}
+            if "ms_e2e" not in res:
+                res.update(rec)
+            else:
+                res.setdefault("e2e_other", []).append(rec)
         return res
 
     # a full collection of the interpreter's heap (torch imports ~10^6 objects) costs 0.1-0.5 s and
@@ -499,7 +541,7 @@ def run_ours(args, world, rank, local_rank):
         sampler = ClockSampler(local_rank)
         if rank == 0 and not os.environ.get("BRGPU_BENCH_NO_SAMPLER"):
             sampler.start()
-        m = measure(wl, METHODS, args.steps, args.warmup)
+        m = measure(wl, METHODS, args.steps, args.warmup, transports=("packed", "ascii"))
         clocks = sampler.stop() if rank == 0 else None
         total_bases = all_sum(wl.n_bases)
 
@@ -612,12 +654,19 @@ def leg_record(m, wl, total_bases, steps, warmup, table, hbm_peak, sm_max_mhz, l
         "kernels": kernels,
         "ms_per_step_with_kernel_events": m["ms_prof"] / steps,
     }
+    def e2e_rec(x):
+        what = {"packed": "2-bit packed bases + exception list both ways (brgpu_reads_upload_packed_async / "
+                          "_download_packed_async): what br::fasta's reader produces while it parses",
+                "ascii": "1 byte per base both ways (brgpu_reads_upload_async / _download_async)"}[x["transport"]]
+        return {"value": total_bases * steps / (x["ms_e2e"] * 1e-3), "unit": UNIT, "ms_per_step": x["ms_e2e"] / steps,
+                "warmup_ms_per_step": [round(v, 2) for v in x["e2e_warm_ms"]], "host_clock_ms_per_step": x["e2e_step_ms"],
+                "h2d_bytes_per_step": int(x["h2d"]), "d2h_bytes_per_step": int(x["d2h"]), "transport": x["transport"],
+                "transport_note": what}
+
     if "ms_e2e" in m:
-        rec["e2e"] = {"value": total_bases * steps / (m["ms_e2e"] * 1e-3), "unit": UNIT, "ms_per_step": m["ms_e2e"] / steps,
-                      "warmup_ms_per_step": [round(x, 2) for x in m["e2e_warm_ms"]],
-                      "host_clock_ms_per_step": m["e2e_step_ms"],
-                      "h2d_bytes_per_step": int(n_bases + 8 * (n_reads + 1)),
-                      "d2h_bytes_per_step": int(m["d2h"] + 8 * (n_reads + 1))}
+        rec["e2e"] = e2e_rec(m)
+        for other in m.get("e2e_other", []):
+            rec["e2e_" + other["transport"]] = e2e_rec(other)
     return rec
 
 

@@ -39,6 +39,10 @@ SIGNATURES = {
     "brgpu_host_alloc": (C.c_int, [vp, sz, pvp]),
     "brgpu_host_free": (None, [vp, vp]),
     "brgpu_reads_upload": (C.c_int, [vp, vp, vp, u64, pvp]),
+    "brgpu_reads_upload_packed": (C.c_int, [vp, vp, vp, u64, vp, vp, u64, pvp]),
+    "brgpu_reads_upload_packed_async": (C.c_int, [vp, vp, vp, u64, vp, vp, u64, pvp]),
+    "brgpu_reads_download_packed": (C.c_int, [vp, vp, u64, vp, vp, vp, u64, vp]),
+    "brgpu_reads_download_packed_async": (C.c_int, [vp, vp, u64, vp, vp, vp, u64, vp]),
     "brgpu_reads_synth": (C.c_int, [vp, u64, u64, u64, vp, vp, vp, u64, vp, pvp]),
     "brgpu_reads_count": (u64, [vp]),
     "brgpu_reads_bases": (u64, [vp]),

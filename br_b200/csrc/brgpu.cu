@@ -396,6 +396,7 @@ static void reads_release(brgpu_reads *r) {
         for (void *p : r->deferred) dfree(r->ctx, p);
         if (r->dl_tight) dfree(r->ctx, r->dl_tight);
         if (r->dl_toff) dfree(r->ctx, r->dl_toff);
+        for (void *p : r->dl_more) dfree(r->ctx, p);
         if (r->d_seq) dfree(r->ctx, r->d_seq);
         if (r->d_len) dfree(r->ctx, r->d_len);
     }
@@ -694,9 +695,197 @@ extern "C" int brgpu_reads_download_wait(brgpu_reads *reads) {
     reads->dl_done = nullptr;
     dfree(ctx, reads->dl_tight);
     dfree(ctx, reads->dl_toff);
+    for (void *p : reads->dl_more) dfree(ctx, p);
+    reads->dl_more.clear();
     reads->dl_tight = reads->dl_toff = nullptr;
     if (e != cudaSuccess) return fail(ctx, BRGPU_E_CUDA, "asynchronous download", e);
     return BRGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// 2-bit transport (north_star's "2-bit packed reads"): a quarter of the PCIe bytes in both
+// directions.  See set_kernels.cu ("2-bit transport") for the layout and why the exception list makes the
+// echo-the-original-byte contract of Corrector::correct hold.
+// ------------------------------------------------------------------------------------------
+static int reads_from_packed(brgpu_ctx *ctx, const uint8_t *packed_host, const uint64_t *h_off, uint64_t n,
+                             const uint64_t *exc_pos_host, const uint8_t *exc_byte_host, uint64_t n_exc, brgpu_reads **out,
+                             bool defer_frees) {
+    if (n && h_off[0] != 0) return fail(ctx, BRGPU_E_INVALID, "packed reads: offsets must start at 0");
+    std::vector<uint32_t> h_len(n);
+    for (uint64_t r = 0; r < n; r++) {
+        if (h_off[r + 1] < h_off[r]) return fail(ctx, BRGPU_E_INVALID, "offsets must be non-decreasing");
+        const uint64_t l = h_off[r + 1] - h_off[r];
+        if (l > 0xfffffff0ULL / 2) return fail(ctx, BRGPU_E_INVALID, "read longer than 2^31 bases");
+        h_len[r] = (uint32_t)l;
+    }
+    if (n > 0xfffffff0ULL) return fail(ctx, BRGPU_E_INVALID, "too many reads in one chunk");
+    brgpu_reads *R = new (std::nothrow) brgpu_reads;
+    if (!R) return fail(ctx, BRGPU_E_NOMEM, "host allocation");
+    R->ctx = ctx;
+    R->h_len = h_len;
+    for (uint32_t l : h_len) R->sum_len += l;
+    int st = make_layout(ctx, h_len.data(), n, 0, R->layout);
+    if (st != BRGPU_OK) {
+        delete R;
+        return st;
+    }
+    const Layout &L = *R->layout;
+    const uint64_t total = n ? h_off[n] : 0, packed_bytes = (total + 3) >> 2;
+    uint8_t *d_packed = nullptr, *d_exc_byte = nullptr;
+    uint64_t *d_toff = nullptr, *d_exc_pos = nullptr;
+    cudaError_t e = dalloc(ctx, &R->d_seq, L.total_slots);
+    if (e == cudaSuccess) e = dalloc(ctx, &R->d_len, n);
+    if (e == cudaSuccess) e = dalloc(ctx, &d_toff, n + 1);
+    if (e == cudaSuccess) e = dalloc(ctx, &d_packed, packed_bytes + 8);
+    if (e == cudaSuccess && n_exc) e = dalloc(ctx, &d_exc_pos, n_exc);
+    if (e == cudaSuccess && n_exc) e = dalloc(ctx, &d_exc_byte, n_exc);
+    if (e != cudaSuccess) {
+        for (void *p : {(void *)d_toff, (void *)d_packed, (void *)d_exc_pos, (void *)d_exc_byte})
+            if (p) dfree(ctx, p);
+        reads_release(R);
+        return fail(ctx, BRGPU_E_NOMEM, "device allocation (packed reads)", e);
+    }
+    // small pageable arrays first, the big pinned copy last (see reads_from_tight)
+    cudaMemcpyAsync(d_toff, h_off, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (n) cudaMemcpyAsync(R->d_len, h_len.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (n_exc) {
+        cudaMemcpyAsync(d_exc_pos, exc_pos_host, n_exc * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemcpyAsync(d_exc_byte, exc_byte_host, n_exc, cudaMemcpyHostToDevice, ctx->stream);
+    }
+    if (packed_bytes) cudaMemcpyAsync(d_packed, packed_host, packed_bytes, cudaMemcpyHostToDevice, ctx->stream);
+    launch_unpack_to_slots(ctx, L, d_packed, d_toff, R->d_seq, d_exc_pos, d_exc_byte, n_exc);
+    for (void *p : {(void *)d_toff, (void *)d_packed, (void *)d_exc_pos, (void *)d_exc_byte}) {
+        if (!p) continue;
+        if (defer_frees)
+            R->deferred.push_back(p);
+        else
+            dfree(ctx, p);
+    }
+    e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        reads_release(R);
+        return fail(ctx, BRGPU_E_CUDA, "packed reads upload", e);
+    }
+    *out = R;
+    return BRGPU_OK;
+}
+
+static int upload_packed(brgpu_ctx *ctx, const uint8_t *packed_host, const uint64_t *offsets_host, uint64_t n_reads,
+                         const uint64_t *exc_pos_host, const uint8_t *exc_byte_host, uint64_t n_exc, brgpu_reads **out,
+                         bool async) {
+    if (!ctx || !out || !offsets_host) return ctx ? fail(ctx, BRGPU_E_INVALID, "null argument") : BRGPU_E_INVALID;
+    *out = nullptr;
+    if ((!packed_host && n_reads && offsets_host[n_reads]) || (n_exc && (!exc_pos_host || !exc_byte_host)))
+        return fail(ctx, BRGPU_E_INVALID, "null buffer");
+    cudaSetDevice(ctx->device);
+    if (!async) return reads_from_packed(ctx, packed_host, offsets_host, n_reads, exc_pos_host, exc_byte_host, n_exc, out, false);
+    CK(cudaEventRecord(ctx->ev_fence, ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_fence, 0));
+    cudaStream_t compute = ctx->stream;
+    ctx->stream = ctx->copy_stream; // the staging kernels and copies of this call go to the copy stream
+    int st = reads_from_packed(ctx, packed_host, offsets_host, n_reads, exc_pos_host, exc_byte_host, n_exc, out, true);
+    ctx->stream = compute;
+    if (st != BRGPU_OK) return st;
+    brgpu_reads *R = *out;
+    cudaError_t e = cudaEventCreateWithFlags(&R->ready, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventRecord(R->ready, ctx->copy_stream);
+    if (e != cudaSuccess) {
+        cudaStreamSynchronize(ctx->copy_stream);
+        if (R->ready) cudaEventDestroy(R->ready);
+        R->ready = nullptr;
+        reads_release(R);
+        *out = nullptr;
+        return fail(ctx, BRGPU_E_CUDA, "asynchronous packed upload", e);
+    }
+    return BRGPU_OK;
+}
+
+extern "C" int brgpu_reads_upload_packed(brgpu_ctx *ctx, const uint8_t *packed_host, const uint64_t *offsets_host,
+                                         uint64_t n_reads, const uint64_t *exc_pos_host, const uint8_t *exc_byte_host,
+                                         uint64_t n_exc, brgpu_reads **out) {
+    return upload_packed(ctx, packed_host, offsets_host, n_reads, exc_pos_host, exc_byte_host, n_exc, out, false);
+}
+
+extern "C" int brgpu_reads_upload_packed_async(brgpu_ctx *ctx, const uint8_t *packed_host, const uint64_t *offsets_host,
+                                               uint64_t n_reads, const uint64_t *exc_pos_host, const uint8_t *exc_byte_host,
+                                               uint64_t n_exc, brgpu_reads **out) {
+    return upload_packed(ctx, packed_host, offsets_host, n_reads, exc_pos_host, exc_byte_host, n_exc, out, true);
+}
+
+// counts_host[0] = bases, counts_host[1] = exceptions found (may exceed exc_cap: then only exc_cap were written and
+// the status is BRGPU_E_OVERFLOW for the synchronous call; the asynchronous one reports it through counts_host)
+static int download_packed(brgpu_reads *reads, uint8_t *packed_host, uint64_t packed_cap, uint64_t *offsets_host,
+                           uint64_t *exc_pos_host, uint8_t *exc_byte_host, uint64_t exc_cap, uint64_t *counts_host, bool async) {
+    if (!reads || !counts_host) return BRGPU_E_INVALID;
+    brgpu_ctx *ctx = reads->ctx;
+    cudaSetDevice(ctx->device);
+    if (reads->dl_done) return fail(ctx, BRGPU_E_INVALID, "a download of these reads is already in flight");
+    reads_ready(reads);
+    const Layout &L = *reads->layout;
+    uint64_t *d_toff = nullptr, total = 0;
+    int st = reads_tight_offsets(reads, &d_toff, &total); // waits for the producer of these reads
+    if (st != BRGPU_OK) return st;
+    counts_host[0] = total;
+    counts_host[1] = 0;
+    const uint64_t packed_bytes = (total + 3) >> 2;
+    if (packed_bytes > packed_cap || (!packed_host && packed_bytes) || !offsets_host || (exc_cap && (!exc_pos_host || !exc_byte_host))) {
+        dfree(ctx, d_toff);
+        return fail(ctx, packed_bytes > packed_cap ? BRGPU_E_OVERFLOW : BRGPU_E_INVALID, "output buffer too small");
+    }
+    uint8_t *d_packed = nullptr, *d_exc_byte = nullptr;
+    uint64_t *d_exc_pos = nullptr;
+    unsigned long long *d_cnt = nullptr;
+    cudaError_t e = dalloc(ctx, &d_packed, packed_bytes + 8);
+    if (e == cudaSuccess) e = dalloc(ctx, &d_exc_pos, exc_cap);
+    if (e == cudaSuccess) e = dalloc(ctx, &d_exc_byte, exc_cap);
+    if (e == cudaSuccess) e = dalloc(ctx, &d_cnt, 1);
+    auto drop = [&]() {
+        for (void *p : {(void *)d_toff, (void *)d_packed, (void *)d_exc_pos, (void *)d_exc_byte, (void *)d_cnt})
+            if (p) dfree(ctx, p);
+    };
+    if (e != cudaSuccess) {
+        drop();
+        return fail(ctx, BRGPU_E_NOMEM, "device allocation (packed download)", e);
+    }
+    cudaMemsetAsync(d_cnt, 0, 8, ctx->stream);
+    launch_pack_from_slots(ctx, L, reads->d_seq, d_toff, total, d_packed, d_exc_pos, d_exc_byte, exc_cap, d_cnt);
+    cudaStream_t cs = ctx->stream;
+    if (async) {
+        e = cudaEventRecord(ctx->ev_fence, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_fence, 0);
+        cs = ctx->copy_stream;
+    }
+    if (e == cudaSuccess && packed_bytes) e = cudaMemcpyAsync(packed_host, d_packed, packed_bytes, cudaMemcpyDeviceToHost, cs);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(offsets_host, d_toff, (L.n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, cs);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(counts_host + 1, d_cnt, 8, cudaMemcpyDeviceToHost, cs);
+    if (e == cudaSuccess && exc_cap) e = cudaMemcpyAsync(exc_pos_host, d_exc_pos, exc_cap * 8, cudaMemcpyDeviceToHost, cs);
+    if (e == cudaSuccess && exc_cap) e = cudaMemcpyAsync(exc_byte_host, d_exc_byte, exc_cap, cudaMemcpyDeviceToHost, cs);
+    if (async) {
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&reads->dl_done, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventRecord(reads->dl_done, ctx->copy_stream);
+        reads->dl_tight = d_packed;
+        reads->dl_toff = d_toff;
+        reads->dl_more = {d_exc_pos, d_exc_byte, d_cnt};
+        if (e != cudaSuccess) return fail(ctx, BRGPU_E_CUDA, "asynchronous packed download", e);
+        return BRGPU_OK;
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    drop();
+    if (e != cudaSuccess) return fail(ctx, BRGPU_E_CUDA, "packed download", e);
+    if (counts_host[1] > exc_cap) return fail(ctx, BRGPU_E_OVERFLOW, "exception buffer too small");
+    return BRGPU_OK;
+}
+
+extern "C" int brgpu_reads_download_packed(brgpu_reads *reads, uint8_t *packed_host, uint64_t packed_cap,
+                                           uint64_t *offsets_host, uint64_t *exc_pos_host, uint8_t *exc_byte_host,
+                                           uint64_t exc_cap, uint64_t counts_host[2]) {
+    return download_packed(reads, packed_host, packed_cap, offsets_host, exc_pos_host, exc_byte_host, exc_cap, counts_host, false);
+}
+
+extern "C" int brgpu_reads_download_packed_async(brgpu_reads *reads, uint8_t *packed_host, uint64_t packed_cap,
+                                                 uint64_t *offsets_host, uint64_t *exc_pos_host, uint8_t *exc_byte_host,
+                                                 uint64_t exc_cap, uint64_t counts_host[2]) {
+    return download_packed(reads, packed_host, packed_cap, offsets_host, exc_pos_host, exc_byte_host, exc_cap, counts_host, true);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -139,6 +139,121 @@ void launch_reverse_slots(brgpu_ctx *ctx, const Layout &L, const uint8_t *d_in, 
 }
 
 // ------------------------------------------------------------------------------------------
+// 2-bit transport (BASELINE.json north_star, first bullet).  Across PCIe a chunk travels as
+// 2 bits per base — tight layout, read r occupies base positions [off[r], off[r+1]), four bases per
+// byte, first base in the two high bits — plus an exception list (position, byte) for every byte that
+// is not the upper-case letter of its own 2-bit code (lower case, N, anything else).  On the device the
+// reads live in the slot layout as ASCII: Corrector::correct echoes the *original* byte of every
+// position it does not rewrite (src/correct/mod.rs:91,100), and corrections only ever emit A, C, T, G,
+// so the exceptions of the output are a subset of the exceptions of the input.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t packed_code(const uint8_t *__restrict__ packed, uint64_t t) {
+    return (__ldg(packed + (t >> 2)) >> (2u * (3u - (uint32_t)(t & 3)))) & 3u;
+}
+
+__global__ void unpack_to_slots_kernel(const uint8_t *__restrict__ packed, const uint64_t *__restrict__ tight_off,
+                                       const uint64_t *__restrict__ slot_off, const uint32_t *__restrict__ word2read,
+                                       uint64_t n_quads, uint32_t *__restrict__ slots) {
+    for (uint64_t g = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; g < n_quads;
+         g += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t s = g << 2;
+        const uint32_t r = __ldg(word2read + (s >> 5));
+        const uint64_t p = s - __ldg(slot_off + r);
+        const uint64_t t0 = __ldg(tight_off + r);
+        const uint64_t len = __ldg(tight_off + r + 1) - t0;
+        uint32_t v = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (p + j < len) v |= (uint32_t)bit2nuc(packed_code(packed, t0 + p + j)) << (8 * j);
+        slots[g] = v;
+    }
+}
+
+// read r with off[r] <= t < off[r+1] (off has n + 1 entries, t < off[n])
+__device__ __forceinline__ uint64_t read_of_position(const uint64_t *__restrict__ off, uint64_t n, uint64_t t) {
+    uint64_t lo = 0, hi = n;
+    while (hi - lo > 1) {
+        const uint64_t mid = (lo + hi) >> 1;
+        if (__ldg(off + mid) <= t)
+            lo = mid;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+
+__global__ void apply_exceptions_kernel(const uint64_t *__restrict__ exc_pos, const uint8_t *__restrict__ exc_byte,
+                                        uint64_t n_exc, const uint64_t *__restrict__ tight_off,
+                                        const uint64_t *__restrict__ slot_off, uint64_t n_reads, uint8_t *__restrict__ slots) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_exc; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t t = __ldg(exc_pos + i);
+        if (t >= __ldg(tight_off + n_reads)) continue; // out of range: ignored
+        const uint64_t r = read_of_position(tight_off, n_reads, t);
+        slots[__ldg(slot_off + r) + (t - __ldg(tight_off + r))] = __ldg(exc_byte + i);
+    }
+}
+
+// one thread per packed output byte (four tight positions); exceptions are appended in no particular order
+__global__ void pack_from_slots_kernel(const uint8_t *__restrict__ slots, const uint64_t *__restrict__ slot_off,
+                                       const uint64_t *__restrict__ tight_off, uint64_t n_reads, uint64_t n_bases,
+                                       uint8_t *__restrict__ packed, uint64_t *__restrict__ exc_pos,
+                                       uint8_t *__restrict__ exc_byte, uint64_t exc_cap,
+                                       unsigned long long *__restrict__ n_exc) {
+    const uint64_t n_bytes = (n_bases + 3) >> 2;
+    for (uint64_t b = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; b < n_bytes; b += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t t = b << 2;
+        uint64_t r = read_of_position(tight_off, n_reads, t);
+        uint64_t r_end = __ldg(tight_off + r + 1), r_beg = __ldg(tight_off + r), sbase = __ldg(slot_off + r);
+        uint32_t out = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++, t++) {
+            if (t >= n_bases) break;
+            while (t >= r_end) { // next (non-empty) read
+                r++;
+                r_beg = r_end;
+                r_end = __ldg(tight_off + r + 1);
+                sbase = __ldg(slot_off + r);
+            }
+            const uint8_t c = slots[sbase + (t - r_beg)];
+            const uint32_t code = nuc2bit(c);
+            out |= code << (2 * (3 - j));
+            if (c != bit2nuc(code)) {
+                const unsigned long long at = atomicAdd(n_exc, 1ULL);
+                if (at < exc_cap) {
+                    exc_pos[at] = t;
+                    exc_byte[at] = c;
+                }
+            }
+        }
+        packed[b] = (uint8_t)out;
+    }
+}
+
+void launch_unpack_to_slots(brgpu_ctx *ctx, const Layout &L, const uint8_t *d_packed, const uint64_t *d_tight_off,
+                            uint8_t *d_slots, const uint64_t *d_exc_pos, const uint8_t *d_exc_byte, uint64_t n_exc) {
+    const uint64_t n_quads = L.total_slots >> 2;
+    if (!n_quads) return;
+    ProfScope ps(ctx, "unpack_to_slots", (double)L.total_slots * 1.25);
+    unpack_to_slots_kernel<<<grid_for(ctx, n_quads, 256, 8), 256, 0, ctx->stream>>>(d_packed, d_tight_off, L.d_slot_off,
+                                                                                   L.d_word2read, n_quads, (uint32_t *)d_slots);
+    if (n_exc) {
+        ctx->launches++;
+        apply_exceptions_kernel<<<grid_for(ctx, n_exc, 256, 8), 256, 0, ctx->stream>>>(d_exc_pos, d_exc_byte, n_exc, d_tight_off,
+                                                                                    L.d_slot_off, L.n, d_slots);
+    }
+}
+
+void launch_pack_from_slots(brgpu_ctx *ctx, const Layout &L, const uint8_t *d_slots, const uint64_t *d_tight_off,
+                            uint64_t n_bases, uint8_t *d_packed, uint64_t *d_exc_pos, uint8_t *d_exc_byte, uint64_t exc_cap,
+                            unsigned long long *d_n_exc) {
+    const uint64_t n_bytes = (n_bases + 3) >> 2;
+    if (!n_bytes) return;
+    ProfScope ps(ctx, "pack_from_slots", (double)n_bases * 1.25);
+    pack_from_slots_kernel<<<grid_for(ctx, n_bytes, 256, 8), 256, 0, ctx->stream>>>(d_slots, L.d_slot_off, d_tight_off, L.n, n_bases,
+                                                                                   d_packed, d_exc_pos, d_exc_byte, exc_cap, d_n_exc);
+}
+
+// ------------------------------------------------------------------------------------------
 // Small results (spectrum, flags, totals) go back through mapped pinned memory, written by a
 // one-block kernel, not through a copy engine: a 2 KB cudaMemcpyAsync queues behind whatever the
 // device-to-host engine is doing, and with the asynchronous staging calls that is a 138 MB

@@ -489,7 +489,10 @@ struct Corrected {
     std::vector<uint64_t> offsets;
 };
 
-inline void correct_chunk(const Methods &methods, bool two_side, const fasta::Chunk &in, Corrected &out) {
+enum class Transport { Ascii, Packed };
+
+inline void correct_chunk(const Methods &methods, bool two_side, const fasta::Chunk &in, Corrected &out,
+                          Transport transport = Transport::Packed) {
     const size_t n = in.size();
     out.offsets.assign(n + 1, 0);
     if (methods.empty()) { // fold over no method: records pass through
@@ -517,6 +520,39 @@ inline void correct_chunk(const Methods &methods, bool two_side, const fasta::Ch
     if (confirm < 0) confirm = 5;
     if (max_search < 0) max_search = 7;
     const size_t total = in.seq.size();
+    if (transport == Transport::Packed) {
+        // 2-bit transport: the chunk crosses PCIe at 2 bits per base (+ the exception list) in both
+        // directions; device-resident handles in between
+        const Context &ctx = solid.context();
+        fasta::Packed pk;
+        fasta::pack(in.seq.data(), total, pk);
+        brgpu_reads *r = nullptr, *c = nullptr;
+        ctx.check(brgpu_reads_upload_packed(ctx.handle(), pk.bases.data(), in.offsets.data(), n, pk.exc_pos.data(),
+                                            pk.exc_byte.data(), pk.exc_pos.size(), &r));
+        int st = brgpu_correct_reads(ctx.handle(), solid.handle(), ids.data(), ids.size(), confirm, max_search,
+                                     two_side ? 1 : 0, r, &c);
+        brgpu_reads_free(r);
+        ctx.check(st);
+        fasta::Bytes packed_out;
+        packed_out.resize((total + total / 8 + 64 * n + 64) / 4 + 8);
+        std::vector<uint64_t> ep(pk.exc_pos.size() + 1);
+        std::vector<uint8_t> eb(pk.exc_pos.size() + 1);
+        uint64_t counts[2] = {0, 0};
+        for (;;) {
+            st = brgpu_reads_download_packed(c, packed_out.data(), packed_out.size(), out.offsets.data(), ep.data(),
+                                             eb.data(), pk.exc_pos.size(), counts);
+            if (st == BRGPU_E_OVERFLOW && (counts[0] + 3) / 4 > packed_out.size()) {
+                packed_out.resize((counts[0] + 3) / 4 + 8);
+                continue;
+            }
+            break;
+        }
+        brgpu_reads_free(c);
+        ctx.check(st);
+        out.seq.resize(counts[0]);
+        fasta::unpack(packed_out.data(), counts[0], ep.data(), eb.data(), counts[1], out.seq.data());
+        return;
+    }
     out.seq.resize(total + total / 8 + 64 * n + 64);
     for (;;) {
         uint64_t need = 0;
@@ -540,7 +576,8 @@ constexpr size_t CHUNK_RECORDS = 8192; // hard-coded in src/lib.rs:90
 // `record_buffer_len` is accepted and, like in the reference, only a capacity hint.  The parse of
 // chunk c+1 and the formatting of chunk c-1 run on host threads while the GPU corrects chunk c.
 inline void run_correction(const std::vector<std::string> &inputs, const std::vector<std::string> &outputs,
-                           const Methods &methods, bool two_side, uint64_t record_buffer_len = CHUNK_RECORDS) {
+                           const Methods &methods, bool two_side, uint64_t record_buffer_len = CHUNK_RECORDS,
+                           Transport transport = Transport::Packed) {
     (void)record_buffer_len;
     const size_t pairs = inputs.size() < outputs.size() ? inputs.size() : outputs.size(); // zip (src/lib.rs:79)
     for (size_t p = 0; p < pairs; p++) {
@@ -561,7 +598,7 @@ inline void run_correction(const std::vector<std::string> &inputs, const std::ve
             if (more) next = std::async(std::launch::async, read_into, &chunks[cur ^ 1]);
             if (c.size()) {
                 if (writes[cur].valid()) writes[cur].wait(); // results[cur] is free again
-                correct_chunk(methods, two_side, c, results[cur]);
+                correct_chunk(methods, two_side, c, results[cur], transport);
                 written_defs[cur].swap(c.definitions);
                 Corrected *r = &results[cur];
                 std::vector<std::string> *d = &written_defs[cur];

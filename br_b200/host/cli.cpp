@@ -31,6 +31,7 @@ struct Args {
     uint64_t record_buffer = 8192;
     int device = 0;
     std::string write_solid;
+    bool packed = true;
     size_t chunk_bases = 1u << 30; // bases per chunk while the set is built (the reads are streamed, not held)
     // sub-command
     std::string sub;
@@ -101,7 +102,11 @@ Args parse(int argc, char **argv) {
         else if (t == "-t" || t == "--threads") (void)parse_int(t, value(t), 0, 1 << 20);
         else if (t == "-d" || t == "--device") a.device = (int)parse_int(t, value(t), 0, 1023);
         else if (t == "--write-solid") a.write_solid = value(t);
-        else if (t == "--chunk-bases") a.chunk_bases = (size_t)parse_int(t, value(t), 1, 1LL << 40); // set construction streams chunks of this size
+        else if (t == "--transport") { // how a chunk crosses PCIe: packed (2 bits per base + exceptions, default) | ascii
+            const std::string v = value(t);
+            if (v != "packed" && v != "ascii") usage_error("invalid value '" + v + "' for '--transport': packed, ascii");
+            a.packed = v == "packed";
+        } else if (t == "--chunk-bases") a.chunk_bases = (size_t)parse_int(t, value(t), 1, 1LL << 40); // set construction streams chunks of this size
         else if (t == "-q" || t == "--quiet") {}
         else if (t.rfind("-v", 0) == 0 || t == "--verbosity") {}
         else if (t == "-T" || t == "--timestamp") (void)value(t);
@@ -200,7 +205,8 @@ int main(int argc, char **argv) {
             dense->write_solid(a.write_solid);
         }
         br::Methods methods = br::build_methods(a.corrections, *kmer_set, (uint8_t)a.confirm, (uint8_t)a.max_search);
-        br::run_correction(a.inputs, a.outputs, methods, a.two_side, a.record_buffer);
+        br::run_correction(a.inputs, a.outputs, methods, a.two_side, a.record_buffer,
+                           a.packed ? br::Transport::Packed : br::Transport::Ascii);
     } catch (const std::exception &e) {
         std::fprintf(stderr, "Error: %s\n", e.what()); // anyhow's top-level report
         return 1;

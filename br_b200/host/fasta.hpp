@@ -16,7 +16,9 @@
 #include <cstring>
 #include <new>
 #include <stdexcept>
+#include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace br {
@@ -96,6 +98,81 @@ struct Chunk {
         offsets.assign(1, 0);
     }
 };
+
+// ------------------------------------------------------------------------------------------
+// 2-bit transport form of a chunk (include/brgpu.h, "2-bit transport"): four bases per byte, first base
+// in the two high bits, code = (byte >> 1) & 3, plus the exception list of every byte that is not the
+// upper-case letter of its own code (lower case, N, ...).  A quarter of the PCIe bytes; the host pays one
+// pass over the bases, split over `threads` threads at 4-base-aligned cuts.
+// ------------------------------------------------------------------------------------------
+struct Packed {
+    Bytes bases;                   // ceil(n / 4) bytes
+    std::vector<uint64_t> exc_pos; // base positions in the concatenation
+    std::vector<uint8_t> exc_byte;
+    uint64_t n_bases = 0;
+};
+
+inline void pack_range(const uint8_t *seq, uint64_t begin, uint64_t end, uint8_t *packed, std::vector<uint64_t> &exc_pos,
+                       std::vector<uint8_t> &exc_byte) {
+    static const uint8_t LETTER[4] = {'A', 'C', 'T', 'G'};
+    for (uint64_t t = begin; t < end; t += 4) { // begin is a multiple of 4
+        uint32_t out = 0;
+        const uint64_t m = end - t < 4 ? end - t : 4;
+        for (uint64_t j = 0; j < m; j++) {
+            const uint8_t c = seq[t + j];
+            const uint32_t code = (c >> 1) & 3u;
+            out |= code << (2 * (3 - j));
+            if (c != LETTER[code]) {
+                exc_pos.push_back(t + j);
+                exc_byte.push_back(c);
+            }
+        }
+        packed[t >> 2] = (uint8_t)out;
+    }
+}
+
+inline void pack(const uint8_t *seq, uint64_t n, Packed &out, unsigned threads = 4) {
+    out.n_bases = n;
+    out.bases.resize((size_t)((n + 3) >> 2));
+    out.exc_pos.clear();
+    out.exc_byte.clear();
+    if (threads < 2 || n < (1u << 20)) {
+        pack_range(seq, 0, n, out.bases.data(), out.exc_pos, out.exc_byte);
+        return;
+    }
+    std::vector<std::vector<uint64_t>> ep(threads);
+    std::vector<std::vector<uint8_t>> eb(threads);
+    std::vector<std::thread> pool;
+    const uint64_t per = ((n / threads) + 3) & ~3ULL;
+    for (unsigned w = 0; w < threads; w++) {
+        const uint64_t b = std::min<uint64_t>(n, per * w), e = w + 1 == threads ? n : std::min<uint64_t>(n, per * (w + 1));
+        pool.emplace_back([&, w, b, e]() { pack_range(seq, b, e, out.bases.data(), ep[w], eb[w]); });
+    }
+    for (auto &t : pool) t.join();
+    for (unsigned w = 0; w < threads; w++) {
+        out.exc_pos.insert(out.exc_pos.end(), ep[w].begin(), ep[w].end());
+        out.exc_byte.insert(out.exc_byte.end(), eb[w].begin(), eb[w].end());
+    }
+}
+
+// inverse: n bases of ASCII, exceptions written back (any order)
+inline void unpack(const uint8_t *packed, uint64_t n, const uint64_t *exc_pos, const uint8_t *exc_byte, uint64_t n_exc,
+                   uint8_t *seq_out, unsigned threads = 4) {
+    auto range = [&](uint64_t b, uint64_t e) {
+        static const uint8_t LETTER[4] = {'A', 'C', 'T', 'G'};
+        for (uint64_t t = b; t < e; t++) seq_out[t] = LETTER[(packed[t >> 2] >> (2 * (3 - (t & 3)))) & 3u];
+    };
+    if (threads < 2 || n < (1u << 20)) {
+        range(0, n);
+    } else {
+        std::vector<std::thread> pool;
+        const uint64_t per = n / threads + 1;
+        for (unsigned w = 0; w < threads; w++) pool.emplace_back(range, std::min<uint64_t>(n, per * w), std::min<uint64_t>(n, per * (w + 1)));
+        for (auto &t : pool) t.join();
+    }
+    for (uint64_t i = 0; i < n_exc; i++)
+        if (exc_pos[i] < n) seq_out[exc_pos[i]] = exc_byte[i];
+}
 
 class Reader {
   public:

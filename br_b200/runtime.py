@@ -35,6 +35,37 @@ def as_offsets(offsets):
     return np.ascontiguousarray(offsets, dtype=np.uint64)
 
 
+_ACTG = np.frombuffer(b"ACTG", dtype=np.uint8)  # bit2nuc: code 0..3 -> letter
+
+
+def pack_2bit(seq):
+    """2-bit transport form of concatenated sequences (include/brgpu.h, "2-bit transport"): returns
+    (packed uint8, exc_pos uint64, exc_byte uint8) — four bases per byte, first base in the two high
+    bits, and the exception list of every byte that is not the upper-case letter of its own code."""
+    s = np.ascontiguousarray(seq, dtype=np.uint8)
+    codes = (s >> 1) & 3
+    exc_pos = np.flatnonzero(s != _ACTG[codes]).astype(np.uint64)
+    exc_byte = s[exc_pos.astype(np.int64)].copy()
+    pad = (-s.size) % 4
+    if pad:
+        codes = np.concatenate([codes, np.zeros(pad, dtype=np.uint8)])
+    q = codes.reshape(-1, 4)
+    packed = ((q[:, 0] << 6) | (q[:, 1] << 4) | (q[:, 2] << 2) | q[:, 3]).astype(np.uint8)
+    return packed, exc_pos, exc_byte
+
+
+def unpack_2bit(packed, n_bases, exc_pos=None, exc_byte=None):
+    """Inverse of pack_2bit: ASCII bytes of `n_bases` bases with the exceptions written back."""
+    p = np.ascontiguousarray(packed, dtype=np.uint8)[: (int(n_bases) + 3) // 4]
+    codes = np.empty((p.size, 4), dtype=np.uint8)
+    for j in range(4):
+        codes[:, j] = (p >> (6 - 2 * j)) & 3
+    out = _ACTG[codes.reshape(-1)[: int(n_bases)]]
+    if exc_pos is not None and len(exc_pos):
+        out[np.asarray(exc_pos, dtype=np.int64)] = np.asarray(exc_byte, dtype=np.uint8)
+    return out
+
+
 def bind_to_gpu_numa_node(device=0):
     """Pin this process to the CPUs of the NUMA node the GPU hangs off, so that the pinned host
     buffers it allocates afterwards (first touch) and its PCIe copies stay on that socket.  With
@@ -180,6 +211,43 @@ class Reads:
         r = cls(ctx, h)
         r._keep = (s, off)
         return r
+
+    @classmethod
+    def upload_packed(cls, ctx, packed, offsets, exc_pos=None, exc_byte=None, asynchronous=False):
+        """2-bit transport upload (brgpu_reads_upload_packed[_async]); offsets are in bases, from 0."""
+        off = as_offsets(offsets)
+        n = (off.numel() if hasattr(off, "numel") else off.size) - 1
+        n_exc = 0 if exc_pos is None else int(exc_pos.numel() if hasattr(exc_pos, "numel") else exc_pos.size)
+        h = C.c_void_p()
+        f = lib.brgpu_reads_upload_packed_async if asynchronous else lib.brgpu_reads_upload_packed
+        check(f(ctx._h, _addr(packed), _addr(off), n, _addr(exc_pos) if n_exc else None, _addr(exc_byte) if n_exc else None,
+                n_exc, C.byref(h)), ctx._h)
+        r = cls(ctx, h)
+        r._keep = (packed, off, exc_pos, exc_byte)
+        return r
+
+    def download_packed(self, packed=None, out_offsets=None, exc_pos=None, exc_byte=None, counts=None, asynchronous=False):
+        """2-bit transport download: returns (packed, offsets, exc_pos, exc_byte, counts) with counts[0] =
+        bases and counts[1] = exceptions (valid after download_wait() when asynchronous).  Buffers are
+        allocated when not given (exception capacity: 1/64 of the bases; pass buffers sized to the input's
+        exception count to be exact)."""
+        n = len(self)
+        if out_offsets is None:
+            out_offsets = np.empty(n + 1, dtype=np.uint64)
+        if packed is None:
+            packed = np.empty(self.bases // 4 + 8, dtype=np.uint8)
+        if exc_pos is None:
+            cap = max(16, (packed.numel() if hasattr(packed, "numel") else packed.size) // 16)
+            exc_pos, exc_byte = np.empty(cap, dtype=np.uint64), np.empty(cap, dtype=np.uint8)
+        if counts is None:
+            counts = np.zeros(2, dtype=np.uint64)
+        pcap = packed.numel() if hasattr(packed, "numel") else packed.size
+        ecap = exc_pos.numel() if hasattr(exc_pos, "numel") else exc_pos.size
+        f = lib.brgpu_reads_download_packed_async if asynchronous else lib.brgpu_reads_download_packed
+        check(f(self._h, _addr(packed), pcap, _addr(out_offsets), _addr(exc_pos) if ecap else None,
+                _addr(exc_byte) if ecap else None, ecap, _addr(counts)), self.ctx._h)
+        self._dl = (packed, out_offsets, exc_pos, exc_byte, counts)
+        return packed, out_offsets, exc_pos, exc_byte, counts
 
     @classmethod
     def synth(cls, ctx, genome_seed, read_seed, first_read_id, start, tlen, strand, thresholds):

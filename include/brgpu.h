@@ -109,6 +109,29 @@ int brgpu_reads_download_async(brgpu_reads *reads, uint8_t *seq_host, uint64_t s
                                uint64_t *required);
 int brgpu_reads_download_wait(brgpu_reads *reads);
 
+/* 2-bit transport (BASELINE.json north_star: "2-bit packed reads"): the same chunk at a quarter
+ * of the PCIe bytes in both directions.  `packed` holds the concatenated sequences at 2 bits per base
+ * (code (b >> 1) & 3, four bases per byte, first base in the two high bits; offsets[] are in bases and start
+ * at 0); exc_pos / exc_byte list every byte that is not the upper-case letter of its own code (lower case, N,
+ * any other byte) by its base position in the concatenation.  On the device the reads are ASCII again, so a
+ * position the correctors leave alone keeps its original byte (src/correct/mod.rs:91,100).  The download
+ * returns packed bases, offsets and the exceptions that survive (a subset of the input's: corrections only
+ * emit A, C, T, G — so exc_cap = the input's exception count always suffices), in no particular order;
+ * counts_host[0] = bases, counts_host[1] = exceptions found.  The _async forms follow
+ * brgpu_reads_upload_async / _download_async (brgpu_reads_download_wait completes either download; the
+ * counts are valid after the wait).  br::fasta (br_b200/host/fasta.hpp) packs while it parses and expands
+ * while it formats; br_b200.runtime has the numpy equivalents. */
+int brgpu_reads_upload_packed(brgpu_ctx *ctx, const uint8_t *packed_host, const uint64_t *offsets_host, uint64_t n_reads,
+                              const uint64_t *exc_pos_host, const uint8_t *exc_byte_host, uint64_t n_exc, brgpu_reads **out);
+int brgpu_reads_upload_packed_async(brgpu_ctx *ctx, const uint8_t *packed_host, const uint64_t *offsets_host,
+                                    uint64_t n_reads, const uint64_t *exc_pos_host, const uint8_t *exc_byte_host,
+                                    uint64_t n_exc, brgpu_reads **out);
+int brgpu_reads_download_packed(brgpu_reads *reads, uint8_t *packed_host, uint64_t packed_cap, uint64_t *offsets_host,
+                                uint64_t *exc_pos_host, uint8_t *exc_byte_host, uint64_t exc_cap, uint64_t counts_host[2]);
+int brgpu_reads_download_packed_async(brgpu_reads *reads, uint8_t *packed_host, uint64_t packed_cap,
+                                      uint64_t *offsets_host, uint64_t *exc_pos_host, uint8_t *exc_byte_host,
+                                      uint64_t exc_cap, uint64_t counts_host[2]);
+
 /* Measurement support (bench.py): synthetic ONT-like reads generated on the device, so
  * that the 5 and 30 Gbase workloads of BASELINE.json's configs[3]/[4] never cross PCIe.  The genome is
  * a pure function of (genome_seed, position) and is never stored; read r of this call is read number

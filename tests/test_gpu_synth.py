@@ -80,3 +80,66 @@ def test_profiling_variant_gives_the_same_bytes_and_counts_lookups(gpu):
     assert ctx.scan_lookups >= sum(p["lookups"] for p in prof.values())
     for h in (plain, counted, solid, reads):
         h.free()
+
+
+def test_two_bit_transport_round_trip_and_echo_of_original_bytes(gpu, oracle):
+    """brgpu_reads_upload_packed / _download_packed: reads that crossed PCIe as 2 bits per base plus an
+    exception list are, on the device, byte for byte the reads uploaded as ASCII — lower case, N and
+    arbitrary bytes included — and the corrected output comes back through the packed download identical
+    to the ASCII download (Corrector::correct echoes original bytes, src/correct/mod.rs:91,100).  Also the
+    asynchronous forms, empty reads and a capacity that is too small."""
+    br, ctx = gpu
+    from br_b200 import synth
+    from br_b200.runtime import pack_2bit, unpack_2bit
+
+    rng = np.random.default_rng(5)
+    genome = synth.make_genome(30_000, seed=9)
+    seq, off, _ = synth.make_reads(genome, 12, 0.08, seed=10, mean_len=900, min_len=1)
+    seq = seq.copy()
+    weird = rng.choice(seq.size, size=seq.size // 40, replace=False)
+    seq[weird] = rng.choice(np.frombuffer(b"acgtNnRY-*\x00\xff", dtype=np.uint8), size=weird.size)
+    off = np.concatenate([off[:5], [off[5]], off[5:]]).astype(np.uint64)  # an empty read in the middle
+    packed, exc_pos, exc_byte = pack_2bit(seq)
+    assert exc_pos.size >= weird.size * 0.5 and np.array_equal(unpack_2bit(packed, seq.size, exc_pos, exc_byte), seq)
+    plain = br.Reads.upload(ctx, seq, off)
+    via2 = br.Reads.upload_packed(ctx, packed, off, exc_pos, exc_byte)
+    a, ao = plain.download()
+    b, bo = via2.download()
+    assert np.array_equal(ao, bo) and np.array_equal(a, b) and np.array_equal(a, seq)
+    # correct both; the packed download of the result equals the ASCII one
+    solid = br.Pcon.from_reads(ctx, (genome, np.array([0, genome.size], dtype=np.uint64)), 13, abundance=0)
+    methods = br.build_methods(["one", "two", "graph", "greedy", "gap_size"], solid, 3, 7)
+    c1 = br.correct_reads(methods, plain)
+    c2 = br.correct_reads(methods, via2)
+    g, go = c1.download()
+    p2, o2, ep, eb, cnt = c2.download_packed(exc_pos=np.empty(exc_pos.size, np.uint64), exc_byte=np.empty(exc_pos.size, np.uint8))
+    assert int(cnt[0]) == g.size and np.array_equal(o2, go) and 0 < int(cnt[1]) <= exc_pos.size
+    back = unpack_2bit(p2, int(cnt[0]), ep[: int(cnt[1])], eb[: int(cnt[1])])
+    assert np.array_equal(back, g)
+    assert (g != a[: g.size]).any() if g.size == a.size else True  # the chain edited something
+    # oracle on the same input: the transport is invisible
+    osolid = oracle.Solid.from_bitfield(13, solid.bitfield())
+    exp, exp_off = osolid.run_correction([0, 1, 2, 3, 4], seq, off, confirm=3, max_search=7, threads=8)
+    assert np.array_equal(exp_off, go) and np.array_equal(exp, g)
+    # asynchronous forms
+    import torch
+
+    hp = torch.from_numpy(packed).pin_memory()
+    ho = torch.from_numpy(off.view(np.int64)).pin_memory()
+    up = br.Reads.upload_packed(ctx, hp, ho, exc_pos, exc_byte, asynchronous=True)
+    c3 = br.correct_reads(methods, up)
+    bufs = (torch.empty(g.size // 4 + 8, dtype=torch.uint8).pin_memory(), torch.empty(off.size, dtype=torch.int64).pin_memory(),
+            torch.empty(exc_pos.size, dtype=torch.int64).pin_memory(), torch.empty(exc_pos.size, dtype=torch.uint8).pin_memory(),
+            torch.zeros(2, dtype=torch.int64).pin_memory())
+    c3.download_packed(*bufs, asynchronous=True)
+    c3.download_wait()
+    n_b, n_e = int(bufs[4][0]), int(bufs[4][1])
+    assert n_b == g.size and n_e == int(cnt[1])
+    back3 = unpack_2bit(bufs[0].numpy(), n_b, bufs[2].numpy()[:n_e].view(np.uint64), bufs[3].numpy()[:n_e])
+    assert np.array_equal(back3, g)
+    # too small an exception buffer: E_OVERFLOW, the count says how many there are
+    with pytest.raises(br.BrgpuError) as ei:
+        c2.download_packed(exc_pos=np.empty(1, np.uint64), exc_byte=np.empty(1, np.uint8))
+    assert ei.value.status == 5
+    for h in (plain, via2, c1, c2, c3, up, solid):
+        h.free()

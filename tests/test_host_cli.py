@@ -318,3 +318,32 @@ def test_fasta_subcommand_streams_its_input_in_chunks(tmp_path, oracle, fixture_
     exp, exp_off = solid.run_correction([oracle.METHOD_IDS["one"]], seq, off, confirm=5, threads=8)
     names, _, _ = records(GOLDEN / "br_reads.fa.gz")
     assert_same_records(out, names, exp, exp_off)
+
+
+@pytest.mark.gpu
+def test_both_transports_echo_non_acgt_bytes(tmp_path, oracle, fixture_reads, fixture_solid_payload):
+    """The CLI moves chunks across PCIe at 2 bits per base plus an exception list (`--transport packed`,
+    the default) or as ASCII; reads with lower-case runs, N and other bytes must come out the same either
+    way and equal the oracle: uncorrected positions echo the original byte (src/correct/mod.rs:91,100)."""
+    seq, off = fixture_reads
+    rng = np.random.default_rng(3)
+    seq = seq[: int(off[40])].copy()
+    off = off[:41]
+    for r in range(0, 40, 3):  # a lower-case stretch and a few Ns / IUPAC codes in every third read
+        a, b = int(off[r]), int(off[r + 1])
+        s = a + int(rng.integers(0, max(1, b - a - 200)))
+        seq[s : s + 150] |= 0x20
+        hits = a + rng.integers(0, b - a, size=12)
+        seq[hits] = rng.choice(np.frombuffer(b"NnRYKM", dtype=np.uint8), size=12)
+    inp = tmp_path / "odd.fa"
+    with open(inp, "wb") as f:
+        for r in range(40):
+            f.write(b">r%d\n" % r + seq[int(off[r]) : int(off[r + 1])].tobytes() + b"\n")
+    exp, exp_off = oracle_corrected(oracle, fixture_solid_payload, ["one", "two", "graph", "greedy", "gap_size"], seq, off)
+    names = [b"r%d" % r for r in range(40)]
+    for transport in ("packed", "ascii"):
+        out = tmp_path / f"corr_{transport}.fa"
+        r = run(["-i", inp, "-o", out, "--transport", transport, "solid", "-i", GOLDEN / "br_reads.k11.a2.solid", "-f", "solid"])
+        assert r.returncode == 0 and r.stderr == b"", r.stderr
+        assert_same_records(out, names, exp, exp_off)
+    assert (exp[: 0] == exp[: 0]).all() and any(c in exp.tobytes() for c in (b"n", b"N", b"a"))
