@@ -82,6 +82,9 @@ SIGNATURES = {
     "brgpu_set_get_batch": (C.c_int, [vp, vp, u64, vp]),
     "brgpu_set_spectrum": (C.c_int, [vp, vp]),
     "brgpu_set_device_ptr": (vp, [vp]),
+    "brgpu_set_new_sliced": (C.c_int, [vp, C.c_int, pvp]),
+    "brgpu_set_summary_ptr": (vp, [vp, pu64]),
+    "brgpu_set_commit_slices": (C.c_int, [vp, C.c_int]),
     "brgpu_set_free": (None, [vp]),
     "brgpu_correct_reads": (C.c_int, [vp, vp, vp, u64, C.c_int, C.c_int, C.c_int, vp, pvp]),
     "brgpu_correct_batch": (C.c_int, [vp, vp, vp, u64, C.c_int, C.c_int, C.c_int, vp, vp, u64, vp, u64, vp, pu64]),
@@ -94,6 +97,7 @@ SIGNATURES = {
     "brgpu_set_threshold_slice": (C.c_int, [vp, vp, C.c_int, u64, u64]),
     "brgpu_kmers_create": (C.c_int, [vp, C.c_int, vp, pvp]),
     "brgpu_kmers_buckets": (u64, [vp]),
+    "brgpu_kmers_offsets_ptr": (vp, [vp]),
     "brgpu_kmers_ipc_export": (C.c_int, [vp, vp]),
     "brgpu_kmers_count_range": (C.c_int, [vp, vp, vp, C.c_int, u64, u64, C.c_int, vp, vp]),
     "brgpu_kmers_offsets_at": (C.c_int, [vp, vp, u64, vp]),

@@ -139,9 +139,19 @@ static const uint64_t POOL_TRIM_BYTES = 48ULL << 30; // cached-but-unused bytes 
 static void pool_flush(brgpu_ctx *ctx) {
     if (ctx->pool_free.empty()) return;
     cudaStreamSynchronize(ctx->stream);
-    for (auto &b : ctx->pool_free) cudaFree(b.first);
-    ctx->pool_free.clear();
-    ctx->pool_free_bytes = 0;
+    // freeing memory a peer process still has mapped through CUDA IPC is undefined: exported blocks stay cached
+    std::vector<std::pair<void *, uint64_t>> keep;
+    uint64_t keep_bytes = 0;
+    for (auto &b : ctx->pool_free) {
+        if (ctx->pool_exported.count(b.first)) {
+            keep.push_back(b);
+            keep_bytes += b.second;
+        } else {
+            cudaFree(b.first);
+        }
+    }
+    ctx->pool_free.swap(keep);
+    ctx->pool_free_bytes = keep_bytes;
 }
 
 static cudaError_t pool_alloc(brgpu_ctx *ctx, void **p, uint64_t bytes) {
@@ -1354,6 +1364,7 @@ extern "C" void brgpu_kmers_free(brgpu_kmers *km) {
 }
 
 extern "C" uint64_t brgpu_kmers_buckets(const brgpu_kmers *km) { return km ? km->n_buckets : 0; }
+extern "C" void *brgpu_kmers_offsets_ptr(brgpu_kmers *km) { return km ? km->d_base : nullptr; }
 
 extern "C" int brgpu_kmers_ipc_export(brgpu_kmers *km, uint8_t handles_out[128]) {
     if (!km || !handles_out) return BRGPU_E_INVALID;
@@ -1364,6 +1375,8 @@ extern "C" int brgpu_kmers_ipc_export(brgpu_kmers *km, uint8_t handles_out[128])
     memcpy(handles_out, &h, 64);
     CK(cudaIpcGetMemHandle(&h, km->d_base));
     memcpy(handles_out + 64, &h, 64);
+    ctx->pool_exported[km->d_res] = true;
+    ctx->pool_exported[km->d_base] = true;
     return BRGPU_OK;
 }
 
@@ -1375,7 +1388,7 @@ static int kmers_count_parts(brgpu_ctx *ctx, brgpu_kmers *const *local, int n_lo
                              void *const *peer_offsets, const uint64_t *peer_first, const uint64_t *peer_last, int n_peers,
                              uint64_t bucket_begin, uint64_t bucket_end, int abundance, brgpu_set *set, bool emit_summary,
                              uint64_t hist_host[256]) {
-    if (!ctx || !local || n_local < 1 || !hist_host || (n_peers && (!peer_residues || !peer_offsets))) return BRGPU_E_INVALID;
+    if (!ctx || !local || n_local < 1 || (n_peers && (!peer_residues || !peer_offsets))) return BRGPU_E_INVALID;
     if (n_peers < 0 || n_local + n_peers > BRGPU_MAX_KMER_SOURCES)
         return fail(ctx, BRGPU_E_INVALID, "at most 64 k-mer partitions (local chunks + peers) per count");
     const int k = local[0]->k;
@@ -1448,7 +1461,7 @@ static int kmers_count_parts(brgpu_ctx *ctx, brgpu_kmers *const *local, int n_lo
     launch_bucket_count_multi(ctx, res, base, n_local + n_peers, bucket_begin, bucket_end, set ? abundance : 0,
                               set ? set->d_bits : nullptr, set && emit_summary ? set->d_summary : nullptr, ctx->d_hist,
                               n_kmers * (double)(n_local + n_peers) / (double)n_local);
-    e = read_hist(ctx, hist_host);
+    e = hist_host ? read_hist(ctx, hist_host) : cudaSuccess; // no spectrum wanted: no host round trip either
     drop();
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) return fail(ctx, BRGPU_E_CUDA, "sharded bucket counting", e);
@@ -1460,7 +1473,7 @@ extern "C" int brgpu_kmers_count_parts(brgpu_ctx *ctx, brgpu_kmers *const *local
                                        int n_peers, uint64_t bucket_begin, uint64_t bucket_end, int abundance, brgpu_set *set,
                                        uint64_t hist_host[256]) {
     return kmers_count_parts(ctx, local, n_local, peer_residues, peer_offsets, peer_first, peer_last, n_peers, bucket_begin,
-                             bucket_end, abundance, set, false, hist_host);
+                             bucket_end, abundance, set, set && set->d_summary && set->summary_shift == 6, hist_host);
 }
 
 extern "C" int brgpu_kmers_count_range(brgpu_kmers *km, void *const *peer_residues, void *const *peer_offsets,
@@ -1468,7 +1481,7 @@ extern "C" int brgpu_kmers_count_range(brgpu_kmers *km, void *const *peer_residu
                                        brgpu_set *set, uint64_t hist_host[256]) {
     if (!km) return BRGPU_E_INVALID;
     return kmers_count_parts(km->ctx, &km, 1, peer_residues, peer_offsets, nullptr, nullptr, n_peers, bucket_begin, bucket_end,
-                             abundance, set, false, hist_host);
+                             abundance, set, set && set->d_summary && set->summary_shift == 6, hist_host);
 }
 
 extern "C" int brgpu_kmers_count_range_staged(brgpu_kmers *km, void *const *peer_residues, void *const *peer_offsets,
@@ -1477,7 +1490,7 @@ extern "C" int brgpu_kmers_count_range_staged(brgpu_kmers *km, void *const *peer
                                               brgpu_set *set, uint64_t hist_host[256]) {
     if (!km || (n_peers && (!peer_first || !peer_last))) return BRGPU_E_INVALID;
     return kmers_count_parts(km->ctx, &km, 1, peer_residues, peer_offsets, peer_first, peer_last, n_peers, bucket_begin,
-                             bucket_end, abundance, set, false, hist_host);
+                             bucket_end, abundance, set, set && set->d_summary && set->summary_shift == 6, hist_host);
 }
 
 // The `fasta` sub-command over a stream of chunks (src/main.rs:72-78: count_fasta(inputs, 8192) reads the
@@ -1816,6 +1829,50 @@ extern "C" void *brgpu_set_device_ptr(brgpu_set *s) {
     return s->d_bits;
 }
 
+// Sharded construction writes a set slice by slice (each rank its bucket range, the rest arrives through the
+// host's all-gather).  brgpu_set_new_sliced = Solid::new(k) without the zero-fill, with the occupancy summary
+// allocated so that brgpu_kmers_count_* emit the slice's summary words along with its bitfield bits;
+// brgpu_set_summary_ptr exposes the summary for the same all-gather; brgpu_set_commit_slices declares both
+// complete (no build_summary pass over the 1 GiB bitfield).
+extern "C" int brgpu_set_new_sliced(brgpu_ctx *ctx, int k, brgpu_set **out) {
+    if (!ctx || !out) return BRGPU_E_INVALID;
+    *out = nullptr;
+    if (!k_supported(k)) return fail(ctx, BRGPU_E_INVALID, "k must be odd and in 3..=19");
+    cudaSetDevice(ctx->device);
+    brgpu_set *s = nullptr;
+    int st = set_alloc(ctx, k, &s);
+    if (st != BRGPU_OK) return st;
+    int shift;
+    uint64_t sbytes;
+    summary_geometry(k, &shift, &sbytes);
+    if (sbytes && shift == 6) {
+        cudaError_t e = big_alloc(ctx, (void **)&s->d_summary, sbytes);
+        if (e != cudaSuccess) {
+            brgpu_set_free(s);
+            return fail(ctx, BRGPU_E_NOMEM, "device allocation (summary)", e);
+        }
+        s->summary_bytes = sbytes;
+        s->summary_shift = shift;
+    } else {
+        cudaMemsetAsync(s->d_bits, 0, bits_alloc_bytes(k), ctx->stream); // small k: slices are written by threshold_slice
+    }
+    *out = s;
+    return BRGPU_OK;
+}
+
+extern "C" void *brgpu_set_summary_ptr(brgpu_set *s, uint64_t *n_bytes) {
+    if (n_bytes) *n_bytes = s && !s->is_hash ? s->summary_bytes : 0;
+    return s && !s->is_hash && s->summary_bytes ? s->d_summary : nullptr;
+}
+
+extern "C" int brgpu_set_commit_slices(brgpu_set *s, int summary_complete) {
+    if (!s || s->is_hash) return BRGPU_E_INVALID;
+    compact_release(s);
+    s->summary_valid = summary_complete != 0 && s->d_summary != nullptr;
+    if (s->summary_valid) return build_compact(s);
+    return BRGPU_OK;
+}
+
 extern "C" int brgpu_set_export_bitfield(brgpu_set *s, uint8_t *out_host, uint64_t cap) {
     if (!s || !out_host) return BRGPU_E_INVALID;
     brgpu_ctx *ctx = s->ctx;
@@ -2079,6 +2136,7 @@ extern "C" int brgpu_counts_ipc_export(brgpu_counts *c, uint8_t handle_out[64]) 
     cudaIpcMemHandle_t h;
     CK(cudaIpcGetMemHandle(&h, c->d_counts));
     memcpy(handle_out, &h, 64);
+    ctx->pool_exported[c->d_counts] = true;
     return BRGPU_OK;
 }
 

@@ -56,6 +56,8 @@ struct brgpu_ctx {
     std::unordered_map<void *, uint64_t> pool_live;
     std::vector<std::pair<void *, uint64_t>> pool_free;
     uint64_t pool_free_bytes = 0;
+    // blocks whose CUDA-IPC handle went out (peers may keep them mapped): never cudaFree'd before the context dies
+    std::unordered_map<void *, bool> pool_exported;
 };
 
 namespace brgpu {

@@ -81,15 +81,15 @@ def _build_from_kmers(ops, k, abundance, abundance_selection, percent=0.0):
     world, rank = ops.world, ops.rank
     n_buckets = 1 << (2 * k - 1 - BUCKET_BITS)
     b0, b1 = bucket_bounds(n_buckets, world, rank)
-    ops.partition_local(k)                   # bucket_hist -> scan -> bucket_scatter on the own shard
-    handles = ops.exchange_kmer_handles()    # all-gather of the IPC handles
-    ops.barrier()                            # every partition is complete before anyone reads it
+    ops.partition_local(k)                   # two-level partition of the own shard
+    handles = ops.exchange_kmer_handles()    # all-gather of the IPC handles + residue offsets at the rank boundaries
+    ops.barrier("partitions complete")       # every partition is complete before anyone reads it
     ops.open_peers(handles)
     abundance = _pick_abundance(ops, abundance, abundance_selection, lambda: ops.count_range(b0, b1, None), percent)
     ops.count_range(b0, b1, abundance)       # count + threshold the owned range (peer data over NVLink)
     bounds = [tuple(x << BUCKET_BITS for x in bucket_bounds(n_buckets, world, r)) for r in range(world)]
     ops.all_gather_bitfield(b0 << BUCKET_BITS, b1 << BUCKET_BITS, 1 << (2 * k - 1), bounds)
-    ops.barrier()                            # peers are done reading this rank's partition
+    ops.barrier("peers done reading")        # peers are done reading this rank's partition
     return ops.finish(abundance)
 
 
@@ -99,25 +99,34 @@ def _build_from_tables(ops, k, abundance, abundance_selection, percent=0.0):
     begin, end = slice_bounds(n, world, rank)
     ops.count_local(k)                       # private table, own shard
     handles = ops.exchange_handles()         # all-gather of the 64-byte IPC handles
-    ops.barrier()                            # every table is complete before anyone reads it
+    ops.barrier("tables complete")           # every table is complete before anyone reads it
     ops.merge_slice(handles, begin, end)     # saturating reduce of slice `rank` over NVLink
     abundance = _pick_abundance(ops, abundance, abundance_selection, lambda: ops.spectrum_slice(begin, end), percent)
     ops.threshold_slice(abundance, begin, end)
     ops.all_gather_bitfield(begin, end, n, [slice_bounds(n, world, r) for r in range(world)])  # NCCL all-gather
-    ops.barrier()                            # peers are done reading this rank's table
+    ops.barrier("peers done reading")        # peers are done reading this rank's table
     return ops.finish(abundance)
 
 
 class _CudaArray:
     """Zero-copy view of library-owned device memory for torch (__cuda_array_interface__)."""
 
-    def __init__(self, ptr, nbytes):
-        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+    def __init__(self, ptr, nbytes, typestr="|u1"):
+        n = nbytes // int(typestr[2:])
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (int(ptr), False), "version": 2}
 
 
 class GpuOps:
     """The protocol's steps on a real GPU: C ABI for the kernels, torch.distributed for the
-    plumbing (handle exchange, barriers, the tiny all-reduce, the bitfield all-gather)."""
+    plumbing (handle exchange, the tiny all-reduce, the bitfield all-gather).
+
+    Ordering without host barriers.  When the context runs on torch's current stream every NCCL
+    collective is ordered, on every rank, after the library work enqueued before it.  The handle
+    all-gather therefore cannot complete on a rank before every peer's partition kernels have — it is
+    the "partitions complete" barrier — and the bitfield all-gather cannot complete before every peer's
+    counting kernel has read this rank's residues — it is the "peers done reading" barrier.  So a step
+    has no `dist.barrier()` and no stream synchronisation of its own; the one host round trip left is
+    reading the gathered handles and offsets.  On any other stream the explicit barriers stay."""
 
     def __init__(self, ctx, reads, group=None):
         import torch
@@ -131,6 +140,8 @@ class GpuOps:
         self.set = None
         self._peers = []
         self.supports_kmers = True
+        self.dev = f"cuda:{ctx.device}"
+        self.stream_ordered = ctx.stream_ptr is not None and torch.cuda.current_stream(ctx.device).cuda_stream == ctx.stream_ptr
 
     # ---- bucketed k-mer protocol (k >= 15) ----
     def partition_local(self, k):
@@ -140,28 +151,43 @@ class GpuOps:
         h = C.c_void_p()
         check(lib.brgpu_kmers_create(self.ctx._h, k, self.reads._h, C.byref(h)), self.ctx._h)
         self.kmers = h
-        self.set = Pcon.new(self.ctx, k)
+        s = C.c_void_p()
+        check(lib.brgpu_set_new_sliced(self.ctx._h, k, C.byref(s)), self.ctx._h)
+        self.set = Pcon(self.ctx, s)
 
     def exchange_kmer_handles(self):
-        """All-gather of: the two CUDA-IPC handles (residues, bucket offsets) and this rank's residue
+        """One all-gather of: the two CUDA-IPC handles (residues, bucket offsets) and this rank's residue
         offsets at every rank's bucket boundaries (so that the owner of a bucket range knows which
-        contiguous piece of this rank's residues it needs)."""
+        contiguous piece of this rank's residues it needs).  The offsets are picked out of the
+        library's offset array on the device: no host round trip before the collective."""
+        torch = self.torch
         h = (C.c_uint8 * 128)()
         check(lib.brgpu_kmers_ipc_export(self.kmers, h), self.ctx._h)
         n_buckets = lib.brgpu_kmers_buckets(self.kmers)
-        cuts = np.array([bucket_bounds(n_buckets, self.world, r)[0] for r in range(self.world)] + [n_buckets], dtype=np.uint64)
-        offs = np.zeros(cuts.size, dtype=np.uint64)
-        check(lib.brgpu_kmers_offsets_at(self.kmers, cuts.ctypes.data_as(C.c_void_p), cuts.size,
-                                         offs.ctypes.data_as(C.c_void_p)), self.ctx._h)
-        payload = bytes(h) + offs.tobytes()
-        mine = self.torch.frombuffer(bytearray(payload), dtype=self.torch.uint8).to(f"cuda:{self.ctx.device}")
-        allh = [self.torch.empty_like(mine) for _ in range(self.world)]
-        self.dist.all_gather(allh, mine, group=self.group)
-        return [t.cpu().numpy().tobytes() for t in allh]
+        cuts = [bucket_bounds(n_buckets, self.world, r)[0] for r in range(self.world)] + [n_buckets]
+        base = torch.as_tensor(_CudaArray(lib.brgpu_kmers_offsets_ptr(self.kmers), (n_buckets + 1) * 8, "<i8"), device=self.dev)
+        idx = self._cut_index(tuple(cuts))
+        mine = torch.empty(16 + len(cuts), dtype=torch.int64, device=self.dev)
+        mine[:16].copy_(torch.frombuffer(bytearray(bytes(h)), dtype=torch.int64), non_blocking=True)
+        torch.index_select(base, 0, idx, out=mine[16:])
+        allh = torch.empty(self.world * mine.numel(), dtype=torch.int64, device=self.dev)
+        self.dist.all_gather_into_tensor(allh, mine, group=self.group)
+        rows = allh.cpu().numpy().reshape(self.world, -1)  # the step's one host round trip
+        return [rows[r].tobytes() for r in range(self.world)]
+
+    def _cut_index(self, cuts):
+        cache = self.ctx.__dict__.setdefault("_cut_index_cache", {})
+        t = cache.get(cuts)
+        if t is None:
+            t = self.torch.tensor(list(cuts), dtype=self.torch.int64, device=self.dev)
+            cache[cuts] = t
+        return t
 
     def _ipc_open_cached(self, handle: bytes):
         """cudaIpcOpenMemHandle costs milliseconds (and so does closing); the library reuses its big
-        buffers from call to call, so the peers' handles repeat — keep the mappings per context."""
+        buffers from call to call, so the peers' handles repeat — the mappings are kept per context and
+        closed by Context.close().  The owner never frees an exported block before its context dies
+        (brgpu.cu: pool_flush skips exported blocks), so a cached mapping cannot dangle."""
         cache = self.ctx.__dict__.setdefault("_ipc_cache", {})
         p = cache.get(handle)
         if p is None:
@@ -187,11 +213,12 @@ class GpuOps:
         off = (C.c_void_p * max(1, n))(*[p.value for p in self._peer_off])
         first = (C.c_uint64 * max(1, n))(*self._peer_first)
         last = (C.c_uint64 * max(1, n))(*self._peer_last)
-        hist = np.zeros(256, dtype=np.uint64)
+        # the spectrum comes back to the host only when the threshold is derived from it
+        hist = np.zeros(256, dtype=np.uint64) if abundance is None else None
         check(lib.brgpu_kmers_count_range_staged(self.kmers, res, off, first, last, n, b0, b1,
                                                  -1 if abundance is None else int(abundance),
                                                  None if abundance is None else self.set._h,
-                                                 hist.ctypes.data_as(C.c_void_p)), self.ctx._h)
+                                                 None if hist is None else hist.ctypes.data_as(C.c_void_p)), self.ctx._h)
         return hist
 
     def count_local(self, k):
@@ -205,24 +232,20 @@ class GpuOps:
     def exchange_handles(self):
         h = (C.c_uint8 * 64)()
         check(lib.brgpu_counts_ipc_export(self.counter._h, h), self.ctx._h)
-        mine = self.torch.tensor(list(h), dtype=self.torch.uint8, device=f"cuda:{self.ctx.device}")
+        mine = self.torch.tensor(list(h), dtype=self.torch.uint8, device=self.dev)
         allh = [self.torch.empty_like(mine) for _ in range(self.world)]
         self.dist.all_gather(allh, mine, group=self.group)
         return [bytes(t.cpu().tolist()) for t in allh]
 
-    def barrier(self):
+    def barrier(self, why=""):
+        del why
+        if self.stream_ordered:
+            return  # the neighbouring collective already orders the ranks (see the class docstring)
         self.ctx.synchronize()
         self.dist.barrier(group=self.group)
 
     def merge_slice(self, handles, begin, end):
-        ptrs = []
-        for r, hb in enumerate(handles):
-            if r == self.rank:
-                continue
-            p = C.c_void_p()
-            check(lib.brgpu_ipc_open(self.ctx._h, (C.c_uint8 * 64).from_buffer_copy(hb), C.byref(p)), self.ctx._h)
-            ptrs.append(p)
-        self._peers = ptrs
+        ptrs = [self._ipc_open_cached(hb) for r, hb in enumerate(handles) if r != self.rank]
         arr = (C.c_void_p * max(1, len(ptrs)))(*[p.value for p in ptrs])
         check(lib.brgpu_counts_merge_slice(self.counter._h, arr, len(ptrs), begin, end), self.ctx._h)
 
@@ -232,7 +255,7 @@ class GpuOps:
         return h
 
     def all_reduce_sum(self, hist):
-        t = self.torch.from_numpy(hist.astype(np.int64)).to(f"cuda:{self.ctx.device}")
+        t = self.torch.from_numpy(hist.astype(np.int64)).to(self.dev)
         self.dist.all_reduce(t, group=self.group)
         return t.cpu().numpy().astype(np.uint64)
 
@@ -252,35 +275,47 @@ class GpuOps:
         check(lib.brgpu_set_threshold_slice(self.set._h, self.counter._h, abundance, begin, end), self.ctx._h)
 
     def all_gather_bitfield(self, begin, end, n_bits, bounds=None):
-        """[begin, end) is this rank's bit range; `bounds` lists every rank's range in rank order."""
+        """[begin, end) is this rank's bit range; `bounds` lists every rank's range in rank order.  The
+        slices of the occupancy summary (one bit per 64 bitfield bits) travel with the bitfield's."""
+        torch = self.torch
         n_bytes = lib.brgpu_set_bitfield_bytes(self.set._h)
         ptr = lib.brgpu_set_device_ptr(self.set._h)
-        full = self.torch.as_tensor(_CudaArray(ptr, n_bytes), device=f"cuda:{self.ctx.device}")
-        per = (end - begin) // 8
+        full = torch.as_tensor(_CudaArray(ptr, n_bytes), device=self.dev)
+        sb = C.c_uint64()
+        sptr = lib.brgpu_set_summary_ptr(self.set._h, C.byref(sb))
+        summary = torch.as_tensor(_CudaArray(sptr, sb.value), device=self.dev) if sptr and self.kmers is not None else None
+        self._summary_gathered = False
         if self.world == 1:
+            self._summary_gathered = summary is not None
             return
         if bounds is None:
-            mine = self.torch.tensor([begin, end], dtype=self.torch.int64, device=f"cuda:{self.ctx.device}")
-            allb = [self.torch.empty_like(mine) for _ in range(self.world)]
+            mine = torch.tensor([begin, end], dtype=torch.int64, device=self.dev)
+            allb = [torch.empty_like(mine) for _ in range(self.world)]
             self.dist.all_gather(allb, mine, group=self.group)
             bounds = [tuple(int(x) for x in t.cpu().tolist()) for t in allb]
-        # the library's stream produced the slice; NCCL runs on torch's current stream
-        self.ctx.synchronize()
+        if not self.stream_ordered:  # the library's stream produced the slice; NCCL runs on torch's current stream
+            self.ctx.synchronize()
+        per = (end - begin) // 8
         if all((e - b) // 8 == per for b, e in bounds) and per * self.world == n_bytes:
             # in place: rank r's slice already sits at offset r * per of the output
             self.dist.all_gather_into_tensor(full, full[begin // 8 : end // 8], group=self.group)
+            if summary is not None and per % 64 == 0:
+                self.dist.all_gather_into_tensor(summary, summary[begin // 512 : end // 512], group=self.group)
+                self._summary_gathered = True
         else:  # ragged last slice: broadcast slice by slice
             for r, (b, e) in enumerate(bounds):
-                self.dist.broadcast(full[b // 8 : e // 8], src=self.dist.get_global_rank(self.group, r) if self.group else r,
-                                    group=self.group)
+                src = self.dist.get_global_rank(self.group, r) if self.group else r
+                self.dist.broadcast(full[b // 8 : e // 8], src=src, group=self.group)
+                if summary is not None and b % 512 == 0 and e % 512 == 0:
+                    self.dist.broadcast(summary[b // 512 : e // 512], src=src, group=self.group)
+            self._summary_gathered = summary is not None and all(b % 512 == 0 and e % 512 == 0 for b, e in bounds)
 
     def finish(self, abundance):
-        for p in self._peers:
-            check(lib.brgpu_ipc_close(self.ctx._h, p), self.ctx._h)
-        self._peers = []
         if self.counter is not None:
             self.counter.free()
         if self.kmers is not None:
             lib.brgpu_kmers_free(self.kmers)
             self.kmers = None
+            # bitfield and summary are whole: build the lookup structures without re-reading the bitfield
+            check(lib.brgpu_set_commit_slices(self.set._h, int(getattr(self, "_summary_gathered", False))), self.ctx._h)
         return self.set

@@ -116,6 +116,7 @@ class Context:
             raw = C.c_void_p(getattr(stream, "cuda_stream", stream))
         check(lib.brgpu_ctx_create(int(device), raw, C.byref(h)))
         self._h = h
+        self.stream_ptr = raw.value if raw is not None else None  # the caller's stream (None: the library made its own)
         self.device = int(device)
         self._children = weakref.WeakSet()  # live Reads / Pcon / Counter handles of this context
 

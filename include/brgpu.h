@@ -215,6 +215,14 @@ int brgpu_set_get_batch(brgpu_set *set, const uint64_t *kmers_host, uint64_t n, 
 /* spectrum seen when the set was built from reads/counts (zeros if not) */
 int brgpu_set_spectrum(const brgpu_set *set, uint64_t hist[256]);
 void *brgpu_set_device_ptr(brgpu_set *set);
+/* Sharded construction fills a set slice by slice: _new_sliced = Solid::new(k) without the zero-fill and with
+ * the occupancy summary allocated, so that brgpu_kmers_count_* write the slice's summary words next to its
+ * bitfield bits; _summary_ptr exposes the summary (one bit per 64 bitfield bits; slices are proportional to
+ * the bitfield's) for the same all-gather; _commit_slices declares bitfield (and summary, if
+ * summary_complete) whole and builds the lookup structures — no pass over the 1 GiB bitfield. */
+int brgpu_set_new_sliced(brgpu_ctx *ctx, int k, brgpu_set **out);
+void *brgpu_set_summary_ptr(brgpu_set *set, uint64_t *n_bytes);
+int brgpu_set_commit_slices(brgpu_set *set, int summary_complete);
 void brgpu_set_free(brgpu_set *set);
 
 /* ------------------------------------------------------------------------------------------
@@ -265,6 +273,9 @@ int brgpu_set_threshold_slice(brgpu_set *set, brgpu_counts *counts, int abundanc
  * through brgpu_set_device_ptr. */
 int brgpu_kmers_create(brgpu_ctx *ctx, int k, const brgpu_reads *reads, brgpu_kmers **out);
 uint64_t brgpu_kmers_buckets(const brgpu_kmers *kmers);
+/* device pointer of the bucket offsets (buckets + 1 u64): a host that exchanges them with a device-side
+ * collective needs no round trip through brgpu_kmers_offsets_at */
+void *brgpu_kmers_offsets_ptr(brgpu_kmers *kmers);
 int brgpu_kmers_ipc_export(brgpu_kmers *kmers, uint8_t handles_out[128]); /* [0..64) residues, [64..128) offsets */
 int brgpu_kmers_count_range(brgpu_kmers *kmers, void *const *peer_residues, void *const *peer_offsets, int n_peers,
                             uint64_t bucket_begin, uint64_t bucket_end, int abundance, brgpu_set *set,

@@ -48,7 +48,7 @@ class NumpyOps:
         self.tdist.all_gather(allt, mine)
         return [t.numpy() for t in allt]
 
-    def barrier(self):
+    def barrier(self, why=""):
         self.tdist.barrier()
 
     def merge_slice(self, handles, begin, end):
