@@ -1093,7 +1093,10 @@ __device__ __forceinline__ void correct_segment(Rd &rd, const CorrectParams &p, 
     flush_copy(rd, i < rd.len ? i : rd.len);
 }
 
-template <int METHOD, int KT>
+// DIRECT: the set is known to be in its rank-compacted form (SolidView::dir), the usual case for a sparse set:
+// the other two lookup arms (summary + bitfield, hash table) are compiled out — a third of the code of a
+// kernel whose warps stall on instruction fetch as often as on memory (profiles/ncu_r2_scan_full.txt)
+template <int METHOD, int KT, bool DIRECT>
 __global__ void __launch_bounds__(SCAN_WARPS_PER_BLOCK * 32, (METHOD == BRGPU_ONE || METHOD == BRGPU_TWO) ? BRGPU_SCAN_MINB : 1)
     scan_spec_kernel(const uint8_t *__restrict__ in, const uint32_t *__restrict__ len_in,
                      const uint64_t *__restrict__ slot_off, const uint32_t *__restrict__ bitmap,
@@ -1104,6 +1107,11 @@ __global__ void __launch_bounds__(SCAN_WARPS_PER_BLOCK * 32, (METHOD == BRGPU_ON
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     Rd rd;
     if (KT) p.k = KT; // compile-time k: the k-mer arithmetic below folds to immediates
+    if (DIRECT) {
+        set.hash = nullptr;
+        set.summary = nullptr;
+        __builtin_assume(set.dir != nullptr);
+    }
     rd.set = set;
     rd.set.k = p.k;
     rd.k = p.k;
@@ -1615,75 +1623,92 @@ __device__ __forceinline__ Corr g_exist_correct_error(G8 &g, const SolidView &se
             for (int h = 0; h < 2; h++) m16 |= g_ballot(g, want[h] && hit[h]) << (8 * h);
         }
         const uint32_t N0 = m16 & 0xf, N1 = (m16 >> 4) & 0xf, N2 = (m16 >> 8) & 0xf, N0p = (m16 >> 12) & 0xf;
+        // The 13 scenarios are evaluated once: lane gl owns scenarios gl and gl + 8 and keeps their k-mer and
+        // their four small fields (offa | offc << 8 | n_emit << 16 | codes << 24); whoever needs scenario s
+        // later takes it from lane s & 7 by shuffle instead of running scen_two again.
+        uint64_t myK[2];
+        uint32_t myMeta[2];
+        bool myValid[2];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int s = g.gl + 8 * h;
+            myK[h] = 0;
+            myMeta[h] = 0;
+            myValid[h] = false;
+            if (s < NS) {
+                const Scen t = scen_two(s, K0, sublen, sb, N0, N1, N2, N0p, mask);
+                myK[h] = t.K;
+                myMeta[h] = t.offa | (t.offc << 8) | (t.n_emit << 16) | (t.codes << 24);
+                myValid[h] = t.valid && !(t.offa + c > sublen); // get_score's length test (exist/mod.rs:29-31)
+            }
+        }
+        auto scen_K = [&](int s) -> uint64_t { // all lanes of the group take part
+            const uint64_t a = g_shfl64(g, myK[0], s & 7), b = g_shfl64(g, myK[1], s & 7);
+            return (s >> 3) ? b : a;
+        };
+        auto scen_meta = [&](int s) -> uint32_t {
+            const uint32_t a = g_shfl(g, myMeta[0], s & 7), b = g_shfl(g, myMeta[1], s & 7);
+            return (s >> 3) ? b : a;
+        };
         // round 3a: get(K) of every valid scenario that is long enough, two scenarios per lane
         cand = 0;
         {
-            uint64_t km[2];
-            bool want[2], hit[2];
+            bool hit[2];
+            g_lookup_n<2>(g, set, myK, myValid, hit);
 #pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const int s = g.gl + 8 * h;
-                want[h] = false;
-                km[h] = 0;
-                if (s < NS) {
-                    const Scen t = scen_two(s, K0, sublen, sb, N0, N1, N2, N0p, mask);
-                    want[h] = t.valid && !(t.offa + c > sublen);
-                    km[h] = t.K;
-                }
-            }
-            g_lookup_n<2>(g, set, km, want, hit);
-#pragma unroll
-            for (int h = 0; h < 2; h++) cand |= g_ballot(g, want[h] && hit[h]) << (8 * h);
+            for (int h = 0; h < 2; h++) cand |= g_ballot(g, myValid[h] && hit[h]) << (8 * h);
         }
-        // round 3b: the c confirmations of the survivors
-        const uint32_t Q = (uint32_t)__popc(cand) * c;
-        if (Q <= 24u) {
+        // round 3b: the c confirmations of the survivors.  Survivor r is scenario (ids >> 4r) & 15: every
+        // surviving scenario's owner contributes its id at its rank among the survivors.
+        const uint32_t n_alive = (uint32_t)__popc(cand);
+        const uint32_t Q = n_alive * c;
+        uint32_t ids_lo = 0, ids_hi = 0;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const uint32_t s = (uint32_t)g.gl + 8u * (uint32_t)h;
+            if ((cand >> s) & 1u) {
+                const uint32_t r = (uint32_t)__popc(cand & ((1u << s) - 1u));
+                if (r < 8u) ids_lo |= s << (4u * r);
+                else ids_hi |= s << (4u * (r - 8u));
+            }
+        }
+        ids_lo = g_or(g, ids_lo);
+        ids_hi = g_or(g, ids_hi);
+        const uint32_t inv_c = c > 1 ? 0xffffffffu / c + 1u : 0u; // q / c by multiplication (q < 2^16)
+        for (uint32_t q0 = 0; q0 < Q; q0 += 24) {
             uint64_t km[3];
             bool want[3], hit[3];
             int sc_of[3];
 #pragma unroll
             for (int h = 0; h < 3; h++) {
-                const uint32_t q = (uint32_t)g.gl + 8u * (uint32_t)h;
+                const uint32_t q = q0 + (uint32_t)g.gl + 8u * (uint32_t)h;
                 want[h] = q < Q;
-                km[h] = 0;
-                sc_of[h] = 0;
-                if (want[h]) {
-                    const uint32_t r = q / c, u = q - r * c + 1u;
-                    const int s = (int)__fns(cand, 0u, (int)r + 1);
-                    const Scen t = scen_two(s, K0, sublen, sb, N0, N1, N2, N0p, mask);
-                    sc_of[h] = s;
-                    km[h] = sub_push(t.K, t.offa, u);
-                }
+                const uint32_t r = want[h] ? (c > 1 ? __umulhi(q, inv_c) : q) : 0u, u = q - r * c + 1u;
+                const int s = (int)(((r < 8u ? ids_lo >> (4u * r) : ids_hi >> (4u * (r - 8u)))) & 0xfu);
+                const uint64_t K = scen_K(s);
+                const uint32_t offa = scen_meta(s) & 0xffu;
+                sc_of[h] = s;
+                km[h] = want[h] ? sub_push(K, offa, u) : 0ULL;
             }
             g_lookup_n<3>(g, set, km, want, hit);
 #pragma unroll
             for (int h = 0; h < 3; h++)
                 if (want[h] && !hit[h]) bad |= 1u << sc_of[h];
-        } else {
-            for (uint32_t q0 = 0; q0 < Q; q0 += 8) {
-                const uint32_t q = q0 + (uint32_t)g.gl;
-                if (q < Q) {
-                    const uint32_t r = q / c, u = q - r * c + 1u;
-                    const int s = (int)__fns(cand, 0u, (int)r + 1);
-                    const Scen t = scen_two(s, K0, sublen, sb, N0, N1, N2, N0p, mask);
-                    if (!g_lookup(g, set, sub_push(t.K, t.offa, u))) bad |= 1u << s;
-                }
-            }
         }
         cand &= ~g_or(g, bad);
         if (cand == 0) return res;
-        // round 3c, only on a tie: one_more of the tied scenarios
+        // round 3c, only on a tie: one_more of the tied scenarios, asked by their owners
         if (__popc(cand) > 1) {
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 const int s = g.gl + 8 * h;
                 bool m = false;
                 if (s < NS && ((cand >> s) & 1u)) {
-                    const Scen t = scen_two(s, K0, sublen, sb, N0, N1, N2, N0p, mask);
-                    if (sublen > c + t.offc + 1) {
+                    const uint32_t offc = (myMeta[h] >> 8) & 0xffu, n_emit = (myMeta[h] >> 16) & 0xffu, codes = myMeta[h] >> 24;
+                    if (sublen > c + offc + 1) {
                         uint64_t km = K0 >> 2;
-                        for (int e = (int)t.n_emit - 1; e >= 0; e--) km = push(km, (t.codes >> (2 * e)) & 3u, mask);
-                        m = g_lookup(g, set, sub_push(km, t.offc, c + 1));
+                        for (int e = (int)n_emit - 1; e >= 0; e--) km = push(km, (codes >> (2 * e)) & 3u, mask);
+                        m = g_lookup(g, set, sub_push(km, offc, c + 1));
                     }
                 }
                 more |= g_ballot(g, m) << (8 * h);
@@ -1691,7 +1716,15 @@ __device__ __forceinline__ Corr g_exist_correct_error(G8 &g, const SolidView &se
             cand &= more;
             if (__popc(cand) != 1) return res;
         }
-        win = scen_two(__ffs(cand) - 1, K0, sublen, sb, N0, N1, N2, N0p, mask);
+        {
+            const uint32_t meta = scen_meta(__ffs(cand) - 1);
+            win.valid = true;
+            win.K = 0;
+            win.offa = meta & 0xffu;
+            win.offc = (meta >> 8) & 0xffu;
+            win.n_emit = (meta >> 16) & 0xffu;
+            win.codes = meta >> 24;
+        }
     }
     res.some = true;
     res.n_emit = win.n_emit;
@@ -1700,7 +1733,7 @@ __device__ __forceinline__ Corr g_exist_correct_error(G8 &g, const SolidView &se
     return res;
 }
 
-template <int METHOD, int KT>
+template <int METHOD, int KT, bool DIRECT>
 __global__ void __launch_bounds__(SCAN_WARPS_PER_BLOCK * 32, BRGPU_SCAN8_MINB)
     scan_spec8_kernel(const uint8_t *__restrict__ in, const uint32_t *__restrict__ len_in,
                       const uint64_t *__restrict__ slot_off, const uint32_t *__restrict__ bitmap,
@@ -1710,6 +1743,11 @@ __global__ void __launch_bounds__(SCAN_WARPS_PER_BLOCK * 32, BRGPU_SCAN8_MINB)
     constexpr int NS = METHOD == BRGPU_ONE ? 3 : 13;
     if (KT) p.k = KT;
     set.k = p.k;
+    if (DIRECT) {
+        set.hash = nullptr;
+        set.summary = nullptr;
+        __builtin_assume(set.dir != nullptr);
+    }
     const uint32_t k = (uint32_t)p.k, c = (uint32_t)p.confirm;
     G8 g;
     g.gl = threadIdx.x & 7;
@@ -1948,19 +1986,33 @@ template <int M, int KT> static void launch_scan_method(const ScanArgs &a) {
         // the same scheme measured slower than a warp per segment (its rounds are already lane-filling:
         // 2.37 vs 1.72 ms), so it is off unless asked for (ctx option "scan_mode": A/B runs, tests).
         const bool force_warp = ctx->opt_scan_mode == 1, force_groups = ctx->opt_scan_mode == 2;
+        // the specialised kernels exist for the methods and the k of the headline configs; others share the general one
+        const bool direct = a.sv.dir != nullptr && a.sv.hash == nullptr && KT == 17 && (M == BRGPU_ONE || M == BRGPU_TWO);
         if ((M == BRGPU_ONE && !force_warp) || (M == BRGPU_TWO && force_groups)) {
             // four segments per warp: a quarter of the warps for the same number of segments in flight
             constexpr int MG = (M == BRGPU_ONE || M == BRGPU_TWO) ? M : BRGPU_ONE;
             const uint64_t groups = scan_max_segments(L);
-            scan_spec8_kernel<MG, KT><<<grid_for_warps((uint64_t)occupancy_warps(ctx, scan_spec8_kernel<MG, KT>), (groups + 3) / 4),
-                                        threads, 0, ctx->stream>>>(a.d_in, a.d_len_in, L.d_slot_off, a.d_bitmap, w.d_seg_first,
-                                                                   (uint32_t)L.n, w.d_seg_out, (SegRec *)w.d_seg_recs,
-                                                                   ctx->d_flags, a.sv, a.p, gc);
+            const unsigned grid = grid_for_warps((uint64_t)occupancy_warps(ctx, scan_spec8_kernel<MG, KT, false>), (groups + 3) / 4);
+            if (direct)
+                scan_spec8_kernel<MG, KT, true><<<grid, threads, 0, ctx->stream>>>(a.d_in, a.d_len_in, L.d_slot_off, a.d_bitmap,
+                                                                                w.d_seg_first, (uint32_t)L.n, w.d_seg_out,
+                                                                                (SegRec *)w.d_seg_recs, ctx->d_flags, a.sv, a.p, gc);
+            else
+                scan_spec8_kernel<MG, KT, false><<<grid, threads, 0, ctx->stream>>>(a.d_in, a.d_len_in, L.d_slot_off, a.d_bitmap,
+                                                                                 w.d_seg_first, (uint32_t)L.n, w.d_seg_out,
+                                                                                 (SegRec *)w.d_seg_recs, ctx->d_flags, a.sv, a.p, gc);
         } else {
-            scan_spec_kernel<M, KT><<<grid_for_warps((uint64_t)occupancy_warps(ctx, scan_spec_kernel<M, KT>), scan_max_segments(L)),
-                                      threads, 0, ctx->stream>>>(a.d_in, a.d_len_in, L.d_slot_off, a.d_bitmap, w.d_seg_first,
-                                                                 (uint32_t)L.n, w.d_seg_out, (SegRec *)w.d_seg_recs,
-                                                                 ctx->d_flags, a.sv, a.p, a.d_scratch, a.scratch_per_warp, gc);
+            const unsigned grid = grid_for_warps((uint64_t)occupancy_warps(ctx, scan_spec_kernel<M, KT, false>), scan_max_segments(L));
+            if (direct)
+                scan_spec_kernel<M, KT, true><<<grid, threads, 0, ctx->stream>>>(a.d_in, a.d_len_in, L.d_slot_off, a.d_bitmap,
+                                                                              w.d_seg_first, (uint32_t)L.n, w.d_seg_out,
+                                                                              (SegRec *)w.d_seg_recs, ctx->d_flags, a.sv, a.p,
+                                                                              a.d_scratch, a.scratch_per_warp, gc);
+            else
+                scan_spec_kernel<M, KT, false><<<grid, threads, 0, ctx->stream>>>(a.d_in, a.d_len_in, L.d_slot_off, a.d_bitmap,
+                                                                               w.d_seg_first, (uint32_t)L.n, w.d_seg_out,
+                                                                               (SegRec *)w.d_seg_recs, ctx->d_flags, a.sv, a.p,
+                                                                               a.d_scratch, a.scratch_per_warp, gc);
         }
     }
     SegCopy *d_copies = reinterpret_cast<SegCopy *>((uint8_t *)w.d_seg_recs + scan_max_segments(L) * sizeof(SegRec));
