@@ -57,6 +57,8 @@ METRIC = "corrected bases/sec (count + threshold + correct, whole pipeline)"
 UNIT = "bases/s"
 CONFIG3 = {"genome": 100_000_000, "coverage": 50, "error": 0.12}  # BASELINE.json configs[3]
 CONFIG2_METHODS = ["graph", "greedy", "gap_size"]                  # BASELINE.json configs[2]
+CONFIG4 = {"genome": 1_000_000_000, "coverage": 30, "error": 0.10}  # BASELINE.json configs[4] (8 GPUs)
+CHUNK_TEMPLATE_BASES = 1_300_000_000  # a rank's shard is held in chunks of at most this many bases (u32 slot cursors)
 
 
 def load_synth():
@@ -81,13 +83,20 @@ def headline_descriptors(synth, n_gpus, rank, genome_per_gpu):
             "strand": strand, "thr": synth.error_thresholds(ERROR)}
 
 
-def config3_descriptors(synth, n_gpus, rank):
-    """One 100 Mb genome, 50x, 12 %: the read list is global, rank r takes a contiguous range of it."""
-    start, tlen, strand = synth.read_descriptors(CONFIG3["genome"], CONFIG3["coverage"], seed=READ_SEED)
+def sharded_descriptors(synth, cfg, n_gpus, rank):
+    """One genome, one global read list (configs[3]: 100 Mb, 50x, 12 %; configs[4]: 1 Gb, 30x, 10 %): rank r
+    takes a contiguous range of the list, balanced by bases."""
+    start, tlen, strand = synth.read_descriptors(cfg["genome"], cfg["coverage"], seed=READ_SEED)
     lo, hi = synth.shard_descriptors(tlen, n_gpus, rank)
     return {"genome_seed": GENOME_SEED, "read_seed": READ_SEED, "first": lo, "start": start[lo:hi], "tlen": tlen[lo:hi],
-            "strand": strand[lo:hi], "thr": synth.error_thresholds(CONFIG3["error"]), "n_reads_total": int(tlen.size),
+            "strand": strand[lo:hi], "thr": synth.error_thresholds(cfg["error"]), "n_reads_total": int(tlen.size),
             "template_bases_total": int(tlen.astype(np.int64).sum())}
+
+
+def chunk_cuts(tlen, n_chunks):
+    """Read-index cuts that split a shard into n_chunks pieces of about equal bases."""
+    cs = np.concatenate([[0], np.cumsum(tlen.astype(np.int64))])
+    return [int(np.searchsorted(cs, cs[-1] * j // n_chunks, side="left")) for j in range(n_chunks)] + [int(tlen.size)]
 
 
 def host_cores():
@@ -361,17 +370,33 @@ def run_ours(args, world, rank, local_rank):
         return all_max(a.elapsed_time(b))
 
     def build_set(reads):
+        """reads: one device-resident chunk, or the list of chunks a large shard is held in"""
         if world == 1:
+            if isinstance(reads, list):
+                return br_b200.Pcon.from_reads(ctx, reads[0], K, abundance=ABUNDANCE) if len(reads) == 1 else \
+                    br_b200.Pcon.from_chunks(ctx, reads, K, abundance=ABUNDANCE)
             return br_b200.Pcon.from_reads(ctx, reads, K, abundance=ABUNDANCE)
         return bdist.build_set_sharded(bdist.GpuOps(ctx, reads), K, abundance=ABUNDANCE)
 
     class Workload:
         """Device-resident reads of one config + the pinned host buffers of its e2e steps."""
 
-        def __init__(self, desc):
+        def __init__(self, desc, n_chunks=1):
             self.desc = desc
+            if n_chunks > 1:  # a shard too large for one chunk: device-resident only (no host copy, no e2e)
+                cuts = chunk_cuts(desc["tlen"], n_chunks)
+                self.chunks = [br_b200.Reads.synth(ctx, desc["genome_seed"], desc["read_seed"], desc["first"] + a,
+                                                   desc["start"][a:b], desc["tlen"][a:b], desc["strand"][a:b], desc["thr"])
+                               for a, b in zip(cuts[:-1], cuts[1:])]
+                self.dev_reads = self.chunks
+                self.n_reads = sum(len(c) for c in self.chunks)
+                self.n_bases = sum(int(c.bases) for c in self.chunks)
+                self.n_kmers = self.n_bases - (K - 1) * self.n_reads  # every synthetic read is longer than k
+                self.h_seq = None
+                return
             self.dev_reads = br_b200.Reads.synth(ctx, desc["genome_seed"], desc["read_seed"], desc["first"], desc["start"],
                                                  desc["tlen"], desc["strand"], desc["thr"])
+            self.chunks = [self.dev_reads]
             self.n_reads = len(self.dev_reads)
             self.n_bases = int(self.dev_reads.bases)
             self.h_seq = torch.empty(max(1, self.n_bases), dtype=torch.uint8).pin_memory()
@@ -400,12 +425,26 @@ def run_ours(args, world, rank, local_rank):
             return self.h_seq.numpy()[: self.n_bases], self.h_off.numpy().view(np.uint64)
 
         def free(self):
-            self.dev_reads.free()
+            for c in self.chunks:
+                c.free()
             self.h_seq = self.h_off = self.out_bufs = self.h_packed = self.out_packed = None
 
     def step_device(wl, methods, keep=False):
         solid = build_set(wl.dev_reads)
-        out = br_b200.correct_reads(br_b200.build_methods(methods, solid, CONFIRM, MAX_SEARCH), wl.dev_reads)
+        m = br_b200.build_methods(methods, solid, CONFIRM, MAX_SEARCH)
+        if len(wl.chunks) > 1:  # chunk after chunk against the same replicated set
+            outs = []
+            for c in wl.chunks:
+                o = br_b200.correct_reads(m, c)
+                if keep:
+                    outs.append(o)
+                else:
+                    o.free()
+            if keep:
+                return solid, outs
+            solid.free()
+            return None
+        out = br_b200.correct_reads(m, wl.dev_reads)
         if keep:
             return solid, out
         out.free()
@@ -564,19 +603,25 @@ def run_ours(args, world, rank, local_rank):
                                                  workload_name(1, args.genome_per_gpu, CONFIG2_METHODS), "weak", world)
             else:
                 wl.free()
-                wl3 = Workload(config3_descriptors(synth, world, rank))
-                steps3, warm3 = 2, 1
-                m3 = measure(wl3, METHODS, steps3, warm3, e2e_warm_extra=2)
-                total3 = all_sum(wl3.n_bases)
-                name3 = (f"synthetic {CONFIG3['genome'] / 1e6:.0f} Mb genome (seed {GENOME_SEED}), {CONFIG3['coverage']}x ONT-like "
-                         f"reads (seed {READ_SEED}), {int(CONFIG3['error'] * 100)}% error, k={K}, -a {ABUNDANCE}, methods "
-                         f"{'+'.join(METHODS)}, confirm {CONFIRM}, reversed pass on; reads sharded over {world} GPUs")
-                extra["configs[3]"] = leg_record(m3, wl3, total3, steps3, warm3, table, hbm_peak, sm_max_mhz, l2_gather, name3,
-                                                 "strong", world)
-                if not args.no_parity:
-                    extra["configs[3]"]["parity_check"] = parity_check(args, ctx, wl3, world, rank, tdist, dev, step_device,
-                                                                        all_and, single_gpu_rebuild=False)
-                wl3.free()
+                legs = [("configs[3]", CONFIG3)] + ([("configs[4]", CONFIG4)] if world == 8 and not args.no_config4 else [])
+                for leg, cfg in legs:
+                    desc = sharded_descriptors(synth, cfg, world, rank)
+                    shard_bases = int(desc["tlen"].astype(np.int64).sum())
+                    n_chunks = -(-shard_bases // args.chunk_template_bases)
+                    wlx = Workload(desc, n_chunks=n_chunks)
+                    stepsx, warmx = 2, 1
+                    mx = measure(wlx, METHODS, stepsx, warmx, want_e2e=n_chunks == 1, e2e_warm_extra=2)
+                    totalx = all_sum(wlx.n_bases)
+                    namex = (f"synthetic {cfg['genome'] / 1e6:.0f} Mb genome (seed {GENOME_SEED}), {cfg['coverage']}x ONT-like "
+                             f"reads (seed {READ_SEED}), {int(cfg['error'] * 100)}% error, k={K}, -a {ABUNDANCE}, methods "
+                             f"{'+'.join(METHODS)}, confirm {CONFIRM}, reversed pass on; reads sharded over {world} GPUs"
+                             + (f", {n_chunks} chunks per GPU, generated on the device" if n_chunks > 1 else ""))
+                    extra[leg] = leg_record(mx, wlx, totalx, stepsx, warmx, table, hbm_peak, sm_max_mhz, l2_gather, namex,
+                                            "strong", world)
+                    if not args.no_parity:
+                        extra[leg]["parity_check"] = parity_check(args, ctx, wlx, world, rank, tdist, dev, step_device,
+                                                                  all_and, single_gpu_rebuild=False)
+                    wlx.free()
 
     if rank != 0:
         if tdist is not None:
@@ -708,8 +753,14 @@ def parity_check(args, ctx, wl, world, rank, tdist, dev, step_device, all_and, s
         res["equals_single_gpu_table_path" if world > 1 else "bitfield_equals_table_path"] = bool(same)
         ref.free()
         c.free()
-    # oracle replay of a read sample
-    seq, off = wl.seq_off()
+    # oracle replay of a read sample (a chunked shard: of its first chunk)
+    if isinstance(out, list):
+        for o_ in out[1:]:
+            o_.free()
+        out = out[0]
+        seq, off = wl.chunks[0].download()
+    else:
+        seq, off = wl.seq_off()
     n = off.size - 1
     ids = np.sort(np.random.default_rng(7 + rank).choice(n, size=min(sample, n), replace=False))
     got, got_off = out.download()
@@ -750,6 +801,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the untimed parity checks on the benched data")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra legs (configs[2] at N = 1, configs[3] at N >= 2)")
+    ap.add_argument("--no-config4", action="store_true", help="at N = 8: skip the configs[4] leg (1 Gb genome, 30x)")
+    ap.add_argument("--chunk-template-bases", type=int, default=CHUNK_TEMPLATE_BASES,
+                    help="bases per device-resident chunk of a rank's shard in the sharded legs (testing the chunked path)")
     ap.add_argument("--no-e2e-pipeline", action="store_true", help="e2e steps one at a time")
     ap.add_argument("--e2e-mode", choices=["stream", "serial"], default="stream",
                     help="`stream` = copies of the neighbouring steps on the context's copy stream (default); "

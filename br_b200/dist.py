@@ -133,7 +133,10 @@ class GpuOps:
         import torch.distributed as dist
 
         self.torch, self.dist = torch, dist
-        self.ctx, self.reads, self.group = ctx, reads, group
+        # `reads`: this rank's shard as one device-resident chunk or as a list of chunks (a shard larger than
+        # 2^32 slot bytes is held in several; every rank must hold the same number of chunks)
+        self.chunks = list(reads) if isinstance(reads, (list, tuple)) else [reads]
+        self.ctx, self.reads, self.group = ctx, self.chunks[0], group
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.counter = None
         self.kmers = None
@@ -148,9 +151,12 @@ class GpuOps:
         from .set import Pcon
 
         self.k = k
-        h = C.c_void_p()
-        check(lib.brgpu_kmers_create(self.ctx._h, k, self.reads._h, C.byref(h)), self.ctx._h)
-        self.kmers = h
+        self.parts = []
+        for ch in self.chunks:
+            h = C.c_void_p()
+            check(lib.brgpu_kmers_create(self.ctx._h, k, ch._h, C.byref(h)), self.ctx._h)
+            self.parts.append(h)
+        self.kmers = self.parts[0]
         s = C.c_void_p()
         check(lib.brgpu_set_new_sliced(self.ctx._h, k, C.byref(s)), self.ctx._h)
         self.set = Pcon(self.ctx, s)
@@ -161,19 +167,21 @@ class GpuOps:
         contiguous piece of this rank's residues it needs).  The offsets are picked out of the
         library's offset array on the device: no host round trip before the collective."""
         torch = self.torch
-        h = (C.c_uint8 * 128)()
-        check(lib.brgpu_kmers_ipc_export(self.kmers, h), self.ctx._h)
         n_buckets = lib.brgpu_kmers_buckets(self.kmers)
         cuts = [bucket_bounds(n_buckets, self.world, r)[0] for r in range(self.world)] + [n_buckets]
-        base = torch.as_tensor(_CudaArray(lib.brgpu_kmers_offsets_ptr(self.kmers), (n_buckets + 1) * 8, "<i8"), device=self.dev)
         idx = self._cut_index(tuple(cuts))
-        mine = torch.empty(16 + len(cuts), dtype=torch.int64, device=self.dev)
-        mine[:16].copy_(torch.frombuffer(bytearray(bytes(h)), dtype=torch.int64), non_blocking=True)
-        torch.index_select(base, 0, idx, out=mine[16:])
+        per = 16 + len(cuts)  # int64 words per partition: 128 B of handles + the offsets at the cuts
+        mine = torch.empty(per * len(self.parts), dtype=torch.int64, device=self.dev)
+        for j, part in enumerate(self.parts):
+            h = (C.c_uint8 * 128)()
+            check(lib.brgpu_kmers_ipc_export(part, h), self.ctx._h)
+            base = torch.as_tensor(_CudaArray(lib.brgpu_kmers_offsets_ptr(part), (n_buckets + 1) * 8, "<i8"), device=self.dev)
+            mine[j * per : j * per + 16].copy_(torch.frombuffer(bytearray(bytes(h)), dtype=torch.int64), non_blocking=True)
+            torch.index_select(base, 0, idx, out=mine[j * per + 16 : (j + 1) * per])
         allh = torch.empty(self.world * mine.numel(), dtype=torch.int64, device=self.dev)
-        self.dist.all_gather_into_tensor(allh, mine, group=self.group)
-        rows = allh.cpu().numpy().reshape(self.world, -1)  # the step's one host round trip
-        return [rows[r].tobytes() for r in range(self.world)]
+        self.dist.all_gather_into_tensor(allh, mine, group=self.group)  # every rank holds the same number of chunks
+        rows = allh.cpu().numpy().reshape(self.world, len(self.parts), per)  # the step's one host round trip
+        return [[rows[r, j].tobytes() for j in range(len(self.parts))] for r in range(self.world)]
 
     def _cut_index(self, cuts):
         cache = self.ctx.__dict__.setdefault("_cut_index_cache", {})
@@ -198,14 +206,15 @@ class GpuOps:
 
     def open_peers(self, handles):
         self._peer_res, self._peer_off, self._peer_first, self._peer_last = [], [], [], []
-        for r, hb in enumerate(handles):
+        for r, parts in enumerate(handles):
             if r == self.rank:
                 continue
-            self._peer_res.append(self._ipc_open_cached(hb[:64]))
-            self._peer_off.append(self._ipc_open_cached(hb[64:128]))
-            cuts = np.frombuffer(hb[128:], dtype=np.uint64)  # peer r's residue offsets at the rank boundaries
-            self._peer_first.append(int(cuts[self.rank]))
-            self._peer_last.append(int(cuts[self.rank + 1]))
+            for hb in (parts if isinstance(parts, list) else [parts]):  # one entry per chunk of peer r
+                self._peer_res.append(self._ipc_open_cached(hb[:64]))
+                self._peer_off.append(self._ipc_open_cached(hb[64:128]))
+                cuts = np.frombuffer(hb[128:], dtype=np.uint64)  # the partition's residue offsets at the rank boundaries
+                self._peer_first.append(int(cuts[self.rank]))
+                self._peer_last.append(int(cuts[self.rank + 1]))
 
     def count_range(self, b0, b1, abundance):
         n = len(self._peer_res)
@@ -215,10 +224,11 @@ class GpuOps:
         last = (C.c_uint64 * max(1, n))(*self._peer_last)
         # the spectrum comes back to the host only when the threshold is derived from it
         hist = np.zeros(256, dtype=np.uint64) if abundance is None else None
-        check(lib.brgpu_kmers_count_range_staged(self.kmers, res, off, first, last, n, b0, b1,
-                                                 -1 if abundance is None else int(abundance),
-                                                 None if abundance is None else self.set._h,
-                                                 None if hist is None else hist.ctypes.data_as(C.c_void_p)), self.ctx._h)
+        local = (C.c_void_p * len(self.parts))(*[p.value for p in self.parts])
+        check(lib.brgpu_kmers_count_parts(self.ctx._h, local, len(self.parts), res, off, first, last, n, b0, b1,
+                                          -1 if abundance is None else int(abundance),
+                                          None if abundance is None else self.set._h,
+                                          None if hist is None else hist.ctypes.data_as(C.c_void_p)), self.ctx._h)
         return hist
 
     def count_local(self, k):
@@ -226,7 +236,8 @@ class GpuOps:
 
         self.k = k
         self.counter = Counter(self.ctx, k)
-        self.counter.count(self.reads)
+        for ch in self.chunks:
+            self.counter.count(ch)
         self.set = Pcon.new(self.ctx, k)
 
     def exchange_handles(self):
@@ -314,8 +325,9 @@ class GpuOps:
         if self.counter is not None:
             self.counter.free()
         if self.kmers is not None:
-            lib.brgpu_kmers_free(self.kmers)
-            self.kmers = None
+            for part in self.parts:
+                lib.brgpu_kmers_free(part)
+            self.parts, self.kmers = [], None
             # bitfield and summary are whole: build the lookup structures without re-reading the bitfield
             check(lib.brgpu_set_commit_slices(self.set._h, int(getattr(self, "_summary_gathered", False))), self.ctx._h)
         return self.set

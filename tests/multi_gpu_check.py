@@ -50,6 +50,19 @@ def main():
             print(f"rank {rank}/{world} k={k} {kwargs}: abundance {sharded.abundance}, bitfield identical: {same}, "
                   f"corrected shard identical: {same_corr} ({hi - lo} reads)", flush=True)
             ok = ok and same and same_corr
+        # a shard held in three chunks (how a shard larger than 2^32 slot bytes is processed): every chunk is
+        # partitioned on its own, the owned bucket range is counted over all local and all peer partitions
+        cuts = [0, (hi - lo) // 5, (hi - lo) // 2, hi - lo]
+        for k, kwargs in ((17, {"abundance": 2}), (15, {"abundance_selection": "first-minimum"})):
+            chunks = [br_b200.Reads.upload(ctx, my_seq, my_off[a : b + 1]) for a, b in zip(cuts[:-1], cuts[1:])]
+            sharded = bdist.build_set_sharded(bdist.GpuOps(ctx, chunks), k, **kwargs)
+            single = br_b200.Pcon.from_reads(ctx, (seq, off), k, **kwargs)
+            same = np.array_equal(sharded.bitfield(), single.bitfield()) and sharded.abundance == single.abundance
+            a = np.concatenate([br_b200.correct_reads(br_b200.build_methods(["one", "two"], sharded), c).download()[0] for c in chunks])
+            b, _ = br_b200.correct_batch(br_b200.build_methods(["one", "two"], single), my_seq, my_off)
+            same_corr = np.array_equal(a, b)
+            print(f"rank {rank}/{world} k={k} {kwargs} 3 chunks per rank: bitfield identical: {same}, corrected shard identical: {same_corr}", flush=True)
+            ok = ok and same and same_corr
     t = torch.tensor([1 if ok else 0], device=f"cuda:{local}")
     tdist.all_reduce(t, op=tdist.ReduceOp.MIN)
     tdist.barrier()
