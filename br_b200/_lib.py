@@ -56,6 +56,7 @@ SIGNATURES = {
     "brgpu_counts_spectrum": (C.c_int, [vp, vp]),
     "brgpu_spectrum_first_minimum": (C.c_int, [vp]),
     "brgpu_spectrum_threshold": (C.c_int, [vp, C.c_int, C.c_double]),
+    "brgpu_counts_upload": (C.c_int, [vp, vp, u64]),
     "brgpu_counts_download": (C.c_int, [vp, vp, u64]),
     "brgpu_counts_device_ptr": (vp, [vp]),
     "brgpu_counts_len": (u64, [vp]),

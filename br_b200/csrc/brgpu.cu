@@ -1015,6 +1015,18 @@ extern "C" int brgpu_spectrum_threshold(const uint64_t hist[256], int selection,
     return -1;
 }
 
+// pcon Counter::from_stream's payload (src/main.rs:59-70): the raw table of a count file, already read and
+// decompressed by the host, replaces the table's content
+extern "C" int brgpu_counts_upload(brgpu_counts *c, const uint8_t *counts_host, uint64_t n) {
+    if (!c || !counts_host) return BRGPU_E_INVALID;
+    brgpu_ctx *ctx = c->ctx;
+    if (n != c->n) return fail(ctx, BRGPU_E_INVALID, "n must be 2^(2k-1)");
+    cudaSetDevice(ctx->device);
+    CK(cudaMemcpyAsync(c->d_counts, counts_host, n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return BRGPU_OK;
+}
+
 extern "C" int brgpu_counts_download(brgpu_counts *c, uint8_t *out_host, uint64_t n) {
     if (!c || !out_host) return BRGPU_E_INVALID;
     brgpu_ctx *ctx = c->ctx;

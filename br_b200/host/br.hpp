@@ -304,6 +304,107 @@ class Pcon : public DeviceSet {
         return std::make_unique<Pcon>(ctx, h);
     }
 
+    // The `count` sub-command (src/main.rs:59-70): pcon Counter::from_stream + count2solid.  pcon is not vendored
+    // and no fixture of the reference holds a count file, so the container is restated as recalled from pcon
+    // @0184ae77 (PARITY UNPINNED): one raw byte k, then the 2^(2k-1) u8 counters as a (multi-member) gzip stream;
+    // a file that is gzip as a whole (niffler sniffing, src/cli.rs:400-420) is unwrapped first, and raw
+    // counters after the k byte are accepted too.
+    static std::unique_ptr<Pcon> from_pcon_count(const Context &ctx, const std::string &path, int abundance,
+                                                 AbundanceSelection selection, double percent = 0.0) {
+        std::vector<uint8_t> file = read_maybe_gzip(path);
+        if (file.empty()) throw std::runtime_error("empty count file " + path);
+        const int k = file[0];
+        if (k < 3 || k > 19 || !(k & 1)) throw std::runtime_error("count file: k must be odd and in 3..=19");
+        const uint64_t n = 1ULL << (2 * k - 1);
+        std::vector<uint8_t> counts;
+        if (file.size() >= 3 && file[1] == 0x1f && file[2] == 0x8b)
+            counts = gunzip_members(file.data() + 1, file.size() - 1, n);
+        else
+            counts.assign(file.begin() + 1, file.end());
+        if (counts.size() != n) throw std::runtime_error("count file: expected 2^(2k-1) counters");
+        int sel = BRGPU_ABUNDANCE_EXPLICIT;
+        if (abundance < 0) {
+            switch (selection) {
+            case AbundanceSelection::FirstMinimum: sel = BRGPU_ABUNDANCE_FIRST_MINIMUM; break;
+            case AbundanceSelection::Rarefaction: sel = BRGPU_ABUNDANCE_RAREFACTION; break;
+            case AbundanceSelection::PercentMost: sel = BRGPU_ABUNDANCE_PERCENT_AT_MOST; break;
+            case AbundanceSelection::PercentLeast: sel = BRGPU_ABUNDANCE_PERCENT_AT_LEAST; break;
+            case AbundanceSelection::None: break;
+            }
+        }
+        brgpu_counts *c = nullptr;
+        brgpu_set *h = nullptr;
+        ctx.check(brgpu_counts_create(ctx.handle(), k, &c));
+        try {
+            ctx.check(brgpu_counts_upload(c, counts.data(), n));
+            if (abundance < 0) { // count2solid's match (src/main.rs:95-110)
+                if (sel == BRGPU_ABUNDANCE_EXPLICIT) ctx.check(BRGPU_E_NEED_ABUNDANCE);
+                uint64_t hist[256];
+                ctx.check(brgpu_counts_spectrum(c, hist));
+                abundance = brgpu_spectrum_threshold(hist, sel, percent);
+                if (abundance < 0) ctx.check(BRGPU_E_NO_THRESHOLD);
+            }
+            ctx.check(brgpu_set_from_counts(c, abundance, &h));
+        } catch (...) {
+            brgpu_counts_free(c);
+            throw;
+        }
+        brgpu_counts_free(c);
+        return std::make_unique<Pcon>(ctx, h);
+    }
+
+    // the whole file; gzip as a whole is unwrapped (gzread reads plain files transparently)
+    static std::vector<uint8_t> read_maybe_gzip(const std::string &path) {
+        gzFile gz = gzopen(path.c_str(), "rb");
+        if (!gz) throw std::runtime_error("can't open " + path);
+        std::vector<uint8_t> data, buf(1u << 20);
+        int n;
+        while ((n = gzread(gz, buf.data(), (unsigned)buf.size())) > 0) data.insert(data.end(), buf.begin(), buf.begin() + n);
+        gzclose(gz);
+        if (n < 0) throw std::runtime_error("read error in " + path);
+        return data;
+    }
+    // concatenated gzip members -> at most `limit` bytes (flate2's MultiGzDecoder)
+    static std::vector<uint8_t> gunzip_members(const uint8_t *src, size_t len, uint64_t limit) {
+        std::vector<uint8_t> out;
+        out.reserve((size_t)limit);
+        z_stream z;
+        std::memset(&z, 0, sizeof(z));
+        if (inflateInit2(&z, 15 + 16) != Z_OK) throw std::runtime_error("zlib init failed");
+        z.next_in = const_cast<uint8_t *>(src);
+        z.avail_in = (uInt)std::min<size_t>(len, 0xffffffffu);
+        size_t consumed_base = 0;
+        std::vector<uint8_t> buf(1u << 20);
+        for (;;) {
+            z.next_out = buf.data();
+            z.avail_out = (uInt)buf.size();
+            int rc = inflate(&z, Z_NO_FLUSH);
+            out.insert(out.end(), buf.data(), buf.data() + (buf.size() - z.avail_out));
+            if (out.size() > limit) break;
+            if (rc == Z_STREAM_END) { // next member, if any
+                const size_t used = consumed_base + (z.next_in - (src + consumed_base));
+                if (used >= len) break;
+                consumed_base = used;
+                inflateReset(&z);
+                z.next_in = const_cast<uint8_t *>(src + used);
+                z.avail_in = (uInt)std::min<size_t>(len - used, 0xffffffffu);
+                continue;
+            }
+            if (rc == Z_BUF_ERROR && z.avail_in == 0) {
+                const size_t used = (size_t)(z.next_in - src);
+                if (used >= len) break;
+                z.avail_in = (uInt)std::min<size_t>(len - used, 0xffffffffu);
+                continue;
+            }
+            if (rc != Z_OK) {
+                inflateEnd(&z);
+                throw std::runtime_error("count file: corrupt gzip stream");
+            }
+        }
+        inflateEnd(&z);
+        return out;
+    }
+
     // Pcon::get (src/set/pcon.rs:189-191), forward k-mers accepted.  Served from a host mirror of
     // the bitfield (exported once): a GPU round trip per k-mer would be useless.  Batches go
     // through get_batch.

@@ -158,6 +158,14 @@ std::unique_ptr<br::set::DeviceSet> build_set(const br::Context &ctx, const Args
         // count_fasta(inputs, 8192) streams the records (src/main.rs:74): so does this, 1 Gbase per chunk
         return Pcon::from_count_stream(ctx, a.sub_inputs, a.k, a.abundance, sel, a.percent, a.chunk_bases);
     }
+    if (a.sub == "count") { // src/main.rs:59-70 (pcon's count-file container: restated as recalled, see Pcon::from_pcon_count)
+        AbundanceSelection sel = AbundanceSelection::None;
+        if (a.selection == "first-minimum") sel = AbundanceSelection::FirstMinimum;
+        else if (a.selection == "rarefaction") sel = AbundanceSelection::Rarefaction;
+        else if (a.selection == "percent-most") sel = AbundanceSelection::PercentMost;
+        else if (a.selection == "percent-least") sel = AbundanceSelection::PercentLeast;
+        return Pcon::from_pcon_count(ctx, a.sub_inputs[0], a.abundance, sel, a.percent);
+    }
     if (a.sub == "solid") { // src/main.rs:117-145
         if (a.format == "solid") return Pcon::from_pcon_solid(ctx, a.sub_inputs[0]);
         if (a.format == "fasta") {
@@ -174,7 +182,7 @@ std::unique_ptr<br::set::DeviceSet> build_set(const br::Context &ctx, const Args
         if (a.k < 3 || a.k > 31) throw std::runtime_error("large-kmer: k must be in 3..=31 (k-mers are 2-bit packed in 64 bits)");
         return br::set::Hash::from_fasta(ctx, {a.sub_inputs[0]}, a.k, a.chunk_bases);
     }
-    throw std::runtime_error("sub-command '" + a.sub + "' is not supported by brgpu (pcon's count-file format is not pinned by any fixture)");
+    throw std::runtime_error("sub-command '" + a.sub + "' is not supported by brgpu");
 }
 
 } // namespace

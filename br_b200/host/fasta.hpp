@@ -17,6 +17,7 @@
 #include <new>
 #include <stdexcept>
 #include <algorithm>
+#include <functional>
 #include <string>
 #include <thread>
 #include <vector>
@@ -25,6 +26,12 @@ namespace br {
 namespace fasta {
 
 constexpr size_t LINE_BASES = 80;
+
+// host threads the reader / writer / 2-bit packer fan out over (br's -t sizes a rayon pool, src/main.rs:30-33)
+inline unsigned default_threads() {
+    unsigned h = std::thread::hardware_concurrency();
+    return h == 0 ? 4 : (h > 8 ? 8 : h);
+}
 
 // Growable byte buffer without value initialisation (std::vector<uint8_t>::resize zero-fills, which
 // doubles the memory traffic of a parser that only appends).
@@ -178,10 +185,23 @@ class Reader {
   public:
     // path == "-" or empty: stdin.  gzopen reads plain files transparently.
     explicit Reader(const std::string &path) {
-        if (path.empty() || path == "-")
+        if (path.empty() || path == "-") {
             gz_ = gzdopen(0, "rb");
-        else
+        } else {
+            // an uncompressed file is read in large blocks and parsed by several threads (the reference fans its
+            // records over rayon workers, src/lib.rs:93-128); gzip input and stdin go through zlib's serial stream
+            FILE *f = fopen(path.c_str(), "rb");
+            if (!f) throw std::runtime_error("can't open " + path);
+            unsigned char magic[2] = {0, 0};
+            const size_t got = fread(magic, 1, 2, f);
+            if (!(got == 2 && magic[0] == 0x1f && magic[1] == 0x8b)) {
+                rewind(f);
+                plain_ = f;
+                return;
+            }
+            fclose(f);
             gz_ = gzopen(path.c_str(), "rb");
+        }
         if (!gz_) throw std::runtime_error("can't open " + (path.empty() ? std::string("stdin") : path));
         gzbuffer(gz_, 1u << 20);
         buf_.resize(1u << 22);
@@ -190,11 +210,15 @@ class Reader {
     Reader &operator=(const Reader &) = delete;
     ~Reader() {
         if (gz_) gzclose(gz_);
+        if (plain_) fclose(plain_);
     }
+
+    void set_threads(unsigned t) { threads_ = t ? t : 1; }
 
     // Appends up to max_records records to `out`; returns false once the stream is exhausted
     // (the last call may still have appended records, like populate_buffer's `false`).
     bool read_chunk(Chunk &out, size_t max_records) {
+        if (plain_) return read_chunk_parallel(out, max_records);
         size_t got = 0;
         while (got < max_records) {
             if (!next_record(out)) return false;
@@ -276,10 +300,129 @@ class Reader {
         return true;
     }
 
+    // ---- plain files: block reads + parallel parse ----
+    // raw_[rpos_, rend_) holds file bytes not yet handed out; a record starts at a '>' that begins a line
+    bool refill_raw() {
+        if (reof_) return false;
+        if (rpos_ > 0 && rpos_ == rend_) rpos_ = rend_ = 0;
+        if (rpos_ > (raw_.size() >> 1)) { // compact
+            std::memmove(raw_.data(), raw_.data() + rpos_, rend_ - rpos_);
+            rend_ -= rpos_;
+            rpos_ = 0;
+        }
+        const size_t block = (size_t)1 << 25;
+        if (raw_.size() < rend_ + block) raw_.resize(rend_ + block);
+        const size_t n = fread(raw_.data() + rend_, 1, block, plain_);
+        if (n == 0) {
+            if (ferror(plain_)) throw std::runtime_error("read error in FASTA input");
+            reof_ = true;
+            return false;
+        }
+        rend_ += n;
+        return true;
+    }
+    static void parse_records(const char *base, const std::vector<size_t> &starts, size_t lo, size_t hi, Chunk &dst) {
+        for (size_t r = lo; r < hi; r++) {
+            const char *p = base + starts[r] + 1, *end = base + starts[r + 1]; // after '>'
+            const char *nl = (const char *)memchr(p, '\n', (size_t)(end - p));
+            const char *dend = nl ? nl : end;
+            size_t dl = (size_t)(dend - p);
+            if (dl && p[dl - 1] == '\r') dl--;
+            dst.definitions.emplace_back(p, dl);
+            p = nl ? nl + 1 : end;
+            while (p < end) {
+                nl = (const char *)memchr(p, '\n', (size_t)(end - p));
+                size_t n = nl ? (size_t)(nl - p) : (size_t)(end - p);
+                const char *next = nl ? nl + 1 : end;
+                if (n && p[n - 1] == '\r') n--;
+                dst.seq.append(p, n);
+                p = next;
+            }
+            dst.offsets.push_back(dst.seq.size());
+        }
+    }
+    bool read_chunk_parallel(Chunk &out, size_t max_records) {
+        // record starts inside the buffered bytes; more bytes are read until max_records + 1 starts are known
+        // (the extra one delimits the last record) or the file ends
+        std::vector<size_t> starts;
+        size_t scan = rpos_;
+        bool at_line_start = true; // rpos_ always sits at the start of a line
+        for (;;) {
+            const char *b = raw_.data();
+            while (scan < rend_ && starts.size() <= max_records) {
+                if (at_line_start && b[scan] == '>') starts.push_back(scan);
+                const char *nl = (const char *)memchr(b + scan, '\n', rend_ - scan);
+                if (!nl) {
+                    scan = rend_;
+                    at_line_start = false;
+                    break;
+                }
+                scan = (size_t)(nl - b) + 1;
+                at_line_start = true;
+            }
+            if (starts.size() > max_records) break;
+            const size_t old_pos = rpos_;
+            if (!refill_raw()) break;
+            if (rpos_ != old_pos) { // the buffer was compacted: shift what we know
+                const size_t shift = old_pos - rpos_;
+                for (auto &x : starts) x -= shift;
+                scan -= shift;
+            }
+        }
+        const bool more = starts.size() > max_records; // the (max_records + 1)-th start belongs to the next call
+        const size_t n_rec = more ? max_records : starts.size();
+        const size_t stop = more ? starts[max_records] : rend_;
+        if (n_rec == 0) {
+            rpos_ = stop;
+            return more;
+        }
+        starts.resize(n_rec);
+        starts.push_back(stop);
+        const unsigned T = (stop - starts[0]) > (1u << 22) ? threads_ : 1;
+        if (T < 2) {
+            parse_records(raw_.data(), starts, 0, n_rec, out);
+        } else {
+            std::vector<Chunk> parts(T);
+            std::vector<std::thread> pool;
+            size_t lo = 0;
+            const size_t bytes = stop - starts[0];
+            for (unsigned t = 0; t < T; t++) { // cut by input bytes, at record boundaries
+                size_t hi = lo;
+                const size_t want = starts[0] + bytes / T * (t + 1);
+                while (hi < n_rec && (t + 1 == T || starts[hi + 1] <= want)) hi++;
+                pool.emplace_back(parse_records, raw_.data(), std::cref(starts), lo, hi, std::ref(parts[t]));
+                lo = hi;
+            }
+            for (auto &th : pool) th.join();
+            size_t total = out.seq.size();
+            std::vector<size_t> at(T);
+            for (unsigned t = 0; t < T; t++) {
+                at[t] = total;
+                total += parts[t].seq.size();
+            }
+            out.seq.resize(total);
+            pool.clear();
+            for (unsigned t = 0; t < T; t++)
+                pool.emplace_back([&, t]() { if (parts[t].seq.size()) std::memcpy(out.seq.data() + at[t], parts[t].seq.data(), parts[t].seq.size()); });
+            for (unsigned t = 0; t < T; t++) {
+                for (auto &d : parts[t].definitions) out.definitions.push_back(std::move(d));
+                for (size_t i = 1; i < parts[t].offsets.size(); i++) out.offsets.push_back(at[t] + parts[t].offsets[i]);
+            }
+            for (auto &th : pool) th.join();
+        }
+        rpos_ = stop;
+        return more;
+    }
+
     gzFile gz_ = nullptr;
     std::vector<char> buf_;
     size_t pos_ = 0, end_ = 0;
     bool eof_ = false;
+    FILE *plain_ = nullptr;
+    std::vector<char> raw_;
+    size_t rpos_ = 0, rend_ = 0;
+    bool reof_ = false;
+    unsigned threads_ = default_threads();
 };
 
 class Writer {
@@ -311,28 +454,59 @@ class Writer {
             total += 2 + definitions[i].size() + n + (n + LINE_BASES - 1) / LINE_BASES;
         }
         line_.resize(total);
-        uint8_t *w = line_.data();
+        // every record's place in the output is known up front, so the records are formatted by `threads_`
+        // threads (the reference formats inside its rayon workers too, src/lib.rs:112-127) and leave in one write
+        start_.resize(definitions.size() + 1);
+        size_t at = 0;
         for (size_t i = 0; i < definitions.size(); i++) {
-            *w++ = '>';
-            std::memcpy(w, definitions[i].data(), definitions[i].size());
-            w += definitions[i].size();
-            *w++ = '\n';
-            const uint8_t *s = seq + offsets[i];
+            start_[i] = at;
             const size_t n = (size_t)(offsets[i + 1] - offsets[i]);
-            for (size_t p = 0; p < n; p += LINE_BASES) {
-                const size_t m = n - p < LINE_BASES ? n - p : LINE_BASES;
-                std::memcpy(w, s + p, m);
-                w += m;
+            at += 2 + definitions[i].size() + n + (n + LINE_BASES - 1) / LINE_BASES;
+        }
+        start_[definitions.size()] = at;
+        auto format = [&](size_t lo, size_t hi) {
+            for (size_t i = lo; i < hi; i++) {
+                uint8_t *w = line_.data() + start_[i];
+                *w++ = '>';
+                std::memcpy(w, definitions[i].data(), definitions[i].size());
+                w += definitions[i].size();
                 *w++ = '\n';
+                const uint8_t *s = seq + offsets[i];
+                const size_t n = (size_t)(offsets[i + 1] - offsets[i]);
+                for (size_t p = 0; p < n; p += LINE_BASES) {
+                    const size_t m = n - p < LINE_BASES ? n - p : LINE_BASES;
+                    std::memcpy(w, s + p, m);
+                    w += m;
+                    *w++ = '\n';
+                }
             }
+        };
+        const unsigned T = total > (1u << 22) ? threads_ : 1;
+        if (T < 2) {
+            format(0, definitions.size());
+        } else {
+            std::vector<std::thread> pool;
+            size_t lo = 0;
+            for (unsigned t = 0; t < T; t++) { // cut by output bytes
+                size_t hi = lo;
+                const size_t want = total / T * (t + 1);
+                while (hi < definitions.size() && (t + 1 == T || start_[hi + 1] <= want)) hi++;
+                pool.emplace_back(format, lo, hi);
+                lo = hi;
+            }
+            for (auto &th : pool) th.join();
         }
         if (total && fwrite(line_.data(), 1, total, f_) != total) throw std::runtime_error("write error in FASTA output");
     }
+
+    void set_threads(unsigned t) { threads_ = t ? t : 1; }
 
   private:
     FILE *f_ = nullptr;
     bool own_ = false;
     Bytes line_;
+    std::vector<size_t> start_;
+    unsigned threads_ = default_threads();
 };
 
 } // namespace fasta

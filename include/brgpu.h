@@ -158,6 +158,9 @@ int brgpu_spectrum_first_minimum(const uint64_t hist[256]);
 /* Spectrum::get_threshold(method, percent) for any BRGPU_ABUNDANCE_* method but EXPLICIT
  * (src/main.rs:95-108); -1 for None.  Host arithmetic on the 256 bins the GPU produced. */
 int brgpu_spectrum_threshold(const uint64_t hist[256], int selection, double percent);
+/* Counter::from_stream (src/main.rs:59-70, the `count` sub-command): the raw table of a pcon count file —
+ * the host reads and decompresses the file — replaces the table's content; n must be 2^(2k-1) */
+int brgpu_counts_upload(brgpu_counts *counts, const uint8_t *counts_host, uint64_t n);
 /* Copy the raw table to the host (Counter::raw, src/main.rs:76-78); n must be 2^(2k-1) */
 int brgpu_counts_download(brgpu_counts *counts, uint8_t *out_host, uint64_t n);
 /* device pointer and element count of the table, for multi-GPU merge plumbing */

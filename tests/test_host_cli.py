@@ -347,3 +347,35 @@ def test_both_transports_echo_non_acgt_bytes(tmp_path, oracle, fixture_reads, fi
         assert r.returncode == 0 and r.stderr == b"", r.stderr
         assert_same_records(out, names, exp, exp_off)
     assert (exp[: 0] == exp[: 0]).all() and any(c in exp.tobytes() for c in (b"n", b"N", b"a"))
+
+
+@pytest.mark.gpu
+def test_count_subcommand_reads_a_pcon_count_file(tmp_path, oracle, fixture_reads, fixture_solid_payload):
+    """`count -i FILE -a 2` (src/main.rs:59-70): Counter::from_stream + count2solid.  No reference fixture holds
+    a count file (PARITY UNPINNED for the container; restated as recalled from pcon: one raw byte k, then the
+    counters as a multi-member gzip stream) — the counters come from the oracle's count of the fixture reads, so
+    the set must be the `.solid` fixture and the corrected reads the oracle's; the all-gzip and the raw-counters
+    spellings are accepted too, and first-minimum works on the file's spectrum."""
+    seq, off = fixture_reads
+    c = oracle.Counter(11)
+    c.count(seq, off, threads=8)
+    raw = c.raw().tobytes()
+    members = gzip.compress(raw[: len(raw) // 3]) + gzip.compress(raw[len(raw) // 3 :])  # two gzip members
+    spellings = {"members": bytes([11]) + members, "raw": bytes([11]) + raw, "all_gzip": gzip.compress(bytes([11]) + raw)}
+    names, _, _ = records(GOLDEN / "br_reads.fa.gz")
+    exp, exp_off = oracle_corrected(oracle, fixture_solid_payload, ["one"], seq, off)
+    for name, blob in spellings.items():
+        path = tmp_path / f"{name}.pcon"
+        path.write_bytes(blob)
+        out, solid_out = tmp_path / f"corr_{name}.fa", tmp_path / f"{name}.solid"
+        r = run(["-i", GOLDEN / "br_reads.fa.gz", "-o", out, "-c", "one", "--write-solid", solid_out, "count", "-i", path, "-a", "2"])
+        assert r.returncode == 0 and r.stderr == b"", r.stderr
+        assert gzip.open(solid_out).read() == fixture_solid_payload
+        assert_same_records(out, names, exp, exp_off)
+    r = run(["-i", GOLDEN / "br_reads.fa.gz", "-o", tmp_path / "fm.fa", "-c", "one", "--write-solid", tmp_path / "fm.solid",
+             "count", "-i", tmp_path / "members.pcon", "first-minimum"])
+    assert r.returncode == 0 and r.stderr == b"", r.stderr
+    thr = oracle.Counter.first_minimum(c.spectrum(8))
+    assert np.array_equal(np.frombuffer(gzip.open(tmp_path / "fm.solid").read()[1:], dtype=np.uint8), c.to_solid(thr, 8).bits())
+    r = run(["-i", GOLDEN / "br_reads.fa.gz", "-o", tmp_path / "x.fa", "count", "-i", tmp_path / "members.pcon"])
+    assert r.returncode == 1 and b"abundance" in r.stderr
