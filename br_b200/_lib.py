@@ -106,6 +106,15 @@ SIGNATURES = {
     "brgpu_kmers_count_parts": (C.c_int, [vp, vp, C.c_int, vp, vp, vp, vp, C.c_int, u64, u64, C.c_int, vp, vp]),
     "brgpu_set_from_kmers": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_double, pvp]),
     "brgpu_kmers_free": (None, [vp]),
+    "brgpu_group_create": (C.c_int, [vp, C.c_int, pvp]),
+    "brgpu_group_destroy": (None, [vp]),
+    "brgpu_group_size": (C.c_int, [vp]),
+    "brgpu_group_ctx": (vp, [vp, C.c_int]),
+    "brgpu_group_last_error": (C.c_char_p, [vp]),
+    "brgpu_group_set_from_reads": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_double, vp, vp]),
+    "brgpu_group_set_from_host_reads": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_double, vp, vp, u64, vp]),
+    "brgpu_group_sets_free": (None, [vp, vp]),
+    "brgpu_group_correct_batch": (C.c_int, [vp, vp, vp, u64, C.c_int, C.c_int, C.c_int, vp, vp, u64, vp, u64, vp, pu64]),
     "brgpu_profile_enable": (C.c_int, [vp, C.c_int]),
     "brgpu_profile_reset": (C.c_int, [vp]),
     "brgpu_profile_count": (C.c_int, [vp]),

@@ -14,7 +14,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 OBJ = PKG / "build_obj"
 SO = PKG / "libbrgpu.so"
-SOURCES = ["brgpu.cu", "set_kernels.cu", "correct_kernels.cu", "scan_methods.cu", "synth_kernels.cu", "hash_kernels.cu"]
+SOURCES = ["brgpu.cu", "set_kernels.cu", "correct_kernels.cu", "scan_methods.cu", "synth_kernels.cu", "hash_kernels.cu", "group.cu"]
 HEADERS = ["internal.h", "kmer.cuh", "scan_common.cuh", "scan_device.cuh", "../../include/brgpu.h"]
 # C++ host side (br's own interface over the C ABI) and its command line
 HOST = PKG / "host"

@@ -30,6 +30,7 @@ struct Args {
     int confirm = 5, max_search = 7; // src/cli.rs:135-142
     uint64_t record_buffer = 8192;
     int device = 0;
+    std::vector<int> devices; // more than one: single-process multi-GPU
     std::string write_solid;
     bool packed = true;
     size_t chunk_bases = 1u << 30; // bases per chunk while the set is built (the reads are streamed, not held)
@@ -100,7 +101,18 @@ Args parse(int argc, char **argv) {
         else if (t == "-M" || t == "--max-search") a.max_search = (int)parse_int(t, value(t), 0, 255);
         else if (t == "-b" || t == "--record_buffer") a.record_buffer = (uint64_t)parse_int(t, value(t), 0, 1L << 40);
         else if (t == "-t" || t == "--threads") (void)parse_int(t, value(t), 0, 1 << 20);
-        else if (t == "-d" || t == "--device") a.device = (int)parse_int(t, value(t), 0, 1023);
+        else if (t == "-d" || t == "--device") { // one device, or a comma-separated list: the group path (brgpu_group_*)
+            std::string v = value(t);
+            a.devices.clear();
+            size_t p = 0;
+            while (p <= v.size()) {
+                const size_t q = v.find(',', p);
+                a.devices.push_back((int)parse_int(t, v.substr(p, q == std::string::npos ? q : q - p), 0, 1023));
+                if (q == std::string::npos) break;
+                p = q + 1;
+            }
+            a.device = a.devices[0];
+        }
         else if (t == "--write-solid") a.write_solid = value(t);
         else if (t == "--transport") { // how a chunk crosses PCIe: packed (2 bits per base + exceptions, default) | ascii
             const std::string v = value(t);
@@ -185,6 +197,74 @@ std::unique_ptr<br::set::DeviceSet> build_set(const br::Context &ctx, const Args
     throw std::runtime_error("sub-command '" + a.sub + "' is not supported by brgpu");
 }
 
+// `-d 0,1,...`: one process owns several GPUs (brgpu_group_*): the `fasta` sub-command shards the k-mer
+// counting over them, every device holds a replica of the set and corrects its share of each chunk
+int run_group(const Args &a) {
+    if (a.sub != "fasta") throw std::runtime_error("-d with several devices supports the fasta sub-command");
+    if (a.k < 0) usage_error("the following required arguments were not provided: --kmer-size");
+    if (a.sub_inputs.empty()) usage_error("the following required arguments were not provided: --inputs");
+    brgpu_group *g = nullptr;
+    int st = brgpu_group_create(a.devices.data(), (int)a.devices.size(), &g);
+    if (st != BRGPU_OK) throw std::runtime_error(st == BRGPU_E_NO_DEVICE ? "no CUDA device / no peer access between the devices (brgpu has no CPU path)" : "can't create the device group");
+    const int n = brgpu_group_size(g);
+    std::vector<brgpu_set *> sets((size_t)n, nullptr);
+    auto check = [&](int s) {
+        if (s == BRGPU_OK) return;
+        std::string msg = brgpu_group_last_error(g);
+        if (s == BRGPU_E_NEED_ABUNDANCE) msg = "need an abundance threshold or an abundance method";
+        brgpu_group_sets_free(g, sets.data());
+        brgpu_group_destroy(g);
+        throw std::runtime_error(msg);
+    };
+    int sel = BRGPU_ABUNDANCE_EXPLICIT;
+    if (a.abundance < 0) {
+        if (a.selection == "first-minimum") sel = BRGPU_ABUNDANCE_FIRST_MINIMUM;
+        else if (a.selection == "rarefaction") sel = BRGPU_ABUNDANCE_RAREFACTION;
+        else if (a.selection == "percent-most") sel = BRGPU_ABUNDANCE_PERCENT_AT_MOST;
+        else if (a.selection == "percent-least") sel = BRGPU_ABUNDANCE_PERCENT_AT_LEAST;
+    }
+    {
+        br::fasta::Chunk reads;
+        read_all(a.sub_inputs, reads);
+        const int k = a.k - (!(a.k & 1) & 1);
+        check(brgpu_group_set_from_host_reads(g, k, a.abundance, sel, a.percent, reads.seq.data(), reads.offsets.data(),
+                                              reads.size(), sets.data()));
+    }
+    std::vector<uint8_t> ids;
+    for (auto m : a.corrections) ids.push_back((uint8_t)m);
+    const size_t pairs = std::min(a.inputs.size(), a.outputs.size());
+    for (size_t p = 0; p < pairs; p++) {
+        br::fasta::Reader reader(a.inputs[p]);
+        br::fasta::Writer writer(a.outputs[p]);
+        br::fasta::Chunk c;
+        br::fasta::Bytes out;
+        std::vector<uint64_t> out_off;
+        bool more = true;
+        while (more) {
+            c.clear();
+            more = reader.read_chunk(c, br::CHUNK_RECORDS);
+            if (!c.size()) continue;
+            out.resize(c.seq.size() + c.seq.size() / 8 + 64 * c.size() + 64);
+            out_off.assign(c.size() + 1, 0);
+            for (;;) {
+                uint64_t need = 0;
+                st = brgpu_group_correct_batch(g, sets.data(), ids.data(), ids.size(), a.confirm, a.max_search, a.two_side ? 1 : 0,
+                                               c.seq.data(), c.offsets.data(), c.size(), out.data(), out.size(), out_off.data(), &need);
+                if (st == BRGPU_E_OVERFLOW && need > out.size()) {
+                    out.resize(need);
+                    continue;
+                }
+                break;
+            }
+            check(st);
+            writer.write(c.definitions, out.data(), out_off.data());
+        }
+    }
+    brgpu_group_sets_free(g, sets.data());
+    brgpu_group_destroy(g);
+    return 0;
+}
+
 } // namespace
 
 int main(int argc, char **argv) {
@@ -205,6 +285,7 @@ int main(int argc, char **argv) {
             }
             return 0;
         }
+        if (a.devices.size() > 1) return run_group(a);
         br::Context ctx(a.device);
         std::unique_ptr<br::set::DeviceSet> kmer_set = build_set(ctx, a);
         if (!a.write_solid.empty()) {

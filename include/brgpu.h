@@ -312,6 +312,35 @@ int brgpu_set_from_kmers(brgpu_ctx *ctx, brgpu_kmers *const *parts, int n_parts,
 void brgpu_kmers_free(brgpu_kmers *kmers);
 
 /* ------------------------------------------------------------------------------------------
+ * multi-GPU, one process that owns several GPUs (SURVEY §8b "Threading"): a group is one context per
+ * device with peer access between every pair; no torch.distributed, no CUDA IPC.  Part 1 is the sharded
+ * protocol above, driven inside the library (device i counts bucket range i over all devices' partitions,
+ * peer residues pulled over NVLink, slices pushed to every peer; k < 15: count tables + saturating merge);
+ * the result is one replicated set per device, bit-identical to the single-GPU set.  Part 2 shards the
+ * records by bases, one host thread per device, and returns them in input order.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct brgpu_group brgpu_group;
+int brgpu_group_create(const int *devices, int n, brgpu_group **out); /* BRGPU_E_NO_DEVICE without peer access */
+void brgpu_group_destroy(brgpu_group *group);
+int brgpu_group_size(const brgpu_group *group);
+brgpu_ctx *brgpu_group_ctx(brgpu_group *group, int i); /* for uploads into device i (brgpu_reads_upload, ...) */
+const char *brgpu_group_last_error(const brgpu_group *group);
+/* the `fasta` sub-command glue (src/main.rs:72-115) over the group: reads[i] lives in context i;
+ * out_sets[i] receives device i's replica (free them with brgpu_group_sets_free or brgpu_set_free) */
+int brgpu_group_set_from_reads(brgpu_group *group, int k, int abundance, int selection, double percent,
+                               brgpu_reads *const *reads, brgpu_set **out_sets);
+/* same from host buffers: the records are cut into contiguous ranges balanced by bases, one per device */
+int brgpu_group_set_from_host_reads(brgpu_group *group, int k, int abundance, int selection, double percent,
+                                    const uint8_t *seq_host, const uint64_t *offsets_host, uint64_t n_reads,
+                                    brgpu_set **out_sets);
+void brgpu_group_sets_free(brgpu_group *group, brgpu_set **sets);
+/* brgpu_correct_batch over the group (same arguments, sets[i] = device i's replica) */
+int brgpu_group_correct_batch(brgpu_group *group, brgpu_set *const *sets, const uint8_t *methods, uint64_t n_methods,
+                              int confirm, int max_search, int two_side, const uint8_t *seq_host,
+                              const uint64_t *offsets_host, uint64_t n_reads, uint8_t *out_host, uint64_t out_cap,
+                              uint64_t *out_offsets_host, uint64_t *required);
+
+/* ------------------------------------------------------------------------------------------
  * instrumentation (bench.py): per-kernel CUDA-event timings on the library's stream
  * ---------------------------------------------------------------------------------------- */
 int brgpu_profile_enable(brgpu_ctx *ctx, int on);
