@@ -330,3 +330,36 @@ def test_set_built_from_a_stream_of_chunks_equals_the_one_shot_set(gpu, oracle, 
         assert np.array_equal(o1, o2) and np.array_equal(g1, g2)
         whole.free()
         streamed.free()
+
+
+@pytest.mark.parametrize("k", [15, 17])
+def test_warp_per_bucket_and_block_per_bucket_counting_agree(gpu, oracle, k, request):
+    """Small buckets are counted by a warp in a shared-memory hash table, large ones (here: the poly-A and
+    the tandem-repeat reads, thousands of k-mers in a handful of buckets) by a block in a direct-addressed
+    counter array; `count_block_only` sends everything through the block kernel.  Same spectrum, same
+    bitfield, equal to the oracle's — for an explicit threshold, threshold 0 and first-minimum."""
+    br, ctx = gpu
+    from br_b200 import synth
+
+    genome = synth.make_genome(200_000, seed=31)
+    seq, off, _ = synth.make_reads(genome, 12, 0.08, seed=32, mean_len=2500)
+    extra = np.frombuffer(b"A" * 4000 + b"ACGGT" * 1500 + b"TTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTT", dtype=np.uint8)
+    seq = np.concatenate([seq, extra])
+    off = np.concatenate([off, [off[-1] + 4000, off[-1] + 4000 + 7500, off[-1] + extra.size]]).astype(np.uint64)
+    reads = br.Reads.upload(ctx, seq, off)
+    oc = oracle.Counter(k)
+    oc.count(seq, off, threads=8)
+    ohist = oc.spectrum(threads=8)
+    request.addfinalizer(lambda: ctx.set_option("count_block_only", 0))
+    for kwargs in ({"abundance": 2}, {"abundance": 0}, {"abundance_selection": "first-minimum"}):
+        got = {}
+        for mode in (0, 1):
+            ctx.set_option("count_block_only", mode)
+            s = br.Pcon.from_reads(ctx, reads, k, **kwargs)
+            got[mode] = (s.abundance, s.spectrum(), s.bitfield())
+            s.free()
+        assert got[0][0] == got[1][0]
+        assert np.array_equal(got[0][1], ohist) and np.array_equal(got[1][1], ohist), kwargs
+        assert np.array_equal(got[0][2], got[1][2]), kwargs
+        assert np.array_equal(got[0][2], oc.to_solid(got[0][0], threads=8).bits()), kwargs
+    reads.free()
