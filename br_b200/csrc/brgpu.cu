@@ -257,7 +257,7 @@ extern "C" int brgpu_ctx_create(int device, void *cuda_stream, brgpu_ctx **out) 
     };
     ctx->opt_no_compact = env_on("BRGPU_NO_COMPACT") ? 1 : 0;
     ctx->opt_one_level_partition = env_on("BRGPU_ONE_LEVEL_PARTITION") ? 1 : 0;
-    ctx->opt_count_block_only = env_on("BRGPU_COUNT_BLOCK_ONLY") ? 1 : 0;
+    if (const char *v = getenv("BRGPU_COUNT_BLOCK_ONLY")) ctx->opt_count_block_only = (*v >= '0' && *v <= '3') ? *v - '0' : 0;
     if (const char *m = getenv("BRGPU_SCAN")) ctx->opt_scan_mode = m[0] == 'w' ? 1 : (m[0] == 'g' ? 2 : 0);
     *out = ctx;
     return BRGPU_OK;
@@ -292,7 +292,7 @@ extern "C" int brgpu_ctx_set_option(brgpu_ctx *ctx, const char *name, int value)
     if (!ctx || !name) return BRGPU_E_INVALID;
     if (!strcmp(name, "no_compact")) ctx->opt_no_compact = value != 0;
     else if (!strcmp(name, "one_level_partition")) ctx->opt_one_level_partition = value != 0;
-    else if (!strcmp(name, "count_block_only")) ctx->opt_count_block_only = value != 0;
+    else if (!strcmp(name, "count_block_only")) ctx->opt_count_block_only = value < 0 || value > 3 ? 0 : value;
     else if (!strcmp(name, "scan_mode")) {
         if (value < 0 || value > 2) return fail(ctx, BRGPU_E_INVALID, "scan_mode must be 0 (default), 1 (warp) or 2 (groups)");
         ctx->opt_scan_mode = value;
@@ -1321,18 +1321,11 @@ static int set_from_reads_bucketed(brgpu_ctx *ctx, int k, int abundance, int sel
         s->summary_shift = shift;
     }
     uint64_t hist[256];
-    // scratch of the warp-per-bucket kernel: the buckets it hands to the block kernel (+ their number)
-    uint32_t *d_list = nullptr;
-    if (!ctx->opt_count_block_only && dalloc(ctx, &d_list, km->n_buckets + 4) != cudaSuccess) {
-        cudaGetLastError();
-        d_list = nullptr; // not fatal: every bucket goes to the block kernel
-    }
-    unsigned int *d_n_list = d_list ? d_list + km->n_buckets : nullptr;
     if (selection != BRGPU_ABUNDANCE_EXPLICIT) {
         // the threshold depends on the spectrum: one counting sweep without output first
         cudaMemsetAsync(ctx->d_hist, 0, 256 * sizeof(uint64_t), ctx->stream);
         launch_bucket_count(ctx, km->d_res, km->d_base, km->n_buckets, 0, nullptr, nullptr, 0, ctx->d_hist,
-                            km->n_kmers_hint, d_list, d_n_list);
+                            km->n_kmers_hint);
         e = read_hist(ctx, hist);
         if (e == cudaSuccess) {
             abundance = brgpu_spectrum_threshold(hist, selection, percent);
@@ -1342,10 +1335,9 @@ static int set_from_reads_bucketed(brgpu_ctx *ctx, int k, int abundance, int sel
     if (e == cudaSuccess && st == BRGPU_OK) {
         cudaMemsetAsync(ctx->d_hist, 0, 256 * sizeof(uint64_t), ctx->stream);
         launch_bucket_count(ctx, km->d_res, km->d_base, km->n_buckets, abundance, s->d_bits, s->d_summary,
-                            s->summary_shift, ctx->d_hist, km->n_kmers_hint, d_list, d_n_list);
+                            s->summary_shift, ctx->d_hist, km->n_kmers_hint);
         e = read_hist(ctx, hist);
     }
-    if (d_list) dfree(ctx, d_list);
     if (e == cudaSuccess) e = cudaGetLastError();
     kmers_release(km);
     if (e != cudaSuccess) st = fail(ctx, BRGPU_E_CUDA, "bucketed counting", e);

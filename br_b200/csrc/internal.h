@@ -51,7 +51,7 @@ struct brgpu_ctx {
     // BRGPU_ONE_LEVEL_PARTITION, BRGPU_SCAN=warp|groups), changed with brgpu_ctx_set_option
     int opt_no_compact = 0;          // lookups through summary + bitfield even for sparse sets
     int opt_one_level_partition = 0; // the k = 19 partition path for k <= 17
-    int opt_count_block_only = 0;    // every bucket through the block-per-bucket counting kernel (no warp-per-bucket hash tables)
+    int opt_count_block_only = 0;    // the 256-thread shape of the counting kernel even for sparse buckets
     int opt_scan_mode = 0;           // 0: per method default, 1: warp per segment, 2: four segments per warp
     // caching device allocator (brgpu.cu): blocks handed out (ptr -> bytes) and cached free blocks
     std::unordered_map<void *, uint64_t> pool_live;
@@ -201,7 +201,7 @@ void launch_bucket_partition(brgpu_ctx *ctx, const Layout &L, const uint8_t *d_s
                              uint16_t *d_residues, uint32_t *d_coarse_kmers, uint64_t *d_coarse_base, double n_kmers);
 void launch_bucket_count(brgpu_ctx *ctx, const uint16_t *d_residues, const uint64_t *d_base, uint64_t n_buckets,
                          int abundance, uint8_t *d_bits, uint32_t *d_summary, int summary_shift, uint64_t *d_hist,
-                         double n_kmers, uint32_t *d_list = nullptr, unsigned int *d_n_list = nullptr);
+                         double n_kmers);
 void launch_bucket_count_multi(brgpu_ctx *ctx, const uint16_t *const *d_res, const uint64_t *const *d_base, int n_src,
                                uint64_t b0, uint64_t b1, int abundance, uint8_t *d_bits, uint32_t *d_summary,
                                uint64_t *d_hist, double n_kmers);

@@ -572,61 +572,76 @@ __global__ void bucket_cursor_kernel(const uint64_t *__restrict__ base, uint64_t
 // reads the final count, tallies the spectrum, sets the bit in a 4 KiB shared bitfield slice
 // if count > abundance, and stores 0 to its counter byte — so the slice is clean again for
 // the next bucket without ever being swept.  hist[0] is 2^15 minus the owners.
-constexpr int BUCKET_REG_ROUNDS = 4; // residues kept in registers per thread between the two phases
+constexpr int BUCKET_REG_ROUNDS = 4; // residues kept in registers per thread between the two phases (multi-source kernel)
 
-__global__ void __launch_bounds__(BUCKET_THREADS)
-    bucket_count_kernel(const uint16_t *__restrict__ residues, const uint64_t *__restrict__ base, uint64_t n_buckets_,
+// THREADS x ROUNDS residues of a bucket are held in registers between the two phases; the rest (large
+// buckets) is read twice; the next bucket's residues are requested while the owners of this one finish.
+// The kernel is a chain of short phases per bucket (zero the slice, CAS increments, barrier, owners,
+// barrier, write the slice, barrier: ~6 us per bucket at 256 threads) and what hides that chain is the
+// number of buckets in flight per SM, which the 32 KiB counter array caps at 5.  Measured on the E. coli
+// configuration (262 144 buckets of ~530 k-mers), profiles/count_shapes_r2.txt:
+//   256 threads x 4 rounds  1.52 ms  (the default for every bucket size)
+//   128 threads x 6 rounds  2.00 ms,  64 threads x 12 rounds  3.57 ms  — fewer threads per bucket lengthen
+//       every phase and do not buy more buckets in flight (shared memory, not threads, is the limit);
+//   a warp per bucket with a 1024-entry shared-memory hash table instead of the counter array (9.6 KB per
+//       bucket, 20 buckets in flight per SM) 2.3-2.6 ms: per-lane linear probing diverges (8.7 of 32 lanes
+//       active per instruction, 1.22 G warp instructions against 0.92 G).
+template <int THREADS, int ROUNDS>
+__global__ void __launch_bounds__(THREADS)
+    bucket_count_kernel(const uint16_t *__restrict__ residues, const uint64_t *__restrict__ base, uint64_t n_buckets,
                         int abundance, uint32_t *__restrict__ bitfield32, uint32_t *__restrict__ summary32,
-                        int summary_shift, unsigned long long *__restrict__ g_hist, const uint32_t *__restrict__ list,
-                        const unsigned int *__restrict__ n_list) {
-    // list != nullptr: only the buckets list[0 .. *n_list) (the ones too large for bucket_count_warp_kernel)
-    const uint64_t n_buckets = list ? (uint64_t)*n_list : n_buckets_;
-    auto bucket_id = [&](uint64_t i) -> uint64_t { return list ? (uint64_t)__ldg(list + i) : i; };
+                        int summary_shift, unsigned long long *__restrict__ g_hist) {
     extern __shared__ uint32_t cnt[];          // BUCKET_COUNTERS / 4 words of u8 counters
     __shared__ uint64_t sh_bits64[BUCKET_COUNTERS / 64]; // the bucket's slice of the bitfield
     __shared__ unsigned int sh_hist[256];
     uint32_t *sh_bits = reinterpret_cast<uint32_t *>(sh_bits64);
     uint8_t *cnt8 = reinterpret_cast<uint8_t *>(cnt);
-    for (int t = threadIdx.x; t < 256; t += BUCKET_THREADS) sh_hist[t] = 0;
-    for (int t = threadIdx.x; t < BUCKET_COUNTERS / 4; t += BUCKET_THREADS) cnt[t] = 0; // once: owners keep it clean
+    for (int t = threadIdx.x; t < 256; t += THREADS) sh_hist[t] = 0;
+    for (int t = threadIdx.x; t < BUCKET_COUNTERS / 4; t += THREADS) cnt[t] = 0; // once: owners keep it clean
     uint32_t c1 = 0, c2 = 0, c3 = 0, owners = 0; // per-thread tallies of the values that hold the mass
     unsigned long long zeros = 0;
     uint64_t begin = 0, end = 0;
+    uint32_t nres[ROUNDS]; // the register-held residues of the bucket the loop is about to enter
+    auto fetch = [&](uint64_t from, uint64_t to) {
+#pragma unroll
+        for (int q = 0; q < ROUNDS; q++) {
+            const uint64_t j = from + threadIdx.x + (uint64_t)q * THREADS;
+            nres[q] = j < to ? (uint32_t)__ldcs(residues + j) : 0xffffffffu;
+        }
+    };
     if (blockIdx.x < n_buckets) {
-        begin = __ldg(base + bucket_id(blockIdx.x));
-        end = __ldg(base + bucket_id(blockIdx.x) + 1);
+        begin = __ldg(base + blockIdx.x);
+        end = __ldg(base + blockIdx.x + 1);
+        fetch(begin, end);
     }
     __syncthreads();
-    for (uint64_t bi = blockIdx.x; bi < n_buckets; bi += gridDim.x) {
-        const uint64_t b = bucket_id(bi);
-        uint32_t res[BUCKET_REG_ROUNDS];
+    for (uint64_t b = blockIdx.x; b < n_buckets; b += gridDim.x) {
+        uint32_t res[ROUNDS];
 #pragma unroll
-        for (int q = 0; q < BUCKET_REG_ROUNDS; q++) {
-            uint64_t j = begin + threadIdx.x + (uint64_t)q * BUCKET_THREADS;
-            res[q] = j < end ? (uint32_t)__ldcs(residues + j) : 0xffffffffu;
-        }
-        // bounds of this block's next bucket: requested now, needed only after the barriers
+        for (int q = 0; q < ROUNDS; q++) res[q] = nres[q];
+        // bounds of this block's next bucket: requested now, needed after phase 1
         uint64_t nb_begin = 0, nb_end = 0;
-        if (bi + gridDim.x < n_buckets) {
-            const uint64_t nb = bucket_id(bi + gridDim.x);
-            nb_begin = __ldg(base + nb);
-            nb_end = __ldg(base + nb + 1);
+        const bool has_next = b + gridDim.x < n_buckets;
+        if (has_next) {
+            nb_begin = __ldg(base + b + gridDim.x);
+            nb_end = __ldg(base + b + gridDim.x + 1);
         }
-        for (int t = threadIdx.x; t < BUCKET_COUNTERS / 32; t += BUCKET_THREADS) sh_bits[t] = 0;
+        for (int t = threadIdx.x; t < BUCKET_COUNTERS / 32; t += THREADS) sh_bits[t] = 0;
         // ---- phase 1: saturating increments ----
         uint32_t own = 0; // bit q: res[q] is an owner
 #pragma unroll
-        for (int q = 0; q < BUCKET_REG_ROUNDS; q++)
+        for (int q = 0; q < ROUNDS; q++)
             if (res[q] != 0xffffffffu && sat_inc_owner(cnt + (res[q] >> 2), (res[q] & 3u) * 8u)) own |= 1u << q;
-        const uint64_t rest_begin = begin + (uint64_t)BUCKET_REG_ROUNDS * BUCKET_THREADS;
-        for (uint64_t j = rest_begin + threadIdx.x; j < end; j += BUCKET_THREADS) {
+        const uint64_t rest_begin = begin + (uint64_t)ROUNDS * THREADS;
+        for (uint64_t j = rest_begin + threadIdx.x; j < end; j += THREADS) {
             uint32_t r = __ldcs(residues + j);
             sat_inc_owner(cnt + (r >> 2), (r & 3u) * 8u);
         }
+        if (has_next) fetch(nb_begin, nb_end); // the next bucket's residues travel while this one is finished
         __syncthreads();
         // ---- phase 2: owners read the final count, tally, threshold and clear ----
 #pragma unroll
-        for (int q = 0; q < BUCKET_REG_ROUNDS; q++) {
+        for (int q = 0; q < ROUNDS; q++) {
             if ((own >> q) & 1u) {
                 const uint32_t r = res[q];
                 const uint32_t c = cnt8[r];
@@ -642,7 +657,7 @@ __global__ void __launch_bounds__(BUCKET_THREADS)
         // big buckets: the overflow occurrences claim their counter with an atomic swap-to-zero —
         // after the register-held owners have cleared theirs (block-uniform condition)
         if (end > rest_begin) __syncthreads();
-        for (uint64_t j = rest_begin + threadIdx.x; j < end; j += BUCKET_THREADS) {
+        for (uint64_t j = rest_begin + threadIdx.x; j < end; j += THREADS) {
             const uint32_t r = __ldcs(residues + j);
             const uint32_t sh = (r & 3u) * 8u;
             const uint32_t old = atomicAnd(cnt + (r >> 2), ~(0xffu << sh));
@@ -656,14 +671,15 @@ __global__ void __launch_bounds__(BUCKET_THREADS)
         __syncthreads();
         // ---- write the slice of the bitfield (+ its summary bits) ----
         if (bitfield32) {
-            uint64_t *bitfield64 = reinterpret_cast<uint64_t *>(bitfield32);
-            for (int t = threadIdx.x; t < BUCKET_COUNTERS / 64; t += BUCKET_THREADS) {
+            uint64_t *bitfield64 = reinterpret_cast<uint64_t *>(bitfield32) + b * (BUCKET_COUNTERS / 64);
+            uint32_t *summary = summary32 && summary_shift == 6 ? summary32 + b * (BUCKET_COUNTERS / 64 / 32) : nullptr;
+#pragma unroll 4
+            for (int t = threadIdx.x; t < BUCKET_COUNTERS / 64; t += THREADS) {
                 const uint64_t out = sh_bits64[t];
-                const uint64_t block = b * (BUCKET_COUNTERS / 64) + (uint64_t)t;
-                bitfield64[block] = out;
-                if (summary32 && summary_shift == 6) { // one summary bit per 64-bit block
-                    uint32_t m = __ballot_sync(FULL, out != 0);
-                    if ((threadIdx.x & 31) == 0) summary32[block >> 5] = m;
+                bitfield64[t] = out;
+                if (summary) { // one summary bit per 64-bit block
+                    const uint32_t m = __ballot_sync(FULL, out != 0);
+                    if ((threadIdx.x & 31) == 0) summary[t >> 5] = m;
                 }
             }
         }
@@ -687,148 +703,9 @@ __global__ void __launch_bounds__(BUCKET_THREADS)
         if (owners) atomicAdd(&sh_owners, (unsigned long long)owners);
     }
     __syncthreads();
-    for (int t = threadIdx.x; t < 256; t += BUCKET_THREADS)
+    for (int t = threadIdx.x; t < 256; t += THREADS)
         if (t > 0 && sh_hist[t]) atomicAdd(g_hist + t, (unsigned long long)sh_hist[t]);
     if (threadIdx.x == 0 && zeros >= sh_owners) atomicAdd(g_hist + 0, zeros - sh_owners);
-}
-
-// ------------------------------------------------------------------------------------------
-// Small buckets, one WARP per bucket.  At the E. coli configuration a bucket holds ~530 k-mers for its
-// 32 768 counters, and the block-per-bucket kernel above spends its instructions on what does not depend on
-// the k-mers at all (barriers, zeroing and writing the slice with 256 threads, 64-bit bucket arithmetic in
-// every thread: 440 instructions per thread and bucket, 917 M warp instructions per step, 58 % issue
-// utilisation — profiles/launches_r2.txt).  A bucket that small does not need a direct-addressed counter
-// array: the warp counts it in a hash table of SLOTS entries in shared memory — entry = (residue + 1) << 16 |
-// occurrences, linear probing, load <= 2/3; the lane whose atomicCAS claims an empty entry is the k-mer's
-// owner and, after the warp has inserted everything, reads the final count, tallies the spectrum, sets the
-// bit in the warp's slice of the bitfield if count > abundance and clears the entry.  min(255, occurrences)
-// per canonical k-mer either way, so spectrum and bitfield are those of the other kernels.  Buckets with
-// more than SLOTS * 2 / 3 k-mers are appended to `large_list` and counted by bucket_count_kernel.
-// ------------------------------------------------------------------------------------------
-constexpr int BCW_WARPS = 4; // warps per block
-
-template <int LOG_SLOTS> struct BcwGeometry {
-    static constexpr int SLOTS = 1 << LOG_SLOTS;
-    static constexpr int MAXN = SLOTS * 2 / 3;
-    static constexpr int ROUNDS = (MAXN + 31) / 32;
-    // per warp: table (u32 x SLOTS), bitfield slice (4 KiB), owner slots (u16 x ROUNDS x 32)
-    static constexpr int WARP_BYTES = SLOTS * 4 + BUCKET_COUNTERS / 8 + ((ROUNDS * 32 * 2 + 15) & ~15);
-    static constexpr int BLOCK_BYTES = WARP_BYTES * BCW_WARPS;
-};
-
-template <int LOG_SLOTS>
-__global__ void __launch_bounds__(BCW_WARPS * 32)
-    bucket_count_warp_kernel(const uint16_t *__restrict__ residues, const uint64_t *__restrict__ base, uint64_t n_buckets,
-                             int abundance, uint32_t *__restrict__ bitfield32, uint32_t *__restrict__ summary32,
-                             unsigned long long *__restrict__ g_hist, uint32_t *__restrict__ large_list,
-                             unsigned int *__restrict__ n_large) {
-    using G = BcwGeometry<LOG_SLOTS>;
-    extern __shared__ __align__(16) uint8_t bcw_smem[];
-    __shared__ unsigned int sh_hist[256];
-    __shared__ unsigned long long sh_owners, sh_zeros;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    uint8_t *mine = bcw_smem + (size_t)wid * G::WARP_BYTES;
-    uint32_t *tab = reinterpret_cast<uint32_t *>(mine);
-    uint64_t *bits64 = reinterpret_cast<uint64_t *>(mine + G::SLOTS * 4);
-    uint32_t *bits = reinterpret_cast<uint32_t *>(bits64);
-    uint16_t *own = reinterpret_cast<uint16_t *>(mine + G::SLOTS * 4 + BUCKET_COUNTERS / 8);
-    for (int t = threadIdx.x; t < 256; t += blockDim.x) sh_hist[t] = 0;
-    if (threadIdx.x == 0) sh_owners = sh_zeros = 0;
-    for (int t = lane; t < G::SLOTS; t += 32) tab[t] = 0; // once: owners keep it clean
-    __syncthreads();
-    uint32_t c1 = 0, c2 = 0, c3 = 0, owners = 0, buckets_done = 0;
-    const uint64_t warp = (uint64_t)blockIdx.x * BCW_WARPS + wid, n_warps = (uint64_t)gridDim.x * BCW_WARPS;
-    uint64_t begin = 0, end = 0;
-    if (warp < n_buckets) {
-        begin = __ldg(base + warp);
-        end = __ldg(base + warp + 1);
-    }
-    for (uint64_t b = warp; b < n_buckets; b += n_warps) {
-        const uint32_t n = (uint32_t)(end - begin);
-        const uint64_t cur_begin = begin;
-        if (b + n_warps < n_buckets) { // the next bucket's bounds: requested now, needed at the end of this one
-            begin = __ldg(base + b + n_warps);
-            end = __ldg(base + b + n_warps + 1);
-        }
-        if (n > (uint32_t)G::MAXN) { // too many k-mers for the table: bucket_count_kernel takes it
-            if (lane == 0) large_list[atomicAdd(n_large, 1u)] = (uint32_t)b;
-            continue;
-        }
-        {
-            uint4 *z = reinterpret_cast<uint4 *>(bits64);
-#pragma unroll
-            for (int t = 0; t < BUCKET_COUNTERS / 8 / 16 / 32; t++) z[t * 32 + lane] = make_uint4(0u, 0u, 0u, 0u);
-        }
-        __syncwarp();
-        // ---- insert: every lane takes k-mers lane, lane + 32, ... ----
-        uint32_t n_own = 0;
-        for (uint32_t j = (uint32_t)lane; j < n; j += 32) {
-            const uint32_t res = (uint32_t)__ldcs(residues + cur_begin + j);
-            const uint32_t key = (res + 1u) << 16;
-            uint32_t h = ((res * 40503u) & 0xffffu) >> (16 - LOG_SLOTS);
-            for (;;) {
-                uint32_t old = tab[h];
-                if (old == 0u) {
-                    old = atomicCAS(&tab[h], 0u, key | 1u);
-                    if (old == 0u) { // this occurrence owns the k-mer
-                        own[n_own * 32u + (uint32_t)lane] = (uint16_t)h;
-                        n_own++;
-                        break;
-                    }
-                }
-                if ((old & 0xffff0000u) == key) {
-                    atomicAdd(&tab[h], 1u); // at most MAXN < 2^16 occurrences: the count cannot reach the key bits
-                    break;
-                }
-                h = (h + 1u) & (uint32_t)(G::SLOTS - 1);
-            }
-        }
-        __syncwarp();
-        // ---- owners: final count -> spectrum, threshold, clear ----
-        for (uint32_t t = 0; t < n_own; t++) {
-            const uint32_t slot = own[t * 32u + (uint32_t)lane];
-            const uint32_t e = tab[slot];
-            tab[slot] = 0u;
-            const uint32_t occ = e & 0xffffu, c = occ < 255u ? occ : 255u, r = (e >> 16) - 1u;
-            if (c == 1) c1++;
-            else if (c == 2) c2++;
-            else if (c == 3) c3++;
-            else atomicAdd(&sh_hist[c], 1u);
-            if (c > (uint32_t)abundance) atomicOr(&bits[r >> 5], 1u << (r & 31));
-        }
-        owners += n_own;
-        __syncwarp();
-        // ---- the slice of the bitfield (+ its summary bits): 512 64-bit words, 32 per warp store ----
-        if (bitfield32) {
-            uint64_t *bitfield64 = reinterpret_cast<uint64_t *>(bitfield32) + b * (BUCKET_COUNTERS / 64);
-#pragma unroll 4
-            for (int t = 0; t < BUCKET_COUNTERS / 64 / 32; t++) {
-                const uint64_t out = bits64[t * 32 + lane];
-                bitfield64[t * 32 + lane] = out;
-                if (summary32) {
-                    const uint32_t m = __ballot_sync(FULL, out != 0);
-                    if (lane == 0) summary32[b * (BUCKET_COUNTERS / 64 / 32) + (uint64_t)t] = m;
-                }
-            }
-        }
-        buckets_done++;
-        __syncwarp();
-    }
-    c1 = __reduce_add_sync(FULL, c1);
-    c2 = __reduce_add_sync(FULL, c2);
-    c3 = __reduce_add_sync(FULL, c3);
-    owners = __reduce_add_sync(FULL, owners);
-    if (lane == 0) {
-        if (c1) atomicAdd(&sh_hist[1], c1);
-        if (c2) atomicAdd(&sh_hist[2], c2);
-        if (c3) atomicAdd(&sh_hist[3], c3);
-        if (owners) atomicAdd(&sh_owners, (unsigned long long)owners);
-        if (buckets_done) atomicAdd(&sh_zeros, (unsigned long long)buckets_done * BUCKET_COUNTERS);
-    }
-    __syncthreads();
-    for (int t = threadIdx.x; t < 256; t += blockDim.x)
-        if (t > 0 && sh_hist[t]) atomicAdd(g_hist + t, (unsigned long long)sh_hist[t]);
-    if (threadIdx.x == 0 && sh_zeros >= sh_owners) atomicAdd(g_hist + 0, sh_zeros - sh_owners); // counters nobody touched
 }
 
 // Multi-source variant for the multi-GPU path: the k-mers of bucket b come from this rank's
@@ -1279,75 +1156,44 @@ void launch_bucket_partition(brgpu_ctx *ctx, const Layout &L, const uint8_t *d_s
     }
 }
 
-int bucket_count_configure() {
-    static bool done = false;
-    if (!done) {
-        cudaFuncSetAttribute(bucket_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BUCKET_COUNTERS);
-        cudaFuncSetAttribute(bucket_count_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                             cudaSharedmemCarveoutMaxShared);
-        done = true;
-    }
-    return BUCKET_COUNTERS;
-}
-
-template <int LOG_SLOTS>
-static void launch_bucket_count_warp(brgpu_ctx *ctx, const uint16_t *d_residues, const uint64_t *d_base, uint64_t n_buckets,
-                                     int abundance, uint8_t *d_bits, uint32_t *d_summary, uint64_t *d_hist, uint32_t *d_list,
-                                     unsigned int *d_n_list) {
-    using G = BcwGeometry<LOG_SLOTS>;
+template <int THREADS, int ROUNDS>
+static void launch_bucket_count_shape(brgpu_ctx *ctx, const uint16_t *d_residues, const uint64_t *d_base, uint64_t n_buckets,
+                                      int abundance, uint8_t *d_bits, uint32_t *d_summary, int summary_shift, uint64_t *d_hist) {
     static bool configured = false;
     if (!configured) {
-        cudaFuncSetAttribute(bucket_count_warp_kernel<LOG_SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::BLOCK_BYTES);
-        cudaFuncSetAttribute(bucket_count_warp_kernel<LOG_SLOTS>, cudaFuncAttributePreferredSharedMemoryCarveout,
+        cudaFuncSetAttribute(bucket_count_kernel<THREADS, ROUNDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, BUCKET_COUNTERS);
+        cudaFuncSetAttribute(bucket_count_kernel<THREADS, ROUNDS>, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
         configured = true;
     }
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bucket_count_warp_kernel<LOG_SLOTS>, BCW_WARPS * 32, G::BLOCK_BYTES) !=
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bucket_count_kernel<THREADS, ROUNDS>, THREADS, BUCKET_COUNTERS) !=
             cudaSuccess || per_sm < 1) {
         cudaGetLastError();
         per_sm = 1;
     }
-    const uint64_t cap = (uint64_t)ctx->sm_count * (uint64_t)per_sm, need = (n_buckets + BCW_WARPS - 1) / BCW_WARPS;
-    bucket_count_warp_kernel<LOG_SLOTS><<<(unsigned)(need < cap ? need : cap), BCW_WARPS * 32, G::BLOCK_BYTES, ctx->stream>>>(
-        d_residues, d_base, n_buckets, abundance, reinterpret_cast<uint32_t *>(d_bits), d_summary,
-        reinterpret_cast<unsigned long long *>(d_hist), d_list, d_n_list);
+    const uint64_t cap = (uint64_t)ctx->sm_count * (uint64_t)per_sm;
+    bucket_count_kernel<THREADS, ROUNDS><<<(unsigned)(n_buckets < cap ? n_buckets : cap), THREADS, BUCKET_COUNTERS, ctx->stream>>>(
+        d_residues, d_base, n_buckets, abundance, reinterpret_cast<uint32_t *>(d_bits), d_summary, summary_shift,
+        reinterpret_cast<unsigned long long *>(d_hist));
 }
 
-// d_list (n_buckets x u32) + d_n_list (one zeroed word): scratch for the buckets the warp kernel hands to the
-// block kernel; nullptr = every bucket goes to the block kernel (the round-1 path).
 void launch_bucket_count(brgpu_ctx *ctx, const uint16_t *d_residues, const uint64_t *d_base, uint64_t n_buckets,
                          int abundance, uint8_t *d_bits, uint32_t *d_summary, int summary_shift, uint64_t *d_hist,
-                         double n_kmers, uint32_t *d_list, unsigned int *d_n_list) {
-    const int smem = bucket_count_configure();
-    // 2 B residue in per k-mer + the slice's share of the bitfield out
+                         double n_kmers) {
+    // 2 B residue in per k-mer + the slice's share of the bitfield out (a sweep that reads the
+    // residues twice for the rare buckets that overflow the register rounds is not counted)
     ProfScope ps(ctx, "bucket_count", n_kmers * 2.0 + (double)n_buckets * (BUCKET_COUNTERS / 8));
-    int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bucket_count_kernel, BUCKET_THREADS, smem) != cudaSuccess ||
-        per_sm < 1) {
-        cudaGetLastError();
-        per_sm = 1;
-    }
-    uint64_t cap = (uint64_t)ctx->sm_count * (uint64_t)per_sm;
-    unsigned grid = (unsigned)(n_buckets < cap ? n_buckets : cap);
     const double mean = n_kmers / (double)(n_buckets ? n_buckets : 1);
-    const bool summary6 = d_summary == nullptr || summary_shift == 6; // the warp kernel writes one summary bit per 64-bit block
-    if (d_list && d_n_list && summary6 && mean <= (double)BcwGeometry<11>::MAXN * 0.8) {
-        // most buckets are small: a warp per bucket with a shared-memory hash table; the stragglers go to the block kernel
-        cudaMemsetAsync(d_n_list, 0, sizeof(unsigned int), ctx->stream);
-        if (mean <= (double)BcwGeometry<10>::MAXN * 0.85)
-            launch_bucket_count_warp<10>(ctx, d_residues, d_base, n_buckets, abundance, d_bits, d_summary, d_hist, d_list, d_n_list);
-        else
-            launch_bucket_count_warp<11>(ctx, d_residues, d_base, n_buckets, abundance, d_bits, d_summary, d_hist, d_list, d_n_list);
-        ctx->launches++;
-        bucket_count_kernel<<<grid, BUCKET_THREADS, smem, ctx->stream>>>(
-            d_residues, d_base, n_buckets, abundance, reinterpret_cast<uint32_t *>(d_bits), d_summary, summary_shift,
-            reinterpret_cast<unsigned long long *>(d_hist), d_list, d_n_list);
-        return;
-    }
-    bucket_count_kernel<<<grid, BUCKET_THREADS, smem, ctx->stream>>>(
-        d_residues, d_base, n_buckets, abundance, reinterpret_cast<uint32_t *>(d_bits), d_summary, summary_shift,
-        reinterpret_cast<unsigned long long *>(d_hist), nullptr, nullptr);
+    const int shape = ctx->opt_count_block_only; // 0 / 1: 256 threads, 2: 128, 3: 64 (A/B runs, tests)
+    (void)mean;
+    if (shape == 3)
+        launch_bucket_count_shape<64, 12>(ctx, d_residues, d_base, n_buckets, abundance, d_bits, d_summary, summary_shift, d_hist);
+    else if (shape == 2)
+        launch_bucket_count_shape<128, 6>(ctx, d_residues, d_base, n_buckets, abundance, d_bits, d_summary, summary_shift, d_hist);
+    else
+        launch_bucket_count_shape<BUCKET_THREADS, BUCKET_REG_ROUNDS>(ctx, d_residues, d_base, n_buckets, abundance, d_bits, d_summary,
+                                                                     summary_shift, d_hist);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -72,7 +72,7 @@ int brgpu_ctx_synchronize(brgpu_ctx *ctx);
  * environment once, at brgpu_ctx_create (BRGPU_NO_COMPACT, BRGPU_ONE_LEVEL_PARTITION,
  * BRGPU_COUNT_BLOCK_ONLY, BRGPU_SCAN=warp|groups).  name: "no_compact" (0/1: solidity lookups through summary + bitfield
  * even for sparse sets), "one_level_partition" (0/1: the k = 19 partition path for k <= 17),
- * "count_block_only" (0/1: every bucket through the block-per-bucket counting kernel),
+ * "count_block_only" (threads per bucket of the counting kernel: 0 or 1 = 256, the default; 2 = 128; 3 = 64),
  * "scan_mode" (0 per-method default, 1 warp per segment, 2 four segments per warp, for One/Two). */
 int brgpu_ctx_set_option(brgpu_ctx *ctx, const char *name, int value);
 const char *brgpu_last_error(const brgpu_ctx *ctx);

@@ -333,11 +333,11 @@ def test_set_built_from_a_stream_of_chunks_equals_the_one_shot_set(gpu, oracle, 
 
 
 @pytest.mark.parametrize("k", [15, 17])
-def test_warp_per_bucket_and_block_per_bucket_counting_agree(gpu, oracle, k, request):
-    """Small buckets are counted by a warp in a shared-memory hash table, large ones (here: the poly-A and
-    the tandem-repeat reads, thousands of k-mers in a handful of buckets) by a block in a direct-addressed
-    counter array; `count_block_only` sends everything through the block kernel.  Same spectrum, same
-    bitfield, equal to the oracle's — for an explicit threshold, threshold 0 and first-minimum."""
+def test_both_shapes_of_the_bucket_counting_kernel_agree(gpu, oracle, k, request):
+    """The bucket-counting kernel exists in three shapes (256 / 128 / 64 threads per bucket, holding 1024 /
+    768 / 768 k-mers in registers; the poly-A and the tandem-repeat reads put thousands of k-mers into a
+    handful of buckets, which overflows all of them).  Same spectrum, same bitfield, equal to the oracle's —
+    for an explicit threshold, threshold 0 and first-minimum."""
     br, ctx = gpu
     from br_b200 import synth
 
@@ -353,13 +353,13 @@ def test_warp_per_bucket_and_block_per_bucket_counting_agree(gpu, oracle, k, req
     request.addfinalizer(lambda: ctx.set_option("count_block_only", 0))
     for kwargs in ({"abundance": 2}, {"abundance": 0}, {"abundance_selection": "first-minimum"}):
         got = {}
-        for mode in (0, 1):
+        for mode in (0, 3, 2):
             ctx.set_option("count_block_only", mode)
             s = br.Pcon.from_reads(ctx, reads, k, **kwargs)
             got[mode] = (s.abundance, s.spectrum(), s.bitfield())
             s.free()
-        assert got[0][0] == got[1][0]
-        assert np.array_equal(got[0][1], ohist) and np.array_equal(got[1][1], ohist), kwargs
-        assert np.array_equal(got[0][2], got[1][2]), kwargs
+        assert got[0][0] == got[3][0] == got[2][0]
+        assert all(np.array_equal(got[m][1], ohist) for m in (0, 2, 3)), kwargs
+        assert np.array_equal(got[0][2], got[3][2]) and np.array_equal(got[0][2], got[2][2]), kwargs
         assert np.array_equal(got[0][2], oc.to_solid(got[0][0], threads=8).bits()), kwargs
     reads.free()
