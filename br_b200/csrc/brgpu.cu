@@ -235,6 +235,9 @@ extern "C" int brgpu_ctx_create(int device, void *cuda_stream, brgpu_ctx **out) 
         ctx->own_stream = true;
     }
     if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_aux_in, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_aux_out, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_fence, cudaEventDisableTiming) != cudaSuccess) {
         cudaGetLastError();
         brgpu_ctx_destroy(ctx);
@@ -272,6 +275,12 @@ extern "C" void brgpu_ctx_destroy(brgpu_ctx *ctx) {
         cudaStreamDestroy(ctx->copy_stream);
     }
     if (ctx->ev_fence) cudaEventDestroy(ctx->ev_fence);
+    if (ctx->aux_stream) {
+        cudaStreamSynchronize(ctx->aux_stream);
+        cudaStreamDestroy(ctx->aux_stream);
+    }
+    if (ctx->ev_aux_in) cudaEventDestroy(ctx->ev_aux_in);
+    if (ctx->ev_aux_out) cudaEventDestroy(ctx->ev_aux_out);
     for (auto &p : ctx->prof)
         for (auto &ev : p.pending) {
             cudaEventDestroy(ev.first);
@@ -1297,15 +1306,11 @@ static cudaError_t read_hist(brgpu_ctx *ctx, uint64_t hist[256]) {
 
 static int set_from_reads_bucketed(brgpu_ctx *ctx, int k, int abundance, int selection, double percent,
                                    const brgpu_reads *reads, brgpu_set **out) {
-    brgpu_kmers *km = nullptr;
-    int st = kmers_create(ctx, k, reads, &km);
-    if (st != BRGPU_OK) return st;
+    // the set first: its bitfield and summary are zeroed on the auxiliary stream while the partition kernels
+    // run, so that the counting kernel only has to set the bits of the solid k-mers
     brgpu_set *s = nullptr;
-    st = set_alloc(ctx, k, &s);
-    if (st != BRGPU_OK) {
-        kmers_release(km);
-        return st;
-    }
+    int st = set_alloc(ctx, k, &s);
+    if (st != BRGPU_OK) return st;
     cudaError_t e = cudaSuccess;
     int shift;
     uint64_t sbytes;
@@ -1313,12 +1318,28 @@ static int set_from_reads_bucketed(brgpu_ctx *ctx, int k, int abundance, int sel
     if (sbytes && shift == 6) {
         e = big_alloc(ctx, (void **)&s->d_summary, sbytes);
         if (e != cudaSuccess) {
-            kmers_release(km);
             brgpu_set_free(s);
             return fail(ctx, BRGPU_E_NOMEM, "device allocation (summary)", e);
         }
         s->summary_bytes = sbytes;
         s->summary_shift = shift;
+    }
+    // the blocks may still be read by work enqueued earlier on the compute stream: the memsets start behind it
+    bool prezeroed = cudaEventRecord(ctx->ev_aux_in, ctx->stream) == cudaSuccess &&
+                     cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_aux_in, 0) == cudaSuccess &&
+                     cudaMemsetAsync(s->d_bits, 0, bits_alloc_bytes(k), ctx->aux_stream) == cudaSuccess &&
+                     (!s->d_summary || cudaMemsetAsync(s->d_summary, 0, s->summary_bytes, ctx->aux_stream) == cudaSuccess) &&
+                     cudaEventRecord(ctx->ev_aux_out, ctx->aux_stream) == cudaSuccess;
+    if (!prezeroed) cudaGetLastError();
+    brgpu_kmers *km = nullptr;
+    st = kmers_create(ctx, k, reads, &km);
+    if (prezeroed && cudaStreamWaitEvent(ctx->stream, ctx->ev_aux_out, 0) != cudaSuccess) { // also orders the set's release
+        cudaGetLastError();
+        cudaStreamSynchronize(ctx->aux_stream);
+    }
+    if (st != BRGPU_OK) {
+        brgpu_set_free(s);
+        return st;
     }
     uint64_t hist[256];
     if (selection != BRGPU_ABUNDANCE_EXPLICIT) {
@@ -1335,7 +1356,7 @@ static int set_from_reads_bucketed(brgpu_ctx *ctx, int k, int abundance, int sel
     if (e == cudaSuccess && st == BRGPU_OK) {
         cudaMemsetAsync(ctx->d_hist, 0, 256 * sizeof(uint64_t), ctx->stream);
         launch_bucket_count(ctx, km->d_res, km->d_base, km->n_buckets, abundance, s->d_bits, s->d_summary,
-                            s->summary_shift, ctx->d_hist, km->n_kmers_hint);
+                            s->summary_shift, ctx->d_hist, km->n_kmers_hint, prezeroed);
         e = read_hist(ctx, hist);
     }
     if (e == cudaSuccess) e = cudaGetLastError();

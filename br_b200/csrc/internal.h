@@ -34,6 +34,9 @@ struct brgpu_ctx {
     // _download_async): copies of the neighbouring chunks run while this chunk's kernels do
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_fence = nullptr; // orders the two streams against each other
+    // third stream: memsets that run beside the kernels of the compute stream (the bitfield of a set under construction)
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t ev_aux_in = nullptr, ev_aux_out = nullptr;
     std::string err;
     bool profiling = false;
     std::vector<brgpu::ProfEntry> prof;
@@ -201,7 +204,7 @@ void launch_bucket_partition(brgpu_ctx *ctx, const Layout &L, const uint8_t *d_s
                              uint16_t *d_residues, uint32_t *d_coarse_kmers, uint64_t *d_coarse_base, double n_kmers);
 void launch_bucket_count(brgpu_ctx *ctx, const uint16_t *d_residues, const uint64_t *d_base, uint64_t n_buckets,
                          int abundance, uint8_t *d_bits, uint32_t *d_summary, int summary_shift, uint64_t *d_hist,
-                         double n_kmers);
+                         double n_kmers, bool prezeroed = false);
 void launch_bucket_count_multi(brgpu_ctx *ctx, const uint16_t *const *d_res, const uint64_t *const *d_base, int n_src,
                                uint64_t b0, uint64_t b1, int abundance, uint8_t *d_bits, uint32_t *d_summary,
                                uint64_t *d_hist, double n_kmers);

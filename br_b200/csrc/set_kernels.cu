@@ -586,15 +586,32 @@ constexpr int BUCKET_REG_ROUNDS = 4; // residues kept in registers per thread be
 //   a warp per bucket with a 1024-entry shared-memory hash table instead of the counter array (9.6 KB per
 //       bucket, 20 buckets in flight per SM) 2.3-2.6 ms: per-lane linear probing diverges (8.7 of 32 lanes
 //       active per instruction, 1.22 G warp instructions against 0.92 G).
-template <int THREADS, int ROUNDS>
+// DIRECT: bitfield and summary were zeroed beforehand (a memset that runs beside the partition kernels) and
+// the owners of solid k-mers set their bits in global memory (a few million `red.or` per step, absorbed by
+// L2) — no slice in shared memory, nothing to zero or to write per bucket, two barriers instead of five,
+// and one more bucket in flight per SM.
+template <int THREADS, int ROUNDS, bool DIRECT>
 __global__ void __launch_bounds__(THREADS)
     bucket_count_kernel(const uint16_t *__restrict__ residues, const uint64_t *__restrict__ base, uint64_t n_buckets,
                         int abundance, uint32_t *__restrict__ bitfield32, uint32_t *__restrict__ summary32,
                         int summary_shift, unsigned long long *__restrict__ g_hist) {
     extern __shared__ uint32_t cnt[];          // BUCKET_COUNTERS / 4 words of u8 counters
-    __shared__ uint64_t sh_bits64[BUCKET_COUNTERS / 64]; // the bucket's slice of the bitfield
+    __shared__ uint64_t sh_bits64[DIRECT ? 1 : BUCKET_COUNTERS / 64]; // the bucket's slice of the bitfield
     __shared__ unsigned int sh_hist[256];
     uint32_t *sh_bits = reinterpret_cast<uint32_t *>(sh_bits64);
+    const bool emit = bitfield32 != nullptr;
+    const bool emit_summary = summary32 != nullptr && summary_shift == 6;
+    auto set_bit = [&](uint64_t b, uint32_t r) { // r: residue of a solid k-mer of bucket b
+        if (DIRECT) {
+            if (emit) {
+                const uint64_t bit = b * BUCKET_COUNTERS + r;
+                atomicOr(bitfield32 + (bit >> 5), 1u << (bit & 31));
+                if (emit_summary) atomicOr(summary32 + (bit >> 11), 1u << ((bit >> 6) & 31));
+            }
+        } else {
+            atomicOr(&sh_bits[r >> 5], 1u << (r & 31));
+        }
+    };
     uint8_t *cnt8 = reinterpret_cast<uint8_t *>(cnt);
     for (int t = threadIdx.x; t < 256; t += THREADS) sh_hist[t] = 0;
     for (int t = threadIdx.x; t < BUCKET_COUNTERS / 4; t += THREADS) cnt[t] = 0; // once: owners keep it clean
@@ -626,7 +643,8 @@ __global__ void __launch_bounds__(THREADS)
             nb_begin = __ldg(base + b + gridDim.x);
             nb_end = __ldg(base + b + gridDim.x + 1);
         }
-        for (int t = threadIdx.x; t < BUCKET_COUNTERS / 32; t += THREADS) sh_bits[t] = 0;
+        if (!DIRECT)
+            for (int t = threadIdx.x; t < BUCKET_COUNTERS / 32; t += THREADS) sh_bits[t] = 0;
         // ---- phase 1: saturating increments ----
         uint32_t own = 0; // bit q: res[q] is an owner
 #pragma unroll
@@ -651,7 +669,7 @@ __global__ void __launch_bounds__(THREADS)
                 else if (c == 2) c2++;
                 else if (c == 3) c3++;
                 else atomicAdd(&sh_hist[c], 1u);
-                if (c > (uint32_t)abundance) atomicOr(&sh_bits[r >> 5], 1u << (r & 31));
+                if (c > (uint32_t)abundance) set_bit(b, r);
             }
         }
         // big buckets: the overflow occurrences claim their counter with an atomic swap-to-zero —
@@ -665,12 +683,12 @@ __global__ void __launch_bounds__(THREADS)
             if (c) { // not yet claimed by a register-held owner or another overflow occurrence
                 owners++;
                 atomicAdd(&sh_hist[c], 1u);
-                if (c > (uint32_t)abundance) atomicOr(&sh_bits[r >> 5], 1u << (r & 31));
+                if (c > (uint32_t)abundance) set_bit(b, r);
             }
         }
-        __syncthreads();
+        __syncthreads(); // every counter of this bucket is clean again (DIRECT: the next bucket may start)
         // ---- write the slice of the bitfield (+ its summary bits) ----
-        if (bitfield32) {
+        if (!DIRECT && bitfield32) {
             uint64_t *bitfield64 = reinterpret_cast<uint64_t *>(bitfield32) + b * (BUCKET_COUNTERS / 64);
             uint32_t *summary = summary32 && summary_shift == 6 ? summary32 + b * (BUCKET_COUNTERS / 64 / 32) : nullptr;
 #pragma unroll 4
@@ -686,7 +704,7 @@ __global__ void __launch_bounds__(THREADS)
         if (threadIdx.x == 0) zeros += BUCKET_COUNTERS;
         begin = nb_begin;
         end = nb_end;
-        __syncthreads(); // sh_bits is re-zeroed at the top of the next iteration
+        if (!DIRECT) __syncthreads(); // sh_bits is re-zeroed at the top of the next iteration
     }
     // hist[0] = counters nobody touched = all counters of this block's buckets - owners
     c1 = __reduce_add_sync(FULL, c1);
@@ -1156,44 +1174,48 @@ void launch_bucket_partition(brgpu_ctx *ctx, const Layout &L, const uint8_t *d_s
     }
 }
 
-template <int THREADS, int ROUNDS>
+template <int THREADS, int ROUNDS, bool DIRECT>
 static void launch_bucket_count_shape(brgpu_ctx *ctx, const uint16_t *d_residues, const uint64_t *d_base, uint64_t n_buckets,
                                       int abundance, uint8_t *d_bits, uint32_t *d_summary, int summary_shift, uint64_t *d_hist) {
     static bool configured = false;
     if (!configured) {
-        cudaFuncSetAttribute(bucket_count_kernel<THREADS, ROUNDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, BUCKET_COUNTERS);
-        cudaFuncSetAttribute(bucket_count_kernel<THREADS, ROUNDS>, cudaFuncAttributePreferredSharedMemoryCarveout,
+        cudaFuncSetAttribute(bucket_count_kernel<THREADS, ROUNDS, DIRECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, BUCKET_COUNTERS);
+        cudaFuncSetAttribute(bucket_count_kernel<THREADS, ROUNDS, DIRECT>, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
         configured = true;
     }
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bucket_count_kernel<THREADS, ROUNDS>, THREADS, BUCKET_COUNTERS) !=
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bucket_count_kernel<THREADS, ROUNDS, DIRECT>, THREADS, BUCKET_COUNTERS) !=
             cudaSuccess || per_sm < 1) {
         cudaGetLastError();
         per_sm = 1;
     }
     const uint64_t cap = (uint64_t)ctx->sm_count * (uint64_t)per_sm;
-    bucket_count_kernel<THREADS, ROUNDS><<<(unsigned)(n_buckets < cap ? n_buckets : cap), THREADS, BUCKET_COUNTERS, ctx->stream>>>(
+    bucket_count_kernel<THREADS, ROUNDS, DIRECT><<<(unsigned)(n_buckets < cap ? n_buckets : cap), THREADS, BUCKET_COUNTERS, ctx->stream>>>(
         d_residues, d_base, n_buckets, abundance, reinterpret_cast<uint32_t *>(d_bits), d_summary, summary_shift,
         reinterpret_cast<unsigned long long *>(d_hist));
 }
 
 void launch_bucket_count(brgpu_ctx *ctx, const uint16_t *d_residues, const uint64_t *d_base, uint64_t n_buckets,
                          int abundance, uint8_t *d_bits, uint32_t *d_summary, int summary_shift, uint64_t *d_hist,
-                         double n_kmers) {
+                         double n_kmers, bool prezeroed) {
     // 2 B residue in per k-mer + the slice's share of the bitfield out (a sweep that reads the
     // residues twice for the rare buckets that overflow the register rounds is not counted)
     ProfScope ps(ctx, "bucket_count", n_kmers * 2.0 + (double)n_buckets * (BUCKET_COUNTERS / 8));
     const double mean = n_kmers / (double)(n_buckets ? n_buckets : 1);
     const int shape = ctx->opt_count_block_only; // 0 / 1: 256 threads, 2: 128, 3: 64 (A/B runs, tests)
     (void)mean;
-    if (shape == 3)
-        launch_bucket_count_shape<64, 12>(ctx, d_residues, d_base, n_buckets, abundance, d_bits, d_summary, summary_shift, d_hist);
+    // prezeroed: the caller zeroed bitfield and summary (or wants no output): owners write their bits directly
+    if (prezeroed && (d_summary == nullptr || summary_shift == 6) && shape != 1)
+        launch_bucket_count_shape<BUCKET_THREADS, BUCKET_REG_ROUNDS, true>(ctx, d_residues, d_base, n_buckets, abundance, d_bits,
+                                                                           d_summary, summary_shift, d_hist);
+    else if (shape == 3)
+        launch_bucket_count_shape<64, 12, false>(ctx, d_residues, d_base, n_buckets, abundance, d_bits, d_summary, summary_shift, d_hist);
     else if (shape == 2)
-        launch_bucket_count_shape<128, 6>(ctx, d_residues, d_base, n_buckets, abundance, d_bits, d_summary, summary_shift, d_hist);
+        launch_bucket_count_shape<128, 6, false>(ctx, d_residues, d_base, n_buckets, abundance, d_bits, d_summary, summary_shift, d_hist);
     else
-        launch_bucket_count_shape<BUCKET_THREADS, BUCKET_REG_ROUNDS>(ctx, d_residues, d_base, n_buckets, abundance, d_bits, d_summary,
-                                                                     summary_shift, d_hist);
+        launch_bucket_count_shape<BUCKET_THREADS, BUCKET_REG_ROUNDS, false>(ctx, d_residues, d_base, n_buckets, abundance, d_bits,
+                                                                            d_summary, summary_shift, d_hist);
 }
 
 // ------------------------------------------------------------------------------------------
