@@ -79,7 +79,11 @@ Args parse(int argc, char **argv) {
     // a multi-valued option takes every following token up to the next option / sub-command
     auto values = [&](const std::string &flag, std::vector<std::string> &dst, bool stop_at_sub) {
         size_t before = dst.size();
-        while (i + 1 < argc && argv[i + 1][0] != '-' && !(stop_at_sub && is_sub(argv[i + 1]))) dst.push_back(argv[++i]);
+        auto is_method = [](const std::string &v) { // the abundance sub-sub-commands end a value list too (clap)
+            return v == "first-minimum" || v == "rarefaction" || v == "percent-most" || v == "percent-least";
+        };
+        while (i + 1 < argc && argv[i + 1][0] != '-' && !(stop_at_sub && is_sub(argv[i + 1])) && !(!stop_at_sub && is_method(argv[i + 1])))
+            dst.push_back(argv[++i]);
         if (dst.size() == before) usage_error("a value is required for '" + flag + "'");
     };
     for (; i < argc; i++) {
