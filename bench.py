@@ -686,6 +686,26 @@ def leg_record(m, wl, total_bases, steps, warmup, table, hbm_peak, sm_max_mhz, l
     kernels = kernel_table(m["prof"], steps, n_bases, n_kmers, table, hbm_peak, issue_peak, l2_gather, counters)
     dominant = max(m["prof"], key=lambda k_: m["prof"][k_]["ms"])
     dk = kernels[dominant]
+    # SURVEY §8(d) aggregates: the count path as a whole (0.25 B/base + 64 B/k-mer over the time of its kernels) and
+    # the solidity lookups of the step (bitmap passes + every KmerSet::get of the scans) per second of the step
+    count_names = ("coarse_hist", "coarse_scatter", "fine_partition", "bucket_count", "bucket_count_multi", "peer_residue_copy",
+                   "bucket_hist", "bucket_scatter", "count_kmers", "zero_counts", "spectrum_threshold", "spectrum", "summary_popc",
+                   "compact_blocks", "build_summary", "exclusive_scan")
+    count_ms = sum(m["prof"][k_]["ms"] for k_ in m["prof"] if k_ in count_names) / steps
+    scan_excl = sum(m["prof"][k_]["ms"] for k_ in m["prof"] if k_ == "exclusive_scan") / steps
+    count_bytes = 0.25 * n_bases + 64.0 * n_kmers
+    lookups_step = sum(p_["lookups"] for p_ in m["prof"].values()) / steps
+    aggregates = {
+        "count_path": {"ms_per_step": round(count_ms, 4), "algorithmic_bytes": count_bytes,
+                       "achieved_gbs": round(count_bytes / (count_ms * 1e-3) / 1e9, 1) if count_ms else None,
+                       "frac_of_hbm": round(count_bytes / (count_ms * 1e-3) / 1e9 / hbm_peak, 4) if count_ms else None,
+                       "note": "0.25 B/base + 64 B/k-mer (SURVEY §8d) over the summed time of the set-construction kernels "
+                               "(the exclusive scans of the correction passes are in: %.3f ms)" % scan_excl},
+        "solid_lookups": {"per_step": lookups_step, "per_s_over_step": round(lookups_step / (m["ms_prof"] / steps * 1e-3), 1),
+                          "sector_view_gbs": round(32.0 * lookups_step / (m["ms_prof"] / steps * 1e-3) / 1e9, 1),
+                          "note": "bitmap passes + every KmerSet::get of the scans, counted by the profiling variant of the "
+                                  "kernels; sector_view = 32 B per lookup over the whole (profiled) step"},
+    }
     rec = {
         "metric": METRIC, "value": total_bases * steps / (m["ms_dev"] * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps,
         "warmup": warmup, "ms_per_step": m["ms_dev"] / steps, "higher_is_better": True, "scaling": scaling,
@@ -696,6 +716,7 @@ def leg_record(m, wl, total_bases, steps, warmup, table, hbm_peak, sm_max_mhz, l
                          traffic_source=counters_src, algorithmic_bytes_per_launch=dk["algo_bytes_per_launch"],
                          hbm_view=dk["hbm_view"], lookups_per_launch=dk["lookups_per_launch"],
                          warp_inst_per_launch=dk.get("warp_inst_per_launch_ncu")),
+        "aggregates": aggregates,
         "kernels": kernels,
         "ms_per_step_with_kernel_events": m["ms_prof"] / steps,
     }
