@@ -22,6 +22,21 @@ using namespace brgpu;
 
 static inline void dfree(brgpu_ctx *ctx, void *p); // caching allocator, below
 
+// call-scoped device temporaries: whatever is still registered goes back to the context's cache when the
+// function returns, on every path (the CK() early returns used to leave blocks in pool_live)
+struct Temps {
+    brgpu_ctx *ctx;
+    std::vector<void *> blocks;
+    explicit Temps(brgpu_ctx *c) : ctx(c) {}
+    Temps(const Temps &) = delete;
+    Temps &operator=(const Temps &) = delete;
+    ~Temps();
+    template <class T> T *keep(T *p) {
+        if (p) blocks.push_back((void *)p);
+        return p;
+    }
+};
+
 namespace brgpu {
 
 int fail(brgpu_ctx *ctx, int code, const char *what, cudaError_t e) {
@@ -201,6 +216,9 @@ template <class T> static cudaError_t dalloc(brgpu_ctx *ctx, T **p, uint64_t cou
     return pool_alloc(ctx, (void **)p, count * sizeof(T));
 }
 static inline void dfree(brgpu_ctx *ctx, void *p) { pool_release(ctx, p); }
+Temps::~Temps() {
+    for (void *p : blocks) dfree(ctx, p);
+}
 
 // ------------------------------------------------------------------------------------------
 // context
@@ -1842,11 +1860,12 @@ extern "C" int brgpu_set_insert_batch(brgpu_set *s, const uint64_t *kmers_host, 
     if (!n) return BRGPU_OK;
     if (s->is_hash) return hash_insert_host_keys(s, kmers_host, n);
     uint64_t *d_k = nullptr;
+    Temps tmp(ctx);
     CK(dalloc(ctx, &d_k, n));
+    tmp.keep(d_k);
     CK(cudaMemcpyAsync(d_k, kmers_host, n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
     s->summary_valid = false;
     launch_insert_batch(ctx, s->d_bits, s->k, d_k, n);
-    dfree(ctx, d_k);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(ctx->stream));
     return BRGPU_OK;
@@ -1926,16 +1945,17 @@ extern "C" int brgpu_set_get_batch(brgpu_set *s, const uint64_t *kmers_host, uin
     if (!n) return BRGPU_OK;
     uint64_t *d_k = nullptr;
     uint8_t *d_o = nullptr;
+    Temps tmp(ctx);
     CK(dalloc(ctx, &d_k, n));
+    tmp.keep(d_k);
     CK(dalloc(ctx, &d_o, n));
+    tmp.keep(d_o);
     CK(cudaMemcpyAsync(d_k, kmers_host, n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
     if (s->is_hash)
         launch_get_batch_view(ctx, set_view(s), d_k, n, d_o);
     else
         launch_get_batch(ctx, s->d_bits, s->k, d_k, n, d_o);
     CK(cudaMemcpyAsync(out_host, d_o, n, cudaMemcpyDeviceToHost, ctx->stream));
-    dfree(ctx, d_k);
-    dfree(ctx, d_o);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(ctx->stream));
     return BRGPU_OK;
@@ -2087,18 +2107,18 @@ static int reads_reslot(brgpu_reads *in, unsigned slack_extra, brgpu_reads **out
     brgpu_ctx *ctx = in->ctx;
     const uint64_t n = in->layout->n;
     uint64_t *d_toff = nullptr, total = 0;
+    Temps tmp(ctx);
     int st = reads_tight_offsets(in, &d_toff, &total);
     if (st != BRGPU_OK) return st;
+    tmp.keep(d_toff);
     std::vector<uint64_t> h_off(n + 1);
     uint8_t *d_tight = nullptr;
     CK(dalloc(ctx, &d_tight, total));
+    tmp.keep(d_tight);
     launch_gather_from_slots(ctx, *in->layout, in->d_seq, in->d_len, d_toff, d_tight, false);
     CK(cudaMemcpyAsync(h_off.data(), d_toff, (n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    st = reads_from_tight(ctx, d_tight, true, h_off.data(), n, slack_extra, out);
-    dfree(ctx, d_tight);
-    dfree(ctx, d_toff);
-    return st;
+    return reads_from_tight(ctx, d_tight, true, h_off.data(), n, slack_extra, out);
 }
 
 extern "C" int brgpu_correct_reads(brgpu_ctx *ctx, const brgpu_set *set, const uint8_t *methods, uint64_t n_methods,
