@@ -88,6 +88,8 @@ SIGNATURES = {
     "brgpu_set_commit_slices": (C.c_int, [vp, C.c_int]),
     "brgpu_set_free": (None, [vp]),
     "brgpu_correct_reads": (C.c_int, [vp, vp, vp, u64, C.c_int, C.c_int, C.c_int, vp, pvp]),
+    "brgpu_correct_reads_async": (C.c_int, [vp, vp, vp, u64, C.c_int, C.c_int, C.c_int, vp, pvp]),
+    "brgpu_reads_wait": (C.c_int, [vp]),
     "brgpu_correct_batch": (C.c_int, [vp, vp, vp, u64, C.c_int, C.c_int, C.c_int, vp, vp, u64, vp, u64, vp, pu64]),
     "brgpu_correct_one": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp, u64, vp, u64, pu64]),
     "brgpu_counts_ipc_export": (C.c_int, [vp, vp]),

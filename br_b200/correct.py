@@ -132,15 +132,21 @@ def _chain_params(methods):
     return ids, (confirm.pop() if confirm else DEFAULT_CONFIRM), (max_search.pop() if max_search else DEFAULT_MAX_SEARCH), solid
 
 
-def correct_reads(methods, reads: Reads, two_side=False) -> Reads:
-    """Device-resident chunk in, device-resident corrected chunk out (input order kept)."""
+def correct_reads(methods, reads: Reads, two_side=False, asynchronous=False) -> Reads:
+    """Device-resident chunk in, device-resident corrected chunk out (input order kept).
+    asynchronous: return once the chain is enqueued (brgpu_correct_reads_async); the set and `reads` must
+    stay alive until the result's first use (download, `.bases`, `.wait()`)."""
     ids, confirm, max_search, solid = _chain_params(methods)
     if solid is None:
         raise ValueError("empty method list")
     h = C.c_void_p()
-    check(lib.brgpu_correct_reads(solid.ctx._h, solid._h, _ptr(ids), ids.size, confirm, max_search, int(bool(two_side)),
-                                  reads._h, C.byref(h)), solid.ctx._h)
-    return Reads(solid.ctx, h)
+    f = lib.brgpu_correct_reads_async if asynchronous else lib.brgpu_correct_reads
+    check(f(solid.ctx._h, solid._h, _ptr(ids), ids.size, confirm, max_search, int(bool(two_side)), reads._h, C.byref(h)),
+          solid.ctx._h)
+    out = Reads(solid.ctx, h)
+    if asynchronous:
+        out._keep = (solid, reads)
+    return out
 
 
 def correct_batch(methods, seq, offsets, two_side=False, out=None, out_offsets=None):

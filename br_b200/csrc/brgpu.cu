@@ -407,8 +407,11 @@ static int make_layout(brgpu_ctx *ctx, const uint32_t *h_len, uint64_t n, unsign
 // A consumer of reads that may still be uploading on the copy stream: order the compute stream
 // after the upload and hand the upload's temporaries back to the allocator (everything enqueued
 // from here on, on either stream, runs after the upload).
+static void reads_resolve(brgpu_reads *r); // below (needs the correction entry point)
+
 static void reads_ready(const brgpu_reads *cr) {
     brgpu_reads *r = const_cast<brgpu_reads *>(cr);
+    if (r && r->pending) reads_resolve(r);
     if (!r || !r->ready) return;
     cudaStreamWaitEvent(r->ctx->stream, r->ready, 0);
     // later uploads reuse these blocks on the copy stream: they are fenced behind the compute stream
@@ -630,6 +633,7 @@ extern "C" int brgpu_reads_download(brgpu_reads *reads, uint8_t *seq_host, uint6
     brgpu_ctx *ctx = reads->ctx;
     cudaSetDevice(ctx->device);
     reads_ready(reads);
+    if (reads->resolve_status != BRGPU_OK) return fail(ctx, reads->resolve_status, "the asynchronous correction that produced these reads failed");
     const Layout &L = *reads->layout;
     uint64_t *d_toff = nullptr, total = 0;
     int st = reads_tight_offsets(reads, &d_toff, &total);
@@ -695,6 +699,7 @@ extern "C" int brgpu_reads_download_async(brgpu_reads *reads, uint8_t *seq_host,
     cudaSetDevice(ctx->device);
     if (reads->dl_done) return fail(ctx, BRGPU_E_INVALID, "a download of these reads is already in flight");
     reads_ready(reads);
+    if (reads->resolve_status != BRGPU_OK) return fail(ctx, reads->resolve_status, "the asynchronous correction that produced these reads failed");
     const Layout &L = *reads->layout;
     uint64_t *d_toff = nullptr, total = 0;
     int st = reads_tight_offsets(reads, &d_toff, &total); // waits for the producer of these reads
@@ -860,6 +865,7 @@ static int download_packed(brgpu_reads *reads, uint8_t *packed_host, uint64_t pa
     cudaSetDevice(ctx->device);
     if (reads->dl_done) return fail(ctx, BRGPU_E_INVALID, "a download of these reads is already in flight");
     reads_ready(reads);
+    if (reads->resolve_status != BRGPU_OK) return fail(ctx, reads->resolve_status, "the asynchronous correction that produced these reads failed");
     const Layout &L = *reads->layout;
     uint64_t *d_toff = nullptr, total = 0;
     int st = reads_tight_offsets(reads, &d_toff, &total); // waits for the producer of these reads
@@ -1982,7 +1988,8 @@ static int validate_methods(brgpu_ctx *ctx, const uint8_t *methods, uint64_t n_m
 
 // one attempt at the whole chain on the given layout; *overflow tells whether a read outgrew its slot
 static int correct_attempt(brgpu_ctx *ctx, const brgpu_set *set, const uint8_t *methods, uint64_t n_methods, int confirm,
-                           int max_search, int two_side, const brgpu_reads *in, brgpu_reads **out, bool *overflow) {
+                           int max_search, int two_side, const brgpu_reads *in, brgpu_reads **out, bool *overflow,
+                           bool async = false) {
     const Layout &L = *in->layout;
     const uint64_t n = L.n;
     uint8_t *buf[2] = {nullptr, nullptr};
@@ -2069,17 +2076,18 @@ static int correct_attempt(brgpu_ctx *ctx, const brgpu_set *set, const uint8_t *
         src = buf[0];
         src_len = len[0];
     }
+    const int flag_slot = async ? 384 + (int)(ctx->next_flag_slot++ % 64u) : 0;
     e = cudaGetLastError();
     if (e == cudaSuccess) {
-        launch_readback(ctx, ctx->h_pinned, ctx->d_flags + 1, sizeof(uint32_t));
+        launch_readback(ctx, ctx->h_pinned + flag_slot, ctx->d_flags + 1, sizeof(uint32_t));
         e = cudaGetLastError();
     }
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess && !async) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) {
         cleanup();
         return fail(ctx, BRGPU_E_CUDA, "correction kernels", e);
     }
-    *overflow = (*(volatile uint32_t *)ctx->h_pinned) != 0;
+    *overflow = !async && (*(volatile uint32_t *)ctx->h_pinned) != 0; // async: looked at by the first consumer
     if (*overflow) {
         cleanup();
         return BRGPU_OK;
@@ -2092,6 +2100,8 @@ static int correct_attempt(brgpu_ctx *ctx, const brgpu_set *set, const uint8_t *
     R->ctx = ctx;
     R->layout = in->layout;
     R->sum_len = in->sum_len; // hint only: lengths change by a few bases per event
+    R->pending = async;
+    R->flag_slot = flag_slot;
     int keep = (src == buf[0]) ? 0 : 1;
     R->d_seq = buf[keep];
     R->d_len = len[keep];
@@ -2121,8 +2131,8 @@ static int reads_reslot(brgpu_reads *in, unsigned slack_extra, brgpu_reads **out
     return reads_from_tight(ctx, d_tight, true, h_off.data(), n, slack_extra, out);
 }
 
-extern "C" int brgpu_correct_reads(brgpu_ctx *ctx, const brgpu_set *set, const uint8_t *methods, uint64_t n_methods,
-                                   int confirm, int max_search, int two_side, const brgpu_reads *in, brgpu_reads **out) {
+static int correct_reads_impl(brgpu_ctx *ctx, const brgpu_set *set, const uint8_t *methods, uint64_t n_methods,
+                              int confirm, int max_search, int two_side, const brgpu_reads *in, brgpu_reads **out, bool async) {
     if (!ctx || !set || !in || !out) return ctx ? fail(ctx, BRGPU_E_INVALID, "null argument") : BRGPU_E_INVALID;
     *out = nullptr;
     if (set->ctx != ctx || in->ctx != ctx) return fail(ctx, BRGPU_E_INVALID, "handles belong to another context");
@@ -2130,8 +2140,23 @@ extern "C" int brgpu_correct_reads(brgpu_ctx *ctx, const brgpu_set *set, const u
     if (st != BRGPU_OK) return st;
     cudaSetDevice(ctx->device);
     reads_ready(in);
+    if (in->resolve_status != BRGPU_OK) return fail(ctx, in->resolve_status, "the asynchronous correction that produced these reads failed");
     st = ensure_summary(const_cast<brgpu_set *>(set));
     if (st != BRGPU_OK) return st;
+    if (async) { // one attempt, no look at its overflow flag: the first consumer of *out does that (reads_resolve)
+        bool overflow = false;
+        st = correct_attempt(ctx, set, methods, n_methods, confirm, max_search, two_side, in, out, &overflow, true);
+        if (st == BRGPU_OK && *out) {
+            brgpu_reads *R = *out;
+            R->redo_set = set;
+            R->redo_in = in;
+            R->redo_methods.assign(methods, methods + n_methods);
+            R->redo_confirm = confirm;
+            R->redo_max_search = max_search;
+            R->redo_two_side = two_side;
+        }
+        return st;
+    }
 
     const brgpu_reads *cur = in;
     brgpu_reads *owned = nullptr;
@@ -2150,6 +2175,47 @@ extern "C" int brgpu_correct_reads(brgpu_ctx *ctx, const brgpu_set *set, const u
     if (owned) reads_release(owned);
     if (st == BRGPU_OK && !*out) st = fail(ctx, BRGPU_E_OVERFLOW, "a corrected read outgrew its slot after 8 retries");
     return st;
+}
+
+extern "C" int brgpu_correct_reads(brgpu_ctx *ctx, const brgpu_set *set, const uint8_t *methods, uint64_t n_methods,
+                                   int confirm, int max_search, int two_side, const brgpu_reads *in, brgpu_reads **out) {
+    return correct_reads_impl(ctx, set, methods, n_methods, confirm, max_search, two_side, in, out, false);
+}
+
+extern "C" int brgpu_correct_reads_async(brgpu_ctx *ctx, const brgpu_set *set, const uint8_t *methods, uint64_t n_methods,
+                                         int confirm, int max_search, int two_side, const brgpu_reads *in, brgpu_reads **out) {
+    return correct_reads_impl(ctx, set, methods, n_methods, confirm, max_search, two_side, in, out, true);
+}
+
+// first consumer of an asynchronously corrected chunk: wait for the chain, look at its overflow flag and, if a
+// read outgrew its slot (rare: Graph paths), redo the chain synchronously with the retry loop
+static void reads_resolve(brgpu_reads *r) {
+    brgpu_ctx *ctx = r->ctx;
+    r->pending = false;
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+        r->resolve_status = fail(ctx, BRGPU_E_CUDA, "asynchronous correction", cudaGetLastError());
+        return;
+    }
+    if (*(volatile uint32_t *)(ctx->h_pinned + r->flag_slot) == 0) return;
+    brgpu_reads *redo = nullptr;
+    const int st = correct_reads_impl(ctx, r->redo_set, r->redo_methods.data(), r->redo_methods.size(), r->redo_confirm,
+                                      r->redo_max_search, r->redo_two_side, r->redo_in, &redo, false);
+    if (st != BRGPU_OK || !redo) {
+        r->resolve_status = st != BRGPU_OK ? st : BRGPU_E_OVERFLOW;
+        return;
+    }
+    std::swap(r->layout, redo->layout);
+    std::swap(r->d_seq, redo->d_seq);
+    std::swap(r->d_len, redo->d_len);
+    r->sum_len = redo->sum_len;
+    reads_release(redo);
+}
+
+extern "C" int brgpu_reads_wait(brgpu_reads *reads) {
+    if (!reads) return BRGPU_E_INVALID;
+    cudaSetDevice(reads->ctx->device);
+    reads_ready(reads);
+    return reads->resolve_status;
 }
 
 extern "C" int brgpu_correct_batch(brgpu_ctx *ctx, const brgpu_set *set, const uint8_t *methods, uint64_t n_methods,

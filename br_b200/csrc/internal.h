@@ -18,6 +18,7 @@ struct ProfEntry {
     std::string name;
     double ms = 0.0;
     uint64_t launches = 0;
+    unsigned next_flag_slot = 0; // rotating slots of h_pinned for the overflow flags of asynchronous corrections
     double bytes = 0.0;
     uint64_t lookups = 0; // KmerSet::get calls the kernel issued (scan kernels, counted while profiling)
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
@@ -42,6 +43,7 @@ struct brgpu_ctx {
     std::vector<brgpu::ProfEntry> prof;
     std::vector<cudaEvent_t> event_pool;
     uint64_t launches = 0;
+    unsigned next_flag_slot = 0; // rotating slots of h_pinned for the overflow flags of asynchronous corrections
     // small device scratch reused by every call
     uint32_t *d_flags = nullptr; // [0] work-queue cursor, [1] overflow flag, [2..] spare
     uint64_t *d_hist = nullptr;  // 256 bins
@@ -91,6 +93,16 @@ struct brgpu_reads {
     cudaEvent_t ready = nullptr;     // upload in flight: consumers make the compute stream wait for it
     std::vector<void *> deferred;    // upload temporaries, released once a consumer has ordered itself after `ready`
     cudaEvent_t dl_done = nullptr;   // download in flight
+    // asynchronous correction (brgpu_correct_reads_async): the chain is enqueued, its overflow flag has not been
+    // looked at yet; the first consumer (reads_ready) synchronises and, in the rare overflow case, redoes the
+    // chain synchronously from the input the caller promised to keep alive
+    bool pending = false;
+    int flag_slot = 0; // index into ctx->h_pinned
+    const brgpu_set *redo_set = nullptr;
+    const brgpu_reads *redo_in = nullptr;
+    std::vector<uint8_t> redo_methods;
+    int redo_confirm = 0, redo_max_search = 0, redo_two_side = 0;
+    int resolve_status = 0; // BRGPU_OK, or what the redo returned
     void *dl_tight = nullptr, *dl_toff = nullptr;
     std::vector<void *> dl_more;     // further device buffers of an in-flight packed download
 };

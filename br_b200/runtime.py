@@ -272,6 +272,11 @@ class Reads:
         self._dl = (out, out_offsets)
         return int(req.value)
 
+    def wait(self):
+        """Completes an asynchronous correction (brgpu_reads_wait): the chain has run, overflow handled."""
+        check(lib.brgpu_reads_wait(self._h), self.ctx._h)
+        self._keep = None
+
     def download_wait(self):
         check(lib.brgpu_reads_download_wait(self._h), self.ctx._h)
         self._dl = None

@@ -239,6 +239,15 @@ void brgpu_set_free(brgpu_set *set);
 int brgpu_correct_reads(brgpu_ctx *ctx, const brgpu_set *set, const uint8_t *methods, uint64_t n_methods, int confirm,
                         int max_search, int two_side, const brgpu_reads *in, brgpu_reads **out);
 
+/* brgpu_correct_reads without the wait at its end: the chain is enqueued and the call returns, so that the
+ * host can stage the next chunk and issue the previous chunk's download while the kernels run.  The first
+ * call that takes *out (a download, brgpu_reads_bases, another correction, brgpu_reads_wait) waits for the
+ * chain and, if a read outgrew its slot, redoes it synchronously — `set` and `in` must stay alive until
+ * then.  brgpu_reads_wait returns the status of that step. */
+int brgpu_correct_reads_async(brgpu_ctx *ctx, const brgpu_set *set, const uint8_t *methods, uint64_t n_methods,
+                              int confirm, int max_search, int two_side, const brgpu_reads *in, brgpu_reads **out);
+int brgpu_reads_wait(brgpu_reads *reads);
+
 int brgpu_correct_batch(brgpu_ctx *ctx, const brgpu_set *set, const uint8_t *methods, uint64_t n_methods, int confirm,
                         int max_search, int two_side, const uint8_t *seq_host, const uint64_t *offsets_host,
                         uint64_t n_reads, uint8_t *out_host, uint64_t out_cap, uint64_t *out_offsets_host,

@@ -193,6 +193,41 @@ def test_graph_path_longer_than_the_slot_triggers_reslot(gpu, oracle):
     assert [got[int(got_off[i]) : int(got_off[i + 1])].tobytes() for i in range(3)] == [exp] * 3
 
 
+def test_asynchronous_correction_matches_the_synchronous_call(gpu, oracle, fixture_sets, fixture_reads):
+    """brgpu_correct_reads_async returns once the chain is enqueued; the first consumer waits for it.  Same
+    bytes as the synchronous call on the fixture, chained into a second asynchronous correction, and in the
+    overflow case (a Graph path that outgrows its slot: the chain is redone with the retry loop)."""
+    br, ctx = gpu
+    gs, os_ = fixture_sets
+    seq, off = fixture_reads
+    reads = br.Reads.upload(ctx, seq, off)
+    methods = br.build_methods(["one", "two", "gap_size"], gs, 4, 7)
+    a, ao = br.correct_reads(methods, reads).download()
+    pending = br.correct_reads(methods, reads, asynchronous=True)
+    second = br.correct_reads(br.build_methods(["one"], gs, 4, 7), pending, asynchronous=True)  # consumes `pending`
+    b, bo = pending.download()
+    assert np.array_equal(ao, bo) and np.array_equal(a, b)
+    second.wait()
+    c, co = second.download()
+    exp, exp_off = os_.run_correction([oracle.METHOD_IDS[m] for m in ("one", "two", "gap_size")], seq, off, confirm=4, threads=8)
+    assert np.array_equal(exp_off, ao) and np.array_equal(exp, a)
+    exp2, exp2_off = os_.run_correction([oracle.ONE], exp, exp_off, confirm=4, threads=8)
+    assert np.array_equal(exp2_off, co) and np.array_equal(exp2, c)
+    # overflow: the long Graph walk of test_graph_path_longer_than_the_slot_triggers_reslot
+    rng = np.random.default_rng(9)
+    refe = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=800)].tobytes()
+    read = refe[:60] + refe[360:440]
+    g2 = br.Pcon.new(ctx, 11)
+    g2.insert_all_kmers(refe)
+    want = oracle.Solid.from_bitfield(11, g2.bitfield()).correct(2, read)
+    r2 = br.Reads.upload(ctx, np.frombuffer(read * 2, dtype=np.uint8), np.array([0, len(read), 2 * len(read)], dtype=np.uint64))
+    out = br.correct_reads([br.Graph(g2)], r2, two_side=True, asynchronous=True)
+    got, got_off = out.download()
+    assert [got[int(got_off[i]) : int(got_off[i + 1])].tobytes() for i in range(2)] == [want] * 2
+    for h in (reads, pending, second, r2, out, g2):
+        h.free()
+
+
 def test_parameter_validation(gpu, fixture_sets):
     br, ctx = gpu
     gs, _ = fixture_sets
