@@ -877,10 +877,11 @@ static int download_packed(brgpu_reads *reads, uint8_t *packed_host, uint64_t pa
         dfree(ctx, d_toff);
         return fail(ctx, packed_bytes > packed_cap ? BRGPU_E_OVERFLOW : BRGPU_E_INVALID, "output buffer too small");
     }
-    uint8_t *d_packed = nullptr, *d_exc_byte = nullptr;
+    uint8_t *d_packed = nullptr, *d_exc_byte = nullptr, *d_tight = nullptr;
     uint64_t *d_exc_pos = nullptr;
     unsigned long long *d_cnt = nullptr;
-    cudaError_t e = dalloc(ctx, &d_packed, packed_bytes + 8);
+    cudaError_t e = dalloc(ctx, &d_packed, packed_bytes + 16);
+    if (e == cudaSuccess) e = dalloc(ctx, &d_tight, total + 32); // slots -> tight ASCII -> packed (two streaming passes)
     if (e == cudaSuccess) e = dalloc(ctx, &d_exc_pos, exc_cap);
     if (e == cudaSuccess) e = dalloc(ctx, &d_exc_byte, exc_cap);
     if (e == cudaSuccess) e = dalloc(ctx, &d_cnt, 1);
@@ -889,11 +890,14 @@ static int download_packed(brgpu_reads *reads, uint8_t *packed_host, uint64_t pa
             if (p) dfree(ctx, p);
     };
     if (e != cudaSuccess) {
+        if (d_tight) dfree(ctx, d_tight);
         drop();
         return fail(ctx, BRGPU_E_NOMEM, "device allocation (packed download)", e);
     }
     cudaMemsetAsync(d_cnt, 0, 8, ctx->stream);
-    launch_pack_from_slots(ctx, L, reads->d_seq, d_toff, total, d_packed, d_exc_pos, d_exc_byte, exc_cap, d_cnt);
+    launch_gather_from_slots(ctx, L, reads->d_seq, reads->d_len, d_toff, d_tight, false);
+    launch_pack_tight(ctx, d_tight, total, d_packed, d_exc_pos, d_exc_byte, exc_cap, d_cnt);
+    dfree(ctx, d_tight); // same stream: reusable as soon as the two kernels above have run
     cudaStream_t cs = ctx->stream;
     if (async) {
         e = cudaEventRecord(ctx->ev_fence, ctx->stream);

@@ -183,9 +183,8 @@ void launch_gather_from_slots(brgpu_ctx *ctx, const Layout &L, const uint8_t *d_
 // 2-bit transport: packed tight layout (+ exception list) <-> ASCII slot layout
 void launch_unpack_to_slots(brgpu_ctx *ctx, const Layout &L, const uint8_t *d_packed, const uint64_t *d_tight_off,
                             uint8_t *d_slots, const uint64_t *d_exc_pos, const uint8_t *d_exc_byte, uint64_t n_exc);
-void launch_pack_from_slots(brgpu_ctx *ctx, const Layout &L, const uint8_t *d_slots, const uint64_t *d_tight_off,
-                            uint64_t n_bases, uint8_t *d_packed, uint64_t *d_exc_pos, uint8_t *d_exc_byte, uint64_t exc_cap,
-                            unsigned long long *d_n_exc);
+void launch_pack_tight(brgpu_ctx *ctx, const uint8_t *d_tight, uint64_t n_bases, uint8_t *d_packed, uint64_t *d_exc_pos,
+                       uint8_t *d_exc_byte, uint64_t exc_cap, unsigned long long *d_n_exc);
 void launch_reverse_slots(brgpu_ctx *ctx, const Layout &L, const uint8_t *d_in, const uint32_t *d_len, uint8_t *d_out);
 void launch_exclusive_scan_u32(brgpu_ctx *ctx, const uint32_t *d_in, uint64_t n, uint64_t *d_out /* n+1 */,
                                uint64_t *d_tmp /* >= n/4096 + 2 */);

@@ -193,39 +193,50 @@ __global__ void apply_exceptions_kernel(const uint64_t *__restrict__ exc_pos, co
     }
 }
 
-// one thread per packed output byte (four tight positions); exceptions are appended in no particular order
-__global__ void pack_from_slots_kernel(const uint8_t *__restrict__ slots, const uint64_t *__restrict__ slot_off,
-                                       const uint64_t *__restrict__ tight_off, uint64_t n_reads, uint64_t n_bases,
-                                       uint8_t *__restrict__ packed, uint64_t *__restrict__ exc_pos,
-                                       uint8_t *__restrict__ exc_byte, uint64_t exc_cap,
-                                       unsigned long long *__restrict__ n_exc) {
-    const uint64_t n_bytes = (n_bases + 3) >> 2;
-    for (uint64_t b = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; b < n_bytes; b += (uint64_t)gridDim.x * blockDim.x) {
-        uint64_t t = b << 2;
-        uint64_t r = read_of_position(tight_off, n_reads, t);
-        uint64_t r_end = __ldg(tight_off + r + 1), r_beg = __ldg(tight_off + r), sbase = __ldg(slot_off + r);
-        uint32_t out = 0;
+// tight ASCII -> packed: one thread per 16 bases (one 16 B load, one 4 B store); exceptions are appended in no
+// particular order.  (The first version packed straight out of the slot layout, one thread per output byte
+// with its own read lookup: 0.64 ms per step on the E. coli configuration; gather + this pass: see DESIGN §2.)
+__global__ void __launch_bounds__(256)
+    pack_tight_kernel(const uint8_t *__restrict__ tight, uint64_t n_bases, uint32_t *__restrict__ packed32,
+                      uint64_t *__restrict__ exc_pos, uint8_t *__restrict__ exc_byte, uint64_t exc_cap,
+                      unsigned long long *__restrict__ n_exc) {
+    const uint64_t n_words = (n_bases + 15) >> 4;
+    for (uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < n_words; w += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t t0 = w << 4;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (t0 + 16 <= n_bases) {
+            v = __ldcs(reinterpret_cast<const uint4 *>(tight + t0)); // the staging buffer is 16 B aligned and padded
+        } else {
+            uint32_t q[4] = {0u, 0u, 0u, 0u};
+            for (uint64_t t = t0; t < n_bases; t++) q[(t - t0) >> 2] |= (uint32_t)tight[t] << (8 * ((t - t0) & 3));
+            v = make_uint4(q[0], q[1], q[2], q[3]);
+        }
+        const uint32_t codes = pack16(v); // first base in the top pair
+        // a byte is an exception unless it is the upper-case letter of its code: rebuild the letters and compare
+        const uint32_t in[4] = {v.x, v.y, v.z, v.w};
+        uint32_t bad = 0;
 #pragma unroll
-        for (int j = 0; j < 4; j++, t++) {
-            if (t >= n_bases) break;
-            while (t >= r_end) { // next (non-empty) read
-                r++;
-                r_beg = r_end;
-                r_end = __ldg(tight_off + r + 1);
-                sbase = __ldg(slot_off + r);
-            }
-            const uint8_t c = slots[sbase + (t - r_beg)];
-            const uint32_t code = nuc2bit(c);
-            out |= code << (2 * (3 - j));
-            if (c != bit2nuc(code)) {
-                const unsigned long long at = atomicAdd(n_exc, 1ULL);
-                if (at < exc_cap) {
-                    exc_pos[at] = t;
-                    exc_byte[at] = c;
-                }
+        for (int q = 0; q < 4; q++) {
+            uint32_t letters = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) letters |= (uint32_t)bit2nuc((codes >> (2 * (15 - (4 * q + j)))) & 3u) << (8 * j);
+            const uint32_t diff = in[q] ^ letters;
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if ((diff >> (8 * j)) & 0xffu) bad |= 1u << (4 * q + j);
+        }
+        if (t0 + 16 > n_bases) bad &= (1u << (n_bases - t0)) - 1u;
+        while (bad) {
+            const int j = __ffs(bad) - 1;
+            bad &= bad - 1;
+            const unsigned long long at = atomicAdd(n_exc, 1ULL);
+            if (at < exc_cap) {
+                exc_pos[at] = t0 + (uint64_t)j;
+                exc_byte[at] = (uint8_t)(in[j >> 2] >> (8 * (j & 3)));
             }
         }
-        packed[b] = (uint8_t)out;
+        // bytes of the packed stream in memory order: base 0..3 in byte 0 -> the big-endian image of `codes`
+        packed32[w] = __byte_perm(codes, 0u, 0x0123);
     }
 }
 
@@ -243,14 +254,13 @@ void launch_unpack_to_slots(brgpu_ctx *ctx, const Layout &L, const uint8_t *d_pa
     }
 }
 
-void launch_pack_from_slots(brgpu_ctx *ctx, const Layout &L, const uint8_t *d_slots, const uint64_t *d_tight_off,
-                            uint64_t n_bases, uint8_t *d_packed, uint64_t *d_exc_pos, uint8_t *d_exc_byte, uint64_t exc_cap,
-                            unsigned long long *d_n_exc) {
-    const uint64_t n_bytes = (n_bases + 3) >> 2;
-    if (!n_bytes) return;
-    ProfScope ps(ctx, "pack_from_slots", (double)n_bases * 1.25);
-    pack_from_slots_kernel<<<grid_for(ctx, n_bytes, 256, 8), 256, 0, ctx->stream>>>(d_slots, L.d_slot_off, d_tight_off, L.n, n_bases,
-                                                                                   d_packed, d_exc_pos, d_exc_byte, exc_cap, d_n_exc);
+void launch_pack_tight(brgpu_ctx *ctx, const uint8_t *d_tight, uint64_t n_bases, uint8_t *d_packed, uint64_t *d_exc_pos,
+                       uint8_t *d_exc_byte, uint64_t exc_cap, unsigned long long *d_n_exc) {
+    const uint64_t n_words = (n_bases + 15) >> 4;
+    if (!n_words) return;
+    ProfScope ps(ctx, "pack_tight", (double)n_bases * 1.25);
+    pack_tight_kernel<<<grid_for(ctx, n_words, 256, 8), 256, 0, ctx->stream>>>(d_tight, n_bases, reinterpret_cast<uint32_t *>(d_packed),
+                                                                              d_exc_pos, d_exc_byte, exc_cap, d_n_exc);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -29,3 +29,14 @@ with torch.cuda.stream(stream):
     print("upload_packed_async host ms:", [round(x, 3) for x in tu])
     print("download_packed_async host ms:", [round(x, 3) for x in td])
     print("wait+sync ms:", [round(x, 3) for x in tw])
+    # per-kernel times of the staging path (profiling on): upload -> unpack, download -> pack
+    ctx.profile_reset(); ctx.profile_enable(True)
+    for it in range(4):
+        r = br_b200.Reads.upload_packed(ctx, hp, ho, ep, eb)
+        o2 = br_b200.correct_reads(m, r)
+        o2.download_packed(*outp)
+        r.free(); o2.free()
+    prof = ctx.profile(); ctx.profile_enable(False)
+    for k, v in prof.items():
+        if not (k.startswith("scan_") or k.startswith("merge_") or k.startswith("solid_")):
+            print(f"  {k:20s} x{v['launches']/4:.0f} {v['ms']/max(1,v['launches']):.4f} ms")
