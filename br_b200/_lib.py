@@ -84,6 +84,9 @@ SIGNATURES = {
     "brgpu_set_spectrum": (C.c_int, [vp, vp]),
     "brgpu_set_device_ptr": (vp, [vp]),
     "brgpu_set_new_sliced": (C.c_int, [vp, C.c_int, pvp]),
+    "brgpu_set_slice_compact": (C.c_int, [vp, u64, u64, pvp, pu64]),
+    "brgpu_set_compact_alloc": (C.c_int, [vp, u64, pvp]),
+    "brgpu_set_compact_commit": (C.c_int, [vp]),
     "brgpu_set_summary_ptr": (vp, [vp, pu64]),
     "brgpu_set_commit_slices": (C.c_int, [vp, C.c_int]),
     "brgpu_set_free": (None, [vp]),

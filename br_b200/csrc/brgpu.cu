@@ -1112,6 +1112,8 @@ static void summary_geometry(int k, int *shift, uint64_t *bytes) {
 // negative lookup from L2, so it is built as long as the blocks take less than half the bitfield.
 static uint64_t compact_max_block_bytes(const brgpu_set *s) { return s->n_bytes / 2; }
 
+static int ensure_dense(brgpu_set *s); // below: the dense bitfield of a set held in rank-compacted form only
+
 static void compact_release(brgpu_set *s) {
     if (s->d_dir) big_free(s->ctx, s->d_dir, s->dir_bytes);
     if (s->d_blocks) big_free(s->ctx, s->d_blocks, s->blocks_bytes);
@@ -1181,6 +1183,10 @@ static int build_compact(brgpu_set *s) {
 static int ensure_summary(brgpu_set *s) {
     brgpu_ctx *ctx = s->ctx;
     if (s->is_hash || s->summary_valid) return BRGPU_OK;
+    if (!s->bits_complete) { // the summary is rebuilt from the dense bitfield
+        const int st = ensure_dense(s);
+        if (st != BRGPU_OK) return st;
+    }
     compact_release(s);
     int shift;
     uint64_t bytes;
@@ -1219,6 +1225,7 @@ extern "C" void brgpu_set_free(brgpu_set *s) {
     if (!s) return;
     cudaSetDevice(s->ctx->device);
     compact_release(s);
+    if (s->d_slice_blocks) big_free(s->ctx, s->d_slice_blocks, s->slice_blocks_bytes);
     if (s->d_summary) big_free(s->ctx, s->d_summary, s->summary_bytes);
     if (s->d_bits) big_free(s->ctx, s->d_bits, bits_alloc_bytes(s->k));
     if (s->d_hash) big_free(s->ctx, s->d_hash, s->hash_slots * 8);
@@ -1869,6 +1876,10 @@ extern "C" int brgpu_set_insert_batch(brgpu_set *s, const uint64_t *kmers_host, 
     cudaSetDevice(ctx->device);
     if (!n) return BRGPU_OK;
     if (s->is_hash) return hash_insert_host_keys(s, kmers_host, n);
+    {
+        const int st = ensure_dense(s);
+        if (st != BRGPU_OK) return st;
+    }
     uint64_t *d_k = nullptr;
     Temps tmp(ctx);
     CK(dalloc(ctx, &d_k, n));
@@ -1889,8 +1900,114 @@ extern "C" uint64_t brgpu_set_hash_size(const brgpu_set *s) { return s && s->is_
 extern "C" void *brgpu_set_device_ptr(brgpu_set *s) {
     if (!s) return nullptr;
     if (s->is_hash) return s->d_hash;
+    if (!s->bits_complete && ensure_dense(s) != BRGPU_OK) return nullptr;
     s->summary_valid = false; // the caller may write through the pointer (bitfield all-gather)
     return s->d_bits;
+}
+
+// The dense bitfield of a set that is held in its rank-compacted form only (see brgpu_set_compact_commit)
+static int ensure_dense(brgpu_set *s) {
+    if (s->is_hash || s->bits_complete) return BRGPU_OK;
+    brgpu_ctx *ctx = s->ctx;
+    if (!s->compact_valid) return fail(ctx, BRGPU_E_INVALID, "the set's bitfield is incomplete");
+    CK(cudaMemsetAsync(s->d_bits, 0, bits_alloc_bytes(s->k), ctx->stream));
+    launch_expand_blocks(ctx, s->d_dir, s->d_blocks, s->summary_bytes >> 2, s->d_bits);
+    CK(cudaGetLastError());
+    s->bits_complete = true;
+    return BRGPU_OK;
+}
+
+// Sharded construction of a sparse set: instead of the bitfield slices (1 GiB in total at k = 17) the GPUs
+// exchange their slices in rank-compacted form.  _slice_compact compacts this GPU's slice [bit_begin, bit_end)
+// (multiples of 2048) and tells how many occupied 64-bit blocks it has (*blocks_dev = NULL: compaction is not
+// available for this set — exchange the bitfield instead); _compact_alloc sizes the replica's block array for
+// the total of all slices and returns it for the host's exchange to fill in slice order; _compact_commit (after
+// the summary slices have been gathered too) builds the rank directory.  The dense bitfield is then rebuilt
+// only when somebody asks for it (brgpu_set_export_bitfield, brgpu_set_insert_batch, ...).
+extern "C" int brgpu_set_slice_compact(brgpu_set *s, uint64_t bit_begin, uint64_t bit_end, void **blocks_dev, uint64_t *n_blocks) {
+    if (!s || !blocks_dev || !n_blocks || s->is_hash) return BRGPU_E_INVALID;
+    brgpu_ctx *ctx = s->ctx;
+    *blocks_dev = nullptr;
+    *n_blocks = 0;
+    if (!s->d_summary || s->summary_shift != 6 || ctx->opt_no_compact) return BRGPU_OK;
+    if ((bit_begin & 2047) || (bit_end & 2047) || bit_begin > bit_end || (bit_end >> 3) > s->n_bytes)
+        return fail(ctx, BRGPU_E_INVALID, "slice must be 2048-bit aligned");
+    cudaSetDevice(ctx->device);
+    const uint64_t g0 = bit_begin >> 11, nw = (bit_end - bit_begin) >> 11;
+    Temps tmp(ctx);
+    uint32_t *d_pop = nullptr;
+    uint64_t *d_rank = nullptr, *d_tmp = nullptr;
+    CK(dalloc(ctx, &d_pop, nw));
+    tmp.keep(d_pop);
+    CK(dalloc(ctx, &d_rank, nw + 1));
+    tmp.keep(d_rank);
+    CK(dalloc(ctx, &d_tmp, nw / 4096 + 4));
+    tmp.keep(d_tmp);
+    launch_summary_rank(ctx, s->d_summary + g0, nw, d_pop, d_rank, d_tmp);
+    launch_readback(ctx, ctx->h_pinned + 301, d_rank + nw, sizeof(uint64_t));
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    const uint64_t total = ctx->h_pinned[301];
+    const uint64_t bytes = ((total * 8 + (8ULL << 20)) >> 23) << 23;
+    if (s->d_slice_blocks && s->slice_blocks_bytes < bytes) {
+        big_free(ctx, s->d_slice_blocks, s->slice_blocks_bytes);
+        s->d_slice_blocks = nullptr;
+    }
+    if (!s->d_slice_blocks) {
+        cudaError_t e = big_alloc(ctx, (void **)&s->d_slice_blocks, bytes);
+        if (e != cudaSuccess) return fail(ctx, BRGPU_E_NOMEM, "device allocation (compacted slice)", e);
+        s->slice_blocks_bytes = bytes;
+    }
+    launch_compact_blocks(ctx, s->d_summary + g0, d_rank, s->d_bits + (bit_begin >> 3), nw, total, nullptr, s->d_slice_blocks);
+    CK(cudaGetLastError());
+    *blocks_dev = s->d_slice_blocks;
+    *n_blocks = total;
+    return BRGPU_OK;
+}
+
+extern "C" int brgpu_set_compact_alloc(brgpu_set *s, uint64_t n_blocks_total, void **blocks_dev) {
+    if (!s || !blocks_dev || s->is_hash || !s->d_summary || s->summary_shift != 6) return BRGPU_E_INVALID;
+    brgpu_ctx *ctx = s->ctx;
+    cudaSetDevice(ctx->device);
+    compact_release(s);
+    const uint64_t n_words = s->summary_bytes >> 2;
+    const uint64_t bbytes = ((n_blocks_total * 8 + (8ULL << 20)) >> 23) << 23;
+    cudaError_t e = big_alloc(ctx, &s->d_dir, n_words * 8);
+    if (e == cudaSuccess) {
+        s->dir_bytes = n_words * 8;
+        e = big_alloc(ctx, (void **)&s->d_blocks, bbytes);
+        if (e == cudaSuccess) s->blocks_bytes = bbytes;
+    }
+    if (e != cudaSuccess) {
+        compact_release(s);
+        return fail(ctx, BRGPU_E_NOMEM, "device allocation (compacted set)", e);
+    }
+    s->n_occupied = n_blocks_total;
+    *blocks_dev = s->d_blocks;
+    return BRGPU_OK;
+}
+
+extern "C" int brgpu_set_compact_commit(brgpu_set *s) {
+    if (!s || s->is_hash || !s->d_dir || !s->d_blocks) return BRGPU_E_INVALID;
+    brgpu_ctx *ctx = s->ctx;
+    cudaSetDevice(ctx->device);
+    const uint64_t n_words = s->summary_bytes >> 2;
+    Temps tmp(ctx);
+    uint32_t *d_pop = nullptr;
+    uint64_t *d_rank = nullptr, *d_tmp = nullptr;
+    CK(dalloc(ctx, &d_pop, n_words));
+    tmp.keep(d_pop);
+    CK(dalloc(ctx, &d_rank, n_words + 1));
+    tmp.keep(d_rank);
+    CK(dalloc(ctx, &d_tmp, n_words / 4096 + 4));
+    tmp.keep(d_tmp);
+    launch_summary_rank(ctx, s->d_summary, n_words, d_pop, d_rank, d_tmp);
+    launch_dir_only(ctx, s->d_summary, d_rank, n_words, s->d_dir);
+    CK(cudaGetLastError());
+    s->summary_valid = true;
+    s->compact_valid = true;
+    s->bits_complete = false; // only this GPU's slice of the dense bitfield was ever written
+    return BRGPU_OK;
 }
 
 // Sharded construction writes a set slice by slice (each rank its bucket range, the rest arrives through the
@@ -1943,6 +2060,10 @@ extern "C" int brgpu_set_export_bitfield(brgpu_set *s, uint8_t *out_host, uint64
     if (s->is_hash) return fail(ctx, BRGPU_E_INVALID, "a hash set has no bitfield");
     if (cap < s->n_bytes) return fail(ctx, BRGPU_E_OVERFLOW, "output buffer too small");
     cudaSetDevice(ctx->device);
+    {
+        const int st = ensure_dense(s);
+        if (st != BRGPU_OK) return st;
+    }
     CK(cudaMemcpyAsync(out_host, s->d_bits, s->n_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return BRGPU_OK;
@@ -1961,7 +2082,7 @@ extern "C" int brgpu_set_get_batch(brgpu_set *s, const uint64_t *kmers_host, uin
     CK(dalloc(ctx, &d_o, n));
     tmp.keep(d_o);
     CK(cudaMemcpyAsync(d_k, kmers_host, n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
-    if (s->is_hash)
+    if (s->is_hash || !s->bits_complete)
         launch_get_batch_view(ctx, set_view(s), d_k, n, d_o);
     else
         launch_get_batch(ctx, s->d_bits, s->k, d_k, n, d_o);

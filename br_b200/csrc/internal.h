@@ -144,6 +144,11 @@ struct brgpu_set {
     uint64_t blocks_bytes = 0;   // allocation size
     uint64_t n_occupied = 0;     // occupied 64-bit blocks
     bool compact_valid = false;  // d_dir/d_blocks describe the current bitfield
+    // sharded construction may leave only this GPU's slice of the dense bitfield written and hold the whole set in
+    // its rank-compacted form; the dense form is then rebuilt when somebody asks for it (export, insert, ...)
+    bool bits_complete = true;
+    uint64_t *d_slice_blocks = nullptr; // this GPU's slice, compacted (what it sends to its peers)
+    uint64_t slice_blocks_bytes = 0;
     // set::Hash (src/set/hash.rs): open-addressing table of canonical k-mers instead of a bitfield
     bool is_hash = false;
     uint64_t *d_hash = nullptr;
@@ -237,6 +242,9 @@ void launch_summary_rank(brgpu_ctx *ctx, const uint32_t *d_summary, uint64_t n_w
 // dir[g] = {summary[g], rank[g]}; blocks[rank[g] + i] = i-th occupied 64-bit block of group g
 void launch_compact_blocks(brgpu_ctx *ctx, const uint32_t *d_summary, const uint64_t *d_rank, const uint8_t *d_bits,
                            uint64_t n_words, uint64_t n_occupied, void *d_dir, uint64_t *d_blocks);
+
+void launch_dir_only(brgpu_ctx *ctx, const uint32_t *d_summary, const uint64_t *d_rank, uint64_t n_words, void *d_dir);
+void launch_expand_blocks(brgpu_ctx *ctx, const void *d_dir, const uint64_t *d_blocks, uint64_t n_words, uint8_t *d_bits);
 
 // device view of a set for the correction kernels
 struct SetView {

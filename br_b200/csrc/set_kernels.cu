@@ -1386,7 +1386,7 @@ __global__ void __launch_bounds__(256)
          g += (uint64_t)gridDim.x * blockDim.x) {
         uint32_t occ = summary[g];
         uint64_t r = rank[g];
-        dir[g] = make_uint2(occ, (uint32_t)r);
+        if (dir) dir[g] = make_uint2(occ, (uint32_t)r);
         while (occ) {
             const int i = __ffs(occ) - 1;
             blocks[r++] = __ldcs(bits64 + (g << 5) + (uint64_t)i);
@@ -1409,9 +1409,41 @@ __global__ void __launch_bounds__(256)
         const uint64_t blk = __ldcs(bits64 + (g << 5) + (uint64_t)lane);
         const uint32_t occ = __ldg(summary + g);
         const uint64_t r = __ldg(rank + g);
-        if (lane == 0) dir[g] = make_uint2(occ, (uint32_t)r);
+        if (lane == 0 && dir) dir[g] = make_uint2(occ, (uint32_t)r);
         if ((occ >> lane) & 1u) blocks[r + (uint64_t)__popc(occ & ((1u << lane) - 1u))] = blk;
     }
+}
+
+// dir[g] = {summary[g], rank[g]} alone: the blocks came from elsewhere (the sharded construction gathers every
+// rank's compacted slice, in index order, instead of the 1 GiB bitfield)
+__global__ void dir_only_kernel(const uint32_t *__restrict__ summary, const uint64_t *__restrict__ rank, uint64_t n_words,
+                                uint2 *__restrict__ dir) {
+    for (uint64_t g = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; g < n_words; g += (uint64_t)gridDim.x * blockDim.x)
+        dir[g] = make_uint2(summary[g], (uint32_t)rank[g]);
+}
+
+void launch_dir_only(brgpu_ctx *ctx, const uint32_t *d_summary, const uint64_t *d_rank, uint64_t n_words, void *d_dir) {
+    ProfScope ps(ctx, "rank_directory", (double)n_words * 20.0);
+    dir_only_kernel<<<grid_for(ctx, n_words, 256, 8), 256, 0, ctx->stream>>>(d_summary, d_rank, n_words, reinterpret_cast<uint2 *>(d_dir));
+}
+
+// the dense bitfield back from its rank-compacted form (the bitfield must be zero): a warp per group
+__global__ void __launch_bounds__(256)
+    expand_blocks_kernel(const uint2 *__restrict__ dir, const uint64_t *__restrict__ blocks, uint64_t n_words,
+                         uint64_t *__restrict__ bits64) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t g = warp; g < n_words; g += n_warps) {
+        const uint2 e = __ldg(dir + g);
+        if ((e.x >> lane) & 1u) bits64[(g << 5) + (uint64_t)lane] = __ldg(blocks + e.y + __popc(e.x & ((1u << lane) - 1u)));
+    }
+}
+
+void launch_expand_blocks(brgpu_ctx *ctx, const void *d_dir, const uint64_t *d_blocks, uint64_t n_words, uint8_t *d_bits) {
+    ProfScope ps(ctx, "expand_blocks", (double)n_words * 8.0);
+    expand_blocks_kernel<<<grid_for(ctx, n_words * 32, 256, 8), 256, 0, ctx->stream>>>(reinterpret_cast<const uint2 *>(d_dir), d_blocks,
+                                                                                    n_words, reinterpret_cast<uint64_t *>(d_bits));
 }
 
 void launch_compact_blocks(brgpu_ctx *ctx, const uint32_t *d_summary, const uint64_t *d_rank, const uint8_t *d_bits,

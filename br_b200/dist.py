@@ -306,6 +306,8 @@ class GpuOps:
             bounds = [tuple(int(x) for x in t.cpu().tolist()) for t in allb]
         if not self.stream_ordered:  # the library's stream produced the slice; NCCL runs on torch's current stream
             self.ctx.synchronize()
+        if summary is not None and self._exchange_compacted(begin, end, bounds, n_bytes, summary):
+            return
         per = (end - begin) // 8
         if all((e - b) // 8 == per for b, e in bounds) and per * self.world == n_bytes:
             # in place: rank r's slice already sits at offset r * per of the output
@@ -321,6 +323,41 @@ class GpuOps:
                     self.dist.broadcast(summary[b // 512 : e // 512], src=src, group=self.group)
             self._summary_gathered = summary is not None and all(b % 512 == 0 and e % 512 == 0 for b, e in bounds)
 
+    def _exchange_compacted(self, begin, end, bounds, n_bytes, summary):
+        """A sparse set travels in rank-compacted form: every rank compacts its slice (occupied 64-bit blocks in
+        index order), the counts are all-gathered (the step's second small host round trip), and if the blocks of
+        all slices together take less than half the bitfield each rank broadcasts its blocks into everybody's
+        block array — slices are contiguous index ranges, so their concatenation in rank order IS the compacted
+        set — along with the summary slices.  E. coli x 8 at N = 8: 0.3 GB instead of 1 GiB on the wire, and no
+        compaction pass over the gathered bitfield.  Returns False when the dense exchange should run instead."""
+        torch = self.torch
+        if any(b % 2048 or e % 2048 for b, e in bounds) or any(((e - b) // 8) != ((end - begin) // 8) for b, e in bounds):
+            return False
+        ptr, n_mine = C.c_void_p(), C.c_uint64()
+        check(lib.brgpu_set_slice_compact(self.set._h, begin, end, C.byref(ptr), C.byref(n_mine)), self.ctx._h)
+        mine = torch.tensor([n_mine.value if ptr.value else -1], dtype=torch.int64, device=self.dev)
+        counts = torch.empty(self.world, dtype=torch.int64, device=self.dev)
+        self.dist.all_gather_into_tensor(counts, mine, group=self.group)
+        counts = counts.cpu().tolist()
+        total = sum(counts)
+        if min(counts) < 0 or total * 8 > n_bytes // 2:
+            return False  # compaction unavailable somewhere, or the set is too dense to gain from it
+        dst = C.c_void_p()
+        check(lib.brgpu_set_compact_alloc(self.set._h, total, C.byref(dst)), self.ctx._h)
+        blocks = torch.as_tensor(_CudaArray(dst.value, max(1, total) * 8, "<i8"), device=self.dev)
+        self.dist.all_gather_into_tensor(summary, summary[begin // 512 : end // 512], group=self.group)
+        at = 0
+        for r, c in enumerate(counts):
+            if c:
+                region = blocks[at : at + c]
+                if r == self.rank:
+                    region.copy_(torch.as_tensor(_CudaArray(ptr.value, c * 8, "<i8"), device=self.dev), non_blocking=True)
+                src = self.dist.get_global_rank(self.group, r) if self.group else r
+                self.dist.broadcast(region, src=src, group=self.group)
+            at += c
+        self._compact_exchanged = True
+        return True
+
     def finish(self, abundance):
         if self.counter is not None:
             self.counter.free()
@@ -328,6 +365,8 @@ class GpuOps:
             for part in self.parts:
                 lib.brgpu_kmers_free(part)
             self.parts, self.kmers = [], None
-            # bitfield and summary are whole: build the lookup structures without re-reading the bitfield
-            check(lib.brgpu_set_commit_slices(self.set._h, int(getattr(self, "_summary_gathered", False))), self.ctx._h)
+            if getattr(self, "_compact_exchanged", False):  # blocks and summary are whole: only the rank directory is missing
+                check(lib.brgpu_set_compact_commit(self.set._h), self.ctx._h)
+            else:  # bitfield and summary are whole: build the lookup structures without re-reading the bitfield
+                check(lib.brgpu_set_commit_slices(self.set._h, int(getattr(self, "_summary_gathered", False))), self.ctx._h)
         return self.set

@@ -225,6 +225,15 @@ void *brgpu_set_device_ptr(brgpu_set *set);
  * the bitfield's) for the same all-gather; _commit_slices declares bitfield (and summary, if
  * summary_complete) whole and builds the lookup structures — no pass over the 1 GiB bitfield. */
 int brgpu_set_new_sliced(brgpu_ctx *ctx, int k, brgpu_set **out);
+/* A sparse set travels cheaper in rank-compacted form (§2 of DESIGN.md: occupied 64-bit blocks in index order):
+ * _slice_compact compacts this GPU's slice [bit_begin, bit_end) (multiples of 2048) and returns its blocks and
+ * their number (*blocks_dev = NULL: not available for this set, exchange the bitfield); _compact_alloc sizes the
+ * replica's block array for the total over all slices and returns it for the host's exchange to fill in slice
+ * order; _compact_commit (summary slices gathered too) builds the rank directory.  The dense bitfield of such a
+ * set is rebuilt on demand (brgpu_set_export_bitfield, brgpu_set_insert_batch, brgpu_set_device_ptr). */
+int brgpu_set_slice_compact(brgpu_set *set, uint64_t bit_begin, uint64_t bit_end, void **blocks_dev, uint64_t *n_blocks);
+int brgpu_set_compact_alloc(brgpu_set *set, uint64_t n_blocks_total, void **blocks_dev);
+int brgpu_set_compact_commit(brgpu_set *set);
 void *brgpu_set_summary_ptr(brgpu_set *set, uint64_t *n_bytes);
 int brgpu_set_commit_slices(brgpu_set *set, int summary_complete);
 void brgpu_set_free(brgpu_set *set);
