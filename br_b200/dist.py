@@ -346,15 +346,22 @@ class GpuOps:
         check(lib.brgpu_set_compact_alloc(self.set._h, total, C.byref(dst)), self.ctx._h)
         blocks = torch.as_tensor(_CudaArray(dst.value, max(1, total) * 8, "<i8"), device=self.dev)
         self.dist.all_gather_into_tensor(summary, summary[begin // 512 : end // 512], group=self.group)
-        at = 0
-        for r, c in enumerate(counts):
-            if c:
-                region = blocks[at : at + c]
-                if r == self.rank:
-                    region.copy_(torch.as_tensor(_CudaArray(ptr.value, c * 8, "<i8"), device=self.dev), non_blocking=True)
-                src = self.dist.get_global_rank(self.group, r) if self.group else r
-                self.dist.broadcast(region, src=src, group=self.group)
+        regions, at = [], 0
+        for c in counts:
+            regions.append(blocks[at : at + c])
             at += c
+        mine_blocks = torch.as_tensor(_CudaArray(ptr.value, max(1, n_mine.value) * 8, "<i8"), device=self.dev)[: n_mine.value]
+        if min(counts) > 0:
+            # ragged all-gather: ProcessGroupNCCL turns output tensors of different sizes into ONE group of
+            # broadcasts (a single launch, all roots in flight together) instead of `world` launches in a row
+            self.dist.all_gather(regions, mine_blocks, group=self.group)
+        else:  # an empty slice somewhere (tiny inputs): one broadcast per non-empty slice
+            for r, c in enumerate(counts):
+                if c:
+                    if r == self.rank:
+                        regions[r].copy_(mine_blocks, non_blocking=True)
+                    src = self.dist.get_global_rank(self.group, r) if self.group else r
+                    self.dist.broadcast(regions[r], src=src, group=self.group)
         self._compact_exchanged = True
         return True
 
