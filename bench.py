@@ -688,7 +688,7 @@ def leg_record(m, wl, total_bases, steps, warmup, table, hbm_peak, sm_max_mhz, l
     dk = kernels[dominant]
     # SURVEY §8(d) aggregates: the count path as a whole (0.25 B/base + 64 B/k-mer over the time of its kernels) and
     # the solidity lookups of the step (bitmap passes + every KmerSet::get of the scans) per second of the step
-    count_names = ("coarse_hist", "coarse_scatter", "fine_partition", "bucket_count", "bucket_count_multi", "peer_residue_copy",
+    count_names = ("coarse_hist", "coarse_scatter", "fine_partition", "bucket_count", "bucket_count_multi", "peer_pull",
                    "bucket_hist", "bucket_scatter", "count_kmers", "zero_counts", "spectrum_threshold", "spectrum", "summary_popc",
                    "compact_blocks", "build_summary", "exclusive_scan")
     count_ms = sum(m["prof"][k_]["ms"] for k_ in m["prof"] if k_ in count_names) / steps

@@ -278,6 +278,7 @@ extern "C" int brgpu_ctx_create(int device, void *cuda_stream, brgpu_ctx **out) 
     };
     ctx->opt_no_compact = env_on("BRGPU_NO_COMPACT") ? 1 : 0;
     ctx->opt_one_level_partition = env_on("BRGPU_ONE_LEVEL_PARTITION") ? 1 : 0;
+    ctx->opt_no_pos8 = env_on("BRGPU_NO_POS8") ? 1 : 0;
     if (const char *v = getenv("BRGPU_COUNT_BLOCK_ONLY")) ctx->opt_count_block_only = (*v >= '0' && *v <= '3') ? *v - '0' : 0;
     if (const char *m = getenv("BRGPU_SCAN")) ctx->opt_scan_mode = m[0] == 'w' ? 1 : (m[0] == 'g' ? 2 : 0);
     *out = ctx;
@@ -319,6 +320,7 @@ extern "C" int brgpu_ctx_set_option(brgpu_ctx *ctx, const char *name, int value)
     if (!ctx || !name) return BRGPU_E_INVALID;
     if (!strcmp(name, "no_compact")) ctx->opt_no_compact = value != 0;
     else if (!strcmp(name, "one_level_partition")) ctx->opt_one_level_partition = value != 0;
+    else if (!strcmp(name, "no_pos8")) ctx->opt_no_pos8 = value != 0;
     else if (!strcmp(name, "count_block_only")) ctx->opt_count_block_only = value < 0 || value > 3 ? 0 : value;
     else if (!strcmp(name, "scan_mode")) {
         if (value < 0 || value > 2) return fail(ctx, BRGPU_E_INVALID, "scan_mode must be 0 (default), 1 (warp) or 2 (groups)");
@@ -1117,10 +1119,29 @@ static int ensure_dense(brgpu_set *s); // below: the dense bitfield of a set hel
 static void compact_release(brgpu_set *s) {
     if (s->d_dir) big_free(s->ctx, s->d_dir, s->dir_bytes);
     if (s->d_blocks) big_free(s->ctx, s->d_blocks, s->blocks_bytes);
+    if (s->d_pos8) big_free(s->ctx, s->d_pos8, s->pos8_bytes);
     s->d_dir = nullptr;
     s->d_blocks = nullptr;
-    s->dir_bytes = s->blocks_bytes = 0;
+    s->d_pos8 = nullptr;
+    s->dir_bytes = s->blocks_bytes = s->pos8_bytes = 0;
     s->compact_valid = false;
+}
+
+// The one-byte form of the compacted blocks (SolidView::pos8); without it lookups read the 64-bit blocks.
+static void build_pos8(brgpu_set *s) {
+    brgpu_ctx *ctx = s->ctx;
+    if (s->d_pos8) big_free(ctx, s->d_pos8, s->pos8_bytes);
+    s->d_pos8 = nullptr;
+    s->pos8_bytes = 0;
+    if (ctx->opt_no_pos8 || !s->n_occupied) return;
+    const uint64_t bytes = ((s->n_occupied + 4 + (1ULL << 20)) >> 20) << 20;
+    if (big_alloc(ctx, (void **)&s->d_pos8, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        s->d_pos8 = nullptr;
+        return;
+    }
+    s->pos8_bytes = bytes;
+    launch_block_bytes(ctx, s->d_blocks, s->n_occupied, s->d_pos8);
 }
 
 // Build the rank directory + compacted blocks from a valid shift-6 summary.  One host round trip
@@ -1170,6 +1191,7 @@ static int build_compact(brgpu_set *s) {
         } else {
             launch_compact_blocks(ctx, s->d_summary, d_rank, s->d_bits, n_words, s->n_occupied, s->d_dir, s->d_blocks);
             s->compact_valid = true;
+            build_pos8(s);
         }
     }
     drop();
@@ -1217,6 +1239,7 @@ static SetView set_view(const brgpu_set *s) {
     if (s->compact_valid) {
         v.dir = s->d_dir;
         v.blocks = s->d_blocks;
+        v.pos8 = s->d_pos8;
     }
     return v;
 }
@@ -1480,7 +1503,8 @@ static int kmers_count_parts(brgpu_ctx *ctx, brgpu_kmers *const *local, int n_lo
         if (d_stage) dfree(ctx, d_stage);
     };
     cudaError_t e = cudaSuccess;
-    if (n_peers) e = dalloc(ctx, &d_pb, (uint64_t)n_peers * (nb + 1));
+    // a peer's slice of offsets lands at an address congruent (mod 16) to its source: nb + 1 entries + 1 of slack
+    if (n_peers) e = dalloc(ctx, &d_pb, (uint64_t)n_peers * (nb + 2) + 2);
     if (e == cudaSuccess && n_peers && peer_first) {
         uint64_t total = 0;
         for (int p = 0; p < n_peers; p++) {
@@ -1488,9 +1512,9 @@ static int kmers_count_parts(brgpu_ctx *ctx, brgpu_kmers *const *local, int n_lo
                 drop();
                 return fail(ctx, BRGPU_E_INVALID, "bad peer residue range");
             }
-            total += peer_last[p] - peer_first[p];
+            total += peer_last[p] - peer_first[p] + 8; // up to 7 residues of alignment padding per peer
         }
-        e = dalloc(ctx, &d_stage, total + 1);
+        e = dalloc(ctx, &d_stage, total + 8);
     }
     if (e != cudaSuccess) {
         drop();
@@ -1502,23 +1526,40 @@ static int kmers_count_parts(brgpu_ctx *ctx, brgpu_kmers *const *local, int n_lo
         res[q] = local[q]->d_res;
         base[q] = local[q]->d_base;
     }
+    auto congruent = [](uintptr_t dst, uintptr_t src, unsigned unit) { // smallest dst' >= dst with dst' == src (mod 16)
+        return dst + (((src - dst) & 15u) / unit) * unit;
+    };
+    PullSegments segs;
+    segs.n = 0;
+    double pulled = 0;
     uint64_t staged = 0;
-    for (int p = 0; p < n_peers && e == cudaSuccess; p++) {
-        uint64_t *dst = d_pb + (uint64_t)p * (nb + 1);
-        e = cudaMemcpyAsync(dst, (const uint64_t *)peer_offsets[p] + bucket_begin, (nb + 1) * 8, cudaMemcpyDefault, ctx->stream);
+    for (int p = 0; p < n_peers; p++) {
+        const uint64_t *src_off = (const uint64_t *)peer_offsets[p] + bucket_begin;
+        uint64_t *dst = reinterpret_cast<uint64_t *>(
+            congruent(reinterpret_cast<uintptr_t>(d_pb + (uint64_t)p * (nb + 2)), reinterpret_cast<uintptr_t>(src_off), 8));
+        segs.src[segs.n] = reinterpret_cast<const uint8_t *>(src_off);
+        segs.dst[segs.n] = reinterpret_cast<uint8_t *>(dst);
+        segs.bytes[segs.n++] = (nb + 1) * 8;
+        pulled += (double)(nb + 1) * 8.0;
         base[n_local + p] = dst - bucket_begin; // indexable by absolute bucket id inside the range
         if (d_stage) {
             const uint64_t n = peer_last[p] - peer_first[p];
-            ProfScope ps(ctx, "peer_residue_copy", (double)n * 2.0, false);
-            if (n && e == cudaSuccess)
-                e = cudaMemcpyAsync(d_stage + staged, (const uint16_t *)peer_residues[p] + peer_first[p], n * 2,
-                                    cudaMemcpyDefault, ctx->stream);
-            res[n_local + p] = d_stage + staged - peer_first[p]; // the kernel indexes by the peer's absolute offsets
-            staged += n;
+            const uint16_t *src_res = (const uint16_t *)peer_residues[p] + peer_first[p];
+            uint16_t *to = reinterpret_cast<uint16_t *>(
+                congruent(reinterpret_cast<uintptr_t>(d_stage + staged), reinterpret_cast<uintptr_t>(src_res), 2));
+            if (n) {
+                segs.src[segs.n] = reinterpret_cast<const uint8_t *>(src_res);
+                segs.dst[segs.n] = reinterpret_cast<uint8_t *>(to);
+                segs.bytes[segs.n++] = n * 2;
+                pulled += (double)n * 2.0;
+            }
+            res[n_local + p] = to - peer_first[p]; // the kernel indexes by the peer's absolute offsets
+            staged = (uint64_t)(to - d_stage) + n;
         } else {
             res[n_local + p] = (const uint16_t *)peer_residues[p];
         }
     }
+    launch_peer_pull(ctx, segs, pulled);
     if (e == cudaSuccess) e = cudaMemsetAsync(ctx->d_hist, 0, 256 * sizeof(uint64_t), ctx->stream);
     if (e != cudaSuccess) {
         drop();
@@ -2003,6 +2044,7 @@ extern "C" int brgpu_set_compact_commit(brgpu_set *s) {
     tmp.keep(d_tmp);
     launch_summary_rank(ctx, s->d_summary, n_words, d_pop, d_rank, d_tmp);
     launch_dir_only(ctx, s->d_summary, d_rank, n_words, s->d_dir);
+    build_pos8(s);
     CK(cudaGetLastError());
     s->summary_valid = true;
     s->compact_valid = true;

@@ -90,15 +90,20 @@ __global__ void __launch_bounds__(256)
                         e[j] = make_uint2(0u, 0u);
                         if (go[j]) e[j] = __ldg(set.dir + (idx[j] >> 11));
                     }
-                    uint64_t blk[8];
+                    uint32_t r[8], pv[8]; // then the block's byte (1 B) and, for a block with several k-mers, the block (8 B)
 #pragma unroll
                     for (int j = 0; j < 8; j++) {
                         const uint32_t b = (uint32_t)(idx[j] >> 6) & 31u;
-                        blk[j] = 0;
-                        if ((e[j].x >> b) & 1u) blk[j] = __ldg(set.blocks + (e[j].y + __popc(e[j].x & ((1u << b) - 1u))));
+                        r[j] = e[j].y + __popc(e[j].x & ((1u << b) - 1u));
+                        pv[j] = POS8_NONE;
+                        if ((e[j].x >> b) & 1u) pv[j] = set.pos8 ? (uint32_t)__ldg(set.pos8 + r[j]) : POS8_MULTI;
                     }
 #pragma unroll
-                    for (int j = 0; j < 8; j++) out |= (uint32_t)((blk[j] >> (idx[j] & 63)) & 1ULL) << (g + j);
+                    for (int j = 0; j < 8; j++) {
+                        uint32_t hit = pv[j] == (uint32_t)(idx[j] & 63);
+                        if (pv[j] == POS8_MULTI) hit = (uint32_t)((__ldg(set.blocks + r[j]) >> (idx[j] & 63)) & 1ULL);
+                        out |= hit << (g + j);
+                    }
                     continue;
                 }
                 if (set.summary) {

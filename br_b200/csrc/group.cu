@@ -212,17 +212,46 @@ extern "C" int brgpu_group_set_from_reads(brgpu_group *g, int k, int abundance, 
             }
         }
         if (st == BRGPU_OK) st = count_phase(abundance, true, &hist);
-        // every device pushes its slice of the bitfield (and of the summary) to every peer
+        // A sparse set travels in rank-compacted form (the same decision as dist.py's _exchange_compacted): every
+        // device compacts its slice, and if the blocks of all slices take less than half the bitfield each device
+        // pushes its blocks into every replica's block array at its slice's offset, together with its summary slice;
+        // the replicas then only build the rank directory.  Otherwise the bitfield slices themselves are pushed.
+        std::vector<void *> my_blocks(n, nullptr), all_blocks(n, nullptr);
+        std::vector<uint64_t> n_blocks(n, 0);
+        bool compacted = false;
+        if (st == BRGPU_OK) {
+            st = for_each_device(g, [&](int i) {
+                uint64_t b0, b1;
+                bucket_range(n_buckets, n, i, &b0, &b1);
+                return brgpu_set_slice_compact(sets[i], b0 << GROUP_BUCKET_BITS, b1 << GROUP_BUCKET_BITS, &my_blocks[i], &n_blocks[i]);
+            });
+            uint64_t total = 0;
+            compacted = st == BRGPU_OK;
+            for (int i = 0; i < n; i++) {
+                compacted = compacted && my_blocks[i] != nullptr;
+                total += n_blocks[i];
+            }
+            compacted = compacted && total * 8 <= (table >> 3) / 2;
+            if (compacted)
+                st = for_each_device(g, [&](int i) { return brgpu_set_compact_alloc(sets[i], total, &all_blocks[i]); });
+        }
         if (st == BRGPU_OK)
             st = for_each_device(g, [&](int i) {
                 uint64_t b0, b1;
                 bucket_range(n_buckets, n, i, &b0, &b1);
                 const uint64_t byte0 = (b0 << GROUP_BUCKET_BITS) >> 3, bytes = ((b1 - b0) << GROUP_BUCKET_BITS) >> 3;
+                uint64_t at = 0; // this slice's position in the block array
+                for (int j = 0; j < i; j++) at += n_blocks[j];
                 for (int j = 0; j < n; j++) {
-                    if (j == i) continue;
-                    if (cudaMemcpyAsync(sets[j]->d_bits + byte0, sets[i]->d_bits + byte0, bytes, cudaMemcpyDefault, g->ctx[i]->stream) != cudaSuccess)
+                    if (compacted) { // own replica included: the slice's blocks sit in scratch
+                        if (n_blocks[i] && cudaMemcpyAsync((uint64_t *)all_blocks[j] + at, my_blocks[i], n_blocks[i] * 8, cudaMemcpyDefault,
+                                                           g->ctx[i]->stream) != cudaSuccess)
+                            return fail(g->ctx[i], BRGPU_E_CUDA, "compacted slice copy", cudaGetLastError());
+                    } else if (j != i && cudaMemcpyAsync(sets[j]->d_bits + byte0, sets[i]->d_bits + byte0, bytes, cudaMemcpyDefault,
+                                                         g->ctx[i]->stream) != cudaSuccess) {
                         return fail(g->ctx[i], BRGPU_E_CUDA, "bitfield slice copy", cudaGetLastError());
-                    if (sets[i]->d_summary && sets[j]->d_summary &&
+                    }
+                    if (j != i && sets[i]->d_summary && sets[j]->d_summary &&
                         cudaMemcpyAsync((uint8_t *)sets[j]->d_summary + (byte0 >> 6), (uint8_t *)sets[i]->d_summary + (byte0 >> 6), bytes >> 6,
                                         cudaMemcpyDefault, g->ctx[i]->stream) != cudaSuccess)
                         return fail(g->ctx[i], BRGPU_E_CUDA, "summary slice copy", cudaGetLastError());
@@ -233,7 +262,7 @@ extern "C" int brgpu_group_set_from_reads(brgpu_group *g, int k, int abundance, 
             st = for_each_device(g, [&](int i) {
                 memcpy(sets[i]->hist, hist.data(), 256 * sizeof(uint64_t));
                 sets[i]->abundance = abundance;
-                return brgpu_set_commit_slices(sets[i], sets[i]->d_summary != nullptr ? 1 : 0);
+                return compacted ? brgpu_set_compact_commit(sets[i]) : brgpu_set_commit_slices(sets[i], sets[i]->d_summary != nullptr ? 1 : 0);
             });
         drop_parts();
     } else {

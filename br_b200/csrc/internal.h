@@ -58,6 +58,7 @@ struct brgpu_ctx {
     int opt_one_level_partition = 0; // the k = 19 partition path for k <= 17
     int opt_count_block_only = 0;    // the 256-thread shape of the counting kernel even for sparse buckets
     int opt_scan_mode = 0;           // 0: per method default, 1: warp per segment, 2: four segments per warp
+    int opt_no_pos8 = 0;             // A/B: lookups read the 64-bit blocks instead of the one-byte form
     // caching device allocator (brgpu.cu): blocks handed out (ptr -> bytes) and cached free blocks
     std::unordered_map<void *, uint64_t> pool_live;
     std::vector<std::pair<void *, uint64_t>> pool_free;
@@ -143,6 +144,8 @@ struct brgpu_set {
     uint64_t *d_blocks = nullptr;
     uint64_t blocks_bytes = 0;   // allocation size
     uint64_t n_occupied = 0;     // occupied 64-bit blocks
+    uint8_t *d_pos8 = nullptr;   // one byte per occupied block (SolidView::pos8); nullptr: not built
+    uint64_t pos8_bytes = 0;
     bool compact_valid = false;  // d_dir/d_blocks describe the current bitfield
     // sharded construction may leave only this GPU's slice of the dense bitfield written and hold the whole set in
     // its rank-compacted form; the dense form is then rebuilt when somebody asks for it (export, insert, ...)
@@ -225,6 +228,15 @@ void launch_bucket_count_multi(brgpu_ctx *ctx, const uint16_t *const *d_res, con
                                uint64_t b0, uint64_t b1, int abundance, uint8_t *d_bits, uint32_t *d_summary,
                                uint64_t *d_hist, double n_kmers);
 constexpr int BRGPU_MAX_KMER_SOURCES = 64; // == BUCKET_MAX_SOURCES in set_kernels.cu
+// one launch copying up to 128 (peer) segments into local HBM; src[q] and dst[q] congruent modulo 16, bytes[q] even
+struct PullSegments {
+    const uint8_t *src[2 * BRGPU_MAX_KMER_SOURCES];
+    uint8_t *dst[2 * BRGPU_MAX_KMER_SOURCES];
+    uint64_t bytes[2 * BRGPU_MAX_KMER_SOURCES];
+    uint32_t first_chunk[2 * BRGPU_MAX_KMER_SOURCES + 1]; // filled by launch_peer_pull
+    int n;
+};
+void launch_peer_pull(brgpu_ctx *ctx, PullSegments &segs, double bytes);
 void launch_get_batch(brgpu_ctx *ctx, const uint8_t *d_bits, int k, const uint64_t *d_kmers, uint64_t n,
                       uint8_t *d_out);
 void launch_insert_batch(brgpu_ctx *ctx, uint8_t *d_bits, int k, const uint64_t *d_kmers, uint64_t n);
@@ -244,6 +256,7 @@ void launch_compact_blocks(brgpu_ctx *ctx, const uint32_t *d_summary, const uint
                            uint64_t n_words, uint64_t n_occupied, void *d_dir, uint64_t *d_blocks);
 
 void launch_dir_only(brgpu_ctx *ctx, const uint32_t *d_summary, const uint64_t *d_rank, uint64_t n_words, void *d_dir);
+void launch_block_bytes(brgpu_ctx *ctx, const uint64_t *d_blocks, uint64_t n_occupied, uint8_t *d_pos8);
 void launch_expand_blocks(brgpu_ctx *ctx, const void *d_dir, const uint64_t *d_blocks, uint64_t n_words, uint8_t *d_bits);
 
 // device view of a set for the correction kernels
@@ -254,6 +267,7 @@ struct SetView {
     int k;
     const void *dir = nullptr;        // uint2 *
     const uint64_t *blocks = nullptr;
+    const uint8_t *pos8 = nullptr;
     const uint64_t *hash = nullptr;   // set::Hash table (then everything above is unused)
     uint64_t hash_mask = 0;
 };

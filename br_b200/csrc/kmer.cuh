@@ -62,6 +62,8 @@ __device__ __forceinline__ uint64_t canonical_kmer(uint64_t kmer, int k) {
 
 // set::Hash on the device (hash_kernels.cu): open addressing, linear probing, empty = all ones
 constexpr uint64_t HASH_EMPTY = ~0ULL;
+constexpr uint32_t POS8_MULTI = 0xFFu; // SolidView::pos8: the block holds more than one solid k-mer
+constexpr uint32_t POS8_NONE = 0xFEu;  // in-register marker of a lookup that needs no second load
 __host__ __device__ __forceinline__ uint64_t hash_mix64(uint64_t x) {
     x += 0x9E3779B97F4A7C15ULL;
     x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
@@ -93,6 +95,12 @@ struct SolidView {
     // arrays together are 69 MB and stay in L2, where the bitfield costs a DRAM access per hit.
     const uint2 *dir;
     const uint64_t *blocks;
+    // One byte per occupied block (nullptr: not built): the position of the block's only set bit, or POS8_MULTI
+    // when it has several — then (and only then) the 64-bit block itself is read.  A sparse set has one solid
+    // k-mer in almost every occupied block (98 % at 4.6 M k-mers, 87 % at 37 M), so the second load of a lookup
+    // lands in an array eight times smaller: 32 MiB of directory + 1 B per block stay in L2 where 8 B per
+    // block (294 MB for the eight-genome set of the weak-scaled N = 8 run) did not.
+    const uint8_t *pos8;
     // set::Hash (nullptr: a dense set): table of canonical k-mers, hash_mask = slots - 1
     const uint64_t *hash;
     uint64_t hash_mask;
@@ -100,7 +108,7 @@ struct SolidView {
 
 // host side: the kernels' view of a brgpu::SetView (internal.h)
 template <class SV> inline SolidView solid_view(const SV &s) {
-    return SolidView{s.bits, s.summary, s.shift, s.k, (const uint2 *)s.dir, s.blocks, s.hash, s.hash_mask};
+    return SolidView{s.bits, s.summary, s.shift, s.k, (const uint2 *)s.dir, s.blocks, s.pos8, s.hash, s.hash_mask};
 }
 
 __device__ __forceinline__ bool hash_contains(const uint64_t *__restrict__ table, uint64_t slot_mask, uint64_t key) {
@@ -122,6 +130,10 @@ __device__ __forceinline__ bool solid(const SolidView &v, uint64_t kmer) {
         const uint32_t b = (uint32_t)j & 31u;
         if (!((e.x >> b) & 1u)) return false;
         const uint32_t r = e.y + __popc(e.x & ((1u << b) - 1u));
+        if (v.pos8) {
+            const uint32_t p = __ldg(v.pos8 + r);
+            if (p != POS8_MULTI) return p == (uint32_t)(idx & 63);
+        }
         return (__ldg(v.blocks + r) >> (idx & 63)) & 1ULL;
     }
     if (v.summary) {

@@ -883,6 +883,99 @@ void launch_bucket_count_multi(brgpu_ctx *ctx, const uint16_t *const *d_res, con
         src, b0, b1, abundance, reinterpret_cast<uint32_t *>(d_bits), d_summary, reinterpret_cast<unsigned long long *>(d_hist));
 }
 
+// SolidView::pos8 from the compacted blocks: position of the only set bit, or POS8_MULTI
+__global__ void __launch_bounds__(256) block_bytes_kernel(const uint64_t *__restrict__ blocks, uint64_t n, uint8_t *__restrict__ pos8) {
+    // a thread turns 4 consecutive blocks into one 32-bit store
+    for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q * 4 < n; q += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t w = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint64_t i = q * 4 + j;
+            uint32_t v = POS8_MULTI;
+            if (i < n) {
+                const uint64_t b = __ldcs(blocks + i);
+                if (__popcll(b) == 1) v = (uint32_t)__ffsll((long long)b) - 1u;
+            }
+            w |= v << (8 * j);
+        }
+        reinterpret_cast<uint32_t *>(pos8)[q] = w;
+    }
+}
+
+void launch_block_bytes(brgpu_ctx *ctx, const uint64_t *d_blocks, uint64_t n_occupied, uint8_t *d_pos8) {
+    if (!n_occupied) return;
+    ProfScope ps(ctx, "block_bytes", (double)n_occupied * 9.0);
+    const uint64_t quads = (n_occupied + 3) / 4, want = (quads + 255) / 256, cap = (uint64_t)ctx->sm_count * 16;
+    block_bytes_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, ctx->stream>>>(d_blocks, n_occupied, d_pos8);
+}
+
+// Staged variant of the exchange: ONE launch pulls this rank's bucket range out of every peer partition —
+// the residues (2 B per k-mer) and the slice of bucket offsets — with 16 B loads over NVLink, all peers in
+// flight together (NVSwitch gives the reader its full inbound bandwidth whatever the number of sources; one
+// cudaMemcpyAsync per peer, in stream order, ran at a third of it: 7 x 0.07 ms for 7 x 23 MB at N = 8).
+// Source and destination of a segment are congruent modulo 16 (the caller pads the destination), sizes are
+// multiples of 2: head and tail of a segment move as 2 B pieces, the body as uint4.
+constexpr int PULL_THREADS = 256;
+constexpr int PULL_UNROLL = 4;
+constexpr uint32_t PULL_CHUNK_VECS = PULL_THREADS * PULL_UNROLL * 4; // 64 KiB per block and turn
+
+__global__ void __launch_bounds__(PULL_THREADS) peer_pull_kernel(PullSegments segs) {
+    const uint32_t total = segs.first_chunk[segs.n];
+    for (uint32_t chunk = blockIdx.x; chunk < total; chunk += gridDim.x) {
+        int lo = 0, hi = segs.n - 1; // last segment whose first chunk is <= chunk
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (segs.first_chunk[mid] <= chunk) lo = mid;
+            else hi = mid - 1;
+        }
+        const uint8_t *src = segs.src[lo];
+        uint8_t *dst = segs.dst[lo];
+        const uint64_t bytes = segs.bytes[lo];
+        const uint32_t local = chunk - segs.first_chunk[lo];
+        uint64_t head = (16u - (uint32_t)(reinterpret_cast<uintptr_t>(src) & 15u)) & 15u;
+        if (head > bytes) head = bytes;
+        const uint64_t n_vec = (bytes - head) >> 4;
+        const uint64_t tail = bytes - head - (n_vec << 4);
+        const uint4 *sv = reinterpret_cast<const uint4 *>(src + head);
+        uint4 *dv = reinterpret_cast<uint4 *>(dst + head);
+        const uint64_t v0 = (uint64_t)local * PULL_CHUNK_VECS;
+        const uint64_t v1 = v0 + PULL_CHUNK_VECS < n_vec ? v0 + PULL_CHUNK_VECS : n_vec;
+        for (uint64_t v = v0 + threadIdx.x; v < v1; v += PULL_THREADS * PULL_UNROLL) {
+            uint4 r[PULL_UNROLL];
+#pragma unroll
+            for (int u = 0; u < PULL_UNROLL; u++)
+                if (v + (uint64_t)u * PULL_THREADS < v1) r[u] = __ldcs(sv + v + (uint64_t)u * PULL_THREADS);
+#pragma unroll
+            for (int u = 0; u < PULL_UNROLL; u++)
+                if (v + (uint64_t)u * PULL_THREADS < v1) dv[v + (uint64_t)u * PULL_THREADS] = r[u];
+        }
+        if (local == 0) {
+            const uint16_t *s2 = reinterpret_cast<const uint16_t *>(src);
+            uint16_t *d2 = reinterpret_cast<uint16_t *>(dst);
+            if (threadIdx.x < (head >> 1)) d2[threadIdx.x] = s2[threadIdx.x];
+            const uint64_t t0 = (head + (n_vec << 4)) >> 1;
+            if (threadIdx.x < (tail >> 1)) d2[t0 + threadIdx.x] = s2[t0 + threadIdx.x];
+        }
+    }
+}
+
+void launch_peer_pull(brgpu_ctx *ctx, PullSegments &segs, double bytes) {
+    uint32_t at = 0;
+    for (int q = 0; q < segs.n; q++) {
+        segs.first_chunk[q] = at;
+        uint64_t head = (16u - (uint32_t)(reinterpret_cast<uintptr_t>(segs.src[q]) & 15u)) & 15u;
+        if (head > segs.bytes[q]) head = segs.bytes[q];
+        const uint64_t n_vec = (segs.bytes[q] - head) >> 4;
+        const uint64_t chunks = (n_vec + PULL_CHUNK_VECS - 1) / PULL_CHUNK_VECS;
+        at += (uint32_t)(chunks ? chunks : 1); // a segment without a body still has its head / tail turn
+    }
+    segs.first_chunk[segs.n] = at;
+    if (!segs.n || !at) return;
+    ProfScope ps(ctx, "peer_pull", bytes);
+    const uint32_t cap = (uint32_t)ctx->sm_count * 8u;
+    peer_pull_kernel<<<at < cap ? at : cap, PULL_THREADS, 0, ctx->stream>>>(segs);
+}
+
 // ------------------------------------------------------------------------------------------
 // Two-level partition (k <= 17: at most 2^18 buckets).  The one-level scheme above pays one L2
 // atomic per k-mer twice (sizes, then cursors: 138 M `red` + 138 M `atom` on the E. coli config,

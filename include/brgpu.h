@@ -70,8 +70,9 @@ void brgpu_ctx_destroy(brgpu_ctx *ctx);
 int brgpu_ctx_synchronize(brgpu_ctx *ctx);
 /* Switches for tests and A/B measurements; none changes a result.  Defaults come from the
  * environment once, at brgpu_ctx_create (BRGPU_NO_COMPACT, BRGPU_ONE_LEVEL_PARTITION,
- * BRGPU_COUNT_BLOCK_ONLY, BRGPU_SCAN=warp|groups).  name: "no_compact" (0/1: solidity lookups through summary + bitfield
+ * BRGPU_COUNT_BLOCK_ONLY, BRGPU_NO_POS8, BRGPU_SCAN=warp|groups).  name: "no_compact" (0/1: solidity lookups through summary + bitfield
  * even for sparse sets), "one_level_partition" (0/1: the k = 19 partition path for k <= 17),
+ * "no_pos8" (0/1: lookups of a rank-compacted set read its 64-bit blocks instead of the one-byte-per-block form),
  * "count_block_only" (threads per bucket of the counting kernel: 0 or 1 = 256, the default; 2 = 128; 3 = 64),
  * "scan_mode" (0 per-method default, 1 warp per segment, 2 four segments per warp, for One/Two). */
 int brgpu_ctx_set_option(brgpu_ctx *ctx, const char *name, int value);

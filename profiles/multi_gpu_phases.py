@@ -15,12 +15,35 @@ def main():
     stream = torch.cuda.Stream()
     with torch.cuda.stream(stream):
         ctx = br_b200.Context(local, stream=stream)
-        genome = synth.make_genome(4_600_000 * world, seed=42)
-        seq, off, _ = synth.make_reads(genome, 30 / world, 0.10, seed=43 + rank)
+        if "weak" in sys.argv[1:]:  # the bench's weak-scaled headline: every rank holds 30x of the SAME 4.6 Mb genome
+            genome = synth.make_genome(4_600_000, seed=42)
+            seq, off, _ = synth.make_reads(genome, 30, 0.10, seed=43 + rank)
+        else:  # a genome that grows with the box, 30x in total
+            genome = synth.make_genome(4_600_000 * world, seed=42)
+            seq, off, _ = synth.make_reads(genome, 30 / world, 0.10, seed=43 + rank)
         reads = br_b200.Reads.upload(ctx, seq, off)
         acc = {}
+        class DistProxy:  # times the collectives (with a device synchronise on both sides) by name and payload
+            def __init__(self, d):
+                self._d = d
+            def __getattr__(self, name):
+                f = getattr(self._d, name)
+                if name not in ("all_gather_into_tensor", "all_gather", "broadcast", "all_reduce"):
+                    return f
+                def g(*a, **k):
+                    torch.cuda.synchronize(); t = time.perf_counter()
+                    r = f(*a, **k)
+                    torch.cuda.synchronize()
+                    out = a[0]
+                    n = sum(x.numel() * x.element_size() for x in out) if isinstance(out, (list, tuple)) else out.numel() * out.element_size()
+                    key = f"  nccl {name} {'>=1MB' if n >= 1 << 20 else 'small'}"
+                    acc[key] = acc.get(key, 0.0) + time.perf_counter() - t
+                    return r
+                return g
         class Timed(bdist.GpuOps):
-            pass
+            def __init__(self, *a, **k):
+                super().__init__(*a, **k)
+                self.dist = DistProxy(self.dist)
         def wrap(name):
             orig = getattr(bdist.GpuOps, name)
             def f(self, *a, **k):

@@ -284,9 +284,10 @@ def test_segment_scratch_overflow_falls_back_to_the_merge_warp(gpu, oracle):
 
 
 @pytest.mark.parametrize("k", [15, 17])
-def test_large_k_sets_correct_like_the_oracle_on_every_lookup_path(gpu, oracle, k):
+def test_large_k_sets_correct_like_the_oracle_on_every_lookup_path(gpu, oracle, k, request):
     """k = 15 / 17 (BASELINE configs 2-5): the set is looked up through the rank-compacted copy
-    (directory + occupied 64-bit blocks) when it is sparse, through summary + bitfield otherwise.
+    (directory + one byte per occupied block, the 64-bit block only where it holds several k-mers)
+    when it is sparse, through summary + bitfield otherwise.
     Both paths, for a set built by counting and for the same set loaded as a bitfield, must give
     the oracle's bytes for all five methods chained with the reversed pass."""
     br, ctx = gpu
@@ -301,19 +302,23 @@ def test_large_k_sets_correct_like_the_oracle_on_every_lookup_path(gpu, oracle, 
     exp, exp_off = osolid.run_correction(ids, seq, off, confirm=4, max_search=7, threads=8)
     changed = int((np.diff(exp_off.astype(np.int64)) != np.diff(off.astype(np.int64))).sum())
     assert changed > 10  # the chain really edits reads
-    for no_compact in ("0", "1"):
+    request.addfinalizer(lambda: (ctx.set_option("no_compact", 0), ctx.set_option("no_pos8", 0)))
+    # compacted with the one-byte form of the blocks (default) / compacted, 64-bit blocks only / summary + bitfield
+    for no_compact, no_pos8 in (("0", 0), ("0", 1), ("1", 0)):
         ctx.set_option("no_compact", int(no_compact))
+        ctx.set_option("no_pos8", no_pos8)
         counted = br.Pcon.from_reads(ctx, (seq, off), k, abundance=2)
         assert np.array_equal(counted.bitfield(), osolid.bits())
         loaded = br.Pcon.from_bitfield(ctx, k, osolid.bits())
         for name, s in (("counted", counted), ("loaded", loaded)):
             got, got_off = br.correct_batch(br.build_methods(METHODS, s, 4, 7), seq, off)
-            compare_batches(f"k={k} {name} no_compact={no_compact}", got, got_off, exp, exp_off, seq, off)
+            compare_batches(f"k={k} {name} no_compact={no_compact} no_pos8={no_pos8}", got, got_off, exp, exp_off, seq, off)
         counted.free()
         loaded.free()
     # a denser set (17 % of the 64-bit blocks occupied): the rank-compacted copy is built by the
     # streaming kernel instead of the sparse one
     ctx.set_option("no_compact", 0)
+    ctx.set_option("no_pos8", 0)
     rng = np.random.default_rng(k)
     dense_bits = osolid.bits().copy()
     pos = rng.integers(0, dense_bits.size * 8, size=int(dense_bits.size * 8 * 0.003), dtype=np.int64)
