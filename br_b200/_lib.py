@@ -87,6 +87,8 @@ SIGNATURES = {
     "brgpu_set_slice_compact": (C.c_int, [vp, u64, u64, pvp, pu64]),
     "brgpu_set_compact_alloc": (C.c_int, [vp, u64, pvp]),
     "brgpu_set_compact_commit": (C.c_int, [vp]),
+    "brgpu_set_slice_ipc_export": (C.c_int, [vp, vp]),
+    "brgpu_set_compact_pull": (C.c_int, [vp, vp, vp, C.c_int]),
     "brgpu_set_summary_ptr": (vp, [vp, pu64]),
     "brgpu_set_commit_slices": (C.c_int, [vp, C.c_int]),
     "brgpu_set_free": (None, [vp]),

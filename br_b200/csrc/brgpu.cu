@@ -2028,6 +2028,41 @@ extern "C" int brgpu_set_compact_alloc(brgpu_set *s, uint64_t n_blocks_total, vo
     return BRGPU_OK;
 }
 
+extern "C" int brgpu_set_slice_ipc_export(brgpu_set *s, uint8_t handle_out[64]) {
+    if (!s || !handle_out || !s->d_slice_blocks) return BRGPU_E_INVALID;
+    brgpu_ctx *ctx = s->ctx;
+    cudaSetDevice(ctx->device);
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, s->d_slice_blocks));
+    memcpy(handle_out, &h, 64);
+    ctx->pool_exported[s->d_slice_blocks] = true;
+    return BRGPU_OK;
+}
+
+extern "C" int brgpu_set_compact_pull(brgpu_set *s, void *const *slice_blocks, const uint64_t *n_blocks, int n_slices) {
+    if (!s || !slice_blocks || !n_blocks || s->is_hash || !s->d_blocks) return BRGPU_E_INVALID;
+    brgpu_ctx *ctx = s->ctx;
+    if (n_slices < 1 || n_slices > 2 * BRGPU_MAX_KMER_SOURCES) return fail(ctx, BRGPU_E_INVALID, "at most 128 slices");
+    cudaSetDevice(ctx->device);
+    PullSegments segs;
+    segs.n = 0;
+    uint64_t at = 0;
+    for (int i = 0; i < n_slices; i++) {
+        const void *src = slice_blocks[i] ? slice_blocks[i] : (const void *)s->d_slice_blocks;
+        if (n_blocks[i]) {
+            if (!src || (reinterpret_cast<uintptr_t>(src) & 15u)) return fail(ctx, BRGPU_E_INVALID, "compacted slice pointer");
+            segs.src[segs.n] = static_cast<const uint8_t *>(src);
+            segs.dst[segs.n] = reinterpret_cast<uint8_t *>(s->d_blocks + at);
+            segs.bytes[segs.n++] = n_blocks[i] * 8;
+        }
+        at += n_blocks[i];
+    }
+    if (at != s->n_occupied) return fail(ctx, BRGPU_E_INVALID, "slices do not add up to the allocated block array");
+    launch_peer_pull(ctx, segs, (double)at * 8.0);
+    CK(cudaGetLastError());
+    return BRGPU_OK;
+}
+
 extern "C" int brgpu_set_compact_commit(brgpu_set *s) {
     if (!s || s->is_hash || !s->d_dir || !s->d_blocks) return BRGPU_E_INVALID;
     brgpu_ctx *ctx = s->ctx;

@@ -214,7 +214,7 @@ extern "C" int brgpu_group_set_from_reads(brgpu_group *g, int k, int abundance, 
         if (st == BRGPU_OK) st = count_phase(abundance, true, &hist);
         // A sparse set travels in rank-compacted form (the same decision as dist.py's _exchange_compacted): every
         // device compacts its slice, and if the blocks of all slices take less than half the bitfield each device
-        // pushes its blocks into every replica's block array at its slice's offset, together with its summary slice;
+        // pulls all slices into its replica's block array (brgpu_set_compact_pull) and pushes its summary slice to the peers;
         // the replicas then only build the rank directory.  Otherwise the bitfield slices themselves are pushed.
         std::vector<void *> my_blocks(n, nullptr), all_blocks(n, nullptr);
         std::vector<uint64_t> n_blocks(n, 0);
@@ -240,17 +240,16 @@ extern "C" int brgpu_group_set_from_reads(brgpu_group *g, int k, int abundance, 
                 uint64_t b0, b1;
                 bucket_range(n_buckets, n, i, &b0, &b1);
                 const uint64_t byte0 = (b0 << GROUP_BUCKET_BITS) >> 3, bytes = ((b1 - b0) << GROUP_BUCKET_BITS) >> 3;
-                uint64_t at = 0; // this slice's position in the block array
-                for (int j = 0; j < i; j++) at += n_blocks[j];
+                if (compacted) { // every replica pulls all slices into its block array: one kernel, all peers in flight
+                    std::vector<void *> src(n);
+                    for (int j = 0; j < n; j++) src[j] = j == i ? nullptr : my_blocks[j];
+                    int s = brgpu_set_compact_pull(sets[i], src.data(), n_blocks.data(), n);
+                    if (s != BRGPU_OK) return s;
+                }
                 for (int j = 0; j < n; j++) {
-                    if (compacted) { // own replica included: the slice's blocks sit in scratch
-                        if (n_blocks[i] && cudaMemcpyAsync((uint64_t *)all_blocks[j] + at, my_blocks[i], n_blocks[i] * 8, cudaMemcpyDefault,
-                                                           g->ctx[i]->stream) != cudaSuccess)
-                            return fail(g->ctx[i], BRGPU_E_CUDA, "compacted slice copy", cudaGetLastError());
-                    } else if (j != i && cudaMemcpyAsync(sets[j]->d_bits + byte0, sets[i]->d_bits + byte0, bytes, cudaMemcpyDefault,
-                                                         g->ctx[i]->stream) != cudaSuccess) {
+                    if (!compacted && j != i && cudaMemcpyAsync(sets[j]->d_bits + byte0, sets[i]->d_bits + byte0, bytes, cudaMemcpyDefault,
+                                                                g->ctx[i]->stream) != cudaSuccess)
                         return fail(g->ctx[i], BRGPU_E_CUDA, "bitfield slice copy", cudaGetLastError());
-                    }
                     if (j != i && sets[i]->d_summary && sets[j]->d_summary &&
                         cudaMemcpyAsync((uint8_t *)sets[j]->d_summary + (byte0 >> 6), (uint8_t *)sets[i]->d_summary + (byte0 >> 6), bytes >> 6,
                                         cudaMemcpyDefault, g->ctx[i]->stream) != cudaSuccess)

@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdint>
 #include <memory>
 #include <string>
@@ -169,6 +170,14 @@ void prof_begin(brgpu_ctx *ctx, const char *name, double algo_bytes, bool is_ker
 void prof_end(brgpu_ctx *ctx);
 // device counter for the KmerSet::get calls of the kernel whose ProfScope is open
 unsigned long long *prof_counter_slot(brgpu_ctx *ctx);
+
+// cudaFuncSetAttribute applies to the CURRENT device only: a process that drives several GPUs (brgpu_group_*)
+// configures a kernel once per device, not once per process
+struct PerDeviceOnce {
+    std::atomic<uint64_t> done{0};
+    bool need(int device) const { return !((done.load(std::memory_order_acquire) >> (device & 63)) & 1ULL); }
+    void mark(int device) { done.fetch_or(1ULL << (device & 63), std::memory_order_release); }
+};
 
 struct ProfScope {
     brgpu_ctx *c;

@@ -855,12 +855,12 @@ __global__ void __launch_bounds__(BUCKET_THREADS)
 void launch_bucket_count_multi(brgpu_ctx *ctx, const uint16_t *const *d_res, const uint64_t *const *d_base, int n_src,
                                uint64_t b0, uint64_t b1, int abundance, uint8_t *d_bits, uint32_t *d_summary,
                                uint64_t *d_hist, double n_kmers) {
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (configured.need(ctx->device)) {
         cudaFuncSetAttribute(bucket_count_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BUCKET_COUNTERS);
         cudaFuncSetAttribute(bucket_count_multi_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
-        configured = true;
+        configured.mark(ctx->device);
     }
     if (b1 <= b0) return;
     BucketSources src;
@@ -913,8 +913,9 @@ void launch_block_bytes(brgpu_ctx *ctx, const uint64_t *d_blocks, uint64_t n_occ
 // the residues (2 B per k-mer) and the slice of bucket offsets — with 16 B loads over NVLink, all peers in
 // flight together (NVSwitch gives the reader its full inbound bandwidth whatever the number of sources; one
 // cudaMemcpyAsync per peer, in stream order, ran at a third of it: 7 x 0.07 ms for 7 x 23 MB at N = 8).
-// Source and destination of a segment are congruent modulo 16 (the caller pads the destination), sizes are
-// multiples of 2: head and tail of a segment move as 2 B pieces, the body as uint4.
+// Source and destination of a segment are congruent modulo 16 (the caller pads the destination) or differ by 8
+// (compacted slices land at their block offset: the body is then stored as two 8 B halves); sizes are
+// multiples of 2: head and tail of a segment move as 2 B pieces, the body as 16 B loads.
 constexpr int PULL_THREADS = 256;
 constexpr int PULL_UNROLL = 4;
 constexpr uint32_t PULL_CHUNK_VECS = PULL_THREADS * PULL_UNROLL * 4; // 64 KiB per block and turn
@@ -938,6 +939,8 @@ __global__ void __launch_bounds__(PULL_THREADS) peer_pull_kernel(PullSegments se
         const uint64_t tail = bytes - head - (n_vec << 4);
         const uint4 *sv = reinterpret_cast<const uint4 *>(src + head);
         uint4 *dv = reinterpret_cast<uint4 *>(dst + head);
+        uint2 *dh = reinterpret_cast<uint2 *>(dst + head);
+        const bool halves = ((reinterpret_cast<uintptr_t>(dst) - reinterpret_cast<uintptr_t>(src)) & 15u) != 0;
         const uint64_t v0 = (uint64_t)local * PULL_CHUNK_VECS;
         const uint64_t v1 = v0 + PULL_CHUNK_VECS < n_vec ? v0 + PULL_CHUNK_VECS : n_vec;
         for (uint64_t v = v0 + threadIdx.x; v < v1; v += PULL_THREADS * PULL_UNROLL) {
@@ -946,8 +949,16 @@ __global__ void __launch_bounds__(PULL_THREADS) peer_pull_kernel(PullSegments se
             for (int u = 0; u < PULL_UNROLL; u++)
                 if (v + (uint64_t)u * PULL_THREADS < v1) r[u] = __ldcs(sv + v + (uint64_t)u * PULL_THREADS);
 #pragma unroll
-            for (int u = 0; u < PULL_UNROLL; u++)
-                if (v + (uint64_t)u * PULL_THREADS < v1) dv[v + (uint64_t)u * PULL_THREADS] = r[u];
+            for (int u = 0; u < PULL_UNROLL; u++) {
+                const uint64_t at = v + (uint64_t)u * PULL_THREADS;
+                if (at >= v1) continue;
+                if (!halves) {
+                    dv[at] = r[u];
+                } else {
+                    dh[2 * at] = make_uint2(r[u].x, r[u].y);
+                    dh[2 * at + 1] = make_uint2(r[u].z, r[u].w);
+                }
+            }
         }
         if (local == 0) {
             const uint16_t *s2 = reinterpret_cast<const uint16_t *>(src);
@@ -1233,11 +1244,11 @@ void launch_bucket_partition(brgpu_ctx *ctx, const Layout &L, const uint8_t *d_s
             const uint64_t n_tiles = (n_words + CP_THREADS - 1) / CP_THREADS;
             int per_sm = 0;
             const size_t cs_smem = 2 * CP_TILE_KMERS * sizeof(uint32_t);
-            static bool cs_configured = false;
-            if (!cs_configured) {
+            static PerDeviceOnce cs_configured; // 64 KiB of dynamic shared memory: opt-in, per device
+            if (cs_configured.need(ctx->device)) {
                 cudaFuncSetAttribute(coarse_scatter_kernel<17>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs_smem);
                 cudaFuncSetAttribute(coarse_scatter_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cs_smem);
-                cs_configured = true;
+                cs_configured.mark(ctx->device);
             }
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, coarse_scatter_kernel<17>, CP_THREADS, cs_smem) != cudaSuccess ||
                 per_sm < 1) {
@@ -1280,12 +1291,12 @@ void launch_bucket_partition(brgpu_ctx *ctx, const Layout &L, const uint8_t *d_s
 template <int THREADS, int ROUNDS, bool DIRECT>
 static void launch_bucket_count_shape(brgpu_ctx *ctx, const uint16_t *d_residues, const uint64_t *d_base, uint64_t n_buckets,
                                       int abundance, uint8_t *d_bits, uint32_t *d_summary, int summary_shift, uint64_t *d_hist) {
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (configured.need(ctx->device)) {
         cudaFuncSetAttribute(bucket_count_kernel<THREADS, ROUNDS, DIRECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, BUCKET_COUNTERS);
         cudaFuncSetAttribute(bucket_count_kernel<THREADS, ROUNDS, DIRECT>, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
-        configured = true;
+        configured.mark(ctx->device);
     }
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bucket_count_kernel<THREADS, ROUNDS, DIRECT>, THREADS, BUCKET_COUNTERS) !=

@@ -325,43 +325,45 @@ class GpuOps:
 
     def _exchange_compacted(self, begin, end, bounds, n_bytes, summary):
         """A sparse set travels in rank-compacted form: every rank compacts its slice (occupied 64-bit blocks in
-        index order), the counts are all-gathered (the step's second small host round trip), and if the blocks of
-        all slices together take less than half the bitfield each rank broadcasts its blocks into everybody's
-        block array — slices are contiguous index ranges, so their concatenation in rank order IS the compacted
-        set — along with the summary slices.  E. coli x 8 at N = 8: 0.3 GB instead of 1 GiB on the wire, and no
-        compaction pass over the gathered bitfield.  Returns False when the dense exchange should run instead."""
+        index order); ONE small all-gather carries the slice's block count and CUDA-IPC handle (the step's second
+        host round trip); if the blocks of all slices together take less than half the bitfield, every rank pulls
+        all slices over NVLink into its block array with one kernel (`brgpu_set_compact_pull`: slices are
+        contiguous index ranges, so their concatenation in rank order IS the compacted set) and the summary
+        slices are all-gathered.  E. coli x 8 at N = 8: 0.3 GB instead of 1 GiB on the wire, no compaction pass
+        over the gathered bitfield.  Returns False when the dense exchange should run instead.
+
+        Ordering (context on torch's current stream): the small all-gather completes on a rank only after every
+        peer's compaction kernel has (slices complete before anybody pulls); the summary all-gather AFTER the pull
+        completes only after every peer's pull has (nobody reuses its slice buffer while a peer still reads it)."""
         torch = self.torch
         if any(b % 2048 or e % 2048 for b, e in bounds) or any(((e - b) // 8) != ((end - begin) // 8) for b, e in bounds):
             return False
         ptr, n_mine = C.c_void_p(), C.c_uint64()
         check(lib.brgpu_set_slice_compact(self.set._h, begin, end, C.byref(ptr), C.byref(n_mine)), self.ctx._h)
-        mine = torch.tensor([n_mine.value if ptr.value else -1], dtype=torch.int64, device=self.dev)
-        counts = torch.empty(self.world, dtype=torch.int64, device=self.dev)
-        self.dist.all_gather_into_tensor(counts, mine, group=self.group)
-        counts = counts.cpu().tolist()
+        words = [-1] + [0] * 8
+        if ptr.value:
+            h = (C.c_uint8 * 64)()
+            check(lib.brgpu_set_slice_ipc_export(self.set._h, h), self.ctx._h)
+            words = [n_mine.value] + np.frombuffer(bytes(h), dtype=np.int64).tolist()
+        if not self.stream_ordered:
+            self.ctx.synchronize()
+        mine = torch.tensor(words, dtype=torch.int64, device=self.dev)
+        rows = torch.empty(self.world * 9, dtype=torch.int64, device=self.dev)
+        self.dist.all_gather_into_tensor(rows, mine, group=self.group)
+        rows = rows.cpu().numpy().reshape(self.world, 9)
+        counts = [int(c) for c in rows[:, 0]]
         total = sum(counts)
         if min(counts) < 0 or total * 8 > n_bytes // 2:
             return False  # compaction unavailable somewhere, or the set is too dense to gain from it
         dst = C.c_void_p()
         check(lib.brgpu_set_compact_alloc(self.set._h, total, C.byref(dst)), self.ctx._h)
-        blocks = torch.as_tensor(_CudaArray(dst.value, max(1, total) * 8, "<i8"), device=self.dev)
+        slices = [None if r == self.rank or not counts[r] else self._ipc_open_cached(rows[r, 1:].tobytes()).value
+                  for r in range(self.world)]
+        check(lib.brgpu_set_compact_pull(self.set._h, (C.c_void_p * self.world)(*slices), (C.c_uint64 * self.world)(*counts),
+                                         self.world), self.ctx._h)
+        if not self.stream_ordered:
+            self.ctx.synchronize()
         self.dist.all_gather_into_tensor(summary, summary[begin // 512 : end // 512], group=self.group)
-        regions, at = [], 0
-        for c in counts:
-            regions.append(blocks[at : at + c])
-            at += c
-        mine_blocks = torch.as_tensor(_CudaArray(ptr.value, max(1, n_mine.value) * 8, "<i8"), device=self.dev)[: n_mine.value]
-        if min(counts) > 0:
-            # ragged all-gather: ProcessGroupNCCL turns output tensors of different sizes into ONE group of
-            # broadcasts (a single launch, all roots in flight together) instead of `world` launches in a row
-            self.dist.all_gather(regions, mine_blocks, group=self.group)
-        else:  # an empty slice somewhere (tiny inputs): one broadcast per non-empty slice
-            for r, c in enumerate(counts):
-                if c:
-                    if r == self.rank:
-                        regions[r].copy_(mine_blocks, non_blocking=True)
-                    src = self.dist.get_global_rank(self.group, r) if self.group else r
-                    self.dist.broadcast(regions[r], src=src, group=self.group)
         self._compact_exchanged = True
         return True
 

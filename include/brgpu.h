@@ -235,6 +235,14 @@ int brgpu_set_new_sliced(brgpu_ctx *ctx, int k, brgpu_set **out);
 int brgpu_set_slice_compact(brgpu_set *set, uint64_t bit_begin, uint64_t bit_end, void **blocks_dev, uint64_t *n_blocks);
 int brgpu_set_compact_alloc(brgpu_set *set, uint64_t n_blocks_total, void **blocks_dev);
 int brgpu_set_compact_commit(brgpu_set *set);
+/* The exchange itself over peer memory instead of a collective: _slice_ipc_export hands out the CUDA-IPC handle of
+ * the compacted slice (processes) — inside one process the peer's pointer is used as it is; _compact_pull, after
+ * _compact_alloc, copies every slice (slice_blocks[i] == NULL: this GPU's own) to its place in the block array with
+ * ONE kernel that has all peers' NVLink loads in flight together.  The caller orders it after every peer's
+ * _slice_compact and keeps the slices alive until every peer has pulled (dist.py: the two small collectives either
+ * side of it; group.cu: the joins). */
+int brgpu_set_slice_ipc_export(brgpu_set *set, uint8_t handle_out[64]);
+int brgpu_set_compact_pull(brgpu_set *set, void *const *slice_blocks, const uint64_t *n_blocks, int n_slices);
 void *brgpu_set_summary_ptr(brgpu_set *set, uint64_t *n_bytes);
 int brgpu_set_commit_slices(brgpu_set *set, int summary_complete);
 void brgpu_set_free(brgpu_set *set);
