@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
                     for (int j = 0; j < 8; j++) {
                         e[j] = make_uint2(0u, 0u);
-                        if (go[j]) e[j] = __ldg(set.dir + (idx[j] >> 11));
+                        if (go[j]) e[j] = set_ld(set.dir + (idx[j] >> 11));
                     }
                     uint32_t r[8], pv[8]; // then the block's byte (1 B) and, for a block with several k-mers, the block (8 B)
 #pragma unroll
@@ -96,12 +96,12 @@ __global__ void __launch_bounds__(256)
                         const uint32_t b = (uint32_t)(idx[j] >> 6) & 31u;
                         r[j] = e[j].y + __popc(e[j].x & ((1u << b) - 1u));
                         pv[j] = POS8_NONE;
-                        if ((e[j].x >> b) & 1u) pv[j] = set.pos8 ? (uint32_t)__ldg(set.pos8 + r[j]) : POS8_MULTI;
+                        if ((e[j].x >> b) & 1u) pv[j] = set.pos8 ? set_ld(set.pos8 + r[j]) : POS8_MULTI;
                     }
 #pragma unroll
                     for (int j = 0; j < 8; j++) {
                         uint32_t hit = pv[j] == (uint32_t)(idx[j] & 63);
-                        if (pv[j] == POS8_MULTI) hit = (uint32_t)((__ldg(set.blocks + r[j]) >> (idx[j] & 63)) & 1ULL);
+                        if (pv[j] == POS8_MULTI) hit = (uint32_t)((set_ld(set.blocks + r[j]) >> (idx[j] & 63)) & 1ULL);
                         out |= hit << (g + j);
                     }
                     continue;

@@ -111,6 +111,44 @@ template <class SV> inline SolidView solid_view(const SV &s) {
     return SolidView{s.bits, s.summary, s.shift, s.k, (const uint2 *)s.dir, s.blocks, s.pos8, s.hash, s.hash_mask};
 }
 
+// Loads of the lookup structures (directory, block bytes, blocks).  BRGPU_SET_LOAD_MODE: 0 = ld.global.nc (__ldg),
+// 1 = ld.global.cg (L2 only), 2 = ld.global.nc with an L2 evict_last cache hint — the set is what every lookup of a
+// correction pass returns to, the reads / bitmap / scratch stream past it once; the policy is a compile-time
+// constant that ptxas folds into the load's descriptor.
+#ifndef BRGPU_SET_LOAD_MODE
+#define BRGPU_SET_LOAD_MODE 0
+#endif
+#if BRGPU_SET_LOAD_MODE == 2
+__device__ __forceinline__ uint64_t l2_keep_policy() {
+    uint64_t p;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint2 set_ld(const uint2 *p) {
+    uint2 r;
+    asm("ld.global.nc.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(r.x), "=r"(r.y) : "l"(p), "l"(l2_keep_policy()));
+    return r;
+}
+__device__ __forceinline__ uint32_t set_ld(const uint8_t *p) {
+    uint32_t r;
+    asm("ld.global.nc.L2::cache_hint.u8 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(l2_keep_policy()));
+    return r;
+}
+__device__ __forceinline__ uint64_t set_ld(const uint64_t *p) {
+    uint64_t r;
+    asm("ld.global.nc.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(r) : "l"(p), "l"(l2_keep_policy()));
+    return r;
+}
+#elif BRGPU_SET_LOAD_MODE == 1
+__device__ __forceinline__ uint2 set_ld(const uint2 *p) { return __ldcg(p); }
+__device__ __forceinline__ uint32_t set_ld(const uint8_t *p) { return __ldcg(p); }
+__device__ __forceinline__ uint64_t set_ld(const uint64_t *p) { return (uint64_t)__ldcg(reinterpret_cast<const unsigned long long *>(p)); }
+#else
+__device__ __forceinline__ uint2 set_ld(const uint2 *p) { return __ldg(p); }
+__device__ __forceinline__ uint32_t set_ld(const uint8_t *p) { return __ldg(p); }
+__device__ __forceinline__ uint64_t set_ld(const uint64_t *p) { return __ldg(p); }
+#endif
+
 __device__ __forceinline__ bool hash_contains(const uint64_t *__restrict__ table, uint64_t slot_mask, uint64_t key) {
     uint64_t h = hash_mix64(key) & slot_mask;
     for (;;) {
@@ -126,15 +164,15 @@ __device__ __forceinline__ bool solid(const SolidView &v, uint64_t kmer) {
     uint64_t idx = canonical_index(kmer, v.k);
     if (v.dir) {
         const uint64_t j = idx >> 6;
-        const uint2 e = __ldg(v.dir + (j >> 5));
+        const uint2 e = set_ld(v.dir + (j >> 5));
         const uint32_t b = (uint32_t)j & 31u;
         if (!((e.x >> b) & 1u)) return false;
         const uint32_t r = e.y + __popc(e.x & ((1u << b) - 1u));
         if (v.pos8) {
-            const uint32_t p = __ldg(v.pos8 + r);
+            const uint32_t p = set_ld(v.pos8 + r);
             if (p != POS8_MULTI) return p == (uint32_t)(idx & 63);
         }
-        return (__ldg(v.blocks + r) >> (idx & 63)) & 1ULL;
+        return (set_ld(v.blocks + r) >> (idx & 63)) & 1ULL;
     }
     if (v.summary) {
         uint64_t j = idx >> v.shift;

@@ -1348,7 +1348,7 @@ __device__ __forceinline__ void g_lookup_n(G8 &g, const SolidView &set, const ui
 #pragma unroll
         for (int t = 0; t < N; t++) {
             e[t] = make_uint2(0u, 0u);
-            if (want[t]) e[t] = __ldg(set.dir + (idx[t] >> 11));
+            if (want[t]) e[t] = set_ld(set.dir + (idx[t] >> 11));
         }
         uint32_t r[N], pv[N]; // rank of the block among the occupied ones; its byte (kmer.cuh: SolidView::pos8)
 #pragma unroll
@@ -1356,12 +1356,12 @@ __device__ __forceinline__ void g_lookup_n(G8 &g, const SolidView &set, const ui
             const uint32_t b = (uint32_t)(idx[t] >> 6) & 31u;
             r[t] = e[t].y + __popc(e[t].x & ((1u << b) - 1u));
             pv[t] = POS8_NONE;
-            if ((e[t].x >> b) & 1u) pv[t] = set.pos8 ? (uint32_t)__ldg(set.pos8 + r[t]) : POS8_MULTI;
+            if ((e[t].x >> b) & 1u) pv[t] = set.pos8 ? set_ld(set.pos8 + r[t]) : POS8_MULTI;
         }
 #pragma unroll
         for (int t = 0; t < N; t++) {
             out[t] = pv[t] == (uint32_t)(idx[t] & 63);
-            if (pv[t] == POS8_MULTI) out[t] = (__ldg(set.blocks + r[t]) >> (idx[t] & 63)) & 1ULL;
+            if (pv[t] == POS8_MULTI) out[t] = (set_ld(set.blocks + r[t]) >> (idx[t] & 63)) & 1ULL;
         }
         return;
     }

@@ -1,6 +1,8 @@
-"""Multi-GPU parity as a pytest: needs >= 2 visible GPUs (skipped on the single-GPU box the driver
-uses for `-m gpu`; run with `gpurun --gpus 2 -- python -m pytest tests/test_gpu_multi.py -m gpu`; the log
-of that run is kept under profiles/).  Spawns tests/multi_gpu_check.py under torch.distributed.run:
+"""Multi-GPU parity as a pytest.  The torch.distributed test needs >= 2 visible GPUs (skipped on the
+single-GPU box the driver uses for `-m gpu`; run with `gpurun --gpus 2 -- python -m pytest
+tests/test_gpu_multi.py -m gpu`; the log of that run is kept under profiles/).  The group tests also run
+with two contexts on ONE GPU (`-d 0,0`): the same partition / pull / count / compacted-exchange code path,
+"peer" pointers being plain device pointers.  Spawns tests/multi_gpu_check.py under torch.distributed.run:
 sharded set == single-GPU set (k = 17 / 15 k-mer protocol, k = 13 table protocol; explicit and
 first-minimum thresholds) and every rank's corrected shard == the same records corrected alone."""
 import subprocess
@@ -28,8 +30,9 @@ def test_sharded_set_and_correction_equal_single_gpu():
     assert "multi-GPU parity OK" in r.stdout
 
 
-def test_group_api_single_process_two_gpus(oracle, fixture_reads):
-    """brgpu_group_*: ONE process owning two GPUs builds the set (k = 15: k-mer protocol, k = 13: table
+@pytest.mark.parametrize("second", [0, 1])
+def test_group_api_single_process_two_gpus(oracle, fixture_reads, second):
+    """brgpu_group_*: ONE process owning two GPUs (or two contexts on one GPU) builds the set (k = 15: k-mer protocol, k = 13: table
     protocol; explicit and first-minimum thresholds) and corrects a batch through the C ABI alone — no
     torch.distributed, no CUDA IPC.  Every replica's bitfield equals the oracle's, the corrected batch
     equals the oracle's bytes in input order."""
@@ -38,14 +41,14 @@ def test_group_api_single_process_two_gpus(oracle, fixture_reads):
     import numpy as np
     import torch
 
-    if torch.cuda.device_count() < 2:
+    if torch.cuda.device_count() < 1 + second:
         pytest.skip("needs at least 2 GPUs")
     import br_b200  # noqa: F401
     from br_b200._lib import lib
 
     seq, off = fixture_reads
     n = off.size - 1
-    devs = (C.c_int * 2)(0, 1)
+    devs = (C.c_int * 2)(0, second)
     g = C.c_void_p()
     assert lib.brgpu_group_create(devs, 2, C.byref(g)) == 0
     try:
@@ -80,7 +83,8 @@ def test_group_api_single_process_two_gpus(oracle, fixture_reads):
         lib.brgpu_group_destroy(g)
 
 
-def test_cli_with_a_device_list_uses_the_group(tmp_path, oracle, fixture_reads, fixture_solid_payload):
+@pytest.mark.parametrize("second", [0, 1])
+def test_cli_with_a_device_list_uses_the_group(tmp_path, oracle, fixture_reads, fixture_solid_payload, second):
     """`brgpu-cli -d 0,1 ... fasta -k 11 -a 2`: the single-process multi-GPU path of the command line."""
     import gzip
 
@@ -89,10 +93,10 @@ def test_cli_with_a_device_list_uses_the_group(tmp_path, oracle, fixture_reads, 
 
     from conftest import GOLDEN, parse_fasta
 
-    if torch.cuda.device_count() < 2:
+    if torch.cuda.device_count() < 1 + second:
         pytest.skip("needs at least 2 GPUs")
     out = tmp_path / "corr.fa"
-    r = subprocess.run([str(ROOT / "br_b200" / "brgpu-cli"), "-d", "0,1", "-i", str(GOLDEN / "br_reads.fa.gz"), "-o", str(out), "-c", "one",
+    r = subprocess.run([str(ROOT / "br_b200" / "brgpu-cli"), "-d", f"0,{second}", "-i", str(GOLDEN / "br_reads.fa.gz"), "-o", str(out), "-c", "one",
                         "two", "fasta", "-i", str(GOLDEN / "br_reads.fa.gz"), "-k", "11", "-a", "2"], capture_output=True, timeout=600)
     assert r.returncode == 0 and r.stderr == b"", r.stderr
     seq, off = fixture_reads
