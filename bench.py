@@ -601,6 +601,11 @@ def run_ours(args, world, rank, local_rank):
                 m2 = measure(wl, CONFIG2_METHODS, steps2, warm2, e2e_warm_extra=4)
                 extra["configs[2]"] = leg_record(m2, wl, wl.n_bases, steps2, warm2, table, hbm_peak, sm_max_mhz, l2_gather,
                                                  workload_name(1, args.genome_per_gpu, CONFIG2_METHODS), "weak", world)
+                if not args.no_parity:  # same reads, same set: only the replay of a read sample with this chain is new
+                    p2 = parity_check(args, ctx, wl, world, rank, tdist, dev, step_device, all_and, single_gpu_rebuild=False,
+                                      sample=100, methods=CONFIG2_METHODS)
+                    p2["note"] = "greedy's alignment (bio 1.6.0 custom global) is restated in the oracle from memory: parity unpinned (DESIGN.md §3)"
+                    extra["configs[2]"]["parity_check"] = p2
             else:
                 wl.free()
                 legs = [("configs[3]", CONFIG3)] + ([("configs[4]", CONFIG4)] if world == 8 and not args.no_config4 else [])
@@ -690,7 +695,7 @@ def leg_record(m, wl, total_bases, steps, warmup, table, hbm_peak, sm_max_mhz, l
     # the solidity lookups of the step (bitmap passes + every KmerSet::get of the scans) per second of the step
     count_names = ("coarse_hist", "coarse_scatter", "fine_partition", "bucket_count", "bucket_count_multi", "peer_pull",
                    "bucket_hist", "bucket_scatter", "count_kmers", "zero_counts", "spectrum_threshold", "spectrum", "summary_popc",
-                   "compact_blocks", "build_summary", "exclusive_scan")
+                   "compact_blocks", "block_bytes", "rank_directory", "build_summary", "exclusive_scan")
     count_ms = sum(m["prof"][k_]["ms"] for k_ in m["prof"] if k_ in count_names) / steps
     scan_excl = sum(m["prof"][k_]["ms"] for k_ in m["prof"] if k_ == "exclusive_scan") / steps
     count_bytes = 0.25 * n_bases + 64.0 * n_kmers
@@ -736,7 +741,7 @@ def leg_record(m, wl, total_bases, steps, warmup, table, hbm_peak, sm_max_mhz, l
     return rec
 
 
-def parity_check(args, ctx, wl, world, rank, tdist, dev, step_device, all_and, single_gpu_rebuild=True, sample=200):
+def parity_check(args, ctx, wl, world, rank, tdist, dev, step_device, all_and, single_gpu_rebuild=True, sample=200, methods=None):
     """Untimed checks on the benched data: (N > 1) every rank's replicated bitfield is the same and equals
     the one a single GPU builds from all ranks' reads through the literal count-table path; (any N) the
     bucketed path's bitfield equals the table path's; a sample of this rank's reads corrected on the GPU
@@ -748,7 +753,8 @@ def parity_check(args, ctx, wl, world, rank, tdist, dev, step_device, all_and, s
 
     o.build()
     res = {}
-    solid, out = step_device(wl, METHODS, keep=True)
+    methods = methods or METHODS
+    solid, out = step_device(wl, methods, keep=True)
     bits = solid.bitfield()
     digest = hashlib.blake2b(bits.tobytes()).hexdigest()
     res["bitfield_blake2b"] = digest
@@ -790,7 +796,7 @@ def parity_check(args, ctx, wl, world, rank, tdist, dev, step_device, all_and, s
     sub_off[1:] = np.cumsum((off[ids + 1] - off[ids]).astype(np.uint64))
     sub_seq = np.concatenate([seq[int(off[i]) : int(off[i + 1])] for i in ids]) if ids.size else np.empty(0, np.uint8)
     osolid = o.Solid.from_bitfield(K, bits)
-    exp, exp_off = osolid.run_correction([o.METHOD_IDS[x] for x in METHODS], sub_seq, sub_off, confirm=CONFIRM,
+    exp, exp_off = osolid.run_correction([o.METHOD_IDS[x] for x in methods], sub_seq, sub_off, confirm=CONFIRM,
                                          max_search=MAX_SEARCH, two_side=False, threads=min(8, host_cores()))
     exp_off = exp_off.astype(np.int64)
     ok = True

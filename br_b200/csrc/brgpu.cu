@@ -1691,6 +1691,10 @@ extern "C" int brgpu_set_from_reads_ex(brgpu_ctx *ctx, int k, int abundance, int
     cudaSetDevice(ctx->device);
     reads_ready(reads);
     if (bucketed_applicable(k, reads)) return set_from_reads_bucketed(ctx, k, abundance, selection, percent, reads, out);
+    // A chunk of 2^32 slot bytes or more cannot be partitioned (32-bit cursors).  At k = 19 the literal table is
+    // 128 GiB: say what to do instead of failing on the allocation; at k <= 17 the table path below still works.
+    if (k >= 19 && reads->layout->n > 0)
+        return fail(ctx, BRGPU_E_INVALID, "reads too large for one chunk at this k: build the set over several chunks (brgpu_kmers_create + brgpu_set_from_kmers)");
     // table path: Counter::new + count_fasta + Spectrum + Solid::from_count, literally
     brgpu_counts *c = nullptr;
     int st = brgpu_counts_create(ctx, k, &c);

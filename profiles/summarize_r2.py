@@ -18,7 +18,7 @@ METHODS = ["one", "two", "graph", "greedy", "gap_size"]
 PRIMARY = {  # kernel function -> (bench name, opens a scope)
     "coarse_hist_kernel": "coarse_hist", "coarse_scatter_kernel": "coarse_scatter", "fine_partition_kernel": "fine_partition",
     "bucket_count_kernel": "bucket_count", "summary_popc_kernel": "summary_popc", "compact_blocks_kernel": "compact_blocks",
-    "compact_blocks_stream_kernel": "compact_blocks", "reverse_slots_kernel": "reverse_slots", "seg_count_kernel": "seg_count",
+    "compact_blocks_stream_kernel": "compact_blocks", "block_bytes_kernel": "block_bytes", "peer_pull_kernel": "peer_pull", "reverse_slots_kernel": "reverse_slots", "seg_count_kernel": "seg_count",
     "bucket_hist_kernel": "bucket_hist", "bucket_scatter_kernel": "bucket_scatter", "build_summary_kernel": "build_summary",
     "count_kernel": "count_kmers", "spectrum_threshold_kernel": "spectrum_threshold",
 }
