@@ -1093,10 +1093,27 @@ __device__ __forceinline__ void correct_segment(Rd &rd, const CorrectParams &p, 
     flush_copy(rd, i < rd.len ? i : rd.len);
 }
 
-// DIRECT: the set is known to be in its rank-compacted form (SolidView::dir), the usual case for a sparse set:
-// the other two lookup arms (summary + bitfield, hash table) are compiled out — a third of the code of a
-// kernel whose warps stall on instruction fetch as often as on memory (profiles/ncu_r2_scan_full.txt)
-template <int METHOD, int KT, bool DIRECT>
+// ARM: which form of the set the kernel is compiled for.  ARM_COMPACT: the rank-compacted form (SolidView::dir),
+// the usual case for a sparse set; ARM_DENSE: summary + bitfield (sets too dense to compact: configs[3] / [4]);
+// ARM_ANY: decided at run time (hash sets, k != 17, the other methods).  In the specialised kernels the other
+// lookup arms are compiled out — a third of the code of a kernel whose warps stall on instruction fetch as often
+// as on memory (profiles/ncu_r2_scan_full.txt); growing the compacted arm by the block bytes cost the dense
+// sets 10 % in the shared kernel, which is why they have their own.
+constexpr int ARM_ANY = 0, ARM_COMPACT = 1, ARM_DENSE = 2;
+__device__ __forceinline__ void specialise_view(SolidView &set, int arm) {
+    if (arm == ARM_COMPACT) {
+        set.hash = nullptr;
+        set.summary = nullptr;
+        __builtin_assume(set.dir != nullptr);
+    } else if (arm == ARM_DENSE) {
+        set.hash = nullptr;
+        set.dir = nullptr;
+        set.blocks = nullptr;
+        set.pos8 = nullptr;
+        __builtin_assume(set.summary != nullptr);
+    }
+}
+template <int METHOD, int KT, int ARM>
 __global__ void __launch_bounds__(SCAN_WARPS_PER_BLOCK * 32, (METHOD == BRGPU_ONE || METHOD == BRGPU_TWO) ? BRGPU_SCAN_MINB : 1)
     scan_spec_kernel(const uint8_t *__restrict__ in, const uint32_t *__restrict__ len_in,
                      const uint64_t *__restrict__ slot_off, const uint32_t *__restrict__ bitmap,
@@ -1107,11 +1124,7 @@ __global__ void __launch_bounds__(SCAN_WARPS_PER_BLOCK * 32, (METHOD == BRGPU_ON
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     Rd rd;
     if (KT) p.k = KT; // compile-time k: the k-mer arithmetic below folds to immediates
-    if (DIRECT) {
-        set.hash = nullptr;
-        set.summary = nullptr;
-        __builtin_assume(set.dir != nullptr);
-    }
+    specialise_view(set, ARM);
     rd.set = set;
     rd.set.k = p.k;
     rd.k = p.k;
@@ -1737,7 +1750,7 @@ __device__ __forceinline__ Corr g_exist_correct_error(G8 &g, const SolidView &se
     return res;
 }
 
-template <int METHOD, int KT, bool DIRECT>
+template <int METHOD, int KT, int ARM>
 __global__ void __launch_bounds__(SCAN_WARPS_PER_BLOCK * 32, BRGPU_SCAN8_MINB)
     scan_spec8_kernel(const uint8_t *__restrict__ in, const uint32_t *__restrict__ len_in,
                       const uint64_t *__restrict__ slot_off, const uint32_t *__restrict__ bitmap,
@@ -1747,11 +1760,7 @@ __global__ void __launch_bounds__(SCAN_WARPS_PER_BLOCK * 32, BRGPU_SCAN8_MINB)
     constexpr int NS = METHOD == BRGPU_ONE ? 3 : 13;
     if (KT) p.k = KT;
     set.k = p.k;
-    if (DIRECT) {
-        set.hash = nullptr;
-        set.summary = nullptr;
-        __builtin_assume(set.dir != nullptr);
-    }
+    specialise_view(set, ARM);
     const uint32_t k = (uint32_t)p.k, c = (uint32_t)p.confirm;
     G8 g;
     g.gl = threadIdx.x & 7;
@@ -1972,6 +1981,11 @@ template <class K> static int occupancy_warps(brgpu_ctx *ctx, K kernel) {
 }
 
 // One pass of method M over all reads: speculative per-segment scan, per-read merge, parallel splice.
+// the specialised kernels are only instantiated where they are launched (One / Two at k = 17)
+template <int M, int KT> constexpr int special_arm(int arm) {
+    return (KT == 17 && (M == BRGPU_ONE || M == BRGPU_TWO)) ? arm : ARM_ANY;
+}
+
 template <int M, int KT> static void launch_scan_method(const ScanArgs &a) {
     brgpu_ctx *ctx = a.ctx;
     const Layout &L = *a.L;
@@ -1991,32 +2005,34 @@ template <int M, int KT> static void launch_scan_method(const ScanArgs &a) {
         // 2.37 vs 1.72 ms), so it is off unless asked for (ctx option "scan_mode": A/B runs, tests).
         const bool force_warp = ctx->opt_scan_mode == 1, force_groups = ctx->opt_scan_mode == 2;
         // the specialised kernels exist for the methods and the k of the headline configs; others share the general one
-        const bool direct = a.sv.dir != nullptr && a.sv.hash == nullptr && KT == 17 && (M == BRGPU_ONE || M == BRGPU_TWO);
+        const bool special = a.sv.hash == nullptr && KT == 17 && (M == BRGPU_ONE || M == BRGPU_TWO);
+#ifdef BRGPU_NO_ARM_DENSE // A/B builds: dense sets through the run-time dispatching kernel
+        const int arm = special && a.sv.dir != nullptr ? ARM_COMPACT : ARM_ANY;
+#else
+        const int arm = !special ? ARM_ANY : a.sv.dir != nullptr ? ARM_COMPACT : a.sv.summary != nullptr ? ARM_DENSE : ARM_ANY;
+#endif
         if ((M == BRGPU_ONE && !force_warp) || (M == BRGPU_TWO && force_groups)) {
             // four segments per warp: a quarter of the warps for the same number of segments in flight
             constexpr int MG = (M == BRGPU_ONE || M == BRGPU_TWO) ? M : BRGPU_ONE;
             const uint64_t groups = scan_max_segments(L);
-            const unsigned grid = grid_for_warps((uint64_t)occupancy_warps(ctx, scan_spec8_kernel<MG, KT, false>), (groups + 3) / 4);
-            if (direct)
-                scan_spec8_kernel<MG, KT, true><<<grid, threads, 0, ctx->stream>>>(a.d_in, a.d_len_in, L.d_slot_off, a.d_bitmap,
-                                                                                w.d_seg_first, (uint32_t)L.n, w.d_seg_out,
-                                                                                (SegRec *)w.d_seg_recs, ctx->d_flags, a.sv, a.p, gc);
-            else
-                scan_spec8_kernel<MG, KT, false><<<grid, threads, 0, ctx->stream>>>(a.d_in, a.d_len_in, L.d_slot_off, a.d_bitmap,
-                                                                                 w.d_seg_first, (uint32_t)L.n, w.d_seg_out,
-                                                                                 (SegRec *)w.d_seg_recs, ctx->d_flags, a.sv, a.p, gc);
+            const unsigned grid = grid_for_warps((uint64_t)occupancy_warps(ctx, scan_spec8_kernel<MG, KT, ARM_ANY>), (groups + 3) / 4);
+            auto go = [&](auto kernel) {
+                kernel<<<grid, threads, 0, ctx->stream>>>(a.d_in, a.d_len_in, L.d_slot_off, a.d_bitmap, w.d_seg_first, (uint32_t)L.n,
+                                                          w.d_seg_out, (SegRec *)w.d_seg_recs, ctx->d_flags, a.sv, a.p, gc);
+            };
+            if (arm == ARM_COMPACT) go(scan_spec8_kernel<MG, KT, special_arm<M, KT>(ARM_COMPACT)>);
+            else if (arm == ARM_DENSE) go(scan_spec8_kernel<MG, KT, special_arm<M, KT>(ARM_DENSE)>);
+            else go(scan_spec8_kernel<MG, KT, ARM_ANY>);
         } else {
-            const unsigned grid = grid_for_warps((uint64_t)occupancy_warps(ctx, scan_spec_kernel<M, KT, false>), scan_max_segments(L));
-            if (direct)
-                scan_spec_kernel<M, KT, true><<<grid, threads, 0, ctx->stream>>>(a.d_in, a.d_len_in, L.d_slot_off, a.d_bitmap,
-                                                                              w.d_seg_first, (uint32_t)L.n, w.d_seg_out,
-                                                                              (SegRec *)w.d_seg_recs, ctx->d_flags, a.sv, a.p,
-                                                                              a.d_scratch, a.scratch_per_warp, gc);
-            else
-                scan_spec_kernel<M, KT, false><<<grid, threads, 0, ctx->stream>>>(a.d_in, a.d_len_in, L.d_slot_off, a.d_bitmap,
-                                                                               w.d_seg_first, (uint32_t)L.n, w.d_seg_out,
-                                                                               (SegRec *)w.d_seg_recs, ctx->d_flags, a.sv, a.p,
-                                                                               a.d_scratch, a.scratch_per_warp, gc);
+            const unsigned grid = grid_for_warps((uint64_t)occupancy_warps(ctx, scan_spec_kernel<M, KT, ARM_ANY>), scan_max_segments(L));
+            auto go = [&](auto kernel) {
+                kernel<<<grid, threads, 0, ctx->stream>>>(a.d_in, a.d_len_in, L.d_slot_off, a.d_bitmap, w.d_seg_first, (uint32_t)L.n,
+                                                          w.d_seg_out, (SegRec *)w.d_seg_recs, ctx->d_flags, a.sv, a.p, a.d_scratch,
+                                                          a.scratch_per_warp, gc);
+            };
+            if (arm == ARM_COMPACT) go(scan_spec_kernel<M, KT, special_arm<M, KT>(ARM_COMPACT)>);
+            else if (arm == ARM_DENSE) go(scan_spec_kernel<M, KT, special_arm<M, KT>(ARM_DENSE)>);
+            else go(scan_spec_kernel<M, KT, ARM_ANY>);
         }
     }
     SegCopy *d_copies = reinterpret_cast<SegCopy *>((uint8_t *)w.d_seg_recs + scan_max_segments(L) * sizeof(SegRec));
