@@ -279,6 +279,12 @@ extern "C" int brgpu_ctx_create(int device, void *cuda_stream, brgpu_ctx **out) 
     ctx->opt_no_compact = env_on("BRGPU_NO_COMPACT") ? 1 : 0;
     ctx->opt_one_level_partition = env_on("BRGPU_ONE_LEVEL_PARTITION") ? 1 : 0;
     ctx->opt_no_pos8 = env_on("BRGPU_NO_POS8") ? 1 : 0;
+    ctx->opt_no_fine_summary = env_on("BRGPU_NO_FINE_SUMMARY") ? 1 : 0;
+    ctx->opt_fine_in_scans = env_on("BRGPU_FINE_IN_SCANS") ? 1 : 0;
+    if (const char *v = getenv("BRGPU_COMPACT_MAX_PCT")) {
+        const int pct = atoi(v);
+        ctx->opt_compact_max_pct = pct < 0 ? 0 : pct > 100 ? 100 : pct;
+    }
     if (const char *v = getenv("BRGPU_COUNT_BLOCK_ONLY")) ctx->opt_count_block_only = (*v >= '0' && *v <= '3') ? *v - '0' : 0;
     if (const char *m = getenv("BRGPU_SCAN")) ctx->opt_scan_mode = m[0] == 'w' ? 1 : (m[0] == 'g' ? 2 : 0);
     *out = ctx;
@@ -321,6 +327,8 @@ extern "C" int brgpu_ctx_set_option(brgpu_ctx *ctx, const char *name, int value)
     if (!strcmp(name, "no_compact")) ctx->opt_no_compact = value != 0;
     else if (!strcmp(name, "one_level_partition")) ctx->opt_one_level_partition = value != 0;
     else if (!strcmp(name, "no_pos8")) ctx->opt_no_pos8 = value != 0;
+    else if (!strcmp(name, "no_fine_summary")) ctx->opt_no_fine_summary = value != 0;
+    else if (!strcmp(name, "compact_max_pct")) ctx->opt_compact_max_pct = value < 0 ? 0 : value > 100 ? 100 : value;
     else if (!strcmp(name, "count_block_only")) ctx->opt_count_block_only = value < 0 || value > 3 ? 0 : value;
     else if (!strcmp(name, "scan_mode")) {
         if (value < 0 || value > 2) return fail(ctx, BRGPU_E_INVALID, "scan_mode must be 0 (default), 1 (warp) or 2 (groups)");
@@ -1112,7 +1120,7 @@ static void summary_geometry(int k, int *shift, uint64_t *bytes) {
 // E. coli config 32 + 37 MB).  Beyond that a positive lookup still costs one DRAM access — as it
 // does in the bitfield — but into an array 3-30x smaller, with the directory answering every
 // negative lookup from L2, so it is built as long as the blocks take less than half the bitfield.
-static uint64_t compact_max_block_bytes(const brgpu_set *s) { return s->n_bytes / 2; }
+static uint64_t compact_max_block_bytes(const brgpu_set *s) { return s->n_bytes / 100 * (uint64_t)s->ctx->opt_compact_max_pct; }
 
 static int ensure_dense(brgpu_set *s); // below: the dense bitfield of a set held in rank-compacted form only
 
@@ -1120,6 +1128,9 @@ static void compact_release(brgpu_set *s) {
     if (s->d_dir) big_free(s->ctx, s->d_dir, s->dir_bytes);
     if (s->d_blocks) big_free(s->ctx, s->d_blocks, s->blocks_bytes);
     if (s->d_pos8) big_free(s->ctx, s->d_pos8, s->pos8_bytes);
+    if (s->d_fine) big_free(s->ctx, s->d_fine, s->fine_bytes);
+    s->d_fine = nullptr;
+    s->fine_bytes = 0;
     s->d_dir = nullptr;
     s->d_blocks = nullptr;
     s->d_pos8 = nullptr;
@@ -1193,6 +1204,20 @@ static int build_compact(brgpu_set *s) {
             s->compact_valid = true;
             build_pos8(s);
         }
+    } else if (!ctx->opt_no_fine_summary && s->bits_complete && s->n_bytes >= 4096 && s->n_bytes <= (1ULL << 30) &&
+               s->n_occupied * 16 <= (s->n_bytes / 8) * 15) { // with (nearly) every block occupied it rejects too little (configs[4]: +14 %)
+        // Too dense to compact (configs[3]: 100 M solid 17-mers, 53 % of the 64-bit blocks occupied): the one-bit-per-
+        // block summary lets every second weak k-mer through to the bitfield in DRAM.  At one bit per 16 bitfield
+        // bits (64 MiB at k = 17, still L2 resident) it is every sixth: the bitmap passes over such a set are bound by
+        // the DRAM random-gather rate, so their time goes with the gathers (profiles/lookup_variants_r2.txt).
+        const uint64_t fbytes = s->n_bytes / 16;
+        if (big_alloc(ctx, (void **)&s->d_fine, fbytes) == cudaSuccess) {
+            s->fine_bytes = fbytes;
+            launch_fine_summary(ctx, s->d_bits, s->n_bytes / 8, s->d_fine);
+        } else {
+            cudaGetLastError();
+            s->d_fine = nullptr;
+        }
     }
     drop();
     e = cudaGetLastError();
@@ -1229,7 +1254,10 @@ static int ensure_summary(brgpu_set *s) {
     return build_compact(s);
 }
 
-static SetView set_view(const brgpu_set *s) {
+// for_bitmap: the view of the position-parallel bitmap passes.  Only they use the fine summary of a dense set: they
+// are bound by the DRAM gathers it saves (configs[3] shard: 14.2 -> 12.7 ms forward, 9.6 -> 6.7 ms reversed), while the
+// scans' latency chains only see a bigger first-level structure competing for L2 (+2-4 %).
+static SetView set_view(const brgpu_set *s, bool for_bitmap = false) {
     SetView v{s->d_bits, s->summary_bytes ? s->d_summary : nullptr, s->summary_shift, s->k};
     if (s->is_hash) {
         v.hash = s->d_hash;
@@ -1240,6 +1268,9 @@ static SetView set_view(const brgpu_set *s) {
         v.dir = s->d_dir;
         v.blocks = s->d_blocks;
         v.pos8 = s->d_pos8;
+    } else if ((for_bitmap || s->ctx->opt_fine_in_scans) && s->d_fine && s->summary_valid) {
+        v.summary = s->d_fine;
+        v.shift = 4;
     }
     return v;
 }
@@ -2253,7 +2284,7 @@ static int correct_attempt(brgpu_ctx *ctx, const brgpu_set *set, const uint8_t *
         for (uint64_t i = 0; i < n_methods; i++) {
             CorrectParams p{set->k, methods[i], confirm, max_search, reversed ? 1 : 0};
             // after a method of the same orientation only the reads it edited need new bitmap words
-            launch_solid_bitmap(ctx, L, src, src_len, set_view(set), d_bitmap, i > 0 ? work.d_changed : nullptr,
+            launch_solid_bitmap(ctx, L, src, src_len, set_view(set, true), d_bitmap, i > 0 ? work.d_changed : nullptr,
                                 (double)in->sum_len, reversed);
             launch_scan(ctx, L, src, src_len, buf[nxt], len[nxt], d_bitmap, set_view(set), p, d_scratch,
                         scratch_per_warp, n_warps, work, (double)in->sum_len);

@@ -59,6 +59,9 @@ struct brgpu_ctx {
     int opt_one_level_partition = 0; // the k = 19 partition path for k <= 17
     int opt_count_block_only = 0;    // the 256-thread shape of the counting kernel even for sparse buckets
     int opt_scan_mode = 0;           // 0: per method default, 1: warp per segment, 2: four segments per warp
+    int opt_compact_max_pct = 50;    // the compacted form is built while its 64-bit blocks take at most this share of the bitfield
+    int opt_fine_in_scans = 0;       // A/B: the scans, too, look dense sets up through the fine summary
+    int opt_no_fine_summary = 0;     // A/B: dense sets are looked up through the one-bit-per-64 summary
     int opt_no_pos8 = 0;             // A/B: lookups read the 64-bit blocks instead of the one-byte form
     // caching device allocator (brgpu.cu): blocks handed out (ptr -> bytes) and cached free blocks
     std::unordered_map<void *, uint64_t> pool_live;
@@ -146,6 +149,8 @@ struct brgpu_set {
     uint64_t blocks_bytes = 0;   // allocation size
     uint64_t n_occupied = 0;     // occupied 64-bit blocks
     uint8_t *d_pos8 = nullptr;   // one byte per occupied block (SolidView::pos8); nullptr: not built
+    uint32_t *d_fine = nullptr;  // dense sets: occupancy summary at one bit per 16 bitfield bits (nullptr: not built)
+    uint64_t fine_bytes = 0;
     uint64_t pos8_bytes = 0;
     bool compact_valid = false;  // d_dir/d_blocks describe the current bitfield
     // sharded construction may leave only this GPU's slice of the dense bitfield written and hold the whole set in
@@ -265,6 +270,7 @@ void launch_compact_blocks(brgpu_ctx *ctx, const uint32_t *d_summary, const uint
                            uint64_t n_words, uint64_t n_occupied, void *d_dir, uint64_t *d_blocks);
 
 void launch_dir_only(brgpu_ctx *ctx, const uint32_t *d_summary, const uint64_t *d_rank, uint64_t n_words, void *d_dir);
+void launch_fine_summary(brgpu_ctx *ctx, const uint8_t *d_bits, uint64_t n_blocks64, uint32_t *d_fine);
 void launch_block_bytes(brgpu_ctx *ctx, const uint64_t *d_blocks, uint64_t n_occupied, uint8_t *d_pos8);
 void launch_expand_blocks(brgpu_ctx *ctx, const void *d_dir, const uint64_t *d_blocks, uint64_t n_words, uint8_t *d_bits);
 

@@ -86,7 +86,7 @@ __device__ __forceinline__ bool solid(const uint8_t *__restrict__ bits, uint64_t
 struct SolidView {
     const uint8_t *bits;
     const uint32_t *summary; // nullptr: no summary (small k: the bitfield itself is cache resident)
-    int shift;               // log2(bitfield bits per summary bit), >= 5
+    int shift;               // log2(bitfield bits per summary bit): 6 or more; 4 for the fine summary of a dense set
     int k;
     // Rank-compacted copy of a sparse bitfield (nullptr: not built).  dir[g] = {occupancy of the
     // 32 64-bit blocks 32g .. 32g+31, number of occupied blocks before block 32g}; blocks[] holds

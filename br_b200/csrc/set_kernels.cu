@@ -883,6 +883,30 @@ void launch_bucket_count_multi(brgpu_ctx *ctx, const uint16_t *const *d_res, con
         src, b0, b1, abundance, reinterpret_cast<uint32_t *>(d_bits), d_summary, reinterpret_cast<unsigned long long *>(d_hist));
 }
 
+// Occupancy of a dense bitfield at 16-bit granularity: summary bit j <=> any of the bitfield bits [16 j, 16 j + 16).
+// A thread turns 8 consecutive 64-bit blocks (two 32 B sectors) into one 32-bit word.
+__global__ void __launch_bounds__(256) fine_summary_kernel(const uint4 *__restrict__ bits, uint64_t n_words, uint32_t *__restrict__ fine) {
+    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t out = 0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) { // uint4 = two 64-bit blocks = eight 16-bit granules
+            const uint4 v = __ldcs(bits + w * 4 + q);
+            const uint32_t g = (v.x & 0xffffu ? 1u : 0u) | (v.x >> 16 ? 2u : 0u) | (v.y & 0xffffu ? 4u : 0u) | (v.y >> 16 ? 8u : 0u) |
+                               (v.z & 0xffffu ? 16u : 0u) | (v.z >> 16 ? 32u : 0u) | (v.w & 0xffffu ? 64u : 0u) | (v.w >> 16 ? 128u : 0u);
+            out |= g << (8 * q);
+        }
+        fine[w] = out;
+    }
+}
+
+void launch_fine_summary(brgpu_ctx *ctx, const uint8_t *d_bits, uint64_t n_blocks64, uint32_t *d_fine) {
+    const uint64_t n_words = n_blocks64 / 8;
+    if (!n_words) return;
+    ProfScope ps(ctx, "fine_summary", (double)n_blocks64 * 8.5);
+    const uint64_t want = (n_words + 255) / 256, cap = (uint64_t)ctx->sm_count * 16;
+    fine_summary_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, ctx->stream>>>(reinterpret_cast<const uint4 *>(d_bits), n_words, d_fine);
+}
+
 // SolidView::pos8 from the compacted blocks: position of the only set bit, or POS8_MULTI
 __global__ void __launch_bounds__(256) block_bytes_kernel(const uint64_t *__restrict__ blocks, uint64_t n, uint8_t *__restrict__ pos8) {
     // a thread turns 4 consecutive blocks into one 32-bit store

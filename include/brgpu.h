@@ -70,9 +70,11 @@ void brgpu_ctx_destroy(brgpu_ctx *ctx);
 int brgpu_ctx_synchronize(brgpu_ctx *ctx);
 /* Switches for tests and A/B measurements; none changes a result.  Defaults come from the
  * environment once, at brgpu_ctx_create (BRGPU_NO_COMPACT, BRGPU_ONE_LEVEL_PARTITION,
- * BRGPU_COUNT_BLOCK_ONLY, BRGPU_NO_POS8, BRGPU_SCAN=warp|groups).  name: "no_compact" (0/1: solidity lookups through summary + bitfield
+ * BRGPU_COUNT_BLOCK_ONLY, BRGPU_NO_POS8, BRGPU_COMPACT_MAX_PCT, BRGPU_NO_FINE_SUMMARY, BRGPU_SCAN=warp|groups).  name: "no_compact" (0/1: solidity lookups through summary + bitfield
  * even for sparse sets), "one_level_partition" (0/1: the k = 19 partition path for k <= 17),
  * "no_pos8" (0/1: lookups of a rank-compacted set read its 64-bit blocks instead of the one-byte-per-block form),
+ * "compact_max_pct" (0..100, default 50: a set is held rank-compacted while its occupied 64-bit blocks take at most this
+ * share of the bitfield's bytes), "no_fine_summary" (0/1: denser sets without the one-bit-per-16 occupancy summary),
  * "count_block_only" (threads per bucket of the counting kernel: 0 or 1 = 256, the default; 2 = 128; 3 = 64),
  * "scan_mode" (0 per-method default, 1 warp per segment, 2 four segments per warp, for One/Two). */
 int brgpu_ctx_set_option(brgpu_ctx *ctx, const char *name, int value);

@@ -302,23 +302,26 @@ def test_large_k_sets_correct_like_the_oracle_on_every_lookup_path(gpu, oracle, 
     exp, exp_off = osolid.run_correction(ids, seq, off, confirm=4, max_search=7, threads=8)
     changed = int((np.diff(exp_off.astype(np.int64)) != np.diff(off.astype(np.int64))).sum())
     assert changed > 10  # the chain really edits reads
-    request.addfinalizer(lambda: (ctx.set_option("no_compact", 0), ctx.set_option("no_pos8", 0)))
-    # compacted with the one-byte form of the blocks (default) / compacted, 64-bit blocks only / summary + bitfield
-    for no_compact, no_pos8 in (("0", 0), ("0", 1), ("1", 0)):
+    request.addfinalizer(lambda: (ctx.set_option("no_compact", 0), ctx.set_option("no_pos8", 0), ctx.set_option("compact_max_pct", 50)))
+    # compacted with the one-byte form of the blocks (default) / compacted, 64-bit blocks only / summary + bitfield /
+    # treated as too dense to compact: fine (one bit per 16) summary + bitfield
+    for no_compact, no_pos8, max_pct in (("0", 0, 50), ("0", 1, 50), ("1", 0, 50), ("0", 0, 0)):
         ctx.set_option("no_compact", int(no_compact))
         ctx.set_option("no_pos8", no_pos8)
+        ctx.set_option("compact_max_pct", max_pct)
         counted = br.Pcon.from_reads(ctx, (seq, off), k, abundance=2)
         assert np.array_equal(counted.bitfield(), osolid.bits())
         loaded = br.Pcon.from_bitfield(ctx, k, osolid.bits())
         for name, s in (("counted", counted), ("loaded", loaded)):
             got, got_off = br.correct_batch(br.build_methods(METHODS, s, 4, 7), seq, off)
-            compare_batches(f"k={k} {name} no_compact={no_compact} no_pos8={no_pos8}", got, got_off, exp, exp_off, seq, off)
+            compare_batches(f"k={k} {name} no_compact={no_compact} no_pos8={no_pos8} compact_max_pct={max_pct}", got, got_off, exp, exp_off, seq, off)
         counted.free()
         loaded.free()
     # a denser set (17 % of the 64-bit blocks occupied): the rank-compacted copy is built by the
     # streaming kernel instead of the sparse one
     ctx.set_option("no_compact", 0)
     ctx.set_option("no_pos8", 0)
+    ctx.set_option("compact_max_pct", 50)
     rng = np.random.default_rng(k)
     dense_bits = osolid.bits().copy()
     pos = rng.integers(0, dense_bits.size * 8, size=int(dense_bits.size * 8 * 0.003), dtype=np.int64)
@@ -326,10 +329,12 @@ def test_large_k_sets_correct_like_the_oracle_on_every_lookup_path(gpu, oracle, 
     dsolid = oracle.Solid.from_bitfield(k, dense_bits)
     sub = off[:41]
     exp, exp_off = dsolid.run_correction(ids, seq, sub, confirm=4, max_search=7, threads=8)
-    dense = br.Pcon.from_bitfield(ctx, k, dense_bits)
-    got, got_off = br.correct_batch(br.build_methods(METHODS, dense, 4, 7), seq, sub)
-    compare_batches(f"k={k} dense set", got, got_off, exp, exp_off, seq, sub)
-    dense.free()
+    for max_pct in (50, 10):  # 10: the same set counts as too dense to compact (fine summary + bitfield)
+        ctx.set_option("compact_max_pct", max_pct)
+        dense = br.Pcon.from_bitfield(ctx, k, dense_bits)
+        got, got_off = br.correct_batch(br.build_methods(METHODS, dense, 4, 7), seq, sub)
+        compare_batches(f"k={k} dense set compact_max_pct={max_pct}", got, got_off, exp, exp_off, seq, sub)
+        dense.free()
 
 
 @pytest.mark.parametrize("mode", ["warp", "groups"])
