@@ -281,6 +281,7 @@ extern "C" int brgpu_ctx_create(int device, void *cuda_stream, brgpu_ctx **out) 
     ctx->opt_no_pos8 = env_on("BRGPU_NO_POS8") ? 1 : 0;
     ctx->opt_no_fine_summary = env_on("BRGPU_NO_FINE_SUMMARY") ? 1 : 0;
     ctx->opt_fine_in_scans = env_on("BRGPU_FINE_IN_SCANS") ? 1 : 0;
+    ctx->opt_keep_summary = env_on("BRGPU_KEEP_SUMMARY") ? 1 : 0;
     if (const char *v = getenv("BRGPU_COMPACT_MAX_PCT")) {
         const int pct = atoi(v);
         ctx->opt_compact_max_pct = pct < 0 ? 0 : pct > 100 ? 100 : pct;
@@ -1271,6 +1272,8 @@ static SetView set_view(const brgpu_set *s, bool for_bitmap = false) {
     } else if ((for_bitmap || s->ctx->opt_fine_in_scans) && s->d_fine && s->summary_valid) {
         v.summary = s->d_fine;
         v.shift = 4;
+    } else if (s->summary_valid && s->summary_shift == 6 && s->n_occupied * 16 > (s->n_bytes / 8) * 15 && !s->ctx->opt_keep_summary) {
+        v.summary = nullptr; // saturated (configs[4]: every block occupied): the summary is a load that rejects nothing
     }
     return v;
 }

@@ -60,6 +60,7 @@ struct brgpu_ctx {
     int opt_count_block_only = 0;    // the 256-thread shape of the counting kernel even for sparse buckets
     int opt_scan_mode = 0;           // 0: per method default, 1: warp per segment, 2: four segments per warp
     int opt_compact_max_pct = 50;    // the compacted form is built while its 64-bit blocks take at most this share of the bitfield
+    int opt_keep_summary = 0;        // A/B: saturated sets are still looked up through the summary
     int opt_fine_in_scans = 0;       // A/B: the scans, too, look dense sets up through the fine summary
     int opt_no_fine_summary = 0;     // A/B: dense sets are looked up through the one-bit-per-64 summary
     int opt_no_pos8 = 0;             // A/B: lookups read the 64-bit blocks instead of the one-byte form

@@ -1109,8 +1109,7 @@ __device__ __forceinline__ void specialise_view(SolidView &set, int arm) {
         set.hash = nullptr;
         set.dir = nullptr;
         set.blocks = nullptr;
-        set.pos8 = nullptr;
-        __builtin_assume(set.summary != nullptr);
+        set.pos8 = nullptr; // the summary stays a run-time choice: a saturated set (configs[4]) is looked up without it
     }
 }
 template <int METHOD, int KT, int ARM>
@@ -2009,7 +2008,7 @@ template <int M, int KT> static void launch_scan_method(const ScanArgs &a) {
 #ifdef BRGPU_NO_ARM_DENSE // A/B builds: dense sets through the run-time dispatching kernel
         const int arm = special && a.sv.dir != nullptr ? ARM_COMPACT : ARM_ANY;
 #else
-        const int arm = !special ? ARM_ANY : a.sv.dir != nullptr ? ARM_COMPACT : a.sv.summary != nullptr ? ARM_DENSE : ARM_ANY;
+        const int arm = !special ? ARM_ANY : a.sv.dir != nullptr ? ARM_COMPACT : ARM_DENSE;
 #endif
         if ((M == BRGPU_ONE && !force_warp) || (M == BRGPU_TWO && force_groups)) {
             // four segments per warp: a quarter of the warps for the same number of segments in flight

@@ -335,6 +335,18 @@ def test_large_k_sets_correct_like_the_oracle_on_every_lookup_path(gpu, oracle, 
         got, got_off = br.correct_batch(br.build_methods(METHODS, dense, 4, 7), seq, sub)
         compare_batches(f"k={k} dense set compact_max_pct={max_pct}", got, got_off, exp, exp_off, seq, sub)
         dense.free()
+    # a saturated set (every 64-bit block occupied, one k-mer in eight solid — configs[4]'s regime): looked up in
+    # the bitfield directly, the summary would reject nothing
+    ctx.set_option("compact_max_pct", 50)
+    sat_bits = osolid.bits() | (rng.integers(0, 256, dense_bits.size, dtype=np.uint8) & rng.integers(0, 256, dense_bits.size, dtype=np.uint8)
+                                & rng.integers(0, 256, dense_bits.size, dtype=np.uint8))
+    ssolid = oracle.Solid.from_bitfield(k, sat_bits)
+    sub = off[:21]
+    exp, exp_off = ssolid.run_correction(ids, seq, sub, confirm=4, max_search=7, threads=8)
+    sat = br.Pcon.from_bitfield(ctx, k, sat_bits)
+    got, got_off = br.correct_batch(br.build_methods(METHODS, sat, 4, 7), seq, sub)
+    compare_batches(f"k={k} saturated set", got, got_off, exp, exp_off, seq, sub)
+    sat.free()
 
 
 @pytest.mark.parametrize("mode", ["warp", "groups"])
