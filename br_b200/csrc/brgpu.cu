@@ -2163,6 +2163,7 @@ extern "C" void *brgpu_set_summary_ptr(brgpu_set *s, uint64_t *n_bytes) {
 
 extern "C" int brgpu_set_commit_slices(brgpu_set *s, int summary_complete) {
     if (!s || s->is_hash) return BRGPU_E_INVALID;
+    cudaSetDevice(s->ctx->device);
     compact_release(s);
     s->summary_valid = summary_complete != 0 && s->d_summary != nullptr;
     if (s->summary_valid) return build_compact(s);
