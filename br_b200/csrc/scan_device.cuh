@@ -1980,9 +1980,13 @@ template <class K> static int occupancy_warps(brgpu_ctx *ctx, K kernel) {
 }
 
 // One pass of method M over all reads: speculative per-segment scan, per-read merge, parallel splice.
-// the specialised kernels are only instantiated where they are launched (One / Two at k = 17)
+// the specialised kernels are only instantiated where they are launched (k = 17, the k of every BASELINE config)
 template <int M, int KT> constexpr int special_arm(int arm) {
+#ifdef BRGPU_SPECIAL_ONE_TWO_ONLY // A/B builds: Graph / Greedy / GapSize through the run-time dispatching kernel
     return (KT == 17 && (M == BRGPU_ONE || M == BRGPU_TWO)) ? arm : ARM_ANY;
+#else
+    return KT == 17 ? arm : ARM_ANY;
+#endif
 }
 
 template <int M, int KT> static void launch_scan_method(const ScanArgs &a) {
@@ -2003,8 +2007,8 @@ template <int M, int KT> static void launch_scan_method(const ScanArgs &a) {
         // the same scheme measured slower than a warp per segment (its rounds are already lane-filling:
         // 2.37 vs 1.72 ms), so it is off unless asked for (ctx option "scan_mode": A/B runs, tests).
         const bool force_warp = ctx->opt_scan_mode == 1, force_groups = ctx->opt_scan_mode == 2;
-        // the specialised kernels exist for the methods and the k of the headline configs; others share the general one
-        const bool special = a.sv.hash == nullptr && KT == 17 && (M == BRGPU_ONE || M == BRGPU_TWO);
+        // the specialised kernels exist for the k of the BASELINE configs; other k share the general one
+        const bool special = a.sv.hash == nullptr && special_arm<M, KT>(ARM_COMPACT) == ARM_COMPACT;
 #ifdef BRGPU_NO_ARM_DENSE // A/B builds: dense sets through the run-time dispatching kernel
         const int arm = special && a.sv.dir != nullptr ? ARM_COMPACT : ARM_ANY;
 #else
