@@ -37,13 +37,23 @@ namespace brgpu {
 // ------------------------------------------------------------------------------------------
 // KT: compile-time k (0 = take it from the set).  k = 17 is the size every BASELINE config uses;
 // with a constant k the 64-bit shifts and masks of the k-mer arithmetic become immediates.
-template <int KT>
+// ARM: 0 = the form of the set is a run-time matter, 1 = rank-compacted, 2 = summary + bitfield (the other arms of
+// the lookup are compiled out, as in the scan kernels)
+template <int KT, int ARM>
 __global__ void __launch_bounds__(256)
     solid_bitmap_kernel(const uint8_t *__restrict__ seq, const uint32_t *__restrict__ len,
                         const uint64_t *__restrict__ slot_off, const uint32_t *__restrict__ word2read,
                         uint64_t n_words, SolidView set, uint32_t *__restrict__ bitmap,
                         const uint8_t *__restrict__ changed, unsigned long long *get_counter) {
     const int k = KT ? KT : set.k;
+    if (ARM == 1) {
+        set.hash = nullptr;
+        set.summary = nullptr;
+        __builtin_assume(set.dir != nullptr);
+    } else if (ARM == 2) {
+        set.hash = nullptr;
+        set.dir = nullptr;
+    }
     const uint8_t *__restrict__ bits = set.bits;
     const uint64_t mask = kmask(k);
     uint32_t n_looked = 0; // k-mers this thread looked up (reported by profiling runs only)
@@ -145,10 +155,13 @@ void launch_solid_bitmap(brgpu_ctx *ctx, const Layout &L, const uint8_t *d_seq, 
     const SolidView sv = solid_view(set);
     const unsigned grid = (unsigned)(need < capb ? need : capb);
     unsigned long long *gc = ctx->profiling ? prof_counter_slot(ctx) : nullptr;
-    if (set.k == 17)
-        solid_bitmap_kernel<17><<<grid, 256, 0, ctx->stream>>>(d_seq, d_len, L.d_slot_off, L.d_word2read, n_words, sv, d_bitmap, d_changed, gc);
-    else
-        solid_bitmap_kernel<0><<<grid, 256, 0, ctx->stream>>>(d_seq, d_len, L.d_slot_off, L.d_word2read, n_words, sv, d_bitmap, d_changed, gc);
+    auto go = [&](auto kernel) {
+        kernel<<<grid, 256, 0, ctx->stream>>>(d_seq, d_len, L.d_slot_off, L.d_word2read, n_words, sv, d_bitmap, d_changed, gc);
+    };
+    if (set.k != 17) go(solid_bitmap_kernel<0, 0>);
+    else if (sv.hash) go(solid_bitmap_kernel<17, 0>);
+    else if (sv.dir) go(solid_bitmap_kernel<17, 1>);
+    else go(solid_bitmap_kernel<17, 2>);
 }
 
 // per-warp scratch of the scan kernels (Greedy's alignment; layout in scan_device.cuh: greedy_scratch)

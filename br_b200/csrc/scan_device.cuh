@@ -1183,7 +1183,7 @@ __global__ void __launch_bounds__(SCAN_WARPS_PER_BLOCK * 32, (METHOD == BRGPU_ON
 #endif
 }
 
-template <int METHOD, int KT>
+template <int METHOD, int KT, int ARM>
 __global__ void __launch_bounds__(SCAN_WARPS_PER_BLOCK * 32)
     scan_merge_kernel(const uint8_t *__restrict__ in, const uint32_t *__restrict__ len_in, uint8_t *__restrict__ out,
                       uint32_t *__restrict__ len_out, const uint64_t *__restrict__ slot_off,
@@ -1196,6 +1196,7 @@ __global__ void __launch_bounds__(SCAN_WARPS_PER_BLOCK * 32)
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (KT) p.k = KT; // compile-time k: the k-mer arithmetic below folds to immediates
     const uint32_t k = (uint32_t)p.k;
+    specialise_view(set, ARM);
     Rd rd;
     rd.set = set;
     rd.set.k = p.k;
@@ -2043,11 +2044,18 @@ template <int M, int KT> static void launch_scan_method(const ScanArgs &a) {
     {
         ProfScope ps(ctx, a.merge_name, a.n_bases_hint * 2.0);
         unsigned long long *gc = prof_counter_slot(ctx);
-        scan_merge_kernel<M, KT><<<grid_for_warps((uint64_t)occupancy_warps(ctx, scan_merge_kernel<M, KT>), L.n), threads, 0,
-                               ctx->stream>>>(a.d_in, a.d_len_in, a.d_out, a.d_len_out, L.d_slot_off, a.d_bitmap, L.d_order,
-                                              w.d_seg_first, (uint32_t)L.n, w.d_seg_out, (const SegRec *)w.d_seg_recs,
-                                              ctx->d_flags, a.sv, a.p, a.d_scratch, a.scratch_per_warp, w.d_changed, d_copies,
-                                              gc);
+        const bool special = a.sv.hash == nullptr && special_arm<M, KT>(ARM_COMPACT) == ARM_COMPACT;
+        const int arm = !special ? ARM_ANY : a.sv.dir != nullptr ? ARM_COMPACT : ARM_DENSE;
+        const unsigned grid = grid_for_warps((uint64_t)occupancy_warps(ctx, scan_merge_kernel<M, KT, ARM_ANY>), L.n);
+        auto go = [&](auto kernel) {
+            kernel<<<grid, threads, 0, ctx->stream>>>(a.d_in, a.d_len_in, a.d_out, a.d_len_out, L.d_slot_off, a.d_bitmap, L.d_order,
+                                                      w.d_seg_first, (uint32_t)L.n, w.d_seg_out, (const SegRec *)w.d_seg_recs,
+                                                      ctx->d_flags, a.sv, a.p, a.d_scratch, a.scratch_per_warp, w.d_changed, d_copies,
+                                                      gc);
+        };
+        if (arm == ARM_COMPACT) go(scan_merge_kernel<M, KT, special_arm<M, KT>(ARM_COMPACT)>);
+        else if (arm == ARM_DENSE) go(scan_merge_kernel<M, KT, special_arm<M, KT>(ARM_DENSE)>);
+        else go(scan_merge_kernel<M, KT, ARM_ANY>);
         // all spliced pieces at once (the merge warps only decided where they go)
         launch_scan_splice(ctx, d_copies, scan_max_segments(L), w.d_seg_out, a.d_out);
     }
