@@ -8,6 +8,8 @@
 //   writer: `>` + definition + `\n`, then the sequence wrapped at 80 columns (noodles' default).
 // Parity tests compare sequences per record, not file bytes ("FASTA framing").
 #pragma once
+#include <sys/mman.h>
+#include <sys/stat.h>
 #include <zlib.h>
 
 #include <cstdint>
@@ -122,7 +124,31 @@ struct Packed {
 inline void pack_range(const uint8_t *seq, uint64_t begin, uint64_t end, uint8_t *packed, std::vector<uint64_t> &exc_pos,
                        std::vector<uint8_t> &exc_byte) {
     static const uint8_t LETTER[4] = {'A', 'C', 'T', 'G'};
-    for (uint64_t t = begin; t < end; t += 4) { // begin is a multiple of 4
+    uint64_t t = begin; // a multiple of 4
+    // eight bases per step on 64-bit words (little endian: byte j of the word is base t + j).  codes = (byte >> 1) & 3
+    // in every byte; the letter a code stands for is 'A' + 2 b0 + 19 b1 - 15 (b0 & b1) (A C T G = 0x41 0x43 0x54 0x47),
+    // so "every byte is the upper-case letter of its code" is one XOR; four codes are gathered into one output byte by
+    // a multiplication whose partial products do not overlap (c0 << 30 | c1 << 28 | c2 << 26 | c3 << 24 after it).
+    constexpr uint64_t ONES = 0x0101010101010101ULL, GATHER = (1ULL << 30) | (1ULL << 20) | (1ULL << 10) | 1ULL;
+    for (; t + 8 <= end; t += 8) {
+        uint64_t w;
+        std::memcpy(&w, seq + t, 8);
+        const uint64_t x = (w >> 1) & (3 * ONES);
+        const uint64_t b0 = x & ONES, b1 = (x >> 1) & ONES;
+        const uint64_t expect = 0x41 * ONES + 2 * b0 + 19 * b1 - 15 * (b0 & b1);
+        if (w != expect) {
+            for (int j = 0; j < 8; j++) {
+                const uint8_t c = seq[t + j];
+                if (c != LETTER[(c >> 1) & 3u]) {
+                    exc_pos.push_back(t + j);
+                    exc_byte.push_back(c);
+                }
+            }
+        }
+        packed[t >> 2] = (uint8_t)((((x & 0xffffffffULL) * GATHER) >> 24) & 0xffu);
+        packed[(t >> 2) + 1] = (uint8_t)((((x >> 32) * GATHER) >> 24) & 0xffu);
+    }
+    for (; t < end; t += 4) {
         uint32_t out = 0;
         const uint64_t m = end - t < 4 ? end - t : 4;
         for (uint64_t j = 0; j < m; j++) {
@@ -165,15 +191,26 @@ inline void pack(const uint8_t *seq, uint64_t n, Packed &out, unsigned threads =
 // inverse: n bases of ASCII, exceptions written back (any order)
 inline void unpack(const uint8_t *packed, uint64_t n, const uint64_t *exc_pos, const uint8_t *exc_byte, uint64_t n_exc,
                    uint8_t *seq_out, unsigned threads = 4) {
+    static const uint8_t LETTER[4] = {'A', 'C', 'T', 'G'};
+    struct Lut { // the four letters of every packed byte, in memory order
+        uint8_t v[256][4];
+        Lut() {
+            for (int b = 0; b < 256; b++)
+                for (int j = 0; j < 4; j++) v[b][j] = LETTER[(b >> (2 * (3 - j))) & 3];
+        }
+    };
+    static const Lut lut;
     auto range = [&](uint64_t b, uint64_t e) {
-        static const uint8_t LETTER[4] = {'A', 'C', 'T', 'G'};
-        for (uint64_t t = b; t < e; t++) seq_out[t] = LETTER[(packed[t >> 2] >> (2 * (3 - (t & 3)))) & 3u];
+        uint64_t t = b;
+        for (; t < e && (t & 3); t++) seq_out[t] = LETTER[(packed[t >> 2] >> (2 * (3 - (t & 3)))) & 3u];
+        for (; t + 4 <= e; t += 4) std::memcpy(seq_out + t, lut.v[packed[t >> 2]], 4);
+        for (; t < e; t++) seq_out[t] = LETTER[(packed[t >> 2] >> (2 * (3 - (t & 3)))) & 3u];
     };
     if (threads < 2 || n < (1u << 20)) {
         range(0, n);
     } else {
         std::vector<std::thread> pool;
-        const uint64_t per = n / threads + 1;
+        const uint64_t per = (n / threads + 4) & ~3ULL;
         for (unsigned w = 0; w < threads; w++) pool.emplace_back(range, std::min<uint64_t>(n, per * w), std::min<uint64_t>(n, per * (w + 1)));
         for (auto &t : pool) t.join();
     }
@@ -197,6 +234,17 @@ class Reader {
             if (!(got == 2 && magic[0] == 0x1f && magic[1] == 0x8b)) {
                 rewind(f);
                 plain_ = f;
+                // a regular file is mapped: the parser threads read the page cache directly (no read() copy, no
+                // buffer compaction); pipes and special files keep the block reads
+                struct stat st;
+                if (fstat(fileno(f), &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0) {
+                    void *m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fileno(f), 0);
+                    if (m != MAP_FAILED) {
+                        map_ = static_cast<const char *>(m);
+                        map_len_ = (size_t)st.st_size;
+                        madvise(m, map_len_, MADV_SEQUENTIAL);
+                    }
+                }
                 return;
             }
             fclose(f);
@@ -209,6 +257,7 @@ class Reader {
     Reader(const Reader &) = delete;
     Reader &operator=(const Reader &) = delete;
     ~Reader() {
+        if (map_) munmap(const_cast<char *>(map_), map_len_);
         if (gz_) gzclose(gz_);
         if (plain_) fclose(plain_);
     }
@@ -218,6 +267,7 @@ class Reader {
     // Appends up to max_records records to `out`; returns false once the stream is exhausted
     // (the last call may still have appended records, like populate_buffer's `false`).
     bool read_chunk(Chunk &out, size_t max_records) {
+        if (map_) return read_chunk_mapped(out, max_records);
         if (plain_) return read_chunk_parallel(out, max_records);
         size_t got = 0;
         while (got < max_records) {
@@ -266,7 +316,10 @@ class Reader {
         bool line_start = true;
         size_t line_len = 0; // bytes of the current line already appended (a line may span two buffer fills)
         for (;;) {
-            if (pos_ == end_ && !fill()) return;
+            if (pos_ == end_ && !fill()) { // end of the stream inside a line: a lone '\r' is still a line end
+                if (line_len && dst.back() == '\r') dst.pop_back();
+                return;
+            }
             const char *p = buf_.data() + pos_;
             if (line_start && *p == '>') return;
             const char *nl = (const char *)memchr(p, '\n', end_ - pos_);
@@ -378,9 +431,39 @@ class Reader {
         }
         starts.resize(n_rec);
         starts.push_back(stop);
+        parse_parallel(raw_.data(), starts, n_rec, out);
+        rpos_ = stop;
+        return more;
+    }
+    // Mapped file: record starts are the '>' that begin a line.  '>' is rare (definition lines only), so one memchr
+    // per record finds them at memory speed — the line-by-line scan of the block reader costs as much as parsing.
+    bool read_chunk_mapped(Chunk &out, size_t max_records) {
+        std::vector<size_t> starts;
+        size_t scan = mpos_;
+        while (scan < map_len_ && starts.size() <= max_records) {
+            const char *gt = (const char *)memchr(map_ + scan, '>', map_len_ - scan);
+            if (!gt) break;
+            const size_t at = (size_t)(gt - map_);
+            if (at == 0 || map_[at - 1] == '\n') starts.push_back(at);
+            scan = at + 1;
+        }
+        const bool more = starts.size() > max_records;
+        const size_t n_rec = more ? max_records : starts.size();
+        const size_t stop = more ? starts[max_records] : map_len_;
+        if (n_rec) {
+            starts.resize(n_rec);
+            starts.push_back(stop);
+            parse_parallel(map_, starts, n_rec, out);
+        }
+        mpos_ = stop;
+        return more;
+    }
+    // records [0, n_rec) of `starts` (starts[n_rec] = end of the last one) -> out, parsed by up to threads_ threads
+    void parse_parallel(const char *base, const std::vector<size_t> &starts, size_t n_rec, Chunk &out) {
+        const size_t stop = starts[n_rec];
         const unsigned T = (stop - starts[0]) > (1u << 22) ? threads_ : 1;
         if (T < 2) {
-            parse_records(raw_.data(), starts, 0, n_rec, out);
+            parse_records(base, starts, 0, n_rec, out);
         } else {
             std::vector<Chunk> parts(T);
             std::vector<std::thread> pool;
@@ -390,7 +473,7 @@ class Reader {
                 size_t hi = lo;
                 const size_t want = starts[0] + bytes / T * (t + 1);
                 while (hi < n_rec && (t + 1 == T || starts[hi + 1] <= want)) hi++;
-                pool.emplace_back(parse_records, raw_.data(), std::cref(starts), lo, hi, std::ref(parts[t]));
+                pool.emplace_back(parse_records, base, std::cref(starts), lo, hi, std::ref(parts[t]));
                 lo = hi;
             }
             for (auto &th : pool) th.join();
@@ -410,8 +493,6 @@ class Reader {
             }
             for (auto &th : pool) th.join();
         }
-        rpos_ = stop;
-        return more;
     }
 
     gzFile gz_ = nullptr;
@@ -422,6 +503,8 @@ class Reader {
     std::vector<char> raw_;
     size_t rpos_ = 0, rend_ = 0;
     bool reof_ = false;
+    const char *map_ = nullptr; // regular plain file: the whole file, mapped
+    size_t map_len_ = 0, mpos_ = 0;
     unsigned threads_ = default_threads();
 };
 
