@@ -592,20 +592,57 @@ struct Corrected {
 
 enum class Transport { Ascii, Packed };
 
-inline void correct_chunk(const Methods &methods, bool two_side, const fasta::Chunk &in, Corrected &out,
-                          Transport transport = Transport::Packed) {
-    const size_t n = in.size();
+// a corrected chunk still in its 2-bit transport form (what comes back over PCIe)
+struct CorrectedPacked {
+    fasta::Bytes bases;
+    std::vector<uint64_t> offsets, exc_pos;
+    std::vector<uint8_t> exc_byte;
+    uint64_t n_bases = 0, n_exc = 0;
+};
+
+// device leg of the packed transport: upload the packed chunk, correct, download packed
+inline void correct_packed(const set::DeviceSet &solid, const std::vector<uint8_t> &ids, int confirm, int max_search, bool two_side,
+                           const fasta::Chunk &in, const fasta::Packed &pk, CorrectedPacked &out) {
+    const Context &ctx = solid.context();
+    const size_t n = in.size(), total = in.seq.size();
     out.offsets.assign(n + 1, 0);
-    if (methods.empty()) { // fold over no method: records pass through
-        out.seq = in.seq;
-        out.offsets = in.offsets;
-        return;
+    brgpu_reads *r = nullptr, *c = nullptr;
+    ctx.check(brgpu_reads_upload_packed(ctx.handle(), pk.bases.data(), in.offsets.data(), n, pk.exc_pos.data(), pk.exc_byte.data(),
+                                        pk.exc_pos.size(), &r));
+    int st = brgpu_correct_reads(ctx.handle(), solid.handle(), ids.data(), ids.size(), confirm, max_search, two_side ? 1 : 0, r, &c);
+    brgpu_reads_free(r);
+    ctx.check(st);
+    out.bases.resize((total + total / 8 + 64 * n + 64) / 4 + 8);
+    out.exc_pos.resize(pk.exc_pos.size() + 1);
+    out.exc_byte.resize(pk.exc_pos.size() + 1);
+    uint64_t counts[2] = {0, 0};
+    for (;;) {
+        st = brgpu_reads_download_packed(c, out.bases.data(), out.bases.size(), out.offsets.data(), out.exc_pos.data(),
+                                         out.exc_byte.data(), pk.exc_pos.size(), counts);
+        if (st == BRGPU_E_OVERFLOW && (counts[0] + 3) / 4 > out.bases.size()) {
+            out.bases.resize((counts[0] + 3) / 4 + 8);
+            continue;
+        }
+        break;
     }
+    brgpu_reads_free(c);
+    ctx.check(st);
+    out.n_bases = counts[0];
+    out.n_exc = counts[1];
+}
+
+inline void unpack_corrected(const CorrectedPacked &cp, fasta::Bytes &seq) {
+    seq.resize(cp.n_bases);
+    fasta::unpack(cp.bases.data(), cp.n_bases, cp.exc_pos.data(), cp.exc_byte.data(), cp.n_exc, seq.data());
+}
+
+// the (confirm, max_search) pair and the method ids of a chain, as the C ABI takes them
+inline const set::DeviceSet &chain_parameters(const Methods &methods, std::vector<uint8_t> &ids, int &confirm, int &max_search) {
     const set::DeviceSet &solid = methods[0]->valid_kmer();
-    std::vector<uint8_t> ids;
     // the C ABI takes one (confirm, max_search) pair for the chain, as br's command line does (build_methods
     // passes one -C and one -M, src/lib.rs:141-164); a hand-built chain that disagrees is refused
-    int confirm = -1, max_search = -1;
+    confirm = -1, max_search = -1;
+    ids.clear();
     for (auto &m : methods) {
         ids.push_back((uint8_t)m->method());
         if (&m->valid_kmer() != &solid) throw std::invalid_argument("all methods of a chain must share the set");
@@ -620,38 +657,31 @@ inline void correct_chunk(const Methods &methods, bool two_side, const fasta::Ch
     }
     if (confirm < 0) confirm = 5;
     if (max_search < 0) max_search = 7;
+    return solid;
+}
+
+inline void correct_chunk(const Methods &methods, bool two_side, const fasta::Chunk &in, Corrected &out,
+                          Transport transport = Transport::Packed) {
+    const size_t n = in.size();
+    out.offsets.assign(n + 1, 0);
+    if (methods.empty()) { // fold over no method: records pass through
+        out.seq = in.seq;
+        out.offsets = in.offsets;
+        return;
+    }
+    std::vector<uint8_t> ids;
+    int confirm, max_search;
+    const set::DeviceSet &solid = chain_parameters(methods, ids, confirm, max_search);
     const size_t total = in.seq.size();
     if (transport == Transport::Packed) {
         // 2-bit transport: the chunk crosses PCIe at 2 bits per base (+ the exception list) in both
         // directions; device-resident handles in between
-        const Context &ctx = solid.context();
         fasta::Packed pk;
         fasta::pack(in.seq.data(), total, pk);
-        brgpu_reads *r = nullptr, *c = nullptr;
-        ctx.check(brgpu_reads_upload_packed(ctx.handle(), pk.bases.data(), in.offsets.data(), n, pk.exc_pos.data(),
-                                            pk.exc_byte.data(), pk.exc_pos.size(), &r));
-        int st = brgpu_correct_reads(ctx.handle(), solid.handle(), ids.data(), ids.size(), confirm, max_search,
-                                     two_side ? 1 : 0, r, &c);
-        brgpu_reads_free(r);
-        ctx.check(st);
-        fasta::Bytes packed_out;
-        packed_out.resize((total + total / 8 + 64 * n + 64) / 4 + 8);
-        std::vector<uint64_t> ep(pk.exc_pos.size() + 1);
-        std::vector<uint8_t> eb(pk.exc_pos.size() + 1);
-        uint64_t counts[2] = {0, 0};
-        for (;;) {
-            st = brgpu_reads_download_packed(c, packed_out.data(), packed_out.size(), out.offsets.data(), ep.data(),
-                                             eb.data(), pk.exc_pos.size(), counts);
-            if (st == BRGPU_E_OVERFLOW && (counts[0] + 3) / 4 > packed_out.size()) {
-                packed_out.resize((counts[0] + 3) / 4 + 8);
-                continue;
-            }
-            break;
-        }
-        brgpu_reads_free(c);
-        ctx.check(st);
-        out.seq.resize(counts[0]);
-        fasta::unpack(packed_out.data(), counts[0], ep.data(), eb.data(), counts[1], out.seq.data());
+        CorrectedPacked cp;
+        correct_packed(solid, ids, confirm, max_search, two_side, in, pk, cp);
+        out.offsets.swap(cp.offsets);
+        unpack_corrected(cp, out.seq);
         return;
     }
     out.seq.resize(total + total / 8 + 64 * n + 64);
@@ -681,30 +711,48 @@ inline void run_correction(const std::vector<std::string> &inputs, const std::ve
                            Transport transport = Transport::Packed) {
     (void)record_buffer_len;
     const size_t pairs = inputs.size() < outputs.size() ? inputs.size() : outputs.size(); // zip (src/lib.rs:79)
+    const bool packed = transport == Transport::Packed && !methods.empty();
+    std::vector<uint8_t> ids;
+    int confirm = 5, max_search = 7;
+    const set::DeviceSet *solid = methods.empty() ? nullptr : &chain_parameters(methods, ids, confirm, max_search);
     for (size_t p = 0; p < pairs; p++) {
         fasta::Reader reader(inputs[p]);
         fasta::Writer writer(outputs[p]);
+        // Three stages, two buffers each.  Reader thread: parse chunk c+1 and (2-bit transport) pack it.  This thread:
+        // upload, correct, download chunk c — nothing but the library calls, so the GPU is not left waiting for host
+        // passes over the bases.  Writer thread: unpack and format chunk c-1, in input order.
         fasta::Chunk chunks[2];
+        fasta::Packed packs[2];
+        CorrectedPacked cps[2];
         Corrected results[2];
         std::vector<std::string> written_defs[2];
-        auto read_into = [&reader](fasta::Chunk *c) {
+        auto read_into = [&reader, packed](fasta::Chunk *c, fasta::Packed *pk) {
             c->clear();
-            return reader.read_chunk(*c, CHUNK_RECORDS);
+            const bool more = reader.read_chunk(*c, CHUNK_RECORDS);
+            if (packed && c->size()) fasta::pack(c->seq.data(), c->seq.size(), *pk);
+            return more;
         };
-        std::future<bool> next = std::async(std::launch::async, read_into, &chunks[0]);
-        std::shared_future<void> writes[2]; // writes[b]: the write that still reads results[b]
+        std::future<bool> next = std::async(std::launch::async, read_into, &chunks[0], &packs[0]);
+        std::shared_future<void> writes[2]; // writes[b]: the write that still reads results[b] / cps[b]
         for (int cur = 0;; cur ^= 1) {
             const bool more = next.get();
             fasta::Chunk &c = chunks[cur];
-            if (more) next = std::async(std::launch::async, read_into, &chunks[cur ^ 1]);
+            // chunks[cur ^ 1] and packs[cur ^ 1] went through the (synchronous) device calls one turn ago: both are free
+            if (more) next = std::async(std::launch::async, read_into, &chunks[cur ^ 1], &packs[cur ^ 1]);
             if (c.size()) {
-                if (writes[cur].valid()) writes[cur].wait(); // results[cur] is free again
-                correct_chunk(methods, two_side, c, results[cur], transport);
+                if (writes[cur].valid()) writes[cur].wait(); // results[cur] / cps[cur] are free again
+                if (packed) correct_packed(*solid, ids, confirm, max_search, two_side, c, packs[cur], cps[cur]);
+                else correct_chunk(methods, two_side, c, results[cur], transport);
                 written_defs[cur].swap(c.definitions);
                 Corrected *r = &results[cur];
+                CorrectedPacked *cp = &cps[cur];
                 std::vector<std::string> *d = &written_defs[cur];
                 std::shared_future<void> before = writes[cur ^ 1]; // keep the records in input order
-                writes[cur] = std::async(std::launch::async, [&writer, r, d, before]() {
+                writes[cur] = std::async(std::launch::async, [&writer, r, cp, d, before, packed]() {
+                                  if (packed) {
+                                      unpack_corrected(*cp, r->seq);
+                                      r->offsets.swap(cp->offsets);
+                                  }
                                   if (before.valid()) before.wait();
                                   writer.write(*d, r->seq.data(), r->offsets.data());
                               }).share();

@@ -435,25 +435,51 @@ class Reader {
         rpos_ = stop;
         return more;
     }
-    // Mapped file: record starts are the '>' that begin a line.  '>' is rare (definition lines only), so one memchr
-    // per record finds them at memory speed — the line-by-line scan of the block reader costs as much as parsing.
-    bool read_chunk_mapped(Chunk &out, size_t max_records) {
-        std::vector<size_t> starts;
-        size_t scan = mpos_;
-        while (scan < map_len_ && starts.size() <= max_records) {
-            const char *gt = (const char *)memchr(map_ + scan, '>', map_len_ - scan);
-            if (!gt) break;
-            const size_t at = (size_t)(gt - map_);
-            if (at == 0 || map_[at - 1] == '\n') starts.push_back(at);
-            scan = at + 1;
+    // Mapped file: record starts are the '>' that begin a line.  '>' is rare (definition lines only), so memchr finds
+    // them at memory speed — the line-by-line scan of the block reader costs as much as parsing.  The file is scanned
+    // one window ahead of the records handed out, the window split over the threads; starts found beyond the chunk
+    // are kept for the next call.
+    void scan_window() {
+        const size_t lo = scanned_, hi = std::min(map_len_, scanned_ + ((size_t)64 << 20));
+        const unsigned T = (hi - lo) > (1u << 22) ? threads_ : 1;
+        std::vector<std::vector<size_t>> found(T);
+        auto scan = [&](unsigned t) {
+            size_t at = lo + (hi - lo) / T * t;
+            const size_t end = t + 1 == T ? hi : lo + (hi - lo) / T * (t + 1);
+            while (at < end) {
+                const char *gt = (const char *)memchr(map_ + at, '>', end - at);
+                if (!gt) break;
+                at = (size_t)(gt - map_);
+                if (at == 0 || map_[at - 1] == '\n') found[t].push_back(at);
+                at++;
+            }
+        };
+        if (T < 2) {
+            scan(0);
+        } else {
+            std::vector<std::thread> pool;
+            for (unsigned t = 0; t < T; t++) pool.emplace_back(scan, t);
+            for (auto &th : pool) th.join();
         }
-        const bool more = starts.size() > max_records;
-        const size_t n_rec = more ? max_records : starts.size();
-        const size_t stop = more ? starts[max_records] : map_len_;
+        for (auto &f : found) known_.insert(known_.end(), f.begin(), f.end());
+        scanned_ = hi;
+    }
+    bool read_chunk_mapped(Chunk &out, size_t max_records) {
+        // known_[next_ ...] are the record starts at or after mpos_ found so far
+        while (known_.size() - next_ <= max_records && scanned_ < map_len_) scan_window();
+        const size_t have = known_.size() - next_;
+        const bool more = have > max_records;
+        const size_t n_rec = more ? max_records : have;
+        const size_t stop = more ? known_[next_ + max_records] : map_len_;
         if (n_rec) {
-            starts.resize(n_rec);
+            std::vector<size_t> starts(known_.begin() + (long)next_, known_.begin() + (long)(next_ + n_rec));
             starts.push_back(stop);
             parse_parallel(map_, starts, n_rec, out);
+        }
+        next_ += n_rec;
+        if (next_ > ((size_t)1 << 20)) { // drop the starts already handed out
+            known_.erase(known_.begin(), known_.begin() + (long)next_);
+            next_ = 0;
         }
         mpos_ = stop;
         return more;
@@ -465,7 +491,10 @@ class Reader {
         if (T < 2) {
             parse_records(base, starts, 0, n_rec, out);
         } else {
-            std::vector<Chunk> parts(T);
+            // the per-thread pieces live in the reader: their buffers are paged in once, not once per chunk
+            if (parts_.size() < T) parts_.resize(T);
+            std::vector<Chunk> &parts = parts_;
+            for (unsigned t = 0; t < T; t++) parts[t].clear();
             std::vector<std::thread> pool;
             size_t lo = 0;
             const size_t bytes = stop - starts[0];
@@ -505,6 +534,10 @@ class Reader {
     bool reof_ = false;
     const char *map_ = nullptr; // regular plain file: the whole file, mapped
     size_t map_len_ = 0, mpos_ = 0;
+    size_t scanned_ = 0;        // the file has been searched for record starts up to here
+    std::vector<size_t> known_; // record starts found, in file order; known_[next_] is the next one to hand out
+    size_t next_ = 0;
+    std::vector<Chunk> parts_;
     unsigned threads_ = default_threads();
 };
 

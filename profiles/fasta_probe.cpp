@@ -17,16 +17,18 @@ int main(int argc, char **argv) {
         double t_read = 0, t_pack = 0, t_unpack = 0, t_write = 0;
         uint64_t bases = 0, records = 0;
         bool more = true;
-        while (more) {
-            br::fasta::Chunk c;
+        br::fasta::Chunk chunks[2]; // reused in turn, as br::run_correction does
+        br::fasta::Packed p;
+        br::fasta::Bytes back;
+        for (int cur = 0; more; cur ^= 1) {
+            br::fasta::Chunk &c = chunks[cur];
+            c.clear();
             auto t0 = clk::now();
             more = rd.read_chunk(c, 8192);
             auto t1 = clk::now();
             if (!c.size()) break;
-            br::fasta::Packed p;
             br::fasta::pack(c.seq.data(), c.offsets.back(), p, threads);
             auto t2 = clk::now();
-            br::fasta::Bytes back;
             back.resize(c.offsets.back());
             br::fasta::unpack(p.bases.data(), p.n_bases, p.exc_pos.data(), p.exc_byte.data(), p.exc_pos.size(), back.data(), threads);
             auto t3 = clk::now();
