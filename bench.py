@@ -42,6 +42,7 @@ import numpy as np
 
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
+T_START = time.time()
 
 K = 17
 ABUNDANCE = 2
@@ -359,6 +360,11 @@ def run_ours(args, world, rank, local_rank):
         tdist.all_reduce(t, op=tdist.ReduceOp.MIN)
         return bool(t.item())
 
+    def time_left(need_s):
+        """True on every rank when the slowest rank still has `need_s` seconds of --time-budget-s: an extra leg that
+        could push the run past the driver's per-run limit is skipped (and said so) instead of losing the whole line."""
+        return all_and(time.time() - T_START + need_s <= args.time_budget_s)
+
     def timed(fn, steps):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
@@ -596,7 +602,9 @@ def run_ours(args, world, rank, local_rank):
         # ---- the other configs this run can hold ----
         extra = {}
         if not args.no_extra:
-            if world == 1:
+            if world == 1 and not time_left(120):
+                extra["configs[2]"] = {"skipped": f"time budget ({args.time_budget_s:.0f} s, --time-budget-s)"}
+            elif world == 1:
                 steps2, warm2 = max(1, min(args.steps, 3)), max(1, min(args.warmup, 2))
                 m2 = measure(wl, CONFIG2_METHODS, steps2, warm2, e2e_warm_extra=4)
                 extra["configs[2]"] = leg_record(m2, wl, wl.n_bases, steps2, warm2, table, hbm_peak, sm_max_mhz, l2_gather,
@@ -610,6 +618,9 @@ def run_ours(args, world, rank, local_rank):
                 wl.free()
                 legs = [("configs[3]", CONFIG3)] + ([("configs[4]", CONFIG4)] if world == 8 and not args.no_config4 else [])
                 for leg, cfg in legs:
+                    if not time_left(180 if leg == "configs[3]" else 330):
+                        extra[leg] = {"skipped": f"time budget ({args.time_budget_s:.0f} s, --time-budget-s)"}
+                        continue
                     desc = sharded_descriptors(synth, cfg, world, rank)
                     shard_bases = int(desc["tlen"].astype(np.int64).sum())
                     n_chunks = -(-shard_bases // args.chunk_template_bases)
@@ -653,7 +664,9 @@ def run_ours(args, world, rank, local_rank):
         line["parity_check"] = parity
     if extra:
         line["extra"] = extra
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and time.time() - T_START + 120 > args.time_budget_s:
+        line["cpu_baseline"] = {"skipped": f"time budget ({args.time_budget_s:.0f} s, --time-budget-s)"}
+    elif world == 1 and not args.no_cpu_baseline:
         from oracle import br_oracle as o
 
         o.build()
@@ -664,6 +677,7 @@ def run_ours(args, world, rank, local_rank):
         if osolid is not None and parity is not None:
             # the CPU leg counted the whole benched data set: its bitfield must be the GPU's
             parity["bitfield_equals_oracle"] = bool(hashlib.blake2b(osolid.bits().tobytes()).hexdigest() == parity["bitfield_blake2b"])
+    line["wall_s"] = round(time.time() - T_START, 1)
     print(json.dumps(line), flush=True)
     if tdist is not None:
         tdist.barrier()
@@ -829,6 +843,9 @@ def main():
     ap.add_argument("--no-parity", action="store_true", help="skip the untimed parity checks on the benched data")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra legs (configs[2] at N = 1, configs[3] at N >= 2)")
     ap.add_argument("--no-config4", action="store_true", help="at N = 8: skip the configs[4] leg (1 Gb genome, 30x)")
+    ap.add_argument("--time-budget-s", type=float, default=780.0,
+                    help="wall-clock budget of the whole run: an extra leg (or the CPU baseline) that does not fit is skipped "
+                         "and reported as skipped; the headline line is never affected")
     ap.add_argument("--chunk-template-bases", type=int, default=CHUNK_TEMPLATE_BASES,
                     help="bases per device-resident chunk of a rank's shard in the sharded legs (testing the chunked path)")
     ap.add_argument("--no-e2e-pipeline", action="store_true", help="e2e steps one at a time")
