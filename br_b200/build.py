@@ -21,7 +21,7 @@ HOST = PKG / "host"
 CLI = PKG / "brgpu-cli"
 KAT = PKG / "brgpu-kat"  # known-answer-test runner over the C++ interface (tests/test_host_cli.py)
 HOST_SOURCES = ["cli.cpp", "kat_runner.cpp"]
-HOST_HEADERS = ["br.hpp", "fasta.hpp"]
+HOST_HEADERS = ["br.hpp", "fasta.hpp", "formats.hpp"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -1,10 +1,13 @@
-"""Minimal FASTA reader/writer for the host side of run_correction (src/lib.rs:30-31,57-60).
+"""Minimal FASTA reader/writer for the host side of run_correction (src/lib.rs:30-31,57-60), plus the two
+other inputs a solid set can be built from: FASTQ records and a CSV of k-mers (cargo features `fastq` / `csv`:
+src/set/pcon.rs:27-45,114-181, src/set/hash.rs:20-39,102-175).
 
 The reference uses noodles-fasta 0.38 (not vendored).  Reader: `>` definition line, sequence =
 the following lines joined.  Writer: definition line verbatim, sequence wrapped at 80 columns
 (noodles' default line base count; recalled, see SURVEY §8c — parity tests compare sequences
 per record, not file bytes).  Input may be gzip (niffler sniffing in the reference).
 """
+import csv
 import gzip
 import io
 
@@ -68,3 +71,45 @@ def write_fasta(out, defs, seq, off, line_bases=LINE_BASES):
         for p in range(0, len(s), line_bases):
             buf.write(s[p : p + line_bases] + b"\n")
     out.write(buf.getvalue())
+
+
+def read_fastq(path_or_file):
+    """noodles::fastq::Reader::records() as the reference's set builders consume it
+    (`while let Some(Ok(record)) = records.next()`, src/set/pcon.rs:122): four lines per record —
+    `@` name [description], the sequence on one line, a `+` line, the qualities; the first malformed or
+    truncated record ends the input silently.  Returns (definitions, seq, offsets) like read_fasta."""
+    data = _open(path_or_file)
+    lines = data.split(b"\n")
+    if lines and lines[-1] == b"":
+        lines.pop()  # the final newline does not start a line
+    defs, parts, lens = [], [], []
+    for i in range(0, len(lines), 4):
+        rec = [l[:-1] if l.endswith(b"\r") else l for l in lines[i : i + 4]]
+        if len(rec) < 4 or not rec[0].startswith(b"@") or not rec[2].startswith(b"+"):
+            break
+        defs.append(rec[0][1:])
+        parts.append(rec[1])
+        lens.append(len(rec[1]))
+    off = np.zeros(len(defs) + 1, dtype=np.uint64)
+    if lens:
+        off[1:] = np.cumsum(np.asarray(lens, dtype=np.uint64))
+    seq = np.frombuffer(b"".join(parts), dtype=np.uint8) if parts else np.empty(0, dtype=np.uint8)
+    return defs, seq, off
+
+
+def read_csv_first_column(path_or_file):
+    """csv::Reader::from_reader(input).byte_records() reduced to `record.get(0)` (src/set/pcon.rs:34-42):
+    `,` delimiter, `"` quoting, the first record is the header and is skipped, empty lines are not records,
+    a record with another number of fields than the header is an error.  Returns a list of bytes."""
+    text = _open(path_or_file).decode("latin-1")  # byte-transparent
+    out, n_fields = [], None
+    for row in csv.reader(io.StringIO(text, newline="")):
+        if not row:
+            continue
+        if n_fields is None:
+            n_fields = len(row)  # header
+            continue
+        if len(row) != n_fields:
+            raise ValueError(f"CSV error: found record with {len(row)} fields, but the previous record has {n_fields} fields")
+        out.append(row[0].encode("latin-1"))
+    return out

@@ -4,8 +4,9 @@
 // written in C++ with the reference's names, argument meaning and error behaviour:
 //
 //   br::set::KmerSet { get(kmer) -> bool, k() -> u8 }                    src/set.rs:17-23
-//   br::set::Pcon    { from_pcon_solid, from_fasta, from_count, new_ }   src/set/pcon.rs:13-196,
-//                                                                        count2solid src/main.rs:87-115
+//   br::set::Pcon    { from_pcon_solid, from_fasta, from_fastq, from_csv, from_count, new_ }
+//                                                                        src/set/pcon.rs:13-196, count2solid src/main.rs:87-115
+//   br::set::Hash    { from_fasta, from_fastq, from_csv }                src/set/hash.rs:14-186
 //   br::correct::Corrector { valid_kmer, k, correct }                    src/correct/mod.rs:44-108
 //   br::correct::{One, Two, Graph, Greedy, GapSize}                      src/correct/*.rs
 //   br::build_methods(params, solid, confirm, max_search)                src/lib.rs:141-164
@@ -27,6 +28,7 @@
 
 #include "../../include/brgpu.h"
 #include "fasta.hpp"
+#include "formats.hpp"
 
 namespace br {
 
@@ -157,10 +159,12 @@ class DeviceSet : public KmerSet {
 };
 
 // upload chunk after chunk: `each(chunk)` is called once per chunk of at most `chunk_bases` bases
-template <class F> inline void for_each_chunk(const std::vector<std::string> &paths, size_t chunk_bases, F each) {
+// (RecordReader: fasta::Reader or fastq::Reader — both fill the same Chunk)
+template <class RecordReader = fasta::Reader, class F>
+inline void for_each_chunk(const std::vector<std::string> &paths, size_t chunk_bases, F each) {
     fasta::Chunk c;
     for (auto &p : paths) {
-        fasta::Reader r(p);
+        RecordReader r(p);
         bool more = true;
         while (more) {
             more = r.read_chunk(c, 8192); // appends
@@ -171,6 +175,28 @@ template <class F> inline void for_each_chunk(const std::vector<std::string> &pa
         }
     }
     if (c.size()) each(c);
+}
+
+// from_csv's loop (src/set/pcon.rs:34-42, src/set/hash.rs:27-36): seq2bit of the first field of every data record,
+// handed over in batches (a library call per k-mer would be a GPU round trip per line).  The reference feeds whatever
+// the field holds to seq2bit; a field that is not k letters long cannot name a k-mer of the set (in the dense set it
+// would index outside the bitfield), so it is refused here.
+template <class F> inline void for_each_csv_batch(const std::string &path, int k, F each, size_t batch = 1u << 20) {
+    csv::FirstColumn rows(path);
+    std::vector<uint64_t> kmers;
+    std::string field;
+    size_t line = 1;
+    while (rows.next(field)) {
+        line++;
+        if ((int)field.size() != k)
+            throw std::runtime_error("csv record " + std::to_string(line) + ": the first column must hold a " + std::to_string(k) + "-mer");
+        kmers.push_back(kmer::seq2bit((const uint8_t *)field.data(), field.size()));
+        if (kmers.size() >= batch) {
+            each(kmers);
+            kmers.clear();
+        }
+    }
+    if (!kmers.empty()) each(kmers);
 }
 
 // set::Pcon (src/set/pcon.rs:13-196): the dense canonical bitfield, resident in HBM
@@ -229,6 +255,22 @@ class Pcon : public DeviceSet {
         ctx.check(brgpu_set_from_host_reads(ctx.handle(), k, 0, BRGPU_ABUNDANCE_EXPLICIT, reads.seq.data(),
                                             reads.offsets.data(), reads.size(), &h));
         return std::make_unique<Pcon>(ctx, h);
+    }
+
+    // Pcon::from_fastq (src/set/pcon.rs:114-181, cargo feature `fastq`): from_fasta over FASTQ records
+    static std::unique_ptr<Pcon> from_fastq(const Context &ctx, const std::string &path, int k) {
+        fasta::Chunk reads;
+        fastq::Reader r(path);
+        while (r.read_chunk(reads, 1u << 20)) {}
+        return from_fasta(ctx, reads, k);
+    }
+
+    // Pcon::from_csv (src/set/pcon.rs:27-45, cargo feature `csv`): Solid::new(k), then
+    // set.set(seq2bit(record[0]), true) for every data record (the first record is the header)
+    static std::unique_ptr<Pcon> from_csv(const Context &ctx, const std::string &path, int k) {
+        std::unique_ptr<Pcon> out = new_(ctx, k);
+        for_each_csv_batch(path, k, [&](const std::vector<uint64_t> &kmers) { out->set(kmers); });
+        return out;
     }
 
     // The same over a stream of files (src/main.rs:72-78: count_fasta(inputs, 8192) reads the records chunk by
@@ -485,6 +527,29 @@ class Hash : public DeviceSet {
             brgpu_reads_free(r);
             ctx.check(st);
         });
+        return out;
+    }
+    // Hash::from_fastq (src/set/hash.rs:102-175, cargo feature `fastq`).  The reference's non-parallel build reads the
+    // stream with the FASTA reader (hash.rs:110); its parallel build and Pcon::from_fastq use the FASTQ reader — that is
+    // what this does.
+    static std::unique_ptr<Hash> from_fastq(const Context &ctx, const std::vector<std::string> &paths, int k,
+                                            size_t chunk_bases = 1u << 28) {
+        brgpu_set *h = nullptr;
+        ctx.check(brgpu_set_hash_new(ctx.handle(), k, 1u << 20, &h));
+        auto out = std::make_unique<Hash>(ctx, h);
+        for_each_chunk<fastq::Reader>(paths, chunk_bases, [&](const fasta::Chunk &ch) {
+            brgpu_reads *r = nullptr;
+            ctx.check(brgpu_reads_upload(ctx.handle(), ch.seq.data(), ch.offsets.data(), ch.size(), &r));
+            int st = brgpu_set_hash_add_reads(h, r);
+            brgpu_reads_free(r);
+            ctx.check(st);
+        });
+        return out;
+    }
+    // Hash::from_csv (src/set/hash.rs:20-39, cargo feature `csv`): canonical(seq2bit(record[0]), k) of every data record
+    static std::unique_ptr<Hash> from_csv(const Context &ctx, const std::string &path, int k) {
+        std::unique_ptr<Hash> out = new_(ctx, k);
+        for_each_csv_batch(path, k, [&](const std::vector<uint64_t> &kmers) { out->insert(kmers); });
         return out;
     }
     // an empty Hash and insertion of (forward or canonical) k-mers, for the unit KATs

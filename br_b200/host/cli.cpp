@@ -2,9 +2,9 @@
 //
 //   brgpu-cli [-i IN..] [-o OUT..] [-s] [-c METHOD..] [-C CONFIRM] [-M MAX_SEARCH] [-b N] [-t N] [-d DEVICE] [-q] [-v..]
 //             fasta -i READS.. -k K [-a N] [first-minimum | rarefaction P | percent-most P | percent-least P]   src/main.rs:72-115
-//           | solid -i FILE -f solid|fasta [-k K]                      src/main.rs:117-145
-//           | large-kmer -i FILE -f fasta -k K   (set::Hash, 3 <= K <= 31; src/main.rs:147-163)
-//           | count ...                          (rejected: no fixture pins pcon's count-file format)
+//           | solid -i FILE -f solid|fasta|fastq|csv [-k K]            src/main.rs:117-145
+//           | large-kmer -i FILE -f fasta|fastq|csv -k K   (set::Hash, 3 <= K <= 31; src/main.rs:147-163)
+//           | count -i FILE [-a N | method]      (pcon count file, src/main.rs:59-70; container restated as recalled)
 //
 // Same flag names, defaults and quirks as the reference: -s *disables* the
 // reversed pass; -b is accepted and does not change the 8192-record chunk; `fasta -k` decrements an
@@ -190,12 +190,19 @@ std::unique_ptr<br::set::DeviceSet> build_set(const br::Context &ctx, const Args
             read_all({a.sub_inputs[0]}, reads);
             return Pcon::from_fasta(ctx, reads, a.k);
         }
-        usage_error("invalid value '" + a.format + "' for '--format': solid, fasta");
+        if (a.format == "fastq" || a.format == "csv") { // br's cargo features `fastq` / `csv` (src/main.rs:120-139)
+            if (a.k < 0) throw std::runtime_error("Solid input in this format require a kmer size");
+            return a.format == "fastq" ? Pcon::from_fastq(ctx, a.sub_inputs[0], a.k) : Pcon::from_csv(ctx, a.sub_inputs[0], a.k);
+        }
+        usage_error("invalid value '" + a.format + "' for '--format': solid, fasta, fastq, csv");
     }
     if (a.sub == "large-kmer") { // src/main.rs:147-163: set::Hash == presence-only set of canonical k-mers
         if (a.k < 0) usage_error("the following required arguments were not provided: --kmer-size");
-        if (a.format != "fasta") usage_error("invalid value '" + a.format + "' for '--format': fasta");
+        if (a.format != "fasta" && a.format != "fastq" && a.format != "csv")
+            usage_error("invalid value '" + a.format + "' for '--format': fasta, fastq, csv");
         if (a.k < 3 || a.k > 31) throw std::runtime_error("large-kmer: k must be in 3..=31 (k-mers are 2-bit packed in 64 bits)");
+        if (a.format == "fastq") return br::set::Hash::from_fastq(ctx, {a.sub_inputs[0]}, a.k, a.chunk_bases);
+        if (a.format == "csv") return br::set::Hash::from_csv(ctx, a.sub_inputs[0], a.k);
         return br::set::Hash::from_fasta(ctx, {a.sub_inputs[0]}, a.k, a.chunk_bases);
     }
     throw std::runtime_error("sub-command '" + a.sub + "' is not supported by brgpu");

@@ -55,6 +55,22 @@ def spectrum_threshold(hist, abundance_selection, percent=0.0):
     return None if r < 0 else r
 
 
+def csv_kmers(stream, k):
+    """seq2bit of the first column of every data record of a CSV (the loop of from_csv, src/set/pcon.rs:34-42,
+    src/set/hash.rs:27-36).  A field that is not k letters long cannot name a k-mer of the set and is refused."""
+    from .fasta import read_csv_first_column
+
+    fields = read_csv_first_column(stream)
+    for i, f in enumerate(fields):
+        if len(f) != k:
+            raise ValueError(f"csv record {i + 2}: the first column must hold a {k}-mer")
+    if not fields:
+        return np.empty(0, dtype=np.uint64)
+    codes = (np.frombuffer(b"".join(fields), dtype=np.uint8).reshape(len(fields), k).astype(np.uint64) >> np.uint64(1)) & np.uint64(3)
+    shifts = (np.uint64(2) * np.arange(k - 1, -1, -1, dtype=np.uint64))
+    return np.bitwise_or.reduce(codes << shifts, axis=1)
+
+
 class KmerSet:
     """src/set.rs:17-21"""
 
@@ -160,6 +176,38 @@ class Pcon(KmerSet):
                 lib.brgpu_kmers_free(p)
         return cls(ctx, out)
 
+    @classmethod
+    def from_fasta(cls, ctx, stream, k):
+        """Pcon::from_fasta (src/set/pcon.rs:47-112): presence of every canonical k-mer of every record with
+        len >= k — the counting pass with the threshold `count > 0`."""
+        from .fasta import read_fasta
+
+        _, seq, off = read_fasta(stream)
+        return cls._presence(ctx, seq, off, k)
+
+    @classmethod
+    def from_fastq(cls, ctx, stream, k):
+        """Pcon::from_fastq (src/set/pcon.rs:114-181, cargo feature `fastq`): from_fasta over FASTQ records."""
+        from .fasta import read_fastq
+
+        _, seq, off = read_fastq(stream)
+        return cls._presence(ctx, seq, off, k)
+
+    @classmethod
+    def _presence(cls, ctx, seq, off, k):
+        h = C.c_void_p()
+        s, o = as_u8(seq), as_offsets(off)
+        check(lib.brgpu_set_from_host_reads(ctx._h, k, 0, _lib.ABUNDANCE_EXPLICIT, _addr(s), _addr(o), o.size - 1, C.byref(h)), ctx._h)
+        return cls(ctx, h)
+
+    @classmethod
+    def from_csv(cls, ctx, stream, k):
+        """Pcon::from_csv (src/set/pcon.rs:27-45, cargo feature `csv`): Solid::new(k), then
+        set.set(seq2bit(record[0]), true) for every data record (the first record is the header)."""
+        out = cls.new(ctx, k)
+        out.insert(csv_kmers(stream, k))
+        return out
+
     # --- KmerSet --------------------------------------------------------------------------------
     def k(self):
         return lib.brgpu_set_k(self._h)
@@ -244,6 +292,18 @@ class Hash(Pcon):
             n = (off.numel() if hasattr(off, "numel") else off.size) - 1
             check(lib.brgpu_set_hash_from_host_reads(ctx._h, k, _addr(s), _addr(off), n, C.byref(h)), ctx._h)
         return cls(ctx, h)
+
+    @classmethod
+    def _presence(cls, ctx, seq, off, k):  # Hash::from_fasta / from_fastq over parsed records
+        return cls.from_reads(ctx, (seq, off), k)
+
+    @classmethod
+    def from_csv(cls, ctx, stream, k):
+        """Hash::from_csv (src/set/hash.rs:20-39): canonical(seq2bit(record[0]), k) of every data record."""
+        km = csv_kmers(stream, k)
+        out = cls.new(ctx, k, expected_kmers=int(km.size))
+        out.insert(km)
+        return out
 
     def add_reads(self, reads: Reads):
         """One more chunk of records (the 8192-record loop of src/set/hash.rs:76-97)."""
