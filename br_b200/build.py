@@ -60,11 +60,13 @@ def build_cli(force=False):
     if not force and not cli_needs_build():
         return CLI
     for src, exe in (("cli.cpp", CLI), ("kat_runner.cpp", KAT)):
-        cmd = ["/usr/bin/g++", "-O2", "-std=c++17", "-Wall", "-Wextra", "-pthread", "-o", str(exe), str(HOST / src),
+        tmp = exe.with_name(exe.name + ".tmp")
+        cmd = ["/usr/bin/g++", "-O2", "-std=c++17", "-Wall", "-Wextra", "-pthread", "-o", str(tmp), str(HOST / src),
                f"-L{PKG}", "-lbrgpu", "-lz", "-Wl,-rpath,$ORIGIN"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("g++ failed:\n" + r.stdout + r.stderr)
+        os.replace(tmp, exe)
     return CLI
 
 
@@ -107,11 +109,14 @@ def build(force=False, verbose=False, out=None, extra_defines=()):
             raise RuntimeError(f"nvcc failed on {obj.name}:\n" + r.stdout + r.stderr)
         if verbose:
             print(r.stdout + r.stderr)
-    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-ccbin", "/usr/bin/g++", "-o", str(target),
+    # link beside the target and rename: a process that has the old library mapped keeps its (now unlinked) file
+    tmp = target.with_name(target.name + ".tmp")
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-ccbin", "/usr/bin/g++", "-o", str(tmp),
            *[str(obj) for obj, _ in results]]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc link failed:\n" + r.stdout + r.stderr)
+    os.replace(tmp, target)
     if not out:
         build_cli(force=True)
     return target
