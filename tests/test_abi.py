@@ -123,3 +123,53 @@ def test_spectrum_threshold_is_host_arithmetic_and_matches_the_oracle():
         for m in ("rarefaction", "percent-most", "percent-least"):
             for p in (0.001, 0.05, 0.5, 0.99, 1.5):
                 assert bset.spectrum_threshold(h, m, p) == o.Counter.spectrum_threshold(h, m, p), (m, p)
+
+
+def header_declarations():
+    """(return type, name, [parameter declarations]) of every function include/brgpu.h declares."""
+    src = (ROOT / "include" / "brgpu.h").read_text()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    out = []
+    for ret, name, params in re.findall(r"([\w\s\*]+?)\b(brgpu_\w+)\s*\(([^;{]*?)\)\s*;", src):
+        params = params.strip()
+        out.append((ret.strip(), name, [] if params in ("", "void") else [p.strip() for p in params.split(",")]))
+    return out
+
+
+def test_ctypes_table_matches_the_header_argument_by_argument():
+    """The Python binding restates every prototype by hand (br_b200/_lib.py): arity, pointer-ness and the width of
+    every scalar must be the header's — a drifted entry would corrupt arguments silently."""
+    from br_b200 import _lib
+
+    scalars = {"int": C.c_int, "uint64_t": C.c_uint64, "size_t": C.c_size_t, "double": C.c_double}
+
+    def is_pointer(t):
+        return t in (C.c_void_p, C.c_char_p) or hasattr(t, "contents")
+
+    decls = header_declarations()
+    assert sorted(n for _, n, _ in decls) == sorted(_lib.SIGNATURES)
+    for ret, name, params in decls:
+        res, args = _lib.SIGNATURES[name]
+        assert len(args) == len(params), name
+        for p, a in zip(params, args):
+            if "*" in p or "[" in p:
+                assert is_pointer(a), (name, p, a)
+            else:
+                ctype = re.sub(r"\bconst\b", "", p).split()[0]
+                assert a is scalars[ctype], (name, p, a)
+        if ret == "void":
+            assert res is None, name
+        elif "*" in ret:
+            assert is_pointer(res), name
+        else:
+            assert res is scalars[re.sub(r"\bconst\b", "", ret).split()[0]], (name, ret, res)
+
+
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: include/brgpu.h must compile as C99 on its own (no C++, no CUDA, no torch types)."""
+    import subprocess
+
+    src = tmp_path / "use_header.c"
+    src.write_text('#include "brgpu.h"\nint main(void) { brgpu_ctx *c = 0; (void)c; return BRGPU_OK; }\n')
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", f"-I{ROOT / 'include'}", "-c", str(src), "-o",
+                    str(tmp_path / "use_header.o")], check=True)
