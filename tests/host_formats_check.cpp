@@ -3,6 +3,7 @@
 //   host_formats_check fastq INPUT PREFIX CHUNK_RECORDS     -> PREFIX.seq / .off / .defs, prints "malformed" when the
 //                                                              reader stopped at a bad record
 //   host_formats_check csv INPUT K BATCH                    -> one line per k-mer (decimal u64), "ERROR <what>" on a throw
+//   host_formats_check csvfields INPUT - -                  -> the first field of every data record in hex
 #include "br.hpp"
 
 #include <cstdio>
@@ -53,6 +54,19 @@ int main(int argc, char **argv) {
                 for (uint64_t v : kmers) printf("%llu\n", (unsigned long long)v);
                 puts("-");
             }, batch);
+        } catch (const std::exception &e) {
+            printf("ERROR %s\n", e.what());
+        }
+        return 0;
+    }
+    if (mode == "csvfields") { // the first field of every data record, hex, one per line (no k-mer conversion)
+        try {
+            br::csv::FirstColumn rows(in);
+            std::string f;
+            while (rows.next(f)) {
+                for (unsigned char ch : f) printf("%02x", ch);
+                puts("");
+            }
         } catch (const std::exception &e) {
             printf("ERROR %s\n", e.what());
         }

@@ -154,3 +154,48 @@ def test_csv_header_only_empty_and_errors(checker, tmp_path):
     assert err is not None and "5-mer" in err
     with pytest.raises(ValueError, match="5-mer"):
         csv_kmers(str(p), 5)
+
+
+def test_csv_reader_differential_fuzz_against_the_csv_module(checker, tmp_path):
+    """Random soups of `A C , " LF CR space`: the C++ state machine and Python's csv module (both restating the same
+    convention: quote at field start opens a quoted field, `""` inside is a quote, anything after the closing quote is
+    literal, LF / CR / CRLF end a record, empty lines are no records, header first, ragged rows are an error) must see
+    the same first column or both fail."""
+    import io
+
+    from br_b200.fasta import read_csv_first_column
+
+    rng = np.random.default_rng(2)
+    alphabet = np.frombuffer(b'AC,"\n\r ', dtype=np.uint8)
+    p = tmp_path / "fuzz.csv"
+    for _ in range(500):
+        data = rng.choice(alphabet, size=int(rng.integers(0, 60)), p=[.25, .25, .15, .12, .13, .05, .05]).tobytes()
+        p.write_bytes(data)
+        r = subprocess.run([str(checker), "csvfields", str(p), "-", "-"], check=True, capture_output=True, timeout=60)
+        lines = r.stdout.decode().split("\n")[:-1]
+        try:
+            expect = read_csv_first_column(io.BytesIO(data))
+        except ValueError:
+            assert lines and lines[-1].startswith("ERROR"), data
+            continue
+        assert [bytes.fromhex(l) for l in lines] == expect, data
+
+
+def test_fastq_reader_differential_fuzz(checker, tmp_path):
+    """Random soups of `@ + A C LF CR`: the streaming C++ reader and the line-based Python parse agree on where the
+    input stops being FASTQ and on every record before that."""
+    import io
+
+    from br_b200.fasta import read_fastq
+
+    rng = np.random.default_rng(3)
+    alphabet = np.frombuffer(b"@+AC\n\r", dtype=np.uint8)
+    p = tmp_path / "fuzz.fq"
+    for i in range(400):
+        n_good = int(rng.integers(0, 4))  # a few well-formed records, then noise
+        good = b"".join(b"@r%d\nAC\n+\nII\n" % j for j in range(n_good))
+        data = good + rng.choice(alphabet, size=int(rng.integers(0, 40)), p=[.12, .12, .25, .25, .2, .06]).tobytes()
+        p.write_bytes(data)
+        defs, seq, off, _ = run_fastq(checker, p, tmp_path / "fz", 1 + i % 3)
+        pdefs, pseq, poff = read_fastq(io.BytesIO(data))
+        assert defs == pdefs and np.array_equal(seq, pseq) and np.array_equal(off, poff), data
