@@ -40,11 +40,12 @@ def read_fasta(path_or_file):
     for rec in records:
         nl = rec.find(b"\n")
         if nl < 0:
-            defs.append(rec.rstrip(b"\r"))
+            defs.append(rec[:-1] if rec.endswith(b"\r") else rec)
             lens.append(0)
             continue
-        defs.append(rec[:nl].rstrip(b"\r"))
-        body = rec[nl + 1 :].replace(b"\n", b"").replace(b"\r", b"")
+        defs.append(rec[: nl - 1] if nl and rec[nl - 1 : nl] == b"\r" else rec[:nl])
+        # a line ends in LF or CRLF; a CR anywhere else is a sequence byte like any other (as in the C++ reader)
+        body = b"".join(l[:-1] if l.endswith(b"\r") else l for l in rec[nl + 1 :].split(b"\n"))
         parts.append(body)
         lens.append(len(body))
     off = np.zeros(len(defs) + 1, dtype=np.uint64)

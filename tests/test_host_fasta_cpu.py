@@ -105,3 +105,24 @@ def test_reader_packer_writer(checker, tmp_path, threads, chunk_records, n_recor
         check_against(names, seqs, seq2, off2, defs2)
         lines = open(str(tmp_path / tag) + ".fa", "rb").read().split(b"\n")
         assert max(len(l) for l in lines if not l.startswith(b">")) <= 80
+
+
+def test_fasta_reader_differential_fuzz(checker, tmp_path):
+    """Random soups of `> A C LF CR space`: the C++ reader (mapped file and gzip stream, chunk sizes 1..3) and the
+    Python mirror agree on every record — '>' only starts a record at the start of a line, a line ends in LF or CRLF
+    (one CR is dropped, any other CR is a byte like any other), text before the first record is skipped."""
+    import io
+
+    from br_b200.fasta import read_fasta
+
+    rng = np.random.default_rng(8)
+    alphabet = np.frombuffer(b">AC\n\r ", dtype=np.uint8)
+    plain, gz = tmp_path / "fuzz.fa", tmp_path / "fuzz.fa.gz"
+    for i in range(300):
+        data = rng.choice(alphabet, size=int(rng.integers(0, 80)), p=[.1, .3, .3, .2, .05, .05]).tobytes()
+        plain.write_bytes(data)
+        gz.write_bytes(gzip.compress(data, 1))
+        pdefs, pseq, poff = read_fasta(io.BytesIO(data))
+        for path in (plain, gz):
+            seq, off, defs = run_and_load(checker, path, tmp_path / "fz", 2, 1 + i % 3)
+            assert defs == pdefs and np.array_equal(seq, pseq) and np.array_equal(off, poff), (path.name, data)
