@@ -26,6 +26,8 @@ all-gathered with NCCL, and each rank corrects its own reads.  Reads are generat
            N = 1, configs[3] (100 Mb genome, 50x, 12 %, reads sharded: strong scaling) at N >= 2.
 `cpu_baseline` / `--impl reference`: the CPU restatement of br (oracle/, C++ + OpenMP on all host
            cores; the Rust reference cannot be built in this image) on a bounded sample.
+`--time-budget-s` (780): an extra leg or the CPU baseline that would push the run past the budget is
+           reported as {"skipped": ...}; the headline line is never affected.  `wall_s` = the run's wall clock.
 """
 import argparse
 import hashlib
