@@ -48,7 +48,8 @@ struct brgpu_set {
     uint64_t hist[256];
 };
 struct brgpu_group {
-    int unused;
+    std::vector<brgpu_ctx *> ctx;
+    std::string err;
 };
 
 namespace {
@@ -344,21 +345,83 @@ int brgpu_correct_one(brgpu_ctx *ctx, const brgpu_set *set, int method, int conf
     return n > out_cap ? fail(ctx, BRGPU_E_OVERFLOW, "output buffer too small") : BRGPU_OK;
 }
 
-// ---- several GPUs in one process: there is no device here ----
-int brgpu_group_create(const int *, int, brgpu_group **out) {
-    if (out) *out = nullptr;
-    return BRGPU_E_NO_DEVICE;
+// ---- several GPUs in one process (brgpu_group_*): N contexts of the double stand for N devices, so that the host
+// side of `brgpu-cli -d 0,1,...` (its own chunk loop, the replicas, the error path) runs on the CPU stage too ----
+int brgpu_group_create(const int *devices, int n, brgpu_group **out) {
+    if (!devices || n < 1 || !out) return BRGPU_E_INVALID;
+    brgpu_group *g = new brgpu_group();
+    for (int i = 0; i < n; i++) g->ctx.push_back(new brgpu_ctx());
+    *out = g;
+    return BRGPU_OK;
 }
-void brgpu_group_destroy(brgpu_group *) {}
-int brgpu_group_size(const brgpu_group *) { return 0; }
-const char *brgpu_group_last_error(const brgpu_group *) { return "no device"; }
-int brgpu_group_set_from_host_reads(brgpu_group *, int, int, int, double, const uint8_t *, const uint64_t *, uint64_t, brgpu_set **) {
-    return BRGPU_E_NO_DEVICE;
+void brgpu_group_destroy(brgpu_group *g) {
+    if (!g) return;
+    for (auto c : g->ctx) delete c;
+    delete g;
 }
-void brgpu_group_sets_free(brgpu_group *, brgpu_set **) {}
-int brgpu_group_correct_batch(brgpu_group *, brgpu_set *const *, const uint8_t *, uint64_t, int, int, int, const uint8_t *, const uint64_t *,
-                              uint64_t, uint8_t *, uint64_t, uint64_t *, uint64_t *) {
-    return BRGPU_E_NO_DEVICE;
+int brgpu_group_size(const brgpu_group *g) { return g ? (int)g->ctx.size() : 0; }
+const char *brgpu_group_last_error(const brgpu_group *g) { return g ? g->err.c_str() : ""; }
+int brgpu_group_set_from_host_reads(brgpu_group *g, int k, int abundance, int selection, double percent, const uint8_t *seq,
+                                    const uint64_t *off, uint64_t n, brgpu_set **out_sets) {
+    if (!g || !out_sets) return BRGPU_E_INVALID;
+    for (size_t i = 0; i < g->ctx.size(); i++) { // one replica per device
+        const int st = brgpu_set_from_host_reads_ex(g->ctx[i], k, abundance, selection, percent, seq, off, n, &out_sets[i]);
+        if (st != BRGPU_OK) {
+            g->err = g->ctx[i]->err;
+            for (size_t j = 0; j < i; j++) {
+                brgpu_set_free(out_sets[j]);
+                out_sets[j] = nullptr;
+            }
+            return st;
+        }
+    }
+    return BRGPU_OK;
+}
+void brgpu_group_sets_free(brgpu_group *g, brgpu_set **sets) {
+    if (!g || !sets) return;
+    for (size_t i = 0; i < g->ctx.size(); i++) {
+        brgpu_set_free(sets[i]);
+        sets[i] = nullptr;
+    }
+}
+int brgpu_group_correct_batch(brgpu_group *g, brgpu_set *const *sets, const uint8_t *methods, uint64_t n_methods, int confirm, int max_search,
+                              int two_side, const uint8_t *seq, const uint64_t *off, uint64_t n, uint8_t *out, uint64_t out_cap,
+                              uint64_t *out_off, uint64_t *required) {
+    if (!g || !sets || !off) return BRGPU_E_INVALID;
+    const size_t devs = g->ctx.size();
+    std::vector<brgpu_reads *> parts(devs, nullptr);
+    uint64_t total = 0, first = 0;
+    int st = BRGPU_OK;
+    for (size_t d = 0; d < devs && st == BRGPU_OK; d++) { // contiguous record ranges balanced by bases, one per device
+        uint64_t last = first;
+        const uint64_t want = off[0] + (off[n] - off[0]) * (d + 1) / devs;
+        while (last < n && (d + 1 == devs || off[last + 1] <= want)) last++;
+        brgpu_reads *in = nullptr;
+        st = brgpu_reads_upload(g->ctx[d], seq, off + first, last - first, &in);
+        if (st == BRGPU_OK) st = brgpu_correct_reads(g->ctx[d], sets[d], methods, n_methods, confirm, max_search, two_side, in, &parts[d]);
+        brgpu_reads_free(in);
+        if (st != BRGPU_OK) g->err = g->ctx[d]->err;
+        else total += parts[d]->seq.size();
+        first = last;
+    }
+    if (st == BRGPU_OK) {
+        if (required) *required = total;
+        if (total > out_cap) {
+            g->err = "output buffer too small";
+            st = BRGPU_E_OVERFLOW;
+        }
+    }
+    if (st == BRGPU_OK) {
+        uint64_t at = 0, r = 0;
+        out_off[0] = 0;
+        for (size_t d = 0; d < devs; d++) {
+            std::memcpy(out + at, parts[d]->seq.data(), parts[d]->seq.size());
+            for (size_t i = 1; i < parts[d]->off.size(); i++) out_off[++r] = at + parts[d]->off[i];
+            at += parts[d]->seq.size();
+        }
+    }
+    for (auto p : parts) brgpu_reads_free(p);
+    return st;
 }
 
 } // extern "C"

@@ -115,3 +115,29 @@ def test_pipeline_under_sanitizers(tmp_path, oracle, fixture_reads, fixture_soli
     for rep in (0, 39, 40, 117, COPIES - 1):  # every copy of the fixture comes back as the oracle's correction, in order
         a = int(o1[rep * (off.size - 1)])
         assert np.array_equal(s1[a : a + per], exp)
+
+
+def test_device_list_goes_through_the_group_calls(doubles, tmp_path, oracle, fixture_reads, fixture_solid_payload):
+    """`brgpu-cli -d 0,1,2 ... fasta`: run_group's own chunk loop over brgpu_group_* (three contexts of the double stand
+    for three devices): records in input order, the reference's error when neither -a nor a method is given."""
+    cli, _ = doubles
+    seq, off = fixture_reads
+    reads = GOLDEN / "br_reads.fa.gz"
+    out = tmp_path / "corr.fa"
+    r = subprocess.run([str(cli), "-d", "0,1,2", "-i", str(reads), "-o", str(out), "-c", "one", "two", "fasta", "-i", str(reads), "-k", "12",
+                        "-a", "2"], capture_output=True, timeout=600)  # -k 12 is decremented to 11 (src/cli.rs:277-279)
+    assert r.returncode == 0 and r.stderr == b"", r.stderr.decode()[-2000:]
+    exp, exp_off = cli_tests.oracle_corrected(oracle, fixture_solid_payload, ["one", "two"], seq, off)
+    names, _, _ = cli_tests.records(reads)
+    cli_tests.assert_same_records(out, names, exp, exp_off)
+    r = subprocess.run([str(cli), "-d", "0,1", "-i", str(reads), "-o", str(out), "-s", "-c", "gap-size", "fasta", "-i", str(reads), "-k", "11",
+                        "first-minimum"], capture_output=True, timeout=600)
+    assert r.returncode == 0 and r.stderr == b"", r.stderr.decode()[-2000:]
+    c = oracle.Counter(11)
+    c.count(seq, off, threads=8)
+    solid = c.to_solid(oracle.Counter.first_minimum(c.spectrum(8)), 8)
+    exp, exp_off = solid.run_correction([oracle.METHOD_IDS["gap_size"]], seq, off, confirm=5, max_search=7, two_side=True, threads=8)
+    cli_tests.assert_same_records(out, names, exp, exp_off)
+    r = subprocess.run([str(cli), "-d", "0,1", "-i", str(reads), "-o", str(out), "fasta", "-i", str(reads), "-k", "11"], capture_output=True,
+                       timeout=600)
+    assert r.returncode == 1 and b"abundance" in r.stderr
