@@ -209,7 +209,9 @@ std::unique_ptr<br::set::DeviceSet> build_set(const br::Context &ctx, const Args
 }
 
 // `-d 0,1,...`: one process owns several GPUs (brgpu_group_*): the `fasta` sub-command shards the k-mer
-// counting over them, every device holds a replica of the set and corrects its share of each chunk
+// counting over them, every device holds a replica of the set and corrects its share of each chunk.
+// Limit of this mode: the set-construction input is read whole (one host buffer, one device chunk per GPU:
+// about 3.5 Gbases per device); the single-device path streams it chunk by chunk (Pcon::from_count_stream).
 int run_group(const Args &a) {
     if (a.sub != "fasta") throw std::runtime_error("-d with several devices supports the fasta sub-command");
     if (a.k < 0) usage_error("the following required arguments were not provided: --kmer-size");
