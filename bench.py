@@ -79,6 +79,19 @@ def workload_name(n_gpus, genome_per_gpu, methods=None):
             f"reversed pass on")
 
 
+L2_NOTE = ("no flush: every step streams more than L2 holds (155 MB of read slots per pass x 4 passes, 0.55 GB of "
+           "partitioned k-mers, the 1 GiB bitfield written per step); the 69 MB rank-compacted copy of the "
+           "solid set is L2 resident by design and is rebuilt every step")
+
+
+def headline_config(n_gpus, genome_per_gpu, n_reads, n_bases, n_kmers):
+    """`config` of the headline line — the same dict on both arms (the reference arm runs on this arm's config);
+    the per-GPU figures are rank 0's shard."""
+    return {"workload": workload_name(n_gpus, genome_per_gpu), "reads_per_gpu": int(n_reads), "bases_per_gpu": int(n_bases),
+            "kmers_per_gpu": int(n_kmers), "l2": L2_NOTE, "parallelism": f"reads sharded over {n_gpus} GPU(s)",
+            "generator": "counter-based (brgpu_reads_synth on the device; br_b200/synth.py host mirror)"}
+
+
 def headline_descriptors(synth, n_gpus, rank, genome_per_gpu):
     """Every rank draws its reads from the whole (N x 4.6 Mb) genome; its share is 30 x 4.6 Mb of bases."""
     start, tlen, strand = synth.read_descriptors(genome_per_gpu * n_gpus, COVERAGE / n_gpus, seed=READ_SEED + rank)
@@ -231,6 +244,7 @@ def run_reference(args, world, rank):
     d = headline_descriptors(synth, args.gpus, 0, args.genome_per_gpu)
     seq, off = synth.host_reads(d["genome_seed"], d["read_seed"], d["first"], d["start"], d["tlen"], d["strand"], d["thr"])
     total = int(off[-1]) * args.gpus
+    n_kmers = int(np.maximum(np.diff(off.astype(np.int64)) - K + 1, 0).sum())
     vals, desc = [], ""
     # the CPU pipeline takes seconds per pass: one untimed-quality pass would cost as much as a timed one,
     # so it is measured once plus one repeat whatever --steps / --warmup say
@@ -242,7 +256,7 @@ def run_reference(args, world, rank):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / value, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": workload_name(args.gpus, args.genome_per_gpu)},
+        "config": headline_config(args.gpus, args.genome_per_gpu, off.size - 1, int(off[-1]), n_kmers),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc,
                          "repeats": [round(x) for x in vals]},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -650,12 +664,8 @@ def run_ours(args, world, rank, local_rank):
     line = leg_record(m, wl if world == 1 or args.no_extra else None, total_bases, args.steps, args.warmup, table, hbm_peak,
                       sm_max_mhz, l2_gather, workload_name(world, args.genome_per_gpu), "weak", world,
                       per_gpu=(wl.n_reads, wl.n_bases, wl.n_kmers))
-    line["config"].update({
-        "l2": "no flush: every step streams more than L2 holds (155 MB of read slots per pass x 4 passes, 0.55 GB of "
-              "partitioned k-mers, the 1 GiB bitfield written per step); the 69 MB rank-compacted copy of the "
-              "solid set is L2 resident by design and is rebuilt every step",
-        "parallelism": f"reads sharded over {world} GPU(s)", "rank0_numa_node": numa_node,
-        "generator": "counter-based (brgpu_reads_synth on the device; br_b200/synth.py host mirror)"})
+    line["config"] = headline_config(world, args.genome_per_gpu, wl.n_reads, wl.n_bases, wl.n_kmers)
+    line["rank0_numa_node"] = numa_node
     line["e2e"]["mode"] = e2e_mode
     line["clocks"] = clocks
     line["roofline"]["peak_source"] = peak_src
