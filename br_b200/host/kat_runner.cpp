@@ -3,7 +3,8 @@
 // (+ extra k-mers), construct a corrector, assert correct(read) == expected
 // (e.g. src/correct/exist/one.rs:89-107).  The vectors come on stdin, one KAT per block:
 //
-//   KAT <name> <k> <One|Two|Graph|Greedy|GapSize> <confirm> <max_search>
+//   KAT <name> <k> <One|Two|Graph|Greedy|GapSize> <confirm> <max_search>      the set is a br::set::Pcon
+//   HASHKAT <name> <k> <method> <confirm> <max_search>                         the set is a br::set::Hash (src/set/hash.rs)
 //   ALL <sequence>            every k-mer of the sequence is set (Tokenizer loop)
 //   KMER <kmer>               one more k-mer is set
 //   CASE <input> <expected>   assert corrector.correct(input) == expected
@@ -23,7 +24,13 @@ int main() {
     try {
         br::Context ctx(0);
         std::string line, name;
-        std::unique_ptr<br::set::Pcon> solid;
+        std::unique_ptr<br::set::DeviceSet> solid; // Pcon or Hash: the correctors only see KmerSet
+        br::set::Pcon *dense = nullptr;
+        br::set::Hash *hash = nullptr;
+        auto insert = [&](const std::vector<uint64_t> &kmers) { // Solid::set / FxHashSet::insert (both canonicalise)
+            if (dense) dense->set(kmers);
+            else hash->insert(kmers);
+        };
         std::unique_ptr<br::correct::Corrector> corrector;
         std::string method;
         int k = 0, confirm = 0, max_search = 0;
@@ -43,16 +50,31 @@ int main() {
             if (tag == "KAT") {
                 ss >> name >> k >> method >> confirm >> max_search;
                 corrector.reset();
-                solid = br::set::Pcon::new_(ctx, k);
+                auto p = br::set::Pcon::new_(ctx, k);
+                dense = p.get(), hash = nullptr;
+                solid = std::move(p);
+                kats++;
+            } else if (tag == "HASHKAT") {
+                ss >> name >> k >> method >> confirm >> max_search;
+                corrector.reset();
+                auto p = br::set::Hash::new_(ctx, k);
+                hash = p.get(), dense = nullptr;
+                solid = std::move(p);
                 kats++;
             } else if (tag == "ALL") {
                 std::string s;
                 ss >> s;
-                solid->set_all_kmers(s);
+                if (dense) {
+                    dense->set_all_kmers(s);
+                } else if ((int)s.size() >= k) { // Tokenizer(seq, k)
+                    std::vector<uint64_t> kmers;
+                    for (size_t i = 0; i + (size_t)k <= s.size(); i++) kmers.push_back(br::kmer::seq2bit((const uint8_t *)s.data() + i, (size_t)k));
+                    insert(kmers);
+                }
             } else if (tag == "KMER") {
                 std::string s;
                 ss >> s;
-                solid->set({br::kmer::seq2bit((const uint8_t *)s.data(), s.size())});
+                insert({br::kmer::seq2bit((const uint8_t *)s.data(), s.size())});
             } else if (tag == "CASE") {
                 std::string in, expected;
                 ss >> in >> expected;
@@ -77,6 +99,7 @@ int main() {
             } else if (tag == "END") {
                 corrector.reset();
                 solid.reset();
+                dense = nullptr, hash = nullptr;
             }
         }
     } catch (const std::exception &e) {

@@ -41,6 +41,7 @@ def through_the_double(doubles, monkeypatch):
     monkeypatch.setattr(cli_tests, "CLI", cli)
     monkeypatch.setattr(cli_tests, "KAT", kat)
     monkeypatch.setattr(format_tests, "CLI", cli)
+    monkeypatch.setattr(format_tests, "KAT", kat)
 
 
 def test_solid_subcommand(through_the_double, tmp_path, oracle, fixture_reads, fixture_solid_payload):
@@ -77,6 +78,7 @@ def test_fastq_and_csv_set_inputs(through_the_double, tmp_path, oracle, fixture_
 
 def test_reference_unit_kats_through_the_cpp_interface(through_the_double, kats):
     cli_tests.test_reference_unit_kats_through_the_cpp_interface(kats)
+    format_tests.test_hash_set_kats_through_the_cpp_interface(None, kats, corrector_ks=(5, 7, 11))  # the same over br::set::Hash
 
 
 @pytest.mark.parametrize("sanitizer", ["thread", "address,undefined"])

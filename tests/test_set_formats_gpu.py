@@ -217,3 +217,42 @@ def test_cli_solid_and_large_kmer_take_fastq_and_csv(built, oracle, tmp_path, fi
     bad.write_bytes(b"kmer,count\nACGTACGTACG,3\nACGTACGTACG\n")
     r = run(["-i", reads_fa, "-o", tmp_path / "x.fa", "solid", "-i", bad, "-f", "csv", "-k", "11"])
     assert r.returncode == 1 and b"fields" in r.stderr
+
+
+def hash_kat_script(kats, corrector_ks):
+    """KAT blocks for brgpu-kat with the set held as br::set::Hash: the reference's four hash-set KATs (src/set/hash.rs:185-242:
+    canonical and forward k-mers present, get(0) false) and the corrector KATs with k in corrector_ks replayed over a hash set
+    (the correctors only see KmerSet::get, so every expectation holds unchanged)."""
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    lines, n = [], 0
+    for h in kats["hash_set"]:
+        k, seq = h["k"], h["seq"]
+        lines += [f"HASHKAT set::hash {k} One 2 7", f"ALL {seq}"]
+        for i in range(len(seq) - k + 1):
+            fwd = seq[i : i + k]
+            lines += [f"GET {fwd} 1", f"GET {fwd.encode().translate(comp)[::-1].decode()} 1"]
+        lines += [f"GET {'A' * k} 0", "END"]
+        n += 1
+    for c in kats["correctors"]:
+        if c["ignored_upstream"] or c["k"] not in corrector_ks:
+            continue
+        cor = c["corrector"]
+        confirm = cor.get("confirm", cor.get("nb_validate", 2))
+        lines.append(f"HASHKAT {c['module']}::{c['name']} {c['k']} {cor['method']} {confirm} {cor.get('max_search', 7)}")
+        lines += [f"ALL {x}" for x in c["insert_all_kmers_of"]] + [f"KMER {x}" for x in c["insert_kmers"]]
+        lines += [f"CASE {a['input']} {a['expected']}" for a in c["asserts"]] + ["END"]
+        n += 1
+    return "\n".join(lines).encode(), n
+
+
+KAT = ROOT / "br_b200" / "brgpu-kat"
+
+
+def test_hash_set_kats_through_the_cpp_interface(built, kats, corrector_ks=(11,)):
+    """br::set::Hash through brgpu-kat: the reference's hash-set KATs, and its k = 11 corrector KATs over a hash set
+    (every k on the CPU stage, tests/test_host_cli_double_cpu.py)."""
+    script, n = hash_kat_script(kats, corrector_ks)
+    r = subprocess.run([str(KAT)], input=script, capture_output=True, timeout=600)
+    assert r.returncode == 0, r.stdout.decode()[-3000:] + r.stderr.decode()[-2000:]
+    assert n > len(kats["hash_set"]) and f"{n} KATs".encode() in r.stdout and b" 0 failed" in r.stdout
+
