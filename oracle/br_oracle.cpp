@@ -1166,7 +1166,7 @@ long bro_correct_error(const bro_set *s, int method, int confirm, int max_search
     Params p{method, (size_t)confirm, (size_t)max_search};
     auto r = correct_error(*s, p, kmer, seq, len);
     if (!r) return -1;
-    memcpy(out, r->first.data(), std::min(cap, r->first.size()));
+    if (!r->first.empty()) memcpy(out, r->first.data(), std::min(cap, r->first.size())); /* DCI emits no base */
     *offset = r->second;
     return (long)r->first.size();
 }
@@ -1175,7 +1175,7 @@ size_t bro_correct(const bro_set *s, int method, int confirm, int max_search, co
                    uint8_t *out, size_t cap) {
     Params p{method, (size_t)confirm, (size_t)max_search};
     Bytes r = correct(*s, p, seq, len);
-    memcpy(out, r.data(), std::min(cap, r.size()));
+    if (!r.empty()) memcpy(out, r.data(), std::min(cap, r.size()));
     return r.size();
 }
 
