@@ -379,3 +379,24 @@ def test_count_subcommand_reads_a_pcon_count_file(tmp_path, oracle, fixture_read
     assert np.array_equal(np.frombuffer(gzip.open(tmp_path / "fm.solid").read()[1:], dtype=np.uint8), c.to_solid(thr, 8).bits())
     r = run(["-i", GOLDEN / "br_reads.fa.gz", "-o", tmp_path / "x.fa", "count", "-i", tmp_path / "members.pcon"])
     assert r.returncode == 1 and b"abundance" in r.stderr
+
+
+def test_cpp_writer_and_python_writer_emit_the_same_bytes(tmp_path):
+    """Both host mirrors restate noodles' writer (definition line verbatim, 80-column lines): the C++ `echo` sub-command and
+    br_b200.fasta.write_fasta must produce identical files for the same records (empty records included)."""
+    from br_b200 import fasta
+
+    rng = np.random.default_rng(12)
+    src = tmp_path / "in.fa"
+    with open(src, "wb") as f:
+        for i in range(60):
+            n = [0, 1, 79, 80, 81, 160, int(rng.integers(0, 2000))][i % 7]
+            s = bytes(np.frombuffer(b"ACGTNacgt", dtype=np.uint8)[rng.integers(0, 9, size=n)])
+            f.write(b">r%d some description\n" % i + s + b"\n")
+    out_cpp, out_py = tmp_path / "cpp.fa", tmp_path / "py.fa"
+    r = run(["-i", src, "-o", out_cpp, "echo"])
+    assert r.returncode == 0 and r.stderr == b""
+    defs, seq, off = fasta.read_fasta(src)
+    with open(out_py, "wb") as f:
+        fasta.write_fasta(f, defs, seq, off)
+    assert out_cpp.read_bytes() == out_py.read_bytes()
