@@ -49,6 +49,34 @@ struct Args {
     std::exit(2);
 }
 
+const char *USAGE =
+    "Usage: brgpu-cli [OPTIONS] <COMMAND>\n"
+    "\n"
+    "br's command line (src/cli.rs) in front of libbrgpu.so: the solid k-mer set is built and the reads are corrected on the GPU.\n"
+    "\n"
+    "Commands:\n"
+    "  fasta       count the k-mers of FASTA files: -i FILE.. -k K [-a N | first-minimum | rarefaction P | percent-most P | percent-least P]\n"
+    "  solid       load or build a dense set:        -i FILE -f solid|fasta|fastq|csv [-k K]\n"
+    "  count       load a pcon count file:            -i FILE [-a N | <method>]\n"
+    "  large-kmer  hash set for k <= 31:              -i FILE -f fasta|fastq|csv -k K\n"
+    "  echo        FASTA reader -> writer, no GPU\n"
+    "\n"
+    "Options:\n"
+    "  -i, --inputs <FILE>...       reads to correct (default: stdin)\n"
+    "  -o, --outputs <FILE>...      corrected reads, paired with the inputs (default: stdout)\n"
+    "  -c, --corrections <M>...     one, two, graph, greedy, gap-size (default: all five, in this order)\n"
+    "  -C, --confirm <N>            solid k-mers that must follow a correction [default: 5]\n"
+    "  -M, --max-search <N>         greedy: bases explored [default: 7]\n"
+    "  -s, --two-side               do NOT run the reversed pass (br's flag, br's meaning)\n"
+    "  -b, --record_buffer <N>      accepted; the chunk is 8192 records like br's\n"
+    "  -t, --threads <N>            accepted; the GPU is the pool\n"
+    "  -d, --device <D[,D...]>      CUDA device, or a list: one process drives all of them\n"
+    "      --transport <T>          packed (2 bits per base + exceptions, default) | ascii\n"
+    "      --chunk-bases <N>        bases per chunk while a set is built from FASTA / FASTQ\n"
+    "      --write-solid <FILE>     also store the dense set as a pcon .solid file\n"
+    "  -h, --help                   print this\n"
+    "  -V, --version                print the library version\n";
+
 bool is_sub(const std::string &s) {
     return s == "fasta" || s == "solid" || s == "large-kmer" || s == "count" || s == "echo";
 }
@@ -123,6 +151,13 @@ Args parse(int argc, char **argv) {
             if (v != "packed" && v != "ascii") usage_error("invalid value '" + v + "' for '--transport': packed, ascii");
             a.packed = v == "packed";
         } else if (t == "--chunk-bases") a.chunk_bases = (size_t)parse_int(t, value(t), 1, 1LL << 40); // set construction streams chunks of this size
+        else if (t == "-h" || t == "--help") {
+            std::fputs(USAGE, stdout);
+            std::exit(0);
+        } else if (t == "-V" || t == "--version") {
+            std::printf("brgpu-cli (%s)\n", brgpu_version());
+            std::exit(0);
+        }
         else if (t == "-q" || t == "--quiet") {}
         else if (t.rfind("-v", 0) == 0 || t == "--verbosity") {}
         else if (t == "-T" || t == "--timestamp") (void)value(t);

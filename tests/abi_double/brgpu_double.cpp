@@ -96,6 +96,7 @@ int brgpu_ctx_create(int, void *, brgpu_ctx **out) {
 }
 void brgpu_ctx_destroy(brgpu_ctx *ctx) { delete ctx; }
 const char *brgpu_last_error(const brgpu_ctx *ctx) { return ctx ? ctx->err.c_str() : ""; }
+const char *brgpu_version(void) { return "brgpu ABI test double (tests/abi_double): not the product"; }
 int brgpu_host_alloc(brgpu_ctx *, size_t bytes, void **out) {
     *out = std::malloc(bytes ? bytes : 1);
     return *out ? BRGPU_OK : BRGPU_E_NOMEM;

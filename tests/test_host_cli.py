@@ -115,6 +115,13 @@ def test_inputs_and_outputs_are_zipped_pairwise(tmp_path):
     assert r.returncode == 0 and ob.read_bytes() == b">b\nCCCC\n"
 
 
+def test_help_and_version_need_no_device():
+    r = run(["--help"])
+    assert r.returncode == 0 and r.stderr == b"" and b"large-kmer" in r.stdout and b"--two-side" in r.stdout
+    r = run(["-V"])
+    assert r.returncode == 0 and r.stdout.startswith(b"brgpu-cli (brgpu")
+
+
 def test_argument_contract():
     assert run([]).returncode == 2  # a sub-command is required
     assert run(["-c", "three", "echo"]).returncode == 2
